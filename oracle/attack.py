@@ -1,0 +1,237 @@
+"""Oracle restatement of the reference's perturbation loop.  Test infrastructure only.
+
+Follows, line by line where it matters:
+  * ``attack_our``  -- /root/reference/attack_rd.py:332-379
+  * ``attack_``     -- /root/reference/attack_rd.py:381-575
+  * ``eval``        -- /root/reference/self_ensemble.py:173-252
+  * sign update     -- /root/reference/attack_ifgsm.py:348-438
+  * RD loss / optimisers / --adv step -- /root/reference/train.py:37-96, 335-366; coder.py:50-86
+
+Differences from the reference text, all forced by it being un-runnable off-GPU: the perturbation
+is created on ``im_s.device`` instead of ``.cuda()`` (attack_rd.py:501), and ms_ssim comes from
+``oracle.msssim`` (variant 1) instead of the missing ``pytorch_msssim``.
+"""
+import math
+from types import SimpleNamespace
+
+import torch
+
+from .layers import low_bound, up_bound
+from .msssim import MS_SSIM, ms_ssim
+
+
+def default_args(**kw):
+    """Defaults of ``coder.config()`` (coder.py:166-220) for the flags the hot path reads."""
+    a = dict(model="hyper", metric="ms-ssim", quality=3, steps=1001, random=1, lamb_attack=0.2,
+             noise=1e-4, lr_attack=0.01, att_metric="L2", epsilon=16.0, pad=None, debug=False,
+             clamp=True, defend=False, method="ensemble", adv=False, lr_train=1e-4,
+             target=None, mask_loc=None, lamb_bkg_in=1.0, lamb_bkg_out=1.0, lamb_tar=1.0)
+    a.update(kw)
+    return SimpleNamespace(**a)
+
+
+def bpp_from_likelihoods(likelihoods, num_pixels):
+    """attack_rd.py:419 / self_ensemble.py:222."""
+    return sum(torch.log(l).sum() / (-math.log(2) * num_pixels) for l in likelihoods.values())
+
+
+def attack_our(im_s, output_s, im_in, net, args):
+    """attack_rd.py:332-379."""
+    loss_i = torch.mean((im_s - im_in) ** 2)
+    if loss_i > args.noise:                                            # :334 (host sync)
+        if args.att_metric == "ms-ssim":
+            loss = 1.0 - ms_ssim(im_s, im_in, data_range=1.0, size_average=True)
+        if args.att_metric == "L2":
+            loss = loss_i
+        loss_o = torch.zeros(1)
+        branch = "A"
+    else:
+        y_main = net.g_a(im_in)                                        # :344 no quantiser
+        x_ = net.g_s(y_main)                                           # :349
+        output_ = up_bound(low_bound(x_, 0.0), 1.0) if args.clamp else x_   # :353-356
+        if args.att_metric == "ms-ssim":
+            loss_o = ms_ssim(output_, output_s, data_range=1.0, size_average=True)
+        if args.att_metric == "L2":
+            loss_o = 1.0 - torch.mean((output_s - output_) * (output_s - output_))  # :364
+        loss = loss_o
+        branch = "B"
+    return loss, loss_i, loss_o, branch
+
+
+@torch.no_grad()
+def eval_metrics(im_adv, im_s, output_s, net, args):
+    """self_ensemble.py:173-252 (defence branches are out of scope)."""
+    net.eval()
+    im_ = torch.clamp(im_adv, min=0.0, max=1.0) if args.clamp else im_adv
+    result = net(im_)
+    x_hat = result["x_hat"]
+    mse_in = torch.mean((im_ - im_s) ** 2)
+    output_ = torch.clamp(x_hat, min=0.0, max=1.0) if args.clamp else x_hat
+    num_pixels = im_adv.shape[2] * im_adv.shape[3]
+    bpp = bpp_from_likelihoods(result["likelihoods"], num_pixels)
+    mse_out = torch.mean((output_ - output_s) ** 2)
+    small = min(im_.shape[-2:]) <= 160  # pytorch_msssim asserts; oracle reports None instead
+    msim_out = None if small else ms_ssim(output_, output_s, data_range=1.0).item()
+    msim_in = None if small else ms_ssim(im_, im_s, data_range=1.0).item()
+    mse_results = {"mse_in": mse_in.item(), "mse_out": mse_out.item()}
+    vi_results = {"vi": None, "vi_msim": None}
+    if mse_in > 1e-20 and mse_out > 1e-20:
+        vi_results["vi"] = 10.0 * math.log10(mse_out.item() / mse_in.item())
+        if not args.adv and msim_in is not None and msim_in < 0.9999:
+            vi_results["vi_msim"] = 10.0 * math.log10((1 - msim_out) / (1 - msim_in))
+    return im_, output_, bpp, mse_results, vi_results
+
+
+def clean_pass(im_s, net, args):
+    """attack_rd.py:402-419: eval-mode full forward -> output_s, bpp_ori."""
+    H, W = im_s.shape[2], im_s.shape[3]
+    with torch.no_grad():
+        net.eval()
+        result = net(im_s)
+        output_s = torch.clamp(result["x_hat"], 0.0, 1.0) if args.clamp else result["x_hat"]
+        bpp_ori = bpp_from_likelihoods(result["likelihoods"], H * W)
+    return output_s, bpp_ori, result
+
+
+def attack_(im_s, net, args, record=None, noise_init=None):
+    """attack_rd.py:381-575.  ``record`` (a list) receives per-step
+    ``(branch, loss, loss_i)``; ``noise_init`` lets a test share the ``-random>1`` start."""
+    output_s, bpp_ori, _ = clean_pass(im_s, net, args)
+    noise_range = args.epsilon / 255.0                                  # :490
+    if noise_init is not None:
+        noise = noise_init.clone()
+    elif args.random > 1:
+        noise = torch.empty_like(im_s).uniform_(-1e-2, 1e-2)            # :498-499
+    else:
+        noise = torch.zeros_like(im_s)                                  # :496
+    noise = noise.to(im_s.device).requires_grad_(True)
+    optimizer = torch.optim.Adam([noise], lr=args.lr_attack)            # :502
+    sched = torch.optim.lr_scheduler.MultiStepLR(optimizer, [1, 2, 3], gamma=0.33)  # :503
+    net.train()                                                         # :504
+    for i in range(args.steps):
+        noise_clipped = up_bound(low_bound(noise, -noise_range), noise_range)      # :507
+        im_in = up_bound(low_bound(im_s + noise_clipped, 0.0), 1.0)                # :517
+        loss, loss_i, loss_o, branch = attack_our(im_s, output_s, im_in, net, args)
+        optimizer.zero_grad()
+        loss.backward()
+        optimizer.step()                                                # :546-548
+        if record is not None:
+            record.append((branch, float(loss.detach()), float(loss_i.detach())))
+        if i % (args.steps // 3) == 0:                                  # :553 (ZeroDivisionError if steps<3)
+            sched.step()
+    im_adv, output_adv, bpp, mse_results, vi_results = eval_metrics(
+        im_in.detach(), im_s, output_s, net, args)                      # :573
+    return im_adv, output_adv, output_s, bpp_ori, bpp, mse_results, vi_results
+
+
+def lr_schedule(steps, lr0=0.01, gamma=0.33):
+    """LR used at iteration i under MultiStepLR([1,2,3]) stepped when i % (steps//3) == 0."""
+    out, lr, n = [], lr0, 0
+    for i in range(steps):
+        out.append(lr)
+        if i % (steps // 3) == 0:
+            n += 1
+            if n in (1, 2, 3):
+                lr = lr * gamma
+    return out
+
+
+def attack_ifgsm(im_s, net, args, momentum=False, record=None, start=None):
+    """attack_ifgsm.py:364-438 (single start).  ``start`` injects the PGD random start."""
+    output_s, bpp_ori, _ = clean_pass(im_s, net, args)
+    eps = args.epsilon / 255.0
+    im_adv = (im_s if start is None else torch.clamp(start, 0, 1)).detach().requires_grad_(True)
+    net.train()
+    g, alpha = 0, eps / args.steps
+    for i in range(args.steps):
+        output_ = net.g_s(net.g_a(im_adv))
+        loss_o = torch.mean((output_s - output_) * (output_s - output_))
+        net.zero_grad()
+        grad, = torch.autograd.grad(loss_o, im_adv)
+        if momentum:                                                    # :348-362
+            g = 1.0 * g + grad / torch.norm(grad, p=1)
+            im_new = torch.clamp(im_adv + alpha * torch.sign(g), 0, 1)
+        else:
+            im_new = im_adv + eps / args.steps * grad.sign()            # :409-415
+        im_new = torch.where(im_new > im_s + eps, im_s + eps, im_new)   # :417-418
+        im_new = torch.where(im_new < im_s - eps, im_s - eps, im_new)
+        im_adv = im_new.detach().requires_grad_(True)
+        if record is not None:
+            record.append(("B", float(loss_o), float(torch.mean((im_adv - im_s) ** 2))))
+    im_, output_adv, bpp, mse_results, vi_results = eval_metrics(im_adv.detach(), im_s, output_s, net, args)
+    return im_, output_adv, output_s, bpp_ori, bpp, mse_results, vi_results
+
+
+# ---------------------------------------------------------------- train.py --adv pieces
+LAMBDA_MSE = {1: 0.0018, 2: 0.0035, 3: 0.0067, 4: 0.0130, 5: 0.0250, 6: 0.0483, 7: 0.0932, 8: 0.1800}
+LAMBDA_MSSSIM = {1: 2.40, 2: 4.58, 3: 8.73, 4: 16.64, 5: 31.73, 6: 60.50, 7: 115.37, 8: 220.00}
+
+
+class RateDistortionLoss(torch.nn.Module):
+    """train.py:37-96 (training branch; lpips is out of scope)."""
+
+    def __init__(self, metric="mse", lmbda=1e-2):
+        super().__init__()
+        self.metric, self.lmbda = metric, lmbda
+        self.mssim = MS_SSIM(data_range=1, size_average=True, channel=3)
+
+    def forward(self, output, target):
+        N, _, H, W = target.shape
+        num_pixels = N * H * W
+        out = {}
+        bpp = 0.0
+        for lik in output["likelihoods"].values():
+            lik = torch.clamp(lik, min=1.0 / 65536)                     # :62
+            bpp = bpp + torch.log(lik).sum() / (-math.log(2) * num_pixels)
+        out["bpp_loss"] = bpp
+        if self.metric == "mse":
+            out["distortion_loss"] = torch.mean((output["x_hat"] - target) ** 2)
+            out["loss"] = self.lmbda * 255 ** 2 * out["distortion_loss"] + out["bpp_loss"]
+        else:
+            out["distortion_loss"] = self.mssim(output["x_hat"], target)
+            out["loss"] = self.lmbda * (1 - out["distortion_loss"]) + out["bpp_loss"]
+        return out
+
+
+def configure_optimizers(net, lr_train):
+    """coder.py:50-86."""
+    params = dict(net.named_parameters())
+    main = sorted(n for n in params if not n.endswith(".quantiles"))
+    aux = sorted(n for n in params if n.endswith(".quantiles"))
+    return (torch.optim.Adam((params[n] for n in main), lr=lr_train),
+            torch.optim.Adam((params[n] for n in aux), lr=1e-3))
+
+
+def adv_train_step(batch_x, net, args, criterion, optimizer, aux_optimizer):
+    """One iteration of train.py:335-366 (N_ADV = 0)."""
+    batch_adv = attack_(batch_x, net, args)[0].detach()                 # :342
+    net.train()
+    batch_x = batch_adv.clone()                                         # :347 (in-place overwrite)
+    result = net(batch_x)
+    out = criterion(result, batch_x)                                    # :353
+    optimizer.zero_grad()
+    aux_optimizer.zero_grad()
+    out["loss"].backward()
+    torch.nn.utils.clip_grad_norm_(net.parameters(), 1.0)               # :360
+    optimizer.step()
+    aux = net.aux_loss()
+    aux.backward()
+    aux_optimizer.step()
+    return out, aux
+
+
+# ---------------------------------------------------------------- synthetic inputs
+def synthetic_image(i, H=512, W=768, device="cpu"):
+    """Seeded Kodak-like image on the k/255 lattice: U[0,1) field -> separable Gaussian blur
+    sigma=3 -> affine rescale to [0.05, 0.95] -> round(.*255)/255.  Returns [1,3,H,W] fp32."""
+    g = torch.Generator().manual_seed(1234 + i)
+    x = torch.rand(1, 3, H, W, generator=g)
+    r = 9
+    k = torch.exp(-(torch.arange(-r, r + 1, dtype=torch.float32) ** 2) / (2 * 3.0 ** 2))
+    k = k / k.sum()
+    xp = torch.nn.functional.pad(x, (r, r, r, r), mode="reflect")
+    xp = torch.nn.functional.conv2d(xp, k.view(1, 1, 1, -1).expand(3, 1, 1, -1), groups=3)
+    xp = torch.nn.functional.conv2d(xp, k.view(1, 1, -1, 1).expand(3, 1, -1, 1), groups=3)
+    lo, hi = xp.amin(), xp.amax()
+    xp = 0.05 + 0.9 * (xp - lo) / (hi - lo)
+    return (torch.round(xp * 255.0) / 255.0).to(device)
