@@ -1,0 +1,99 @@
+"""ctypes binding of ``libicadv_b200.so`` (the C ABI declared in ``include/icadv.h``).
+
+There is no fallback: if the shared library is missing or a call fails, this raises.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libicadv_b200.so")
+
+OK = 0
+FORM_SCONV, FORM_TCONV = 0, 1
+EPI_LINEAR, EPI_GDN_FWD, EPI_IGDN_FWD, EPI_GDN_BWD, EPI_IGDN_BWD = 0, 1, 2, 3, 4
+ACT_NONE, ACT_RELU, ACT_LEAKY, ACT_ABS = 0, 1, 2, 3
+RED_BLOCKS = 128
+PACK_CONV_FWD, PACK_CONV_DGRAD, PACK_CONVT_FWD, PACK_CONVT_DGRAD = 0, 1, 2, 3
+
+_fp = C.c_void_p  # device pointers travel as integers
+
+
+class ConvDesc(C.Structure):
+    _fields_ = [("form", C.c_int), ("ksize", C.c_int), ("stride", C.c_int), ("n_img", C.c_int),
+                ("in_h", C.c_int), ("in_w", C.c_int), ("k_ch", C.c_int), ("n_ch", C.c_int),
+                ("inp", _fp), ("wpack", _fp), ("bias", _fp), ("out", _fp),
+                ("epi", C.c_int), ("act", C.c_int),
+                ("gmat", _fp), ("beta", _fp), ("out_scale", _fp), ("y_prev", _fp), ("sc_prev", _fp),
+                ("acc_from_in", C.c_int), ("active", _fp), ("n_active", _fp)]
+
+
+class PerturbState(C.Structure):
+    _fields_ = [("sum_d2", _fp), ("loss_i", _fp), ("branch", _fp), ("active", _fp), ("n_active", _fp),
+                ("step", _fp), ("lr", _fp), ("step_size", _fp), ("bc2_sqrt", _fp)]
+
+
+class IcadvError(RuntimeError):
+    pass
+
+
+_lib = None
+
+_SIGS = {
+    "icadv_last_error": (C.c_char_p, []),
+    "icadv_version": (C.c_int, []),
+    "icadv_check_device": (C.c_int, []),
+    "icadv_conv_out_hw": (C.c_int, [C.POINTER(ConvDesc), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "icadv_conv_plan_create": (C.c_int, [C.POINTER(ConvDesc), C.POINTER(C.c_void_p)]),
+    "icadv_conv_plan_launch": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "icadv_conv_plan_destroy": (C.c_int, [C.c_void_p]),
+    "icadv_conv_tc": (C.c_int, [C.POINTER(ConvDesc), C.c_void_p]),
+    "icadv_conv_tc_supported": (C.c_int, [C.POINTER(ConvDesc)]),
+    "icadv_conv_simt": (C.c_int, [C.POINTER(ConvDesc), C.c_void_p]),
+    "icadv_conv_wgrad": (C.c_int, [C.POINTER(ConvDesc), _fp, _fp, _fp, C.c_void_p]),
+    "icadv_pack_weight": (C.c_int, [_fp, _fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "icadv_unpack_weight": (C.c_int, [_fp, _fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "icadv_nchw_to_nhwc": (C.c_int, [_fp, _fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "icadv_nhwc_to_nchw": (C.c_int, [_fp, _fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "icadv_gdn_reparam": (C.c_int, [_fp, _fp, C.c_int, C.c_int, C.c_float, C.c_float, C.c_int, C.c_void_p]),
+    "icadv_perturb_forward": (C.c_int, [_fp, _fp, _fp, _fp, C.POINTER(PerturbState), C.c_int, C.c_int64, C.c_float,
+                                        C.c_float, C.c_int, C.c_double, C.c_double, C.c_int, C.c_double, C.c_double,
+                                        C.c_void_p]),
+    "icadv_perturb_update_adam": (C.c_int, [_fp, _fp, _fp, _fp, _fp, C.POINTER(PerturbState), C.c_int, C.c_int64,
+                                            C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float,
+                                            C.c_void_p]),
+    "icadv_ifgsm_update": (C.c_int, [_fp, _fp, _fp, C.c_int64, C.c_float, C.c_float, C.c_void_p]),
+    "icadv_output_loss": (C.c_int, [_fp, _fp, _fp, _fp, _fp, C.c_int, C.c_int64, C.c_int, C.c_float, _fp, _fp,
+                                    C.c_void_p]),
+    "icadv_bound_forward": (C.c_int, [_fp, _fp, C.c_int64, C.c_float, C.c_int, C.c_void_p]),
+    "icadv_bound_backward": (C.c_int, [_fp, _fp, _fp, C.c_int64, C.c_float, C.c_int, C.c_void_p]),
+    "icadv_sum_sqdiff": (C.c_int, [_fp, _fp, _fp, _fp, C.c_int, C.c_int64, C.c_void_p]),
+}
+
+
+def exported_symbols():
+    return sorted(_SIGS)
+
+
+def lib():
+    """Load (once) and return the shared library; raises if it is not built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise IcadvError(f"{LIB_PATH} is not built (run `python __graft_entry__.py` / csrc/build.py); "
+                             "there is no fallback path")
+        L = C.CDLL(LIB_PATH)
+        for name, (res, args) in _SIGS.items():
+            fn = getattr(L, name)
+            fn.restype, fn.argtypes = res, args
+        _lib = L
+    return _lib
+
+
+def check(rc):
+    if rc != OK:
+        msg = lib().icadv_last_error()
+        raise IcadvError(f"icadv error {rc}: {msg.decode() if msg else ''}")
+
+
+def call(name, *args):
+    check(getattr(lib(), name)(*args))

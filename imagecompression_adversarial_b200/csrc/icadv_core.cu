@@ -1,0 +1,227 @@
+// Error plumbing, contraction geometry, weight packing, layout conversion, GDN reparametrisation.
+#include <mutex>
+#include <string>
+
+#include "icadv_common.cuh"
+
+namespace icadv {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+static inline int mod2(int v) { return ((v % 2) + 2) % 2; }
+
+int make_geometry(const icadv_conv_desc* d, Geometry* g) {
+  ICADV_REQUIRE(d != nullptr, "null descriptor");
+  ICADV_REQUIRE(d->ksize == 1 || d->ksize == 3 || d->ksize == 5, "ksize %d unsupported", d->ksize);
+  ICADV_REQUIRE(d->stride == 1 || d->stride == 2, "stride %d unsupported", d->stride);
+  ICADV_REQUIRE(d->in_h > 0 && d->in_w > 0 && d->n_img > 0 && d->k_ch > 0 && d->n_ch > 0, "bad sizes");
+  const int k = d->ksize, s = d->stride, p = k / 2;
+  g->form = d->form; g->ksize = k; g->stride = s; g->pad = p;
+  g->in_h = d->in_h; g->in_w = d->in_w;
+  for (int l = 0; l < 4; ++l) { g->n_taps[l] = 0; g->out_a[l] = g->out_b[l] = 0; }
+  if (d->form == ICADV_FORM_SCONV) {
+    g->out_h = (d->in_h + 2 * p - k) / s + 1;
+    g->out_w = (d->in_w + 2 * p - k) / s + 1;
+    g->tile_h = g->out_h; g->tile_w = g->out_w;
+    g->n_launch = 1;
+    int n = 0;
+    for (int kh = 0; kh < k; ++kh)
+      for (int kw = 0; kw < k; ++kw) {
+        Tap t;
+        if (s == 1) {
+          t.plane = 0; t.dy = (int16_t)(kh - p); t.dx = (int16_t)(kw - p);
+        } else {
+          int a = mod2(kh - p), b = mod2(kw - p);
+          t.plane = (int16_t)(a * 2 + b);
+          t.dy = (int16_t)((kh - p - a) / 2);
+          t.dx = (int16_t)((kw - p - b) / 2);
+        }
+        t.wtap = (int16_t)(kh * k + kw);
+        g->taps[0][n++] = t;
+      }
+    g->n_taps[0] = n;
+  } else if (d->form == ICADV_FORM_TCONV) {
+    g->out_h = d->in_h * s; g->out_w = d->in_w * s;
+    g->tile_h = d->in_h; g->tile_w = d->in_w;
+    g->n_launch = s * s;
+    for (int a = 0; a < s; ++a)
+      for (int b = 0; b < s; ++b) {
+        int l = a * s + b, n = 0;
+        g->out_a[l] = a; g->out_b[l] = b;
+        for (int kh = 0; kh < k; ++kh) {
+          if (mod2(a + p - kh) != 0 && s == 2) continue;
+          for (int kw = 0; kw < k; ++kw) {
+            if (mod2(b + p - kw) != 0 && s == 2) continue;
+            Tap t;
+            t.plane = 0;
+            t.dy = (int16_t)((a + p - kh) / s);
+            t.dx = (int16_t)((b + p - kw) / s);
+            t.wtap = (int16_t)(kh * k + kw);
+            g->taps[l][n++] = t;
+          }
+        }
+        g->n_taps[l] = n;
+      }
+  } else {
+    ICADV_REQUIRE(false, "unknown form %d", d->form);
+  }
+  return ICADV_OK;
+}
+
+// ------------------------------------------------------------------ small kernels
+// kind 0: Conv2d fwd      w[co][ci][t] -> P[t][n=co][k=ci]
+// kind 1: Conv2d dgrad    w[co][ci][t] -> P[t][n=ci][k=co]
+// kind 2: ConvT  fwd      w[ci][co][t] -> P[t][n=co][k=ci]
+// kind 3: ConvT  dgrad    w[ci][co][t] -> P[t][n=ci][k=co]
+// (c_out, c_in) are the LAYER's out/in channels; torch dims: Conv2d [c_out,c_in], ConvT [c_in,c_out].
+__device__ __forceinline__ int64_t torch_w_index(int kind, int n, int k, int t, int c_out, int c_in, int taps) {
+  int co, ci;
+  if (kind == 0 || kind == 2) { co = n; ci = k; } else { ci = n; co = k; }
+  if (kind <= 1) return ((int64_t)co * c_in + ci) * taps + t;
+  return ((int64_t)ci * c_out + co) * taps + t;
+}
+
+__global__ void pack_weight_kernel(const float* __restrict__ w, float* __restrict__ P, int kind, int c_out, int c_in,
+                                   int taps) {
+  const int N = (kind == 0 || kind == 2) ? c_out : c_in;
+  const int K = (kind == 0 || kind == 2) ? c_in : c_out;
+  int64_t total = (int64_t)taps * N * K;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int k = (int)(i % K);
+    int n = (int)((i / K) % N);
+    int t = (int)(i / ((int64_t)K * N));
+    P[i] = w[torch_w_index(kind, n, k, t, c_out, c_in, taps)];
+  }
+}
+
+__global__ void unpack_weight_kernel(const float* __restrict__ P, float* __restrict__ w, int kind, int c_out, int c_in,
+                                     int taps, int accumulate) {
+  const int N = (kind == 0 || kind == 2) ? c_out : c_in;
+  const int K = (kind == 0 || kind == 2) ? c_in : c_out;
+  int64_t total = (int64_t)taps * N * K;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int k = (int)(i % K);
+    int n = (int)((i / K) % N);
+    int t = (int)(i / ((int64_t)K * N));
+    int64_t j = torch_w_index(kind, n, k, t, c_out, c_in, taps);
+    w[j] = accumulate ? w[j] + P[i] : P[i];
+  }
+}
+
+// NCHW <-> NHWC through a 32x32 shared tile: both sides coalesced.
+__global__ void transpose_cp_kernel(const float* __restrict__ src, float* __restrict__ dst, int rows, int cols) {
+  // src: [batch][rows][cols] -> dst: [batch][cols][rows]
+  __shared__ float tile[32][33];
+  const int64_t base = (int64_t)blockIdx.z * rows * cols;
+  int c = blockIdx.x * 32 + threadIdx.x;
+  for (int r = threadIdx.y; r < 32; r += 8) {
+    int rr = blockIdx.y * 32 + r;
+    if (rr < rows && c < cols) tile[r][threadIdx.x] = src[base + (int64_t)rr * cols + c];
+  }
+  __syncthreads();
+  int r2 = blockIdx.y * 32 + threadIdx.x;
+  for (int cc = threadIdx.y; cc < 32; cc += 8) {
+    int c2 = blockIdx.x * 32 + cc;
+    if (c2 < cols && r2 < rows) dst[base + (int64_t)c2 * rows + r2] = tile[threadIdx.x][cc];
+  }
+}
+
+__global__ void gdn_reparam_kernel(const float* __restrict__ raw, float* __restrict__ eff, int rows, int cols,
+                                   float bound, float pedestal, int transpose) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * cols) return;
+  int r = i / cols, c = i % cols;
+  float v = fmaxf(raw[i], bound);
+  v = v * v - pedestal;
+  if (transpose) eff[c * rows + r] = v; else eff[i] = v;
+}
+
+}  // namespace icadv
+
+using namespace icadv;
+
+extern "C" {
+
+const char* icadv_last_error(void) { return g_err; }
+int icadv_version(void) { return 100; }
+
+int icadv_check_device(void) {
+  int dev = 0;
+  ICADV_CUDA_TRY(cudaGetDevice(&dev));
+  cudaDeviceProp prop;
+  ICADV_CUDA_TRY(cudaGetDeviceProperties(&prop, dev));
+  if (prop.major != 10) {
+    set_error("device %s is sm_%d%d; this library is sm_100a only (no fallback)", prop.name, prop.major, prop.minor);
+    return ICADV_EARCH;
+  }
+  return ICADV_OK;
+}
+
+int icadv_conv_out_hw(const icadv_conv_desc* d, int* out_h, int* out_w) {
+  Geometry g;
+  int rc = make_geometry(d, &g);
+  if (rc) return rc;
+  if (out_h) *out_h = g.out_h;
+  if (out_w) *out_w = g.out_w;
+  return ICADV_OK;
+}
+
+int icadv_pack_weight(const float* w, float* wpack, int kind, int c_out, int c_in, int ksize, icadv_stream_t stream) {
+  ICADV_REQUIRE(w && wpack && kind >= 0 && kind <= 3, "bad pack_weight args");
+  int taps = ksize * ksize;
+  int64_t total = (int64_t)taps * c_out * c_in;
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 4096) blocks = 4096;
+  pack_weight_kernel<<<blocks, 256, 0, as_stream(stream)>>>(w, wpack, kind, c_out, c_in, taps);
+  ICADV_CUDA_TRY(cudaGetLastError());
+  return ICADV_OK;
+}
+
+int icadv_unpack_weight(const float* dwpack, float* dw, int kind, int c_out, int c_in, int ksize, int accumulate,
+                        icadv_stream_t stream) {
+  ICADV_REQUIRE(dw && dwpack && kind >= 0 && kind <= 3, "bad unpack_weight args");
+  int taps = ksize * ksize;
+  int64_t total = (int64_t)taps * c_out * c_in;
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 4096) blocks = 4096;
+  unpack_weight_kernel<<<blocks, 256, 0, as_stream(stream)>>>(dwpack, dw, kind, c_out, c_in, taps, accumulate);
+  ICADV_CUDA_TRY(cudaGetLastError());
+  return ICADV_OK;
+}
+
+static int launch_transpose(const float* src, float* dst, int batch, int rows, int cols, cudaStream_t s) {
+  dim3 grid((cols + 31) / 32, (rows + 31) / 32, batch), block(32, 8);
+  ICADV_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "transpose grid too large");
+  transpose_cp_kernel<<<grid, block, 0, s>>>(src, dst, rows, cols);
+  ICADV_CUDA_TRY(cudaGetLastError());
+  return ICADV_OK;
+}
+
+int icadv_nchw_to_nhwc(const float* src, float* dst, int n, int c, int h, int w, icadv_stream_t stream) {
+  ICADV_REQUIRE(src && dst, "null pointer");
+  return launch_transpose(src, dst, n, c, h * w, as_stream(stream));  // [n][c][hw] -> [n][hw][c]
+}
+
+int icadv_nhwc_to_nchw(const float* src, float* dst, int n, int c, int h, int w, icadv_stream_t stream) {
+  ICADV_REQUIRE(src && dst, "null pointer");
+  return launch_transpose(src, dst, n, h * w, c, as_stream(stream));  // [n][hw][c] -> [n][c][hw]
+}
+
+int icadv_gdn_reparam(const float* raw, float* eff, int rows, int cols, float bound, float pedestal, int transpose,
+                      icadv_stream_t stream) {
+  ICADV_REQUIRE(raw && eff && rows > 0 && cols > 0, "bad gdn_reparam args");
+  int total = rows * cols;
+  gdn_reparam_kernel<<<(total + 255) / 256, 256, 0, as_stream(stream)>>>(raw, eff, rows, cols, bound, pedestal,
+                                                                          transpose);
+  ICADV_CUDA_TRY(cudaGetLastError());
+  return ICADV_OK;
+}
+
+}  // extern "C"

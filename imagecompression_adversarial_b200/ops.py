@@ -1,0 +1,244 @@
+"""Functional layer over the C ABI: torch tensors in, torch tensors out, every FLOP in libicadv_b200.so.
+
+Internal activation layout is channels-last: tensors of shape [N, H, W, C], contiguous, fp32, CUDA.
+(At the operator surface these are the ``permute(0, 2, 3, 1)`` view of a ``channels_last`` NCHW tensor,
+so crossing it costs no copy.)  PyTorch only provides memory and the stream here.
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib as L
+
+_plans = {}
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _p(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _chk(t, name, dtype=torch.float32):
+    if t is None:
+        return
+    if not (t.is_cuda and t.dtype == dtype and t.is_contiguous()):
+        raise L.IcadvError(f"{name}: expected a contiguous CUDA {dtype} tensor, got {t.dtype} "
+                           f"{'cuda' if t.is_cuda else 'cpu'} contiguous={t.is_contiguous()}")
+
+
+def require_device():
+    if not torch.cuda.is_available():
+        raise L.IcadvError("no CUDA device: imagecompression_adversarial_b200 has no CPU path")
+    L.call("icadv_check_device")
+
+
+def pack_weight(w, kind):
+    """torch Conv2d [Co,Ci,k,k] / ConvTranspose2d [Ci,Co,k,k] weight -> packed [k*k][n_ch][k_ch]."""
+    w = w.detach().contiguous()
+    _chk(w, "weight")
+    k = w.shape[-1]
+    if kind in (L.PACK_CONV_FWD, L.PACK_CONV_DGRAD):
+        c_out, c_in = w.shape[0], w.shape[1]
+    else:
+        c_in, c_out = w.shape[0], w.shape[1]
+    n, kk = (c_out, c_in) if kind in (L.PACK_CONV_FWD, L.PACK_CONVT_FWD) else (c_in, c_out)
+    out = torch.empty(k * k, n, kk, device=w.device, dtype=torch.float32)
+    L.call("icadv_pack_weight", _p(w), _p(out), kind, c_out, c_in, k, _stream())
+    return out
+
+
+def unpack_weight_grad(dwpack, like, kind, accumulate_into=None):
+    """packed dW [k*k][n][k] -> gradient in the torch layout of ``like``."""
+    k = like.shape[-1]
+    if kind in (L.PACK_CONV_FWD, L.PACK_CONV_DGRAD):
+        c_out, c_in = like.shape[0], like.shape[1]
+    else:
+        c_in, c_out = like.shape[0], like.shape[1]
+    dst = accumulate_into if accumulate_into is not None else torch.empty_like(like)
+    L.call("icadv_unpack_weight", _p(dwpack), _p(dst), kind, c_out, c_in, k, 1 if accumulate_into is not None else 0,
+           _stream())
+    return dst
+
+
+def nchw_to_nhwc(x):
+    x = x.contiguous()
+    _chk(x, "x")
+    n, c, h, w = x.shape
+    out = torch.empty(n, h, w, c, device=x.device, dtype=torch.float32)
+    L.call("icadv_nchw_to_nhwc", _p(x), _p(out), n, c, h, w, _stream())
+    return out
+
+
+def nhwc_to_nchw(x):
+    _chk(x, "x")
+    n, h, w, c = x.shape
+    out = torch.empty(n, c, h, w, device=x.device, dtype=torch.float32)
+    L.call("icadv_nhwc_to_nchw", _p(x), _p(out), n, c, h, w, _stream())
+    return out
+
+
+def gdn_reparam(raw, bound, pedestal, transpose=False):
+    raw = raw.detach().contiguous()
+    _chk(raw, "raw")
+    rows, cols = (raw.shape[0], raw.shape[1]) if raw.dim() == 2 else (1, raw.numel())
+    out = torch.empty_like(raw)
+    L.call("icadv_gdn_reparam", _p(raw), _p(out), rows, cols, float(bound), float(pedestal), 1 if transpose else 0,
+           _stream())
+    return out
+
+
+def out_hw(form, ksize, stride, h, w):
+    if form == L.FORM_SCONV:
+        p = ksize // 2
+        return (h + 2 * p - ksize) // stride + 1, (w + 2 * p - ksize) // stride + 1
+    return h * stride, w * stride
+
+
+def make_desc(x, wpack, bias, out, *, form, ksize, stride, n_ch, epi=L.EPI_LINEAR, act=L.ACT_NONE, gmat=None,
+              beta=None, out_scale=None, y_prev=None, sc_prev=None, acc_from_in=False, active=None, n_active=None):
+    n, h, w, k_ch = x.shape
+    d = L.ConvDesc()
+    d.form, d.ksize, d.stride, d.n_img, d.in_h, d.in_w, d.k_ch, d.n_ch = form, ksize, stride, n, h, w, k_ch, n_ch
+    d.inp, d.wpack, d.bias, d.out = _p(x), _p(wpack), _p(bias), _p(out)
+    d.epi, d.act = epi, act
+    d.gmat, d.beta, d.out_scale, d.y_prev, d.sc_prev = _p(gmat), _p(beta), _p(out_scale), _p(y_prev), _p(sc_prev)
+    d.acc_from_in = 1 if acc_from_in else 0
+    d.active, d.n_active = _p(active), _p(n_active)
+    return d
+
+
+def conv(x, wpack, bias=None, *, form, ksize, stride, n_ch, epi=L.EPI_LINEAR, act=L.ACT_NONE, gmat=None, beta=None,
+         y_prev=None, sc_prev=None, acc_from_in=False, active=None, n_active=None, out=None, out_scale=None,
+         path="auto"):
+    """One contraction launch (see include/icadv.h).  Returns ``out`` or ``(out, out_scale)`` for the
+    GDN/IGDN forward epilogues.  ``path``: "auto" (tensor path when the shape allows), "tc", "simt"."""
+    for t, nm in ((x, "x"), (wpack, "wpack"), (bias, "bias"), (gmat, "gmat"), (beta, "beta"), (y_prev, "y_prev"),
+                  (sc_prev, "sc_prev"), (out, "out"), (out_scale, "out_scale")):
+        _chk(t, nm)
+    _chk(active, "active", torch.int32)
+    _chk(n_active, "n_active", torch.int32)
+    n, h, w, _ = x.shape
+    oh, ow = out_hw(form, ksize, stride, h, w)
+    if out is None:
+        out = torch.empty(n, oh, ow, n_ch, device=x.device, dtype=torch.float32)
+    fwd_gdn = epi in (L.EPI_GDN_FWD, L.EPI_IGDN_FWD)
+    if fwd_gdn and out_scale is None:
+        out_scale = torch.empty_like(out)
+    d = make_desc(x, wpack, bias, out, form=form, ksize=ksize, stride=stride, n_ch=n_ch, epi=epi, act=act, gmat=gmat,
+                  beta=beta, out_scale=out_scale, y_prev=y_prev, sc_prev=sc_prev, acc_from_in=acc_from_in,
+                  active=active, n_active=n_active)
+    use_tc = path == "tc" or (path == "auto" and L.lib().icadv_conv_tc_supported(C.byref(d)) == 1)
+    if use_tc:
+        L.call("icadv_conv_tc", C.byref(d), _stream())
+    else:
+        if epi != L.EPI_LINEAR or acc_from_in:
+            raise L.IcadvError("GDN epilogues need the tensor path (k_ch, n_ch multiples of 32)")
+        L.call("icadv_conv_simt", C.byref(d), _stream())
+    return (out, out_scale) if fwd_gdn else out
+
+
+class ConvPlan:
+    """Cached tensor maps + launch geometry for fixed buffers (icadv_conv_plan_*)."""
+
+    def __init__(self, desc, keep):
+        self._keep = keep  # tensors whose pointers are baked into the tensor maps
+        h = C.c_void_p()
+        L.call("icadv_conv_plan_create", C.byref(desc), C.byref(h))
+        self._h = h
+
+    def launch(self):
+        L.call("icadv_conv_plan_launch", self._h, _stream())
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None):
+                L.lib().icadv_conv_plan_destroy(self._h)
+        except Exception:
+            pass
+
+
+class SimtLaunch:
+    """Same interface as ConvPlan for the CUDA-core path (no cached state beyond the descriptor)."""
+
+    def __init__(self, desc, keep):
+        self._keep, self._d = keep, desc
+
+    def launch(self):
+        L.call("icadv_conv_simt", C.byref(self._d), _stream())
+
+
+def conv_wgrad(x, gout, *, form, ksize, stride, n_ch, want_bias=True):
+    """dW (packed) and dbias of a contraction whose forward input was ``x`` and output gradient ``gout``."""
+    _chk(x, "x")
+    _chk(gout, "gout")
+    k_ch = x.shape[-1]
+    dw = torch.empty(ksize * ksize, n_ch, k_ch, device=x.device, dtype=torch.float32)
+    db = torch.empty(n_ch, device=x.device, dtype=torch.float32) if want_bias else None
+    d = make_desc(x, dw, None, gout, form=form, ksize=ksize, stride=stride, n_ch=n_ch)
+    L.call("icadv_conv_wgrad", C.byref(d), _p(gout), _p(dw), _p(db), _stream())
+    return dw, db
+
+
+# ------------------------------------------------------------------ perturbation step
+class PerturbState:
+    """Device-resident per-image loop state (include/icadv.h icadv_perturb_state)."""
+
+    def __init__(self, n_img, device):
+        f = lambda: torch.zeros(n_img, device=device, dtype=torch.float32)
+        i = lambda n=n_img: torch.zeros(n, device=device, dtype=torch.int32)
+        self.n_img = n_img
+        self.sum_d2, self.loss_i, self.lr, self.step_size, self.bc2_sqrt = f(), f(), f(), f(), f()
+        self.branch, self.active, self.step, self.n_active = i(), i(), i(), i(1)
+        self.ws = torch.zeros(n_img * L.RED_BLOCKS, device=device, dtype=torch.float32)
+        s = L.PerturbState()
+        for name in ("sum_d2", "loss_i", "branch", "active", "n_active", "step", "lr", "step_size", "bc2_sqrt"):
+            setattr(s, name, _p(getattr(self, name)))
+        self.c = s
+
+
+def perturb_forward(im_s, noise, im_in, st, *, eps, budget, force_branch=-1, lr0=0.01, lr_gamma=0.33, sched_period,
+                    beta1=0.9, beta2=0.999):
+    per_img = im_s[0].numel()
+    L.call("icadv_perturb_forward", _p(im_s), _p(noise), _p(im_in), _p(st.ws), C.byref(st.c), st.n_img, per_img,
+           float(eps), float(budget), int(force_branch), float(lr0), float(lr_gamma), int(sched_period), float(beta1),
+           float(beta2), _stream())
+
+
+def perturb_update_adam(im_s, noise, g_in, m, v, st, *, eps, beta1=0.9, beta2=0.999, adam_eps=1e-8, gradA_scale,
+                        gradB_scale=1.0):
+    per_img = im_s[0].numel()
+    L.call("icadv_perturb_update_adam", _p(im_s), _p(noise), _p(g_in), _p(m), _p(v), C.byref(st.c), st.n_img, per_img,
+           float(eps), float(beta1), float(beta2), float(adam_eps), float(gradA_scale), float(gradB_scale), _stream())
+
+
+def output_loss(x, ref, g_x, ws, sum_d2, *, do_clamp, grad_scale, active=None, n_active=None):
+    n_img, per_img = x.shape[0], x[0].numel()
+    L.call("icadv_output_loss", _p(x), _p(ref), _p(g_x), _p(ws), _p(sum_d2), n_img, per_img, 1 if do_clamp else 0,
+           float(grad_scale), _p(active), _p(n_active), _stream())
+
+
+def sum_sqdiff(a, b):
+    n_img, per_img = a.shape[0], a[0].numel()
+    ws = torch.empty(n_img * L.RED_BLOCKS, device=a.device, dtype=torch.float32)
+    out = torch.empty(n_img, device=a.device, dtype=torch.float32)
+    L.call("icadv_sum_sqdiff", _p(a), _p(b), _p(ws), _p(out), n_img, per_img, _stream())
+    return out
+
+
+def ifgsm_update(im_s, im_adv, g, *, alpha, eps):
+    L.call("icadv_ifgsm_update", _p(im_s), _p(im_adv), _p(g), im_s.numel(), float(alpha), float(eps), _stream())
+
+
+def bound_forward(x, bound, upper):
+    y = torch.empty_like(x)
+    L.call("icadv_bound_forward", _p(x), _p(y), x.numel(), float(bound), 1 if upper else 0, _stream())
+    return y
+
+
+def bound_backward(x, gy, bound, upper):
+    gx = torch.empty_like(x)
+    L.call("icadv_bound_backward", _p(x), _p(gy), _p(gx), x.numel(), float(bound), 1 if upper else 0, _stream())
+    return gx

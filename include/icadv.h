@@ -1,0 +1,186 @@
+/* icadv.h -- C ABI of libicadv_b200.so: the sm_100a CUDA implementation of the per-image
+ * adversarial-perturbation hot path of tongxyh/ImageCompression_Adversarial.
+ *
+ * Boundary contract:
+ *   - plain C, raw DEVICE pointers + sizes + a cudaStream_t (passed as void*); no torch types;
+ *   - the caller owns every buffer; the library allocates nothing persistent except plan objects
+ *     (tensor maps + launch geometry) that the caller creates and destroys;
+ *   - every entry point returns 0 or a negative ICADV_E* code; icadv_last_error() gives the text;
+ *   - all work is stream-ordered and CUDA-graph capturable (no host synchronisation inside);
+ *   - reductions are fixed-order (deterministic); no floating-point atomics;
+ *   - activations are channels-last (NHWC) fp32; GEMM-shaped work runs as tcgen05 kind::tf32 with
+ *     fp32 accumulation in TMEM (the reference's GPU path is cuDNN with TF32 allowed);
+ *   - there is no CPU path: without an sm_100 device every compute entry point fails.
+ *
+ * Each entry point cites the reference interface (file:line under /root/reference) it replaces.
+ */
+#ifndef ICADV_H_
+#define ICADV_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ICADV_OK 0
+#define ICADV_EINVAL (-1)   /* bad argument / unsupported shape */
+#define ICADV_ECUDA (-2)    /* CUDA runtime / driver error */
+#define ICADV_EARCH (-3)    /* device is not sm_100 */
+#define ICADV_ENOMEM (-4)
+
+typedef void* icadv_stream_t; /* cudaStream_t */
+
+const char* icadv_last_error(void);
+int icadv_version(void);
+/* 0 if the current device is sm_100 (B200), ICADV_EARCH otherwise */
+int icadv_check_device(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Convolution-shaped contractions: nn.Conv2d / nn.ConvTranspose2d of the codec stacks
+ *   net.g_a / net.g_s / net.h_a / net.h_s   (anchors/utils.py:112-130, attack_rd.py:344,349)
+ * forward AND input-gradient (autograd of attack_rd.py:547), with GDN / IGDN
+ * (utils/ops.py:58-97; compressai.layers.GDN) fused into the epilogue in both directions.
+ *
+ * Two geometric forms cover fwd and dgrad of both layer types (stride s, kernel k, pad k/2):
+ *   ICADV_FORM_SCONV  out[n,oh,ow,:] = sum_taps in[n, s*oh+kh-p, s*ow+kw-p, :] * W[tap]
+ *                     (Conv2d forward; ConvTranspose2d input-gradient)
+ *   ICADV_FORM_TCONV  out[n, s*i+kh-p, s*j+kw-p, :] += in[n,i,j,:] * W[tap]      (output_padding s-1)
+ *                     (ConvTranspose2d forward; Conv2d input-gradient)
+ * W is pre-packed [k*k taps][n_ch][k_ch] fp32 (icadv_pack_weight).
+ * ------------------------------------------------------------------------------------------ */
+#define ICADV_FORM_SCONV 0
+#define ICADV_FORM_TCONV 1
+
+#define ICADV_EPI_LINEAR 0   /* out = acc + bias, optional activation */
+#define ICADV_EPI_GDN_FWD 1  /* x = acc+bias; sc = rsqrt(beta + G x^2); out = x*sc; out_scale = sc */
+#define ICADV_EPI_IGDN_FWD 2 /* ... sc = sqrt(...) */
+#define ICADV_EPI_GDN_BWD 3  /* g = acc; t = g*y*sc^2; s = G^T t; out = g*sc - (y/sc)*s */
+#define ICADV_EPI_IGDN_BWD 4 /* t = g*y/sc^2;        out = g*sc + (y/sc)*s */
+
+#define ICADV_ACT_NONE 0
+#define ICADV_ACT_RELU 1
+#define ICADV_ACT_LEAKY 2 /* slope 0.01 */
+#define ICADV_ACT_ABS 3   /* used for h_a(|y|), anchors/balle.py:38 */
+
+typedef struct {
+  int form;            /* ICADV_FORM_* */
+  int ksize, stride;   /* 5/2 (codec stacks), 3/1, 3/2, 1/1, 5/1 */
+  int n_img;           /* images in the buffers */
+  int in_h, in_w;      /* spatial size of `in` */
+  int k_ch, n_ch;      /* input / output channels of this contraction */
+  const float* in;     /* [n_img, in_h, in_w, k_ch] */
+  const float* wpack;  /* [k*k][n_ch][k_ch] */
+  const float* bias;   /* [n_ch] or NULL */
+  float* out;          /* [n_img, out_h, out_w, n_ch] */
+  int epi;             /* ICADV_EPI_* */
+  int act;             /* ICADV_ACT_* (EPI_LINEAR only) */
+  const float* gmat;   /* [n_ch][n_ch]: effective gamma (FWD) or its transpose (BWD) */
+  const float* beta;   /* [n_ch] effective beta (FWD) */
+  float* out_scale;    /* FWD: sc, same shape as out */
+  const float* y_prev; /* BWD: saved out of the matching FWD */
+  const float* sc_prev;/* BWD: saved out_scale of the matching FWD */
+  int acc_from_in;     /* 1: no contraction, acc := in (1x1, k_ch == n_ch); GDN/IGDN as a stand-alone op */
+  const int* active;   /* optional [n_img] image indirection (device) */
+  const int* n_active; /* optional device scalar: number of valid entries of `active` */
+} icadv_conv_desc;
+
+/* output spatial size implied by a descriptor */
+int icadv_conv_out_hw(const icadv_conv_desc* d, int* out_h, int* out_w);
+
+/* tcgen05/TMEM/TMA implicit-GEMM path.  Requires k_ch % 32 == 0, n_ch % 32 == 0, n_ch <= 256
+ * (<= 192 for the GDN epilogues unless n_ch == 256 fits 512 TMEM columns).  A plan caches the
+ * TMA tensor maps for fixed buffers; launching is stream-ordered. */
+typedef struct icadv_conv_plan icadv_conv_plan;
+int icadv_conv_plan_create(const icadv_conv_desc* d, icadv_conv_plan** plan);
+int icadv_conv_plan_launch(const icadv_conv_plan* plan, icadv_stream_t stream);
+int icadv_conv_plan_destroy(icadv_conv_plan* plan);
+int icadv_conv_tc(const icadv_conv_desc* d, icadv_stream_t stream); /* create + launch + destroy */
+int icadv_conv_tc_supported(const icadv_conv_desc* d);             /* 1 / 0 */
+
+/* CUDA-core path for the shapes the tensor path does not take (3-channel end layers, odd widths).
+ * Same descriptor; only ICADV_EPI_LINEAR. */
+int icadv_conv_simt(const icadv_conv_desc* d, icadv_stream_t stream);
+
+/* weight gradient of a contraction (train.py:359 only; the attack never reads parameter grads):
+ * dW[tap][n][k] = sum_px gout[px,n] * in[tap-shifted px,k]; deterministic split reduction. */
+int icadv_conv_wgrad(const icadv_conv_desc* d, const float* gout, float* dwpack, float* dbias,
+                     icadv_stream_t stream);
+
+/* torch layouts -> packed [taps][n_ch][k_ch].  kind: 0 Conv2d.weight [Co,Ci,k,k] for its forward,
+ * 1 Conv2d.weight for its input-gradient, 2 ConvTranspose2d.weight [Ci,Co,k,k] for its forward,
+ * 3 ConvTranspose2d.weight for its input-gradient. */
+int icadv_pack_weight(const float* w, float* wpack, int kind, int c_out, int c_in, int ksize,
+                      icadv_stream_t stream);
+/* inverse of the above for gradients: packed dW -> torch layout (accumulate = add into dst) */
+int icadv_unpack_weight(const float* dwpack, float* dw, int kind, int c_out, int c_in, int ksize,
+                        int accumulate, icadv_stream_t stream);
+
+/* layout conversion at the operator surface: NCHW <-> NHWC fp32 */
+int icadv_nchw_to_nhwc(const float* src, float* dst, int n, int c, int h, int w, icadv_stream_t stream);
+int icadv_nhwc_to_nchw(const float* src, float* dst, int n, int c, int h, int w, icadv_stream_t stream);
+
+/* GDN parameter reparametrisation (compressai NonNegativeParametrizer; utils/ops.py:83-90):
+ * eff = max(raw, bound)^2 - pedestal.  transpose != 0 writes eff^T (rows x rows). */
+int icadv_gdn_reparam(const float* raw, float* eff, int rows, int cols, float bound, float pedestal,
+                      int transpose, icadv_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Perturbation step (attack_rd.py:507,517,546-554; utils/ops.py:28-56; torch.optim.Adam +
+ * MultiStepLR).  Elementwise and layout-agnostic; per_img = elements per image (C*H*W, % 4 == 0).
+ * Per-image semantics: every image behaves like one N=1 call of the reference's attack_().
+ * ------------------------------------------------------------------------------------------ */
+#define ICADV_RED_BLOCKS 128 /* partial sums per image; reduction workspaces hold n_img*128 floats */
+
+/* Device-resident per-image state (all arrays of n_img unless noted): no host sync in the loop. */
+typedef struct {
+  float* sum_d2;    /* sum (im_s - im_in)^2 */
+  float* loss_i;    /* sum_d2 / per_img               (attack_rd.py:333) */
+  int* branch;      /* 0 = A (over budget), 1 = B (network pass)   (attack_rd.py:334) */
+  int* active;      /* compacted indices of the branch-B images */
+  int* n_active;    /* [1] */
+  int* step;        /* iteration counter i (0-based before the call, incremented by perturb_forward) */
+  float* lr;        /* lr used at this iteration (MultiStepLR([1,2,3]) stepped every steps//3) */
+  float* step_size; /* lr / (1 - beta1^t) */
+  float* bc2_sqrt;  /* sqrt(1 - beta2^t) */
+} icadv_perturb_state;
+
+/* noise -> clamp(+-eps) -> im_in = clamp(im_s + noise_clipped, 0, 1); loss_i; branch (force_branch
+ * -1 = by budget, 0/1 = forced); compaction; LR schedule and Adam coefficients for this iteration. */
+int icadv_perturb_forward(const float* im_s, const float* noise, float* im_in, float* ws,
+                          const icadv_perturb_state* st, int n_img, int64_t per_img, float eps,
+                          float noise_budget, int force_branch, double lr0, double lr_gamma,
+                          int sched_period, double beta1, double beta2, icadv_stream_t stream);
+
+/* Backward of the two clamp pairs (custom Low/Up_bound rule) + Adam on the perturbation, fused.
+ * Branch A forms d loss_i / d im_in in-kernel (x gradA_scale = 1/per_img); branch B reads g_in =
+ * dLoss/d im_in from the network backward (x gradB_scale). */
+int icadv_perturb_update_adam(const float* im_s, float* noise, const float* g_in, float* m, float* v,
+                              const icadv_perturb_state* st, int n_img, int64_t per_img, float eps,
+                              float beta1, float beta2, float adam_eps, float gradA_scale,
+                              float gradB_scale, icadv_stream_t stream);
+
+/* I-FGSM / PGD step (attack_ifgsm.py:409-418): x += alpha*sign(g); project to [x0-eps, x0+eps]. */
+int icadv_ifgsm_update(const float* im_s, float* im_adv, const float* g, int64_t n, float alpha,
+                       float eps, icadv_stream_t stream);
+
+/* Output clamp + distortion (attack_rd.py:353-364) and its gradient seed:
+ * o = clamp(x,0,1) (if do_clamp); sum_d2[n] = sum (ref - o)^2;
+ * g_x = grad_scale * 2 (ref - o) passed through the Low/Up_bound backward rule (g_x may be NULL). */
+int icadv_output_loss(const float* x, const float* ref, float* g_x, float* ws, float* sum_d2, int n_img,
+                      int64_t per_img, int do_clamp, float grad_scale, const int* active,
+                      const int* n_active, icadv_stream_t stream);
+
+/* Low_bound / Up_bound as stand-alone ops (utils/ops.py:28-56) */
+int icadv_bound_forward(const float* x, float* y, int64_t n, float bound, int upper, icadv_stream_t stream);
+int icadv_bound_backward(const float* x, const float* gy, float* gx, int64_t n, float bound, int upper,
+                         icadv_stream_t stream);
+
+/* per-image sum of squared differences, deterministic two-stage reduction */
+int icadv_sum_sqdiff(const float* a, const float* b, float* ws, float* out, int n_img, int64_t per_img,
+                     icadv_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ICADV_H_ */

@@ -1,0 +1,324 @@
+"""Per-kernel parity on a B200: every C-ABI compute entry point against the same op in plain torch
+(fp32, TF32 off) / the oracle layers, forward and backward.  Tolerances are written per test:
+bit-exact for clamps and layout moves, 1e-5 relative for CUDA-core fp32 contractions, and a TF32
+bound (inputs truncated to 10 mantissa bits, fp32 accumulate) for the tcgen05 path.
+"""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def dev():
+    from imagecompression_adversarial_b200 import ops
+    ops.require_device()
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    return torch.device("cuda:0")
+
+
+def nhwc(x):
+    return x.permute(0, 2, 3, 1).contiguous()
+
+
+def nchw(x):
+    return x.permute(0, 3, 1, 2).contiguous()
+
+
+def rel_err(a, b):
+    return float((a - b).abs().max() / (b.abs().max() + 1e-30))
+
+
+def rms_err(a, b):
+    return float((a - b).pow(2).mean().sqrt() / (b.pow(2).mean().sqrt() + 1e-30))
+
+
+def ref_contraction(kind, x, w, b, k, s):
+    """kind 0 Conv2d fwd, 1 Conv2d dgrad (x = grad_out), 2 ConvT fwd, 3 ConvT dgrad (x = grad_out)."""
+    p = k // 2
+    if kind == 0:
+        return F.conv2d(x, w, b, stride=s, padding=p)
+    if kind == 2:
+        return F.conv_transpose2d(x, w, b, stride=s, padding=p, output_padding=s - 1)
+    if kind == 1:  # gradient of conv2d wrt its input == conv_transpose2d with the same weight
+        return F.conv_transpose2d(x, w, None, stride=s, padding=p, output_padding=s - 1)
+    return F.conv2d(x, w, None, stride=s, padding=p)  # gradient of conv_transpose2d wrt its input
+
+
+def run_contraction(kind, x, w, b, k, s, path):
+    from imagecompression_adversarial_b200 import _lib as L
+    from imagecompression_adversarial_b200 import ops
+    form = L.FORM_SCONV if kind in (0, 3) else L.FORM_TCONV
+    wp = ops.pack_weight(w, kind)
+    out = ops.conv(nhwc(x), wp, b, form=form, ksize=k, stride=s, n_ch=wp.shape[1], path=path)
+    return nchw(out)
+
+
+def make_w(kind, cin_layer, cout_layer, k, dev, g):
+    # torch weight of the LAYER (Conv2d [co,ci,k,k]; ConvT [ci,co,k,k]) and the channel count of `x`
+    if kind in (0, 1):
+        w = torch.randn(cout_layer, cin_layer, k, k, device=dev, generator=g) / math.sqrt(cin_layer * k * k)
+    else:
+        w = torch.randn(cin_layer, cout_layer, k, k, device=dev, generator=g) / math.sqrt(cin_layer * k * k)
+    x_ch = cin_layer if kind in (0, 2) else cout_layer
+    return w, x_ch
+
+
+def test_layout_roundtrip(dev):
+    from imagecompression_adversarial_b200 import ops
+    x = torch.randn(3, 5, 37, 41, device=dev)
+    y = ops.nchw_to_nhwc(x)
+    assert torch.equal(y, x.permute(0, 2, 3, 1).contiguous())
+    assert torch.equal(ops.nhwc_to_nchw(y), x)
+
+
+@pytest.mark.parametrize("kind", [0, 1, 2, 3])
+def test_pack_unpack_weight(dev, kind):
+    from imagecompression_adversarial_b200 import ops
+    g = torch.Generator(device=dev).manual_seed(kind)
+    w, _ = make_w(kind, 6, 10, 5, dev, g)
+    wp = ops.pack_weight(w, kind)
+    back = ops.unpack_weight_grad(wp, w, kind)
+    assert torch.equal(back, w)
+
+
+@pytest.mark.parametrize("kind,cin,cout,k,s,hw", [
+    (0, 3, 16, 5, 2, (20, 28)), (1, 3, 16, 5, 2, (10, 14)), (2, 16, 3, 5, 2, (10, 14)), (3, 16, 3, 5, 2, (20, 28)),
+    (0, 8, 12, 3, 1, (9, 11)), (0, 8, 12, 3, 2, (10, 12)), (2, 128, 3, 5, 2, (6, 10)), (0, 5, 7, 1, 1, (4, 6)),
+    (1, 8, 12, 3, 1, (9, 11)), (0, 16, 24, 5, 2, (17, 23)),
+])
+def test_conv_simt_matches_torch(dev, kind, cin, cout, k, s, hw):
+    g = torch.Generator(device=dev).manual_seed(100 + kind)
+    w, xc = make_w(kind, cin, cout, k, dev, g)
+    x = torch.randn(2, xc, *hw, device=dev, generator=g)
+    b = torch.randn(cout, device=dev, generator=g) if kind in (0, 2) else None
+    if kind in (1, 3) and (s == 2 and any(d % 2 for d in hw) and kind == 3):
+        pytest.skip("odd dgrad geometry")
+    ref = ref_contraction(kind, x, w, b, k, s)
+    got = run_contraction(kind, x, w, b, k, s, "simt")
+    assert got.shape == ref.shape
+    assert rel_err(got, ref) < 2e-5
+
+
+TC_CASES = [
+    (0, 128, 128, 5, 2, (32, 48), 2), (1, 128, 128, 5, 2, (16, 24), 2), (2, 192, 128, 5, 2, (8, 12), 1),
+    (3, 192, 128, 5, 2, (16, 24), 1), (0, 128, 192, 5, 2, (32, 48), 1), (0, 128, 128, 5, 2, (20, 36), 1),
+    (2, 128, 128, 5, 2, (5, 9), 2), (0, 128, 128, 3, 1, (12, 20), 1), (0, 64, 32, 1, 1, (8, 16), 1),
+    (0, 192, 128, 3, 1, (9, 17), 1), (2, 128, 128, 5, 2, (16, 16), 3),
+]
+
+
+@pytest.mark.parametrize("kind,cin,cout,k,s,hw,n", TC_CASES)
+def test_conv_tc_matches_torch(dev, kind, cin, cout, k, s, hw, n):
+    g = torch.Generator(device=dev).manual_seed(200 + kind)
+    w, xc = make_w(kind, cin, cout, k, dev, g)
+    x = torch.randn(n, xc, *hw, device=dev, generator=g)
+    b = torch.randn(cout, device=dev, generator=g) if kind in (0, 2) else None
+    ref = ref_contraction(kind, x, w, b, k, s)
+    got = run_contraction(kind, x, w, b, k, s, "tc")
+    assert got.shape == ref.shape
+    e = rms_err(got, ref)
+    assert e < 2e-3, e           # TF32 operand truncation, fp32 accumulate
+    assert rel_err(got, ref) < 1e-2
+    # and against the CUDA-core path of this library
+    simt = run_contraction(kind, x, w, b, k, s, "simt")
+    assert rms_err(got, simt) < 2e-3
+
+
+def _gdn_params(C, dev, g):
+    gamma = 0.1 * torch.eye(C, device=dev) + 0.02 * torch.rand(C, C, device=dev, generator=g)
+    beta = 0.5 + torch.rand(C, device=dev, generator=g)
+    return gamma.contiguous(), beta.contiguous()
+
+
+def _gdn_ref(x, gamma, beta, inverse):
+    C = x.shape[1]
+    n = F.conv2d(x * x, gamma.view(C, C, 1, 1), beta)
+    sc = torch.sqrt(n) if inverse else torch.rsqrt(n)
+    return x * sc, sc
+
+
+@pytest.mark.parametrize("inverse", [False, True])
+@pytest.mark.parametrize("C,hw", [(128, (16, 32)), (192, (9, 20)), (64, (8, 16))])
+def test_gdn_standalone_fwd_bwd(dev, inverse, C, hw):
+    from imagecompression_adversarial_b200 import _lib as L
+    from imagecompression_adversarial_b200 import ops
+    g = torch.Generator(device=dev).manual_seed(7)
+    gamma, beta = _gdn_params(C, dev, g)
+    x = torch.randn(2, C, *hw, device=dev, generator=g).requires_grad_(True)
+    gy = torch.randn(2, C, *hw, device=dev, generator=g)
+    y_ref, sc_ref = _gdn_ref(x, gamma, beta, inverse)
+    (gx_ref,) = torch.autograd.grad(y_ref, x, gy)
+    xn = nhwc(x.detach())
+    y, sc = ops.conv(xn, None, None, form=L.FORM_SCONV, ksize=1, stride=1, n_ch=C,
+                     epi=L.EPI_IGDN_FWD if inverse else L.EPI_GDN_FWD, gmat=gamma, beta=beta, acc_from_in=True,
+                     path="tc")
+    assert rms_err(nchw(y), y_ref.detach()) < 1e-3
+    assert rms_err(nchw(sc), sc_ref.detach()) < 1e-3
+    gx = ops.conv(nhwc(gy), None, None, form=L.FORM_SCONV, ksize=1, stride=1, n_ch=C,
+                  epi=L.EPI_IGDN_BWD if inverse else L.EPI_GDN_BWD, gmat=gamma.t().contiguous(), y_prev=y, sc_prev=sc,
+                  acc_from_in=True, path="tc")
+    assert rms_err(nchw(gx), gx_ref) < 2e-3
+
+
+@pytest.mark.parametrize("inverse", [False, True])
+def test_conv_gdn_fused_fwd_and_bwd(dev, inverse):
+    """[conv|deconv] -> (I)GDN fused forward; next-layer dgrad -> (I)GDN backward fused."""
+    from imagecompression_adversarial_b200 import _lib as L
+    from imagecompression_adversarial_b200 import ops
+    g = torch.Generator(device=dev).manual_seed(11)
+    C = 128
+    gamma, beta = _gdn_params(C, dev, g)
+    if not inverse:   # g_a: conv -> GDN -> conv
+        w1 = torch.randn(C, C, 5, 5, device=dev, generator=g) / math.sqrt(C * 25)
+        w2 = torch.randn(C, C, 5, 5, device=dev, generator=g) / math.sqrt(C * 25)
+        b1 = torch.randn(C, device=dev, generator=g)
+        x = torch.randn(2, C, 32, 48, device=dev, generator=g)
+        u = F.conv2d(x, w1, b1, stride=2, padding=2).requires_grad_(True)
+        y_ref, _ = _gdn_ref(u, gamma, beta, False)
+        z = F.conv2d(y_ref, w2, None, stride=2, padding=2)
+        gz = torch.randn_like(z)
+        (gu_ref,) = torch.autograd.grad(z, u, gz)
+        y, sc = ops.conv(nhwc(x), ops.pack_weight(w1, 0), b1, form=L.FORM_SCONV, ksize=5, stride=2, n_ch=C,
+                         epi=L.EPI_GDN_FWD, gmat=gamma, beta=beta, path="tc")
+        gu = ops.conv(nhwc(gz), ops.pack_weight(w2, 1), None, form=L.FORM_TCONV, ksize=5, stride=2, n_ch=C,
+                      epi=L.EPI_GDN_BWD, gmat=gamma.t().contiguous(), y_prev=y, sc_prev=sc, path="tc")
+    else:             # g_s: deconv -> IGDN -> deconv
+        w1 = torch.randn(C, C, 5, 5, device=dev, generator=g) / math.sqrt(C * 25 / 4)
+        w2 = torch.randn(C, C, 5, 5, device=dev, generator=g) / math.sqrt(C * 25 / 4)
+        b1 = torch.randn(C, device=dev, generator=g)
+        x = torch.randn(2, C, 8, 12, device=dev, generator=g)
+        u = F.conv_transpose2d(x, w1, b1, stride=2, padding=2, output_padding=1).requires_grad_(True)
+        y_ref, _ = _gdn_ref(u, gamma, beta, True)
+        z = F.conv_transpose2d(y_ref, w2, None, stride=2, padding=2, output_padding=1)
+        gz = torch.randn_like(z)
+        (gu_ref,) = torch.autograd.grad(z, u, gz)
+        y, sc = ops.conv(nhwc(x), ops.pack_weight(w1, 2), b1, form=L.FORM_TCONV, ksize=5, stride=2, n_ch=C,
+                         epi=L.EPI_IGDN_FWD, gmat=gamma, beta=beta, path="tc")
+        gu = ops.conv(nhwc(gz), ops.pack_weight(w2, 3), None, form=L.FORM_SCONV, ksize=5, stride=2, n_ch=C,
+                      epi=L.EPI_IGDN_BWD, gmat=gamma.t().contiguous(), y_prev=y, sc_prev=sc, path="tc")
+    assert rms_err(nchw(y), y_ref.detach()) < 2e-3
+    assert rms_err(nchw(gu), gu_ref) < 4e-3
+
+
+def test_active_list_indirection(dev):
+    """Image compaction: only the listed images are computed, in place of the batch."""
+    from imagecompression_adversarial_b200 import _lib as L
+    from imagecompression_adversarial_b200 import ops
+    g = torch.Generator(device=dev).manual_seed(5)
+    w = torch.randn(64, 64, 3, 3, device=dev, generator=g) / 24
+    x = torch.randn(4, 64, 16, 16, device=dev, generator=g)
+    ref = F.conv2d(x, w, None, padding=1)
+    for path in ("tc", "simt"):
+        out = torch.full((4, 16, 16, 64), -7.0, device=dev)
+        active = torch.tensor([3, 1, 0, 0], device=dev, dtype=torch.int32)
+        n_active = torch.tensor([2], device=dev, dtype=torch.int32)
+        ops.conv(nhwc(x), ops.pack_weight(w, 0), None, form=L.FORM_SCONV, ksize=3, stride=1, n_ch=64, active=active,
+                 n_active=n_active, out=out, path=path)
+        o = nchw(out)
+        assert rms_err(o[3], ref[3]) < 2e-3 and rms_err(o[1], ref[1]) < 2e-3
+        assert torch.all(o[0] == -7.0) and torch.all(o[2] == -7.0)
+
+
+@pytest.mark.parametrize("kind,cin,cout,k,s,hw", [(0, 16, 24, 5, 2, (12, 20)), (2, 24, 16, 5, 2, (6, 10)),
+                                                  (0, 8, 8, 3, 1, (7, 9))])
+def test_conv_wgrad_matches_autograd(dev, kind, cin, cout, k, s, hw):
+    from imagecompression_adversarial_b200 import _lib as L
+    from imagecompression_adversarial_b200 import ops
+    g = torch.Generator(device=dev).manual_seed(300 + kind)
+    w, xc = make_w(kind, cin, cout, k, dev, g)
+    w.requires_grad_(True)
+    b = torch.randn(cout, device=dev, generator=g).requires_grad_(True)
+    x = torch.randn(3, xc, *hw, device=dev, generator=g)
+    out = ref_contraction(kind, x, w, b, k, s)
+    gout = torch.randn_like(out)
+    gw_ref, gb_ref = torch.autograd.grad(out, (w, b), gout)
+    form = L.FORM_SCONV if kind == 0 else L.FORM_TCONV
+    dwp, db = ops.conv_wgrad(nhwc(x), nhwc(gout), form=form, ksize=k, stride=s, n_ch=cout)
+    gw = ops.unpack_weight_grad(dwp, w, kind)
+    assert rel_err(gw, gw_ref) < 5e-5
+    assert rel_err(db, gb_ref) < 5e-5
+
+
+def test_bounds_match_oracle(dev):
+    from imagecompression_adversarial_b200 import ops
+    from oracle import layers as ol
+    g = torch.Generator(device=dev).manual_seed(3)
+    x = (torch.rand(10007, device=dev, generator=g) * 3 - 1)
+    gy = torch.randn(10007, device=dev, generator=g)
+    for bound, upper in ((0.0, False), (1.0, True), (-16 / 255, False), (16 / 255, True)):
+        xr = x.clone().requires_grad_(True)
+        yr = (ol.up_bound if upper else ol.low_bound)(xr, bound)
+        yr.backward(gy)
+        assert torch.equal(ops.bound_forward(x, bound, upper), yr.detach())
+        assert torch.equal(ops.bound_backward(x, gy, bound, upper), xr.grad)
+
+
+def test_perturb_step_matches_oracle_and_torch_adam(dev):
+    """perturb_forward + perturb_update_adam == Up/Low_bound autograd + torch.optim.Adam + MultiStepLR."""
+    from imagecompression_adversarial_b200 import ops
+    from oracle import layers as ol
+    g = torch.Generator(device=dev).manual_seed(9)
+    N, shape = 3, (3, 16, 24)
+    per = 3 * 16 * 24
+    im_s = torch.rand(N, *shape, device=dev, generator=g)
+    im_s[0, :, :4] = 0.0
+    im_s[1, :, :4] = 1.0
+    eps, budget, steps = 16 / 255, 1e-4, 12
+    noise = torch.zeros(N, *shape, device=dev)
+    m, v = torch.zeros_like(noise), torch.zeros_like(noise)
+    im_in = torch.empty_like(noise)
+    st = ops.PerturbState(N, dev)
+    refs = []
+    for n in range(N):
+        z = torch.zeros(1, *shape, device=dev, requires_grad=True)
+        opt = torch.optim.Adam([z], lr=0.01)
+        sch = torch.optim.lr_scheduler.MultiStepLR(opt, [1, 2, 3], gamma=0.33)
+        refs.append((z, opt, sch))
+    for i in range(steps):
+        gB = torch.randn(N, *shape, device=dev, generator=g) * 1e-3   # stands in for the network gradient
+        ops.perturb_forward(im_s, noise, im_in, st, eps=eps, budget=budget, sched_period=steps // 3)
+        branch = st.branch.cpu().tolist()
+        ops.perturb_update_adam(im_s, noise, gB, m, v, st, eps=eps, gradA_scale=1.0 / per)
+        for n, (z, opt, sch) in enumerate(refs):
+            nc = ol.up_bound(ol.low_bound(z, -eps), eps)
+            x_in = ol.up_bound(ol.low_bound(im_s[n:n + 1] + nc, 0.0), 1.0)
+            loss_i = torch.mean((im_s[n:n + 1] - x_in) ** 2)
+            assert abs(float(st.loss_i[n]) - float(loss_i)) <= 1e-6 * max(1e-6, float(loss_i)) + 1e-12
+            want_branch = 0 if float(loss_i) > budget else 1
+            assert branch[n] == want_branch
+            torch.testing.assert_close(im_in[n:n + 1], x_in.detach(), rtol=0, atol=0)
+            loss = loss_i if want_branch == 0 else (x_in * gB[n:n + 1]).sum()
+            opt.zero_grad()
+            loss.backward()
+            opt.step()
+            if i % (steps // 3) == 0:
+                sch.step()
+            torch.testing.assert_close(noise[n:n + 1], z.detach(), rtol=1e-5, atol=1e-7)
+    assert int(st.step[0]) == steps
+
+
+def test_output_loss_matches_oracle(dev):
+    from imagecompression_adversarial_b200 import _lib as L
+    from imagecompression_adversarial_b200 import ops
+    from oracle import layers as ol
+    g = torch.Generator(device=dev).manual_seed(13)
+    N, shape = 2, (3, 8, 12)
+    per = 3 * 8 * 12
+    x = (torch.rand(N, *shape, device=dev, generator=g) * 1.6 - 0.3)
+    ref = torch.rand(N, *shape, device=dev, generator=g)
+    gx = torch.zeros_like(x)
+    ws = torch.zeros(N * L.RED_BLOCKS, device=dev)
+    s = torch.zeros(N, device=dev)
+    ops.output_loss(x, ref, gx, ws, s, do_clamp=True, grad_scale=1.0 / per)
+    for n in range(N):
+        xr = x[n:n + 1].clone().requires_grad_(True)
+        o = ol.up_bound(ol.low_bound(xr, 0.0), 1.0)
+        loss = 1.0 - torch.mean((ref[n:n + 1] - o) * (ref[n:n + 1] - o))
+        loss.backward()
+        torch.testing.assert_close(gx[n:n + 1], xr.grad, rtol=1e-6, atol=1e-9)
+        assert abs(float(s[n]) / per - float(1.0 - loss)) < 1e-6
