@@ -59,13 +59,24 @@ _SIGS = {
                                         C.c_float, C.c_int, C.c_double, C.c_double, C.c_int, C.c_double, C.c_double,
                                         C.c_void_p]),
     "icadv_perturb_update_adam": (C.c_int, [_fp, _fp, _fp, _fp, _fp, C.POINTER(PerturbState), C.c_int, C.c_int64,
-                                            C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float,
+                                            C.c_float, C.c_double, C.c_double, C.c_double, C.c_float, C.c_float,
                                             C.c_void_p]),
     "icadv_ifgsm_update": (C.c_int, [_fp, _fp, _fp, C.c_int64, C.c_float, C.c_float, C.c_void_p]),
     "icadv_output_loss": (C.c_int, [_fp, _fp, _fp, _fp, _fp, C.c_int, C.c_int64, C.c_int, C.c_float, _fp, _fp,
                                     C.c_void_p]),
     "icadv_bound_forward": (C.c_int, [_fp, _fp, C.c_int64, C.c_float, C.c_int, C.c_void_p]),
     "icadv_bound_backward": (C.c_int, [_fp, _fp, _fp, C.c_int64, C.c_float, C.c_int, C.c_void_p]),
+    "icadv_eb_prepare": (C.c_int, [C.POINTER(_fp), C.POINTER(_fp), C.POINTER(_fp), _fp, C.c_int, C.c_void_p]),
+    "icadv_eb_forward": (C.c_int, [_fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, C.c_int, C.c_int64, C.c_int, C.c_int,
+                                   C.c_float, C.c_float, C.c_void_p]),
+    "icadv_gc_forward": (C.c_int, [_fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, C.c_int, C.c_int64, C.c_int, C.c_float,
+                                   C.c_float, C.c_float, C.c_void_p]),
+    "icadv_unary": (C.c_int, [_fp, _fp, _fp, C.c_int64, C.c_int, C.c_void_p]),
+    "icadv_act_backward": (C.c_int, [_fp, _fp, _fp, C.c_int64, C.c_int, C.c_void_p]),
+    "icadv_ssim_workspace_floats": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
+    "icadv_ssim_level": (C.c_int, [_fp, _fp, _fp, _fp, _fp, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float), C.c_int,
+                                   C.c_int, C.c_float, C.c_float, C.c_void_p]),
+    "icadv_avgpool2": (C.c_int, [_fp, _fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "icadv_sum_sqdiff": (C.c_int, [_fp, _fp, _fp, _fp, C.c_int, C.c_int64, C.c_void_p]),
 }
 

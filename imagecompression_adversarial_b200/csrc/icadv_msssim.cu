@@ -1,0 +1,161 @@
+// MS-SSIM level kernel (bandwidth bound): one pass over an image pair produces the per-plane sums of the
+// SSIM and contrast-structure maps.  The five Gaussian-filtered maps (X, Y, X^2, Y^2, XY) never leave the
+// SM: a 32x32 output tile + halo is staged in shared memory, filtered separably, and reduced in fixed order.
+//   variant 1 (valid, separable 11-tap sigma 1.5): pytorch_msssim.ms_ssim  (attack_rd.py:336,362;
+//              self_ensemble.py:225,228; train.py:44,88)
+//   variant 2 (zero "same" padding, 2-D = outer-product window): utils/torch_msssim.py:26-52
+// plus the 2x2 average pooling between levels (padding (H%2, W%2) for variant 1; none for variant 2).
+#include "icadv_common.cuh"
+
+namespace icadv {
+
+constexpr int kT = 32;          // output tile edge
+constexpr int kMaxWin = 11;
+constexpr int kIn = kT + kMaxWin - 1;  // 42
+
+struct SsimParams {
+  const float* X; const float* Y; float* ws;
+  int h, w, out_h, out_w, win, pad;  // pad = 0 (valid) or win/2 (same, zero fill)
+  int tiles_x, tiles_y;
+  float c1, c2;
+  float taps[kMaxWin];
+};
+
+__global__ void __launch_bounds__(256) ssim_level_kernel(const SsimParams p) {
+  __shared__ float sx[kIn][kIn + 1], sy[kIn][kIn + 1];
+  __shared__ float hm[5][kIn][kT + 1];
+  __shared__ float red[2][8];
+  const int plane = blockIdx.z;
+  const int ty0 = blockIdx.y * kT, tx0 = blockIdx.x * kT;
+  const float* X = p.X + (int64_t)plane * p.h * p.w;
+  const float* Y = p.Y + (int64_t)plane * p.h * p.w;
+  const int span = kT + p.win - 1;
+  for (int i = threadIdx.x; i < span * span; i += 256) {
+    const int r = i / span, c = i % span;
+    const int gy = ty0 + r - p.pad, gx = tx0 + c - p.pad;
+    float a = 0.f, b = 0.f;
+    if (gy >= 0 && gy < p.h && gx >= 0 && gx < p.w) { a = __ldg(X + (int64_t)gy * p.w + gx); b = __ldg(Y + (int64_t)gy * p.w + gx); }
+    sx[r][c] = a; sy[r][c] = b;
+  }
+  __syncthreads();
+  // horizontal pass
+  for (int i = threadIdx.x; i < span * kT; i += 256) {
+    const int r = i / kT, c = i % kT;
+    float m1 = 0.f, m2 = 0.f, s11 = 0.f, s22 = 0.f, s12 = 0.f;
+    for (int k = 0; k < p.win; ++k) {
+      const float g = p.taps[k], a = sx[r][c + k], b = sy[r][c + k];
+      m1 = fmaf(g, a, m1); m2 = fmaf(g, b, m2);
+      s11 = fmaf(g, a * a, s11); s22 = fmaf(g, b * b, s22); s12 = fmaf(g, a * b, s12);
+    }
+    hm[0][r][c] = m1; hm[1][r][c] = m2; hm[2][r][c] = s11; hm[3][r][c] = s22; hm[4][r][c] = s12;
+  }
+  __syncthreads();
+  // vertical pass + maps
+  float acc_s = 0.f, acc_c = 0.f;
+  for (int i = threadIdx.x; i < kT * kT; i += 256) {
+    const int r = i / kT, c = i % kT;
+    if (ty0 + r >= p.out_h || tx0 + c >= p.out_w) continue;
+    float m1 = 0.f, m2 = 0.f, s11 = 0.f, s22 = 0.f, s12 = 0.f;
+    for (int k = 0; k < p.win; ++k) {
+      const float g = p.taps[k];
+      m1 = fmaf(g, hm[0][r + k][c], m1); m2 = fmaf(g, hm[1][r + k][c], m2);
+      s11 = fmaf(g, hm[2][r + k][c], s11); s22 = fmaf(g, hm[3][r + k][c], s22); s12 = fmaf(g, hm[4][r + k][c], s12);
+    }
+    const float m11 = m1 * m1, m22 = m2 * m2, m12 = m1 * m2;
+    const float v1 = s11 - m11, v2 = s22 - m22, v12 = s12 - m12;
+    const float cs = (2.f * v12 + p.c2) / (v1 + v2 + p.c2);
+    const float ss = ((2.f * m12 + p.c1) / (m11 + m22 + p.c1)) * cs;
+    acc_s += ss; acc_c += cs;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    acc_s += __shfl_xor_sync(0xffffffffu, acc_s, o);
+    acc_c += __shfl_xor_sync(0xffffffffu, acc_c, o);
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) { red[0][warp] = acc_s; red[1][warp] = acc_c; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float s = 0.f, c = 0.f;
+    for (int k = 0; k < 8; ++k) { s += red[0][k]; c += red[1][k]; }
+    const int nb = p.tiles_x * p.tiles_y, b = blockIdx.y * p.tiles_x + blockIdx.x;
+    p.ws[((int64_t)plane * nb + b) * 2 + 0] = s;
+    p.ws[((int64_t)plane * nb + b) * 2 + 1] = c;
+  }
+}
+
+__global__ void ssim_finalize_kernel(const float* __restrict__ ws, float* __restrict__ ssim_sum,
+                                     float* __restrict__ cs_sum, int planes, int nb) {
+  const int pl = blockIdx.x * blockDim.x + threadIdx.x;
+  if (pl >= planes) return;
+  float s = 0.f, c = 0.f;
+  for (int b = 0; b < nb; ++b) { s += ws[((int64_t)pl * nb + b) * 2]; c += ws[((int64_t)pl * nb + b) * 2 + 1]; }
+  ssim_sum[pl] = s; cs_sum[pl] = c;
+}
+
+// F.avg_pool2d(x, kernel_size=2, stride=2, padding=(ph, pw)), count_include_pad=True
+__global__ void avgpool2_kernel(const float* __restrict__ x, float* __restrict__ y, int planes, int h, int w, int oh,
+                                int ow, int ph, int pw) {
+  const int64_t total = (int64_t)planes * oh * ow;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int ox = (int)(i % ow), oy = (int)((i / ow) % oh);
+    const int64_t pl = i / ((int64_t)ow * oh);
+    const float* src = x + pl * h * w;
+    float s = 0.f;
+#pragma unroll
+    for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+      for (int dx = 0; dx < 2; ++dx) {
+        const int yy = 2 * oy - ph + dy, xx = 2 * ox - pw + dx;
+        if (yy >= 0 && yy < h && xx >= 0 && xx < w) s += __ldg(src + (int64_t)yy * w + xx);
+      }
+    y[i] = 0.25f * s;
+  }
+}
+
+}  // namespace icadv
+
+using namespace icadv;
+
+extern "C" {
+
+int icadv_ssim_workspace_floats(int planes, int h, int w, int win, int same_pad) {
+  const int oh = same_pad ? h : h - win + 1, ow = same_pad ? w : w - win + 1;
+  if (oh <= 0 || ow <= 0) return 0;
+  return planes * ((oh + kT - 1) / kT) * ((ow + kT - 1) / kT) * 2;
+}
+
+int icadv_ssim_level(const float* X, const float* Y, float* ws, float* ssim_sum, float* cs_sum, int planes, int h,
+                     int w, const float* win_taps_host, int win, int same_pad, float c1, float c2,
+                     icadv_stream_t stream) {
+  ICADV_REQUIRE(X && Y && ws && ssim_sum && cs_sum && win_taps_host, "null pointer");
+  ICADV_REQUIRE(win >= 1 && win <= kMaxWin && (win % 2 == 1 || !same_pad), "window must be odd and <= 11");
+  SsimParams p;
+  p.X = X; p.Y = Y; p.ws = ws; p.h = h; p.w = w; p.win = win; p.pad = same_pad ? win / 2 : 0;
+  p.out_h = same_pad ? h : h - win + 1; p.out_w = same_pad ? w : w - win + 1;
+  ICADV_REQUIRE(p.out_h > 0 && p.out_w > 0, "image smaller than the window");
+  p.tiles_x = (p.out_w + kT - 1) / kT; p.tiles_y = (p.out_h + kT - 1) / kT;
+  ICADV_REQUIRE(planes <= 65535 && p.tiles_y <= 65535, "grid too large");
+  p.c1 = c1; p.c2 = c2;
+  for (int k = 0; k < kMaxWin; ++k) p.taps[k] = k < win ? win_taps_host[k] : 0.f;
+  dim3 grid(p.tiles_x, p.tiles_y, planes);
+  ssim_level_kernel<<<grid, 256, 0, as_stream(stream)>>>(p);
+  ICADV_CUDA_TRY(cudaGetLastError());
+  ssim_finalize_kernel<<<(planes + 127) / 128, 128, 0, as_stream(stream)>>>(ws, ssim_sum, cs_sum, planes,
+                                                                            p.tiles_x * p.tiles_y);
+  ICADV_CUDA_TRY(cudaGetLastError());
+  return ICADV_OK;
+}
+
+int icadv_avgpool2(const float* x, float* y, int planes, int h, int w, int pad_h, int pad_w, icadv_stream_t stream) {
+  ICADV_REQUIRE(x && y && planes > 0 && h > 0 && w > 0, "bad avgpool2 args");
+  const int oh = (h + 2 * pad_h - 2) / 2 + 1, ow = (w + 2 * pad_w - 2) / 2 + 1;
+  const int64_t total = (int64_t)planes * oh * ow;
+  int64_t blocks = (total + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  avgpool2_kernel<<<(int)blocks, 256, 0, as_stream(stream)>>>(x, y, planes, h, w, oh, ow, pad_h, pad_w);
+  ICADV_CUDA_TRY(cudaGetLastError());
+  return ICADV_OK;
+}
+
+}  // extern "C"

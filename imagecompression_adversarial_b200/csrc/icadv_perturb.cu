@@ -103,10 +103,13 @@ __device__ __forceinline__ float clamp_chain_grad(float g, float s, float z, flo
   return g;
 }
 
-__device__ __forceinline__ float adam_step(float& z, float& m, float& v, float g, float b1, float b2, float step_size,
-                                           float bc2_sqrt, float adam_eps) {
-  m = m + (g - m) * (1.f - b1);                 // exp_avg.lerp_(grad, 1 - beta1)
-  v = v * b2 + (1.f - b2) * g * g;              // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, 1 - beta2)
+struct AdamCoef { float omb1, b2, omb2, eps; };  // (1-beta1), beta2, (1-beta2) rounded from double like torch does
+
+__device__ __forceinline__ float adam_step(float& z, float& m, float& v, float g, const AdamCoef c, float step_size,
+                                           float bc2_sqrt) {
+  const float adam_eps = c.eps;
+  m = m + (g - m) * c.omb1;                     // exp_avg.lerp_(grad, 1 - beta1)
+  v = v * c.b2 + c.omb2 * g * g;                // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, 1 - beta2)
   const float denom = sqrtf(v) / bc2_sqrt + adam_eps;
   z = z - step_size * (m / denom);              // param.addcdiv_(exp_avg, denom, value=-step_size)
   return z;
@@ -115,9 +118,8 @@ __device__ __forceinline__ float adam_step(float& z, float& m, float& v, float g
 __global__ void __launch_bounds__(256) perturb_update_adam_kernel(const float4* __restrict__ im_s, float4* noise,
                                                                   const float4* __restrict__ g_in, float4* m4,
                                                                   float4* v4, icadv_perturb_state st,
-                                                                  int64_t per_img4, float eps, float b1, float b2,
-                                                                  float adam_eps, float gradA_scale,
-                                                                  float gradB_scale) {
+                                                                  int64_t per_img4, float eps, AdamCoef coef,
+                                                                  float gradA_scale, float gradB_scale) {
   const int n = blockIdx.y;
   const int64_t base = (int64_t)n * per_img4;
   const int br = st.branch[n];
@@ -140,10 +142,10 @@ __global__ void __launch_bounds__(256) perturb_update_adam_kernel(const float4* 
     g.y = clamp_chain_grad(g.y, s.y, z.y, eps);
     g.z = clamp_chain_grad(g.z, s.z, z.z, eps);
     g.w = clamp_chain_grad(g.w, s.w, z.w, eps);
-    adam_step(z.x, m.x, v.x, g.x, b1, b2, step_size, bc2_sqrt, adam_eps);
-    adam_step(z.y, m.y, v.y, g.y, b1, b2, step_size, bc2_sqrt, adam_eps);
-    adam_step(z.z, m.z, v.z, g.z, b1, b2, step_size, bc2_sqrt, adam_eps);
-    adam_step(z.w, m.w, v.w, g.w, b1, b2, step_size, bc2_sqrt, adam_eps);
+    adam_step(z.x, m.x, v.x, g.x, coef, step_size, bc2_sqrt);
+    adam_step(z.y, m.y, v.y, g.y, coef, step_size, bc2_sqrt);
+    adam_step(z.z, m.z, v.z, g.z, coef, step_size, bc2_sqrt);
+    adam_step(z.w, m.w, v.w, g.w, coef, step_size, bc2_sqrt);
     noise[base + i] = z; m4[base + i] = m; v4[base + i] = v;
   }
 }
@@ -268,16 +270,18 @@ int icadv_perturb_forward(const float* im_s, const float* noise, float* im_in, f
 }
 
 int icadv_perturb_update_adam(const float* im_s, float* noise, const float* g_in, float* m, float* v,
-                              const icadv_perturb_state* st, int n_img, int64_t per_img, float eps, float beta1,
-                              float beta2, float adam_eps, float gradA_scale, float gradB_scale,
+                              const icadv_perturb_state* st, int n_img, int64_t per_img, float eps, double beta1,
+                              double beta2, double adam_eps, float gradA_scale, float gradB_scale,
                               icadv_stream_t stream) {
   ICADV_REQUIRE(im_s && noise && m && v && st, "null pointer");
   ICADV_REQUIRE(per_img % 4 == 0, "per_img must be a multiple of 4");
   dim3 grid(kRedBlocks, n_img);
+  AdamCoef coef;
+  coef.omb1 = (float)(1.0 - beta1); coef.b2 = (float)beta2; coef.omb2 = (float)(1.0 - beta2); coef.eps = (float)adam_eps;
   perturb_update_adam_kernel<<<grid, 256, 0, as_stream(stream)>>>(
       reinterpret_cast<const float4*>(im_s), reinterpret_cast<float4*>(noise),
       reinterpret_cast<const float4*>(g_in), reinterpret_cast<float4*>(m), reinterpret_cast<float4*>(v), *st,
-      per_img / 4, eps, beta1, beta2, adam_eps, gradA_scale, gradB_scale);
+      per_img / 4, eps, coef, gradA_scale, gradB_scale);
   ICADV_CUDA_TRY(cudaGetLastError());
   return ICADV_OK;
 }

@@ -1,0 +1,134 @@
+"""Device-resident attack loop: the body of ``attack_`` (attack_rd.py:506-560) for a batch of images with
+PER-IMAGE semantics (every image behaves like its own N=1 call of the reference), no host sync.
+
+Per iteration, all stream-ordered and captured in one CUDA graph:
+  1. perturb_forward    noise -> eps-clamp -> im_in = clamp(im_s + nc, 0, 1); loss_i; branch A/B per image
+                        (attack_rd.py:507,517,333-334); branch-B images are compacted into an active list;
+                        LR schedule (MultiStepLR, attack_rd.py:503,553-554) and Adam coefficients on device
+  2. g_a forward, g_s forward   (attack_rd.py:344,349) over the active images only
+  3. output_loss        clamp + 1 - MSE(output_s, output_) + gradient seed  (attack_rd.py:353-364)
+  4. g_s backward, g_a backward to the input  (attack_rd.py:547, input gradient only)
+  5. perturb_update     clamp backward rule + Adam on the perturbation  (attack_rd.py:546-548)
+"""
+import torch
+
+from . import _lib as L
+from . import ops
+from .program import StackProgram, parse_stack
+
+
+class AttackEngine:
+    def __init__(self, net, n_img, height, width, *, steps, epsilon=16.0, noise_budget=1e-4, lr_attack=0.01,
+                 clamp=True, att_metric="L2", force_branch=-1, use_graph=True, device=None):
+        ops.require_device()
+        if att_metric != "L2":
+            raise L.IcadvError("AttackEngine: only -att_metric L2 is on the fused path so far")
+        if steps < 3:
+            raise ZeroDivisionError("integer division or modulo by zero")  # attack_rd.py:553 with steps//3 == 0
+        dev = device or next(net.parameters()).device
+        self.net, self.n_img, self.H, self.W, self.device = net, n_img, height, width, dev
+        self.steps, self.eps, self.budget, self.lr0 = steps, epsilon / 255.0, noise_budget, lr_attack
+        self.clamp, self.force_branch, self.use_graph = clamp, force_branch, use_graph
+        f = lambda *s: torch.zeros(*s, device=dev, dtype=torch.float32)
+        shape = (n_img, height, width, 3)
+        self.per_img = 3 * height * width
+        self.im_s, self.output_s = f(*shape), f(*shape)
+        self.noise, self.m, self.v, self.im_in = f(*shape), f(*shape), f(*shape), f(*shape)
+        self.st = ops.PerturbState(n_img, dev)
+        self.loss_o_sum = f(n_img)
+        self.ws_out = f(n_img * L.RED_BLOCKS)
+        act, nact = self.st.active, self.st.n_active
+        ga_units, gs_units = parse_stack(net.g_a), parse_stack(net.g_s)
+        lat_h, lat_w = height, width
+        for u in ga_units:
+            lat_h, lat_w = ops.out_hw(u.fwd_form, u.k, u.s, lat_h, lat_w)
+        # gradient wrt the latent: written by g_s.backward, seed of g_a.backward (one shared buffer)
+        self.g_lat = f(n_img, lat_h, lat_w, ga_units[-1].cout)
+        self.ga = StackProgram(ga_units, n_img, height, width, dev, x_in=self.im_in, g_out=self.g_lat, active=act,
+                               n_active=nact)
+        self.gs = StackProgram(gs_units, n_img, lat_h, lat_w, dev, x_in=self.ga.out, g_in=self.g_lat, active=act,
+                               n_active=nact)
+        self.x_out, self.g_x = self.gs.out, self.gs.g_out
+        assert self.x_out.shape == self.im_s.shape, (self.x_out.shape, self.im_s.shape)
+        self._graph = None
+        self.iterations_done = 0
+
+    # ------------------------------------------------------------------ state
+    def load(self, im_s_nchw, output_s_nchw, noise_init_nchw=None):
+        """Start a new attack on a batch: copies inputs in, zeroes the perturbation and Adam state."""
+        self.im_s.copy_(im_s_nchw.permute(0, 2, 3, 1))
+        self.output_s.copy_(output_s_nchw.permute(0, 2, 3, 1))
+        if noise_init_nchw is None:
+            self.noise.zero_()
+        else:
+            self.noise.copy_(noise_init_nchw.permute(0, 2, 3, 1))
+        self.m.zero_()
+        self.v.zero_()
+        self.st.step.zero_()
+        self.iterations_done = 0
+
+    def refresh_parameters(self):
+        self.ga.refresh_parameters()
+        self.gs.refresh_parameters()
+
+    # ------------------------------------------------------------------ one iteration
+    def _iteration(self):
+        ops.perturb_forward(self.im_s, self.noise, self.im_in, self.st, eps=self.eps, budget=self.budget,
+                            force_branch=self.force_branch, lr0=self.lr0, lr_gamma=0.33,
+                            sched_period=self.steps // 3)
+        self.ga.forward()
+        self.gs.forward()
+        ops.output_loss(self.x_out, self.output_s, self.g_x, self.ws_out, self.loss_o_sum, do_clamp=self.clamp,
+                        grad_scale=1.0 / self.per_img, active=self.st.active, n_active=self.st.n_active)
+        self.gs.backward()
+        self.ga.backward()
+        ops.perturb_update_adam(self.im_s, self.noise, self.ga.g_in, self.m, self.v, self.st, eps=self.eps,
+                                gradA_scale=1.0 / self.per_img, gradB_scale=1.0)
+
+    def kernels_per_iteration(self):
+        fa, ba = self.ga.n_kernels()
+        fs, bs = self.gs.n_kernels()
+        return 2 + fa + fs + 2 + bs + ba + 1  # perturb fwd (2) + stacks + output_loss (2) + update (1)
+
+    def run(self, iterations, record=None):
+        """Run ``iterations`` loop iterations.  ``record`` (list) receives per-iteration
+        (branch[n], loss_i[n], loss_o[n]) tensors on the host -- this syncs and is for tests only."""
+        for _ in range(iterations):
+            if self.use_graph and record is None:
+                if self._graph is None:
+                    self._capture()
+                self._graph.replay()
+            else:
+                self._iteration()
+            if record is not None:
+                loss_o = 1.0 - self.loss_o_sum / self.per_img
+                record.append((self.st.branch.cpu().clone(), self.st.loss_i.cpu().clone(), loss_o.cpu().clone()))
+            self.iterations_done += 1
+
+    def _capture(self):
+        # warm-up outside capture (lazy one-time initialisation inside the library), on a side stream
+        state = [t.clone() for t in (self.noise, self.m, self.v, self.st.step)]
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            self._iteration()
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        for t, c in zip((self.noise, self.m, self.v, self.st.step), state):
+            t.copy_(c)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self._iteration()
+        for t, c in zip((self.noise, self.m, self.v, self.st.step), state):
+            t.copy_(c)
+        self._graph = g
+
+    # ------------------------------------------------------------------ results
+    def im_in_nchw(self):
+        """Current adversarial input (after the last perturb_forward) as NCHW."""
+        return self.im_in.permute(0, 3, 1, 2)
+
+    def finalize(self):
+        """Recompute im_in from the final perturbation?  No: the reference evaluates the im_in of the LAST
+        iteration (attack_rd.py:561,573), i.e. before the last optimizer step.  Returns that tensor."""
+        return self.im_in_nchw()

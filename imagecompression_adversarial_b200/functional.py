@@ -1,0 +1,145 @@
+"""Autograd-aware operators at the reference's operator surface (NCHW tensors in, NCHW out).
+
+Every op here is a ``torch.autograd.Function`` whose forward and backward call the C ABI
+(``ops.py``); tensors are kept ``channels_last`` so the NCHW <-> channels-last hop is a view.
+Mirrors: nn.Conv2d / nn.ConvTranspose2d (anchors/utils.py:112-130), compressai GDN
+(utils/ops.py:58-97), ops.Low_bound / ops.Up_bound (utils/ops.py:28-56).
+"""
+import torch
+
+from . import _lib as L
+from . import ops
+
+_PACK_CACHE = {}
+
+
+def to_nhwc(x):
+    """NCHW (any memory format) -> contiguous [N,H,W,C] view/copy."""
+    return x.contiguous(memory_format=torch.channels_last).permute(0, 2, 3, 1)
+
+
+def to_nchw(x_nhwc):
+    """[N,H,W,C] contiguous -> NCHW-shaped channels_last view (no copy)."""
+    return x_nhwc.permute(0, 3, 1, 2)
+
+
+def packed(weight, kind):
+    """Packed copy of a layer weight, cached on (storage, version) so it is rebuilt only after an update."""
+    key = (weight.data_ptr(), kind)
+    hit = _PACK_CACHE.get(key)
+    if hit is not None and hit[0] == weight._version and hit[2] == tuple(weight.shape):
+        return hit[1]
+    wp = ops.pack_weight(weight, kind)
+    _PACK_CACHE[key] = (weight._version, wp, tuple(weight.shape))
+    return wp
+
+
+class Contraction(torch.autograd.Function):
+    """Conv2d (transposed=False) or ConvTranspose2d (transposed=True), padding k//2, output_padding s-1."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, ksize, stride, transposed, act, param_grads):
+        xn = to_nhwc(x)
+        kind = L.PACK_CONVT_FWD if transposed else L.PACK_CONV_FWD
+        form = L.FORM_TCONV if transposed else L.FORM_SCONV
+        n_ch = weight.shape[1] if transposed else weight.shape[0]
+        out = ops.conv(xn, packed(weight, kind), bias.detach() if bias is not None else None, form=form, ksize=ksize,
+                       stride=stride, n_ch=n_ch, act=act)
+        ctx.save_for_backward(xn, weight, out if act != L.ACT_NONE else None)
+        ctx.cfg = (ksize, stride, transposed, act, param_grads, bias is not None)
+        return to_nchw(out)
+
+    @staticmethod
+    def backward(ctx, g):
+        xn, weight, out = ctx.saved_tensors
+        ksize, stride, transposed, act, param_grads, has_bias = ctx.cfg
+        gn = to_nhwc(g)
+        if act != L.ACT_NONE:
+            gn = ops.act_backward(out, gn, act)
+        gx = gw = gb = None
+        if ctx.needs_input_grad[0]:
+            kind = L.PACK_CONVT_DGRAD if transposed else L.PACK_CONV_DGRAD
+            form = L.FORM_SCONV if transposed else L.FORM_TCONV
+            gx = to_nchw(ops.conv(gn, packed(weight, kind), None, form=form, ksize=ksize, stride=stride,
+                                  n_ch=xn.shape[-1]))
+        if param_grads and (ctx.needs_input_grad[1] or (has_bias and ctx.needs_input_grad[2])):
+            form = L.FORM_TCONV if transposed else L.FORM_SCONV
+            n_ch = weight.shape[1] if transposed else weight.shape[0]
+            dwp, db = ops.conv_wgrad(xn, gn.contiguous(), form=form, ksize=ksize, stride=stride, n_ch=n_ch,
+                                     want_bias=has_bias)
+            gw = ops.unpack_weight_grad(dwp, weight, L.PACK_CONVT_FWD if transposed else L.PACK_CONV_FWD)
+            gb = db
+        return gx, gw, gb, None, None, None, None, None
+
+
+class GdnFn(torch.autograd.Function):
+    """y = x * (beta + gamma x^2)^(-1/2)  (inverse: ^(+1/2)); beta/gamma already reparametrised."""
+
+    @staticmethod
+    def forward(ctx, x, beta_eff, gamma_eff, inverse):
+        xn = to_nhwc(x)
+        C = xn.shape[-1]
+        y, sc = ops.conv(xn, None, None, form=L.FORM_SCONV, ksize=1, stride=1, n_ch=C,
+                         epi=L.EPI_IGDN_FWD if inverse else L.EPI_GDN_FWD, gmat=gamma_eff.contiguous(),
+                         beta=beta_eff.contiguous(), acc_from_in=True, path="tc")
+        ctx.save_for_backward(y, sc, gamma_eff)
+        ctx.inverse = inverse
+        return to_nchw(y)
+
+    @staticmethod
+    def backward(ctx, g):
+        y, sc, gamma_eff = ctx.saved_tensors
+        C = y.shape[-1]
+        gx = ops.conv(to_nhwc(g), None, None, form=L.FORM_SCONV, ksize=1, stride=1, n_ch=C,
+                      epi=L.EPI_IGDN_BWD if ctx.inverse else L.EPI_GDN_BWD, gmat=gamma_eff.t().contiguous(),
+                      y_prev=y, sc_prev=sc, acc_from_in=True, path="tc")
+        return to_nchw(gx), None, None, None
+
+
+class BoundFn(torch.autograd.Function):
+    """ops.Low_bound / ops.Up_bound (utils/ops.py:28-56): clamp forward, pass-through-if backward."""
+
+    @staticmethod
+    def forward(ctx, x, bound, upper):
+        xc = x.contiguous()
+        ctx.save_for_backward(xc)
+        ctx.cfg = (float(bound), bool(upper))
+        return ops.bound_forward(xc.view(-1), float(bound), upper).view_as(xc)
+
+    @staticmethod
+    def backward(ctx, g):
+        (xc,) = ctx.saved_tensors
+        bound, upper = ctx.cfg
+        return ops.bound_backward(xc.view(-1), g.contiguous().view(-1), bound, upper).view_as(xc), None, None
+
+
+class Low_bound:
+    """Drop-in for ``ops.Low_bound`` (``.apply(x, b)``)."""
+
+    @staticmethod
+    def apply(x, lower_bound=1e-6):
+        return BoundFn.apply(x, lower_bound, False)
+
+
+class Up_bound:
+    """Drop-in for ``ops.Up_bound`` (``.apply(x, b)``)."""
+
+    @staticmethod
+    def apply(x, up_bound=1.0):
+        return BoundFn.apply(x, up_bound, True)
+
+
+class ActFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, act):
+        xc = x.contiguous(memory_format=torch.channels_last) if x.dim() == 4 else x.contiguous()
+        y = ops.unary(xc, {L.ACT_ABS: 0, L.ACT_RELU: 1, L.ACT_LEAKY: 2}[act])
+        ctx.save_for_backward(xc)
+        ctx.act = act
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        (xc,) = ctx.saved_tensors
+        gc = g.contiguous(memory_format=torch.channels_last) if g.dim() == 4 else g.contiguous()
+        return ops.act_backward(xc, gc, ctx.act), None

@@ -1,0 +1,98 @@
+"""MS-SSIM at the reference's call surface, on the fused level kernel (csrc/icadv_msssim.cu).
+
+``ms_ssim`` / ``MS_SSIM`` mirror ``pytorch_msssim`` (attack_rd.py:19; train.py:18,44) -- variant 1;
+``MS_SSIM_v2`` mirrors ``utils/torch_msssim.MS_SSIM`` (utils/torch_msssim.py:18-76) -- variant 2.
+Forward only for now (final metrics run under no_grad: self_ensemble.py:172).
+"""
+import ctypes as C
+import math
+
+import torch
+
+from . import _lib as L
+from .ops import _p, _stream
+
+WEIGHTS = (0.0448, 0.2856, 0.3001, 0.2363, 0.1333)
+
+
+def _taps(size, sigma):
+    g = [math.exp(-((i - size // 2) ** 2) / (2.0 * sigma * sigma)) for i in range(size)]
+    s = sum(g)
+    return [v / s for v in g]
+
+
+def _level(X, Y, taps, same_pad, c1, c2):
+    planes, h, w = X.shape[0] * X.shape[1], X.shape[2], X.shape[3]
+    n = L.lib().icadv_ssim_workspace_floats(planes, h, w, len(taps), 1 if same_pad else 0)
+    ws = torch.empty(max(n, 1), device=X.device, dtype=torch.float32)
+    ss = torch.empty(planes, device=X.device, dtype=torch.float32)
+    cs = torch.empty(planes, device=X.device, dtype=torch.float32)
+    arr = (C.c_float * len(taps))(*taps)
+    L.call("icadv_ssim_level", _p(X), _p(Y), _p(ws), _p(ss), _p(cs), planes, h, w, arr, len(taps),
+           1 if same_pad else 0, float(c1), float(c2), _stream())
+    oh, ow = (h, w) if same_pad else (h - len(taps) + 1, w - len(taps) + 1)
+    return ss.view(X.shape[0], X.shape[1]) / (oh * ow), cs.view(X.shape[0], X.shape[1]) / (oh * ow)
+
+
+def _pool(X, ph, pw):
+    n, c, h, w = X.shape
+    oh, ow = (h + 2 * ph - 2) // 2 + 1, (w + 2 * pw - 2) // 2 + 1
+    out = torch.empty(n, c, oh, ow, device=X.device, dtype=torch.float32)
+    L.call("icadv_avgpool2", _p(X), _p(out), n * c, h, w, ph, pw, _stream())
+    return out
+
+
+def ms_ssim(X, Y, data_range=1.0, size_average=True, win_size=11, win_sigma=1.5, weights=WEIGHTS, K=(0.01, 0.03)):
+    """pytorch_msssim.ms_ssim (variant 1)."""
+    if X.shape != Y.shape or X.dim() != 4:
+        raise ValueError("Input images should be 4-d tensors of the same shape")
+    assert min(X.shape[-2:]) > (win_size - 1) * 2 ** 4, \
+        "Image size should be larger than %d due to the 4 downsamplings in ms-ssim" % ((win_size - 1) * 2 ** 4)
+    X, Y = X.detach().contiguous().float(), Y.detach().contiguous().float()
+    taps = _taps(win_size, win_sigma)
+    c1, c2 = (K[0] * data_range) ** 2, (K[1] * data_range) ** 2
+    vals = []
+    for lvl in range(len(weights)):
+        ss, cs = _level(X, Y, taps, False, c1, c2)
+        if lvl < len(weights) - 1:
+            vals.append(torch.relu(cs))
+            ph, pw = X.shape[2] % 2, X.shape[3] % 2
+            X, Y = _pool(X, ph, pw), _pool(Y, ph, pw)
+    vals.append(torch.relu(ss))
+    w = torch.tensor(weights, device=X.device, dtype=torch.float32).view(-1, 1, 1)
+    val = torch.prod(torch.stack(vals, 0) ** w, dim=0)
+    return val.mean() if size_average else val.mean(1)
+
+
+class MS_SSIM(torch.nn.Module):
+    """pytorch_msssim.MS_SSIM(data_range=1, size_average=True, channel=3)."""
+
+    def __init__(self, data_range=1.0, size_average=True, channel=3, win_size=11, win_sigma=1.5):
+        super().__init__()
+        self.kw = dict(data_range=data_range, size_average=size_average, win_size=win_size, win_sigma=win_sigma)
+
+    def forward(self, X, Y):
+        return ms_ssim(X, Y, **self.kw)
+
+
+class MS_SSIM_v2(torch.nn.Module):
+    """utils/torch_msssim.MS_SSIM(size_average=True, max_val=255)."""
+
+    def __init__(self, size_average=True, max_val=255, device_id=0):
+        super().__init__()
+        self.max_val = max_val
+
+    def forward(self, img1, img2, levels=5):
+        X, Y = img1.detach().contiguous().float(), img2.detach().contiguous().float()
+        c1, c2 = (0.01 * self.max_val) ** 2, (0.03 * self.max_val) ** 2
+        ms, mcs = [], []
+        for _ in range(levels):
+            wsz = min(X.shape[2], X.shape[3], 11)
+            taps = _taps(wsz, 1.5 * wsz / 11)
+            ss, cs = _level(X, Y, taps, True, c1, c2)
+            ms.append(ss.mean())   # global mean over N, C, H, W (planes have equal size)
+            mcs.append(cs.mean())
+            X, Y = _pool(X, 0, 0), _pool(Y, 0, 0)
+        w = torch.tensor(WEIGHTS, device=X.device, dtype=torch.float32)
+        mcs_t, ms_t = torch.stack(mcs), torch.stack(ms)
+        return torch.prod(mcs_t[:levels - 1] ** w[:levels - 1]) * (ms_t[levels - 1] ** w[levels - 1])

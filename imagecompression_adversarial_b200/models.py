@@ -1,0 +1,364 @@
+"""The reference's operator surface on the sm_100a kernels.
+
+``init_model(MODEL, quality, metric, pretrained)`` (anchors/model.py:60-78) returns an ``nn.Module`` with
+``forward(x) -> {"x_hat", "likelihoods": {"y"[, "z"]}}`` and the attributes the reference's host code
+touches: ``g_a``, ``g_s`` (iterable, Sequential-like: anchors/utils.py:136,141), ``h_a``, ``h_s``,
+``entropy_bottleneck``, ``gaussian_conditional`` (+ ``.quantize``), ``context_prediction``,
+``entropy_parameters``, ``aux_loss()``; parameter names follow CompressAI so ``state_dict`` round-trips
+(train.py:244-247) and only ``*.quantiles`` are auxiliary parameters (coder.py:57-67).
+
+All tensors are fp32 CUDA; activations are kept ``channels_last``.  No module here has a CPU path.
+"""
+import math
+
+import torch
+import torch.nn as nn
+
+from . import _lib as L
+from . import functional as Fn
+from . import ops
+from .program import StackProgram, parse_stack
+
+# compressai.zoo.image.cfgs
+ZOO = {
+    "factorized": {q: (128, 192) if q <= 5 else (192, 320) for q in range(1, 9)},
+    "hyper": {q: (128, 192) if q <= 5 else (192, 320) for q in range(1, 9)},
+    "context": {q: (192, 192) if q <= 4 else (192, 320) for q in range(1, 9)},
+    "cheng2020": {q: (128,) if q <= 3 else (192,) for q in range(1, 7)},
+}
+
+
+class _ContractionModule(nn.Module):
+    transposed = False
+
+    def __init__(self, in_channels, out_channels, kernel_size=5, stride=2):
+        super().__init__()
+        self.in_channels, self.out_channels = in_channels, out_channels
+        self.ksize, self.stride = kernel_size, stride
+        shape = ((in_channels, out_channels) if self.transposed else (out_channels, in_channels)) + (kernel_size,) * 2
+        w = torch.empty(*shape)
+        nn.init.kaiming_normal_(w)  # CompressAI 1.1.x CompressionModel._initialize_weights
+        self.weight = nn.Parameter(w)
+        self.bias = nn.Parameter(torch.zeros(out_channels))
+        self.param_grads = True  # the attack turns weight gradients off (they are never read there)
+
+    def forward(self, x):
+        return Fn.Contraction.apply(x, self.weight, self.bias, self.ksize, self.stride, self.transposed, L.ACT_NONE,
+                                    self.param_grads)
+
+    def extra_repr(self):
+        return f"{self.in_channels}, {self.out_channels}, kernel_size={self.ksize}, stride={self.stride}"
+
+
+class Conv2d(_ContractionModule):
+    """nn.Conv2d(i, o, k, stride=s, padding=k//2)  (anchors/utils.py:112-119)."""
+    transposed = False
+
+
+class ConvTranspose2d(_ContractionModule):
+    """nn.ConvTranspose2d(i, o, k, stride=s, output_padding=s-1, padding=k//2)  (anchors/utils.py:122-130)."""
+    transposed = True
+
+
+def conv(cin, cout, kernel_size=5, stride=2):
+    return Conv2d(cin, cout, kernel_size, stride)
+
+
+def deconv(cin, cout, kernel_size=5, stride=2):
+    return ConvTranspose2d(cin, cout, kernel_size, stride)
+
+
+class NonNegativeParametrizer(nn.Module):
+    """compressai.ops.NonNegativeParametrizer; exposes ``bound``/``pedestal`` (attack_rd.py:294-295 calls it)."""
+
+    def __init__(self, minimum=0.0, reparam_offset=2 ** -18):
+        super().__init__()
+        self.pedestal = float(reparam_offset) ** 2
+        self.bound = (float(minimum) + self.pedestal) ** 0.5
+
+    def init(self, x):
+        return torch.sqrt(torch.clamp(x + self.pedestal, min=self.pedestal))
+
+    def forward(self, x):
+        return ops.gdn_reparam(x, self.bound, self.pedestal)
+
+
+class GDN(nn.Module):
+    """compressai.layers.GDN (utils/ops.py:58-97): y = x * (beta + gamma x^2)^(-+1/2)."""
+
+    def __init__(self, C, inverse=False, beta_min=1e-6, gamma_init=0.1):
+        super().__init__()
+        self.inverse = bool(inverse)
+        self.beta_reparam = NonNegativeParametrizer(minimum=beta_min)
+        self.gamma_reparam = NonNegativeParametrizer()
+        self.beta = nn.Parameter(self.beta_reparam.init(torch.ones(C)))
+        self.gamma = nn.Parameter(self.gamma_reparam.init(gamma_init * torch.eye(C)))
+
+    def effective_parameters(self):
+        """(beta_eff [C], gamma_eff [C,C], gamma_eff^T) after the non-negative reparametrisation."""
+        be = ops.gdn_reparam(self.beta, self.beta_reparam.bound, self.beta_reparam.pedestal)
+        ga = ops.gdn_reparam(self.gamma, self.gamma_reparam.bound, self.gamma_reparam.pedestal)
+        gaT = ops.gdn_reparam(self.gamma, self.gamma_reparam.bound, self.gamma_reparam.pedestal, transpose=True)
+        return be, ga, gaT
+
+    def forward(self, x):
+        be, ga, _ = self.effective_parameters()
+        return Fn.GdnFn.apply(x, be, ga, self.inverse)
+
+
+class Activation(nn.Module):
+    def __init__(self, act, inplace=True):
+        super().__init__()
+        self.act = act
+
+    def forward(self, x):
+        return Fn.ActFn.apply(x, self.act)
+
+
+def ReLU(inplace=True):
+    return Activation(L.ACT_RELU)
+
+
+def LeakyReLU(inplace=True):
+    return Activation(L.ACT_LEAKY)
+
+
+class _StackFn(torch.autograd.Function):
+    """Whole g_a / g_s stack as ONE autograd node running a fused StackProgram."""
+
+    @staticmethod
+    def forward(ctx, x, stack):
+        xn = Fn.to_nhwc(x).contiguous()
+        n, h, w, _ = xn.shape
+        need_grad = x.requires_grad
+        prog = StackProgram(parse_stack(stack), n, h, w, x.device, x_in=xn, need_grad=need_grad)
+        out = prog.forward()
+        ctx.prog = prog if need_grad else None
+        return Fn.to_nchw(out)
+
+    @staticmethod
+    def backward(ctx, g):
+        prog = ctx.prog
+        prog.g_out.copy_(Fn.to_nhwc(g))
+        return Fn.to_nchw(prog.backward()), None
+
+
+class CodecStack(nn.Sequential):
+    """``nn.Sequential`` of Conv2d/ConvTranspose2d/GDN whose forward runs the fused launch program.
+
+    Iterating ``_modules`` still yields the individual layers (anchors/utils.py:136,141).  Parameter
+    gradients are produced only when ``param_grads`` is set (the attack never reads them:
+    attack_rd.py:546-548 steps only the perturbation; train.py:357-358 zeroes them before use).
+    """
+    param_grads = False
+
+    def forward(self, x):
+        if self.param_grads and any(p.requires_grad for p in self.parameters()) and torch.is_grad_enabled():
+            for m in self:   # layer-by-layer autograd path, with weight gradients
+                x = m(x)
+            return x
+        return _StackFn.apply(x, self)
+
+
+# ---------------------------------------------------------------------------------- entropy models
+class LowerBound(nn.Module):
+    def __init__(self, bound):
+        super().__init__()
+        self.bound = float(bound)
+
+    def forward(self, x):
+        return Fn.Low_bound.apply(x, self.bound)
+
+
+class EntropyBottleneck(nn.Module):
+    """compressai EntropyBottleneck, forward on the fused likelihood kernel."""
+
+    def __init__(self, channels, tail_mass=1e-9, init_scale=10.0, filters=(3, 3, 3, 3)):
+        super().__init__()
+        assert tuple(filters) == (3, 3, 3, 3), "kernel is specialised to the 1-3-3-3-3-1 chain"
+        self.channels, self.filters = int(channels), tuple(filters)
+        self.init_scale, self.tail_mass = float(init_scale), float(tail_mass)
+        f = (1,) + self.filters + (1,)
+        scale = self.init_scale ** (1 / (len(self.filters) + 1))
+        C = self.channels
+        for i in range(len(self.filters) + 1):
+            init = math.log(math.expm1(1 / scale / f[i + 1]))
+            self.register_parameter(f"_matrix{i}", nn.Parameter(torch.full((C, f[i + 1], f[i]), init)))
+            self.register_parameter(f"_bias{i}", nn.Parameter(torch.empty(C, f[i + 1], 1).uniform_(-0.5, 0.5)))
+            if i < len(self.filters):
+                self.register_parameter(f"_factor{i}", nn.Parameter(torch.zeros(C, f[i + 1], 1)))
+        self.quantiles = nn.Parameter(torch.tensor([-self.init_scale, 0.0, self.init_scale]).repeat(C, 1, 1))
+        t = math.log(2 / self.tail_mass - 1)
+        self.register_buffer("target", torch.tensor([-t, 0.0, t]))
+        self.likelihood_bound = 1e-9
+        self.noise_override = None  # test hook: U(-.5,.5) sample shared with the oracle (NCHW)
+        self.last_bits = None
+
+    def _table(self):
+        ms = [getattr(self, f"_matrix{i}") for i in range(5)]
+        bs = [getattr(self, f"_bias{i}") for i in range(5)]
+        fs = [getattr(self, f"_factor{i}") for i in range(4)]
+        return ops.eb_prepare(ms, bs, fs, self.channels)
+
+    def loss(self):
+        """Auxiliary loss on the quantiles (parameter-only math, 3*C elements)."""
+        v = self.quantiles
+        for i in range(5):
+            m = getattr(self, f"_matrix{i}").detach()
+            b = getattr(self, f"_bias{i}").detach()
+            v = torch.matmul(torch.nn.functional.softplus(m), v) + b
+            if i < 4:
+                fa = getattr(self, f"_factor{i}").detach()
+                v = v + torch.tanh(fa) * torch.tanh(v)
+        return torch.abs(v - self.target).sum()
+
+    def forward(self, x, training=None):
+        if training is None:
+            training = self.training
+        xn = Fn.to_nhwc(x).contiguous()
+        noise = None
+        if training:
+            noise = (Fn.to_nhwc(self.noise_override).contiguous() if self.noise_override is not None
+                     else torch.empty_like(xn).uniform_(-0.5, 0.5))
+        med = self.quantiles.detach()[:, 0, 1].contiguous()
+        x_hat, lik, bits = ops.eb_forward(xn, self._table(), med, training=training, noise=noise,
+                                          lik_bound=self.likelihood_bound)
+        self.last_bits = bits
+        return Fn.to_nchw(x_hat), Fn.to_nchw(lik)
+
+
+class GaussianConditional(nn.Module):
+    """compressai GaussianConditional (A.4) on the fused erfc likelihood kernel."""
+
+    def __init__(self, scale_table=None, scale_bound=0.11, tail_mass=1e-9):
+        super().__init__()
+        self.scale_bound, self.likelihood_bound = float(scale_bound), 1e-9
+        self.noise_override = None
+        self.last_bits = None
+
+    def quantize(self, inputs, mode, means=None):
+        """compressai ``quantize`` (call site anchors/model.py:102)."""
+        x = inputs.contiguous(memory_format=torch.channels_last)
+        if mode == "noise":
+            nz = (self.noise_override.contiguous(memory_format=torch.channels_last)
+                  if self.noise_override is not None else torch.empty_like(x).uniform_(-0.5, 0.5))
+            return ops.unary(x, 4, nz)
+        if means is not None:
+            m = means.contiguous(memory_format=torch.channels_last)
+            out = ops.unary(ops.unary(x - m, 3), 4, m)
+        else:
+            out = ops.unary(x, 3)
+        if mode == "dequantize":
+            return out
+        assert mode == "symbols", mode
+        return (out - means if means is not None else out).int()
+
+    def forward(self, inputs, scales, means=None, training=None):
+        if training is None:
+            training = self.training
+        y = Fn.to_nhwc(inputs).contiguous()
+        s = Fn.to_nhwc(scales).contiguous()
+        m = Fn.to_nhwc(means).contiguous() if means is not None else None
+        noise = None
+        if training:
+            noise = (Fn.to_nhwc(self.noise_override).contiguous() if self.noise_override is not None
+                     else torch.empty_like(y).uniform_(-0.5, 0.5))
+        y_hat, lik, bits = ops.gc_forward(y, s, m, training=training, noise=noise, scale_bound=self.scale_bound,
+                                          lik_bound=self.likelihood_bound)
+        self.last_bits = bits
+        return Fn.to_nchw(y_hat), Fn.to_nchw(lik)
+
+
+# ---------------------------------------------------------------------------------- codecs
+class CompressionModel(nn.Module):
+    def __init__(self, entropy_bottleneck_channels):
+        super().__init__()
+        self.entropy_bottleneck = EntropyBottleneck(entropy_bottleneck_channels)
+
+    def aux_loss(self):
+        return sum(m.loss() for m in self.modules() if isinstance(m, EntropyBottleneck))
+
+    def to(self, *args, **kwargs):
+        return super().to(*args, **kwargs)
+
+
+def _g_a(N, M):
+    return CodecStack(conv(3, N), GDN(N), conv(N, N), GDN(N), conv(N, N), GDN(N), conv(N, M))
+
+
+def _g_s(N, M):
+    return CodecStack(deconv(M, N), GDN(N, inverse=True), deconv(N, N), GDN(N, inverse=True), deconv(N, N),
+                      GDN(N, inverse=True), deconv(N, 3))
+
+
+class FactorizedPrior(CompressionModel):
+    def __init__(self, N, M):
+        super().__init__(M)
+        self.g_a, self.g_s = _g_a(N, M), _g_s(N, M)
+        self.N, self.M = N, M
+
+    def forward(self, x):
+        y = self.g_a(x)
+        y_hat, y_lik = self.entropy_bottleneck(y)   # anchors/model.py:87-89
+        return {"x_hat": self.g_s(y_hat), "likelihoods": {"y": y_lik}}
+
+
+class ScaleHyperprior(CompressionModel):
+    def __init__(self, N, M):
+        super().__init__(N)
+        self.g_a, self.g_s = _g_a(N, M), _g_s(N, M)
+        self.h_a = nn.Sequential(conv(M, N, 3, 1), ReLU(), conv(N, N), ReLU(), conv(N, N))
+        self.h_s = nn.Sequential(deconv(N, N), ReLU(), deconv(N, N), ReLU(), conv(N, M, 3, 1), ReLU())
+        self.gaussian_conditional = GaussianConditional()
+        self.N, self.M = N, M
+
+    def forward(self, x):
+        y = self.g_a(x)
+        z = self.h_a(Fn.ActFn.apply(y, L.ACT_ABS))  # anchors/model.py:92, anchors/balle.py:38
+        z_hat, z_lik = self.entropy_bottleneck(z)
+        scales_hat = self.h_s(z_hat)
+        y_hat, y_lik = self.gaussian_conditional(y, scales_hat)
+        return {"x_hat": self.g_s(y_hat), "likelihoods": {"y": y_lik, "z": z_lik}}
+
+
+def _build(model, quality):
+    cfg = ZOO[model][quality]
+    if model == "factorized":
+        return FactorizedPrior(*cfg)
+    if model == "hyper":
+        return ScaleHyperprior(*cfg)
+    raise L.IcadvError(f"model family '{model}' is not built yet on the sm_100a path")
+
+
+def _no_zoo(pretrained):
+    if pretrained:
+        raise L.IcadvError("no network in this environment: pass pretrained=False (--new) and load a state_dict")
+
+
+def bmshj2018_factorized(quality, metric="mse", pretrained=False, **kw):
+    _no_zoo(pretrained)
+    return _build("factorized", quality)
+
+
+def bmshj2018_hyperprior(quality, metric="mse", pretrained=False, **kw):
+    _no_zoo(pretrained)
+    return _build("hyper", quality)
+
+
+def mbt2018(quality, metric="mse", pretrained=False, **kw):
+    _no_zoo(pretrained)
+    return _build("context", quality)
+
+
+def cheng2020_anchor(quality, metric="mse", pretrained=False, **kw):
+    _no_zoo(pretrained)
+    return _build("cheng2020", quality)
+
+
+def init_model(MODEL, quality, metric="mse", pretrained=False):
+    """Same dispatch as anchors/model.py:60-78."""
+    table = {"factorized": bmshj2018_factorized, "hyper": bmshj2018_hyperprior, "context": mbt2018,
+             "cheng2020": cheng2020_anchor}
+    if MODEL not in table:
+        raise L.IcadvError(f"unknown model '{MODEL}'")
+    return table[MODEL](quality=quality, metric=metric, pretrained=pretrained)

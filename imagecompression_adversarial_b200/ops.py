@@ -145,6 +145,7 @@ class ConvPlan:
 
     def __init__(self, desc, keep):
         self._keep = keep  # tensors whose pointers are baked into the tensor maps
+        self.kernels = desc.stride * desc.stride if desc.form == L.FORM_TCONV else 1
         h = C.c_void_p()
         L.call("icadv_conv_plan_create", C.byref(desc), C.byref(h))
         self._h = h
@@ -165,6 +166,7 @@ class SimtLaunch:
 
     def __init__(self, desc, keep):
         self._keep, self._d = keep, desc
+        self.kernels = desc.stride * desc.stride if desc.form == L.FORM_TCONV else 1
 
     def launch(self):
         L.call("icadv_conv_simt", C.byref(self._d), _stream())
@@ -242,3 +244,61 @@ def bound_backward(x, gy, bound, upper):
     gx = torch.empty_like(x)
     L.call("icadv_bound_backward", _p(x), _p(gy), _p(gx), x.numel(), float(bound), 1 if upper else 0, _stream())
     return gx
+
+
+# ------------------------------------------------------------------ elementwise helpers
+_UNARY = {L.ACT_ABS: 0, L.ACT_RELU: 1, L.ACT_LEAKY: 2}
+
+
+def unary(x, op, b=None):
+    """op 0 abs, 1 relu, 2 leaky(0.01), 3 round, 4 x + b.  Works on the raw storage order of ``x``."""
+    y = torch.empty_like(x)
+    if b is not None and b.stride() != x.stride():
+        raise L.IcadvError("unary: operands must share a memory layout")
+    L.call("icadv_unary", _p(x), _p(b), _p(y), x.numel(), int(op), _stream())
+    return y
+
+
+def act_backward(x, g, act):
+    if x.stride() != g.stride() or x.shape != g.shape:
+        raise L.IcadvError("act_backward: operands must share shape and memory layout")
+    gx = torch.empty_like(g)
+    L.call("icadv_act_backward", _p(x), _p(g), _p(gx), x.numel(), _UNARY[act], _stream())
+    return gx
+
+
+# ------------------------------------------------------------------ entropy models
+def eb_prepare(matrices, biases, factors, C):
+    """raw EntropyBottleneck parameters -> prepared [58][C] table (softplus / tanh hoisted)."""
+    dev = matrices[0].device
+    table = torch.empty(58, C, device=dev, dtype=torch.float32)
+    keep = [t.detach().contiguous() for t in list(matrices) + list(biases) + list(factors)]
+    arr = lambda ts: (L._fp * len(ts))(*[t.data_ptr() for t in ts])
+    L.call("icadv_eb_prepare", arr(keep[0:5]), arr(keep[5:10]), arr(keep[10:14]), _p(table), C, _stream())
+    return table
+
+
+def eb_forward(x_nhwc, table, medians, *, training, noise=None, lik_bound=1e-9, bits_floor=0.0):
+    """x_nhwc [N,...,C] channels-last.  Returns (x_hat, likelihood, bits[N])."""
+    _chk(x_nhwc, "x")
+    n_img, C = x_nhwc.shape[0], x_nhwc.shape[-1]
+    per_img = x_nhwc[0].numel()
+    x_hat, lik = torch.empty_like(x_nhwc), torch.empty_like(x_nhwc)
+    ws = torch.empty(n_img * L.RED_BLOCKS, device=x_nhwc.device, dtype=torch.float32)
+    bits = torch.empty(n_img, device=x_nhwc.device, dtype=torch.float32)
+    L.call("icadv_eb_forward", _p(x_nhwc), _p(noise), _p(table), _p(medians), _p(x_hat), _p(lik), _p(ws), _p(bits),
+           n_img, per_img, C, 1 if training else 0, float(lik_bound), float(bits_floor), _stream())
+    return x_hat, lik, bits
+
+
+def gc_forward(y, scales, means=None, *, training, noise=None, scale_bound=0.11, lik_bound=1e-9, bits_floor=0.0):
+    """Elementwise over identically laid-out tensors.  Returns (y_hat, likelihood, bits[N])."""
+    for t, nm in ((y, "y"), (scales, "scales"), (means, "means"), (noise, "noise")):
+        _chk(t, nm)
+    n_img, per_img = y.shape[0], y[0].numel()
+    y_hat, lik = torch.empty_like(y), torch.empty_like(y)
+    ws = torch.empty(n_img * L.RED_BLOCKS, device=y.device, dtype=torch.float32)
+    bits = torch.empty(n_img, device=y.device, dtype=torch.float32)
+    L.call("icadv_gc_forward", _p(y), _p(scales), _p(means), _p(noise), _p(y_hat), _p(lik), _p(ws), _p(bits), n_img,
+           per_img, 1 if training else 0, float(scale_bound), float(lik_bound), float(bits_floor), _stream())
+    return y_hat, lik, bits

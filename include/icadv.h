@@ -157,7 +157,7 @@ int icadv_perturb_forward(const float* im_s, const float* noise, float* im_in, f
  * dLoss/d im_in from the network backward (x gradB_scale). */
 int icadv_perturb_update_adam(const float* im_s, float* noise, const float* g_in, float* m, float* v,
                               const icadv_perturb_state* st, int n_img, int64_t per_img, float eps,
-                              float beta1, float beta2, float adam_eps, float gradA_scale,
+                              double beta1, double beta2, double adam_eps, float gradA_scale,
                               float gradB_scale, icadv_stream_t stream);
 
 /* I-FGSM / PGD step (attack_ifgsm.py:409-418): x += alpha*sign(g); project to [x0-eps, x0+eps]. */
@@ -179,6 +179,43 @@ int icadv_bound_backward(const float* x, const float* gy, float* gx, int64_t n, 
 /* per-image sum of squared differences, deterministic two-stage reduction */
 int icadv_sum_sqdiff(const float* a, const float* b, float* ws, float* out, int n_img, int64_t per_img,
                      icadv_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Entropy models (compressai EntropyBottleneck / GaussianConditional; call sites
+ * anchors/model.py:87-106, attack_rd.py:419, self_ensemble.py:222, train.py:60-64).
+ * Channels-last tensors; bits[n] = -sum log2(max(lik, bits_floor)) per image (fixed-order sum).
+ * mode 0 = eval (round(x - mean) + mean), mode 1 = train (x + noise[], noise ~ U(-.5,.5) supplied
+ * by the caller so two implementations can share the sample).
+ * ------------------------------------------------------------------------------------------ */
+/* softplus(matrix_i), bias_i, tanh(factor_i) of the 1-3-3-3-3-1 logits chain -> table [58][C] */
+int icadv_eb_prepare(const float* const* matrices /*[5]*/, const float* const* biases /*[5]*/,
+                     const float* const* factors /*[4]*/, float* table, int C, icadv_stream_t stream);
+int icadv_eb_forward(const float* x, const float* noise, const float* table, const float* medians,
+                     float* x_hat, float* lik, float* ws, float* bits, int n_img, int64_t per_img, int C,
+                     int mode, float lik_bound, float bits_floor, icadv_stream_t stream);
+/* lik = Phi((.5-|v|)/s) - Phi((-.5-|v|)/s), s = max(scale, scale_bound), v = y_hat - mean */
+int icadv_gc_forward(const float* y, const float* scales, const float* means, const float* noise,
+                     float* y_hat, float* lik, float* ws, float* bits, int n_img, int64_t per_img, int mode,
+                     float scale_bound, float lik_bound, float bits_floor, icadv_stream_t stream);
+/* elementwise helpers: op 0 abs (h_a(|y|), anchors/balle.py:38), 1 relu, 2 leaky 0.01, 3 round, 4 y = x + b */
+int icadv_unary(const float* x, const float* b, float* y, int64_t n, int op, icadv_stream_t stream);
+/* gradient of op 0 abs / 1 relu / 2 leaky given the forward input (relu/leaky: or the output) */
+int icadv_act_backward(const float* x, const float* g, float* gx, int64_t n, int op, icadv_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * MS-SSIM (pytorch_msssim.ms_ssim, call sites attack_rd.py:336,362, self_ensemble.py:225,228,
+ * train.py:44,88; and utils/torch_msssim.py:18-76).  NCHW fp32 planes (planes = N*C).  One level
+ * per call: per-plane sums of the ssim and cs maps over the output region; the host composes the
+ * 5-level product.  same_pad = 0: valid separable window (variant 1); 1: zero "same" padding
+ * (variant 2; 2-D window = outer product of win_taps).  win_taps is a HOST array of `win` floats.
+ * ------------------------------------------------------------------------------------------ */
+int icadv_ssim_workspace_floats(int planes, int h, int w, int win, int same_pad);
+int icadv_ssim_level(const float* X, const float* Y, float* ws, float* ssim_sum, float* cs_sum, int planes,
+                     int h, int w, const float* win_taps_host, int win, int same_pad, float c1, float c2,
+                     icadv_stream_t stream);
+/* F.avg_pool2d(x, 2, stride 2, padding (pad_h, pad_w)) between levels */
+int icadv_avgpool2(const float* x, float* y, int planes, int h, int w, int pad_h, int pad_w,
+                   icadv_stream_t stream);
 
 #ifdef __cplusplus
 }
