@@ -33,7 +33,7 @@ struct TcParams {
   Tap taps[kMaxTaps];
   int num_taps, k_chunks, n_ch, n_chunks;
   int tiles_x, tiles_y;
-  int epi, act, acc_from_in;
+  int epi, act, acc_from_in, round_out;
   int num_stages, stage_bytes, tmem_cols;
   const float* bias;
   const float* beta;
@@ -203,7 +203,14 @@ __global__ void __launch_bounds__(192, 1) conv_tc_kernel(const __grid_constant__
         __syncwarp();
         named_bar_sync(1, 128);
       }
-      write_row32(bufO, row, o);
+      if (p.round_out) {
+        float r[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) r[j] = round_tf32(o[j]);
+        write_row32(bufO, row, r);
+      } else {
+        write_row32(bufO, row, o);
+      }
       if (o2 != nullptr) write_row32(bufS, row, o2);
       fence_proxy_async_smem();
       named_bar_sync(1, 128);
@@ -238,20 +245,20 @@ __global__ void __launch_bounds__(192, 1) conv_tc_kernel(const __grid_constant__
         load_acc1(c, v);
         if (!bwd) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) a2[j] = v[j] * v[j];
+          for (int j = 0; j < 32; ++j) a2[j] = round_tf32(v[j] * v[j]);
         } else {
           float yv[32], sv[32];
           read_row32(bufS, row, yv);
           read_row32(bufC, row, sv);
           if (p.epi == ICADV_EPI_GDN_BWD) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) a2[j] = v[j] * yv[j] * sv[j] * sv[j];
+            for (int j = 0; j < 32; ++j) a2[j] = round_tf32(v[j] * yv[j] * sv[j] * sv[j]);
           } else {
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
               // out-of-image rows are zero-filled (sc = 0): keep them finite
               float s2 = sv[j] * sv[j];
-              a2[j] = s2 > 0.f ? v[j] * yv[j] / s2 : 0.f;
+              a2[j] = s2 > 0.f ? round_tf32(v[j] * yv[j] / s2) : 0.f;
             }
           }
         }
@@ -460,7 +467,7 @@ int icadv_conv_plan_create(const icadv_conv_desc* d, icadv_conv_plan** out_plan)
     for (int t = 0; t < p.num_taps; ++t) p.taps[t] = g.taps[l][t];
     p.k_chunks = K / 32; p.n_ch = N; p.n_chunks = N / 32;
     p.tiles_x = (g.tile_w + kTW - 1) / kTW; p.tiles_y = (g.tile_h + kTH - 1) / kTH;
-    p.epi = d->epi; p.act = d->act; p.acc_from_in = d->acc_from_in;
+    p.epi = d->epi; p.act = d->act; p.acc_from_in = d->acc_from_in; p.round_out = d->round_out_tf32;
     p.stage_bytes = kABytes + N * 128;
     int avail = kSmemLimit - 1024 - kEpiBufs * kABytes - kBarBytes;
     p.num_stages = avail / p.stage_bytes;

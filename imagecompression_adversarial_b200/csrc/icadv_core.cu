@@ -3,6 +3,7 @@
 #include <string>
 
 #include "icadv_common.cuh"
+#include "icadv_ptx.cuh"
 
 namespace icadv {
 
@@ -89,7 +90,7 @@ __device__ __forceinline__ int64_t torch_w_index(int kind, int n, int k, int t, 
 }
 
 __global__ void pack_weight_kernel(const float* __restrict__ w, float* __restrict__ P, int kind, int c_out, int c_in,
-                                   int taps) {
+                                   int taps, int round) {
   const int N = (kind == 0 || kind == 2) ? c_out : c_in;
   const int K = (kind == 0 || kind == 2) ? c_in : c_out;
   int64_t total = (int64_t)taps * N * K;
@@ -97,7 +98,8 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, float* __restric
     int k = (int)(i % K);
     int n = (int)((i / K) % N);
     int t = (int)(i / ((int64_t)K * N));
-    P[i] = w[torch_w_index(kind, n, k, t, c_out, c_in, taps)];
+    const float v = w[torch_w_index(kind, n, k, t, c_out, c_in, taps)];
+    P[i] = round ? round_tf32(v) : v;
   }
 }
 
@@ -134,12 +136,13 @@ __global__ void transpose_cp_kernel(const float* __restrict__ src, float* __rest
 }
 
 __global__ void gdn_reparam_kernel(const float* __restrict__ raw, float* __restrict__ eff, int rows, int cols,
-                                   float bound, float pedestal, int transpose) {
+                                   float bound, float pedestal, int transpose, int round) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= rows * cols) return;
   int r = i / cols, c = i % cols;
   float v = fmaxf(raw[i], bound);
   v = v * v - pedestal;
+  if (round) v = round_tf32(v);
   if (transpose) eff[c * rows + r] = v; else eff[i] = v;
 }
 
@@ -173,13 +176,14 @@ int icadv_conv_out_hw(const icadv_conv_desc* d, int* out_h, int* out_w) {
   return ICADV_OK;
 }
 
-int icadv_pack_weight(const float* w, float* wpack, int kind, int c_out, int c_in, int ksize, icadv_stream_t stream) {
+int icadv_pack_weight(const float* w, float* wpack, int kind, int c_out, int c_in, int ksize, int round_tf32,
+                      icadv_stream_t stream) {
   ICADV_REQUIRE(w && wpack && kind >= 0 && kind <= 3, "bad pack_weight args");
   int taps = ksize * ksize;
   int64_t total = (int64_t)taps * c_out * c_in;
   int blocks = (int)((total + 255) / 256);
   if (blocks > 4096) blocks = 4096;
-  pack_weight_kernel<<<blocks, 256, 0, as_stream(stream)>>>(w, wpack, kind, c_out, c_in, taps);
+  pack_weight_kernel<<<blocks, 256, 0, as_stream(stream)>>>(w, wpack, kind, c_out, c_in, taps, round_tf32);
   ICADV_CUDA_TRY(cudaGetLastError());
   return ICADV_OK;
 }
@@ -215,11 +219,11 @@ int icadv_nhwc_to_nchw(const float* src, float* dst, int n, int c, int h, int w,
 }
 
 int icadv_gdn_reparam(const float* raw, float* eff, int rows, int cols, float bound, float pedestal, int transpose,
-                      icadv_stream_t stream) {
+                      int round_tf32, icadv_stream_t stream) {
   ICADV_REQUIRE(raw && eff && rows > 0 && cols > 0, "bad gdn_reparam args");
   int total = rows * cols;
   gdn_reparam_kernel<<<(total + 255) / 256, 256, 0, as_stream(stream)>>>(raw, eff, rows, cols, bound, pedestal,
-                                                                          transpose);
+                                                                          transpose, round_tf32);
   ICADV_CUDA_TRY(cudaGetLastError());
   return ICADV_OK;
 }

@@ -7,6 +7,7 @@
 //   * the round / additive-noise quantisers (utils/ops.py:8-25; compressai quantize, anchors/model.py:102);
 //   * rate:  bits[n] = -sum log2(max(lik, floor))   (attack_rd.py:419, self_ensemble.py:222, train.py:60-64).
 #include "icadv_common.cuh"
+#include "icadv_ptx.cuh"
 
 namespace icadv {
 
@@ -155,7 +156,7 @@ __global__ void sum_ws_kernel(const float* __restrict__ ws, float* __restrict__ 
   out[n] = s;
 }
 
-// elementwise helpers at the operator surface: 0 abs, 1 relu, 2 leaky(0.01), 3 round, 4 add (y = x + b)
+// elementwise helpers at the operator surface: 0 abs, 1 relu, 2 leaky(0.01), 3 round, 4 add (y = x + b), 5 round to TF32
 __global__ void unary_kernel(const float* __restrict__ x, const float* __restrict__ b, float* __restrict__ y, int64_t n,
                              int op) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
@@ -166,6 +167,7 @@ __global__ void unary_kernel(const float* __restrict__ x, const float* __restric
       case 1: r = fmaxf(v, 0.f); break;
       case 2: r = v > 0.f ? v : 0.01f * v; break;
       case 3: r = rintf(v); break;
+      case 5: r = round_tf32(v); break;
       default: r = v + b[i]; break;
     }
     y[i] = r;
@@ -234,7 +236,7 @@ int icadv_gc_forward(const float* y, const float* scales, const float* means, co
 }
 
 int icadv_unary(const float* x, const float* b, float* y, int64_t n, int op, icadv_stream_t stream) {
-  ICADV_REQUIRE(x && y && op >= 0 && op <= 4 && (op != 4 || b), "bad unary args");
+  ICADV_REQUIRE(x && y && op >= 0 && op <= 5 && (op != 4 || b), "bad unary args");
   int64_t blocks = (n + 255) / 256;
   if (blocks > 148 * 16) blocks = 148 * 16;
   if (blocks < 1) blocks = 1;

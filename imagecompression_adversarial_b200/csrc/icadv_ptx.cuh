@@ -157,6 +157,14 @@ __host__ __device__ __forceinline__ uint32_t umma_idesc_tf32(int M, int N) {
   return (1u << 4) | (2u << 7) | (2u << 10) | (static_cast<uint32_t>(N >> 3) << 17) |
          (static_cast<uint32_t>(M >> 4) << 24);
 }
+// round-to-nearest fp32 -> tf32 (10-bit mantissa), returned as an fp32 bit pattern.  tcgen05 kind::tf32 ignores
+// the low 13 mantissa bits (truncation, biased towards zero); operands are therefore rounded once where they
+// are PRODUCED, which makes the contraction error unbiased.
+__device__ __forceinline__ float round_tf32(float x) {
+  uint32_t u;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+  return __uint_as_float(u);
+}
 // byte offset of 16-byte chunk j of row r inside a [rows x 128 B] SWIZZLE_128B tile (1024 B aligned)
 __device__ __forceinline__ uint32_t sw128_off(int r, int j) { return (r << 7) + (((j ^ (r & 7)) & 7) << 4); }
 

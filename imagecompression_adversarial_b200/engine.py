@@ -45,9 +45,9 @@ class AttackEngine:
         # gradient wrt the latent: written by g_s.backward, seed of g_a.backward (one shared buffer)
         self.g_lat = f(n_img, lat_h, lat_w, ga_units[-1].cout)
         self.ga = StackProgram(ga_units, n_img, height, width, dev, x_in=self.im_in, g_out=self.g_lat, active=act,
-                               n_active=nact)
+                               n_active=nact, round_final_out=True)
         self.gs = StackProgram(gs_units, n_img, lat_h, lat_w, dev, x_in=self.ga.out, g_in=self.g_lat, active=act,
-                               n_active=nact)
+                               n_active=nact, round_final_gin=True)
         self.x_out, self.g_x = self.gs.out, self.gs.g_out
         assert self.x_out.shape == self.im_s.shape, (self.x_out.shape, self.im_s.shape)
         self._graph = None

@@ -23,15 +23,29 @@ def to_nchw(x_nhwc):
     return x_nhwc.permute(0, 3, 1, 2)
 
 
+def tc_shape(k_ch, n_ch):
+    """Shapes the tensor path takes (mirrors icadv_conv_tc_supported for the linear epilogue)."""
+    return k_ch % 32 == 0 and n_ch % 32 == 0 and 32 <= n_ch <= 256
+
+
 def packed(weight, kind):
-    """Packed copy of a layer weight, cached on (storage, version) so it is rebuilt only after an update."""
+    """Packed copy of a layer weight, cached on (storage, version) so it is rebuilt only after an update.
+    Weights of tensor-path contractions are rounded to TF32 (nearest) here."""
     key = (weight.data_ptr(), kind)
     hit = _PACK_CACHE.get(key)
     if hit is not None and hit[0] == weight._version and hit[2] == tuple(weight.shape):
         return hit[1]
-    wp = ops.pack_weight(weight, kind)
+    a, b = weight.shape[0], weight.shape[1]
+    n_ch, k_ch = {L.PACK_CONV_FWD: (a, b), L.PACK_CONV_DGRAD: (b, a), L.PACK_CONVT_FWD: (b, a),
+                  L.PACK_CONVT_DGRAD: (a, b)}[kind]
+    wp = ops.pack_weight(weight, kind, round_tf32=tc_shape(k_ch, n_ch))
     _PACK_CACHE[key] = (weight._version, wp, tuple(weight.shape))
     return wp
+
+
+def tc_operand(xn, k_ch, n_ch):
+    """Round an activation to TF32 (nearest) when it is about to feed a tensor-path contraction."""
+    return ops.unary(xn, 5) if tc_shape(k_ch, n_ch) else xn
 
 
 class Contraction(torch.autograd.Function):
@@ -43,8 +57,9 @@ class Contraction(torch.autograd.Function):
         kind = L.PACK_CONVT_FWD if transposed else L.PACK_CONV_FWD
         form = L.FORM_TCONV if transposed else L.FORM_SCONV
         n_ch = weight.shape[1] if transposed else weight.shape[0]
-        out = ops.conv(xn, packed(weight, kind), bias.detach() if bias is not None else None, form=form, ksize=ksize,
-                       stride=stride, n_ch=n_ch, act=act)
+        out = ops.conv(tc_operand(xn, xn.shape[-1], n_ch), packed(weight, kind),
+                       bias.detach() if bias is not None else None, form=form, ksize=ksize, stride=stride, n_ch=n_ch,
+                       act=act)
         ctx.save_for_backward(xn, weight, out if act != L.ACT_NONE else None)
         ctx.cfg = (ksize, stride, transposed, act, param_grads, bias is not None)
         return to_nchw(out)
@@ -60,8 +75,8 @@ class Contraction(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             kind = L.PACK_CONVT_DGRAD if transposed else L.PACK_CONV_DGRAD
             form = L.FORM_SCONV if transposed else L.FORM_TCONV
-            gx = to_nchw(ops.conv(gn, packed(weight, kind), None, form=form, ksize=ksize, stride=stride,
-                                  n_ch=xn.shape[-1]))
+            gx = to_nchw(ops.conv(tc_operand(gn.contiguous(), gn.shape[-1], xn.shape[-1]), packed(weight, kind), None,
+                                  form=form, ksize=ksize, stride=stride, n_ch=xn.shape[-1]))
         if param_grads and (ctx.needs_input_grad[1] or (has_bias and ctx.needs_input_grad[2])):
             form = L.FORM_TCONV if transposed else L.FORM_SCONV
             n_ch = weight.shape[1] if transposed else weight.shape[0]

@@ -94,15 +94,18 @@ class GDN(nn.Module):
         self.beta = nn.Parameter(self.beta_reparam.init(torch.ones(C)))
         self.gamma = nn.Parameter(self.gamma_reparam.init(gamma_init * torch.eye(C)))
 
-    def effective_parameters(self):
-        """(beta_eff [C], gamma_eff [C,C], gamma_eff^T) after the non-negative reparametrisation."""
+    def effective_parameters(self, round_tf32=False):
+        """(beta_eff [C], gamma_eff [C,C], gamma_eff^T) after the non-negative reparametrisation; the gamma
+        matrices optionally rounded to TF32 (they are operands of the tensor-path normalisation GEMM)."""
         be = ops.gdn_reparam(self.beta, self.beta_reparam.bound, self.beta_reparam.pedestal)
-        ga = ops.gdn_reparam(self.gamma, self.gamma_reparam.bound, self.gamma_reparam.pedestal)
-        gaT = ops.gdn_reparam(self.gamma, self.gamma_reparam.bound, self.gamma_reparam.pedestal, transpose=True)
+        ga = ops.gdn_reparam(self.gamma, self.gamma_reparam.bound, self.gamma_reparam.pedestal,
+                             round_tf32=round_tf32)
+        gaT = ops.gdn_reparam(self.gamma, self.gamma_reparam.bound, self.gamma_reparam.pedestal, transpose=True,
+                              round_tf32=round_tf32)
         return be, ga, gaT
 
     def forward(self, x):
-        be, ga, _ = self.effective_parameters()
+        be, ga, _ = self.effective_parameters(round_tf32=True)
         return Fn.GdnFn.apply(x, be, ga, self.inverse)
 
 

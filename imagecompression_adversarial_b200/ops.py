@@ -35,7 +35,7 @@ def require_device():
     L.call("icadv_check_device")
 
 
-def pack_weight(w, kind):
+def pack_weight(w, kind, round_tf32=False):
     """torch Conv2d [Co,Ci,k,k] / ConvTranspose2d [Ci,Co,k,k] weight -> packed [k*k][n_ch][k_ch]."""
     w = w.detach().contiguous()
     _chk(w, "weight")
@@ -46,7 +46,7 @@ def pack_weight(w, kind):
         c_in, c_out = w.shape[0], w.shape[1]
     n, kk = (c_out, c_in) if kind in (L.PACK_CONV_FWD, L.PACK_CONVT_FWD) else (c_in, c_out)
     out = torch.empty(k * k, n, kk, device=w.device, dtype=torch.float32)
-    L.call("icadv_pack_weight", _p(w), _p(out), kind, c_out, c_in, k, _stream())
+    L.call("icadv_pack_weight", _p(w), _p(out), kind, c_out, c_in, k, 1 if round_tf32 else 0, _stream())
     return out
 
 
@@ -80,13 +80,13 @@ def nhwc_to_nchw(x):
     return out
 
 
-def gdn_reparam(raw, bound, pedestal, transpose=False):
+def gdn_reparam(raw, bound, pedestal, transpose=False, round_tf32=False):
     raw = raw.detach().contiguous()
     _chk(raw, "raw")
     rows, cols = (raw.shape[0], raw.shape[1]) if raw.dim() == 2 else (1, raw.numel())
     out = torch.empty_like(raw)
     L.call("icadv_gdn_reparam", _p(raw), _p(out), rows, cols, float(bound), float(pedestal), 1 if transpose else 0,
-           _stream())
+           1 if round_tf32 else 0, _stream())
     return out
 
 
@@ -98,7 +98,8 @@ def out_hw(form, ksize, stride, h, w):
 
 
 def make_desc(x, wpack, bias, out, *, form, ksize, stride, n_ch, epi=L.EPI_LINEAR, act=L.ACT_NONE, gmat=None,
-              beta=None, out_scale=None, y_prev=None, sc_prev=None, acc_from_in=False, active=None, n_active=None):
+              beta=None, out_scale=None, y_prev=None, sc_prev=None, acc_from_in=False, active=None, n_active=None,
+              round_out=False):
     n, h, w, k_ch = x.shape
     d = L.ConvDesc()
     d.form, d.ksize, d.stride, d.n_img, d.in_h, d.in_w, d.k_ch, d.n_ch = form, ksize, stride, n, h, w, k_ch, n_ch
@@ -106,13 +107,14 @@ def make_desc(x, wpack, bias, out, *, form, ksize, stride, n_ch, epi=L.EPI_LINEA
     d.epi, d.act = epi, act
     d.gmat, d.beta, d.out_scale, d.y_prev, d.sc_prev = _p(gmat), _p(beta), _p(out_scale), _p(y_prev), _p(sc_prev)
     d.acc_from_in = 1 if acc_from_in else 0
+    d.round_out_tf32 = 1 if round_out else 0
     d.active, d.n_active = _p(active), _p(n_active)
     return d
 
 
 def conv(x, wpack, bias=None, *, form, ksize, stride, n_ch, epi=L.EPI_LINEAR, act=L.ACT_NONE, gmat=None, beta=None,
          y_prev=None, sc_prev=None, acc_from_in=False, active=None, n_active=None, out=None, out_scale=None,
-         path="auto"):
+         path="auto", round_out=False):
     """One contraction launch (see include/icadv.h).  Returns ``out`` or ``(out, out_scale)`` for the
     GDN/IGDN forward epilogues.  ``path``: "auto" (tensor path when the shape allows), "tc", "simt"."""
     for t, nm in ((x, "x"), (wpack, "wpack"), (bias, "bias"), (gmat, "gmat"), (beta, "beta"), (y_prev, "y_prev"),
@@ -129,7 +131,7 @@ def conv(x, wpack, bias=None, *, form, ksize, stride, n_ch, epi=L.EPI_LINEAR, ac
         out_scale = torch.empty_like(out)
     d = make_desc(x, wpack, bias, out, form=form, ksize=ksize, stride=stride, n_ch=n_ch, epi=epi, act=act, gmat=gmat,
                   beta=beta, out_scale=out_scale, y_prev=y_prev, sc_prev=sc_prev, acc_from_in=acc_from_in,
-                  active=active, n_active=n_active)
+                  active=active, n_active=n_active, round_out=round_out)
     use_tc = path == "tc" or (path == "auto" and L.lib().icadv_conv_tc_supported(C.byref(d)) == 1)
     if use_tc:
         L.call("icadv_conv_tc", C.byref(d), _stream())

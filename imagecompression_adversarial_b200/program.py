@@ -54,8 +54,9 @@ def _tc_ok(k_ch, n_ch, gdn):
 
 class StackProgram:
     def __init__(self, units, n_img, in_h, in_w, device, *, x_in=None, g_out=None, g_in=None, active=None,
-                 n_active=None, need_grad=True):
+                 n_active=None, need_grad=True, round_final_out=False, round_final_gin=False):
         self.units, self.n_img, self.device = units, n_img, device
+        self.round_final_out, self.round_final_gin = round_final_out, round_final_gin
         self.active, self.n_active = active, n_active
         f = lambda *shape: torch.empty(*shape, device=device, dtype=torch.float32)
         U = len(units)
@@ -97,8 +98,11 @@ class StackProgram:
         """(Re)pack weights and reparametrise GDN parameters; call after a codec update."""
         for j, u in enumerate(self.units):
             w = u.conv.weight
-            wf = ops.pack_weight(w, L.PACK_CONVT_FWD if u.transposed else L.PACK_CONV_FWD)
-            wb = ops.pack_weight(w, L.PACK_CONVT_DGRAD if u.transposed else L.PACK_CONV_DGRAD)
+            # tensor-path operands are rounded to TF32 (nearest) once, here; CUDA-core layers keep fp32 weights
+            wf = ops.pack_weight(w, L.PACK_CONVT_FWD if u.transposed else L.PACK_CONV_FWD,
+                                 round_tf32=_tc_ok(u.cin, u.cout, False))
+            wb = ops.pack_weight(w, L.PACK_CONVT_DGRAD if u.transposed else L.PACK_CONV_DGRAD,
+                                 round_tf32=_tc_ok(u.cout, u.cin, False))
             if self.w_fwd[j] is None:       # plans bake these pointers in: later refreshes copy in place
                 self.w_fwd[j], self.w_bwd[j] = wf, wb
             else:
@@ -110,7 +114,7 @@ class StackProgram:
             elif b is not None:
                 self.bias[j].copy_(b)
             if u.gdn is not None:
-                be, ga, gaT = u.gdn.effective_parameters()
+                be, ga, gaT = u.gdn.effective_parameters(round_tf32=True)
                 for store, val in ((self.beta, be), (self.gamma, ga), (self.gammaT, gaT)):
                     if store[j] is None:
                         store[j] = val
@@ -132,22 +136,26 @@ class StackProgram:
         U, units = len(self.units), self.units
         self.fwd, self.bwd = [], []
         x = self.x_in
+        # an activation is rounded to TF32 where it is produced iff its consumer is a tensor-path contraction
+        fwd_round = [(_tc_ok(units[j + 1].cin, units[j + 1].cout, False) if j + 1 < U else self.round_final_out)
+                     for j in range(U)]
+        bwd_round = [(_tc_ok(units[j].cout, units[j].cin, False)) for j in range(U)]  # gu[j] feeds dgrad of unit j
         for j, u in enumerate(units):
             if u.gdn is None:
                 self.fwd.append(self._launch(x, self.w_fwd[j], self.bias[j], self.y[j], form=u.fwd_form, u=u,
-                                             n_ch=u.cout))
+                                             n_ch=u.cout, round_out=fwd_round[j]))
             elif self.fused_fwd[j]:
                 epi = L.EPI_IGDN_FWD if u.gdn.inverse else L.EPI_GDN_FWD
                 self.fwd.append(self._launch(x, self.w_fwd[j], self.bias[j], self.y[j], form=u.fwd_form, u=u,
                                              n_ch=u.cout, epi=epi, gmat=self.gamma[j], beta=self.beta[j],
-                                             out_scale=self.sc[j]))
+                                             out_scale=self.sc[j], round_out=fwd_round[j]))
             else:
                 epi = L.EPI_IGDN_FWD if u.gdn.inverse else L.EPI_GDN_FWD
                 self.fwd.append(self._launch(x, self.w_fwd[j], self.bias[j], self.u[j], form=u.fwd_form, u=u,
                                              n_ch=u.cout))
                 self.fwd.append(self._launch(self.u[j], None, None, self.y[j], form=L.FORM_SCONV, u=u, n_ch=u.cout,
                                              ksize=1, stride=1, epi=epi, gmat=self.gamma[j], beta=self.beta[j],
-                                             out_scale=self.sc[j], acc_from_in=True))
+                                             out_scale=self.sc[j], acc_from_in=True, round_out=fwd_round[j]))
             x = self.y[j]
         if not self.need_grad:
             return
@@ -156,26 +164,29 @@ class StackProgram:
             self.bwd.append(self._launch(self.g_out, None, None, self.gu[-1], form=L.FORM_SCONV, u=units[-1],
                                          n_ch=units[-1].cout, ksize=1, stride=1,
                                          epi=L.EPI_IGDN_BWD if g.inverse else L.EPI_GDN_BWD, gmat=self.gammaT[-1],
-                                         y_prev=self.y[-1], sc_prev=self.sc[-1], acc_from_in=True))
+                                         y_prev=self.y[-1], sc_prev=self.sc[-1], acc_from_in=True,
+                                         round_out=bwd_round[-1]))
         for j in range(U - 1, 0, -1):
             u, prev = units[j], units[j - 1]
             if prev.gdn is None:
                 self.bwd.append(self._launch(self.gu[j], self.w_bwd[j], None, self.gu[j - 1], form=u.bwd_form, u=u,
-                                             n_ch=u.cin))
+                                             n_ch=u.cin, round_out=bwd_round[j - 1]))
                 continue
             epi = L.EPI_IGDN_BWD if prev.gdn.inverse else L.EPI_GDN_BWD
             if self.fused_bwd[j]:
                 self.bwd.append(self._launch(self.gu[j], self.w_bwd[j], None, self.gu[j - 1], form=u.bwd_form, u=u,
                                              n_ch=u.cin, epi=epi, gmat=self.gammaT[j - 1], y_prev=self.y[j - 1],
-                                             sc_prev=self.sc[j - 1]))
+                                             sc_prev=self.sc[j - 1], round_out=bwd_round[j - 1]))
             else:
                 self.bwd.append(self._launch(self.gu[j], self.w_bwd[j], None, self.gy[j], form=u.bwd_form, u=u,
                                              n_ch=u.cin))
                 self.bwd.append(self._launch(self.gy[j], None, None, self.gu[j - 1], form=L.FORM_SCONV, u=prev,
                                              n_ch=prev.cout, ksize=1, stride=1, epi=epi, gmat=self.gammaT[j - 1],
-                                             y_prev=self.y[j - 1], sc_prev=self.sc[j - 1], acc_from_in=True))
+                                             y_prev=self.y[j - 1], sc_prev=self.sc[j - 1], acc_from_in=True,
+                                             round_out=bwd_round[j - 1]))
         u0 = units[0]
-        self.bwd.append(self._launch(self.gu[0], self.w_bwd[0], None, self.g_in, form=u0.bwd_form, u=u0, n_ch=u0.cin))
+        self.bwd.append(self._launch(self.gu[0], self.w_bwd[0], None, self.g_in, form=u0.bwd_form, u=u0, n_ch=u0.cin,
+                                     round_out=self.round_final_gin))
 
     def forward(self):
         for p in self.fwd:

