@@ -24,7 +24,7 @@ class ConvDesc(C.Structure):
                 ("inp", _fp), ("wpack", _fp), ("bias", _fp), ("out", _fp),
                 ("epi", C.c_int), ("act", C.c_int),
                 ("gmat", _fp), ("beta", _fp), ("out_scale", _fp), ("y_prev", _fp), ("sc_prev", _fp),
-                ("acc_from_in", C.c_int), ("round_out_tf32", C.c_int), ("active", _fp), ("n_active", _fp)]
+                ("acc_from_in", C.c_int), ("round_out_tf32", C.c_int), ("in_pad4", C.c_int), ("active", _fp), ("n_active", _fp)]
 
 
 class PerturbState(C.Structure):
@@ -51,6 +51,9 @@ _SIGS = {
     "icadv_conv_simt": (C.c_int, [C.POINTER(ConvDesc), C.c_void_p]),
     "icadv_conv_wgrad": (C.c_int, [C.POINTER(ConvDesc), _fp, _fp, _fp, C.c_void_p]),
     "icadv_pack_weight": (C.c_int, [_fp, _fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "icadv_pack_weight_rgb": (C.c_int, [_fp, _fp, C.c_int, C.c_int, C.c_void_p]),
+    "icadv_pad_rgb4": (C.c_int, [_fp, _fp, C.c_int, C.c_int, C.c_int, C.c_int, _fp, _fp, C.c_void_p]),
+    "icadv_conv_plan_num_launches": (C.c_int, [C.c_void_p]),
     "icadv_unpack_weight": (C.c_int, [_fp, _fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "icadv_nchw_to_nhwc": (C.c_int, [_fp, _fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "icadv_nhwc_to_nchw": (C.c_int, [_fp, _fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),

@@ -22,19 +22,22 @@ namespace icadv {
 
 constexpr int kTH = 8, kTW = 16, kTileM = 128;
 constexpr int kABytes = kTileM * 128;   // one [128 x 32 fp32] operand / staging tile
-constexpr int kEpiBufs = 4;
 constexpr int kMaxStages = 8;
 constexpr int kSmemLimit = 232448;      // 227 KB
 constexpr int kBarBytes = 512;
+constexpr int kEpiCol2im = 5;           // internal epilogue code: narrow-output transposed conv via col2im
+constexpr int kZStride = 77;            // floats per row of the col2im staging tile (odd: conflict-free)
 
 struct TcParams {
   CUtensorMap a_map[4];
   CUtensorMap w_map, g_map, out_map, sc_map, yprev_map, scprev_map;
   Tap taps[kMaxTaps];
-  int num_taps, k_chunks, n_ch, n_chunks;
-  int tiles_x, tiles_y;
-  int epi, act, acc_from_in, round_out;
-  int num_stages, stage_bytes, tmem_cols;
+  int num_taps, k_chunks, n_ch, n_chunks;   // n_ch = MMA N; n_chunks = n_ch / 32
+  int tiles_x, tiles_y, tile_step_y, tile_step_x, tile_off;
+  int epi, act, acc_from_in, round_out, a_rank5;
+  int num_stages, stage_bytes, tmem_cols, epi_bufs;
+  int c2i_in_h, c2i_in_w, c2i_nch;         // col2im: input extent, real output channels
+  float* c2i_out;                           // col2im: dense [n_img, 2*in_h, 2*in_w, c2i_nch]
   const float* bias;
   const float* beta;
   const int* active;
@@ -68,22 +71,22 @@ __global__ void __launch_bounds__(192, 1) conv_tc_kernel(const __grid_constant__
   if (p.n_active != nullptr && slot >= *p.n_active) return;  // whole CTA leaves together
   const int img = p.active != nullptr ? p.active[slot] : slot;
   const int ty = blockIdx.x / p.tiles_x, tx = blockIdx.x % p.tiles_x;
-  const int i0 = ty * kTH, j0 = tx * kTW;
+  const int i0 = ty * p.tile_step_y + p.tile_off, j0 = tx * p.tile_step_x + p.tile_off;
 
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* epi_buf = smem + p.num_stages * p.stage_bytes;
-  uint64_t* full = reinterpret_cast<uint64_t*>(epi_buf + kEpiBufs * kABytes);
+  uint64_t* full = reinterpret_cast<uint64_t*>(epi_buf + p.epi_bufs * kABytes);
   uint64_t* empty = full + kMaxStages;
   uint64_t* acc_full = empty + kMaxStages;   // [2]
   uint64_t* a2_ready = acc_full + 2;         // [8]
-  uint64_t* ld_full = a2_ready + 8;          // [1]
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(ld_full + 1);
+  uint64_t* ld_full = a2_ready + 8;          // [2]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(ld_full + 2);
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.num_stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
     mbar_init(&acc_full[0], 1); mbar_init(&acc_full[1], 1);
     for (int c = 0; c < 8; ++c) mbar_init(&a2_ready[c], 128);
-    mbar_init(ld_full, 1);
+    mbar_init(&ld_full[0], 1); mbar_init(&ld_full[1], 1);
     mbar_fence_init();
   }
   if (warp == 1) { tmem_alloc(tmem_ptr, p.tmem_cols); tmem_relinquish(); }
@@ -95,7 +98,7 @@ __global__ void __launch_bounds__(192, 1) conv_tc_kernel(const __grid_constant__
   tc_fence_after_sync();
   const uint32_t tmem = *tmem_ptr;
 
-  const bool gdn = p.epi != ICADV_EPI_LINEAR;
+  const bool gdn = p.epi >= ICADV_EPI_GDN_FWD && p.epi <= ICADV_EPI_IGDN_BWD;
   const bool bwd = p.epi == ICADV_EPI_GDN_BWD || p.epi == ICADV_EPI_IGDN_BWD;
   const int main_kb = p.acc_from_in ? 0 : p.num_taps * p.k_chunks;
   const int gdn_kb = gdn ? p.n_chunks : 0;
@@ -113,7 +116,10 @@ __global__ void __launch_bounds__(192, 1) conv_tc_kernel(const __grid_constant__
           mbar_wait(&empty[s], ((kb / S) & 1) ^ 1);
           uint8_t* st = smem + s * p.stage_bytes;
           mbar_arrive_expect_tx(&full[s], kABytes + b_bytes);
-          tma_load_4d(st, &p.a_map[tap.plane], &full[s], kc * 32, j0 + tap.dx, i0 + tap.dy, img);
+          if (p.a_rank5)
+            tma_load_5d(st, &p.a_map[0], &full[s], 0, j0 + tap.dx, i0 + tap.dy, tap.plane, img);
+          else
+            tma_load_4d(st, &p.a_map[tap.plane], &full[s], kc * 32, j0 + tap.dx, i0 + tap.dy, img);
           tma_load_2d(st + kABytes, &p.w_map, &full[s], kc * 32, tap.wtap * p.n_ch);
         }
       }
@@ -162,146 +168,207 @@ __global__ void __launch_bounds__(192, 1) conv_tc_kernel(const __grid_constant__
     const int row = q * 32 + lane;       // tile pixel: (row / kTW, row % kTW)
     const uint32_t t_lane = tmem + (static_cast<uint32_t>(q * 32) << 16);
     const bool leader = (row == 0);
-    uint8_t* bufO = epi_buf;                  // out staging
-    uint8_t* bufS = epi_buf + kABytes;        // FWD: scale staging;  BWD: y_prev chunk
-    uint8_t* bufC = epi_buf + 2 * kABytes;    // BWD: sc_prev chunk
-    uint8_t* bufX = epi_buf + 3 * kABytes;    // acc_from_in: x / g chunk
-    const int n_loads = (p.acc_from_in ? 1 : 0) + (bwd ? 2 : 0);
-    uint32_t ld_phase = 0;
-    bool store_pending = false;
 
-    auto fetch_chunk = [&](int c) {  // TMA-load the global operands of chunk c into staging
-      if (n_loads == 0) return;
-      named_bar_sync(1, 128);  // everyone finished reading the previous chunk's staging
-      if (leader) {
-        mbar_arrive_expect_tx(ld_full, n_loads * kABytes);
-        if (p.acc_from_in) tma_load_4d(bufX, &p.a_map[0], ld_full, c * 32, j0, i0, img);
-        if (bwd) {
-          tma_load_4d(bufS, &p.yprev_map, ld_full, c * 32, j0, i0, img);
-          tma_load_4d(bufC, &p.scprev_map, ld_full, c * 32, j0, i0, img);
-        }
-      }
-      __syncwarp();
-      mbar_wait(ld_full, ld_phase);
-      ld_phase ^= 1;
-    };
-    auto load_acc1 = [&](int c, float* v) {
-      if (p.acc_from_in) {
-        read_row32(bufX, row, v);
-      } else {
-        tmem_ld32(t_lane + c * 32, v);
-        tmem_ld_wait();
-      }
-      if (p.bias != nullptr) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] += __ldg(p.bias + c * 32 + j);
-      }
-    };
-    auto store_chunk = [&](int c, const float* o, const float* o2) {  // o2: second output (scale) or null
-      if (store_pending) {
-        if (leader) tma_store_wait_read0();
-        __syncwarp();
-        named_bar_sync(1, 128);
-      }
-      if (p.round_out) {
-        float r[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) r[j] = round_tf32(o[j]);
-        write_row32(bufO, row, r);
-      } else {
-        write_row32(bufO, row, o);
-      }
-      if (o2 != nullptr) write_row32(bufS, row, o2);
-      fence_proxy_async_smem();
-      named_bar_sync(1, 128);
-      if (leader) {
-        tma_store_4d(&p.out_map, bufO, c * 32, j0, i0, img);
-        if (o2 != nullptr) tma_store_4d(&p.sc_map, bufS, c * 32, j0, i0, img);
-        tma_store_commit();
-      }
-      __syncwarp();
-      store_pending = true;
-    };
-
-    if (main_kb > 0) {
+    if (p.epi == kEpiCol2im) {
+      // ---- Z[128 px][taps*nch] -> smem, then gather the transposed-conv outputs of the tile interior ----
+      float* Zs = reinterpret_cast<float*>(epi_buf);
+      const int zcols = 25 * p.c2i_nch;
       mbar_wait(&acc_full[0], 0);
       tc_fence_after_sync();
-    }
-
-    if (!gdn) {
       for (int c = 0; c < p.n_chunks; ++c) {
         float v[32];
-        fetch_chunk(c);
-        load_acc1(c, v);
+        tmem_ld32(t_lane + c * 32, v);
+        tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], p.act);
-        store_chunk(c, v, nullptr);
+        for (int j = 0; j < 32; ++j)
+          if (c * 32 + j < zcols) Zs[row * kZStride + c * 32 + j] = v[j];
+      }
+      named_bar_sync(1, 128);
+      const int OH = 2 * p.c2i_in_h, OW = 2 * p.c2i_in_w, nch = p.c2i_nch;
+      const int cells = p.tile_step_y * p.tile_step_x;
+      for (int o = row; o < cells * 4; o += 128) {
+        const int cell = o >> 2, a = (o >> 1) & 1, b = o & 1;
+        const int ti = 1 + cell / p.tile_step_x, tj = 1 + cell % p.tile_step_x;
+        const int gi = i0 + ti, gj = j0 + tj;
+        if (gi >= p.c2i_in_h || gj >= p.c2i_in_w) continue;
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int kh = a; kh < 5; kh += 2) {
+          const int dh = (a + 2 - kh) / 2;
+          for (int kw = b; kw < 5; kw += 2) {
+            const int dw = (b + 2 - kw) / 2;
+            const float* z = Zs + ((ti + dh) * kTW + (tj + dw)) * kZStride + (kh * 5 + kw) * nch;
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+              if (c < nch) acc[c] += z[c];
+          }
+        }
+        float* dst = p.c2i_out + (((int64_t)img * OH + 2 * gi + a) * OW + 2 * gj + b) * nch;
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+          if (c < nch) dst[c] = acc[c] + (p.bias != nullptr ? __ldg(p.bias + c) : 0.f);
       }
     } else {
-      // ---- pass 1: build the A operand of the normalisation GEMM ----
-      for (int c = 0; c < p.n_chunks; ++c) {
-        float v[32], a2[32];
-        fetch_chunk(c);
-        load_acc1(c, v);
-        if (!bwd) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) a2[j] = round_tf32(v[j] * v[j]);
-        } else {
-          float yv[32], sv[32];
-          read_row32(bufS, row, yv);
-          read_row32(bufC, row, sv);
-          if (p.epi == ICADV_EPI_GDN_BWD) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) a2[j] = round_tf32(v[j] * yv[j] * sv[j] * sv[j]);
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              // out-of-image rows are zero-filled (sc = 0): keep them finite
-              float s2 = sv[j] * sv[j];
-              a2[j] = s2 > 0.f ? round_tf32(v[j] * yv[j] / s2) : 0.f;
-            }
+      // staging: O[2] out | S[2] FWD scale out / BWD y_prev in | C[2] BWD sc_prev in, FWD x in | X[2] BWD x in
+      auto bufO = [&](int i) { return epi_buf + (0 + i) * kABytes; };
+      auto bufS = [&](int i) { return epi_buf + (2 + i) * kABytes; };
+      auto bufC = [&](int i) { return epi_buf + (4 + i) * kABytes; };
+      auto bufX = [&](int i) { return bwd ? epi_buf + (6 + i) * kABytes : epi_buf + (4 + i) * kABytes; };
+      const int n_loads = (p.acc_from_in ? 1 : 0) + (bwd ? 2 : 0);
+      int fetch_cnt = 0, use_cnt = 0, stores = 0;
+
+      auto issue_fetch = [&](int c) {   // TMA-load the global operands of chunk c (double buffered)
+        if (n_loads == 0) return;
+        const int b = fetch_cnt & 1;
+        if (leader) {
+          mbar_arrive_expect_tx(&ld_full[b], n_loads * kABytes);
+          if (p.acc_from_in) tma_load_4d(bufX(b), &p.a_map[0], &ld_full[b], c * 32, j0, i0, img);
+          if (bwd) {
+            tma_load_4d(bufS(b), &p.yprev_map, &ld_full[b], c * 32, j0, i0, img);
+            tma_load_4d(bufC(b), &p.scprev_map, &ld_full[b], c * 32, j0, i0, img);
           }
         }
-        const int kb = main_kb + c, s = kb % S;
-        mbar_wait(&empty[s], ((kb / S) & 1) ^ 1);   // MMAs that last read this slot are done
-        write_row32(smem + s * p.stage_bytes, row, a2);
-        fence_proxy_async_smem();
-        mbar_arrive(&a2_ready[c]);
-      }
-      // ---- pass 2: normalise ----
-      mbar_wait(&acc_full[1], 0);
-      tc_fence_after_sync();
-      for (int c = 0; c < p.n_chunks; ++c) {
-        float v[32], w[32];
-        fetch_chunk(c);
-        load_acc1(c, v);
-        tmem_ld32(t_lane + p.n_ch + c * 32, w);
-        tmem_ld_wait();
-        if (!bwd) {
-          float sc[32];
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            float n = __ldg(p.beta + c * 32 + j) + w[j];
-            sc[j] = (p.epi == ICADV_EPI_GDN_FWD) ? rsqrtf(n) : sqrtf(n);
-            v[j] *= sc[j];
-          }
-          store_chunk(c, v, sc);
+        __syncwarp();
+        ++fetch_cnt;
+      };
+      auto wait_fetch = [&]() -> int {
+        if (n_loads == 0) return 0;
+        const int b = use_cnt & 1;
+        mbar_wait(&ld_full[b], (use_cnt >> 1) & 1);
+        ++use_cnt;
+        return b;
+      };
+      auto load_acc1 = [&](int c, int b, float* v) {
+        if (p.acc_from_in) {
+          read_row32(bufX(b), row, v);
         } else {
-          float yv[32], sv[32];
-          read_row32(bufS, row, yv);
-          read_row32(bufC, row, sv);
-          const float sign = (p.epi == ICADV_EPI_GDN_BWD) ? -1.f : 1.f;
+          tmem_ld32(t_lane + c * 32, v);
+          tmem_ld_wait();
+        }
+        if (p.bias != nullptr) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            float xs = sv[j] > 0.f ? yv[j] / sv[j] : 0.f;   // x = y / sc
-            v[j] = v[j] * sv[j] + sign * xs * w[j];
-          }
+          for (int j = 0; j < 32; ++j) v[j] += __ldg(p.bias + c * 32 + j);
+        }
+      };
+      // top of a storing chunk: staging O/S[c&1] (store of chunk c-2) and the load set of chunk c-1 are free after this
+      auto chunk_top = [&](int c, int n) {
+        if (leader && stores >= 2) tma_store_wait_read1();
+        __syncwarp();
+        named_bar_sync(1, 128);
+        if (c + 1 < n) issue_fetch(c + 1);
+      };
+      auto store_chunk = [&](int c, const float* o, const float* o2) {  // o2: second output (scale) or null
+        const int sb = stores & 1;
+        if (p.round_out) {
+          float r[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) r[j] = round_tf32(o[j]);
+          write_row32(bufO(sb), row, r);
+        } else {
+          write_row32(bufO(sb), row, o);
+        }
+        if (o2 != nullptr) write_row32(bufS(sb), row, o2);
+        fence_proxy_async_smem();
+        named_bar_sync(1, 128);
+        if (leader) {
+          tma_store_4d(&p.out_map, bufO(sb), c * 32, j0, i0, img);
+          if (o2 != nullptr) tma_store_4d(&p.sc_map, bufS(sb), c * 32, j0, i0, img);
+          tma_store_commit();
+        }
+        __syncwarp();
+        ++stores;
+      };
+
+      issue_fetch(0);   // overlaps the tail of the main loop
+      if (main_kb > 0) {
+        mbar_wait(&acc_full[0], 0);
+        tc_fence_after_sync();
+      }
+
+      if (!gdn) {
+        for (int c = 0; c < p.n_chunks; ++c) {
+          float v[32];
+          chunk_top(c, p.n_chunks);
+          const int b = wait_fetch();
+          load_acc1(c, b, v);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], p.act);
           store_chunk(c, v, nullptr);
         }
+      } else {
+        // ---- pass 1: build the A operand of the normalisation GEMM ----
+        for (int c = 0; c < p.n_chunks; ++c) {
+          float v[32], a2[32];
+          if (c + 1 < p.n_chunks) {
+            if (fetch_cnt >= 2) named_bar_sync(1, 128);   // load set of chunk c-1 fully consumed
+            issue_fetch(c + 1);
+          }
+          const int b = wait_fetch();
+          load_acc1(c, b, v);
+          if (!bwd) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) a2[j] = round_tf32(v[j] * v[j]);
+          } else {
+            float yv[32], sv[32];
+            read_row32(bufS(b), row, yv);
+            read_row32(bufC(b), row, sv);
+            if (p.epi == ICADV_EPI_GDN_BWD) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) a2[j] = round_tf32(v[j] * yv[j] * sv[j] * sv[j]);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                // out-of-image rows are zero-filled (sc = 0): keep them finite
+                float s2 = sv[j] * sv[j];
+                a2[j] = s2 > 0.f ? round_tf32(v[j] * yv[j] / s2) : 0.f;
+              }
+            }
+          }
+          const int kb = main_kb + c, s = kb % S;
+          mbar_wait(&empty[s], ((kb / S) & 1) ^ 1);   // MMAs that last read this slot are done
+          write_row32(smem + s * p.stage_bytes, row, a2);
+          fence_proxy_async_smem();
+          mbar_arrive(&a2_ready[c]);
+        }
+        // ---- pass 2: normalise ----
+        if (n_loads > 0) {
+          named_bar_sync(1, 128);   // pass-1 reads of both load sets are complete
+          issue_fetch(0);
+        }
+        mbar_wait(&acc_full[1], 0);
+        tc_fence_after_sync();
+        for (int c = 0; c < p.n_chunks; ++c) {
+          float v[32], w[32];
+          chunk_top(c, p.n_chunks);
+          const int b = wait_fetch();
+          load_acc1(c, b, v);
+          tmem_ld32(t_lane + p.n_ch + c * 32, w);
+          tmem_ld_wait();
+          if (!bwd) {
+            float sc[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              float n = __ldg(p.beta + c * 32 + j) + w[j];
+              sc[j] = (p.epi == ICADV_EPI_GDN_FWD) ? rsqrtf(n) : sqrtf(n);
+              v[j] *= sc[j];
+            }
+            store_chunk(c, v, sc);
+          } else {
+            float yv[32], sv[32];
+            read_row32(bufS(b), row, yv);
+            read_row32(bufC(b), row, sv);
+            const float sign = (p.epi == ICADV_EPI_GDN_BWD) ? -1.f : 1.f;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              float xs = sv[j] > 0.f ? yv[j] / sv[j] : 0.f;   // x = y / sc
+              v[j] = v[j] * sv[j] + sign * xs * w[j];
+            }
+            store_chunk(c, v, nullptr);
+          }
+        }
       }
+      if (leader) tma_store_wait0();
+      __syncwarp();
     }
-    if (leader) tma_store_wait0();
-    __syncwarp();
   }
 
   tc_fence_before_sync();
@@ -372,6 +439,27 @@ static int encode_plane(CUtensorMap* m, const float* base, int C, int W, int H, 
                      (int64_t)H * W * C);
 }
 
+// padded RGB0 input of the first-layer form: [n_img][in_h + 4][in_w + 8][4] floats, pixel (h, w) at (h+2, w+2)
+static int encode_pad4(CUtensorMap* m, const float* base, int W, int H, int N) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) { set_error("cuTensorMapEncodeTiled not available"); return ICADV_ECUDA; }
+  const int64_t Wp = W + 8, Hp = H + 4;
+  // dims: 32 floats (8 px x 4 ch, overlapping windows) | output column (2 px apart) | output row (2 rows apart)
+  //       | row parity | image
+  cuuint64_t dims[5] = {32, (cuuint64_t)(W / 2), (cuuint64_t)(Hp / 2), 2, (cuuint64_t)N};
+  cuuint64_t strides[4] = {32, (cuuint64_t)(2 * Wp * 16), (cuuint64_t)(Wp * 16), (cuuint64_t)(Hp * Wp * 16)};
+  cuuint32_t box[5] = {32, (cuuint32_t)kTW, (cuuint32_t)kTH, 1, 1};
+  cuuint32_t es[5] = {1, 1, 1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, const_cast<float*>(base), dims, strides, box, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled(5d pad4 W=%d H=%d N=%d) failed: %d", W, H, N, (int)r);
+    return ICADV_ECUDA;
+  }
+  return ICADV_OK;
+}
+
 }  // namespace icadv
 
 using namespace icadv;
@@ -383,39 +471,54 @@ struct icadv_conv_plan {
   int smem_bytes[4];
 };
 
-static int tc_supported(const icadv_conv_desc* d, bool report) {
+enum TcMode { kModeNone = 0, kModeGeneric = 1, kModeRgbIn = 2, kModeCol2im = 3 };
+
+static int tc_mode(const icadv_conv_desc* d, bool report) {
 #define TC_REQ(cond, msg)                     \
   do {                                        \
     if (!(cond)) {                            \
       if (report) set_error("conv_tc: " msg); \
-      return 0;                               \
+      return kModeNone;                       \
     }                                         \
   } while (0)
   TC_REQ(d != nullptr, "null descriptor");
+  TC_REQ(d->epi >= ICADV_EPI_LINEAR && d->epi <= ICADV_EPI_IGDN_BWD, "bad epilogue");
+  if (d->in_pad4) {   // first-layer form: 3 input channels in the padded RGB0 layout, 5x5 stride 2
+    TC_REQ(d->form == ICADV_FORM_SCONV && d->ksize == 5 && d->stride == 2 && d->k_ch == 3, "in_pad4 needs a 5x5/2 SCONV with k_ch = 3");
+    TC_REQ(d->in_h % 2 == 0 && d->in_w % 2 == 0, "in_pad4 needs even image sizes");
+    TC_REQ(d->n_ch % 32 == 0 && d->n_ch >= 32 && d->n_ch <= 256, "n_ch must be a multiple of 32 in [32,256]");
+    if (d->epi != ICADV_EPI_LINEAR) TC_REQ(2 * d->n_ch <= 512, "GDN epilogue needs 2*n_ch <= 512 TMEM columns");
+    TC_REQ(!d->acc_from_in, "in_pad4 excludes acc_from_in");
+    return kModeRgbIn;
+  }
+  if (d->form == ICADV_FORM_TCONV && d->ksize == 5 && d->stride == 2 && d->n_ch <= 4 && d->k_ch % 32 == 0 &&
+      d->k_ch >= 32 && d->epi == ICADV_EPI_LINEAR && d->act == ICADV_ACT_NONE && !d->acc_from_in)
+    return kModeCol2im;   // narrow-output transposed conv (RGB end layer): 1x1 GEMM + col2im epilogue
   TC_REQ(d->k_ch % 32 == 0 && d->k_ch >= 32, "k_ch must be a multiple of 32");
   TC_REQ(d->n_ch % 32 == 0 && d->n_ch >= 32 && d->n_ch <= 256, "n_ch must be a multiple of 32 in [32,256]");
-  TC_REQ(d->epi >= ICADV_EPI_LINEAR && d->epi <= ICADV_EPI_IGDN_BWD, "bad epilogue");
   if (d->epi != ICADV_EPI_LINEAR) TC_REQ(2 * d->n_ch <= 512, "GDN epilogue needs 2*n_ch <= 512 TMEM columns");
   if (d->acc_from_in) TC_REQ(d->k_ch == d->n_ch && d->ksize == 1 && d->stride == 1, "acc_from_in needs a 1x1 identity geometry");
   TC_REQ(d->ksize * d->ksize <= kMaxTaps, "too many taps");
 #undef TC_REQ
-  return 1;
+  return kModeGeneric;
 }
 
 extern "C" {
 
-int icadv_conv_tc_supported(const icadv_conv_desc* d) { return tc_supported(d, false); }
+int icadv_conv_tc_supported(const icadv_conv_desc* d) { return tc_mode(d, false) != kModeNone ? 1 : 0; }
 
 int icadv_conv_plan_create(const icadv_conv_desc* d, icadv_conv_plan** out_plan) {
   ICADV_REQUIRE(out_plan != nullptr, "null plan pointer");
   *out_plan = nullptr;
-  if (!tc_supported(d, true)) return ICADV_EINVAL;
+  const int mode = tc_mode(d, true);
+  if (mode == kModeNone) return ICADV_EINVAL;
   ICADV_REQUIRE(d->in && d->out && (d->acc_from_in || d->wpack), "null tensor pointer");
   const bool gdn = d->epi != ICADV_EPI_LINEAR;
   const bool bwd = d->epi == ICADV_EPI_GDN_BWD || d->epi == ICADV_EPI_IGDN_BWD;
   if (gdn) ICADV_REQUIRE(d->gmat != nullptr, "GDN epilogue needs gmat");
   if (gdn && !bwd) ICADV_REQUIRE(d->beta && d->out_scale, "GDN forward needs beta and out_scale");
   if (bwd) ICADV_REQUIRE(d->y_prev && d->sc_prev, "GDN backward needs y_prev and sc_prev");
+  ICADV_REQUIRE(d->n_img <= 65535, "conv_tc: n_img too large");
   Geometry g;
   int rc = make_geometry(d, &g);
   if (rc) return rc;
@@ -424,14 +527,21 @@ int icadv_conv_plan_create(const icadv_conv_desc* d, icadv_conv_plan** out_plan)
 
   icadv_conv_plan* plan = new (std::nothrow) icadv_conv_plan();
   if (!plan) { set_error("out of host memory"); return ICADV_ENOMEM; }
-  plan->n_launch = g.n_launch;
-  const int K = d->k_ch, N = d->n_ch, taps_total = d->ksize * d->ksize;
+  const int K = d->k_ch, taps_total = d->ksize * d->ksize;
   const int s = d->stride;
-  for (int l = 0; l < g.n_launch; ++l) {
+  const int N = mode == kModeCol2im ? 96 : d->n_ch;   // MMA N
+  plan->n_launch = mode == kModeCol2im ? 1 : g.n_launch;
+  for (int l = 0; l < plan->n_launch; ++l) {
     TcParams& p = plan->params[l];
     memset(&p, 0, sizeof(p));
+    p.tile_step_y = kTH; p.tile_step_x = kTW; p.tile_off = 0;
     // ---- input maps
-    if (d->form == ICADV_FORM_SCONV && s == 2) {
+    if (mode == kModeRgbIn) {
+      rc = encode_pad4(&p.a_map[0], d->in, d->in_w, d->in_h, d->n_img);
+      if (rc) { delete plan; return rc; }
+      p.a_map[1] = p.a_map[2] = p.a_map[3] = p.a_map[0];
+      p.a_rank5 = 1;
+    } else if (d->form == ICADV_FORM_SCONV && s == 2) {
       for (int a = 0; a < 2; ++a)
         for (int b = 0; b < 2; ++b) {
           if (d->in_h <= a || d->in_w <= b) { p.a_map[a * 2 + b] = p.a_map[0]; continue; }
@@ -444,32 +554,60 @@ int icadv_conv_plan_create(const icadv_conv_desc* d, icadv_conv_plan** out_plan)
       if (rc) { delete plan; return rc; }
       p.a_map[1] = p.a_map[2] = p.a_map[3] = p.a_map[0];
     }
-    // ---- output-side maps (dense for SCONV, parity plane for TCONV)
+    // ---- output-side maps (dense for SCONV, parity plane for TCONV); col2im writes with plain stores
     auto out_side = [&](CUtensorMap* m, const float* base) -> int {
       if (d->form == ICADV_FORM_TCONV && s == 2)
         return encode_plane(m, base, N, g.out_w, g.out_h, d->n_img, 2, g.out_a[l], g.out_b[l]);
       return encode_nhwc(m, base, N, g.out_w, g.out_h, d->n_img, N, (int64_t)g.out_w * N,
                          (int64_t)g.out_h * g.out_w * N);
     };
-    rc = out_side(&p.out_map, d->out);
-    if (!rc && gdn && !bwd) rc = out_side(&p.sc_map, d->out_scale);
-    if (!rc && bwd) rc = out_side(&p.yprev_map, d->y_prev);
-    if (!rc && bwd) rc = out_side(&p.scprev_map, d->sc_prev);
-    if (!rc && !d->acc_from_in) rc = encode_mat(&p.w_map, d->wpack, K, taps_total * N, N);
-    if (!rc && gdn) rc = encode_mat(&p.g_map, d->gmat, N, N, N);
-    if (rc) { delete plan; return rc; }
-    if (!(gdn && !bwd)) p.sc_map = p.out_map;
-    if (!bwd) { p.yprev_map = p.out_map; p.scprev_map = p.out_map; }
-    if (d->acc_from_in) p.w_map = p.out_map;
-    if (!gdn) p.g_map = p.out_map;
+    if (mode == kModeCol2im) {
+      rc = encode_mat(&p.w_map, d->wpack, K, taps_total * d->n_ch, N);   // rows >= 25*n_ch read as zeros
+      if (rc) { delete plan; return rc; }
+      p.out_map = p.sc_map = p.yprev_map = p.scprev_map = p.g_map = p.w_map;
+    } else {
+      rc = out_side(&p.out_map, d->out);
+      if (!rc && gdn && !bwd) rc = out_side(&p.sc_map, d->out_scale);
+      if (!rc && bwd) rc = out_side(&p.yprev_map, d->y_prev);
+      if (!rc && bwd) rc = out_side(&p.scprev_map, d->sc_prev);
+      if (!rc && !d->acc_from_in) {
+        if (mode == kModeRgbIn) rc = encode_mat(&p.w_map, d->wpack, 32, 5 * N, N);   // [5 kh][N][32]
+        else rc = encode_mat(&p.w_map, d->wpack, K, taps_total * N, N);
+      }
+      if (!rc && gdn) rc = encode_mat(&p.g_map, d->gmat, N, N, N);
+      if (rc) { delete plan; return rc; }
+      if (!(gdn && !bwd)) p.sc_map = p.out_map;
+      if (!bwd) { p.yprev_map = p.out_map; p.scprev_map = p.out_map; }
+      if (d->acc_from_in) p.w_map = p.out_map;
+      if (!gdn) p.g_map = p.out_map;
+    }
 
-    p.num_taps = g.n_taps[l];
-    for (int t = 0; t < p.num_taps; ++t) p.taps[t] = g.taps[l][t];
-    p.k_chunks = K / 32; p.n_ch = N; p.n_chunks = N / 32;
-    p.tiles_x = (g.tile_w + kTW - 1) / kTW; p.tiles_y = (g.tile_h + kTH - 1) / kTH;
-    p.epi = d->epi; p.act = d->act; p.acc_from_in = d->acc_from_in; p.round_out = d->round_out_tf32;
+    if (mode == kModeRgbIn) {
+      // one K-block per kernel row kh: padded input row 2*oh + kh -> (parity kh & 1, half-row oh + (kh >> 1))
+      p.num_taps = 5; p.k_chunks = 1;
+      for (int kh = 0; kh < 5; ++kh) {
+        Tap t; t.plane = (int16_t)(kh & 1); t.dy = (int16_t)(kh >> 1); t.dx = 0; t.wtap = (int16_t)kh;
+        p.taps[kh] = t;
+      }
+    } else if (mode == kModeCol2im) {
+      p.num_taps = 1; p.k_chunks = K / 32;
+      Tap t; t.plane = 0; t.dy = 0; t.dx = 0; t.wtap = 0;
+      p.taps[0] = t;
+      p.tile_step_y = kTH - 2; p.tile_step_x = kTW - 2; p.tile_off = -1;   // 1-pixel halo, interior 6 x 14
+      p.c2i_in_h = d->in_h; p.c2i_in_w = d->in_w; p.c2i_nch = d->n_ch; p.c2i_out = d->out;
+    } else {
+      p.num_taps = g.n_taps[l];
+      for (int t = 0; t < p.num_taps; ++t) p.taps[t] = g.taps[l][t];
+      p.k_chunks = K / 32;
+    }
+    p.n_ch = N; p.n_chunks = N / 32;
+    p.tiles_x = (g.tile_w + p.tile_step_x - 1) / p.tile_step_x;
+    p.tiles_y = (g.tile_h + p.tile_step_y - 1) / p.tile_step_y;
+    p.epi = mode == kModeCol2im ? kEpiCol2im : d->epi;
+    p.act = d->act; p.acc_from_in = d->acc_from_in; p.round_out = d->round_out_tf32;
     p.stage_bytes = kABytes + N * 128;
-    int avail = kSmemLimit - 1024 - kEpiBufs * kABytes - kBarBytes;
+    p.epi_bufs = mode == kModeCol2im ? 3 : (bwd ? (d->acc_from_in ? 8 : 6) : (d->acc_from_in ? 6 : (gdn ? 4 : 2)));
+    int avail = kSmemLimit - 1024 - p.epi_bufs * kABytes - kBarBytes;
     p.num_stages = avail / p.stage_bytes;
     if (p.num_stages > kMaxStages) p.num_stages = kMaxStages;
     if (p.num_stages < 2) { delete plan; set_error("conv_tc: not enough shared memory for n_ch=%d", N); return ICADV_EINVAL; }
@@ -478,8 +616,7 @@ int icadv_conv_plan_create(const icadv_conv_desc* d, icadv_conv_plan** out_plan)
     p.tmem_cols = pow2;
     p.bias = d->bias; p.beta = d->beta; p.active = d->active; p.n_active = d->n_active;
     plan->grid[l] = dim3(p.tiles_x * p.tiles_y, d->n_img, 1);
-    plan->smem_bytes[l] = 1024 + p.num_stages * p.stage_bytes + kEpiBufs * kABytes + kBarBytes;
-    if (d->n_img > 65535) { delete plan; set_error("conv_tc: n_img too large"); return ICADV_EINVAL; }
+    plan->smem_bytes[l] = 1024 + p.num_stages * p.stage_bytes + p.epi_bufs * kABytes + kBarBytes;
   }
   static std::once_flag attr_once;
   static cudaError_t attr_err = cudaSuccess;
@@ -503,6 +640,8 @@ int icadv_conv_plan_launch(const icadv_conv_plan* plan, icadv_stream_t stream) {
   }
   return ICADV_OK;
 }
+
+int icadv_conv_plan_num_launches(const icadv_conv_plan* plan) { return plan ? plan->n_launch : 0; }
 
 int icadv_conv_plan_destroy(icadv_conv_plan* plan) {
   delete plan;

@@ -117,6 +117,33 @@ __global__ void unpack_weight_kernel(const float* __restrict__ P, float* __restr
   }
 }
 
+__global__ void pack_weight_rgb_kernel(const float* __restrict__ w, float* __restrict__ P, int n_ch, int round) {
+  const int total = 5 * n_ch * 32;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int k = i % 32, n = (i / 32) % n_ch, kh = i / (32 * n_ch);
+    const int kw = k >> 2, c = k & 3;
+    float v = 0.f;
+    if (kw < 5 && c < 3) v = w[((n * 3 + c) * 5 + kh) * 5 + kw];
+    P[i] = round ? round_tf32(v) : v;
+  }
+}
+
+__global__ void pad_rgb4_kernel(const float* __restrict__ src, float4* __restrict__ dst, int h, int w, int round,
+                                const int* __restrict__ active, const int* __restrict__ n_active) {
+  const int slot = blockIdx.y;
+  if (n_active != nullptr && slot >= *n_active) return;
+  const int img = active != nullptr ? active[slot] : slot;
+  const int wp = w + 8, hp = h + 4;
+  const float* s = src + (int64_t)img * h * w * 3;
+  float4* d = dst + (int64_t)img * hp * wp;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < h * w; i += gridDim.x * blockDim.x) {
+    const int y = i / w, x = i - y * w;
+    float a = s[3 * i], b = s[3 * i + 1], c = s[3 * i + 2];
+    if (round) { a = round_tf32(a); b = round_tf32(b); c = round_tf32(c); }
+    d[(int64_t)(y + 2) * wp + x + 2] = make_float4(a, b, c, 0.f);
+  }
+}
+
 // NCHW <-> NHWC through a 32x32 shared tile: both sides coalesced.
 __global__ void transpose_cp_kernel(const float* __restrict__ src, float* __restrict__ dst, int rows, int cols) {
   // src: [batch][rows][cols] -> dst: [batch][cols][rows]
@@ -184,6 +211,24 @@ int icadv_pack_weight(const float* w, float* wpack, int kind, int c_out, int c_i
   int blocks = (int)((total + 255) / 256);
   if (blocks > 4096) blocks = 4096;
   pack_weight_kernel<<<blocks, 256, 0, as_stream(stream)>>>(w, wpack, kind, c_out, c_in, taps, round_tf32);
+  ICADV_CUDA_TRY(cudaGetLastError());
+  return ICADV_OK;
+}
+
+int icadv_pack_weight_rgb(const float* w, float* wpack, int n_ch, int round_tf32, icadv_stream_t stream) {
+  ICADV_REQUIRE(w && wpack && n_ch > 0, "bad pack_weight_rgb args");
+  pack_weight_rgb_kernel<<<(5 * n_ch * 32 + 255) / 256, 256, 0, as_stream(stream)>>>(w, wpack, n_ch, round_tf32);
+  ICADV_CUDA_TRY(cudaGetLastError());
+  return ICADV_OK;
+}
+
+int icadv_pad_rgb4(const float* src, float* dst, int n_img, int h, int w, int round_tf32, const int* active,
+                   const int* n_active, icadv_stream_t stream) {
+  ICADV_REQUIRE(src && dst && n_img > 0 && h > 0 && w > 0 && n_img <= 65535, "bad pad_rgb4 args");
+  int bx = (h * w + 255) / 256;
+  if (bx > 592) bx = 592;
+  pad_rgb4_kernel<<<dim3(bx, n_img), 256, 0, as_stream(stream)>>>(src, reinterpret_cast<float4*>(dst), h, w, round_tf32,
+                                                                  active, n_active);
   ICADV_CUDA_TRY(cudaGetLastError());
   return ICADV_OK;
 }

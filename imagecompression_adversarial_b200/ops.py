@@ -50,6 +50,28 @@ def pack_weight(w, kind, round_tf32=False):
     return out
 
 
+def pack_weight_rgb(w, round_tf32=True):
+    """First-layer form: w[n][3][5][5] -> [5 kh][n][32] (k = kw*4 + c)."""
+    w = w.detach().contiguous()
+    _chk(w, "weight")
+    assert tuple(w.shape[1:]) == (3, 5, 5), w.shape
+    out = torch.empty(5, w.shape[0], 32, device=w.device, dtype=torch.float32)
+    L.call("icadv_pack_weight_rgb", _p(w), _p(out), w.shape[0], 1 if round_tf32 else 0, _stream())
+    return out
+
+
+def alloc_pad4(n_img, h, w, device):
+    """Zeroed padded RGB0 buffer [n, h+4, w+8, 4] (borders stay zero; pad_rgb4 fills the interior)."""
+    return torch.zeros(n_img, h + 4, w + 8, 4, device=device, dtype=torch.float32)
+
+
+def pad_rgb4(src, dst, active=None, n_active=None):
+    n, h, w, c = src.shape
+    assert c == 3 and tuple(dst.shape) == (n, h + 4, w + 8, 4)
+    L.call("icadv_pad_rgb4", _p(src), _p(dst), n, h, w, 1, _p(active), _p(n_active), _stream())
+    return dst
+
+
 def unpack_weight_grad(dwpack, like, kind, accumulate_into=None):
     """packed dW [k*k][n][k] -> gradient in the torch layout of ``like``."""
     k = like.shape[-1]
@@ -99,8 +121,11 @@ def out_hw(form, ksize, stride, h, w):
 
 def make_desc(x, wpack, bias, out, *, form, ksize, stride, n_ch, epi=L.EPI_LINEAR, act=L.ACT_NONE, gmat=None,
               beta=None, out_scale=None, y_prev=None, sc_prev=None, acc_from_in=False, active=None, n_active=None,
-              round_out=False):
-    n, h, w, k_ch = x.shape
+              round_out=False, in_pad4=False):
+    if in_pad4:
+        n, h, w, k_ch = x.shape[0], x.shape[1] - 4, x.shape[2] - 8, 3
+    else:
+        n, h, w, k_ch = x.shape
     d = L.ConvDesc()
     d.form, d.ksize, d.stride, d.n_img, d.in_h, d.in_w, d.k_ch, d.n_ch = form, ksize, stride, n, h, w, k_ch, n_ch
     d.inp, d.wpack, d.bias, d.out = _p(x), _p(wpack), _p(bias), _p(out)
@@ -108,13 +133,14 @@ def make_desc(x, wpack, bias, out, *, form, ksize, stride, n_ch, epi=L.EPI_LINEA
     d.gmat, d.beta, d.out_scale, d.y_prev, d.sc_prev = _p(gmat), _p(beta), _p(out_scale), _p(y_prev), _p(sc_prev)
     d.acc_from_in = 1 if acc_from_in else 0
     d.round_out_tf32 = 1 if round_out else 0
+    d.in_pad4 = 1 if in_pad4 else 0
     d.active, d.n_active = _p(active), _p(n_active)
     return d
 
 
 def conv(x, wpack, bias=None, *, form, ksize, stride, n_ch, epi=L.EPI_LINEAR, act=L.ACT_NONE, gmat=None, beta=None,
          y_prev=None, sc_prev=None, acc_from_in=False, active=None, n_active=None, out=None, out_scale=None,
-         path="auto", round_out=False):
+         path="auto", round_out=False, in_pad4=False):
     """One contraction launch (see include/icadv.h).  Returns ``out`` or ``(out, out_scale)`` for the
     GDN/IGDN forward epilogues.  ``path``: "auto" (tensor path when the shape allows), "tc", "simt"."""
     for t, nm in ((x, "x"), (wpack, "wpack"), (bias, "bias"), (gmat, "gmat"), (beta, "beta"), (y_prev, "y_prev"),
@@ -123,6 +149,8 @@ def conv(x, wpack, bias=None, *, form, ksize, stride, n_ch, epi=L.EPI_LINEAR, ac
     _chk(active, "active", torch.int32)
     _chk(n_active, "n_active", torch.int32)
     n, h, w, _ = x.shape
+    if in_pad4:
+        h, w = h - 4, w - 8
     oh, ow = out_hw(form, ksize, stride, h, w)
     if out is None:
         out = torch.empty(n, oh, ow, n_ch, device=x.device, dtype=torch.float32)
@@ -131,7 +159,7 @@ def conv(x, wpack, bias=None, *, form, ksize, stride, n_ch, epi=L.EPI_LINEAR, ac
         out_scale = torch.empty_like(out)
     d = make_desc(x, wpack, bias, out, form=form, ksize=ksize, stride=stride, n_ch=n_ch, epi=epi, act=act, gmat=gmat,
                   beta=beta, out_scale=out_scale, y_prev=y_prev, sc_prev=sc_prev, acc_from_in=acc_from_in,
-                  active=active, n_active=n_active, round_out=round_out)
+                  active=active, n_active=n_active, round_out=round_out, in_pad4=in_pad4)
     use_tc = path == "tc" or (path == "auto" and L.lib().icadv_conv_tc_supported(C.byref(d)) == 1)
     if use_tc:
         L.call("icadv_conv_tc", C.byref(d), _stream())
@@ -147,10 +175,10 @@ class ConvPlan:
 
     def __init__(self, desc, keep):
         self._keep = keep  # tensors whose pointers are baked into the tensor maps
-        self.kernels = desc.stride * desc.stride if desc.form == L.FORM_TCONV else 1
         h = C.c_void_p()
         L.call("icadv_conv_plan_create", C.byref(desc), C.byref(h))
         self._h = h
+        self.kernels = L.lib().icadv_conv_plan_num_launches(h)
 
     def launch(self):
         L.call("icadv_conv_plan_launch", self._h, _stream())

@@ -2,10 +2,12 @@
 
 A *unit* is one Conv2d/ConvTranspose2d optionally followed by GDN/IGDN.  Forward fuses the
 normalisation into the contraction's epilogue; backward fuses the normalisation's backward into the
-epilogue of the NEXT unit's input-gradient contraction (kernels K1-K5).  Shapes the
-tcgen05 path does not take (3-channel end layers) run on the CUDA-core kernels with a stand-alone
-(I)GDN launch.  Reference semantics: ``y = net.g_a(x)``, ``x_ = net.g_s(y)`` + autograd to the input
-(attack_rd.py:344,349,547).
+epilogue of the NEXT unit's input-gradient contraction (kernels K1-K5).  The RGB end
+layers run on the tensor path too: 3 -> N strided convs read a padded RGB0 copy of the image through an
+overlapping-window tensor map (one K-block per kernel row), N -> 3 transposed convs run as a 1x1 GEMM with
+a col2im epilogue.  Anything else the tensor path does not take falls to the CUDA-core kernels with a
+stand-alone (I)GDN launch.  Reference semantics: ``y = net.g_a(x)``, ``x_ = net.g_s(y)`` + autograd to
+the input (attack_rd.py:344,349,547).
 """
 import ctypes as C
 
@@ -48,8 +50,27 @@ def parse_stack(seq):
     return units
 
 
-def _tc_ok(k_ch, n_ch, gdn):
-    return k_ch % 32 == 0 and n_ch % 32 == 0 and 32 <= n_ch <= 256 and (not gdn or 2 * n_ch <= 512)
+def tc_kind(form, k, s, k_ch, n_ch):
+    """Which tensor-path mode takes this contraction (mirrors tc_mode() in csrc/icadv_conv_tc.cu):
+    "generic", "rgb_in" (3 -> N, 5x5/2, padded RGB0 input), "col2im" (N -> <=4, 5x5/2 transposed) or None."""
+    if form == L.FORM_SCONV and k == 5 and s == 2 and k_ch == 3 and n_ch % 32 == 0 and 32 <= n_ch <= 256:
+        return "rgb_in"
+    if form == L.FORM_TCONV and k == 5 and s == 2 and n_ch <= 4 and k_ch % 32 == 0 and k_ch >= 32:
+        return "col2im"
+    if k_ch % 32 == 0 and k_ch >= 32 and n_ch % 32 == 0 and 32 <= n_ch <= 256:
+        return "generic"
+    return None
+
+
+class PadLaunch:
+    """dense RGB [n,h,w,3] -> padded RGB0 layout (input of the rgb_in contraction)."""
+    kernels = 1
+
+    def __init__(self, src, dst, active, n_active):
+        self.src, self.dst, self.active, self.n_active = src, dst, active, n_active
+
+    def launch(self):
+        ops.pad_rgb4(self.src, self.dst, self.active, self.n_active)
 
 
 class StackProgram:
@@ -66,13 +87,23 @@ class StackProgram:
         self.hw = [(in_h, in_w)]
         for u in units:
             self.hw.append(ops.out_hw(u.fwd_form, u.k, u.s, *self.hw[-1]))
+        # ---- which path takes each contraction
+        self.fwd_kind = [tc_kind(u.fwd_form, u.k, u.s, u.cin, u.cout) for u in units]
+        self.bwd_kind = [tc_kind(u.bwd_form, u.k, u.s, u.cout, u.cin) for u in units]
+        for j in range(U):   # the padded-RGB form needs even image sizes
+            if self.fwd_kind[j] == "rgb_in" and (self.hw[j][0] % 2 or self.hw[j][1] % 2):
+                self.fwd_kind[j] = None
+            if self.bwd_kind[j] == "rgb_in" and (self.hw[j + 1][0] % 2 or self.hw[j + 1][1] % 2):
+                self.bwd_kind[j] = None
+        gdn_ok = lambda j: units[j].gdn is not None and 2 * units[j].cout <= 512
         # ---- forward buffers: y[j] = unit output (after GDN if any); sc[j] = GDN scale; u[j] = pre-GDN (unfused only)
         self.y = [f(n_img, *self.hw[j + 1], units[j].cout) for j in range(U)]
         self.sc = [torch.empty_like(self.y[j]) if units[j].gdn is not None else None for j in range(U)]
-        self.fused_fwd = [units[j].gdn is not None and _tc_ok(units[j].cin, units[j].cout, True) for j in range(U)]
+        self.fused_fwd = [gdn_ok(j) and self.fwd_kind[j] in ("generic", "rgb_in") for j in range(U)]
         self.u = [torch.empty_like(self.y[j]) if (units[j].gdn is not None and not self.fused_fwd[j]) else None
                   for j in range(U)]
         self.out = self.y[-1]
+        self.x_pad = {j: ops.alloc_pad4(n_img, *self.hw[j], device) for j in range(U) if self.fwd_kind[j] == "rgb_in"}
         # ---- parameters in kernel layouts
         self.w_fwd, self.w_bwd, self.bias = [None] * U, [None] * U, [None] * U
         self.beta, self.gamma, self.gammaT = [None] * U, [None] * U, [None] * U
@@ -85,24 +116,33 @@ class StackProgram:
                 assert g_out.shape == self.y[-1].shape
                 self.gu[-1] = g_out
             self.g_out = self.gu[-1] if units[-1].gdn is None else torch.empty_like(self.y[-1])
-            self.fused_bwd = [j > 0 and units[j - 1].gdn is not None and _tc_ok(units[j].cout, units[j].cin, True)
+            # backward of GDN_{j-1} rides in the epilogue of unit j's input-gradient contraction
+            self.fused_bwd = [j > 0 and gdn_ok(j - 1) and self.bwd_kind[j] in ("generic", "rgb_in")
                               for j in range(U)]
             self.gy = [torch.empty_like(self.y[j - 1]) if (j > 0 and units[j - 1].gdn is not None and
                                                           not self.fused_bwd[j]) else None for j in range(U)]
             self.g_in = g_in if g_in is not None else torch.empty_like(self.x_in)
             assert self.g_in.shape == self.x_in.shape
+            self.gu_pad = {j: ops.alloc_pad4(n_img, *self.hw[j + 1], device) for j in range(U)
+                           if self.bwd_kind[j] == "rgb_in"}
         self._build()
 
     # ------------------------------------------------------------------ parameters
     def refresh_parameters(self):
-        """(Re)pack weights and reparametrise GDN parameters; call after a codec update."""
+        """(Re)pack weights and reparametrise GDN parameters; call after a codec update.
+        Tensor-path operands are rounded to TF32 (nearest) once, here; CUDA-core layers keep fp32 weights."""
         for j, u in enumerate(self.units):
             w = u.conv.weight
-            # tensor-path operands are rounded to TF32 (nearest) once, here; CUDA-core layers keep fp32 weights
-            wf = ops.pack_weight(w, L.PACK_CONVT_FWD if u.transposed else L.PACK_CONV_FWD,
-                                 round_tf32=_tc_ok(u.cin, u.cout, False))
-            wb = ops.pack_weight(w, L.PACK_CONVT_DGRAD if u.transposed else L.PACK_CONV_DGRAD,
-                                 round_tf32=_tc_ok(u.cout, u.cin, False))
+            if self.fwd_kind[j] == "rgb_in":
+                wf = ops.pack_weight_rgb(w, round_tf32=True)
+            else:
+                wf = ops.pack_weight(w, L.PACK_CONVT_FWD if u.transposed else L.PACK_CONV_FWD,
+                                     round_tf32=self.fwd_kind[j] is not None)
+            if self.bwd_kind[j] == "rgb_in":
+                wb = ops.pack_weight_rgb(w, round_tf32=True)
+            else:
+                wb = ops.pack_weight(w, L.PACK_CONVT_DGRAD if u.transposed else L.PACK_CONV_DGRAD,
+                                     round_tf32=self.bwd_kind[j] is not None)
             if self.w_fwd[j] is None:       # plans bake these pointers in: later refreshes copy in place
                 self.w_fwd[j], self.w_bwd[j] = wf, wb
             else:
@@ -132,61 +172,72 @@ class StackProgram:
             raise L.IcadvError("normalisation epilogue requested on a shape the tensor path does not take")
         return ops.SimtLaunch(d, keep)
 
+    def _gdn_alone(self, x, out, j, epi, **kw):
+        u = self.units[j]
+        return self._launch(x, None, None, out, form=L.FORM_SCONV, u=u, n_ch=u.cout, ksize=1, stride=1, epi=epi,
+                            acc_from_in=True, **kw)
+
     def _build(self):
         U, units = len(self.units), self.units
         self.fwd, self.bwd = [], []
-        x = self.x_in
         # an activation is rounded to TF32 where it is produced iff its consumer is a tensor-path contraction
-        fwd_round = [(_tc_ok(units[j + 1].cin, units[j + 1].cout, False) if j + 1 < U else self.round_final_out)
-                     for j in range(U)]
-        bwd_round = [(_tc_ok(units[j].cout, units[j].cin, False)) for j in range(U)]  # gu[j] feeds dgrad of unit j
+        fwd_round = [(self.fwd_kind[j + 1] is not None if j + 1 < U else self.round_final_out) for j in range(U)]
+        bwd_round = [self.bwd_kind[j] is not None for j in range(U)]   # gu[j] feeds the input-gradient of unit j
+        x = self.x_in
         for j, u in enumerate(units):
+            extra = {}
+            if self.fwd_kind[j] == "rgb_in":
+                self.fwd.append(PadLaunch(x, self.x_pad[j], self.active, self.n_active))
+                x, extra = self.x_pad[j], {"in_pad4": True}
             if u.gdn is None:
                 self.fwd.append(self._launch(x, self.w_fwd[j], self.bias[j], self.y[j], form=u.fwd_form, u=u,
-                                             n_ch=u.cout, round_out=fwd_round[j]))
-            elif self.fused_fwd[j]:
-                epi = L.EPI_IGDN_FWD if u.gdn.inverse else L.EPI_GDN_FWD
-                self.fwd.append(self._launch(x, self.w_fwd[j], self.bias[j], self.y[j], form=u.fwd_form, u=u,
-                                             n_ch=u.cout, epi=epi, gmat=self.gamma[j], beta=self.beta[j],
-                                             out_scale=self.sc[j], round_out=fwd_round[j]))
+                                             n_ch=u.cout, round_out=fwd_round[j], **extra))
             else:
                 epi = L.EPI_IGDN_FWD if u.gdn.inverse else L.EPI_GDN_FWD
-                self.fwd.append(self._launch(x, self.w_fwd[j], self.bias[j], self.u[j], form=u.fwd_form, u=u,
-                                             n_ch=u.cout))
-                self.fwd.append(self._launch(self.u[j], None, None, self.y[j], form=L.FORM_SCONV, u=u, n_ch=u.cout,
-                                             ksize=1, stride=1, epi=epi, gmat=self.gamma[j], beta=self.beta[j],
-                                             out_scale=self.sc[j], acc_from_in=True, round_out=fwd_round[j]))
+                if self.fused_fwd[j]:
+                    self.fwd.append(self._launch(x, self.w_fwd[j], self.bias[j], self.y[j], form=u.fwd_form, u=u,
+                                                 n_ch=u.cout, epi=epi, gmat=self.gamma[j], beta=self.beta[j],
+                                                 out_scale=self.sc[j], round_out=fwd_round[j], **extra))
+                else:
+                    self.fwd.append(self._launch(x, self.w_fwd[j], self.bias[j], self.u[j], form=u.fwd_form, u=u,
+                                                 n_ch=u.cout, **extra))
+                    self.fwd.append(self._gdn_alone(self.u[j], self.y[j], j, epi, gmat=self.gamma[j],
+                                                    beta=self.beta[j], out_scale=self.sc[j],
+                                                    round_out=fwd_round[j]))
             x = self.y[j]
         if not self.need_grad:
             return
         if units[-1].gdn is not None:
             g = units[-1].gdn
-            self.bwd.append(self._launch(self.g_out, None, None, self.gu[-1], form=L.FORM_SCONV, u=units[-1],
-                                         n_ch=units[-1].cout, ksize=1, stride=1,
-                                         epi=L.EPI_IGDN_BWD if g.inverse else L.EPI_GDN_BWD, gmat=self.gammaT[-1],
-                                         y_prev=self.y[-1], sc_prev=self.sc[-1], acc_from_in=True,
-                                         round_out=bwd_round[-1]))
-        for j in range(U - 1, 0, -1):
-            u, prev = units[j], units[j - 1]
+            self.bwd.append(self._gdn_alone(self.g_out, self.gu[-1], U - 1,
+                                            L.EPI_IGDN_BWD if g.inverse else L.EPI_GDN_BWD, gmat=self.gammaT[-1],
+                                            y_prev=self.y[-1], sc_prev=self.sc[-1], round_out=bwd_round[-1]))
+        for j in range(U - 1, -1, -1):
+            u = units[j]
+            gsrc, extra = self.gu[j], {}
+            if self.bwd_kind[j] == "rgb_in":
+                self.bwd.append(PadLaunch(self.gu[j], self.gu_pad[j], self.active, self.n_active))
+                gsrc, extra = self.gu_pad[j], {"in_pad4": True}
+            if j == 0:
+                self.bwd.append(self._launch(gsrc, self.w_bwd[0], None, self.g_in, form=u.bwd_form, u=u, n_ch=u.cin,
+                                             round_out=self.round_final_gin, **extra))
+                continue
+            prev = units[j - 1]
             if prev.gdn is None:
-                self.bwd.append(self._launch(self.gu[j], self.w_bwd[j], None, self.gu[j - 1], form=u.bwd_form, u=u,
-                                             n_ch=u.cin, round_out=bwd_round[j - 1]))
+                self.bwd.append(self._launch(gsrc, self.w_bwd[j], None, self.gu[j - 1], form=u.bwd_form, u=u,
+                                             n_ch=u.cin, round_out=bwd_round[j - 1], **extra))
                 continue
             epi = L.EPI_IGDN_BWD if prev.gdn.inverse else L.EPI_GDN_BWD
             if self.fused_bwd[j]:
-                self.bwd.append(self._launch(self.gu[j], self.w_bwd[j], None, self.gu[j - 1], form=u.bwd_form, u=u,
+                self.bwd.append(self._launch(gsrc, self.w_bwd[j], None, self.gu[j - 1], form=u.bwd_form, u=u,
                                              n_ch=u.cin, epi=epi, gmat=self.gammaT[j - 1], y_prev=self.y[j - 1],
-                                             sc_prev=self.sc[j - 1], round_out=bwd_round[j - 1]))
+                                             sc_prev=self.sc[j - 1], round_out=bwd_round[j - 1], **extra))
             else:
-                self.bwd.append(self._launch(self.gu[j], self.w_bwd[j], None, self.gy[j], form=u.bwd_form, u=u,
-                                             n_ch=u.cin))
-                self.bwd.append(self._launch(self.gy[j], None, None, self.gu[j - 1], form=L.FORM_SCONV, u=prev,
-                                             n_ch=prev.cout, ksize=1, stride=1, epi=epi, gmat=self.gammaT[j - 1],
-                                             y_prev=self.y[j - 1], sc_prev=self.sc[j - 1], acc_from_in=True,
-                                             round_out=bwd_round[j - 1]))
-        u0 = units[0]
-        self.bwd.append(self._launch(self.gu[0], self.w_bwd[0], None, self.g_in, form=u0.bwd_form, u=u0, n_ch=u0.cin,
-                                     round_out=self.round_final_gin))
+                self.bwd.append(self._launch(gsrc, self.w_bwd[j], None, self.gy[j], form=u.bwd_form, u=u,
+                                             n_ch=u.cin, **extra))
+                self.bwd.append(self._gdn_alone(self.gy[j], self.gu[j - 1], j - 1, epi, gmat=self.gammaT[j - 1],
+                                                y_prev=self.y[j - 1], sc_prev=self.sc[j - 1],
+                                                round_out=bwd_round[j - 1]))
 
     def forward(self):
         for p in self.fwd:

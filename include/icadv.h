@@ -83,6 +83,9 @@ typedef struct {
   int acc_from_in;     /* 1: no contraction, acc := in (1x1, k_ch == n_ch); GDN/IGDN as a stand-alone op */
   int round_out_tf32;  /* 1: round `out` to TF32 (nearest) when stored -- set when its consumer is a tensor-path
                           contraction, so operands are rounded once where produced instead of truncated by the MMA */
+  int in_pad4;         /* 1: `in` is the padded RGB0 layout [n_img][in_h+4][in_w+8][4] (pixel (h,w) at (h+2,w+2),
+                          zero border, 4th channel 0) written by icadv_pad_rgb4; first-layer form: SCONV 5x5/2,
+                          k_ch = 3, wpack from icadv_pack_weight_rgb */
   const int* active;   /* optional [n_img] image indirection (device) */
   const int* n_active; /* optional device scalar: number of valid entries of `active` */
 } icadv_conv_desc;
@@ -97,6 +100,7 @@ typedef struct icadv_conv_plan icadv_conv_plan;
 int icadv_conv_plan_create(const icadv_conv_desc* d, icadv_conv_plan** plan);
 int icadv_conv_plan_launch(const icadv_conv_plan* plan, icadv_stream_t stream);
 int icadv_conv_plan_destroy(icadv_conv_plan* plan);
+int icadv_conv_plan_num_launches(const icadv_conv_plan* plan); /* kernels per icadv_conv_plan_launch */
 int icadv_conv_tc(const icadv_conv_desc* d, icadv_stream_t stream); /* create + launch + destroy */
 int icadv_conv_tc_supported(const icadv_conv_desc* d);             /* 1 / 0 */
 
@@ -114,6 +118,12 @@ int icadv_conv_wgrad(const icadv_conv_desc* d, const float* gout, float* dwpack,
  * 3 ConvTranspose2d.weight for its input-gradient. */
 int icadv_pack_weight(const float* w, float* wpack, int kind, int c_out, int c_in, int ksize,
                       int round_tf32, icadv_stream_t stream);
+/* first-layer form: w[n][3][5][5] (Conv2d.weight [Co,3,5,5] for its forward, or ConvTranspose2d.weight [Ci,3,5,5]
+ * for its input-gradient -- same indexing) -> [5 kh][n_ch][32] with k = kw*4 + c, zero elsewhere */
+int icadv_pack_weight_rgb(const float* w, float* wpack, int n_ch, int round_tf32, icadv_stream_t stream);
+/* dense channels-last RGB [n_img][h][w][3] -> padded RGB0 layout (borders must have been zeroed once) */
+int icadv_pad_rgb4(const float* src, float* dst, int n_img, int h, int w, int round_tf32, const int* active,
+                   const int* n_active, icadv_stream_t stream);
 /* inverse of the above for gradients: packed dW -> torch layout (accumulate = add into dst) */
 int icadv_unpack_weight(const float* dwpack, float* dw, int kind, int c_out, int c_in, int ksize,
                         int accumulate, icadv_stream_t stream);

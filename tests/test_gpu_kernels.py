@@ -129,6 +129,49 @@ def test_conv_tc_matches_torch(dev, kind, cin, cout, k, s, hw, n):
     assert rms_err(got, simt) < 2e-3
 
 
+@pytest.mark.parametrize("hw,n,cout", [((32, 48), 2, 128), ((20, 36), 1, 128), ((64, 64), 1, 192)])
+def test_rgb_in_conv_matches_torch(dev, hw, n, cout):
+    """First-layer form: 3 -> N 5x5/2 conv through the padded RGB0 layout + overlapping-window tensor map."""
+    from imagecompression_adversarial_b200 import _lib as L
+    from imagecompression_adversarial_b200 import ops
+    g = torch.Generator(device=dev).manual_seed(41)
+    w = torch.randn(cout, 3, 5, 5, device=dev, generator=g) / math.sqrt(75)
+    b = torch.randn(cout, device=dev, generator=g)
+    x = torch.rand(n, 3, *hw, device=dev, generator=g)
+    ref = F.conv2d(x, w, b, stride=2, padding=2)
+    pad = ops.pad_rgb4(nhwc(x), ops.alloc_pad4(n, *hw, dev))
+    out = ops.conv(pad, ops.pack_weight_rgb(w), b, form=L.FORM_SCONV, ksize=5, stride=2, n_ch=cout, in_pad4=True,
+                   path="tc")
+    assert rms_err(nchw(out), ref) < 1.5e-3
+    # same form as the input-gradient of ConvTranspose2d(N, 3): weight [N, 3, 5, 5], no bias
+    ref2 = F.conv2d(x, w, None, stride=2, padding=2)
+    out2 = ops.conv(pad, ops.pack_weight_rgb(w), None, form=L.FORM_SCONV, ksize=5, stride=2, n_ch=cout, in_pad4=True,
+                    path="tc")
+    assert rms_err(nchw(out2), ref2) < 1.5e-3
+
+
+@pytest.mark.parametrize("hw,n,cin", [((16, 24), 2, 128), ((13, 30), 1, 128), ((6, 14), 1, 192), ((7, 15), 3, 64)])
+def test_col2im_deconv_matches_torch(dev, hw, n, cin):
+    """Last-layer form: N -> 3 5x5/2 transposed conv as a 1x1 GEMM + col2im epilogue."""
+    from imagecompression_adversarial_b200 import _lib as L
+    from imagecompression_adversarial_b200 import ops
+    g = torch.Generator(device=dev).manual_seed(43)
+    w = torch.randn(cin, 3, 5, 5, device=dev, generator=g) / math.sqrt(cin * 25 / 4)
+    b = torch.randn(3, device=dev, generator=g)
+    x = torch.randn(n, cin, *hw, device=dev, generator=g)
+    ref = F.conv_transpose2d(x, w, b, stride=2, padding=2, output_padding=1)
+    out = ops.conv(nhwc(x), ops.pack_weight(w, L.PACK_CONVT_FWD, round_tf32=True), b, form=L.FORM_TCONV, ksize=5,
+                   stride=2, n_ch=3, path="tc")
+    assert nchw(out).shape == ref.shape
+    assert rms_err(nchw(out), ref) < 1.5e-3
+    # input-gradient of Conv2d(3, N): weight [N, 3, 5, 5]
+    w2 = torch.randn(cin, 3, 5, 5, device=dev, generator=g) / math.sqrt(75)
+    ref2 = F.conv_transpose2d(x, w2, None, stride=2, padding=2, output_padding=1)
+    out2 = ops.conv(nhwc(x), ops.pack_weight(w2, L.PACK_CONV_DGRAD, round_tf32=True), None, form=L.FORM_TCONV,
+                    ksize=5, stride=2, n_ch=3, path="tc")
+    assert rms_err(nchw(out2), ref2) < 1.5e-3
+
+
 def _gdn_params(C, dev, g):
     gamma = 0.1 * torch.eye(C, device=dev) + 0.02 * torch.rand(C, C, device=dev, generator=g)
     beta = 0.5 + torch.rand(C, device=dev, generator=g)
