@@ -54,6 +54,7 @@ _SIGS = {
     "icadv_pack_weight_rgb": (C.c_int, [_fp, _fp, C.c_int, C.c_int, C.c_void_p]),
     "icadv_pad_rgb4": (C.c_int, [_fp, _fp, C.c_int, C.c_int, C.c_int, C.c_int, _fp, _fp, C.c_void_p]),
     "icadv_conv_plan_num_launches": (C.c_int, [C.c_void_p]),
+    "icadv_conv_plan_set_debug": (C.c_int, [C.c_void_p, _fp]),
     "icadv_unpack_weight": (C.c_int, [_fp, _fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "icadv_nchw_to_nhwc": (C.c_int, [_fp, _fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "icadv_nhwc_to_nchw": (C.c_int, [_fp, _fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),

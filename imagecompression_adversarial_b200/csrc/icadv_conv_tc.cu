@@ -24,7 +24,7 @@ constexpr int kTH = 8, kTW = 16, kTileM = 128;
 constexpr int kABytes = kTileM * 128;   // one [128 x 32 fp32] operand / staging tile
 constexpr int kMaxStages = 8;
 constexpr int kSmemLimit = 232448;      // 227 KB
-constexpr int kBarBytes = 512;
+constexpr int kBarBytes = 256 + 2 * 256 * 4 + 64;   // barriers + per-channel bias/beta copies
 constexpr int kEpiCol2im = 5;           // internal epilogue code: narrow-output transposed conv via col2im
 constexpr int kZStride = 77;            // floats per row of the col2im staging tile (odd: conflict-free)
 
@@ -35,14 +35,22 @@ struct TcParams {
   int num_taps, k_chunks, n_ch, n_chunks;   // n_ch = MMA N; n_chunks = n_ch / 32
   int tiles_x, tiles_y, tile_step_y, tile_step_x, tile_off;
   int epi, act, acc_from_in, round_out, a_rank5;
-  int num_stages, stage_bytes, tmem_cols, epi_bufs;
+  int num_stages, stage_bytes, tmem_cols;
+  int t_h, t_w, o_h, o_w, o_s, o_a, o_b;    // tile-space extent; output geometry: pixel (o_s*i + o_a, o_s*j + o_b)
+  const float* yprev; const float* scprev; const float* xin;   // epilogue operands read with plain loads
   int c2i_in_h, c2i_in_w, c2i_nch;         // col2im: input extent, real output channels
   float* c2i_out;                           // col2im: dense [n_img, 2*in_h, 2*in_w, c2i_nch]
   const float* bias;
   const float* beta;
   const int* active;
   const int* n_active;
+  long long* dbg;   // optional per-CTA phase timestamps (16 slots per CTA), developer profiling only
 };
+
+#define TC_STAMP(slot)                                                          \
+  do {                                                                          \
+    if (p.dbg != nullptr) p.dbg[((int64_t)blockIdx.y * gridDim.x + blockIdx.x) * 32 + (slot)] = clock64(); \
+  } while (0)
 
 __device__ __forceinline__ float apply_act(float v, int act) {
   if (act == ICADV_ACT_RELU) return fmaxf(v, 0.f);
@@ -64,7 +72,29 @@ __device__ __forceinline__ void write_row32(uint8_t* buf, int row, const float* 
     *reinterpret_cast<float4*>(buf + sw128_off(row, j)) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
 }
 
-__global__ void __launch_bounds__(192, 1) conv_tc_kernel(const __grid_constant__ TcParams p) {
+constexpr int kThreads = 192;   // warp 0 TMA producer, warp 1 MMA issuer, warps 2-5 epilogue
+
+// 128-byte row chunk (32 channels) of one pixel straight from global memory; zeros when the pixel is outside
+__device__ __forceinline__ void ldg_row32(const float* __restrict__ ptr, bool valid, float* v) {
+  if (valid) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float4 t = __ldg(reinterpret_cast<const float4*>(ptr) + j);
+      v[4 * j] = t.x; v[4 * j + 1] = t.y; v[4 * j + 2] = t.z; v[4 * j + 3] = t.w;
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = 0.f;
+  }
+}
+
+// EPI: ICADV_EPI_* or kEpiCol2im.  FROM_IN: accumulator comes from global memory instead of a contraction.
+// Up to two CTAs share an SM (3 x 32 KB stages, 256 TMEM columns each): one CTA's prologue / epilogue / store
+// drain overlaps the other's main loop.
+template <int EPI, bool FROM_IN>
+__global__ void __launch_bounds__(kThreads, 2) conv_tc_kernel(const __grid_constant__ TcParams p) {
+  constexpr bool gdn = EPI >= ICADV_EPI_GDN_FWD && EPI <= ICADV_EPI_IGDN_BWD;
+  constexpr bool bwd = EPI == ICADV_EPI_GDN_BWD || EPI == ICADV_EPI_IGDN_BWD;
   extern __shared__ uint8_t smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int slot = blockIdx.y;
@@ -74,33 +104,40 @@ __global__ void __launch_bounds__(192, 1) conv_tc_kernel(const __grid_constant__
   const int i0 = ty * p.tile_step_y + p.tile_off, j0 = tx * p.tile_step_x + p.tile_off;
 
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* epi_buf = smem + p.num_stages * p.stage_bytes;
-  uint64_t* full = reinterpret_cast<uint64_t*>(epi_buf + p.epi_bufs * kABytes);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + p.num_stages * p.stage_bytes);
   uint64_t* empty = full + kMaxStages;
   uint64_t* acc_full = empty + kMaxStages;   // [2]
   uint64_t* a2_ready = acc_full + 2;         // [8]
-  uint64_t* ld_full = a2_ready + 8;          // [2]
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(ld_full + 2);
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(a2_ready + 8);
+  float* sbias = reinterpret_cast<float*>(full) + 64;   // [256] after the 256-byte barrier block
+  float* sbeta = sbias + 256;                           // [256]
 
   if (threadIdx.x == 0) {
+    TC_STAMP(0);
     for (int s = 0; s < p.num_stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
     mbar_init(&acc_full[0], 1); mbar_init(&acc_full[1], 1);
     for (int c = 0; c < 8; ++c) mbar_init(&a2_ready[c], 128);
-    mbar_init(&ld_full[0], 1); mbar_init(&ld_full[1], 1);
     mbar_fence_init();
   }
   if (warp == 1) { tmem_alloc(tmem_ptr, p.tmem_cols); tmem_relinquish(); }
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&p.a_map[0]); tma_prefetch_desc(&p.w_map); tma_prefetch_desc(&p.out_map);
+    if (gdn) tma_prefetch_desc(&p.g_map);
+    if (EPI == ICADV_EPI_GDN_FWD || EPI == ICADV_EPI_IGDN_FWD) tma_prefetch_desc(&p.sc_map);
+  }
+  if (threadIdx.x >= 64) {   // parameters the epilogue reads per channel
+    for (int i = threadIdx.x - 64; i < p.n_ch; i += kThreads - 64) {
+      sbias[i] = p.bias != nullptr ? __ldg(p.bias + i) : 0.f;
+      if (EPI == ICADV_EPI_GDN_FWD || EPI == ICADV_EPI_IGDN_FWD) sbeta[i] = __ldg(p.beta + i);
+    }
   }
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem = *tmem_ptr;
+  if (threadIdx.x == 0) TC_STAMP(1);
 
-  const bool gdn = p.epi >= ICADV_EPI_GDN_FWD && p.epi <= ICADV_EPI_IGDN_BWD;
-  const bool bwd = p.epi == ICADV_EPI_GDN_BWD || p.epi == ICADV_EPI_IGDN_BWD;
-  const int main_kb = p.acc_from_in ? 0 : p.num_taps * p.k_chunks;
+  const int main_kb = FROM_IN ? 0 : p.num_taps * p.k_chunks;
   const int gdn_kb = gdn ? p.n_chunks : 0;
   const uint32_t b_bytes = static_cast<uint32_t>(p.n_ch) * 128u;
   const int S = p.num_stages;
@@ -109,7 +146,7 @@ __global__ void __launch_bounds__(192, 1) conv_tc_kernel(const __grid_constant__
     // ===================== TMA producer =====================
     if (lane == 0) {
       int kb = 0;
-      for (int t = 0; t < (p.acc_from_in ? 0 : p.num_taps); ++t) {
+      for (int t = 0; t < (FROM_IN ? 0 : p.num_taps); ++t) {
         const Tap tap = p.taps[t];
         for (int kc = 0; kc < p.k_chunks; ++kc, ++kb) {
           const int s = kb % S;
@@ -139,6 +176,7 @@ __global__ void __launch_bounds__(192, 1) conv_tc_kernel(const __grid_constant__
       for (; kb < main_kb; ++kb) {
         const int s = kb % S;
         mbar_wait(&full[s], (kb / S) & 1);
+        if (kb == 0) TC_STAMP(2);
         tc_fence_after_sync();
         const uint32_t a_addr = smem_u32(smem + s * p.stage_bytes);
         const uint64_t ad = umma_desc_sw128(a_addr), bd = umma_desc_sw128(a_addr + kABytes);
@@ -147,6 +185,7 @@ __global__ void __launch_bounds__(192, 1) conv_tc_kernel(const __grid_constant__
         tc_commit(&empty[s]);
       }
       if (main_kb > 0) tc_commit(&acc_full[0]);
+      TC_STAMP(3);
       for (int c = 0; c < gdn_kb; ++c, ++kb) {
         const int s = kb % S;
         mbar_wait(&full[s], (kb / S) & 1);
@@ -160,22 +199,25 @@ __global__ void __launch_bounds__(192, 1) conv_tc_kernel(const __grid_constant__
         tc_commit(&empty[s]);
       }
       if (gdn_kb > 0) tc_commit(&acc_full[1]);
+      TC_STAMP(4);
     }
     __syncwarp();
   } else {
-    // ===================== epilogue (4 warps = 128 accumulator rows) =====================
+    // ===================== epilogue: 4 warps = 128 accumulator rows =====================
     const int q = warp & 3;              // TMEM lane quadrant this warp may touch
     const int row = q * 32 + lane;       // tile pixel: (row / kTW, row % kTW)
     const uint32_t t_lane = tmem + (static_cast<uint32_t>(q * 32) << 16);
     const bool leader = (row == 0);
+    const int nC = p.n_chunks;
 
-    if (p.epi == kEpiCol2im) {
-      // ---- Z[128 px][taps*nch] -> smem, then gather the transposed-conv outputs of the tile interior ----
-      float* Zs = reinterpret_cast<float*>(epi_buf);
+    if constexpr (EPI == kEpiCol2im) {
+      // ---- Z[128 px][taps*nch] -> smem (the stage ring is idle by now), then gather the transposed-conv
+      //      outputs of the tile interior ----
+      float* Zs = reinterpret_cast<float*>(smem);
       const int zcols = 25 * p.c2i_nch;
       mbar_wait(&acc_full[0], 0);
       tc_fence_after_sync();
-      for (int c = 0; c < p.n_chunks; ++c) {
+      for (int c = 0; c < nC; ++c) {
         float v[32];
         tmem_ld32(t_lane + c * 32, v);
         tmem_ld_wait();
@@ -205,121 +247,107 @@ __global__ void __launch_bounds__(192, 1) conv_tc_kernel(const __grid_constant__
         float* dst = p.c2i_out + (((int64_t)img * OH + 2 * gi + a) * OW + 2 * gj + b) * nch;
 #pragma unroll
         for (int c = 0; c < 4; ++c)
-          if (c < nch) dst[c] = acc[c] + (p.bias != nullptr ? __ldg(p.bias + c) : 0.f);
+          if (c < nch) dst[c] = acc[c] + sbias[c];
       }
     } else {
-      // staging: O[2] out | S[2] FWD scale out / BWD y_prev in | C[2] BWD sc_prev in, FWD x in | X[2] BWD x in
-      auto bufO = [&](int i) { return epi_buf + (0 + i) * kABytes; };
-      auto bufS = [&](int i) { return epi_buf + (2 + i) * kABytes; };
-      auto bufC = [&](int i) { return epi_buf + (4 + i) * kABytes; };
-      auto bufX = [&](int i) { return bwd ? epi_buf + (6 + i) * kABytes : epi_buf + (4 + i) * kABytes; };
-      const int n_loads = (p.acc_from_in ? 1 : 0) + (bwd ? 2 : 0);
-      int fetch_cnt = 0, use_cnt = 0, stores = 0;
+      // global operands of the epilogue (saved y / scale of the matching forward; stand-alone input) are read
+      // straight into registers: this thread's pixel, 128 contiguous bytes per 32-channel chunk
+      const int gi = i0 + row / kTW, gj = j0 + row % kTW;
+      const bool px_ok = gi < p.t_h && gj < p.t_w;
+      const int64_t pix = (((int64_t)img * p.o_h + p.o_s * gi + p.o_a) * p.o_w + p.o_s * gj + p.o_b) * p.n_ch;
+      // store staging aliases the stage ring (idle once the last MMA has completed): 16 KB regions
+      auto stg = [&](int i) -> uint8_t* {
+        return b_bytes >= static_cast<uint32_t>(kABytes) ? smem + (i >> 1) * p.stage_bytes + (i & 1) * kABytes
+                                                          : smem + i * p.stage_bytes;
+      };
+      int stores = 0;
 
-      auto issue_fetch = [&](int c) {   // TMA-load the global operands of chunk c (double buffered)
-        if (n_loads == 0) return;
-        const int b = fetch_cnt & 1;
-        if (leader) {
-          mbar_arrive_expect_tx(&ld_full[b], n_loads * kABytes);
-          if (p.acc_from_in) tma_load_4d(bufX(b), &p.a_map[0], &ld_full[b], c * 32, j0, i0, img);
-          if (bwd) {
-            tma_load_4d(bufS(b), &p.yprev_map, &ld_full[b], c * 32, j0, i0, img);
-            tma_load_4d(bufC(b), &p.scprev_map, &ld_full[b], c * 32, j0, i0, img);
-          }
-        }
-        __syncwarp();
-        ++fetch_cnt;
-      };
-      auto wait_fetch = [&]() -> int {
-        if (n_loads == 0) return 0;
-        const int b = use_cnt & 1;
-        mbar_wait(&ld_full[b], (use_cnt >> 1) & 1);
-        ++use_cnt;
-        return b;
-      };
-      auto load_acc1 = [&](int c, int b, float* v) {
-        if (p.acc_from_in) {
-          read_row32(bufX(b), row, v);
+      auto load_acc1 = [&](int c, float* v) {
+        if constexpr (FROM_IN) {
+          ldg_row32(p.xin + pix + c * 32, px_ok, v);
         } else {
           tmem_ld32(t_lane + c * 32, v);
           tmem_ld_wait();
         }
-        if (p.bias != nullptr) {
+        const float4* b4 = reinterpret_cast<const float4*>(sbias + c * 32);
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] += __ldg(p.bias + c * 32 + j);
+        for (int j = 0; j < 8; ++j) {
+          const float4 b = b4[j];
+          v[4 * j] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
         }
       };
-      // top of a storing chunk: staging O/S[c&1] (store of chunk c-2) and the load set of chunk c-1 are free after this
-      auto chunk_top = [&](int c, int n) {
-        if (leader && stores >= 2) tma_store_wait_read1();
-        __syncwarp();
-        named_bar_sync(1, 128);
-        if (c + 1 < n) issue_fetch(c + 1);
-      };
       auto store_chunk = [&](int c, const float* o, const float* o2) {  // o2: second output (scale) or null
-        const int sb = stores & 1;
+        const int sb = stores & 1;   // double-buffered staging: wait only for the store issued two chunks ago
+        uint8_t* bufO = stg(2 * sb);
+        uint8_t* bufS = stg(2 * sb + 1);
+        if (stores >= 2) {
+          if (leader) tma_store_wait_read1();
+          __syncwarp();
+          named_bar_sync(1, 128);
+        }
         if (p.round_out) {
           float r[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) r[j] = round_tf32(o[j]);
-          write_row32(bufO(sb), row, r);
+          write_row32(bufO, row, r);
         } else {
-          write_row32(bufO(sb), row, o);
+          write_row32(bufO, row, o);
         }
-        if (o2 != nullptr) write_row32(bufS(sb), row, o2);
+        if (o2 != nullptr) write_row32(bufS, row, o2);
         fence_proxy_async_smem();
         named_bar_sync(1, 128);
         if (leader) {
-          tma_store_4d(&p.out_map, bufO(sb), c * 32, j0, i0, img);
-          if (o2 != nullptr) tma_store_4d(&p.sc_map, bufS(sb), c * 32, j0, i0, img);
+          tma_store_4d(&p.out_map, bufO, c * 32, j0, i0, img);
+          if (o2 != nullptr) tma_store_4d(&p.sc_map, bufS, c * 32, j0, i0, img);
           tma_store_commit();
         }
         __syncwarp();
         ++stores;
       };
 
-      issue_fetch(0);   // overlaps the tail of the main loop
       if (main_kb > 0) {
         mbar_wait(&acc_full[0], 0);
         tc_fence_after_sync();
       }
+      if (leader) TC_STAMP(5);
 
-      if (!gdn) {
-        for (int c = 0; c < p.n_chunks; ++c) {
+      if constexpr (!gdn) {
+        for (int c = 0; c < nC; ++c) {
           float v[32];
-          chunk_top(c, p.n_chunks);
-          const int b = wait_fetch();
-          load_acc1(c, b, v);
+          load_acc1(c, v);
+          if (p.act == ICADV_ACT_RELU) {          // uniform branch outside the element loop (no per-element jump table)
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], p.act);
+            for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+          } else if (p.act == ICADV_ACT_LEAKY) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = v[j] > 0.f ? v[j] : 0.01f * v[j];
+          } else if (p.act == ICADV_ACT_ABS) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = fabsf(v[j]);
+          }
           store_chunk(c, v, nullptr);
         }
       } else {
         // ---- pass 1: build the A operand of the normalisation GEMM ----
-        for (int c = 0; c < p.n_chunks; ++c) {
+        for (int c = 0; c < nC; ++c) {
           float v[32], a2[32];
-          if (c + 1 < p.n_chunks) {
-            if (fetch_cnt >= 2) named_bar_sync(1, 128);   // load set of chunk c-1 fully consumed
-            issue_fetch(c + 1);
-          }
-          const int b = wait_fetch();
-          load_acc1(c, b, v);
-          if (!bwd) {
+          load_acc1(c, v);
+          if constexpr (!bwd) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) a2[j] = round_tf32(v[j] * v[j]);
           } else {
             float yv[32], sv[32];
-            read_row32(bufS(b), row, yv);
-            read_row32(bufC(b), row, sv);
-            if (p.epi == ICADV_EPI_GDN_BWD) {
+            ldg_row32(p.yprev + pix + c * 32, px_ok, yv);
+            ldg_row32(p.scprev + pix + c * 32, px_ok, sv);
+            if constexpr (EPI == ICADV_EPI_GDN_BWD) {
 #pragma unroll
               for (int j = 0; j < 32; ++j) a2[j] = round_tf32(v[j] * yv[j] * sv[j] * sv[j]);
             } else {
 #pragma unroll
               for (int j = 0; j < 32; ++j) {
-                // out-of-image rows are zero-filled (sc = 0): keep them finite
-                float s2 = sv[j] * sv[j];
-                a2[j] = s2 > 0.f ? round_tf32(v[j] * yv[j] / s2) : 0.f;
+                // pixels outside the image read as zeros (sc = 0): keep them finite
+                const float s2 = sv[j] * sv[j];
+                a2[j] = s2 > 0.f ? round_tf32(__fdividef(v[j] * yv[j], s2)) : 0.f;
               }
             }
           }
@@ -329,44 +357,48 @@ __global__ void __launch_bounds__(192, 1) conv_tc_kernel(const __grid_constant__
           fence_proxy_async_smem();
           mbar_arrive(&a2_ready[c]);
         }
+        if (leader) TC_STAMP(6);
         // ---- pass 2: normalise ----
-        if (n_loads > 0) {
-          named_bar_sync(1, 128);   // pass-1 reads of both load sets are complete
-          issue_fetch(0);
-        }
         mbar_wait(&acc_full[1], 0);
         tc_fence_after_sync();
-        for (int c = 0; c < p.n_chunks; ++c) {
+        if (leader) TC_STAMP(7);
+        for (int c = 0; c < nC; ++c) {
           float v[32], w[32];
-          chunk_top(c, p.n_chunks);
-          const int b = wait_fetch();
-          load_acc1(c, b, v);
+          load_acc1(c, v);
           tmem_ld32(t_lane + p.n_ch + c * 32, w);
           tmem_ld_wait();
-          if (!bwd) {
+          if constexpr (!bwd) {
             float sc[32];
+            const float4* be4 = reinterpret_cast<const float4*>(sbeta + c * 32);
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              float n = __ldg(p.beta + c * 32 + j) + w[j];
-              sc[j] = (p.epi == ICADV_EPI_GDN_FWD) ? rsqrtf(n) : sqrtf(n);
-              v[j] *= sc[j];
+            for (int j = 0; j < 8; ++j) {
+              const float4 be = be4[j];
+              const float nn[4] = {be.x + w[4 * j], be.y + w[4 * j + 1], be.z + w[4 * j + 2], be.w + w[4 * j + 3]};
+#pragma unroll
+              for (int t = 0; t < 4; ++t) {
+                const float r = rsqrtf(nn[t]);
+                sc[4 * j + t] = (EPI == ICADV_EPI_GDN_FWD) ? r : nn[t] * r;   // sqrt(n) = n * rsqrt(n)
+                v[4 * j + t] *= sc[4 * j + t];
+              }
             }
             store_chunk(c, v, sc);
           } else {
             float yv[32], sv[32];
-            read_row32(bufS(b), row, yv);
-            read_row32(bufC(b), row, sv);
-            const float sign = (p.epi == ICADV_EPI_GDN_BWD) ? -1.f : 1.f;
+            ldg_row32(p.yprev + pix + c * 32, px_ok, yv);
+            ldg_row32(p.scprev + pix + c * 32, px_ok, sv);
+            constexpr float sign = (EPI == ICADV_EPI_GDN_BWD) ? -1.f : 1.f;
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
-              float xs = sv[j] > 0.f ? yv[j] / sv[j] : 0.f;   // x = y / sc
+              const float xs = sv[j] > 0.f ? __fdividef(yv[j], sv[j]) : 0.f;   // x = y / sc
               v[j] = v[j] * sv[j] + sign * xs * w[j];
             }
             store_chunk(c, v, nullptr);
           }
         }
       }
+      if (leader) TC_STAMP(8);
       if (leader) tma_store_wait0();
+      if (leader) TC_STAMP(9);
       __syncwarp();
     }
   }
@@ -374,6 +406,26 @@ __global__ void __launch_bounds__(192, 1) conv_tc_kernel(const __grid_constant__
   tc_fence_before_sync();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem, p.tmem_cols);
+  if (threadIdx.x == 0) TC_STAMP(10);
+}
+
+typedef void (*TcKernelFn)(const TcParams);
+
+static TcKernelFn pick_kernel(int epi, int from_in) {
+  switch (epi * 2 + (from_in ? 1 : 0)) {
+    case ICADV_EPI_LINEAR * 2 + 0: return conv_tc_kernel<ICADV_EPI_LINEAR, false>;
+    case ICADV_EPI_LINEAR * 2 + 1: return conv_tc_kernel<ICADV_EPI_LINEAR, true>;
+    case ICADV_EPI_GDN_FWD * 2 + 0: return conv_tc_kernel<ICADV_EPI_GDN_FWD, false>;
+    case ICADV_EPI_GDN_FWD * 2 + 1: return conv_tc_kernel<ICADV_EPI_GDN_FWD, true>;
+    case ICADV_EPI_IGDN_FWD * 2 + 0: return conv_tc_kernel<ICADV_EPI_IGDN_FWD, false>;
+    case ICADV_EPI_IGDN_FWD * 2 + 1: return conv_tc_kernel<ICADV_EPI_IGDN_FWD, true>;
+    case ICADV_EPI_GDN_BWD * 2 + 0: return conv_tc_kernel<ICADV_EPI_GDN_BWD, false>;
+    case ICADV_EPI_GDN_BWD * 2 + 1: return conv_tc_kernel<ICADV_EPI_GDN_BWD, true>;
+    case ICADV_EPI_IGDN_BWD * 2 + 0: return conv_tc_kernel<ICADV_EPI_IGDN_BWD, false>;
+    case ICADV_EPI_IGDN_BWD * 2 + 1: return conv_tc_kernel<ICADV_EPI_IGDN_BWD, true>;
+    case kEpiCol2im * 2 + 0: return conv_tc_kernel<kEpiCol2im, false>;
+    default: return nullptr;
+  }
 }
 
 // ------------------------------------------------------------------------------------------ host
@@ -466,6 +518,7 @@ using namespace icadv;
 
 struct icadv_conv_plan {
   int n_launch;
+  TcKernelFn fn;
   TcParams params[4];
   dim3 grid[4];
   int smem_bytes[4];
@@ -568,8 +621,6 @@ int icadv_conv_plan_create(const icadv_conv_desc* d, icadv_conv_plan** out_plan)
     } else {
       rc = out_side(&p.out_map, d->out);
       if (!rc && gdn && !bwd) rc = out_side(&p.sc_map, d->out_scale);
-      if (!rc && bwd) rc = out_side(&p.yprev_map, d->y_prev);
-      if (!rc && bwd) rc = out_side(&p.scprev_map, d->sc_prev);
       if (!rc && !d->acc_from_in) {
         if (mode == kModeRgbIn) rc = encode_mat(&p.w_map, d->wpack, 32, 5 * N, N);   // [5 kh][N][32]
         else rc = encode_mat(&p.w_map, d->wpack, K, taps_total * N, N);
@@ -577,7 +628,7 @@ int icadv_conv_plan_create(const icadv_conv_desc* d, icadv_conv_plan** out_plan)
       if (!rc && gdn) rc = encode_mat(&p.g_map, d->gmat, N, N, N);
       if (rc) { delete plan; return rc; }
       if (!(gdn && !bwd)) p.sc_map = p.out_map;
-      if (!bwd) { p.yprev_map = p.out_map; p.scprev_map = p.out_map; }
+      p.yprev_map = p.out_map; p.scprev_map = p.out_map;
       if (d->acc_from_in) p.w_map = p.out_map;
       if (!gdn) p.g_map = p.out_map;
     }
@@ -606,22 +657,39 @@ int icadv_conv_plan_create(const icadv_conv_desc* d, icadv_conv_plan** out_plan)
     p.epi = mode == kModeCol2im ? kEpiCol2im : d->epi;
     p.act = d->act; p.acc_from_in = d->acc_from_in; p.round_out = d->round_out_tf32;
     p.stage_bytes = kABytes + N * 128;
-    p.epi_bufs = mode == kModeCol2im ? 3 : (bwd ? (d->acc_from_in ? 8 : 6) : (d->acc_from_in ? 6 : (gdn ? 4 : 2)));
-    int avail = kSmemLimit - 1024 - p.epi_bufs * kABytes - kBarBytes;
-    p.num_stages = avail / p.stage_bytes;
+    p.t_h = g.tile_h; p.t_w = g.tile_w; p.o_h = g.out_h; p.o_w = g.out_w;
+    if (d->form == ICADV_FORM_TCONV && s == 2) { p.o_s = 2; p.o_a = g.out_a[l]; p.o_b = g.out_b[l]; }
+    else { p.o_s = 1; p.o_a = 0; p.o_b = 0; }
+    p.yprev = d->y_prev; p.scprev = d->sc_prev; p.xin = d->in;
+    // aim for two CTAs per SM (their prologue/epilogue overlap each other's main loop): <= ~112 KB each
+    const int fixed = 1024 + kBarBytes;
+    int stages2 = (113 * 1024 - fixed) / p.stage_bytes;
+    const int need_stg = (N * 128 >= kABytes) ? 2 : 4;       // 16 KB staging regions the epilogue aliases
+    const bool two_ok = stages2 >= 3 && stages2 >= need_stg && (gdn ? 2 * N : N) <= 256;
+    p.num_stages = two_ok ? stages2 : (kSmemLimit - fixed) / p.stage_bytes;
+    if (two_ok && p.num_stages > 3) p.num_stages = 3 > need_stg ? 3 : need_stg;
     if (p.num_stages > kMaxStages) p.num_stages = kMaxStages;
-    if (p.num_stages < 2) { delete plan; set_error("conv_tc: not enough shared memory for n_ch=%d", N); return ICADV_EINVAL; }
+    if (p.num_stages < need_stg || p.num_stages < 2 ||
+        (mode == kModeCol2im && p.num_stages * p.stage_bytes < 128 * kZStride * 4)) {
+      delete plan; set_error("conv_tc: not enough shared memory for n_ch=%d", N); return ICADV_EINVAL;
+    }
     int cols = gdn ? 2 * N : N, pow2 = 32;
     while (pow2 < cols) pow2 <<= 1;
     p.tmem_cols = pow2;
     p.bias = d->bias; p.beta = d->beta; p.active = d->active; p.n_active = d->n_active;
     plan->grid[l] = dim3(p.tiles_x * p.tiles_y, d->n_img, 1);
-    plan->smem_bytes[l] = 1024 + p.num_stages * p.stage_bytes + p.epi_bufs * kABytes + kBarBytes;
+    plan->smem_bytes[l] = 1024 + p.num_stages * p.stage_bytes + kBarBytes;
   }
+  plan->fn = pick_kernel(plan->params[0].epi, d->acc_from_in);
+  if (plan->fn == nullptr) { delete plan; set_error("conv_tc: no kernel for epi=%d from_in=%d", d->epi, d->acc_from_in); return ICADV_EINVAL; }
   static std::once_flag attr_once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(attr_once, [] {
-    attr_err = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
+    for (int e = 0; e <= kEpiCol2im && attr_err == cudaSuccess; ++e)
+      for (int f = 0; f < 2 && attr_err == cudaSuccess; ++f) {
+        TcKernelFn fn = pick_kernel(e, f);
+        if (fn) attr_err = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
+      }
   });
   if (attr_err != cudaSuccess) {
     delete plan;
@@ -635,13 +703,20 @@ int icadv_conv_plan_create(const icadv_conv_desc* d, icadv_conv_plan** out_plan)
 int icadv_conv_plan_launch(const icadv_conv_plan* plan, icadv_stream_t stream) {
   ICADV_REQUIRE(plan != nullptr, "null plan");
   for (int l = 0; l < plan->n_launch; ++l) {
-    conv_tc_kernel<<<plan->grid[l], 192, plan->smem_bytes[l], as_stream(stream)>>>(plan->params[l]);
+    plan->fn<<<plan->grid[l], kThreads, plan->smem_bytes[l], as_stream(stream)>>>(plan->params[l]);
     ICADV_CUDA_TRY(cudaGetLastError());
   }
   return ICADV_OK;
 }
 
 int icadv_conv_plan_num_launches(const icadv_conv_plan* plan) { return plan ? plan->n_launch : 0; }
+
+/* developer profiling: per-CTA phase timestamps (16 x int64 per CTA of launch 0), NULL to disable */
+int icadv_conv_plan_set_debug(icadv_conv_plan* plan, long long* dbg) {
+  ICADV_REQUIRE(plan != nullptr, "null plan");
+  plan->params[0].dbg = dbg;
+  return ICADV_OK;
+}
 
 int icadv_conv_plan_destroy(icadv_conv_plan* plan) {
   delete plan;

@@ -101,6 +101,8 @@ int icadv_conv_plan_create(const icadv_conv_desc* d, icadv_conv_plan** plan);
 int icadv_conv_plan_launch(const icadv_conv_plan* plan, icadv_stream_t stream);
 int icadv_conv_plan_destroy(icadv_conv_plan* plan);
 int icadv_conv_plan_num_launches(const icadv_conv_plan* plan); /* kernels per icadv_conv_plan_launch */
+/* developer profiling: per-CTA phase timestamps (clock64; 16 slots per CTA of the plan's first launch) */
+int icadv_conv_plan_set_debug(icadv_conv_plan* plan, long long* dbg);
 int icadv_conv_tc(const icadv_conv_desc* d, icadv_stream_t stream); /* create + launch + destroy */
 int icadv_conv_tc_supported(const icadv_conv_desc* d);             /* 1 / 0 */
 

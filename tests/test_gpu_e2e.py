@@ -170,7 +170,8 @@ def test_attack_trajectory_matches_oracle(dev, model, quality, hw, n, steps):
             # contractions ~1e-3 of the elements sit within rounding of zero and flip, so loss_i tracks the fp32
             # oracle to ~1e-3 relative, not better (the reference's own cuDNN-TF32 GPU path has the same spread)
             assert abs(pli - loss_i) <= 2.5e-3 * max(loss_i, 1e-7) + 1e-9, (t, pli, loss_i)
-            assert abs(pl - loss) <= 1e-3 * abs(loss) + 1e-9, (t, pl, loss)
+            tol = 1e-3 if pb == 1 else 2.5e-3   # branch A: loss IS loss_i (see above)
+            assert abs(pl - loss) <= tol * abs(loss) + 1e-9, (t, pl, loss)
         if first_div is None:
             # same branch sequence: final metrics within tolerance
             assert abs(psnr(im_adv[i:i + 1], x[i:i + 1]) - psnr(o[0], x[i:i + 1])) < 0.05
