@@ -13,6 +13,8 @@
 // GDN epilogues append n_ch/32 extra K-blocks to the same smem ring: the A operand of those blocks
 // (x^2 forward, g*y*sc^2 backward) is written by the epilogue warps, the B operand (gamma / gamma^T)
 // arrives by TMA, and the product accumulates into a second TMEM region.
+#include <stdlib.h>
+
 #include <mutex>
 
 #include "icadv_common.cuh"
@@ -35,7 +37,7 @@ struct TcParams {
   int num_taps, k_chunks, n_ch, n_chunks;   // n_ch = MMA N; n_chunks = n_ch / 32
   int tiles_x, tiles_y, tile_step_y, tile_step_x, tile_off;
   int epi, act, acc_from_in, round_out, a_rank5;
-  int num_stages, stage_bytes, tmem_cols;
+  int num_stages, stage_bytes, tmem_cols, ld_bufs;
   int t_h, t_w, o_h, o_w, o_s, o_a, o_b;    // tile-space extent; output geometry: pixel (o_s*i + o_a, o_s*j + o_b)
   const float* yprev; const float* scprev; const float* xin;   // epilogue operands read with plain loads
   int c2i_in_h, c2i_in_w, c2i_nch;         // col2im: input extent, real output channels
@@ -44,6 +46,7 @@ struct TcParams {
   const float* beta;
   const int* active;
   const int* n_active;
+  int dbg_flags;    // developer switches (env ICADV_TC_DBG): 1 = no prefetch of saved y/scale, 2 = single-buffered stores
   long long* dbg;   // optional per-CTA phase timestamps (16 slots per CTA), developer profiling only
 };
 
@@ -104,11 +107,13 @@ __global__ void __launch_bounds__(kThreads, 2) conv_tc_kernel(const __grid_const
   const int i0 = ty * p.tile_step_y + p.tile_off, j0 = tx * p.tile_step_x + p.tile_off;
 
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + p.num_stages * p.stage_bytes);
+  uint8_t* ld_buf = smem + p.num_stages * p.stage_bytes;   // BWD: y_prev / sc_prev chunk staging (2 x 16 KB)
+  uint64_t* full = reinterpret_cast<uint64_t*>(ld_buf + p.ld_bufs * kABytes);
   uint64_t* empty = full + kMaxStages;
   uint64_t* acc_full = empty + kMaxStages;   // [2]
   uint64_t* a2_ready = acc_full + 2;         // [8]
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(a2_ready + 8);
+  uint64_t* ld_full = a2_ready + 8;          // [1]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(ld_full + 1);
   float* sbias = reinterpret_cast<float*>(full) + 64;   // [256] after the 256-byte barrier block
   float* sbeta = sbias + 256;                           // [256]
 
@@ -117,6 +122,7 @@ __global__ void __launch_bounds__(kThreads, 2) conv_tc_kernel(const __grid_const
     for (int s = 0; s < p.num_stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
     mbar_init(&acc_full[0], 1); mbar_init(&acc_full[1], 1);
     for (int c = 0; c < 8; ++c) mbar_init(&a2_ready[c], 128);
+    mbar_init(ld_full, 1);
     mbar_fence_init();
   }
   if (warp == 1) { tmem_alloc(tmem_ptr, p.tmem_cols); tmem_relinquish(); }
@@ -261,6 +267,38 @@ __global__ void __launch_bounds__(kThreads, 2) conv_tc_kernel(const __grid_const
                                                           : smem + i * p.stage_bytes;
       };
       int stores = 0;
+      uint32_t ld_cnt = 0;
+      uint8_t* ldY = ld_buf;
+      uint8_t* ldS = ld_buf + kABytes;
+      // BWD: saved y / scale chunks arrive by TMA (single staging pair; the next chunk is requested as soon as every
+      // thread has copied the current one into registers)
+      auto fetch = [&](int c) {
+        if (leader) {
+          mbar_arrive_expect_tx(ld_full, 2 * kABytes);
+          tma_load_4d(ldY, &p.yprev_map, ld_full, c * 32, j0, i0, img);
+          tma_load_4d(ldS, &p.scprev_map, ld_full, c * 32, j0, i0, img);
+        }
+        __syncwarp();
+      };
+      int cur_chunk = 0;
+      auto take = [&](float* yv, float* sv, int next) {   // next: chunk to request afterwards, or -1
+        if (p.dbg_flags & 1) { named_bar_sync(1, 128); fetch(cur_chunk); }
+        mbar_wait(ld_full, ld_cnt & 1);
+        ++ld_cnt;
+        read_row32(ldY, row, yv);
+        read_row32(ldS, row, sv);
+        // The staging pair is about to be overwritten through the async proxy: every shared-memory load above must
+        // have RETURNED (not merely issued) before this thread arrives.  One word of each 16-byte load feeds the
+        // barrier instruction, so the scoreboard holds the arrival until the data is in registers.
+        uint32_t dep = 0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) dep |= __float_as_uint(yv[4 * j]) | __float_as_uint(sv[4 * j]);
+        fence_proxy_async_smem();   // generic-proxy reads above vs the async-proxy (TMA) overwrite that follows
+        asm volatile("{\n.reg .b32 t;\nand.b32 t, %2, 0;\nadd.u32 t, t, %0;\nbar.sync t, %1;\n}" ::"r"(1u), "r"(128u), "r"(dep)
+                     : "memory");
+        if (p.dbg_flags & 1) { cur_chunk = next; } else if (next >= 0) fetch(next);
+      };
+      if constexpr (bwd) { if (!(p.dbg_flags & 1)) fetch(0); }   // overlaps the main loop
 
       auto load_acc1 = [&](int c, float* v) {
         if constexpr (FROM_IN) {
@@ -280,8 +318,8 @@ __global__ void __launch_bounds__(kThreads, 2) conv_tc_kernel(const __grid_const
         const int sb = stores & 1;   // double-buffered staging: wait only for the store issued two chunks ago
         uint8_t* bufO = stg(2 * sb);
         uint8_t* bufS = stg(2 * sb + 1);
-        if (stores >= 2) {
-          if (leader) tma_store_wait_read1();
+        if (stores >= 2 || ((p.dbg_flags & 2) && stores >= 1)) {
+          if (leader) { if (p.dbg_flags & 2) tma_store_wait_read0(); else tma_store_wait_read1(); }
           __syncwarp();
           named_bar_sync(1, 128);
         }
@@ -337,8 +375,7 @@ __global__ void __launch_bounds__(kThreads, 2) conv_tc_kernel(const __grid_const
             for (int j = 0; j < 32; ++j) a2[j] = round_tf32(v[j] * v[j]);
           } else {
             float yv[32], sv[32];
-            ldg_row32(p.yprev + pix + c * 32, px_ok, yv);
-            ldg_row32(p.scprev + pix + c * 32, px_ok, sv);
+            take(yv, sv, c + 1 < nC ? c + 1 : 0);   // after the last chunk: chunk 0 again, for pass 2
             if constexpr (EPI == ICADV_EPI_GDN_BWD) {
 #pragma unroll
               for (int j = 0; j < 32; ++j) a2[j] = round_tf32(v[j] * yv[j] * sv[j] * sv[j]);
@@ -384,8 +421,7 @@ __global__ void __launch_bounds__(kThreads, 2) conv_tc_kernel(const __grid_const
             store_chunk(c, v, sc);
           } else {
             float yv[32], sv[32];
-            ldg_row32(p.yprev + pix + c * 32, px_ok, yv);
-            ldg_row32(p.scprev + pix + c * 32, px_ok, sv);
+            take(yv, sv, c + 1 < nC ? c + 1 : -1);
             constexpr float sign = (EPI == ICADV_EPI_GDN_BWD) ? -1.f : 1.f;
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
@@ -621,6 +657,8 @@ int icadv_conv_plan_create(const icadv_conv_desc* d, icadv_conv_plan** out_plan)
     } else {
       rc = out_side(&p.out_map, d->out);
       if (!rc && gdn && !bwd) rc = out_side(&p.sc_map, d->out_scale);
+      if (!rc && bwd) rc = out_side(&p.yprev_map, d->y_prev);
+      if (!rc && bwd) rc = out_side(&p.scprev_map, d->sc_prev);
       if (!rc && !d->acc_from_in) {
         if (mode == kModeRgbIn) rc = encode_mat(&p.w_map, d->wpack, 32, 5 * N, N);   // [5 kh][N][32]
         else rc = encode_mat(&p.w_map, d->wpack, K, taps_total * N, N);
@@ -628,7 +666,7 @@ int icadv_conv_plan_create(const icadv_conv_desc* d, icadv_conv_plan** out_plan)
       if (!rc && gdn) rc = encode_mat(&p.g_map, d->gmat, N, N, N);
       if (rc) { delete plan; return rc; }
       if (!(gdn && !bwd)) p.sc_map = p.out_map;
-      p.yprev_map = p.out_map; p.scprev_map = p.out_map;
+      if (!bwd) { p.yprev_map = p.out_map; p.scprev_map = p.out_map; }
       if (d->acc_from_in) p.w_map = p.out_map;
       if (!gdn) p.g_map = p.out_map;
     }
@@ -661,11 +699,14 @@ int icadv_conv_plan_create(const icadv_conv_desc* d, icadv_conv_plan** out_plan)
     if (d->form == ICADV_FORM_TCONV && s == 2) { p.o_s = 2; p.o_a = g.out_a[l]; p.o_b = g.out_b[l]; }
     else { p.o_s = 1; p.o_a = 0; p.o_b = 0; }
     p.yprev = d->y_prev; p.scprev = d->sc_prev; p.xin = d->in;
+    p.dbg_flags = getenv("ICADV_TC_DBG") ? atoi(getenv("ICADV_TC_DBG")) : 0;
     // aim for two CTAs per SM (their prologue/epilogue overlap each other's main loop): <= ~112 KB each
-    const int fixed = 1024 + kBarBytes;
+    p.ld_bufs = bwd ? 2 : 0;
+    const int fixed = 1024 + kBarBytes + p.ld_bufs * kABytes;
     int stages2 = (113 * 1024 - fixed) / p.stage_bytes;
     const int need_stg = (N * 128 >= kABytes) ? 2 : 4;       // 16 KB staging regions the epilogue aliases
-    const bool two_ok = stages2 >= 3 && stages2 >= need_stg && (gdn ? 2 * N : N) <= 256;
+    const bool two_ok = stages2 >= 2 && stages2 >= need_stg && (gdn ? 2 * N : N) <= 256 &&
+                        !(getenv("ICADV_TC_ONE_CTA") != nullptr);
     p.num_stages = two_ok ? stages2 : (kSmemLimit - fixed) / p.stage_bytes;
     if (two_ok && p.num_stages > 3) p.num_stages = 3 > need_stg ? 3 : need_stg;
     if (p.num_stages > kMaxStages) p.num_stages = kMaxStages;
@@ -678,7 +719,7 @@ int icadv_conv_plan_create(const icadv_conv_desc* d, icadv_conv_plan** out_plan)
     p.tmem_cols = pow2;
     p.bias = d->bias; p.beta = d->beta; p.active = d->active; p.n_active = d->n_active;
     plan->grid[l] = dim3(p.tiles_x * p.tiles_y, d->n_img, 1);
-    plan->smem_bytes[l] = 1024 + p.num_stages * p.stage_bytes + kBarBytes;
+    plan->smem_bytes[l] = fixed + p.num_stages * p.stage_bytes;
   }
   plan->fn = pick_kernel(plan->params[0].epi, d->acc_from_in);
   if (plan->fn == nullptr) { delete plan; set_error("conv_tc: no kernel for epi=%d from_in=%d", d->epi, d->acc_from_in); return ICADV_EINVAL; }

@@ -365,3 +365,24 @@ def test_output_loss_matches_oracle(dev):
         loss.backward()
         torch.testing.assert_close(gx[n:n + 1], xr.grad, rtol=1e-6, atol=1e-9)
         assert abs(float(s[n]) / per - float(1.0 - loss)) < 1e-6
+
+
+def test_tc_backward_epilogue_is_deterministic(dev):
+    """Regression: the saved-y/scale staging is overwritten by TMA while other threads may still be reading it
+    unless a proxy fence + barrier separates them; outputs must be bit-identical run to run."""
+    from imagecompression_adversarial_b200 import _lib as L
+    from imagecompression_adversarial_b200 import ops
+    g = torch.Generator(device=dev).manual_seed(77)
+    C, n, H, W = 128, 4, 64, 96
+    gm = (0.1 * torch.eye(C, device=dev) + 0.01 * torch.rand(C, C, device=dev, generator=g)).contiguous()
+    x = torch.randn(n, H, W, C, device=dev, generator=g)
+    w = torch.randn(25, C, C, device=dev, generator=g) / 56
+    for form in (L.FORM_SCONV, L.FORM_TCONV):
+        oh, ow = ops.out_hw(form, 5, 2, H, W)
+        y = torch.randn(n, oh, ow, C, device=dev, generator=g)
+        sc = 0.5 + torch.rand(n, oh, ow, C, device=dev, generator=g)
+        for epi in (L.EPI_GDN_BWD, L.EPI_IGDN_BWD):
+            outs = [ops.conv(x, w, None, form=form, ksize=5, stride=2, n_ch=C, epi=epi, gmat=gm, y_prev=y, sc_prev=sc,
+                             path="tc") for _ in range(5)]
+            for o in outs[1:]:
+                assert torch.equal(o, outs[0])
