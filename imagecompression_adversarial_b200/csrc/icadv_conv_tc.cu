@@ -223,6 +223,7 @@ __global__ void __launch_bounds__(kThreads, 2) conv_tc_kernel(const __grid_const
       const int zcols = 25 * p.c2i_nch;
       mbar_wait(&acc_full[0], 0);
       tc_fence_after_sync();
+      if (leader) TC_STAMP(5);
       for (int c = 0; c < nC; ++c) {
         float v[32];
         tmem_ld32(t_lane + c * 32, v);
@@ -232,22 +233,26 @@ __global__ void __launch_bounds__(kThreads, 2) conv_tc_kernel(const __grid_const
           if (c * 32 + j < zcols) Zs[row * kZStride + c * 32 + j] = v[j];
       }
       named_bar_sync(1, 128);
+      if (leader) TC_STAMP(6);
       const int OH = 2 * p.c2i_in_h, OW = 2 * p.c2i_in_w, nch = p.c2i_nch;
-      const int cells = p.tile_step_y * p.tile_step_x;
-      for (int o = row; o < cells * 4; o += 128) {
+      constexpr int kIy = kTH - 2, kIx = kTW - 2;   // tile interior (6 x 14 input pixels)
+      for (int o = row; o < kIy * kIx * 4; o += 128) {
         const int cell = o >> 2, a = (o >> 1) & 1, b = o & 1;
-        const int ti = 1 + cell / p.tile_step_x, tj = 1 + cell % p.tile_step_x;
+        const int ti = 1 + cell / kIx, tj = 1 + cell % kIx;
         const int gi = i0 + ti, gj = j0 + tj;
         if (gi >= p.c2i_in_h || gj >= p.c2i_in_w) continue;
+        // taps kh = a + 2u, kw = b + 2v (u, v < 3; kh, kw < 5); source pixel (ti + 1 - u, tj + 1 - v)
         float acc[4] = {0.f, 0.f, 0.f, 0.f};
-        for (int kh = a; kh < 5; kh += 2) {
-          const int dh = (a + 2 - kh) / 2;
-          for (int kw = b; kw < 5; kw += 2) {
-            const int dw = (b + 2 - kw) / 2;
-            const float* z = Zs + ((ti + dh) * kTW + (tj + dw)) * kZStride + (kh * 5 + kw) * nch;
+#pragma unroll
+        for (int u = 0; u < 3; ++u) {
+#pragma unroll
+          for (int v = 0; v < 3; ++v) {
+            const int kh = a + 2 * u, kw = b + 2 * v;
+            const bool ok = kh < 5 && kw < 5;
+            const float* z = Zs + ((ti + 1 - u) * kTW + (tj + 1 - v)) * kZStride + (ok ? (kh * 5 + kw) * nch : 0);
 #pragma unroll
             for (int c = 0; c < 4; ++c)
-              if (c < nch) acc[c] += z[c];
+              if (c < nch) acc[c] += ok ? z[c] : 0.f;
           }
         }
         float* dst = p.c2i_out + (((int64_t)img * OH + 2 * gi + a) * OW + 2 * gj + b) * nch;
@@ -255,6 +260,7 @@ __global__ void __launch_bounds__(kThreads, 2) conv_tc_kernel(const __grid_const
         for (int c = 0; c < 4; ++c)
           if (c < nch) dst[c] = acc[c] + sbias[c];
       }
+      if (leader) TC_STAMP(8);
     } else {
       // global operands of the epilogue (saved y / scale of the matching forward; stand-alone input) are read
       // straight into registers: this thread's pixel, 128 contiguous bytes per 32-channel chunk
@@ -704,7 +710,7 @@ int icadv_conv_plan_create(const icadv_conv_desc* d, icadv_conv_plan** out_plan)
     p.ld_bufs = bwd ? 2 : 0;
     const int fixed = 1024 + kBarBytes + p.ld_bufs * kABytes;
     int stages2 = (113 * 1024 - fixed) / p.stage_bytes;
-    const int need_stg = (N * 128 >= kABytes) ? 2 : 4;       // 16 KB staging regions the epilogue aliases
+    const int need_stg = mode == kModeCol2im ? 2 : ((N * 128 >= kABytes) ? 2 : 4);   // stages the epilogue staging needs
     const bool two_ok = stages2 >= 2 && stages2 >= need_stg && (gdn ? 2 * N : N) <= 256 &&
                         !(getenv("ICADV_TC_ONE_CTA") != nullptr);
     p.num_stages = two_ok ? stages2 : (kSmemLimit - fixed) / p.stage_bytes;

@@ -63,3 +63,10 @@ gin = torch.empty_like(x2)
 d = ops.make_desc(g2, w2, None, gin, form=L.FORM_TCONV, ksize=5, stride=2, n_ch=128, epi=L.EPI_GDN_BWD, gmat=gm,
                   y_prev=out, sc_prev=sc)
 run("g_a.2 dgrad phase(0,0) + GDN bwd", d, (g2, w2, gin), 192 * n)
+# col2im last layer
+x5 = torch.randn(n, H // 2, W // 2, 128, device=dev)
+w5 = torch.randn(25, 3, 128, device=dev) / 30
+o5 = torch.empty(n, H, W, 3, device=dev)
+b5 = torch.zeros(3, device=dev)
+d = ops.make_desc(x5, w5, b5, o5, form=L.FORM_TCONV, ksize=5, stride=2, n_ch=3)
+run("g_s.6 col2im", d, (x5, w5, o5, b5), 1204 * n)
