@@ -62,7 +62,7 @@ _SIGS = {
     "icadv_perturb_forward": (C.c_int, [_fp, _fp, _fp, _fp, C.POINTER(PerturbState), C.c_int, C.c_int64, C.c_float,
                                         C.c_float, C.c_int, C.c_double, C.c_double, C.c_int, C.c_double, C.c_double,
                                         C.c_void_p]),
-    "icadv_perturb_update_adam": (C.c_int, [_fp, _fp, _fp, _fp, _fp, C.POINTER(PerturbState), C.c_int, C.c_int64,
+    "icadv_perturb_update_adam": (C.c_int, [_fp, _fp, _fp, _fp, _fp, _fp, C.POINTER(PerturbState), C.c_int, C.c_int64,
                                             C.c_float, C.c_double, C.c_double, C.c_double, C.c_float, C.c_float,
                                             C.c_void_p]),
     "icadv_ifgsm_update": (C.c_int, [_fp, _fp, _fp, C.c_int64, C.c_float, C.c_float, C.c_void_p]),
@@ -80,6 +80,9 @@ _SIGS = {
     "icadv_ssim_workspace_floats": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
     "icadv_ssim_level": (C.c_int, [_fp, _fp, _fp, _fp, _fp, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float), C.c_int,
                                    C.c_int, C.c_float, C.c_float, C.c_void_p]),
+    "icadv_ssim_level_backward": (C.c_int, [_fp, _fp, _fp, _fp, _fp, _fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                            C.c_int, C.c_int, C.POINTER(C.c_float), C.c_int, C.c_float, C.c_float,
+                                            C.c_void_p]),
     "icadv_avgpool2": (C.c_int, [_fp, _fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "icadv_sum_sqdiff": (C.c_int, [_fp, _fp, _fp, _fp, C.c_int, C.c_int64, C.c_void_p]),
 }

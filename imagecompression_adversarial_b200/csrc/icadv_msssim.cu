@@ -113,6 +113,116 @@ __global__ void avgpool2_kernel(const float* __restrict__ x, float* __restrict__
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------
+// Backward of one MS-SSIM level (variant 1, valid separable window) with respect to X.
+//   value_l[plane] = mean_px map(X, Y),  map = cs (levels 0..3) or ssim (last level)
+//   dX = coef_cs[plane] * d(sum cs)/dX + coef_ss[plane] * d(sum ssim)/dX + 0.25 * dXnext[pool parent]
+// One block produces a 32x32 tile of dX.  The filtered statistics are RECOMPUTED from a 52x52 input tile (no
+// saved maps): forward separable filter on 5 maps -> A12, A11, B on a 42x42 tile -> transposed separable filter.
+//   cs   = (2 s12 + C2) / (s11 + s22 + C2),   ssim = lum * cs,   lum = (2 mu1 mu2 + C1) / (mu1^2 + mu2^2 + C1)
+//   dX = Y * Gt[A12] + 2 X * Gt[A11] + Gt[B],   A12 = a 2/D,  A11 = -a cs/D,  B = -mu2 A12 - 2 mu1 A11 (+ lum term)
+// ---------------------------------------------------------------------------------------------------------
+constexpr int kBT = 32;                 // dX tile edge
+constexpr int kBA = kBT + kMaxWin - 1;  // 42: tile of the statistics maps
+constexpr int kBX = kBA + kMaxWin - 1;  // 52: input tile
+
+struct SsimBwdParams {
+  const float* X; const float* Y; const float* coef_cs; const float* coef_ss; const float* dXnext; float* dX;
+  int h, w, oh, ow, win, nh, nw, ph, pw;
+  float c1, c2;
+  float taps[kMaxWin];
+};
+
+__global__ void __launch_bounds__(256) ssim_level_bwd_kernel(const SsimBwdParams p) {
+  extern __shared__ float sm[];
+  float (*sx)[kBX + 1] = reinterpret_cast<float (*)[kBX + 1]>(sm);                       // [52][53]
+  float (*sy)[kBX + 1] = reinterpret_cast<float (*)[kBX + 1]>(sm + kBX * (kBX + 1));
+  float* hbase = sm + 2 * kBX * (kBX + 1);                                               // h5[5][52][43]
+  auto h5 = [&](int m, int r, int c) -> float& { return hbase[(m * kBX + r) * (kBA + 1) + c]; };
+  float* abase = hbase + 5 * kBX * (kBA + 1);                                            // a3[3][42][43]
+  auto a3 = [&](int m, int r, int c) -> float& { return abase[(m * kBA + r) * (kBA + 1) + c]; };
+  float* tbase = abase + 3 * kBA * (kBA + 1);                                            // ha[3][42][33]
+  auto ha = [&](int m, int r, int c) -> float& { return tbase[(m * kBA + r) * (kBT + 1) + c]; };
+
+  const int plane = blockIdx.z;
+  const int ty0 = blockIdx.y * kBT, tx0 = blockIdx.x * kBT;
+  const int R = p.win - 1;
+  const float* X = p.X + (int64_t)plane * p.h * p.w;
+  const float* Y = p.Y + (int64_t)plane * p.h * p.w;
+  const float ccs = p.coef_cs[plane], css = p.coef_ss[plane];
+  const int xs = kBT + 2 * R, as = kBT + R;   // used extents (52 / 42 for win = 11)
+  for (int i = threadIdx.x; i < xs * xs; i += 256) {
+    const int r = i / xs, c = i % xs;
+    const int gy = ty0 - R + r, gx = tx0 - R + c;
+    float a = 0.f, b = 0.f;
+    if (gy >= 0 && gy < p.h && gx >= 0 && gx < p.w) { a = __ldg(X + (int64_t)gy * p.w + gx); b = __ldg(Y + (int64_t)gy * p.w + gx); }
+    sx[r][c] = a; sy[r][c] = b;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < xs * as; i += 256) {   // horizontal forward filter
+    const int r = i / as, c = i % as;
+    float m1 = 0.f, m2 = 0.f, s11 = 0.f, s22 = 0.f, s12 = 0.f;
+    for (int k = 0; k < p.win; ++k) {
+      const float g = p.taps[k], a = sx[r][c + k], b = sy[r][c + k];
+      m1 = fmaf(g, a, m1); m2 = fmaf(g, b, m2);
+      s11 = fmaf(g, a * a, s11); s22 = fmaf(g, b * b, s22); s12 = fmaf(g, a * b, s12);
+    }
+    h5(0, r, c) = m1; h5(1, r, c) = m2; h5(2, r, c) = s11; h5(3, r, c) = s22; h5(4, r, c) = s12;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < as * as; i += 256) {   // vertical forward filter + per-position coefficients
+    const int r = i / as, c = i % as;
+    const int oy = ty0 - R + r, ox = tx0 - R + c;      // position in the valid statistics map
+    float A12 = 0.f, A11 = 0.f, B = 0.f;
+    if (oy >= 0 && oy < p.oh && ox >= 0 && ox < p.ow) {
+      float m1 = 0.f, m2 = 0.f, s11 = 0.f, s22 = 0.f, s12 = 0.f;
+      for (int k = 0; k < p.win; ++k) {
+        const float g = p.taps[k];
+        m1 = fmaf(g, h5(0, r + k, c), m1); m2 = fmaf(g, h5(1, r + k, c), m2);
+        s11 = fmaf(g, h5(2, r + k, c), s11); s22 = fmaf(g, h5(3, r + k, c), s22); s12 = fmaf(g, h5(4, r + k, c), s12);
+      }
+      const float m11 = m1 * m1, m22 = m2 * m2, m12 = m1 * m2;
+      const float v1 = s11 - m11, v2 = s22 - m22, v12 = s12 - m12;
+      const float D = v1 + v2 + p.c2, cs = (2.f * v12 + p.c2) / D;
+      const float Dl = m11 + m22 + p.c1, lum = (2.f * m12 + p.c1) / Dl;
+      const float a_cs = ccs + css * lum;               // upstream weight on the cs factor
+      A12 = a_cs * 2.f / D;
+      A11 = -a_cs * cs / D;
+      B = -m2 * A12 - 2.f * m1 * A11 + css * cs * 2.f * (m2 - lum * m1) / Dl;
+    }
+    a3(0, r, c) = A12; a3(1, r, c) = A11; a3(2, r, c) = B;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < as * kBT; i += 256) {  // horizontal transposed filter
+    const int r = i / kBT, c = i % kBT;
+    float t0 = 0.f, t1 = 0.f, t2 = 0.f;
+    for (int k = 0; k < p.win; ++k) {
+      const float g = p.taps[k];
+      t0 = fmaf(g, a3(0, r, c + R - k), t0); t1 = fmaf(g, a3(1, r, c + R - k), t1); t2 = fmaf(g, a3(2, r, c + R - k), t2);
+    }
+    ha(0, r, c) = t0; ha(1, r, c) = t1; ha(2, r, c) = t2;
+  }
+  __syncthreads();
+  float* out = p.dX + (int64_t)plane * p.h * p.w;
+  for (int i = threadIdx.x; i < kBT * kBT; i += 256) { // vertical transposed filter + combine
+    const int r = i / kBT, c = i % kBT;
+    const int gy = ty0 + r, gx = tx0 + c;
+    if (gy >= p.h || gx >= p.w) continue;
+    float t0 = 0.f, t1 = 0.f, t2 = 0.f;
+    for (int k = 0; k < p.win; ++k) {
+      const float g = p.taps[k];
+      t0 = fmaf(g, ha(0, r + R - k, c), t0); t1 = fmaf(g, ha(1, r + R - k, c), t1); t2 = fmaf(g, ha(2, r + R - k, c), t2);
+    }
+    float d = sy[r + R][c + R] * t0 + 2.f * sx[r + R][c + R] * t1 + t2;
+    if (p.dXnext != nullptr) {
+      const int py = (gy + p.ph) >> 1, px = (gx + p.pw) >> 1;
+      if (py < p.nh && px < p.nw) d += 0.25f * __ldg(p.dXnext + ((int64_t)plane * p.nh + py) * p.nw + px);
+    }
+    out[(int64_t)gy * p.w + gx] = d;
+  }
+}
+
 }  // namespace icadv
 
 using namespace icadv;
@@ -154,6 +264,30 @@ int icadv_avgpool2(const float* x, float* y, int planes, int h, int w, int pad_h
   int64_t blocks = (total + 255) / 256;
   if (blocks > 148 * 16) blocks = 148 * 16;
   avgpool2_kernel<<<(int)blocks, 256, 0, as_stream(stream)>>>(x, y, planes, h, w, oh, ow, pad_h, pad_w);
+  ICADV_CUDA_TRY(cudaGetLastError());
+  return ICADV_OK;
+}
+
+int icadv_ssim_level_backward(const float* X, const float* Y, const float* coef_cs, const float* coef_ss,
+                              const float* dXnext, float* dX, int planes, int h, int w, int next_h, int next_w,
+                              int pad_h, int pad_w, const float* win_taps_host, int win, float c1, float c2,
+                              icadv_stream_t stream) {
+  ICADV_REQUIRE(X && Y && coef_cs && coef_ss && dX && win_taps_host, "null pointer");
+  ICADV_REQUIRE(win >= 1 && win <= kMaxWin && h >= win && w >= win, "bad window / image size");
+  SsimBwdParams p;
+  p.X = X; p.Y = Y; p.coef_cs = coef_cs; p.coef_ss = coef_ss; p.dXnext = dXnext; p.dX = dX;
+  p.h = h; p.w = w; p.oh = h - win + 1; p.ow = w - win + 1; p.win = win;
+  p.nh = next_h; p.nw = next_w; p.ph = pad_h; p.pw = pad_w; p.c1 = c1; p.c2 = c2;
+  for (int k = 0; k < kMaxWin; ++k) p.taps[k] = k < win ? win_taps_host[k] : 0.f;
+  const size_t smem = sizeof(float) * (2 * kBX * (kBX + 1) + 5 * kBX * (kBA + 1) + 3 * kBA * (kBA + 1) + 3 * kBA * (kBT + 1));
+  static bool attr_done = false;
+  if (!attr_done) {
+    ICADV_CUDA_TRY(cudaFuncSetAttribute(ssim_level_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_done = true;
+  }
+  dim3 grid((w + kBT - 1) / kBT, (h + kBT - 1) / kBT, planes);
+  ICADV_REQUIRE(planes <= 65535 && grid.y <= 65535, "grid too large");
+  ssim_level_bwd_kernel<<<grid, 256, smem, as_stream(stream)>>>(p);
   ICADV_CUDA_TRY(cudaGetLastError());
   return ICADV_OK;
 }

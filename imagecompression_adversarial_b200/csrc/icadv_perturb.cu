@@ -116,7 +116,8 @@ __device__ __forceinline__ float adam_step(float& z, float& m, float& v, float g
 }
 
 __global__ void __launch_bounds__(256) perturb_update_adam_kernel(const float4* __restrict__ im_s, float4* noise,
-                                                                  const float4* __restrict__ g_in, float4* m4,
+                                                                  const float4* __restrict__ g_in,
+                                                                  const float4* __restrict__ g_a_ext, float4* m4,
                                                                   float4* v4, icadv_perturb_state st,
                                                                   int64_t per_img4, float eps, AdamCoef coef,
                                                                   float gradA_scale, float gradB_scale) {
@@ -131,6 +132,9 @@ __global__ void __launch_bounds__(256) perturb_update_adam_kernel(const float4* 
     if (br) {
       const float4 gi = __ldg(g_in + base + i);
       g = make_float4(gi.x * gradB_scale, gi.y * gradB_scale, gi.z * gradB_scale, gi.w * gradB_scale);
+    } else if (g_a_ext != nullptr) {   // budget branch with an externally computed gradient (1 - ms_ssim)
+      const float4 gi = __ldg(g_a_ext + base + i);
+      g = make_float4(gi.x * gradA_scale, gi.y * gradA_scale, gi.z * gradA_scale, gi.w * gradA_scale);
     } else {
       // loss = mean((im_s - im_in)^2): d/d im_in = 2 (im_in - im_s) / P
       g.x = 2.f * (clampf(s.x + clampf(z.x, -eps, eps), 0.f, 1.f) - s.x) * gradA_scale;
@@ -269,7 +273,8 @@ int icadv_perturb_forward(const float* im_s, const float* noise, float* im_in, f
   return ICADV_OK;
 }
 
-int icadv_perturb_update_adam(const float* im_s, float* noise, const float* g_in, float* m, float* v,
+int icadv_perturb_update_adam(const float* im_s, float* noise, const float* g_in, const float* g_a_ext, float* m,
+                              float* v,
                               const icadv_perturb_state* st, int n_img, int64_t per_img, float eps, double beta1,
                               double beta2, double adam_eps, float gradA_scale, float gradB_scale,
                               icadv_stream_t stream) {
@@ -280,7 +285,8 @@ int icadv_perturb_update_adam(const float* im_s, float* noise, const float* g_in
   coef.omb1 = (float)(1.0 - beta1); coef.b2 = (float)beta2; coef.omb2 = (float)(1.0 - beta2); coef.eps = (float)adam_eps;
   perturb_update_adam_kernel<<<grid, 256, 0, as_stream(stream)>>>(
       reinterpret_cast<const float4*>(im_s), reinterpret_cast<float4*>(noise),
-      reinterpret_cast<const float4*>(g_in), reinterpret_cast<float4*>(m), reinterpret_cast<float4*>(v), *st,
+      reinterpret_cast<const float4*>(g_in), reinterpret_cast<const float4*>(g_a_ext), reinterpret_cast<float4*>(m),
+      reinterpret_cast<float4*>(v), *st,
       per_img / 4, eps, coef, gradA_scale, gradB_scale);
   ICADV_CUDA_TRY(cudaGetLastError());
   return ICADV_OK;

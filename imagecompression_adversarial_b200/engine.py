@@ -21,8 +21,11 @@ class AttackEngine:
     def __init__(self, net, n_img, height, width, *, steps, epsilon=16.0, noise_budget=1e-4, lr_attack=0.01,
                  clamp=True, att_metric="L2", force_branch=-1, use_graph=True, device=None):
         ops.require_device()
-        if att_metric != "L2":
-            raise L.IcadvError("AttackEngine: only -att_metric L2 is on the fused path so far")
+        if att_metric not in ("L2", "ms-ssim"):
+            raise L.IcadvError(f"AttackEngine: -att_metric {att_metric} is not supported (L2, ms-ssim)")
+        self.att_metric = att_metric
+        if att_metric == "ms-ssim":
+            use_graph = False   # the MS-SSIM composition allocates its pyramid per call; runs eagerly for now
         if steps < 3:
             raise ZeroDivisionError("integer division or modulo by zero")  # attack_rd.py:553 with steps//3 == 0
         dev = device or next(net.parameters()).device
@@ -52,12 +55,18 @@ class AttackEngine:
         assert self.x_out.shape == self.im_s.shape, (self.x_out.shape, self.im_s.shape)
         self._graph = None
         self.iterations_done = 0
+        self.im_s_nchw = self.output_s_nchw = None
+        self.last_loss_A = f(n_img)   # loss of the budget branch per image (loss_i, or 1 - ms_ssim(im_s, im_in))
+        self.last_loss_B = f(n_img)   # loss of the network branch per image (1 - MSE, or ms_ssim(out, output_s))
 
     # ------------------------------------------------------------------ state
     def load(self, im_s_nchw, output_s_nchw, noise_init_nchw=None):
         """Start a new attack on a batch: copies inputs in, zeroes the perturbation and Adam state."""
         self.im_s.copy_(im_s_nchw.permute(0, 2, 3, 1))
         self.output_s.copy_(output_s_nchw.permute(0, 2, 3, 1))
+        if self.att_metric == "ms-ssim":
+            self.im_s_nchw = im_s_nchw.detach().contiguous().clone()
+            self.output_s_nchw = output_s_nchw.detach().contiguous().clone()
         if noise_init_nchw is None:
             self.noise.zero_()
         else:
@@ -73,6 +82,8 @@ class AttackEngine:
 
     # ------------------------------------------------------------------ one iteration
     def _iteration(self):
+        if self.att_metric == "ms-ssim":
+            return self._iteration_msssim()
         ops.perturb_forward(self.im_s, self.noise, self.im_in, self.st, eps=self.eps, budget=self.budget,
                             force_branch=self.force_branch, lr0=self.lr0, lr_gamma=0.33,
                             sched_period=self.steps // 3)
@@ -84,6 +95,37 @@ class AttackEngine:
         self.ga.backward()
         ops.perturb_update_adam(self.im_s, self.noise, self.ga.g_in, self.m, self.v, self.st, eps=self.eps,
                                 gradA_scale=1.0 / self.per_img, gradB_scale=1.0)
+
+    def _iteration_msssim(self):
+        """-att_metric ms-ssim (attack_rd.py:335-336, 360-362): budget branch loss = 1 - ms_ssim(im_s, im_in),
+        network branch loss = ms_ssim(output_, output_s); the branch test itself stays on the L2 budget (:333-334)."""
+        from . import metrics
+        ops.perturb_forward(self.im_s, self.noise, self.im_in, self.st, eps=self.eps, budget=self.budget,
+                            force_branch=self.force_branch, lr0=self.lr0, lr_gamma=0.33,
+                            sched_period=self.steps // 3)
+        ones = torch.ones(self.n_img, device=self.device)
+        ms_a, g_a = metrics.ms_ssim_value_and_grad(ops.nhwc_to_nchw(self.im_in), self.im_s_nchw, -ones)
+        g_a_nhwc = ops.nchw_to_nhwc(g_a)
+        self.last_loss_A = 1.0 - ms_a
+        self.ga.forward()
+        self.gs.forward()
+        x = self.x_out
+        if self.clamp:
+            lo = ops.bound_forward(x.view(-1), 0.0, False)
+            out = ops.bound_forward(lo, 1.0, True).view_as(x)
+        else:
+            out = x
+        ms_b, g_o = metrics.ms_ssim_value_and_grad(ops.nhwc_to_nchw(out), self.output_s_nchw, ones)
+        g = ops.nchw_to_nhwc(g_o).view(-1)
+        if self.clamp:
+            g = ops.bound_backward(lo, g, 1.0, True)
+            g = ops.bound_backward(x.view(-1), g, 0.0, False)
+        self.g_x.copy_(g.view_as(self.g_x))
+        self.last_loss_B = ms_b
+        self.gs.backward()
+        self.ga.backward()
+        ops.perturb_update_adam(self.im_s, self.noise, self.ga.g_in, self.m, self.v, self.st, eps=self.eps,
+                                gradA_scale=1.0, gradB_scale=1.0, g_a_ext=g_a_nhwc)
 
     def kernels_per_iteration(self):
         fa, ba = self.ga.n_kernels()
@@ -101,8 +143,12 @@ class AttackEngine:
             else:
                 self._iteration()
             if record is not None:
-                loss_o = 1.0 - self.loss_o_sum / self.per_img
-                record.append((self.st.branch.cpu().clone(), self.st.loss_i.cpu().clone(), loss_o.cpu().clone()))
+                if self.att_metric == "L2":
+                    self.last_loss_A = self.st.loss_i
+                    self.last_loss_B = 1.0 - self.loss_o_sum / self.per_img
+                br = self.st.branch.cpu().clone()
+                loss = torch.where(br == 1, self.last_loss_B.cpu(), self.last_loss_A.cpu())
+                record.append((br, self.st.loss_i.cpu().clone(), loss))
             self.iterations_done += 1
 
     def _capture(self):

@@ -64,6 +64,51 @@ def ms_ssim(X, Y, data_range=1.0, size_average=True, win_size=11, win_sigma=1.5,
     return val.mean() if size_average else val.mean(1)
 
 
+def _level_bwd(X, Y, coef_cs, coef_ss, dXnext, pads, taps, c1, c2):
+    n, c, h, w = X.shape
+    dX = torch.empty_like(X)
+    nh, nw = (dXnext.shape[2], dXnext.shape[3]) if dXnext is not None else (0, 0)
+    arr = (C.c_float * len(taps))(*taps)
+    L.call("icadv_ssim_level_backward", _p(X), _p(Y), _p(coef_cs), _p(coef_ss), _p(dXnext), _p(dX), n * c, h, w, nh, nw,
+           pads[0], pads[1], arr, len(taps), float(c1), float(c2), _stream())
+    return dX
+
+
+def ms_ssim_value_and_grad(X, Y, upstream, data_range=1.0, win_size=11, win_sigma=1.5, weights=WEIGHTS, K=(0.01, 0.03)):
+    """Per-image MS-SSIM (variant 1, mean over channels) and the gradient of ``sum_b upstream[b] * value[b]`` with
+    respect to X.  This is what autograd of ``ms_ssim(X, Y)`` delivers in attack_rd.py:336,362, one image per row."""
+    assert X.shape == Y.shape and X.dim() == 4 and min(X.shape[-2:]) > (win_size - 1) * 2 ** 4
+    X, Y = X.detach().contiguous().float(), Y.detach().contiguous().float()
+    B, Cc = X.shape[0], X.shape[1]
+    taps = _taps(win_size, win_sigma)
+    c1, c2 = (K[0] * data_range) ** 2, (K[1] * data_range) ** 2
+    nl = len(weights)
+    xs, ys, pads, vals, npx = [X], [Y], [], [], []
+    for lvl in range(nl):
+        ss, cs = _level(xs[-1], ys[-1], taps, False, c1, c2)
+        vals.append(torch.relu(cs if lvl < nl - 1 else ss))
+        npx.append((xs[-1].shape[2] - win_size + 1) * (xs[-1].shape[3] - win_size + 1))
+        if lvl < nl - 1:
+            ph, pw = xs[-1].shape[2] % 2, xs[-1].shape[3] % 2
+            pads.append((ph, pw))
+            xs.append(_pool(xs[-1], ph, pw))
+            ys.append(_pool(ys[-1], ph, pw))
+    w = torch.tensor(weights, device=X.device, dtype=torch.float32).view(-1, 1, 1)
+    V = torch.stack(vals, 0)                       # [levels, B, C]
+    P = torch.prod(V ** w, dim=0)                  # [B, C]
+    value = P.mean(1)
+    dP = (upstream.view(B, 1).to(torch.float32) / Cc).expand(B, Cc)
+    dV = torch.where(V > 0, dP.unsqueeze(0) * w * P.unsqueeze(0) / V.clamp(min=1e-30), torch.zeros_like(V))
+    zero = torch.zeros(B * Cc, device=X.device, dtype=torch.float32)
+    dnext = None
+    for lvl in range(nl - 1, -1, -1):
+        coef = (dV[lvl] / npx[lvl]).reshape(-1).contiguous()
+        last = lvl == nl - 1
+        dnext = _level_bwd(xs[lvl], ys[lvl], zero if last else coef, coef if last else zero, dnext,
+                           pads[lvl] if lvl < nl - 1 else (0, 0), taps, c1, c2)
+    return value, dnext
+
+
 class MS_SSIM(torch.nn.Module):
     """pytorch_msssim.MS_SSIM(data_range=1, size_average=True, channel=3)."""
 

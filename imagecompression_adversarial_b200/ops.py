@@ -240,9 +240,9 @@ def perturb_forward(im_s, noise, im_in, st, *, eps, budget, force_branch=-1, lr0
 
 
 def perturb_update_adam(im_s, noise, g_in, m, v, st, *, eps, beta1=0.9, beta2=0.999, adam_eps=1e-8, gradA_scale,
-                        gradB_scale=1.0):
+                        gradB_scale=1.0, g_a_ext=None):
     per_img = im_s[0].numel()
-    L.call("icadv_perturb_update_adam", _p(im_s), _p(noise), _p(g_in), _p(m), _p(v), C.byref(st.c), st.n_img, per_img,
+    L.call("icadv_perturb_update_adam", _p(im_s), _p(noise), _p(g_in), _p(g_a_ext), _p(m), _p(v), C.byref(st.c), st.n_img, per_img,
            float(eps), float(beta1), float(beta2), float(adam_eps), float(gradA_scale), float(gradB_scale), _stream())
 
 

@@ -168,8 +168,10 @@ int icadv_perturb_forward(const float* im_s, const float* noise, float* im_in, f
 
 /* Backward of the two clamp pairs (custom Low/Up_bound rule) + Adam on the perturbation, fused.
  * Branch A forms d loss_i / d im_in in-kernel (x gradA_scale = 1/per_img); branch B reads g_in =
- * dLoss/d im_in from the network backward (x gradB_scale). */
-int icadv_perturb_update_adam(const float* im_s, float* noise, const float* g_in, float* m, float* v,
+ * dLoss/d im_in from the network backward (x gradB_scale).  g_a_ext (nullable): externally computed branch-A
+ * gradient (att_metric ms-ssim: d(1 - ms_ssim(im_s, im_in))/d im_in, attack_rd.py:336), x gradA_scale. */
+int icadv_perturb_update_adam(const float* im_s, float* noise, const float* g_in, const float* g_a_ext, float* m,
+                              float* v,
                               const icadv_perturb_state* st, int n_img, int64_t per_img, float eps,
                               double beta1, double beta2, double adam_eps, float gradA_scale,
                               float gradB_scale, icadv_stream_t stream);
@@ -228,6 +230,14 @@ int icadv_ssim_workspace_floats(int planes, int h, int w, int win, int same_pad)
 int icadv_ssim_level(const float* X, const float* Y, float* ws, float* ssim_sum, float* cs_sum, int planes,
                      int h, int w, const float* win_taps_host, int win, int same_pad, float c1, float c2,
                      icadv_stream_t stream);
+/* Backward of one level (variant 1) w.r.t. X.  coef_cs / coef_ss [planes]: upstream weights on the per-plane SUMS of
+ * the cs / ssim maps; dXnext (nullable): gradient w.r.t. the 2x2-average-pooled next level, folded in.  Statistics are
+ * recomputed in shared memory (nothing saved by the forward).  Used by the ms-ssim attack metric
+ * (attack_rd.py:336,362 under autograd). */
+int icadv_ssim_level_backward(const float* X, const float* Y, const float* coef_cs, const float* coef_ss,
+                              const float* dXnext, float* dX, int planes, int h, int w, int next_h, int next_w,
+                              int pad_h, int pad_w, const float* win_taps_host, int win, float c1, float c2,
+                              icadv_stream_t stream);
 /* F.avg_pool2d(x, 2, stride 2, padding (pad_h, pad_w)) between levels */
 int icadv_avgpool2(const float* x, float* y, int planes, int h, int w, int pad_h, int pad_w,
                    icadv_stream_t stream);

@@ -144,14 +144,34 @@ def test_stack_input_gradient_matches_oracle_autograd(dev):
     assert abs(pl - ol_) < 3e-3 * abs(ol_)   # raw (unclamped) MSE against a random target: TF32 bound
 
 
-@pytest.mark.parametrize("model,quality,hw,n,steps", [("hyper", 3, (192, 256), 2, 12), ("factorized", 1, (192, 192), 1, 9)])
-def test_attack_trajectory_matches_oracle(dev, model, quality, hw, n, steps):
+def test_msssim_gradient_matches_oracle_autograd(dev):
+    from imagecompression_adversarial_b200 import metrics
+    from oracle import msssim as oms
+    g = torch.Generator(device=dev).manual_seed(21)
+    for hw in ((192, 256), (177, 203)):
+        a = torch.rand(2, 3, *hw, device=dev, generator=g)
+        b = (a + 0.05 * torch.randn(2, 3, *hw, device=dev, generator=g)).clamp(0, 1)
+        up = torch.tensor([1.0, -0.5], device=dev)
+        xr = a.clone().requires_grad_(True)
+        val = oms.ms_ssim(xr, b, data_range=1.0, size_average=False)
+        (val * up).sum().backward()
+        v, gx = metrics.ms_ssim_value_and_grad(a, b, up)
+        torch.testing.assert_close(v, val.detach(), rtol=0, atol=2e-5)
+        err = float((gx - xr.grad).abs().max() / xr.grad.abs().max())
+        assert err < 2e-3, err
+
+
+@pytest.mark.parametrize("model,quality,hw,n,steps,metric", [("hyper", 3, (192, 256), 2, 12, "L2"),
+                                                             ("factorized", 1, (192, 192), 1, 9, "L2"),
+                                                             ("hyper", 3, (192, 256), 1, 6, "ms-ssim")])
+def test_attack_trajectory_matches_oracle(dev, model, quality, hw, n, steps, metric):
     """Fused loop vs the oracle's attack_ per image (N=1 semantics): per-step (branch, loss_i, loss)."""
     from imagecompression_adversarial_b200 import attack as patk
     from oracle import attack as oatk
     onet, pnet = pair(model, quality, dev)
     x = images(n, *hw, dev)
-    args = oatk.default_args(model=model, quality=quality, metric="mse", steps=steps, noise=1e-4)
+    args = oatk.default_args(model=model, quality=quality, metric="mse", steps=steps, att_metric=metric,
+                             noise=1e-4 if metric == "L2" else 2e-5)
     rec = []
     im_adv, out_adv, out_s, bpp_ori, bpp, mse, vi = patk.attack_(x, pnet, args, record=rec)
     for i in range(n):
@@ -159,8 +179,7 @@ def test_attack_trajectory_matches_oracle(dev, model, quality, hw, n, steps):
         o = oatk.attack_(x[i:i + 1], onet, args, record=orec)
         first_div = None
         for t, (br, loss, loss_i) in enumerate(orec):
-            pb, pli, plo = int(rec[t][0][i]), float(rec[t][1][i]), float(rec[t][2][i])
-            pl = pli if pb == 0 else plo
+            pb, pli, pl = int(rec[t][0][i]), float(rec[t][1][i]), float(rec[t][2][i])
             if (pb == 1) != (br == "B"):
                 first_div = t
                 # a branch flip must be a near-tie at the budget boundary (chaotic float compare)
