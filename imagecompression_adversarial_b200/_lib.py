@@ -66,6 +66,8 @@ _SIGS = {
                                             C.c_float, C.c_double, C.c_double, C.c_double, C.c_float, C.c_float,
                                             C.c_void_p]),
     "icadv_ifgsm_update": (C.c_int, [_fp, _fp, _fp, C.c_int64, C.c_float, C.c_float, C.c_void_p]),
+    "icadv_mifgsm_update": (C.c_int, [_fp, _fp, _fp, _fp, _fp, _fp, C.c_int, C.c_int64, C.c_float, C.c_float, C.c_float,
+                                      C.c_void_p]),
     "icadv_output_loss": (C.c_int, [_fp, _fp, _fp, _fp, _fp, C.c_int, C.c_int64, C.c_int, C.c_float, _fp, _fp,
                                     C.c_void_p]),
     "icadv_bound_forward": (C.c_int, [_fp, _fp, C.c_int64, C.c_float, C.c_int, C.c_void_p]),

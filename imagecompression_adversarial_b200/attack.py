@@ -11,7 +11,7 @@ import math
 import torch
 
 from . import metrics
-from .engine import AttackEngine
+from .engine import AttackEngine, IfgsmEngine
 
 _ENGINES = {}
 
@@ -82,3 +82,20 @@ def attack_(im_s, net, args, record=None, noise_init=None):
     im_in = eng.im_in_nchw().contiguous()
     im_adv, output_adv, bpp, mse_results, vi_results = eval(im_in, im_s, output_s, net, args)
     return im_adv, output_adv, output_s, bpp_ori, bpp, mse_results, vi_results
+
+
+def attack_ifgsm(im_s, net, args, random_start=False, multi_start=1, momentum=False, record=None, start=None):
+    """Same contract as attack_ifgsm.attack_ifgsm (attack_ifgsm.py:364-438), single start:
+    returns (im_adv, output_adv, output_s, bpp_ori, bpp, mse_in, mse_out, vi)."""
+    output_s, bpp_ori = clean_pass(im_s, net, args)
+    eps = args.epsilon / 255.0
+    if start is None and random_start:
+        start = torch.clamp(im_s + torch.empty_like(im_s).uniform_(-eps, eps), 0, 1)    # attack_ifgsm.py:381-383
+    net.train()
+    n, _, h, w = im_s.shape
+    eng = IfgsmEngine(net, n, h, w, steps=args.steps, epsilon=args.epsilon, momentum=momentum)
+    eng.load(im_s, output_s, start)
+    eng.run(args.steps, record=record)
+    im_adv = eng.im_adv_nchw().contiguous()
+    im_, output_adv, bpp, mse_results, vi_results = eval(im_adv, im_s, output_s, net, args)
+    return im_, output_adv, output_s, bpp_ori, bpp, mse_results["mse_in"], mse_results["mse_out"], vi_results["vi"]

@@ -34,7 +34,8 @@ struct TcParams {
   CUtensorMap a_map[4];
   CUtensorMap w_map, g_map, out_map, sc_map, yprev_map, scprev_map;
   Tap taps[kMaxTaps];
-  int num_taps, k_chunks, n_ch, n_chunks;   // n_ch = MMA N; n_chunks = n_ch / 32
+  int num_taps, k_chunks, n_ch, n_chunks;   // n_ch = MMA N (one N-tile); n_chunks = n_ch / 32
+  int n_total;                              // all output channels (> n_ch when blockIdx.z tiles N; linear epilogue only)
   int tiles_x, tiles_y, tile_step_y, tile_step_x, tile_off;
   int epi, act, acc_from_in, round_out, a_rank5;
   int num_stages, stage_bytes, tmem_cols, ld_bufs;
@@ -105,6 +106,7 @@ __global__ void __launch_bounds__(kThreads, 2) conv_tc_kernel(const __grid_const
   const int img = p.active != nullptr ? p.active[slot] : slot;
   const int ty = blockIdx.x / p.tiles_x, tx = blockIdx.x % p.tiles_x;
   const int i0 = ty * p.tile_step_y + p.tile_off, j0 = tx * p.tile_step_x + p.tile_off;
+  const int n_off = blockIdx.z * p.n_ch;    // first output channel of this CTA's N-tile
 
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* ld_buf = smem + p.num_stages * p.stage_bytes;   // BWD: y_prev / sc_prev chunk staging (2 x 16 KB)
@@ -133,7 +135,7 @@ __global__ void __launch_bounds__(kThreads, 2) conv_tc_kernel(const __grid_const
   }
   if (threadIdx.x >= 64) {   // parameters the epilogue reads per channel
     for (int i = threadIdx.x - 64; i < p.n_ch; i += kThreads - 64) {
-      sbias[i] = p.bias != nullptr ? __ldg(p.bias + i) : 0.f;
+      sbias[i] = p.bias != nullptr ? __ldg(p.bias + n_off + i) : 0.f;
       if (EPI == ICADV_EPI_GDN_FWD || EPI == ICADV_EPI_IGDN_FWD) sbeta[i] = __ldg(p.beta + i);
     }
   }
@@ -163,7 +165,7 @@ __global__ void __launch_bounds__(kThreads, 2) conv_tc_kernel(const __grid_const
             tma_load_5d(st, &p.a_map[0], &full[s], 0, j0 + tap.dx, i0 + tap.dy, tap.plane, img);
           else
             tma_load_4d(st, &p.a_map[tap.plane], &full[s], kc * 32, j0 + tap.dx, i0 + tap.dy, img);
-          tma_load_2d(st + kABytes, &p.w_map, &full[s], kc * 32, tap.wtap * p.n_ch);
+          tma_load_2d(st + kABytes, &p.w_map, &full[s], kc * 32, tap.wtap * p.n_total + n_off);
         }
       }
       for (int c = 0; c < gdn_kb; ++c, ++kb) {
@@ -341,7 +343,7 @@ __global__ void __launch_bounds__(kThreads, 2) conv_tc_kernel(const __grid_const
         fence_proxy_async_smem();
         named_bar_sync(1, 128);
         if (leader) {
-          tma_store_4d(&p.out_map, bufO, c * 32, j0, i0, img);
+          tma_store_4d(&p.out_map, bufO, n_off + c * 32, j0, i0, img);
           if (o2 != nullptr) tma_store_4d(&p.sc_map, bufS, c * 32, j0, i0, img);
           tma_store_commit();
         }
@@ -566,6 +568,13 @@ struct icadv_conv_plan {
   int smem_bytes[4];
 };
 
+// largest multiple of 32 that divides n and is <= 256 (0 if none)
+static int n_tile_of(int n) {
+  for (int t = 256; t >= 32; t -= 32)
+    if (n % t == 0) return t;
+  return 0;
+}
+
 enum TcMode { kModeNone = 0, kModeGeneric = 1, kModeRgbIn = 2, kModeCol2im = 3 };
 
 static int tc_mode(const icadv_conv_desc* d, bool report) {
@@ -590,7 +599,10 @@ static int tc_mode(const icadv_conv_desc* d, bool report) {
       d->k_ch >= 32 && d->epi == ICADV_EPI_LINEAR && d->act == ICADV_ACT_NONE && !d->acc_from_in)
     return kModeCol2im;   // narrow-output transposed conv (RGB end layer): 1x1 GEMM + col2im epilogue
   TC_REQ(d->k_ch % 32 == 0 && d->k_ch >= 32, "k_ch must be a multiple of 32");
-  TC_REQ(d->n_ch % 32 == 0 && d->n_ch >= 32 && d->n_ch <= 256, "n_ch must be a multiple of 32 in [32,256]");
+  TC_REQ(d->n_ch % 32 == 0 && d->n_ch >= 32, "n_ch must be a multiple of 32");
+  if (d->n_ch > 256) {   // N is tiled over blockIdx.z: linear epilogue only
+    TC_REQ(d->epi == ICADV_EPI_LINEAR && !d->acc_from_in && n_tile_of(d->n_ch) > 0, "n_ch > 256 needs a linear epilogue and a tile size");
+  }
   if (d->epi != ICADV_EPI_LINEAR) TC_REQ(2 * d->n_ch <= 512, "GDN epilogue needs 2*n_ch <= 512 TMEM columns");
   if (d->acc_from_in) TC_REQ(d->k_ch == d->n_ch && d->ksize == 1 && d->stride == 1, "acc_from_in needs a 1x1 identity geometry");
   TC_REQ(d->ksize * d->ksize <= kMaxTaps, "too many taps");
@@ -624,7 +636,9 @@ int icadv_conv_plan_create(const icadv_conv_desc* d, icadv_conv_plan** out_plan)
   if (!plan) { set_error("out of host memory"); return ICADV_ENOMEM; }
   const int K = d->k_ch, taps_total = d->ksize * d->ksize;
   const int s = d->stride;
-  const int N = mode == kModeCol2im ? 96 : d->n_ch;   // MMA N
+  const int n_total = mode == kModeCol2im ? 96 : d->n_ch;
+  const int N = n_total > 256 ? n_tile_of(n_total) : n_total;   // MMA N (one N-tile)
+  const int n_tiles = n_total / N;
   plan->n_launch = mode == kModeCol2im ? 1 : g.n_launch;
   for (int l = 0; l < plan->n_launch; ++l) {
     TcParams& p = plan->params[l];
@@ -652,9 +666,9 @@ int icadv_conv_plan_create(const icadv_conv_desc* d, icadv_conv_plan** out_plan)
     // ---- output-side maps (dense for SCONV, parity plane for TCONV); col2im writes with plain stores
     auto out_side = [&](CUtensorMap* m, const float* base) -> int {
       if (d->form == ICADV_FORM_TCONV && s == 2)
-        return encode_plane(m, base, N, g.out_w, g.out_h, d->n_img, 2, g.out_a[l], g.out_b[l]);
-      return encode_nhwc(m, base, N, g.out_w, g.out_h, d->n_img, N, (int64_t)g.out_w * N,
-                         (int64_t)g.out_h * g.out_w * N);
+        return encode_plane(m, base, n_total, g.out_w, g.out_h, d->n_img, 2, g.out_a[l], g.out_b[l]);
+      return encode_nhwc(m, base, n_total, g.out_w, g.out_h, d->n_img, n_total, (int64_t)g.out_w * n_total,
+                         (int64_t)g.out_h * g.out_w * n_total);
     };
     if (mode == kModeCol2im) {
       rc = encode_mat(&p.w_map, d->wpack, K, taps_total * d->n_ch, N);   // rows >= 25*n_ch read as zeros
@@ -667,7 +681,7 @@ int icadv_conv_plan_create(const icadv_conv_desc* d, icadv_conv_plan** out_plan)
       if (!rc && bwd) rc = out_side(&p.scprev_map, d->sc_prev);
       if (!rc && !d->acc_from_in) {
         if (mode == kModeRgbIn) rc = encode_mat(&p.w_map, d->wpack, 32, 5 * N, N);   // [5 kh][N][32]
-        else rc = encode_mat(&p.w_map, d->wpack, K, taps_total * N, N);
+        else rc = encode_mat(&p.w_map, d->wpack, K, taps_total * n_total, N);
       }
       if (!rc && gdn) rc = encode_mat(&p.g_map, d->gmat, N, N, N);
       if (rc) { delete plan; return rc; }
@@ -695,7 +709,7 @@ int icadv_conv_plan_create(const icadv_conv_desc* d, icadv_conv_plan** out_plan)
       for (int t = 0; t < p.num_taps; ++t) p.taps[t] = g.taps[l][t];
       p.k_chunks = K / 32;
     }
-    p.n_ch = N; p.n_chunks = N / 32;
+    p.n_ch = N; p.n_chunks = N / 32; p.n_total = n_total;
     p.tiles_x = (g.tile_w + p.tile_step_x - 1) / p.tile_step_x;
     p.tiles_y = (g.tile_h + p.tile_step_y - 1) / p.tile_step_y;
     p.epi = mode == kModeCol2im ? kEpiCol2im : d->epi;
@@ -724,7 +738,7 @@ int icadv_conv_plan_create(const icadv_conv_desc* d, icadv_conv_plan** out_plan)
     while (pow2 < cols) pow2 <<= 1;
     p.tmem_cols = pow2;
     p.bias = d->bias; p.beta = d->beta; p.active = d->active; p.n_active = d->n_active;
-    plan->grid[l] = dim3(p.tiles_x * p.tiles_y, d->n_img, 1);
+    plan->grid[l] = dim3(p.tiles_x * p.tiles_y, d->n_img, n_tiles);
     plan->smem_bytes[l] = fixed + p.num_stages * p.stage_bytes;
   }
   plan->fn = pick_kernel(plan->params[0].epi, d->acc_from_in);

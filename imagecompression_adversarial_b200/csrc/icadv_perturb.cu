@@ -168,6 +168,39 @@ __global__ void ifgsm_update_kernel(const float* __restrict__ im_s, float* im_ad
   }
 }
 
+// ---- MI-FGSM (attack_ifgsm.py:348-362): g_m = mu g_m + grad / ||grad||_1 ; x = clamp(x + alpha sign(g_m), 0, 1); project
+__global__ void __launch_bounds__(256) sum_abs_kernel(const float4* __restrict__ a, float* __restrict__ ws,
+                                                      int64_t per_img4) {
+  __shared__ float red[8];
+  const int n = blockIdx.y;
+  const int64_t base = (int64_t)n * per_img4;
+  float acc = 0.f;
+  for (int64_t i = blockIdx.x * 256 + threadIdx.x; i < per_img4; i += (int64_t)gridDim.x * 256) {
+    const float4 p = __ldg(a + base + i);
+    acc += fabsf(p.x) + fabsf(p.y) + fabsf(p.z) + fabsf(p.w);
+  }
+  const float s = block_sum_256(acc, red);
+  if (threadIdx.x == 0) ws[(int64_t)n * kRedBlocks + blockIdx.x] = s;
+}
+
+__global__ void mifgsm_update_kernel(const float* __restrict__ im_s, float* im_adv, const float* __restrict__ g,
+                                     float* gm, const float* __restrict__ l1, int64_t per_img, float alpha, float eps,
+                                     float mu) {
+  const int n = blockIdx.y;
+  const int64_t base = (int64_t)n * per_img;
+  const float inv = 1.f / l1[n];
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < per_img; i += (int64_t)gridDim.x * blockDim.x) {
+    const float m = mu * gm[base + i] + g[base + i] * inv;
+    gm[base + i] = m;
+    const float sg = (m > 0.f) ? 1.f : (m < 0.f ? -1.f : 0.f);
+    float x = clampf(im_adv[base + i] + alpha * sg, 0.f, 1.f);
+    const float s = im_s[base + i];
+    x = x > s + eps ? s + eps : x;
+    x = x < s - eps ? s - eps : x;
+    im_adv[base + i] = x;
+  }
+}
+
 // ---- output clamp + distortion + gradient seed (attack_rd.py:353-364)
 __global__ void __launch_bounds__(256) output_loss_kernel(const float4* __restrict__ x, const float4* __restrict__ ref,
                                                           float4* __restrict__ g_x, float* __restrict__ ws,
@@ -296,6 +329,20 @@ int icadv_ifgsm_update(const float* im_s, float* im_adv, const float* g, int64_t
                        icadv_stream_t stream) {
   ICADV_REQUIRE(im_s && im_adv && g, "null pointer");
   ifgsm_update_kernel<<<ew_blocks(n), 256, 0, as_stream(stream)>>>(im_s, im_adv, g, n, alpha, eps);
+  ICADV_CUDA_TRY(cudaGetLastError());
+  return ICADV_OK;
+}
+
+int icadv_mifgsm_update(const float* im_s, float* im_adv, const float* g, float* g_mom, float* ws, float* l1,
+                        int n_img, int64_t per_img, float alpha, float eps, float mu, icadv_stream_t stream) {
+  ICADV_REQUIRE(im_s && im_adv && g && g_mom && ws && l1, "null pointer");
+  ICADV_REQUIRE(per_img % 4 == 0 && n_img >= 1 && n_img <= 65535, "bad sizes");
+  dim3 grid(kRedBlocks, n_img);
+  sum_abs_kernel<<<grid, 256, 0, as_stream(stream)>>>(reinterpret_cast<const float4*>(g), ws, per_img / 4);
+  ICADV_CUDA_TRY(cudaGetLastError());
+  sum_finalize_kernel<<<(n_img + 127) / 128, 128, 0, as_stream(stream)>>>(ws, l1, n_img, nullptr, nullptr);
+  ICADV_CUDA_TRY(cudaGetLastError());
+  mifgsm_update_kernel<<<grid, 256, 0, as_stream(stream)>>>(im_s, im_adv, g, g_mom, l1, per_img, alpha, eps, mu);
   ICADV_CUDA_TRY(cudaGetLastError());
   return ICADV_OK;
 }

@@ -178,3 +178,55 @@ class AttackEngine:
         """Recompute im_in from the final perturbation?  No: the reference evaluates the im_in of the LAST
         iteration (attack_rd.py:561,573), i.e. before the last optimizer step.  Returns that tensor."""
         return self.im_in_nchw()
+
+
+class IfgsmEngine:
+    """I-FGSM / PGD / MI-FGSM loop of attack_ifgsm.py:364-438 on the same launch programs: every step is a network
+    step (no budget branch): loss = mean((output_s - g_s(g_a(x)))^2), x += (eps/steps) sign(grad) [or the momentum
+    form], projection onto [x0 - eps, x0 + eps]."""
+
+    def __init__(self, net, n_img, height, width, *, steps, epsilon=16.0, momentum=False, device=None):
+        ops.require_device()
+        dev = device or next(net.parameters()).device
+        self.n_img, self.steps, self.eps, self.momentum = n_img, steps, epsilon / 255.0, momentum
+        f = lambda *s: torch.zeros(*s, device=dev, dtype=torch.float32)
+        shape = (n_img, height, width, 3)
+        self.per_img = 3 * height * width
+        self.im_s, self.output_s, self.im_adv, self.g_mom = f(*shape), f(*shape), f(*shape), f(*shape)
+        self.loss_sum, self.l1 = f(n_img), f(n_img)
+        self.ws = f(n_img * L.RED_BLOCKS)
+        ga_units, gs_units = parse_stack(net.g_a), parse_stack(net.g_s)
+        lat_h, lat_w = height, width
+        for u in ga_units:
+            lat_h, lat_w = ops.out_hw(u.fwd_form, u.k, u.s, lat_h, lat_w)
+        self.g_lat = f(n_img, lat_h, lat_w, ga_units[-1].cout)
+        self.ga = StackProgram(ga_units, n_img, height, width, dev, x_in=self.im_adv, g_out=self.g_lat,
+                               round_final_out=True)
+        self.gs = StackProgram(gs_units, n_img, lat_h, lat_w, dev, x_in=self.ga.out, g_in=self.g_lat,
+                               round_final_gin=True)
+
+    def load(self, im_s_nchw, output_s_nchw, start_nchw=None):
+        self.im_s.copy_(im_s_nchw.permute(0, 2, 3, 1))
+        self.output_s.copy_(output_s_nchw.permute(0, 2, 3, 1))
+        self.im_adv.copy_((im_s_nchw if start_nchw is None else start_nchw).permute(0, 2, 3, 1))
+        self.g_mom.zero_()
+
+    def run(self, iterations, record=None):
+        for _ in range(iterations):
+            self.ga.forward()
+            self.gs.forward()
+            # loss = +mean(d^2): d loss / d out = -2 d / P  (no output clamp in attack_ifgsm.py:394-396)
+            ops.output_loss(self.gs.out, self.output_s, self.gs.g_out, self.ws, self.loss_sum, do_clamp=False,
+                            grad_scale=-1.0 / self.per_img)
+            self.gs.backward()
+            self.ga.backward()
+            if self.momentum:
+                ops.mifgsm_update(self.im_s, self.im_adv, self.ga.g_in, self.g_mom, self.ws, self.l1,
+                                  alpha=self.eps / self.steps, eps=self.eps, mu=1.0)
+            else:
+                ops.ifgsm_update(self.im_s, self.im_adv, self.ga.g_in, alpha=self.eps / self.steps, eps=self.eps)
+            if record is not None:
+                record.append((self.loss_sum / self.per_img).cpu().clone())
+
+    def im_adv_nchw(self):
+        return self.im_adv.permute(0, 3, 1, 2)

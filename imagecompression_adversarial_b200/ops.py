@@ -264,6 +264,12 @@ def ifgsm_update(im_s, im_adv, g, *, alpha, eps):
     L.call("icadv_ifgsm_update", _p(im_s), _p(im_adv), _p(g), im_s.numel(), float(alpha), float(eps), _stream())
 
 
+def mifgsm_update(im_s, im_adv, g, g_mom, ws, l1, *, alpha, eps, mu=1.0):
+    n_img, per_img = im_s.shape[0], im_s[0].numel()
+    L.call("icadv_mifgsm_update", _p(im_s), _p(im_adv), _p(g), _p(g_mom), _p(ws), _p(l1), n_img, per_img, float(alpha),
+           float(eps), float(mu), _stream())
+
+
 def bound_forward(x, bound, upper):
     y = torch.empty_like(x)
     L.call("icadv_bound_forward", _p(x), _p(y), x.numel(), float(bound), 1 if upper else 0, _stream())

@@ -180,6 +180,11 @@ int icadv_perturb_update_adam(const float* im_s, float* noise, const float* g_in
 int icadv_ifgsm_update(const float* im_s, float* im_adv, const float* g, int64_t n, float alpha,
                        float eps, icadv_stream_t stream);
 
+/* MI-FGSM step (attack_ifgsm.py:348-362), per image: g_mom = mu g_mom + g/||g||_1; x = clamp(x + alpha sign(g_mom), 0, 1);
+ * then the eps projection.  ws: n_img*128 floats; l1: n_img floats (written). */
+int icadv_mifgsm_update(const float* im_s, float* im_adv, const float* g, float* g_mom, float* ws, float* l1,
+                        int n_img, int64_t per_img, float alpha, float eps, float mu, icadv_stream_t stream);
+
 /* Output clamp + distortion (attack_rd.py:353-364) and its gradient seed:
  * o = clamp(x,0,1) (if do_clamp); sum_d2[n] = sum (ref - o)^2;
  * g_x = grad_scale * 2 (ref - o) passed through the Low/Up_bound backward rule (g_x may be NULL). */
