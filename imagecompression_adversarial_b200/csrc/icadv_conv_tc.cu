@@ -2,12 +2,19 @@
 // fused into the epilogue in both directions.  Replaces nn.Conv2d / nn.ConvTranspose2d + compressai GDN
 // under net.g_a / net.g_s (reference: anchors/utils.py:112-130, utils/ops.py:58-97, attack_rd.py:344-349,547).
 //
-// One CTA = one 8x16 tile of "tile-space" pixels (M = 128 rows) x all n_ch output channels (N <= 256).
+// One CTA = one 16x8 tile (16 rows, 8 columns) of "tile-space" pixels (M = 128 rows) x all n_ch output
+// channels (N <= 256).
 //   D[128, N] = sum over taps t, 32-channel chunks kc:  A_t,kc[128, 32] * W_t,kc[N, 32]^T       (kind::tf32)
-// A_t,kc is one TMA box [32 ch, 16 w, 8 h, 1 img] of the channels-last input, shifted by the tap offset
-// (out-of-bounds = zero padding); for stride-2 convs the input is addressed through four parity-plane
-// tensor maps so every tap is a unit-stride box.  W_t,kc is a TMA box [32, N] of the packed weights.
-// Both land in SWIZZLE_128B K-major layout and feed tcgen05.mma directly; the accumulator lives in TMEM.
+// The input is loaded ONCE per (parity plane, 32-channel chunk) as a halo patch: a TMA box
+// [32 ch, 8 + halo w, 16 + halo h, 1 img] of the channels-last input (out-of-bounds = zero padding; stride-2
+// convs address the input through four parity-plane tensor maps so every tap is a unit shift).  The patch
+// lands as consecutive 128-byte pixel rows (SWIZZLE_128B); because a tile row is exactly one 8-row swizzle
+// group, the A operand of tap (dy, dx) is the SAME patch read through a shared-memory descriptor whose start
+// address is shifted by (dy * patch_w + dx) rows and whose group stride (SBO) is patch_w * 128 bytes -- the
+// tensor core applies the swizzle on absolute address bits, so unaligned starts and strides are exact
+// (profiles/r1_umma_descriptor_shift_probe.txt).  That cuts the L2 -> SM operand traffic of a 5x5/2 layer from
+// 25 boxes to 4 patches per chunk; the weights W_t,kc stream through their own ring as TMA boxes [32, N].
+// The accumulator lives in TMEM.
 //
 // Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer, warps 2-5 = epilogue.
 // GDN epilogues append n_ch/32 extra K-blocks to the same smem ring: the A operand of those blocks
@@ -22,23 +29,39 @@
 
 namespace icadv {
 
-constexpr int kTH = 8, kTW = 16, kTileM = 128;
+constexpr int kTH = 16, kTW = 8, kTileM = 128;   // kTW must be 8: one tile row = one 8-row swizzle group
 constexpr int kABytes = kTileM * 128;   // one [128 x 32 fp32] operand / staging tile
-constexpr int kMaxStages = 8;
-constexpr int kSmemLimit = 232448;      // 227 KB
-constexpr int kBarBytes = 256 + 2 * 256 * 4 + 64;   // barriers + per-channel bias/beta copies
+constexpr int kMaxStages = 8;           // weight ring
+constexpr int kMaxPatch = 4;            // patch ring
+constexpr int kMaxGroups = 8;           // patches per 32-channel chunk (parity planes; kernel rows of the RGB form)
+constexpr int kSmemLimit = 232448;      // 227 KB per CTA
+constexpr int kSmemTwoCta = 115712;     // (228 KB per SM) / 2 - 1 KB system reservation per CTA
+constexpr int kBarBlock = 320;          // 35 mbarriers + the TMEM base; followed by per-channel bias / beta copies (2 * n_ch floats)
 constexpr int kEpiCol2im = 5;           // internal epilogue code: narrow-output transposed conv via col2im
 constexpr int kZStride = 77;            // floats per row of the col2im staging tile (odd: conflict-free)
+
+// One halo patch of the input: everything the taps [tap_begin, tap_end) read for one 32-channel chunk.
+struct Group {
+  int16_t map;        // index into a_map (parity plane)
+  int16_t plane5;     // rank-5 (RGB first-layer) form: coordinate 3 of the box
+  int16_t dy0, dx0;   // patch origin relative to the tile origin
+  int16_t tap_begin, tap_end;
+  int32_t sbo_bytes;  // stride between tile rows inside the patch = patch_w * 128
+  int32_t bytes;      // patch_w * patch_h * 128
+};
 
 struct TcParams {
   CUtensorMap a_map[4];
   CUtensorMap w_map, g_map, out_map, sc_map, yprev_map, scprev_map;
-  Tap taps[kMaxTaps];
-  int num_taps, k_chunks, n_ch, n_chunks;   // n_ch = MMA N (one N-tile); n_chunks = n_ch / 32
+  Group groups[kMaxGroups];
+  int32_t tap_aoff[kMaxTaps];   // byte offset of the tap's first row inside its patch
+  int16_t tap_wtap[kMaxTaps];   // row block of the packed weight
+  int num_groups, num_taps, k_chunks, n_ch, n_chunks;   // n_ch = MMA N (one N-tile); n_chunks = n_ch / 32
+  int num_patch, patch_bytes;               // patch ring: slots and bytes per slot (multiple of 1024)
   int n_total;                              // all output channels (> n_ch when blockIdx.z tiles N; linear epilogue only)
   int tiles_x, tiles_y, tile_step_y, tile_step_x, tile_off;
   int epi, act, acc_from_in, round_out, a_rank5;
-  int num_stages, stage_bytes, tmem_cols, ld_bufs;
+  int num_stages, tmem_cols, ld_bufs;       // num_stages: weight ring (n_ch * 128 bytes per stage)
   int t_h, t_w, o_h, o_w, o_s, o_a, o_b;    // tile-space extent; output geometry: pixel (o_s*i + o_a, o_s*j + o_b)
   const float* yprev; const float* scprev; const float* xin;   // epilogue operands read with plain loads
   int c2i_in_h, c2i_in_w, c2i_nch;         // col2im: input extent, real output channels
@@ -109,19 +132,25 @@ __global__ void __launch_bounds__(kThreads, 2) conv_tc_kernel(const __grid_const
   const int n_off = blockIdx.z * p.n_ch;    // first output channel of this CTA's N-tile
 
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* ld_buf = smem + p.num_stages * p.stage_bytes;   // BWD: y_prev / sc_prev chunk staging (2 x 16 KB)
+  const int P = p.num_patch, S = p.num_stages;
+  const uint32_t b_bytes = static_cast<uint32_t>(p.n_ch) * 128u;
+  uint8_t* wring = smem + P * p.patch_bytes;               // weight ring behind the patch ring
+  uint8_t* ld_buf = wring + S * b_bytes;                   // BWD: y_prev / sc_prev chunk staging (2 x 16 KB)
   uint64_t* full = reinterpret_cast<uint64_t*>(ld_buf + p.ld_bufs * kABytes);
   uint64_t* empty = full + kMaxStages;
-  uint64_t* acc_full = empty + kMaxStages;   // [2]
+  uint64_t* pfull = empty + kMaxStages;      // [kMaxPatch]
+  uint64_t* pempty = pfull + kMaxPatch;      // [kMaxPatch]
+  uint64_t* acc_full = pempty + kMaxPatch;   // [2]
   uint64_t* a2_ready = acc_full + 2;         // [8]
   uint64_t* ld_full = a2_ready + 8;          // [1]
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(ld_full + 1);
-  float* sbias = reinterpret_cast<float*>(full) + 64;   // [256] after the 256-byte barrier block
-  float* sbeta = sbias + 256;                           // [256]
+  float* sbias = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(full) + kBarBlock);   // [n_ch]
+  float* sbeta = sbias + p.n_ch;                                                            // [n_ch]
 
   if (threadIdx.x == 0) {
     TC_STAMP(0);
-    for (int s = 0; s < p.num_stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int s = 0; s < S; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int s = 0; s < P; ++s) { mbar_init(&pfull[s], 1); mbar_init(&pempty[s], 1); }
     mbar_init(&acc_full[0], 1); mbar_init(&acc_full[1], 1);
     for (int c = 0; c < 8; ++c) mbar_init(&a2_ready[c], 128);
     mbar_init(ld_full, 1);
@@ -145,34 +174,58 @@ __global__ void __launch_bounds__(kThreads, 2) conv_tc_kernel(const __grid_const
   const uint32_t tmem = *tmem_ptr;
   if (threadIdx.x == 0) TC_STAMP(1);
 
-  const int main_kb = FROM_IN ? 0 : p.num_taps * p.k_chunks;
+  const int main_pc = FROM_IN ? 0 : p.k_chunks * p.num_groups;   // patches of the main loop
+  const int main_kb = FROM_IN ? 0 : p.k_chunks * p.num_taps;     // weight boxes (= K-blocks) of the main loop
   const int gdn_kb = gdn ? p.n_chunks : 0;
-  const uint32_t b_bytes = static_cast<uint32_t>(p.n_ch) * 128u;
-  const int S = p.num_stages;
 
+  // Both single-thread roles below are latency chains (one lane, no ILP): ring positions are carried as
+  // (slot, phase) counters -- no division -- and everything that does not depend on a barrier is computed
+  // before waiting on it, so the path barrier -> issue stays a handful of instructions.
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
-      int kb = 0;
-      for (int t = 0; t < (FROM_IN ? 0 : p.num_taps); ++t) {
-        const Tap tap = p.taps[t];
-        for (int kc = 0; kc < p.k_chunks; ++kc, ++kb) {
-          const int s = kb % S;
-          mbar_wait(&empty[s], ((kb / S) & 1) ^ 1);
-          uint8_t* st = smem + s * p.stage_bytes;
-          mbar_arrive_expect_tx(&full[s], kABytes + b_bytes);
+      if constexpr (bwd) {
+        // the saved y / scale of this tile come from HBM (written by the forward pass long ago): pull them into L2
+        // now, so the epilogue's chunk loads are L2 hits instead of eight serial DRAM round trips
+        if (p.dbg_flags & 4)   // measured: no gain (the chunk round trip, not DRAM, is the latency) -- kept as a switch
+          for (int c = 0; c < p.n_chunks; ++c) {
+            tma_prefetch_4d(&p.yprev_map, c * 32, j0, i0, img);
+            tma_prefetch_4d(&p.scprev_map, c * 32, j0, i0, img);
+          }
+      }
+      int s = 0, ps = 0;
+      uint32_t s_par = 1, p_par = 1;          // parity to wait for on the "empty" barriers (first pass: free)
+      uint8_t* wdst = wring;
+      uint8_t* pdst = smem;
+      const int n_row0 = n_off;
+      for (int kc = 0; kc < (FROM_IN ? 0 : p.k_chunks); ++kc) {
+        const int c0 = kc * 32;
+        for (int g = 0; g < p.num_groups; ++g) {
+          const Group gr = p.groups[g];
+          const int cx = j0 + gr.dx0, cy = i0 + gr.dy0;
+          mbar_wait(&pempty[ps], p_par);
+          mbar_arrive_expect_tx(&pfull[ps], gr.bytes);
           if (p.a_rank5)
-            tma_load_5d(st, &p.a_map[0], &full[s], 0, j0 + tap.dx, i0 + tap.dy, tap.plane, img);
+            tma_load_5d(pdst, &p.a_map[0], &pfull[ps], 0, cx, cy, gr.plane5, img);
           else
-            tma_load_4d(st, &p.a_map[tap.plane], &full[s], kc * 32, j0 + tap.dx, i0 + tap.dy, img);
-          tma_load_2d(st + kABytes, &p.w_map, &full[s], kc * 32, tap.wtap * p.n_total + n_off);
+            tma_load_4d(pdst, &p.a_map[gr.map], &pfull[ps], c0, cx, cy, img);
+          if (++ps == P) { ps = 0; p_par ^= 1; pdst = smem; } else { pdst += p.patch_bytes; }
+          int wrow = p.tap_wtap[gr.tap_begin] * p.n_total + n_row0;
+          for (int t = gr.tap_begin; t < gr.tap_end; ++t) {
+            const int wrow_next = (t + 1 < gr.tap_end ? p.tap_wtap[t + 1] : 0) * p.n_total + n_row0;
+            mbar_wait(&empty[s], s_par);
+            mbar_arrive_expect_tx(&full[s], b_bytes);
+            tma_load_2d(wdst, &p.w_map, &full[s], c0, wrow);
+            wrow = wrow_next;
+            if (++s == S) { s = 0; s_par ^= 1; wdst = wring; } else { wdst += b_bytes; }
+          }
         }
       }
-      for (int c = 0; c < gdn_kb; ++c, ++kb) {
-        const int s = kb % S;
-        mbar_wait(&empty[s], ((kb / S) & 1) ^ 1);
+      for (int c = 0; c < gdn_kb; ++c) {
+        mbar_wait(&empty[s], s_par);
         mbar_arrive_expect_tx(&full[s], b_bytes);
-        tma_load_2d(smem + s * p.stage_bytes + kABytes, &p.g_map, &full[s], c * 32, 0);
+        tma_load_2d(wdst, &p.g_map, &full[s], c * 32, 0);
+        if (++s == S) { s = 0; s_par ^= 1; wdst = wring; } else { wdst += b_bytes; }
       }
     }
     __syncwarp();
@@ -180,31 +233,55 @@ __global__ void __launch_bounds__(kThreads, 2) conv_tc_kernel(const __grid_const
     // ===================== MMA issuer =====================
     if (lane == 0) {
       const uint32_t idesc = umma_idesc_tf32(kTileM, p.n_ch);
-      int kb = 0;
-      for (; kb < main_kb; ++kb) {
-        const int s = kb % S;
-        mbar_wait(&full[s], (kb / S) & 1);
-        if (kb == 0) TC_STAMP(2);
-        tc_fence_after_sync();
-        const uint32_t a_addr = smem_u32(smem + s * p.stage_bytes);
-        const uint64_t ad = umma_desc_sw128(a_addr), bd = umma_desc_sw128(a_addr + kABytes);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) tc_mma_tf32(tmem, ad + 2 * k, bd + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
-        tc_commit(&empty[s]);
+      // shared-memory descriptors: hi word = SBO>>4 | version 1 (bit 14) | SWIZZLE_128B (bit 30); lo word = addr>>4 | LBO 1
+      const uint32_t hi_dense = (1024u >> 4) | (1u << 14) | (2u << 29);
+      const uint32_t w_lo0 = ((smem_u32(wring) >> 4) & 0x3FFFu) | (1u << 16);
+      const uint32_t p_lo0 = ((smem_u32(smem) >> 4) & 0x3FFFu) | (1u << 16);
+      const uint32_t w_step = b_bytes >> 4, p_step = static_cast<uint32_t>(p.patch_bytes) >> 4;
+      int s = 0, ps = 0;
+      uint32_t s_par = 0, p_par = 0, w_lo = w_lo0, p_lo = p_lo0, acc = 0;
+      TC_STAMP(2);
+      for (int kc = 0; kc < (FROM_IN ? 0 : p.k_chunks); ++kc) {
+        for (int g = 0; g < p.num_groups; ++g) {
+          const Group gr = p.groups[g];
+          const uint32_t a_hi = (static_cast<uint32_t>(gr.sbo_bytes) >> 4) | (1u << 14) | (2u << 29);
+          uint32_t aoff = static_cast<uint32_t>(p.tap_aoff[gr.tap_begin]) >> 4;
+          mbar_wait(&pfull[ps], p_par);
+          for (int t = gr.tap_begin; t < gr.tap_end; ++t) {
+            // tap (dy, dx): same patch, start shifted by whole pixel rows; tile rows are patch_w * 128 bytes apart
+            const uint64_t ad = (static_cast<uint64_t>(a_hi) << 32) | (p_lo + aoff);
+            const uint64_t bd = (static_cast<uint64_t>(hi_dense) << 32) | w_lo;
+            aoff = static_cast<uint32_t>(p.tap_aoff[t + 1 < gr.tap_end ? t + 1 : t]) >> 4;   // next tap, off the critical path
+            mbar_wait(&full[s], s_par);
+            tc_fence_after_sync();
+            tc_mma_tf32(tmem, ad, bd, idesc, acc);
+            tc_mma_tf32(tmem, ad + 2, bd + 2, idesc, 1u);
+            tc_mma_tf32(tmem, ad + 4, bd + 4, idesc, 1u);
+            tc_mma_tf32(tmem, ad + 6, bd + 6, idesc, 1u);
+            tc_commit(&empty[s]);
+            acc = 1u;
+            if (++s == S) { s = 0; s_par ^= 1; w_lo = w_lo0; } else { w_lo += w_step; }
+          }
+          tc_commit(&pempty[ps]);
+          if (++ps == P) { ps = 0; p_par ^= 1; p_lo = p_lo0; } else { p_lo += p_step; }
+        }
       }
       if (main_kb > 0) tc_commit(&acc_full[0]);
       TC_STAMP(3);
-      for (int c = 0; c < gdn_kb; ++c, ++kb) {
-        const int s = kb % S;
-        mbar_wait(&full[s], (kb / S) & 1);
+      for (int c = 0; c < gdn_kb; ++c) {
+        const uint64_t ad = (static_cast<uint64_t>(hi_dense) << 32) | p_lo;
+        const uint64_t bd = (static_cast<uint64_t>(hi_dense) << 32) | w_lo;
+        mbar_wait(&full[s], s_par);
         mbar_wait(&a2_ready[c], 0);
         tc_fence_after_sync();
-        const uint32_t a_addr = smem_u32(smem + s * p.stage_bytes);
-        const uint64_t ad = umma_desc_sw128(a_addr), bd = umma_desc_sw128(a_addr + kABytes);
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-          tc_mma_tf32(tmem + p.n_ch, ad + 2 * k, bd + 2 * k, idesc, (c > 0 || k > 0) ? 1u : 0u);
+        tc_mma_tf32(tmem + p.n_ch, ad, bd, idesc, c > 0 ? 1u : 0u);
+        tc_mma_tf32(tmem + p.n_ch, ad + 2, bd + 2, idesc, 1u);
+        tc_mma_tf32(tmem + p.n_ch, ad + 4, bd + 4, idesc, 1u);
+        tc_mma_tf32(tmem + p.n_ch, ad + 6, bd + 6, idesc, 1u);
         tc_commit(&empty[s]);
+        tc_commit(&pempty[ps]);
+        if (++s == S) { s = 0; s_par ^= 1; w_lo = w_lo0; } else { w_lo += w_step; }
+        if (++ps == P) { ps = 0; p_par ^= 1; p_lo = p_lo0; } else { p_lo += p_step; }
       }
       if (gdn_kb > 0) tc_commit(&acc_full[1]);
       TC_STAMP(4);
@@ -237,7 +314,7 @@ __global__ void __launch_bounds__(kThreads, 2) conv_tc_kernel(const __grid_const
       named_bar_sync(1, 128);
       if (leader) TC_STAMP(6);
       const int OH = 2 * p.c2i_in_h, OW = 2 * p.c2i_in_w, nch = p.c2i_nch;
-      constexpr int kIy = kTH - 2, kIx = kTW - 2;   // tile interior (6 x 14 input pixels)
+      constexpr int kIy = kTH - 2, kIx = kTW - 2;   // tile interior (14 x 6 input pixels)
       for (int o = row; o < kIy * kIx * 4; o += 128) {
         const int cell = o >> 2, a = (o >> 1) & 1, b = o & 1;
         const int ti = 1 + cell / kIx, tj = 1 + cell % kIx;
@@ -269,11 +346,8 @@ __global__ void __launch_bounds__(kThreads, 2) conv_tc_kernel(const __grid_const
       const int gi = i0 + row / kTW, gj = j0 + row % kTW;
       const bool px_ok = gi < p.t_h && gj < p.t_w;
       const int64_t pix = (((int64_t)img * p.o_h + p.o_s * gi + p.o_a) * p.o_w + p.o_s * gj + p.o_b) * p.n_ch;
-      // store staging aliases the stage ring (idle once the last MMA has completed): 16 KB regions
-      auto stg = [&](int i) -> uint8_t* {
-        return b_bytes >= static_cast<uint32_t>(kABytes) ? smem + (i >> 1) * p.stage_bytes + (i & 1) * kABytes
-                                                          : smem + i * p.stage_bytes;
-      };
+      // store staging aliases the patch + weight rings (idle once the last MMA has completed): 16 KB regions
+      auto stg = [&](int i) -> uint8_t* { return smem + i * kABytes; };
       int stores = 0;
       uint32_t ld_cnt = 0;
       uint8_t* ldY = ld_buf;
@@ -374,7 +448,9 @@ __global__ void __launch_bounds__(kThreads, 2) conv_tc_kernel(const __grid_const
           store_chunk(c, v, nullptr);
         }
       } else {
-        // ---- pass 1: build the A operand of the normalisation GEMM ----
+        // ---- pass 1: build the A operand of the normalisation GEMM (patch ring, continuing after the main loop) ----
+        int e_ps = main_pc % P;
+        uint32_t e_par = ((main_pc / P) & 1) ^ 1;
         for (int c = 0; c < nC; ++c) {
           float v[32], a2[32];
           load_acc1(c, v);
@@ -396,9 +472,9 @@ __global__ void __launch_bounds__(kThreads, 2) conv_tc_kernel(const __grid_const
               }
             }
           }
-          const int kb = main_kb + c, s = kb % S;
-          mbar_wait(&empty[s], ((kb / S) & 1) ^ 1);   // MMAs that last read this slot are done
-          write_row32(smem + s * p.stage_bytes, row, a2);
+          mbar_wait(&pempty[e_ps], e_par);   // MMAs that last read this patch slot are done
+          write_row32(smem + e_ps * p.patch_bytes, row, a2);
+          if (++e_ps == P) { e_ps = 0; e_par ^= 1; }
           fence_proxy_async_smem();
           mbar_arrive(&a2_ready[c]);
         }
@@ -490,14 +566,15 @@ static EncodeTiledFn get_encode() {
   return fn;
 }
 
-// 4-D channels-last view: dims (C, W, H, N) with arbitrary pixel strides (in floats); box [32, TW, TH, 1]
+// 4-D channels-last view: dims (C, W, H, N) with arbitrary pixel strides (in floats); box [32, box_w, box_h, 1]
+// (the tile itself for outputs, the tile plus its halo for input patches)
 static int encode_nhwc(CUtensorMap* m, const float* base, int C, int W, int H, int N, int64_t sw, int64_t sh,
-                       int64_t sn) {
+                       int64_t sn, int box_w = kTW, int box_h = kTH) {
   EncodeTiledFn enc = get_encode();
   if (!enc) { set_error("cuTensorMapEncodeTiled not available"); return ICADV_ECUDA; }
   cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
   cuuint64_t strides[3] = {(cuuint64_t)sw * 4, (cuuint64_t)sh * 4, (cuuint64_t)sn * 4};
-  cuuint32_t box[4] = {32, (cuuint32_t)kTW, (cuuint32_t)kTH, 1};
+  cuuint32_t box[4] = {32, (cuuint32_t)box_w, (cuuint32_t)box_h, 1};
   cuuint32_t es[4] = {1, 1, 1, 1};
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(base), dims, strides, box, es,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -528,11 +605,12 @@ static int encode_mat(CUtensorMap* m, const float* base, int cols, int rows, int
 }
 
 // parity plane (a,b) of a dense [N,H,W,C] tensor with spatial step s: pixels (s*i+a, s*j+b)
-static int encode_plane(CUtensorMap* m, const float* base, int C, int W, int H, int N, int s, int a, int b) {
+static int encode_plane(CUtensorMap* m, const float* base, int C, int W, int H, int N, int s, int a, int b,
+                        int box_w = kTW, int box_h = kTH) {
   const int Wp = (W - b + s - 1) / s, Hp = (H - a + s - 1) / s;
   if (Wp <= 0 || Hp <= 0) { set_error("empty parity plane"); return ICADV_EINVAL; }
   return encode_nhwc(m, base + ((int64_t)a * W + b) * C, C, Wp, Hp, N, (int64_t)s * C, (int64_t)s * W * C,
-                     (int64_t)H * W * C);
+                     (int64_t)H * W * C, box_w, box_h);
 }
 
 // padded RGB0 input of the first-layer form: [n_img][in_h + 4][in_w + 8][4] floats, pixel (h, w) at (h+2, w+2)
@@ -644,22 +722,85 @@ int icadv_conv_plan_create(const icadv_conv_desc* d, icadv_conv_plan** out_plan)
     TcParams& p = plan->params[l];
     memset(&p, 0, sizeof(p));
     p.tile_step_y = kTH; p.tile_step_x = kTW; p.tile_off = 0;
-    // ---- input maps
+    // ---- taps of this launch, grouped into halo patches: one group per input parity plane (stride-2 SCONV),
+    //      per kernel row (RGB first-layer form), else a single group
+    Tap taps[kMaxTaps];
+    int n_taps = 0;
+    if (mode == kModeRgbIn) {
+      // one K-block per kernel row kh: padded input row 2*oh + kh -> (parity kh & 1, half-row oh + (kh >> 1))
+      for (int kh = 0; kh < 5; ++kh) {
+        Tap t; t.plane = (int16_t)kh; t.dy = (int16_t)(kh >> 1); t.dx = 0; t.wtap = (int16_t)kh;
+        taps[n_taps++] = t;
+      }
+    } else if (mode == kModeCol2im) {
+      Tap t; t.plane = 0; t.dy = 0; t.dx = 0; t.wtap = 0;
+      taps[n_taps++] = t;
+      p.tile_step_y = kTH - 2; p.tile_step_x = kTW - 2; p.tile_off = -1;   // 1-pixel halo, interior 14 x 6
+      p.c2i_in_h = d->in_h; p.c2i_in_w = d->in_w; p.c2i_nch = d->n_ch; p.c2i_out = d->out;
+    } else if (!d->acc_from_in) {
+      n_taps = g.n_taps[l];
+      for (int t = 0; t < n_taps; ++t) taps[t] = g.taps[l][t];
+    }
+    int box_w[kMaxGroups], box_h[kMaxGroups];
+    p.num_groups = 0; p.num_taps = 0;
+    int max_patch = kABytes;
+    for (int t = 0; t < n_taps; ++t) {
+      bool seen = false;
+      for (int u = 0; u < t; ++u) seen = seen || taps[u].plane == taps[t].plane;
+      if (seen) continue;
+      if (p.num_groups == kMaxGroups) { delete plan; set_error("conv_tc: too many tap groups"); return ICADV_EINVAL; }
+      const int plane = taps[t].plane;
+      int dy0 = 1 << 14, dy1 = -(1 << 14), dx0 = 1 << 14, dx1 = -(1 << 14);
+      for (int u = t; u < n_taps; ++u)
+        if (taps[u].plane == plane) {
+          dy0 = taps[u].dy < dy0 ? taps[u].dy : dy0; dy1 = taps[u].dy > dy1 ? taps[u].dy : dy1;
+          dx0 = taps[u].dx < dx0 ? taps[u].dx : dx0; dx1 = taps[u].dx > dx1 ? taps[u].dx : dx1;
+        }
+      Group& gr = p.groups[p.num_groups];
+      const int pw = kTW + dx1 - dx0, ph = kTH + dy1 - dy0;
+      gr.map = (int16_t)(mode == kModeRgbIn ? 0 : plane);
+      gr.plane5 = (int16_t)(plane & 1);
+      gr.dy0 = (int16_t)dy0; gr.dx0 = (int16_t)dx0;
+      gr.sbo_bytes = pw * 128; gr.bytes = pw * ph * 128;
+      gr.tap_begin = (int16_t)p.num_taps;
+      for (int u = t; u < n_taps; ++u)
+        if (taps[u].plane == plane) {
+          p.tap_aoff[p.num_taps] = ((taps[u].dy - dy0) * pw + (taps[u].dx - dx0)) * 128;
+          p.tap_wtap[p.num_taps] = taps[u].wtap;
+          ++p.num_taps;
+        }
+      gr.tap_end = (int16_t)p.num_taps;
+      box_w[p.num_groups] = pw; box_h[p.num_groups] = ph;
+      if (pw > 256 || ph > 256) { delete plan; set_error("conv_tc: patch exceeds the TMA box limit"); return ICADV_EINVAL; }
+      max_patch = gr.bytes > max_patch ? gr.bytes : max_patch;
+      ++p.num_groups;
+    }
+    // ---- input maps: one per group, box = tile + halo
     if (mode == kModeRgbIn) {
       rc = encode_pad4(&p.a_map[0], d->in, d->in_w, d->in_h, d->n_img);
       if (rc) { delete plan; return rc; }
       p.a_map[1] = p.a_map[2] = p.a_map[3] = p.a_map[0];
       p.a_rank5 = 1;
+    } else if (d->acc_from_in) {
+      // no contraction: the maps are placeholders (set below)
     } else if (d->form == ICADV_FORM_SCONV && s == 2) {
-      for (int a = 0; a < 2; ++a)
-        for (int b = 0; b < 2; ++b) {
-          if (d->in_h <= a || d->in_w <= b) { p.a_map[a * 2 + b] = p.a_map[0]; continue; }
-          rc = encode_plane(&p.a_map[a * 2 + b], d->in, K, d->in_w, d->in_h, d->n_img, 2, a, b);
-          if (rc) { delete plan; return rc; }
+      bool have[4] = {false, false, false, false};
+      for (int gi = 0; gi < p.num_groups; ++gi) {
+        const int plane = p.groups[gi].map, a = plane >> 1, b = plane & 1;
+        if (d->in_h <= a || d->in_w <= b) {   // this parity plane is empty: its taps only ever read zeros
+          rc = encode_plane(&p.a_map[plane], d->in, K, d->in_w, d->in_h, d->n_img, 2, 0, 0, box_w[gi], box_h[gi]);
+          p.groups[gi].dy0 = (int16_t)(1 << 13);   // far outside: the whole patch is out-of-bounds fill
+        } else {
+          rc = encode_plane(&p.a_map[plane], d->in, K, d->in_w, d->in_h, d->n_img, 2, a, b, box_w[gi], box_h[gi]);
         }
+        if (rc) { delete plan; return rc; }
+        have[plane] = true;
+      }
+      for (int q = 0; q < 4; ++q)
+        if (!have[q]) p.a_map[q] = p.a_map[p.groups[0].map];
     } else {
       rc = encode_nhwc(&p.a_map[0], d->in, K, d->in_w, d->in_h, d->n_img, K, (int64_t)d->in_w * K,
-                       (int64_t)d->in_h * d->in_w * K);
+                       (int64_t)d->in_h * d->in_w * K, box_w[0], box_h[0]);
       if (rc) { delete plan; return rc; }
       p.a_map[1] = p.a_map[2] = p.a_map[3] = p.a_map[0];
     }
@@ -687,51 +828,51 @@ int icadv_conv_plan_create(const icadv_conv_desc* d, icadv_conv_plan** out_plan)
       if (rc) { delete plan; return rc; }
       if (!(gdn && !bwd)) p.sc_map = p.out_map;
       if (!bwd) { p.yprev_map = p.out_map; p.scprev_map = p.out_map; }
-      if (d->acc_from_in) p.w_map = p.out_map;
+      if (d->acc_from_in) { p.w_map = p.out_map; p.a_map[0] = p.a_map[1] = p.a_map[2] = p.a_map[3] = p.out_map; }
       if (!gdn) p.g_map = p.out_map;
     }
-
-    if (mode == kModeRgbIn) {
-      // one K-block per kernel row kh: padded input row 2*oh + kh -> (parity kh & 1, half-row oh + (kh >> 1))
-      p.num_taps = 5; p.k_chunks = 1;
-      for (int kh = 0; kh < 5; ++kh) {
-        Tap t; t.plane = (int16_t)(kh & 1); t.dy = (int16_t)(kh >> 1); t.dx = 0; t.wtap = (int16_t)kh;
-        p.taps[kh] = t;
-      }
-    } else if (mode == kModeCol2im) {
-      p.num_taps = 1; p.k_chunks = K / 32;
-      Tap t; t.plane = 0; t.dy = 0; t.dx = 0; t.wtap = 0;
-      p.taps[0] = t;
-      p.tile_step_y = kTH - 2; p.tile_step_x = kTW - 2; p.tile_off = -1;   // 1-pixel halo, interior 6 x 14
-      p.c2i_in_h = d->in_h; p.c2i_in_w = d->in_w; p.c2i_nch = d->n_ch; p.c2i_out = d->out;
-    } else {
-      p.num_taps = g.n_taps[l];
-      for (int t = 0; t < p.num_taps; ++t) p.taps[t] = g.taps[l][t];
-      p.k_chunks = K / 32;
-    }
+    p.k_chunks = mode == kModeRgbIn ? 1 : K / 32;
     p.n_ch = N; p.n_chunks = N / 32; p.n_total = n_total;
     p.tiles_x = (g.tile_w + p.tile_step_x - 1) / p.tile_step_x;
     p.tiles_y = (g.tile_h + p.tile_step_y - 1) / p.tile_step_y;
     p.epi = mode == kModeCol2im ? kEpiCol2im : d->epi;
     p.act = d->act; p.acc_from_in = d->acc_from_in; p.round_out = d->round_out_tf32;
-    p.stage_bytes = kABytes + N * 128;
     p.t_h = g.tile_h; p.t_w = g.tile_w; p.o_h = g.out_h; p.o_w = g.out_w;
     if (d->form == ICADV_FORM_TCONV && s == 2) { p.o_s = 2; p.o_a = g.out_a[l]; p.o_b = g.out_b[l]; }
     else { p.o_s = 1; p.o_a = 0; p.o_b = 0; }
     p.yprev = d->y_prev; p.scprev = d->sc_prev; p.xin = d->in;
     p.dbg_flags = getenv("ICADV_TC_DBG") ? atoi(getenv("ICADV_TC_DBG")) : 0;
-    // aim for two CTAs per SM (their prologue/epilogue overlap each other's main loop): <= ~112 KB each
+    // ---- shared memory: [patch ring | weight ring | BWD staging | barriers + bias/beta].  Aim for two CTAs per SM
+    //      (their prologue / epilogue overlap each other's main loop).
+    p.patch_bytes = (max_patch + 1023) & ~1023;
+    const int wbytes = N * 128;
     p.ld_bufs = bwd ? 2 : 0;
-    const int fixed = 1024 + kBarBytes + p.ld_bufs * kABytes;
-    int stages2 = (113 * 1024 - fixed) / p.stage_bytes;
-    const int need_stg = mode == kModeCol2im ? 2 : ((N * 128 >= kABytes) ? 2 : 4);   // stages the epilogue staging needs
-    const bool two_ok = stages2 >= 2 && stages2 >= need_stg && (gdn ? 2 * N : N) <= 256 &&
-                        !(getenv("ICADV_TC_ONE_CTA") != nullptr);
-    p.num_stages = two_ok ? stages2 : (kSmemLimit - fixed) / p.stage_bytes;
-    if (two_ok && p.num_stages > 3) p.num_stages = 3 > need_stg ? 3 : need_stg;
-    if (p.num_stages > kMaxStages) p.num_stages = kMaxStages;
-    if (p.num_stages < need_stg || p.num_stages < 2 ||
-        (mode == kModeCol2im && p.num_stages * p.stage_bytes < 128 * kZStride * 4)) {
+    const int fixed = 1024 + kBarBlock + 2 * N * 4 + p.ld_bufs * kABytes;
+    // bytes of ring the epilogue aliases for its store staging (16 KB regions) / the col2im scatter tile
+    const int need_ring = mode == kModeCol2im ? 128 * kZStride * 4 : ((gdn && !bwd) ? 4 : 2) * kABytes;
+    // a short main loop (the RGB end layers: 4-5 K-blocks) is one DRAM round trip if every patch is in flight at once
+    const int main_patches = p.k_chunks * p.num_groups;
+    const int short_p = (main_patches >= 3 && main_patches <= 8) ? (main_patches > kMaxPatch ? kMaxPatch : main_patches) : 2;
+    auto fit = [&](int budget, int max_p, int max_s) -> bool {
+      int P = 2, S = (budget - fixed - P * p.patch_bytes) / wbytes;
+      if (S > max_s) S = max_s;
+      if (S < 2) return false;
+      if (short_p > 2) {   // trade weight stages for patch slots
+        while (P < short_p && fixed + (P + 1) * p.patch_bytes + 2 * wbytes <= budget) ++P;
+        S = (budget - fixed - P * p.patch_bytes) / wbytes;
+        if (S > max_s) S = max_s;
+      }
+      while (P < max_p && fixed + (P + 1) * p.patch_bytes + S * wbytes <= budget) ++P;
+      while (fixed + P * p.patch_bytes + S * wbytes - fixed < need_ring) {   // grow the rings for the staging
+        if (S < kMaxStages && fixed + P * p.patch_bytes + (S + 1) * wbytes <= budget) ++S;
+        else return false;
+      }
+      p.num_patch = P; p.num_stages = S;
+      return true;
+    };
+    const bool want_two = (gdn ? 2 * N : N) <= 256 && getenv("ICADV_TC_ONE_CTA") == nullptr;
+    const int env_s = getenv("ICADV_TC_S") ? atoi(getenv("ICADV_TC_S")) : 0;   // developer override: weight stages
+    if (!(want_two && fit(kSmemTwoCta, 2, env_s > 0 ? env_s : 4)) && !fit(kSmemLimit, 3, env_s > 0 ? env_s : kMaxStages)) {
       delete plan; set_error("conv_tc: not enough shared memory for n_ch=%d", N); return ICADV_EINVAL;
     }
     int cols = gdn ? 2 * N : N, pow2 = 32;
@@ -739,7 +880,7 @@ int icadv_conv_plan_create(const icadv_conv_desc* d, icadv_conv_plan** out_plan)
     p.tmem_cols = pow2;
     p.bias = d->bias; p.beta = d->beta; p.active = d->active; p.n_active = d->n_active;
     plan->grid[l] = dim3(p.tiles_x * p.tiles_y, d->n_img, n_tiles);
-    plan->smem_bytes[l] = fixed + p.num_stages * p.stage_bytes;
+    plan->smem_bytes[l] = fixed + p.num_patch * p.patch_bytes + p.num_stages * wbytes;
   }
   plan->fn = pick_kernel(plan->params[0].epi, d->acc_from_in);
   if (plan->fn == nullptr) { delete plan; set_error("conv_tc: no kernel for epi=%d from_in=%d", d->epi, d->acc_from_in); return ICADV_EINVAL; }

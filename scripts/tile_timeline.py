@@ -19,7 +19,7 @@ names = ["start", "setup", "first_full", "main_issued", "gdn_issued", "epi_acc1"
 
 def run(name, d, keep, grid):
     plan = ops.ConvPlan(d, keep)
-    dbg = torch.zeros(grid * 32, dtype=torch.int64, device=dev)
+    dbg = torch.zeros(2 * grid * 32, dtype=torch.int64, device=dev)
     L.call("icadv_conv_plan_set_debug", plan._h, C.c_void_p(dbg.data_ptr()))
     for _ in range(2):
         plan.launch()
@@ -29,7 +29,7 @@ def run(name, d, keep, grid):
     rel = (t[:, :32] - t[:, :1])
     med = rel.median(0).values
     print(name, "CTAs", t.shape[0])
-    print("   " + "  ".join(f"{nm}={med[i]/1.9e3:6.2f}us" for i, nm in enumerate(names)))
+    print("   " + "  ".join(f"{nm}={med[i]/1.9e3:6.2f}us" for i, nm in enumerate(names[:11])))
 
 
 H, W = 512, 768
