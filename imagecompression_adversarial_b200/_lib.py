@@ -58,6 +58,8 @@ _SIGS = {
     "icadv_unpack_weight": (C.c_int, [_fp, _fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "icadv_nchw_to_nhwc": (C.c_int, [_fp, _fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "icadv_nhwc_to_nchw": (C.c_int, [_fp, _fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "icadv_pixel_shuffle": (C.c_int, [_fp, _fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "icadv_copy_channels": (C.c_int, [_fp, _fp, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "icadv_gdn_reparam": (C.c_int, [_fp, _fp, C.c_int, C.c_int, C.c_float, C.c_float, C.c_int, C.c_int, C.c_void_p]),
     "icadv_perturb_forward": (C.c_int, [_fp, _fp, _fp, _fp, C.POINTER(PerturbState), C.c_int, C.c_int64, C.c_float,
                                         C.c_float, C.c_int, C.c_double, C.c_double, C.c_int, C.c_double, C.c_double,
@@ -65,6 +67,14 @@ _SIGS = {
     "icadv_perturb_update_adam": (C.c_int, [_fp, _fp, _fp, _fp, _fp, _fp, C.POINTER(PerturbState), C.c_int, C.c_int64,
                                             C.c_float, C.c_double, C.c_double, C.c_double, C.c_float, C.c_float,
                                             C.c_void_p]),
+    "icadv_perturb_forward_roi": (C.c_int, [_fp, _fp, _fp, _fp, C.POINTER(PerturbState), C.c_int, C.c_int64, C.c_float,
+                                            C.c_float, C.c_int, C.c_double, C.c_double, C.c_int, C.c_double,
+                                            C.c_double, _fp, C.c_int, C.c_void_p]),
+    "icadv_perturb_update_adam_roi": (C.c_int, [_fp, _fp, _fp, _fp, _fp, _fp, C.POINTER(PerturbState), C.c_int,
+                                                C.c_int64, C.c_float, C.c_double, C.c_double, C.c_double, C.c_float,
+                                                C.c_float, _fp, C.c_void_p]),
+    "icadv_output_loss_roi": (C.c_int, [_fp, _fp, _fp, _fp, _fp, C.c_int, C.c_int64, C.c_int, C.c_float, _fp, _fp, _fp,
+                                        C.c_void_p]),
     "icadv_ifgsm_update": (C.c_int, [_fp, _fp, _fp, C.c_int64, C.c_float, C.c_float, C.c_void_p]),
     "icadv_mifgsm_update": (C.c_int, [_fp, _fp, _fp, _fp, _fp, _fp, C.c_int, C.c_int64, C.c_float, C.c_float, C.c_float,
                                       C.c_void_p]),

@@ -11,21 +11,32 @@ import math
 import torch
 
 from . import metrics
-from .engine import AttackEngine, IfgsmEngine
+from . import _lib as L
+from .engine import AttackEngine, GenericAttackEngine, IfgsmEngine, RoiSpec
+from .program import parse_stack
 
 _ENGINES = {}
 
 
-def _engine_for(net, im_s, args):
+def _fused_stacks(net):
+    try:
+        parse_stack(net.g_a)
+        parse_stack(net.g_s)
+        return True
+    except L.IcadvError:
+        return False
+
+
+def _engine_for(net, im_s, args, roi=None):
     n, _, h, w = im_s.shape
     force = getattr(args, "force_branch", -1)
     key = (id(net), n, h, w, args.steps, float(args.epsilon), float(args.noise), float(args.lr_attack),
-           bool(args.clamp), args.att_metric, force)
+           bool(args.clamp), args.att_metric, force, roi.key() if roi is not None else None)
     eng = _ENGINES.get(key)
     if eng is None:
-        eng = AttackEngine(net, n, h, w, steps=args.steps, epsilon=args.epsilon, noise_budget=args.noise,
-                           lr_attack=args.lr_attack, clamp=args.clamp, att_metric=args.att_metric,
-                           force_branch=force)
+        cls = AttackEngine if _fused_stacks(net) else GenericAttackEngine
+        eng = cls(net, n, h, w, steps=args.steps, epsilon=args.epsilon, noise_budget=args.noise,
+                  lr_attack=args.lr_attack, clamp=args.clamp, att_metric=args.att_metric, force_branch=force, roi=roi)
         _ENGINES.clear()  # one live engine: its buffers are sized for the batch
         _ENGINES[key] = eng
     else:
@@ -69,15 +80,23 @@ def eval(im_adv, im_s, output_s, net, args):  # noqa: A001 (the reference shadow
     return im_, output_, bpp, mse_results, vi_results
 
 
-def attack_(im_s, net, args, record=None, noise_init=None):
+def attack_(im_s, net, args, record=None, noise_init=None, im_t=None):
     """Same contract as attack_rd.attack_: returns
-    (im_adv, output_adv, output_s, bpp_ori, bpp, mse_results, vi_results)."""
+    (im_adv, output_adv, output_s, bpp_ori, bpp, mse_results, vi_results).
+    ``im_t`` (the ``-t`` target image, same shape as ``im_s``) switches to the targeted / ROI loss with ``args.mask_loc``,
+    ``args.lamb_bkg_in``, ``args.lamb_bkg_out``, ``args.lamb_tar`` (semantics: oracle/attack.py attack_our_roi; the
+    reference's own path for these flags is dead code)."""
     output_s, bpp_ori = clean_pass(im_s, net, args)
+    roi = output_t = None
+    if im_t is not None:
+        output_t, _ = clean_pass(im_t, net, args)
+        roi = RoiSpec(getattr(args, "mask_loc", None), getattr(args, "lamb_bkg_in", 1.0),
+                      getattr(args, "lamb_bkg_out", 1.0), getattr(args, "lamb_tar", 1.0))
     if noise_init is None and getattr(args, "random", 1) > 1:
         noise_init = torch.empty_like(im_s).uniform_(-1e-2, 1e-2)          # attack_rd.py:498-499
     net.train()                                                            # attack_rd.py:504
-    eng = _engine_for(net, im_s, args)
-    eng.load(im_s, output_s, noise_init)
+    eng = _engine_for(net, im_s, args, roi)
+    eng.load(im_s, output_s, noise_init, output_t)
     eng.run(args.steps, record=record)
     im_in = eng.im_in_nchw().contiguous()
     im_adv, output_adv, bpp, mse_results, vi_results = eval(im_in, im_s, output_s, net, args)

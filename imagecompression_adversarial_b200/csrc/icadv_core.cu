@@ -173,11 +173,60 @@ __global__ void gdn_reparam_kernel(const float* __restrict__ raw, float* __restr
   if (transpose) eff[c * rows + r] = v; else eff[i] = v;
 }
 
+// nn.PixelShuffle(r) on channels-last tensors (compressai subpel_conv3x3): out[n, h*r+i, w*r+j, c] = in[n, h, w, c*r*r + i*r + j]
+// inverse != 0 runs the permutation backwards (its gradient).  One thread per element of the LOW-resolution tensor.
+__global__ void pixel_shuffle_kernel(const float* __restrict__ src, float* __restrict__ dst, int64_t total, int h, int w,
+                                     int c_out, int r, int inverse) {
+  const int c_in = c_out * r * r;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int ci = (int)(i % c_in);
+    const int64_t px = i / c_in;
+    const int x = (int)(px % w), y = (int)((px / w) % h);
+    const int64_t n = px / ((int64_t)w * h);
+    const int c = ci / (r * r), ij = ci % (r * r), di = ij / r, dj = ij % r;
+    const int64_t hi = ((n * h * r + (int64_t)y * r + di) * ((int64_t)w * r) + (int64_t)x * r + dj) * c_out + c;
+    if (inverse) dst[i] = src[hi]; else dst[hi] = src[i];
+  }
+}
+
+// copy `count` channels of every pixel: dst[px, dst_off + c] = src[px, src_off + c]   (torch.cat / chunk on dim 1)
+__global__ void copy_channels_kernel(const float* __restrict__ src, float* __restrict__ dst, int64_t n_px, int c_src,
+                                     int c_dst, int src_off, int dst_off, int count) {
+  const int64_t total = n_px * count;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % count);
+    const int64_t px = i / count;
+    dst[px * c_dst + dst_off + c] = src[px * c_src + src_off + c];
+  }
+}
+
 }  // namespace icadv
 
 using namespace icadv;
 
 extern "C" {
+
+int icadv_pixel_shuffle(const float* src, float* dst, int n, int h, int w, int c_out, int r, int inverse,
+                        icadv_stream_t stream) {
+  ICADV_REQUIRE(src && dst && n > 0 && h > 0 && w > 0 && c_out > 0 && r >= 1, "bad pixel_shuffle args");
+  const int64_t total = (int64_t)n * h * w * c_out * r * r;
+  int64_t blocks = (total + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  pixel_shuffle_kernel<<<(int)blocks, 256, 0, as_stream(stream)>>>(src, dst, total, h, w, c_out, r, inverse);
+  ICADV_CUDA_TRY(cudaGetLastError());
+  return ICADV_OK;
+}
+
+int icadv_copy_channels(const float* src, float* dst, int64_t n_px, int c_src, int c_dst, int src_off, int dst_off,
+                        int count, icadv_stream_t stream) {
+  ICADV_REQUIRE(src && dst && n_px > 0 && count > 0 && src_off >= 0 && dst_off >= 0 && src_off + count <= c_src &&
+                    dst_off + count <= c_dst, "bad copy_channels args");
+  int64_t blocks = (n_px * count + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  copy_channels_kernel<<<(int)blocks, 256, 0, as_stream(stream)>>>(src, dst, n_px, c_src, c_dst, src_off, dst_off, count);
+  ICADV_CUDA_TRY(cudaGetLastError());
+  return ICADV_OK;
+}
 
 const char* icadv_last_error(void) { return g_err; }
 int icadv_version(void) { return 100; }

@@ -30,13 +30,16 @@ __device__ __forceinline__ float clampf(float x, float lo, float hi) { return fm
 __global__ void __launch_bounds__(256) perturb_forward_kernel(const float4* __restrict__ im_s,
                                                               const float4* __restrict__ noise,
                                                               float4* __restrict__ im_in, float* __restrict__ ws,
-                                                              int64_t per_img4, float eps) {
+                                                              int64_t per_img4, float eps,
+                                                              const float4* __restrict__ w_in) {
   __shared__ float red[8];
   const int n = blockIdx.y;
   const int64_t base = (int64_t)n * per_img4;
   float acc = 0.f;
   for (int64_t i = blockIdx.x * 256 + threadIdx.x; i < per_img4; i += (int64_t)gridDim.x * 256) {
     const float4 s = __ldg(im_s + base + i), z = __ldg(noise + base + i);
+    // ROI attack (attack_cv.py:149-163): per-pixel weight mask_tar + lamb_bkg_in * mask_bkg, shared by all images
+    const float4 w = w_in != nullptr ? __ldg(w_in + i) : make_float4(1.f, 1.f, 1.f, 1.f);
     float4 o;
     o.x = clampf(s.x + clampf(z.x, -eps, eps), 0.f, 1.f);
     o.y = clampf(s.y + clampf(z.y, -eps, eps), 0.f, 1.f);
@@ -44,7 +47,7 @@ __global__ void __launch_bounds__(256) perturb_forward_kernel(const float4* __re
     o.w = clampf(s.w + clampf(z.w, -eps, eps), 0.f, 1.f);
     im_in[base + i] = o;
     const float dx = s.x - o.x, dy = s.y - o.y, dz = s.z - o.z, dw = s.w - o.w;
-    acc += dx * dx + dy * dy + dz * dz + dw * dw;
+    acc += w.x * dx * dx + w.y * dy * dy + w.z * dz * dz + w.w * dw * dw;
   }
   const float s = block_sum_256(acc, red);
   if (threadIdx.x == 0) ws[(int64_t)n * kRedBlocks + blockIdx.x] = s;
@@ -53,7 +56,7 @@ __global__ void __launch_bounds__(256) perturb_forward_kernel(const float4* __re
 // ---- finalize: per-image loss_i, branch, compaction, LR schedule, Adam bias corrections
 __global__ void perturb_finalize_kernel(const float* __restrict__ ws, icadv_perturb_state st, int n_img,
                                         double inv_per_img, float budget, int force_branch, double lr0,
-                                        double lr_gamma, int sched_period, double beta1, double beta2) {
+                                        double lr_gamma, int sched_period, double beta1, double beta2, int ge_test) {
   __shared__ int s_branch[1024];
   const int n = threadIdx.x;
   if (n < n_img) {
@@ -62,7 +65,8 @@ __global__ void perturb_finalize_kernel(const float* __restrict__ ws, icadv_pert
     const float loss_i = (float)((double)s * inv_per_img);
     st.sum_d2[n] = s;
     st.loss_i[n] = loss_i;
-    int br = (loss_i > budget) ? 0 : 1;  // attack_rd.py:334 -- A when over budget
+    // attack_rd.py:334 -- A when over budget (">"); the ROI variant switches on ">=" (attack_data.py:219)
+    int br = (ge_test ? (loss_i >= budget) : (loss_i > budget)) ? 0 : 1;
     if (force_branch >= 0) br = force_branch;
     st.branch[n] = br;
     s_branch[n] = br;
@@ -120,7 +124,8 @@ __global__ void __launch_bounds__(256) perturb_update_adam_kernel(const float4* 
                                                                   const float4* __restrict__ g_a_ext, float4* m4,
                                                                   float4* v4, icadv_perturb_state st,
                                                                   int64_t per_img4, float eps, AdamCoef coef,
-                                                                  float gradA_scale, float gradB_scale) {
+                                                                  float gradA_scale, float gradB_scale,
+                                                                  const float4* __restrict__ w_in) {
   const int n = blockIdx.y;
   const int64_t base = (int64_t)n * per_img4;
   const int br = st.branch[n];
@@ -141,6 +146,10 @@ __global__ void __launch_bounds__(256) perturb_update_adam_kernel(const float4* 
       g.y = 2.f * (clampf(s.y + clampf(z.y, -eps, eps), 0.f, 1.f) - s.y) * gradA_scale;
       g.z = 2.f * (clampf(s.z + clampf(z.z, -eps, eps), 0.f, 1.f) - s.z) * gradA_scale;
       g.w = 2.f * (clampf(s.w + clampf(z.w, -eps, eps), 0.f, 1.f) - s.w) * gradA_scale;
+      if (w_in != nullptr) {   // weighted budget term of the ROI attack
+        const float4 w = __ldg(w_in + i);
+        g.x *= w.x; g.y *= w.y; g.z *= w.z; g.w *= w.w;
+      }
     }
     g.x = clamp_chain_grad(g.x, s.x, z.x, eps);
     g.y = clamp_chain_grad(g.y, s.y, z.y, eps);
@@ -206,7 +215,8 @@ __global__ void __launch_bounds__(256) output_loss_kernel(const float4* __restri
                                                           float4* __restrict__ g_x, float* __restrict__ ws,
                                                           int64_t per_img4, int do_clamp, float grad_scale,
                                                           const int* __restrict__ active,
-                                                          const int* __restrict__ n_active) {
+                                                          const int* __restrict__ n_active,
+                                                          const float4* __restrict__ w_out) {
   __shared__ float red[8];
   const int slot = blockIdx.y;
   if (n_active != nullptr && slot >= *n_active) return;
@@ -216,13 +226,15 @@ __global__ void __launch_bounds__(256) output_loss_kernel(const float4* __restri
   for (int64_t i = blockIdx.x * 256 + threadIdx.x; i < per_img4; i += (int64_t)gridDim.x * 256) {
     const float4 xv = __ldg(x + base + i), rv = __ldg(ref + base + i);
     const float xs[4] = {xv.x, xv.y, xv.z, xv.w}, rs[4] = {rv.x, rv.y, rv.z, rv.w};
+    const float4 wv = w_out != nullptr ? __ldg(w_out + i) : make_float4(1.f, 1.f, 1.f, 1.f);
+    const float wk[4] = {wv.x, wv.y, wv.z, wv.w};
     float gs[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       const float o = do_clamp ? clampf(xs[k], 0.f, 1.f) : xs[k];
       const float d = rs[k] - o;
-      acc += d * d;
-      float g = 2.f * d * grad_scale;   // d(1 - mean(d^2)) / d o
+      acc += wk[k] * d * d;
+      float g = 2.f * wk[k] * d * grad_scale;   // d(1 - mean(w d^2)) / d o  (grad_scale < 0: d(+mean(w d^2)) / d o)
       if (do_clamp) {
         const float l = fmaxf(xs[k], 0.f);
         g = ((l <= 1.f) || (g > 0.f)) ? g : 0.f;
@@ -291,6 +303,14 @@ int icadv_perturb_forward(const float* im_s, const float* noise, float* im_in, f
                           const icadv_perturb_state* st, int n_img, int64_t per_img, float eps, float noise_budget,
                           int force_branch, double lr0, double lr_gamma, int sched_period, double beta1,
                           double beta2, icadv_stream_t stream) {
+  return icadv_perturb_forward_roi(im_s, noise, im_in, ws, st, n_img, per_img, eps, noise_budget, force_branch, lr0,
+                                   lr_gamma, sched_period, beta1, beta2, nullptr, 0, stream);
+}
+
+int icadv_perturb_forward_roi(const float* im_s, const float* noise, float* im_in, float* ws,
+                              const icadv_perturb_state* st, int n_img, int64_t per_img, float eps,
+                              float noise_budget, int force_branch, double lr0, double lr_gamma, int sched_period,
+                              double beta1, double beta2, const float* w_in, int ge_test, icadv_stream_t stream) {
   ICADV_REQUIRE(im_s && noise && im_in && ws && st, "null pointer");
   ICADV_REQUIRE(per_img % 4 == 0, "per_img must be a multiple of 4");
   ICADV_REQUIRE(n_img >= 1 && n_img <= 1024, "n_img must be in [1,1024]");
@@ -298,10 +318,11 @@ int icadv_perturb_forward(const float* im_s, const float* noise, float* im_in, f
   dim3 grid(kRedBlocks, n_img);
   perturb_forward_kernel<<<grid, 256, 0, as_stream(stream)>>>(
       reinterpret_cast<const float4*>(im_s), reinterpret_cast<const float4*>(noise),
-      reinterpret_cast<float4*>(im_in), ws, per_img / 4, eps);
+      reinterpret_cast<float4*>(im_in), ws, per_img / 4, eps, reinterpret_cast<const float4*>(w_in));
   ICADV_CUDA_TRY(cudaGetLastError());
   perturb_finalize_kernel<<<1, 1024, 0, as_stream(stream)>>>(ws, *st, n_img, 1.0 / (double)per_img, noise_budget,
-                                                              force_branch, lr0, lr_gamma, sched_period, beta1, beta2);
+                                                              force_branch, lr0, lr_gamma, sched_period, beta1, beta2,
+                                                              ge_test);
   ICADV_CUDA_TRY(cudaGetLastError());
   return ICADV_OK;
 }
@@ -311,6 +332,14 @@ int icadv_perturb_update_adam(const float* im_s, float* noise, const float* g_in
                               const icadv_perturb_state* st, int n_img, int64_t per_img, float eps, double beta1,
                               double beta2, double adam_eps, float gradA_scale, float gradB_scale,
                               icadv_stream_t stream) {
+  return icadv_perturb_update_adam_roi(im_s, noise, g_in, g_a_ext, m, v, st, n_img, per_img, eps, beta1, beta2, adam_eps,
+                                       gradA_scale, gradB_scale, nullptr, stream);
+}
+
+int icadv_perturb_update_adam_roi(const float* im_s, float* noise, const float* g_in, const float* g_a_ext, float* m,
+                                  float* v, const icadv_perturb_state* st, int n_img, int64_t per_img, float eps,
+                                  double beta1, double beta2, double adam_eps, float gradA_scale, float gradB_scale,
+                                  const float* w_in, icadv_stream_t stream) {
   ICADV_REQUIRE(im_s && noise && m && v && st, "null pointer");
   ICADV_REQUIRE(per_img % 4 == 0, "per_img must be a multiple of 4");
   dim3 grid(kRedBlocks, n_img);
@@ -320,7 +349,7 @@ int icadv_perturb_update_adam(const float* im_s, float* noise, const float* g_in
       reinterpret_cast<const float4*>(im_s), reinterpret_cast<float4*>(noise),
       reinterpret_cast<const float4*>(g_in), reinterpret_cast<const float4*>(g_a_ext), reinterpret_cast<float4*>(m),
       reinterpret_cast<float4*>(v), *st,
-      per_img / 4, eps, coef, gradA_scale, gradB_scale);
+      per_img / 4, eps, coef, gradA_scale, gradB_scale, reinterpret_cast<const float4*>(w_in));
   ICADV_CUDA_TRY(cudaGetLastError());
   return ICADV_OK;
 }
@@ -350,13 +379,21 @@ int icadv_mifgsm_update(const float* im_s, float* im_adv, const float* g, float*
 int icadv_output_loss(const float* x, const float* ref, float* g_x, float* ws, float* sum_d2, int n_img,
                       int64_t per_img, int do_clamp, float grad_scale, const int* active, const int* n_active,
                       icadv_stream_t stream) {
+  return icadv_output_loss_roi(x, ref, g_x, ws, sum_d2, n_img, per_img, do_clamp, grad_scale, active, n_active, nullptr,
+                               stream);
+}
+
+int icadv_output_loss_roi(const float* x, const float* ref, float* g_x, float* ws, float* sum_d2, int n_img,
+                          int64_t per_img, int do_clamp, float grad_scale, const int* active, const int* n_active,
+                          const float* w_out, icadv_stream_t stream) {
   ICADV_REQUIRE(x && ref && ws && sum_d2, "null pointer");
   ICADV_REQUIRE(per_img % 4 == 0, "per_img must be a multiple of 4");
   dim3 grid(kRedBlocks, n_img);
   output_loss_kernel<<<grid, 256, 0, as_stream(stream)>>>(reinterpret_cast<const float4*>(x),
                                                           reinterpret_cast<const float4*>(ref),
                                                           reinterpret_cast<float4*>(g_x), ws, per_img / 4, do_clamp,
-                                                          grad_scale, active, n_active);
+                                                          grad_scale, active, n_active,
+                                                          reinterpret_cast<const float4*>(w_out));
   ICADV_CUDA_TRY(cudaGetLastError());
   sum_finalize_kernel<<<(n_img + 127) / 128, 128, 0, as_stream(stream)>>>(ws, sum_d2, n_img, active, n_active);
   ICADV_CUDA_TRY(cudaGetLastError());

@@ -17,13 +17,39 @@ from . import ops
 from .program import StackProgram, parse_stack
 
 
+class RoiSpec:
+    """Targeted / ROI attack configuration (flags ``-t``, ``--mask_loc``, ``-la_bkg_in``, ``-la_bkg_out``, ``-la_tar``;
+    coder.py:198-203).  ``mask_loc = (x0, x1, y0, y1)``: W range then H range of the target area (attack_cv.py:160-161);
+    None = the whole image is the target area."""
+
+    def __init__(self, mask_loc=None, lamb_bkg_in=1.0, lamb_bkg_out=1.0, lamb_tar=1.0):
+        self.mask_loc = tuple(mask_loc) if mask_loc is not None else None
+        self.lamb_bkg_in, self.lamb_bkg_out, self.lamb_tar = float(lamb_bkg_in), float(lamb_bkg_out), float(lamb_tar)
+
+    def key(self):
+        return (self.mask_loc, self.lamb_bkg_in, self.lamb_bkg_out, self.lamb_tar)
+
+    def maps(self, height, width, device):
+        """(mask_tar, w_in, w_out) as [H, W, 3] channels-last maps (set-up, once per engine)."""
+        tar = torch.ones(height, width, 3, device=device)
+        if self.mask_loc is not None:
+            x0, x1, y0, y1 = self.mask_loc
+            tar.zero_()
+            tar[y0:y1, x0:x1, :] = 1.0
+        bkg = 1.0 - tar
+        return tar, (tar + self.lamb_bkg_in * bkg).contiguous(), (self.lamb_tar * tar + self.lamb_bkg_out * bkg).contiguous()
+
+
 class AttackEngine:
     def __init__(self, net, n_img, height, width, *, steps, epsilon=16.0, noise_budget=1e-4, lr_attack=0.01,
-                 clamp=True, att_metric="L2", force_branch=-1, use_graph=True, device=None):
+                 clamp=True, att_metric="L2", force_branch=-1, use_graph=True, device=None, roi=None):
         ops.require_device()
         if att_metric not in ("L2", "ms-ssim"):
             raise L.IcadvError(f"AttackEngine: -att_metric {att_metric} is not supported (L2, ms-ssim)")
         self.att_metric = att_metric
+        self.roi = roi
+        if roi is not None and att_metric != "L2":
+            raise L.IcadvError("AttackEngine: the targeted / ROI loss is defined for -att_metric L2 only")
         if att_metric == "ms-ssim":
             use_graph = False   # the MS-SSIM composition allocates its pyramid per call; runs eagerly for now
         if steps < 3:
@@ -40,7 +66,19 @@ class AttackEngine:
         self.st = ops.PerturbState(n_img, dev)
         self.loss_o_sum = f(n_img)
         self.ws_out = f(n_img * L.RED_BLOCKS)
+        self.w_in = self.w_out = self.mask_tar = None
+        if roi is not None:
+            self.mask_tar, self.w_in, self.w_out = roi.maps(height, width, dev)
         act, nact = self.st.active, self.st.n_active
+        self._build_network(net, n_img, height, width, dev, act, nact)
+        self._graph = None
+        self.iterations_done = 0
+        self.im_s_nchw = self.output_s_nchw = None
+        self.last_loss_A = f(n_img)   # loss of the budget branch per image (loss_i, or 1 - ms_ssim(im_s, im_in))
+        self.last_loss_B = f(n_img)   # loss of the network branch per image (1 - MSE, ms_ssim(out, output_s), or loss_o)
+
+    def _build_network(self, net, n_img, height, width, dev, act, nact):
+        f = lambda *s: torch.zeros(*s, device=dev, dtype=torch.float32)
         ga_units, gs_units = parse_stack(net.g_a), parse_stack(net.g_s)
         lat_h, lat_w = height, width
         for u in ga_units:
@@ -53,17 +91,19 @@ class AttackEngine:
                                n_active=nact, round_final_gin=True)
         self.x_out, self.g_x = self.gs.out, self.gs.g_out
         assert self.x_out.shape == self.im_s.shape, (self.x_out.shape, self.im_s.shape)
-        self._graph = None
-        self.iterations_done = 0
-        self.im_s_nchw = self.output_s_nchw = None
-        self.last_loss_A = f(n_img)   # loss of the budget branch per image (loss_i, or 1 - ms_ssim(im_s, im_in))
-        self.last_loss_B = f(n_img)   # loss of the network branch per image (1 - MSE, or ms_ssim(out, output_s))
 
     # ------------------------------------------------------------------ state
-    def load(self, im_s_nchw, output_s_nchw, noise_init_nchw=None):
-        """Start a new attack on a batch: copies inputs in, zeroes the perturbation and Adam state."""
+    def load(self, im_s_nchw, output_s_nchw, noise_init_nchw=None, output_t_nchw=None):
+        """Start a new attack on a batch: copies inputs in, zeroes the perturbation and Adam state.
+        ROI attack: ``output_t_nchw`` is the clean reconstruction of the target image; the distortion reference becomes
+        output_t inside the target area and output_s outside (a one-time select, not part of the loop)."""
         self.im_s.copy_(im_s_nchw.permute(0, 2, 3, 1))
         self.output_s.copy_(output_s_nchw.permute(0, 2, 3, 1))
+        if self.roi is not None:
+            if output_t_nchw is None:
+                raise L.IcadvError("ROI attack: load() needs output_t")
+            self.output_s.copy_(torch.where(self.mask_tar.unsqueeze(0) > 0, output_t_nchw.permute(0, 2, 3, 1),
+                                            self.output_s))
         if self.att_metric == "ms-ssim":
             self.im_s_nchw = im_s_nchw.detach().contiguous().clone()
             self.output_s_nchw = output_s_nchw.detach().contiguous().clone()
@@ -81,20 +121,33 @@ class AttackEngine:
         self.gs.refresh_parameters()
 
     # ------------------------------------------------------------------ one iteration
+    def _perturb_forward(self):
+        ops.perturb_forward(self.im_s, self.noise, self.im_in, self.st, eps=self.eps, budget=self.budget,
+                            force_branch=self.force_branch, lr0=self.lr0, lr_gamma=0.33,
+                            sched_period=self.steps // 3, w_in=self.w_in, ge_test=self.roi is not None)
+
+    def _output_loss(self, x_out, g_x):
+        # untargeted: loss = 1 - mean(d^2) (attack_rd.py:364), seed +2d/P; ROI: loss = +mean(w d^2), seed -2wd/P
+        sign = -1.0 if self.roi is not None else 1.0
+        ops.output_loss(x_out, self.output_s, g_x, self.ws_out, self.loss_o_sum, do_clamp=self.clamp,
+                        grad_scale=sign / self.per_img, active=self.st.active, n_active=self.st.n_active,
+                        w_out=self.w_out)
+
+    def _network_pass(self):
+        self.ga.forward()
+        self.gs.forward()
+        self._output_loss(self.x_out, self.g_x)
+        self.gs.backward()
+        self.ga.backward()
+        return self.ga.g_in
+
     def _iteration(self):
         if self.att_metric == "ms-ssim":
             return self._iteration_msssim()
-        ops.perturb_forward(self.im_s, self.noise, self.im_in, self.st, eps=self.eps, budget=self.budget,
-                            force_branch=self.force_branch, lr0=self.lr0, lr_gamma=0.33,
-                            sched_period=self.steps // 3)
-        self.ga.forward()
-        self.gs.forward()
-        ops.output_loss(self.x_out, self.output_s, self.g_x, self.ws_out, self.loss_o_sum, do_clamp=self.clamp,
-                        grad_scale=1.0 / self.per_img, active=self.st.active, n_active=self.st.n_active)
-        self.gs.backward()
-        self.ga.backward()
-        ops.perturb_update_adam(self.im_s, self.noise, self.ga.g_in, self.m, self.v, self.st, eps=self.eps,
-                                gradA_scale=1.0 / self.per_img, gradB_scale=1.0)
+        self._perturb_forward()
+        g_in = self._network_pass()
+        ops.perturb_update_adam(self.im_s, self.noise, g_in, self.m, self.v, self.st, eps=self.eps,
+                                gradA_scale=1.0 / self.per_img, gradB_scale=1.0, w_in=self.w_in)
 
     def _iteration_msssim(self):
         """-att_metric ms-ssim (attack_rd.py:335-336, 360-362): budget branch loss = 1 - ms_ssim(im_s, im_in),
@@ -145,7 +198,8 @@ class AttackEngine:
             if record is not None:
                 if self.att_metric == "L2":
                     self.last_loss_A = self.st.loss_i
-                    self.last_loss_B = 1.0 - self.loss_o_sum / self.per_img
+                    mse_o = self.loss_o_sum / self.per_img
+                    self.last_loss_B = mse_o if self.roi is not None else 1.0 - mse_o
                 br = self.st.branch.cpu().clone()
                 loss = torch.where(br == 1, self.last_loss_B.cpu(), self.last_loss_A.cpu())
                 record.append((br, self.st.loss_i.cpu().clone(), loss))
@@ -178,6 +232,44 @@ class AttackEngine:
         """Recompute im_in from the final perturbation?  No: the reference evaluates the im_in of the LAST
         iteration (attack_rd.py:561,573), i.e. before the last optimizer step.  Returns that tensor."""
         return self.im_in_nchw()
+
+
+class GenericAttackEngine(AttackEngine):
+    """Same loop for codecs whose ``g_a`` / ``g_s`` are not plain conv/GDN stacks (cheng2020_anchor: residual blocks,
+    sub-pixel convolutions): the network pass runs module by module through the autograd Functions of ``functional``
+    (every FLOP still in the library), over the whole batch; the perturbation kernels, branch logic and Adam are the
+    fused ones.  No CUDA graph (autograd allocates)."""
+
+    def _build_network(self, net, n_img, height, width, dev, act, nact):
+        if self.att_metric != "L2":
+            raise L.IcadvError("GenericAttackEngine: only -att_metric L2 is built for non-stack codecs")
+        self.use_graph = False
+        self.g_x = torch.zeros(n_img, height, width, 3, device=dev, dtype=torch.float32)
+
+    def refresh_parameters(self):
+        pass
+
+    def kernels_per_iteration(self):
+        return -1
+
+    def _network_pass(self):
+        from . import functional as Fn
+        net = self.net
+        params = [p for p in net.parameters() if p.requires_grad]
+        for p in params:               # the attack never reads parameter gradients (attack_rd.py:546-548)
+            p.requires_grad_(False)
+        try:
+            x_in = self.im_in.permute(0, 3, 1, 2).detach().requires_grad_(True)
+            with torch.enable_grad():
+                out = net.g_s(net.g_a(x_in))
+            x_out = Fn.to_nhwc(out.detach()).contiguous()
+            self.g_x.zero_()           # rows of budget-branch images stay zero
+            self._output_loss(x_out, self.g_x)
+            out.backward(Fn.to_nchw(self.g_x))
+        finally:
+            for p in params:
+                p.requires_grad_(True)
+        return Fn.to_nhwc(x_in.grad).contiguous()
 
 
 class IfgsmEngine:

@@ -5,6 +5,8 @@ Every op here is a ``torch.autograd.Function`` whose forward and backward call t
 Mirrors: nn.Conv2d / nn.ConvTranspose2d (anchors/utils.py:112-130), compressai GDN
 (utils/ops.py:58-97), ops.Low_bound / ops.Up_bound (utils/ops.py:28-56).
 """
+import weakref
+
 import torch
 
 from . import _lib as L
@@ -25,21 +27,28 @@ def to_nchw(x_nhwc):
 
 def tc_shape(k_ch, n_ch):
     """Shapes the tensor path takes (mirrors icadv_conv_tc_supported for the linear epilogue)."""
-    return k_ch % 32 == 0 and n_ch % 32 == 0 and 32 <= n_ch <= 256
+    if k_ch % 32 or n_ch % 32 or k_ch < 32 or n_ch < 32:
+        return False
+    return n_ch <= 256 or any(n_ch % t == 0 for t in range(256, 31, -32))   # wider outputs are tiled over N
 
 
 def packed(weight, kind):
     """Packed copy of a layer weight, cached on (storage, version) so it is rebuilt only after an update.
     Weights of tensor-path contractions are rounded to TF32 (nearest) here."""
-    key = (weight.data_ptr(), kind)
+    key = (id(weight), kind)
     hit = _PACK_CACHE.get(key)
-    if hit is not None and hit[0] == weight._version and hit[2] == tuple(weight.shape):
+    # the entry must belong to THIS tensor object (ids and addresses are recycled once a model is freed)
+    if hit is not None and hit[3]() is weight and hit[0] == weight._version and hit[2] == tuple(weight.shape) \
+            and hit[4] == weight.data_ptr():
         return hit[1]
+    if len(_PACK_CACHE) > 512:
+        for k in [k for k, v in _PACK_CACHE.items() if v[3]() is None]:
+            del _PACK_CACHE[k]
     a, b = weight.shape[0], weight.shape[1]
     n_ch, k_ch = {L.PACK_CONV_FWD: (a, b), L.PACK_CONV_DGRAD: (b, a), L.PACK_CONVT_FWD: (b, a),
                   L.PACK_CONVT_DGRAD: (a, b)}[kind]
     wp = ops.pack_weight(weight, kind, round_tf32=tc_shape(k_ch, n_ch))
-    _PACK_CACHE[key] = (weight._version, wp, tuple(weight.shape))
+    _PACK_CACHE[key] = (weight._version, wp, tuple(weight.shape), weakref.ref(weight), weight.data_ptr())
     return wp
 
 
@@ -158,3 +167,74 @@ class ActFn(torch.autograd.Function):
         (xc,) = ctx.saved_tensors
         gc = g.contiguous(memory_format=torch.channels_last) if g.dim() == 4 else g.contiguous()
         return ops.act_backward(xc, gc, ctx.act), None
+
+
+class AddFn(torch.autograd.Function):
+    """a + b (residual connections of the cheng2020 blocks); both operands channels_last, same shape."""
+
+    @staticmethod
+    def forward(ctx, a, b):
+        ac = a.contiguous(memory_format=torch.channels_last)
+        bc = b.contiguous(memory_format=torch.channels_last)
+        return ops.unary(ac, 4, bc)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g, g
+
+
+class PixelShuffleFn(torch.autograd.Function):
+    """nn.PixelShuffle(r) (compressai subpel_conv3x3)."""
+
+    @staticmethod
+    def forward(ctx, x, r):
+        ctx.r = r
+        return to_nchw(ops.pixel_shuffle(to_nhwc(x).contiguous(), r))
+
+    @staticmethod
+    def backward(ctx, g):
+        return to_nchw(ops.pixel_shuffle(to_nhwc(g).contiguous(), ctx.r, inverse=True)), None
+
+
+class CatFn(torch.autograd.Function):
+    """torch.cat((a, b), dim=1) on channels_last tensors (anchors/model.py:104)."""
+
+    @staticmethod
+    def forward(ctx, a, b):
+        an, bn = to_nhwc(a).contiguous(), to_nhwc(b).contiguous()
+        ca, cb = an.shape[-1], bn.shape[-1]
+        out = torch.empty(*an.shape[:-1], ca + cb, device=a.device, dtype=torch.float32)
+        ops.copy_channels(an, out, 0, 0, ca)
+        ops.copy_channels(bn, out, 0, ca, cb)
+        ctx.split = (ca, cb)
+        return to_nchw(out)
+
+    @staticmethod
+    def backward(ctx, g):
+        ca, cb = ctx.split
+        gn = to_nhwc(g).contiguous()
+        ga = torch.empty(*gn.shape[:-1], ca, device=g.device, dtype=torch.float32)
+        gb = torch.empty(*gn.shape[:-1], cb, device=g.device, dtype=torch.float32)
+        ops.copy_channels(gn, ga, 0, 0, ca)
+        ops.copy_channels(gn, gb, ca, 0, cb)
+        return to_nchw(ga), to_nchw(gb)
+
+
+class NarrowFn(torch.autograd.Function):
+    """x[:, start:start+count] (one half of ``chunk(2, 1)``, anchors/model.py:105) as a dense channels_last tensor."""
+
+    @staticmethod
+    def forward(ctx, x, start, count):
+        xn = to_nhwc(x).contiguous()
+        out = torch.empty(*xn.shape[:-1], count, device=x.device, dtype=torch.float32)
+        ops.copy_channels(xn, out, start, 0, count)
+        ctx.cfg = (start, count, xn.shape[-1])
+        return to_nchw(out)
+
+    @staticmethod
+    def backward(ctx, g):
+        start, count, c = ctx.cfg
+        gn = to_nhwc(g).contiguous()
+        gx = torch.zeros(*gn.shape[:-1], c, device=g.device, dtype=torch.float32)
+        ops.copy_channels(gn, gx, 0, start, count)
+        return to_nchw(gx), None, None

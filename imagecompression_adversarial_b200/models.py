@@ -64,6 +64,46 @@ def conv(cin, cout, kernel_size=5, stride=2):
     return Conv2d(cin, cout, kernel_size, stride)
 
 
+def conv3x3(cin, cout, stride=1):
+    return Conv2d(cin, cout, 3, stride)
+
+
+def conv1x1(cin, cout, stride=1):
+    return Conv2d(cin, cout, 1, stride)
+
+
+class PixelShuffle(nn.Module):
+    def __init__(self, r):
+        super().__init__()
+        self.r = int(r)
+
+    def forward(self, x):
+        return Fn.PixelShuffleFn.apply(x, self.r)
+
+
+def subpel_conv3x3(cin, cout, r=1):
+    """compressai.layers.subpel_conv3x3: conv3x3 to cout*r*r channels + PixelShuffle(r)."""
+    return nn.Sequential(Conv2d(cin, cout * r * r, 3, 1), PixelShuffle(r))
+
+
+class MaskedConv2d(Conv2d):
+    """compressai.layers.MaskedConv2d, type-A mask (mbt2018 ``context_prediction``, call site anchors/model.py:103):
+    the weight is masked in place at every forward, as CompressAI does."""
+
+    def __init__(self, in_channels, out_channels, kernel_size=5, stride=1, mask_type="A"):
+        super().__init__(in_channels, out_channels, kernel_size, stride)
+        mask = torch.ones_like(self.weight.data)
+        k = kernel_size
+        mask[:, :, k // 2, k // 2 + (mask_type == "B"):] = 0
+        mask[:, :, k // 2 + 1:] = 0
+        self.register_buffer("mask", mask)
+
+    def forward(self, x):
+        with torch.no_grad():
+            self.weight.mul_(self.mask)
+        return super().forward(x)
+
+
 def deconv(cin, cout, kernel_size=5, stride=2):
     return ConvTranspose2d(cin, cout, kernel_size, stride)
 
@@ -124,6 +164,53 @@ def ReLU(inplace=True):
 
 def LeakyReLU(inplace=True):
     return Activation(L.ACT_LEAKY)
+
+
+class ResidualBlockWithStride(nn.Module):
+    """compressai.layers.ResidualBlockWithStride (cheng2020_anchor g_a)."""
+
+    def __init__(self, cin, cout, stride=2):
+        super().__init__()
+        self.conv1 = conv3x3(cin, cout, stride)
+        self.leaky_relu = LeakyReLU()
+        self.conv2 = conv3x3(cout, cout)
+        self.gdn = GDN(cout)
+        self.skip = conv1x1(cin, cout, stride) if (stride != 1 or cin != cout) else None
+
+    def forward(self, x):
+        out = self.gdn(self.conv2(self.leaky_relu(self.conv1(x))))
+        return Fn.AddFn.apply(out, x if self.skip is None else self.skip(x))
+
+
+class ResidualBlockUpsample(nn.Module):
+    """compressai.layers.ResidualBlockUpsample (cheng2020_anchor g_s)."""
+
+    def __init__(self, cin, cout, upsample=2):
+        super().__init__()
+        self.subpel_conv = subpel_conv3x3(cin, cout, upsample)
+        self.leaky_relu = LeakyReLU()
+        self.conv = conv3x3(cout, cout)
+        self.igdn = GDN(cout, inverse=True)
+        self.upsample = subpel_conv3x3(cin, cout, upsample)
+
+    def forward(self, x):
+        out = self.igdn(self.conv(self.leaky_relu(self.subpel_conv(x))))
+        return Fn.AddFn.apply(out, self.upsample(x))
+
+
+class ResidualBlock(nn.Module):
+    """compressai.layers.ResidualBlock."""
+
+    def __init__(self, cin, cout):
+        super().__init__()
+        self.conv1 = conv3x3(cin, cout)
+        self.leaky_relu = LeakyReLU()
+        self.conv2 = conv3x3(cout, cout)
+        self.skip = conv1x1(cin, cout) if cin != cout else None
+
+    def forward(self, x):
+        out = self.leaky_relu(self.conv2(self.leaky_relu(self.conv1(x))))
+        return Fn.AddFn.apply(out, x if self.skip is None else self.skip(x))
 
 
 class _StackFn(torch.autograd.Function):
@@ -324,13 +411,70 @@ class ScaleHyperprior(CompressionModel):
         return {"x_hat": self.g_s(y_hat), "likelihoods": {"y": y_lik, "z": z_lik}}
 
 
+class JointAutoregressiveHierarchicalPriors(CompressionModel):
+    """compressai mbt2018 (widths pinned by InvCompress/ours.py:22-32); forward of anchors/model.py:96-108."""
+
+    def __init__(self, N, M):
+        super().__init__(N)
+        self.g_a, self.g_s = _g_a(N, M), _g_s(N, M)
+        self.h_a = nn.Sequential(conv(M, N, 3, 1), LeakyReLU(), conv(N, N), LeakyReLU(), conv(N, N))
+        self.h_s = nn.Sequential(deconv(N, M), LeakyReLU(), deconv(M, M * 3 // 2), LeakyReLU(),
+                                 conv(M * 3 // 2, M * 2, 3, 1))
+        self.entropy_parameters = nn.Sequential(
+            Conv2d(M * 12 // 3, M * 10 // 3, 1, 1), LeakyReLU(),
+            Conv2d(M * 10 // 3, M * 8 // 3, 1, 1), LeakyReLU(),
+            Conv2d(M * 8 // 3, M * 6 // 3, 1, 1))
+        self.context_prediction = MaskedConv2d(M, 2 * M, kernel_size=5, stride=1)
+        self.gaussian_conditional = GaussianConditional()
+        self.N, self.M = N, M
+
+    def forward(self, x):
+        y = self.g_a(x)
+        z = self.h_a(y)                                          # anchors/model.py:98 (no abs)
+        z_hat, z_lik = self.entropy_bottleneck(z)
+        params = self.h_s(z_hat)
+        y_hat = self.gaussian_conditional.quantize(y, "noise" if self.training else "dequantize")   # :102
+        ctx = self.context_prediction(y_hat)
+        gp = self.entropy_parameters(Fn.CatFn.apply(params, ctx))                                  # :104
+        half = gp.shape[1] // 2
+        scales_hat, means_hat = Fn.NarrowFn.apply(gp, 0, half), Fn.NarrowFn.apply(gp, half, half)  # :105
+        _, y_lik = self.gaussian_conditional(y, scales_hat, means=means_hat)
+        return {"x_hat": self.g_s(y_hat), "likelihoods": {"y": y_lik, "z": z_lik}}
+
+
+class Cheng2020Anchor(JointAutoregressiveHierarchicalPriors):
+    """compressai cheng2020_anchor (anchors/model.py:77; widths pinned by InvCompress/ours.py:33-55): residual blocks,
+    sub-pixel convolutions, no attention, single Gaussian with mean."""
+
+    def __init__(self, N):
+        super().__init__(N, N)
+        self.g_a = nn.Sequential(
+            ResidualBlockWithStride(3, N, 2), ResidualBlock(N, N),
+            ResidualBlockWithStride(N, N, 2), ResidualBlock(N, N),
+            ResidualBlockWithStride(N, N, 2), ResidualBlock(N, N), conv3x3(N, N, 2))
+        self.h_a = nn.Sequential(conv3x3(N, N), LeakyReLU(), conv3x3(N, N), LeakyReLU(), conv3x3(N, N, 2), LeakyReLU(),
+                                 conv3x3(N, N), LeakyReLU(), conv3x3(N, N, 2))
+        self.h_s = nn.Sequential(conv3x3(N, N), LeakyReLU(), subpel_conv3x3(N, N, 2), LeakyReLU(),
+                                 conv3x3(N, N * 3 // 2), LeakyReLU(),
+                                 subpel_conv3x3(N * 3 // 2, N * 3 // 2, 2), LeakyReLU(),
+                                 conv3x3(N * 3 // 2, N * 2))
+        self.g_s = nn.Sequential(
+            ResidualBlock(N, N), ResidualBlockUpsample(N, N, 2), ResidualBlock(N, N),
+            ResidualBlockUpsample(N, N, 2), ResidualBlock(N, N), ResidualBlockUpsample(N, N, 2),
+            ResidualBlock(N, N), subpel_conv3x3(N, 3, 2))
+
+
 def _build(model, quality):
     cfg = ZOO[model][quality]
     if model == "factorized":
         return FactorizedPrior(*cfg)
     if model == "hyper":
         return ScaleHyperprior(*cfg)
-    raise L.IcadvError(f"model family '{model}' is not built yet on the sm_100a path")
+    if model == "context":
+        return JointAutoregressiveHierarchicalPriors(*cfg)
+    if model == "cheng2020":
+        return Cheng2020Anchor(*cfg)
+    raise L.IcadvError(f"unknown model family '{model}'")
 
 
 def _no_zoo(pretrained):

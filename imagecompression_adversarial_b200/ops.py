@@ -102,6 +102,30 @@ def nhwc_to_nchw(x):
     return out
 
 
+def pixel_shuffle(x_nhwc, r, inverse=False):
+    """nn.PixelShuffle(r) on a channels-last tensor [N,H,W,C*r*r] -> [N,H*r,W*r,C] (inverse: the other way)."""
+    _chk(x_nhwc, "x")
+    n, h, w, c = x_nhwc.shape
+    if inverse:
+        lo_h, lo_w, c_out = h // r, w // r, c
+        out = torch.empty(n, lo_h, lo_w, c * r * r, device=x_nhwc.device, dtype=torch.float32)
+    else:
+        lo_h, lo_w, c_out = h, w, c // (r * r)
+        out = torch.empty(n, h * r, w * r, c_out, device=x_nhwc.device, dtype=torch.float32)
+    L.call("icadv_pixel_shuffle", _p(x_nhwc), _p(out), n, lo_h, lo_w, c_out, r, 1 if inverse else 0, _stream())
+    return out
+
+
+def copy_channels(src, dst, src_off, dst_off, count):
+    """dst[..., dst_off:dst_off+count] = src[..., src_off:src_off+count] on channels-last tensors of equal pixel count."""
+    _chk(src, "src")
+    _chk(dst, "dst")
+    n_px = src.numel() // src.shape[-1]
+    assert dst.numel() // dst.shape[-1] == n_px
+    L.call("icadv_copy_channels", _p(src), _p(dst), n_px, src.shape[-1], dst.shape[-1], src_off, dst_off, count, _stream())
+    return dst
+
+
 def gdn_reparam(raw, bound, pedestal, transpose=False, round_tf32=False):
     raw = raw.detach().contiguous()
     _chk(raw, "raw")
@@ -232,24 +256,25 @@ class PerturbState:
 
 
 def perturb_forward(im_s, noise, im_in, st, *, eps, budget, force_branch=-1, lr0=0.01, lr_gamma=0.33, sched_period,
-                    beta1=0.9, beta2=0.999):
+                    beta1=0.9, beta2=0.999, w_in=None, ge_test=False):
     per_img = im_s[0].numel()
-    L.call("icadv_perturb_forward", _p(im_s), _p(noise), _p(im_in), _p(st.ws), C.byref(st.c), st.n_img, per_img,
+    L.call("icadv_perturb_forward_roi", _p(im_s), _p(noise), _p(im_in), _p(st.ws), C.byref(st.c), st.n_img, per_img,
            float(eps), float(budget), int(force_branch), float(lr0), float(lr_gamma), int(sched_period), float(beta1),
-           float(beta2), _stream())
+           float(beta2), _p(w_in), 1 if ge_test else 0, _stream())
 
 
 def perturb_update_adam(im_s, noise, g_in, m, v, st, *, eps, beta1=0.9, beta2=0.999, adam_eps=1e-8, gradA_scale,
-                        gradB_scale=1.0, g_a_ext=None):
+                        gradB_scale=1.0, g_a_ext=None, w_in=None):
     per_img = im_s[0].numel()
-    L.call("icadv_perturb_update_adam", _p(im_s), _p(noise), _p(g_in), _p(g_a_ext), _p(m), _p(v), C.byref(st.c), st.n_img, per_img,
-           float(eps), float(beta1), float(beta2), float(adam_eps), float(gradA_scale), float(gradB_scale), _stream())
+    L.call("icadv_perturb_update_adam_roi", _p(im_s), _p(noise), _p(g_in), _p(g_a_ext), _p(m), _p(v), C.byref(st.c),
+           st.n_img, per_img, float(eps), float(beta1), float(beta2), float(adam_eps), float(gradA_scale),
+           float(gradB_scale), _p(w_in), _stream())
 
 
-def output_loss(x, ref, g_x, ws, sum_d2, *, do_clamp, grad_scale, active=None, n_active=None):
+def output_loss(x, ref, g_x, ws, sum_d2, *, do_clamp, grad_scale, active=None, n_active=None, w_out=None):
     n_img, per_img = x.shape[0], x[0].numel()
-    L.call("icadv_output_loss", _p(x), _p(ref), _p(g_x), _p(ws), _p(sum_d2), n_img, per_img, 1 if do_clamp else 0,
-           float(grad_scale), _p(active), _p(n_active), _stream())
+    L.call("icadv_output_loss_roi", _p(x), _p(ref), _p(g_x), _p(ws), _p(sum_d2), n_img, per_img, 1 if do_clamp else 0,
+           float(grad_scale), _p(active), _p(n_active), _p(w_out), _stream())
 
 
 def sum_sqdiff(a, b):

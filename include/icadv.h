@@ -134,6 +134,15 @@ int icadv_unpack_weight(const float* dwpack, float* dw, int kind, int c_out, int
 int icadv_nchw_to_nhwc(const float* src, float* dst, int n, int c, int h, int w, icadv_stream_t stream);
 int icadv_nhwc_to_nchw(const float* src, float* dst, int n, int c, int h, int w, icadv_stream_t stream);
 
+/* nn.PixelShuffle(r) on channels-last tensors (compressai subpel_conv3x3, cheng2020_anchor g_s / h_s):
+ * dst[n, h*r+i, w*r+j, c] = src[n, h, w, c*r*r + i*r + j]; inverse != 0 applies the inverse permutation (its gradient).
+ * (h, w) is the LOW-resolution size, c_out the channel count after shuffling. */
+int icadv_pixel_shuffle(const float* src, float* dst, int n, int h, int w, int c_out, int r, int inverse,
+                        icadv_stream_t stream);
+/* torch.cat / chunk along channels (anchors/model.py:104-105): dst[px, dst_off + c] = src[px, src_off + c], c < count */
+int icadv_copy_channels(const float* src, float* dst, int64_t n_px, int c_src, int c_dst, int src_off, int dst_off,
+                        int count, icadv_stream_t stream);
+
 /* GDN parameter reparametrisation (compressai NonNegativeParametrizer; utils/ops.py:83-90):
  * eff = max(raw, bound)^2 - pedestal.  transpose != 0 writes eff^T (rows x rows). */
 int icadv_gdn_reparam(const float* raw, float* eff, int rows, int cols, float bound, float pedestal,
@@ -175,6 +184,25 @@ int icadv_perturb_update_adam(const float* im_s, float* noise, const float* g_in
                               const icadv_perturb_state* st, int n_img, int64_t per_img, float eps,
                               double beta1, double beta2, double adam_eps, float gradA_scale,
                               float gradB_scale, icadv_stream_t stream);
+
+/* ROI / targeted variant of the three calls above (flags coder.py:198-203; formulas attack_cv.py:149-163,
+ * attack_data.py:204-221 -- the reference's own call path for them is dead code, so the semantics are the oracle's
+ * restatement, oracle/attack.py attack_our_roi):
+ *   loss_i = mean(w_in d_in^2),  w_in = mask_tar + lamb_bkg_in * mask_bkg;  branch A iff loss_i >= budget (ge_test);
+ *   loss_o = mean(w_out (ref - o)^2), ref = output_t inside the ROI / output_s outside (mixed by the caller),
+ *            w_out = lamb_tar * mask_tar + lamb_bkg_out * mask_bkg; minimised: pass grad_scale = -1/per_img.
+ * w_in / w_out: [per_img] floats in the image layout, shared by all images of the batch; NULL = all ones. */
+int icadv_perturb_forward_roi(const float* im_s, const float* noise, float* im_in, float* ws,
+                              const icadv_perturb_state* st, int n_img, int64_t per_img, float eps,
+                              float noise_budget, int force_branch, double lr0, double lr_gamma, int sched_period,
+                              double beta1, double beta2, const float* w_in, int ge_test, icadv_stream_t stream);
+int icadv_perturb_update_adam_roi(const float* im_s, float* noise, const float* g_in, const float* g_a_ext, float* m,
+                                  float* v, const icadv_perturb_state* st, int n_img, int64_t per_img, float eps,
+                                  double beta1, double beta2, double adam_eps, float gradA_scale, float gradB_scale,
+                                  const float* w_in, icadv_stream_t stream);
+int icadv_output_loss_roi(const float* x, const float* ref, float* g_x, float* ws, float* sum_d2, int n_img,
+                          int64_t per_img, int do_clamp, float grad_scale, const int* active, const int* n_active,
+                          const float* w_out, icadv_stream_t stream);
 
 /* I-FGSM / PGD step (attack_ifgsm.py:409-418): x += alpha*sign(g); project to [x0-eps, x0+eps]. */
 int icadv_ifgsm_update(const float* im_s, float* im_adv, const float* g, int64_t n, float alpha,

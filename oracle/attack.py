@@ -58,6 +58,37 @@ def attack_our(im_s, output_s, im_in, net, args):
     return loss, loss_i, loss_o, branch
 
 
+def roi_masks(im_s, mask_loc):
+    """attack_cv.py:149-163: ``mask_bkg`` is 1 outside ``[y0:y1, x0:x1]`` (``mask_loc = x0 x1 y0 y1``, W then H) and 0
+    inside; without ``--mask_loc`` the whole image is the target area.  Returns (mask_bkg, mask_tar), [1,C,H,W]."""
+    _, C, H, W = im_s.shape
+    mask = torch.zeros(1, C, H, W, device=im_s.device)
+    if mask_loc is not None:
+        mask = torch.ones(1, C, H, W, device=im_s.device)
+        x0, x1, y0, y1 = mask_loc
+        mask[:, :, y0:y1, x0:x1] = 0.0
+    return mask, 1.0 - mask
+
+
+def attack_our_roi(im_s, output_s, output_t, im_in, net, args, mask_bkg, mask_tar):
+    """Targeted / ROI loss.  The reference's own call path for these flags is dead code
+    (attack_rd.py never reads ``-t`` / ``--mask_loc`` in the loss); the formulas are those of attack_cv.py:149-163 and
+    attack_data.py:204-221, with the per-pixel masks INSIDE the means (the reference text multiplies a scalar mean by
+    a mask tensor, which would not even be a scalar loss): THIS restatement is the definition parity is measured on.
+      loss_i = mean(d_in^2 mask_tar) + lamb_bkg_in mean(d_in^2 mask_bkg);   switch on loss_i >= noise (attack_data.py:219)
+      loss_o = lamb_tar mean((out - output_t)^2 mask_tar) + lamb_bkg_out mean((out - output_s)^2 mask_bkg)  (minimised)
+    """
+    d2 = (im_s - im_in) ** 2
+    loss_i = torch.mean(d2 * mask_tar) + args.lamb_bkg_in * torch.mean(d2 * mask_bkg)
+    if loss_i >= args.noise:
+        return loss_i, loss_i, torch.zeros(1), "A"
+    x_ = net.g_s(net.g_a(im_in))
+    output_ = up_bound(low_bound(x_, 0.0), 1.0) if args.clamp else x_
+    loss_o = (args.lamb_tar * torch.mean((output_ - output_t) ** 2 * mask_tar) +
+              args.lamb_bkg_out * torch.mean((output_ - output_s) ** 2 * mask_bkg))
+    return loss_o, loss_i, loss_o, "B"
+
+
 @torch.no_grad()
 def eval_metrics(im_adv, im_s, output_s, net, args):
     """self_ensemble.py:173-252 (defence branches are out of scope)."""
@@ -93,10 +124,15 @@ def clean_pass(im_s, net, args):
     return output_s, bpp_ori, result
 
 
-def attack_(im_s, net, args, record=None, noise_init=None):
+def attack_(im_s, net, args, record=None, noise_init=None, im_t=None):
     """attack_rd.py:381-575.  ``record`` (a list) receives per-step
-    ``(branch, loss, loss_i)``; ``noise_init`` lets a test share the ``-random>1`` start."""
+    ``(branch, loss, loss_i)``; ``noise_init`` lets a test share the ``-random>1`` start; ``im_t`` (the ``-t`` image)
+    switches to the targeted / ROI loss ``attack_our_roi``."""
     output_s, bpp_ori, _ = clean_pass(im_s, net, args)
+    roi = im_t is not None
+    if roi:
+        output_t = clean_pass(im_t, net, args)[0]
+        mask_bkg, mask_tar = roi_masks(im_s, args.mask_loc)
     noise_range = args.epsilon / 255.0                                  # :490
     if noise_init is not None:
         noise = noise_init.clone()
@@ -111,7 +147,10 @@ def attack_(im_s, net, args, record=None, noise_init=None):
     for i in range(args.steps):
         noise_clipped = up_bound(low_bound(noise, -noise_range), noise_range)      # :507
         im_in = up_bound(low_bound(im_s + noise_clipped, 0.0), 1.0)                # :517
-        loss, loss_i, loss_o, branch = attack_our(im_s, output_s, im_in, net, args)
+        if roi:
+            loss, loss_i, loss_o, branch = attack_our_roi(im_s, output_s, output_t, im_in, net, args, mask_bkg, mask_tar)
+        else:
+            loss, loss_i, loss_o, branch = attack_our(im_s, output_s, im_in, net, args)
         optimizer.zero_grad()
         loss.backward()
         optimizer.step()                                                # :546-548

@@ -42,7 +42,10 @@ def psnr(a, b):
     return -10.0 * math.log10(float(torch.mean((a - b) ** 2)) + 1e-30)
 
 
-@pytest.mark.parametrize("model,quality,hw", [("factorized", 1, (64, 96)), ("hyper", 3, (128, 192))])
+@pytest.mark.parametrize("model,quality,hw", [("factorized", 1, (64, 96)), ("hyper", 3, (128, 192)),
+                                              ("hyper", 6, (64, 128)), ("context", 4, (128, 192)),
+                                              ("context", 5, (64, 64)), ("cheng2020", 1, (128, 128)),
+                                              ("cheng2020", 6, (64, 128))])
 def test_eval_forward_matches_oracle(dev, model, quality, hw):
     onet, pnet = pair(model, quality, dev)
     x = images(2, *hw, dev)
@@ -52,7 +55,18 @@ def test_eval_forward_matches_oracle(dev, model, quality, hw):
         yo, yp = onet.g_a(x), pnet.g_a(x)
     assert p["x_hat"].shape == o["x_hat"].shape
     rms = float((yp - yo).pow(2).mean().sqrt() / yo.pow(2).mean().sqrt())
-    assert rms < 2e-3, rms
+    # cheng2020's g_a is 20 contractions deep (7 blocks): the unbiased TF32 error adds in quadrature
+    assert rms < (4e-3 if model == "cheng2020" else 2e-3), rms
+    if model in ("context", "cheng2020"):
+        # the context model feeds round(y) back through context_prediction -> means: ONE latent that rounds the other way
+        # (a TF32-vs-fp32 near-tie) moves means, likelihoods and x_hat around it.  Compare the entropy path on the
+        # ORACLE's latent instead (below: test_context_entropy_path_matches_oracle) and only bound the end metrics here.
+        num_px = x.shape[0] * hw[0] * hw[1]
+        bpp_o = sum(float(torch.log(l).sum()) for l in o["likelihoods"].values()) / (-math.log(2) * num_px)
+        bpp_p = sum(float(torch.log(l).sum()) for l in p["likelihoods"].values()) / (-math.log(2) * num_px)
+        assert abs(bpp_o - bpp_p) < 2e-2 * abs(bpp_o), (bpp_o, bpp_p)
+        assert abs(psnr(p["x_hat"], x) - psnr(o["x_hat"], x)) < 0.1
+        return
     # quantised latent indices: equal wherever the oracle's y is not within the guard band of a .5 boundary
     med = 0.0
     frac = (yo - med) - torch.floor(yo - med)
@@ -235,3 +249,105 @@ def test_ifgsm_matches_oracle(dev, momentum):
     # a sign step moves every pixel by eps/steps, so mse_in is insensitive to isolated sign flips
     assert abs(p[5] - o[5]["mse_in"]) <= 2e-3 * o[5]["mse_in"]
     assert abs(psnr(p[0], x) - psnr(o[0], x)) < 0.05
+
+
+@pytest.mark.parametrize("model,quality,hw", [("context", 4, (128, 192)), ("cheng2020", 1, (128, 128))])
+def test_context_entropy_path_matches_oracle(dev, model, quality, hw):
+    """h_a, EntropyBottleneck, h_s, MaskedConv2d context_prediction, entropy_parameters, GaussianConditional with means
+    (anchors/model.py:96-108) on the SAME latent y in both implementations."""
+    from imagecompression_adversarial_b200 import functional as Fn
+    onet, pnet = pair(model, quality, dev)
+    onet.eval(); pnet.eval()
+    x = images(1, *hw, dev)
+    with torch.no_grad():
+        y = onet.g_a(x)
+        # oracle
+        z = onet.h_a(y)
+        z_hat, z_lik = onet.entropy_bottleneck(z)
+        params = onet.h_s(z_hat)
+        y_hat = onet.gaussian_conditional.quantize(y, "dequantize")
+        ctx = onet.context_prediction(y_hat)
+        gp = onet.entropy_parameters(torch.cat((params, ctx), dim=1))
+        sc, mu = gp.chunk(2, 1)
+        _, y_lik = onet.gaussian_conditional(y, sc, means=mu)
+        # product, same y
+        zp = pnet.h_a(y)
+        zp_hat, zp_lik = pnet.entropy_bottleneck(zp)
+        rz = float((zp - z).pow(2).mean().sqrt() / z.pow(2).mean().sqrt())
+        assert rz < 2e-3, rz
+        params_p = pnet.h_s(z_hat)
+        yp_hat = pnet.gaussian_conditional.quantize(y, "dequantize")
+        assert torch.equal(yp_hat, y_hat)
+        ctx_p = pnet.context_prediction(y_hat)
+        r = float((ctx_p - ctx).pow(2).mean().sqrt() / ctx.pow(2).mean().sqrt())
+        assert r < 2e-3, r
+        gp_p = pnet.entropy_parameters(Fn.CatFn.apply(params_p, ctx_p))
+        r = float((gp_p - gp).pow(2).mean().sqrt() / gp.pow(2).mean().sqrt())
+        assert r < 3e-3, r
+        half = gp.shape[1] // 2
+        _, yp_lik = pnet.gaussian_conditional(y, Fn.NarrowFn.apply(gp, 0, half), means=Fn.NarrowFn.apply(gp, half, half))
+        torch.testing.assert_close(yp_lik, y_lik, rtol=2e-4, atol=1e-7)
+    # the type-A mask is applied to the weight in place, as CompressAI does
+    w = pnet.context_prediction.weight
+    assert float(w[:, :, 2, 2:].abs().max()) == 0.0 and float(w[:, :, 3:].abs().max()) == 0.0
+
+
+def test_roi_targeted_attack_matches_oracle(dev):
+    """-t / --mask_loc / -la_* (SURVEY section 8 a12): fused loop with weight maps vs the oracle's attack_our_roi."""
+    from imagecompression_adversarial_b200 import attack as patk
+    from oracle import attack as oatk
+    onet, pnet = pair("hyper", 3, dev)
+    x = images(1, 192, 256, dev)
+    t = images(3, 192, 256, dev)[2:3]
+    args = oatk.default_args(model="hyper", quality=3, metric="mse", steps=9, noise=3e-5, mask_loc=[40, 168, 24, 152],
+                             lamb_bkg_in=0.5, lamb_bkg_out=2.0, lamb_tar=1.5)
+    rec, orec = [], []
+    p = patk.attack_(x, pnet, args, record=rec, im_t=t)
+    o = oatk.attack_(x, onet, args, record=orec, im_t=t)
+    seen = set()
+    for k, (br, loss, loss_i) in enumerate(orec):
+        pb, pli, pl = int(rec[k][0][0]), float(rec[k][1][0]), float(rec[k][2][0])
+        assert (pb == 1) == (br == "B"), (k, pb, br, pli, loss_i)
+        seen.add(br)
+        assert abs(pli - loss_i) <= 2.5e-3 * max(loss_i, 1e-7) + 1e-9, (k, pli, loss_i)
+        # network-branch loss is a bare weighted MSE between reconstructions (~1e-3): TF32 error energy bound 5e-3
+        assert abs(pl - loss) <= (5e-3 if pb == 1 else 2.5e-3) * abs(loss) + 1e-9, (k, pl, loss)
+    assert seen == {"A", "B"}, seen
+    assert abs(psnr(p[0], x) - psnr(o[0], x)) < 0.05
+
+
+def test_generic_engine_cheng2020_matches_oracle(dev):
+    """cheng2020_anchor (residual blocks, sub-pixel convs) through the module-by-module engine vs the oracle loop."""
+    from imagecompression_adversarial_b200 import attack as patk
+    from imagecompression_adversarial_b200.engine import GenericAttackEngine
+    from oracle import attack as oatk
+    onet, pnet = pair("cheng2020", 1, dev)
+    x = images(1, 192, 192, dev)   # > 160: the final eval computes MS-SSIM (pytorch_msssim asserts on smaller images)
+    args = oatk.default_args(model="cheng2020", quality=1, metric="mse", steps=6)
+    rec, orec = [], []
+    p = patk.attack_(x, pnet, args, record=rec)
+    assert isinstance(next(iter(patk._ENGINES.values())), GenericAttackEngine)
+    o = oatk.attack_(x, onet, args, record=orec)
+    for k, (br, loss, loss_i) in enumerate(orec):
+        pb, pli, pl = int(rec[k][0][0]), float(rec[k][1][0]), float(rec[k][2][0])
+        assert (pb == 1) == (br == "B"), (k, pb, br)
+        assert abs(pli - loss_i) <= 4e-3 * max(loss_i, 1e-7) + 1e-9, (k, pli, loss_i)
+        assert abs(pl - loss) <= (1e-3 if pb == 1 else 4e-3) * abs(loss) + 1e-9, (k, pl, loss)
+    assert all(q.requires_grad for q in pnet.parameters())
+    assert abs(psnr(p[0], x) - psnr(o[0], x)) < 0.05
+
+
+def test_context_q4_msssim_attack_runs_and_matches(dev):
+    """BASELINE config 3 at test size: mbt2018 q4 (N = M = 192), -att_metric ms-ssim, fused loop vs oracle."""
+    from imagecompression_adversarial_b200 import attack as patk
+    from oracle import attack as oatk
+    onet, pnet = pair("context", 4, dev)
+    x = images(1, 192, 256, dev)
+    args = oatk.default_args(model="context", quality=4, metric="ms-ssim", steps=5, att_metric="ms-ssim", noise=2e-5)
+    rec, orec = [], []
+    patk.attack_(x, pnet, args, record=rec)
+    oatk.attack_(x, onet, args, record=orec)
+    for k, (br, loss, loss_i) in enumerate(orec):
+        pb, pli, pl = int(rec[k][0][0]), float(rec[k][1][0]), float(rec[k][2][0])
+        assert (pb == 1) == (br == "B"), (k, pb, br)
+        assert abs(pl - loss) <= 2.5e-3 * abs(loss) + 1e-9, (k, pl, loss)
