@@ -87,6 +87,19 @@ _SIGS = {
                                    C.c_float, C.c_float, C.c_void_p]),
     "icadv_gc_forward": (C.c_int, [_fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, C.c_int, C.c_int64, C.c_int, C.c_float,
                                    C.c_float, C.c_float, C.c_void_p]),
+    "icadv_eb_backward_workspace_floats": (C.c_int, [C.c_int64, C.c_int]),
+    "icadv_eb_backward": (C.c_int, [_fp, _fp, _fp, C.POINTER(_fp), C.POINTER(_fp), _fp, _fp, _fp, C.c_int64, C.c_int,
+                                    C.c_float, C.c_void_p]),
+    "icadv_gc_backward": (C.c_int, [_fp, _fp, _fp, _fp, _fp, _fp, _fp, C.c_int64, C.c_float, C.c_float, C.c_void_p]),
+    "icadv_log_sum": (C.c_int, [_fp, _fp, _fp, C.c_int64, C.c_float, C.c_void_p]),
+    "icadv_log_sum_backward": (C.c_int, [_fp, _fp, C.c_int64, C.c_float, _fp, C.c_float, C.c_void_p]),
+    "icadv_scaled_diff": (C.c_int, [_fp, _fp, _fp, C.c_int64, _fp, C.c_float, C.c_void_p]),
+    "icadv_gdn_param_grad_workspace_floats": (C.c_int, [C.c_int]),
+    "icadv_gdn_param_grad": (C.c_int, [_fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, C.c_int64, C.c_int, C.c_int, C.c_float,
+                                       C.c_float, C.c_void_p]),
+    "icadv_sumsq": (C.c_int, [_fp, _fp, _fp, C.c_int64, C.c_void_p]),
+    "icadv_adam_clip_step": (C.c_int, [_fp, _fp, _fp, _fp, C.c_int64, _fp, C.c_float, C.c_float, C.c_double, C.c_double,
+                                       C.c_double, C.c_double, C.c_int, C.c_void_p]),
     "icadv_unary": (C.c_int, [_fp, _fp, _fp, C.c_int64, C.c_int, C.c_void_p]),
     "icadv_act_backward": (C.c_int, [_fp, _fp, _fp, C.c_int64, C.c_int, C.c_void_p]),
     "icadv_ssim_workspace_floats": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),

@@ -15,6 +15,11 @@ from . import ops
 _PACK_CACHE = {}
 
 
+def invalidate_pack_cache():
+    """Drop every packed weight (call after parameters were updated behind autograd's version counters)."""
+    _PACK_CACHE.clear()
+
+
 def to_nhwc(x):
     """NCHW (any memory format) -> contiguous [N,H,W,C] view/copy."""
     return x.contiguous(memory_format=torch.channels_last).permute(0, 2, 3, 1)
@@ -238,3 +243,132 @@ class NarrowFn(torch.autograd.Function):
         gx = torch.zeros(*gn.shape[:-1], c, device=g.device, dtype=torch.float32)
         ops.copy_channels(gn, gx, 0, start, count)
         return to_nchw(gx), None, None
+
+
+# ------------------------------------------------------------------ codec update of adversarial training (train.py --adv)
+class GdnTrainFn(torch.autograd.Function):
+    """GDN / IGDN with gradients to the RAW beta / gamma parameters (compressai GDN under train.py:359)."""
+
+    @staticmethod
+    def forward(ctx, x, beta_raw, gamma_raw, inverse, beta_bound, beta_ped, gamma_bound, gamma_ped):
+        be = ops.gdn_reparam(beta_raw, beta_bound, beta_ped)
+        ga = ops.gdn_reparam(gamma_raw, gamma_bound, gamma_ped, round_tf32=True)
+        xn = to_nhwc(x)
+        C = xn.shape[-1]
+        y, sc = ops.conv(xn, None, None, form=L.FORM_SCONV, ksize=1, stride=1, n_ch=C,
+                         epi=L.EPI_IGDN_FWD if inverse else L.EPI_GDN_FWD, gmat=ga.contiguous(), beta=be.contiguous(),
+                         acc_from_in=True, path="tc")
+        ctx.save_for_backward(y, sc, ga, beta_raw, gamma_raw)
+        ctx.cfg = (inverse, beta_bound, gamma_bound)
+        return to_nchw(y)
+
+    @staticmethod
+    def backward(ctx, g):
+        y, sc, ga, beta_raw, gamma_raw = ctx.saved_tensors
+        inverse, beta_bound, gamma_bound = ctx.cfg
+        C = y.shape[-1]
+        gn = to_nhwc(g).contiguous()
+        gx = ops.conv(gn, None, None, form=L.FORM_SCONV, ksize=1, stride=1, n_ch=C,
+                      epi=L.EPI_IGDN_BWD if inverse else L.EPI_GDN_BWD, gmat=ga.t().contiguous(), y_prev=y, sc_prev=sc,
+                      acc_from_in=True, path="tc")
+        gb, gg = ops.gdn_param_grad(gn, y, sc, beta_raw, gamma_raw, inverse=inverse, beta_bound=beta_bound,
+                                    gamma_bound=gamma_bound)
+        return to_nchw(gx), gb, gg, None, None, None, None, None
+
+
+class EbTrainFn(torch.autograd.Function):
+    """Train-mode EntropyBottleneck (x_hat = x + noise, factorised likelihood) with gradients to x and to the
+    matrices / biases / factors (anchors/model.py:87-89,93 under train.py:353-359)."""
+
+    @staticmethod
+    def forward(ctx, x, noise_nhwc, medians, lik_bound, *params):
+        ms, bs, fs = params[0:5], params[5:10], params[10:14]
+        xn = to_nhwc(x).contiguous()
+        C = xn.shape[-1]
+        table = ops.eb_prepare(ms, bs, fs, C)
+        if noise_nhwc is None:
+            noise_nhwc = torch.empty_like(xn).uniform_(-0.5, 0.5)
+        x_hat, lik, _ = ops.eb_forward(xn, table, medians, training=True, noise=noise_nhwc, lik_bound=lik_bound)
+        ctx.save_for_backward(x_hat, table, *params)
+        ctx.lik_bound = lik_bound
+        return to_nchw(x_hat), to_nchw(lik)
+
+    @staticmethod
+    def backward(ctx, g_xhat, g_lik):
+        x_hat, table = ctx.saved_tensors[0:2]
+        params = ctx.saved_tensors[2:]
+        ms, fs = params[0:5], params[10:14]
+        C = x_hat.shape[-1]
+        gl = to_nhwc(g_lik).contiguous() if g_lik is not None else torch.zeros_like(x_hat)
+        g_x, g_raw = ops.eb_backward(x_hat, gl, table, ms, fs, lik_bound=ctx.lik_bound)
+        gx = to_nchw(g_x)
+        if g_xhat is not None:
+            gx = ops.unary(gx.contiguous(memory_format=torch.channels_last), 4,
+                           g_xhat.contiguous(memory_format=torch.channels_last))
+        rows = lambda a, b, shape: g_raw[a:b].t().reshape(C, *shape).contiguous()
+        gm = [rows(0, 3, (3, 1))] + [rows(9 + 15 * i, 18 + 15 * i, (3, 3)) for i in range(3)] + [rows(54, 57, (1, 3))]
+        gb = [rows(3, 6, (3, 1))] + [rows(18 + 15 * i, 21 + 15 * i, (3, 1)) for i in range(3)] + [rows(57, 58, (1, 1))]
+        gf = [rows(6, 9, (3, 1))] + [rows(21 + 15 * i, 24 + 15 * i, (3, 1)) for i in range(3)]
+        return (gx, None, None, None, *gm, *gb, *gf)
+
+
+class GcTrainFn(torch.autograd.Function):
+    """Train-mode GaussianConditional (y_hat = y + noise, discretised Gaussian likelihood) with gradients to y, the
+    scales and the means (anchors/model.py:95,106)."""
+
+    @staticmethod
+    def forward(ctx, y, scales, means, noise_nhwc, scale_bound, lik_bound):
+        yn, sn = to_nhwc(y).contiguous(), to_nhwc(scales).contiguous()
+        mn = to_nhwc(means).contiguous() if means is not None else None
+        if noise_nhwc is None:
+            noise_nhwc = torch.empty_like(yn).uniform_(-0.5, 0.5)
+        y_hat, lik, _ = ops.gc_forward(yn, sn, mn, training=True, noise=noise_nhwc, scale_bound=scale_bound,
+                                       lik_bound=lik_bound)
+        ctx.save_for_backward(y_hat, sn, mn)
+        ctx.cfg = (scale_bound, lik_bound)
+        return to_nchw(y_hat), to_nchw(lik)
+
+    @staticmethod
+    def backward(ctx, g_yhat, g_lik):
+        y_hat, sn, mn = ctx.saved_tensors
+        scale_bound, lik_bound = ctx.cfg
+        gl = to_nhwc(g_lik).contiguous() if g_lik is not None else torch.zeros_like(y_hat)
+        g_y, g_s, g_m = ops.gc_backward(y_hat, sn, mn, gl, scale_bound=scale_bound, lik_bound=lik_bound)
+        gy = to_nchw(g_y)
+        if g_yhat is not None:
+            gy = ops.unary(gy.contiguous(memory_format=torch.channels_last), 4,
+                           g_yhat.contiguous(memory_format=torch.channels_last))
+        return gy, to_nchw(g_s), (to_nchw(g_m) if g_m is not None else None), None, None, None
+
+
+class LogSumFn(torch.autograd.Function):
+    """sum log(clamp(lik, min=floor)) (train.py:62-64) -> 1-element tensor; gradient g / lik inside the clamp range."""
+
+    @staticmethod
+    def forward(ctx, lik, floor):
+        lk = lik if (lik.is_contiguous() or lik.is_contiguous(memory_format=torch.channels_last)) else lik.contiguous()
+        ctx.save_for_backward(lk)
+        ctx.floor = floor
+        return ops.log_sum(lk, floor)
+
+    @staticmethod
+    def backward(ctx, g):
+        (lk,) = ctx.saved_tensors
+        return ops.log_sum_backward(lk, ctx.floor, g.contiguous()), None
+
+
+class MseFn(torch.autograd.Function):
+    """mean((x - t)^2) (train.py:71) -> 1-element tensor; gradient 2 g (x - t) / numel to x."""
+
+    @staticmethod
+    def forward(ctx, x, t):
+        xc = x.contiguous(memory_format=torch.channels_last)
+        tc = t.contiguous(memory_format=torch.channels_last)
+        ctx.save_for_backward(xc, tc)
+        flat = lambda a: a.permute(0, 2, 3, 1).reshape(1, -1)
+        return ops.sum_sqdiff(flat(xc), flat(tc)) * (1.0 / xc.numel())
+
+    @staticmethod
+    def backward(ctx, g):
+        xc, tc = ctx.saved_tensors
+        return ops.scaled_diff(xc, tc, g.contiguous(), 2.0 / xc.numel()), None

@@ -28,6 +28,25 @@ ZOO = {
 }
 
 
+# Parameter gradients are produced only inside a full train-mode ``net(x)`` forward (the codec update, train.py:353-359)
+# or when a module's ``param_grads`` is set by hand.  The attack calls ``net.g_a`` / ``net.g_s`` directly and only steps
+# the perturbation (attack_rd.py:546-548): there the reference computes weight gradients and throws them away
+# (train.py:357-358 zeroes them), so this path does not compute them at all.
+_PARAM_GRADS = [False]
+
+
+class _param_grads_on:
+    def __init__(self, on):
+        self.on = on
+
+    def __enter__(self):
+        self.prev = _PARAM_GRADS[0]
+        _PARAM_GRADS[0] = self.prev or self.on
+
+    def __exit__(self, *exc):
+        _PARAM_GRADS[0] = self.prev
+
+
 class _ContractionModule(nn.Module):
     transposed = False
 
@@ -44,7 +63,7 @@ class _ContractionModule(nn.Module):
 
     def forward(self, x):
         return Fn.Contraction.apply(x, self.weight, self.bias, self.ksize, self.stride, self.transposed, L.ACT_NONE,
-                                    self.param_grads)
+                                    self.param_grads)   # weight gradients only if the weight requires grad (autograd)
 
     def extra_repr(self):
         return f"{self.in_channels}, {self.out_channels}, kernel_size={self.ksize}, stride={self.stride}"
@@ -145,6 +164,9 @@ class GDN(nn.Module):
         return be, ga, gaT
 
     def forward(self, x):
+        if torch.is_grad_enabled() and (self.beta.requires_grad or self.gamma.requires_grad) and _PARAM_GRADS[0]:
+            return Fn.GdnTrainFn.apply(x, self.beta, self.gamma, self.inverse, self.beta_reparam.bound,
+                                       self.beta_reparam.pedestal, self.gamma_reparam.bound, self.gamma_reparam.pedestal)
         be, ga, _ = self.effective_parameters(round_tf32=True)
         return Fn.GdnFn.apply(x, be, ga, self.inverse)
 
@@ -243,9 +265,11 @@ class CodecStack(nn.Sequential):
     param_grads = False
 
     def forward(self, x):
-        if self.param_grads and any(p.requires_grad for p in self.parameters()) and torch.is_grad_enabled():
-            for m in self:   # layer-by-layer autograd path, with weight gradients
-                x = m(x)
+        if (self.param_grads or _PARAM_GRADS[0]) and torch.is_grad_enabled() and \
+                any(p.requires_grad for p in self.parameters()):
+            with _param_grads_on(True):
+                for m in self:   # layer-by-layer autograd path, with weight and GDN-parameter gradients
+                    x = m(x)
             return x
         return _StackFn.apply(x, self)
 
@@ -305,12 +329,17 @@ class EntropyBottleneck(nn.Module):
     def forward(self, x, training=None):
         if training is None:
             training = self.training
+        med = self.quantiles.detach()[:, 0, 1].contiguous()
+        if training and torch.is_grad_enabled() and (x.requires_grad or self._matrix0.requires_grad):
+            noise = Fn.to_nhwc(self.noise_override).contiguous() if self.noise_override is not None else None
+            params = [getattr(self, f"_matrix{i}") for i in range(5)] + [getattr(self, f"_bias{i}") for i in range(5)] + \
+                     [getattr(self, f"_factor{i}") for i in range(4)]
+            return Fn.EbTrainFn.apply(x, noise, med, self.likelihood_bound, *params)
         xn = Fn.to_nhwc(x).contiguous()
         noise = None
         if training:
             noise = (Fn.to_nhwc(self.noise_override).contiguous() if self.noise_override is not None
                      else torch.empty_like(xn).uniform_(-0.5, 0.5))
-        med = self.quantiles.detach()[:, 0, 1].contiguous()
         x_hat, lik, bits = ops.eb_forward(xn, self._table(), med, training=training, noise=noise,
                                           lik_bound=self.likelihood_bound)
         self.last_bits = bits
@@ -346,6 +375,9 @@ class GaussianConditional(nn.Module):
     def forward(self, inputs, scales, means=None, training=None):
         if training is None:
             training = self.training
+        if training and torch.is_grad_enabled() and (inputs.requires_grad or scales.requires_grad):
+            noise = Fn.to_nhwc(self.noise_override).contiguous() if self.noise_override is not None else None
+            return Fn.GcTrainFn.apply(inputs, scales, means, noise, self.scale_bound, self.likelihood_bound)
         y = Fn.to_nhwc(inputs).contiguous()
         s = Fn.to_nhwc(scales).contiguous()
         m = Fn.to_nhwc(means).contiguous() if means is not None else None
@@ -388,9 +420,10 @@ class FactorizedPrior(CompressionModel):
         self.N, self.M = N, M
 
     def forward(self, x):
-        y = self.g_a(x)
-        y_hat, y_lik = self.entropy_bottleneck(y)   # anchors/model.py:87-89
-        return {"x_hat": self.g_s(y_hat), "likelihoods": {"y": y_lik}}
+        with _param_grads_on(self.training):
+            y = self.g_a(x)
+            y_hat, y_lik = self.entropy_bottleneck(y)   # anchors/model.py:87-89
+            return {"x_hat": self.g_s(y_hat), "likelihoods": {"y": y_lik}}
 
 
 class ScaleHyperprior(CompressionModel):
@@ -403,12 +436,13 @@ class ScaleHyperprior(CompressionModel):
         self.N, self.M = N, M
 
     def forward(self, x):
-        y = self.g_a(x)
-        z = self.h_a(Fn.ActFn.apply(y, L.ACT_ABS))  # anchors/model.py:92, anchors/balle.py:38
-        z_hat, z_lik = self.entropy_bottleneck(z)
-        scales_hat = self.h_s(z_hat)
-        y_hat, y_lik = self.gaussian_conditional(y, scales_hat)
-        return {"x_hat": self.g_s(y_hat), "likelihoods": {"y": y_lik, "z": z_lik}}
+        with _param_grads_on(self.training):
+            y = self.g_a(x)
+            z = self.h_a(Fn.ActFn.apply(y, L.ACT_ABS))  # anchors/model.py:92, anchors/balle.py:38
+            z_hat, z_lik = self.entropy_bottleneck(z)
+            scales_hat = self.h_s(z_hat)
+            y_hat, y_lik = self.gaussian_conditional(y, scales_hat)
+            return {"x_hat": self.g_s(y_hat), "likelihoods": {"y": y_lik, "z": z_lik}}
 
 
 class JointAutoregressiveHierarchicalPriors(CompressionModel):
@@ -429,6 +463,10 @@ class JointAutoregressiveHierarchicalPriors(CompressionModel):
         self.N, self.M = N, M
 
     def forward(self, x):
+        with _param_grads_on(self.training):
+            return self._forward(x)
+
+    def _forward(self, x):
         y = self.g_a(x)
         z = self.h_a(y)                                          # anchors/model.py:98 (no abs)
         z_hat, z_lik = self.entropy_bottleneck(z)

@@ -363,3 +363,88 @@ def gc_forward(y, scales, means=None, *, training, noise=None, scale_bound=0.11,
     L.call("icadv_gc_forward", _p(y), _p(scales), _p(means), _p(noise), _p(y_hat), _p(lik), _p(ws), _p(bits), n_img,
            per_img, 1 if training else 0, float(scale_bound), float(lik_bound), float(bits_floor), _stream())
     return y_hat, lik, bits
+
+
+# ------------------------------------------------------------------ codec update of adversarial training (train.py --adv)
+def eb_backward(x_hat, g_lik, table, matrices, factors, *, lik_bound=1e-9):
+    """(g_x, g_raw[58][C]) of the train-mode EntropyBottleneck likelihood; x_hat, g_lik channels-last [..., C]."""
+    _chk(x_hat, "x_hat")
+    _chk(g_lik, "g_lik")
+    Cc = x_hat.shape[-1]
+    rows = x_hat.numel() // Cc
+    g_x = torch.empty_like(x_hat)
+    g_raw = torch.empty(58, Cc, device=x_hat.device, dtype=torch.float32)
+    ws = torch.empty(L.lib().icadv_eb_backward_workspace_floats(rows, Cc), device=x_hat.device, dtype=torch.float32)
+    keep = [t.detach().contiguous() for t in list(matrices) + list(factors)]
+    arr = lambda ts: (L._fp * len(ts))(*[t.data_ptr() for t in ts])
+    L.call("icadv_eb_backward", _p(x_hat), _p(g_lik), _p(table), arr(keep[0:5]), arr(keep[5:9]), _p(g_x), _p(g_raw),
+           _p(ws), rows, Cc, float(lik_bound), _stream())
+    return g_x, g_raw
+
+
+def gc_backward(y_hat, scales, means, g_lik, *, scale_bound=0.11, lik_bound=1e-9):
+    for t, nm in ((y_hat, "y_hat"), (scales, "scales"), (means, "means"), (g_lik, "g_lik")):
+        _chk(t, nm)
+    g_y, g_s = torch.empty_like(y_hat), torch.empty_like(y_hat)
+    g_m = torch.empty_like(y_hat) if means is not None else None
+    L.call("icadv_gc_backward", _p(y_hat), _p(scales), _p(means), _p(g_lik), _p(g_y), _p(g_s), _p(g_m), y_hat.numel(),
+           float(scale_bound), float(lik_bound), _stream())
+    return g_y, g_s, g_m
+
+
+def log_sum(lik, floor):
+    """sum log(max(lik, floor)) as a 1-element device tensor (any memory layout: the sum is order-free per block)."""
+    _chk_dense(lik)
+    ws = torch.empty(L.RED_BLOCKS, device=lik.device, dtype=torch.float32)
+    out = torch.empty(1, device=lik.device, dtype=torch.float32)
+    L.call("icadv_log_sum", _p(lik), _p(ws), _p(out), lik.numel(), float(floor), _stream())
+    return out
+
+
+def log_sum_backward(lik, floor, scale_dev, scale_host=1.0):
+    _chk_dense(lik)
+    g = torch.empty_like(lik)
+    L.call("icadv_log_sum_backward", _p(lik), _p(g), lik.numel(), float(floor), _p(scale_dev), float(scale_host), _stream())
+    return g
+
+
+def scaled_diff(a, b, scale_dev, scale_host=1.0):
+    _chk_dense(a)
+    if a.stride() != b.stride() or a.shape != b.shape:
+        raise L.IcadvError("scaled_diff: operands must share shape and memory layout")
+    out = torch.empty_like(a)
+    L.call("icadv_scaled_diff", _p(a), _p(b), _p(out), a.numel(), _p(scale_dev), float(scale_host), _stream())
+    return out
+
+
+def _chk_dense(t):
+    if not (t.is_cuda and t.dtype == torch.float32 and
+            (t.is_contiguous() or t.is_contiguous(memory_format=torch.channels_last))):
+        raise L.IcadvError("expected a dense CUDA float32 tensor")
+
+
+def gdn_param_grad(g, y, sc, beta_raw, gamma_raw, *, inverse, beta_bound, gamma_bound):
+    """(d beta_raw [C], d gamma_raw [C,C]) from g = dL/dy, saved y and scale (channels-last)."""
+    for t, nm in ((g, "g"), (y, "y"), (sc, "sc")):
+        _chk(t, nm)
+    Cc = y.shape[-1]
+    gb = torch.empty(Cc, device=y.device, dtype=torch.float32)
+    gg = torch.empty(Cc, Cc, device=y.device, dtype=torch.float32)
+    ws = torch.empty(L.lib().icadv_gdn_param_grad_workspace_floats(Cc), device=y.device, dtype=torch.float32)
+    L.call("icadv_gdn_param_grad", _p(g), _p(y), _p(sc), _p(beta_raw.detach().contiguous()),
+           _p(gamma_raw.detach().contiguous()), _p(gb), _p(gg), _p(ws), y.numel() // Cc, Cc, 1 if inverse else 0,
+           float(beta_bound), float(gamma_bound), _stream())
+    return gb, gg
+
+
+def sumsq(flat):
+    ws = torch.empty(L.RED_BLOCKS, device=flat.device, dtype=torch.float32)
+    out = torch.empty(1, device=flat.device, dtype=torch.float32)
+    L.call("icadv_sumsq", _p(flat), _p(ws), _p(out), flat.numel(), _stream())
+    return out
+
+
+def adam_clip_step(params, grads, m, v, *, sumsq_dev, max_norm, lr, step, grad_scale=1.0, beta1=0.9, beta2=0.999,
+                   eps=1e-8):
+    L.call("icadv_adam_clip_step", _p(params), _p(grads), _p(m), _p(v), params.numel(), _p(sumsq_dev), float(max_norm),
+           float(grad_scale), float(lr), float(beta1), float(beta2), float(eps), int(step), _stream())

@@ -1,0 +1,161 @@
+"""The codec update of adversarial training (``train.py --adv``, train.py:335-366) on the sm_100a kernels.
+
+Mirrors, with the reference's names and argument meaning:
+  * ``RateDistortionLoss``      train.py:37-96  (training branch; rate term with the 1/65536 likelihood clamp)
+  * ``configure_optimizers``    coder.py:50-86  (main parameters vs ``*.quantiles``; Adam(lr_train) / Adam(1e-3))
+  * ``adv_train_step``          train.py:335-366 (attack_ on the batch, train-mode forward, RD loss, backward with
+                                weight gradients, clip_grad_norm_(1.0), Adam, aux loss on the quantiles)
+
+Design for one process per GPU: all main parameters live in ONE flat fp32 buffer (parameters are views into it) and so do
+their gradients, so the data-parallel exchange is a single NCCL all-reduce of 20 MB (hyperprior N=128/M=192) and
+clip + Adam is one kernel over the flat buffer with the clip coefficient formed on the device (no host sync).
+The unmodified reference ``train.py`` also works on these modules with its own torch optimisers.
+"""
+import math
+
+import torch
+import torch.distributed as dist
+
+from . import functional as Fn
+from . import metrics
+from . import ops
+
+LAMBDA_MSE = {1: 0.0018, 2: 0.0035, 3: 0.0067, 4: 0.0130, 5: 0.0250, 6: 0.0483, 7: 0.0932, 8: 0.1800}
+LAMBDA_MSSSIM = {1: 2.40, 2: 4.58, 3: 8.73, 4: 16.64, 5: 31.73, 6: 60.50, 7: 115.37, 8: 220.00}
+
+
+class _MsssimFn(torch.autograd.Function):
+    """pytorch_msssim.MS_SSIM(data_range=1, size_average=True) with its gradient to the first argument."""
+
+    @staticmethod
+    def forward(ctx, x, target):
+        xc, tc = x.detach().contiguous(), target.detach().contiguous()
+        up = torch.ones(xc.shape[0], device=xc.device)
+        val, grad = metrics.ms_ssim_value_and_grad(xc, tc, up)
+        ctx.save_for_backward(grad)
+        ctx.n = xc.shape[0]
+        return val.mean().reshape(1)
+
+    @staticmethod
+    def backward(ctx, g):
+        (grad,) = ctx.saved_tensors
+        return ops.scaled_diff(grad, torch.zeros_like(grad), g.contiguous(), 1.0 / ctx.n), None
+
+
+class RateDistortionLoss(torch.nn.Module):
+    """train.py:37-96, training branch (``lpips`` is out of scope)."""
+
+    def __init__(self, metric="mse", lmbda=1e-2):
+        super().__init__()
+        self.metric, self.lmbda = metric, lmbda
+
+    def forward(self, output, target):
+        N, _, H, W = target.shape
+        num_pixels = N * H * W
+        out = {}
+        bpp = None
+        for lik in output["likelihoods"].values():                       # train.py:61-64
+            term = Fn.LogSumFn.apply(lik, 1.0 / 65536) * (1.0 / (-math.log(2) * num_pixels))
+            bpp = term if bpp is None else bpp + term
+        out["bpp_loss"] = bpp.reshape(())
+        lamb_r = 0 if self.lmbda == 100 else 1                           # train.py:77-80
+        if self.metric == "mse":
+            out["distortion_loss"] = Fn.MseFn.apply(output["x_hat"], target).reshape(())
+            out["loss"] = self.lmbda * 255 ** 2 * out["distortion_loss"] + lamb_r * out["bpp_loss"]
+        elif self.metric == "ms-ssim":
+            out["distortion_loss"] = _MsssimFn.apply(output["x_hat"], target).reshape(())
+            out["loss"] = self.lmbda * (1 - out["distortion_loss"]) + lamb_r * out["bpp_loss"]
+        else:
+            raise ValueError(f"metric {self.metric} is not built")
+        return out
+
+
+def exchange_gradients(flat_grad, group=None):
+    """The one exchange step of data-parallel adversarial training: SUM all-reduce of the flat gradient buffer (NCCL over
+    NVLink on GPUs; gloo in the CPU tests).  Returns the factor the optimiser must scale gradients by (1/world)."""
+    if not (dist.is_available() and dist.is_initialized()):
+        return 1.0
+    world = dist.get_world_size(group)
+    if world == 1:
+        return 1.0
+    dist.all_reduce(flat_grad, op=dist.ReduceOp.SUM, group=group)
+    return 1.0 / world
+
+
+class FusedAdamClip:
+    """Adam over ONE flat parameter buffer with ``clip_grad_norm_(max_norm)`` folded in (train.py:360-361).
+
+    ``params`` keep their identity (``state_dict`` keys, shapes) but their storage becomes a view of ``self.flat`` and
+    their ``.grad`` a view of ``self.flat_grad``; ``zero_grad`` zeroes the flat buffer in place."""
+
+    def __init__(self, params, lr, max_norm=None, betas=(0.9, 0.999), eps=1e-8):
+        self.params = [p for p in params]
+        assert self.params, "no parameters"
+        dev = self.params[0].device
+        total = sum(p.numel() for p in self.params)
+        self.flat = torch.empty(total, device=dev, dtype=torch.float32)
+        self.flat_grad = torch.zeros(total, device=dev, dtype=torch.float32)
+        self.m, self.v = torch.zeros_like(self.flat), torch.zeros_like(self.flat)
+        off = 0
+        for p in self.params:
+            n = p.numel()
+            self.flat[off:off + n].copy_(p.detach().reshape(-1))
+            p.data = self.flat[off:off + n].view(p.shape)
+            p.grad = self.flat_grad[off:off + n].view(p.shape)
+            off += n
+        self.lr, self.max_norm, self.betas, self.eps = lr, max_norm, betas, eps
+        self.steps = 0
+        self.last_sumsq = None
+
+    def zero_grad(self, set_to_none=False):
+        self.flat_grad.zero_()
+        off = 0
+        for p in self.params:      # autograd may have replaced a view: re-attach
+            n = p.numel()
+            if p.grad is None or p.grad.data_ptr() != self.flat_grad[off:off + n].data_ptr():
+                p.grad = self.flat_grad[off:off + n].view(p.shape)
+            off += n
+
+    def step(self, group=None):
+        off = 0
+        for p in self.params:      # a gradient that autograd re-allocated is copied back into the flat buffer
+            n = p.numel()
+            if p.grad is not None and p.grad.data_ptr() != self.flat_grad[off:off + n].data_ptr():
+                self.flat_grad[off:off + n].copy_(p.grad.reshape(-1))
+            off += n
+        scale = exchange_gradients(self.flat_grad, group)
+        self.steps += 1
+        sumsq = ops.sumsq(self.flat_grad) if self.max_norm is not None else None
+        self.last_sumsq = sumsq
+        ops.adam_clip_step(self.flat, self.flat_grad, self.m, self.v, sumsq_dev=sumsq,
+                           max_norm=self.max_norm if self.max_norm is not None else 0.0, lr=self.lr, step=self.steps,
+                           grad_scale=scale, beta1=self.betas[0], beta2=self.betas[1], eps=self.eps)
+        Fn.invalidate_pack_cache()   # the kernel updated weights behind autograd's version counters
+
+
+def configure_optimizers(net, args):
+    """coder.py:50-86 on the fused optimiser: (main, aux)."""
+    named = dict(net.named_parameters())
+    main = sorted(n for n, p in named.items() if not n.endswith(".quantiles") and p.requires_grad)
+    aux = sorted(n for n, p in named.items() if n.endswith(".quantiles") and p.requires_grad)
+    assert not (set(main) & set(aux))
+    return (FusedAdamClip([named[n] for n in main], lr=args.lr_train, max_norm=1.0),
+            FusedAdamClip([named[n] for n in aux], lr=1e-3, max_norm=None))
+
+
+def adv_train_step(batch_x, net, args, criterion, optimizer, aux_optimizer, group=None):
+    """One iteration of train.py:335-366 with N_ADV = 0.  Returns (out_criterion, aux_loss)."""
+    from .attack import attack_
+    batch_adv = attack_(batch_x, net, args)[0].detach()                  # :342-343
+    net.train()                                                          # :346
+    batch = batch_adv.clone()                                            # :347
+    result = net(batch)                                                  # :351
+    out = criterion(result, batch)                                       # :353
+    optimizer.zero_grad()
+    aux_optimizer.zero_grad()
+    out["loss"].backward()                                               # :359
+    optimizer.step(group)                                                # all-reduce + clip_grad_norm_(1.0) + Adam (:360-361)
+    aux = net.aux_loss()                                                 # :363 (parameter-only math: identical on all ranks)
+    aux.backward()
+    aux_optimizer.step(None)
+    return out, aux

@@ -253,6 +253,47 @@ int icadv_unary(const float* x, const float* b, float* y, int64_t n, int op, ica
 int icadv_act_backward(const float* x, const float* g, float* gx, int64_t n, int op, icadv_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Codec update of adversarial training (train.py:335-366 under --adv; RateDistortionLoss train.py:37-96;
+ * optimisers coder.py:50-86).  Only the update step uses these; the attack loop never does.
+ * ------------------------------------------------------------------------------------------ */
+/* Backward of the EntropyBottleneck likelihood (train mode, x_hat = x + noise): g_x = dL/dx; g_raw [58][C] = dL/d(raw
+ * parameters) in the row order of the prepared table (rows 0-2 matrix0, 3-5 bias0, 6-8 factor0, then 15 rows per
+ * middle layer: 9 matrix, 3 bias, 3 factor; 54-56 matrix4, 57 bias4) -- softplus / tanh chain rule included.
+ * rows = n_img * pixels (channels-last rows of C).  ws: icadv_eb_backward_workspace_floats(rows, C) floats. */
+int icadv_eb_backward_workspace_floats(int64_t rows, int C);
+int icadv_eb_backward(const float* x_hat, const float* g_lik, const float* table, const float* const* matrices /*[5]*/,
+                      const float* const* factors /*[4]*/, float* g_x, float* g_raw, float* ws, int64_t rows, int C,
+                      float lik_bound, icadv_stream_t stream);
+/* Backward of the GaussianConditional likelihood (train mode): g_y, g_scales, g_means (NULL iff means is NULL);
+ * LowerBound backward rule on both the likelihood and the scale bound. */
+int icadv_gc_backward(const float* y_hat, const float* scales, const float* means, const float* g_lik, float* g_y,
+                      float* g_scales, float* g_means, int64_t n, float scale_bound, float lik_bound,
+                      icadv_stream_t stream);
+/* out[0] = sum log(max(lik, floor))  (train.py:62-64; ws: 128 floats) and its gradient scale/lik (0 below floor);
+ * scale = scale_host * scale_dev[0] (scale_dev nullable) */
+int icadv_log_sum(const float* lik, float* ws, float* out, int64_t n, float floor_, icadv_stream_t stream);
+int icadv_log_sum_backward(const float* lik, float* g_lik, int64_t n, float floor_, const float* scale_dev,
+                           float scale_host, icadv_stream_t stream);
+/* out = scale * (a - b): gradient of the MSE distortion term (train.py:71) */
+int icadv_scaled_diff(const float* a, const float* b, float* out, int64_t n, const float* scale_dev, float scale_host,
+                      icadv_stream_t stream);
+/* Gradients of the GDN / IGDN parameters (compressai GDN; utils/ops.py:58-97) w.r.t. the RAW beta [C] and gamma [C][C]
+ * (non-negative reparametrisation + LowerBound rule included), from g = dL/dy, the saved output y and scale sc
+ * (channels-last rows of C).  ws: icadv_gdn_param_grad_workspace_floats(C) floats. */
+int icadv_gdn_param_grad_workspace_floats(int C);
+int icadv_gdn_param_grad(const float* g, const float* y, const float* sc, const float* beta_raw, const float* gamma_raw,
+                         float* g_beta, float* g_gamma, float* ws, int64_t n_px, int C, int inverse, float beta_bound,
+                         float gamma_bound, icadv_stream_t stream);
+/* out[0] = sum g^2 over a flat gradient buffer (ws: 128 floats): the global norm of clip_grad_norm_ (train.py:360) */
+int icadv_sumsq(const float* g, float* ws, float* out, int64_t n, icadv_stream_t stream);
+/* clip_grad_norm_(max_norm) + torch.optim.Adam step over ONE flat buffer (after the gradient all-reduce): gradients
+ * are g * grad_scale (1/world after a SUM all-reduce); the clip coefficient min(1, max_norm / (grad_scale *
+ * sqrt(sumsq[0]) + 1e-6)) is formed on the device; sumsq NULL = no clipping. */
+int icadv_adam_clip_step(float* params, const float* grads, float* m, float* v, int64_t n, const float* sumsq,
+                         float max_norm, float grad_scale, double lr, double beta1, double beta2, double eps, int step,
+                         icadv_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
  * MS-SSIM (pytorch_msssim.ms_ssim, call sites attack_rd.py:336,362, self_ensemble.py:225,228,
  * train.py:44,88; and utils/torch_msssim.py:18-76).  NCHW fp32 planes (planes = N*C).  One level
  * per call: per-plane sums of the ssim and cs maps over the output region; the host composes the
