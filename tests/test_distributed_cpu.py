@@ -45,3 +45,38 @@ def test_shard_indices_properties():
             parts = [shard_indices(n, r, w) for r in range(w)]
             assert sorted(sum(parts, [])) == list(range(n))
             assert max(len(p) for p in parts) - min(len(p) for p in parts) <= 1
+
+
+def _grad_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from imagecompression_adversarial_b200.training import exchange_gradients
+    flat = torch.arange(10, dtype=torch.float32) * (rank + 1)        # rank-dependent "gradients"
+    scale = exchange_gradients(flat)                                   # one SUM all-reduce of the flat buffer
+    q.put((rank, scale, flat.tolist()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_training_gradient_exchange_world2():
+    """The one exchange step of data-parallel adversarial training (train.py --adv): a SUM all-reduce
+    of the flat gradient buffer and the 1/world factor the fused clip + Adam kernel applies."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_grad_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    want = [float(i) * 3.0 for i in range(10)]                         # (1 + 2) * i on both ranks
+    for rank, scale, flat in res:
+        assert scale == 0.5 and flat == want
+
+
+def test_training_gradient_exchange_single_process():
+    from imagecompression_adversarial_b200.training import exchange_gradients
+    flat = torch.ones(4)
+    assert exchange_gradients(flat) == 1.0 and flat.tolist() == [1.0] * 4
