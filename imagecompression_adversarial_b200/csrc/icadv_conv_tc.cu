@@ -183,11 +183,11 @@ __global__ void __launch_bounds__(kThreads, 2) conv_tc_kernel(const __grid_const
   // before waiting on it, so the path barrier -> issue stays a handful of instructions.
   if (warp == 0) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
+    {   // all 32 lanes run the loop (uniform state); one elected lane issues
       if constexpr (bwd) {
         // the saved y / scale of this tile come from HBM (written by the forward pass long ago): pull them into L2
         // now, so the epilogue's chunk loads are L2 hits instead of eight serial DRAM round trips
-        if (p.dbg_flags & 4)   // measured: no gain (the chunk round trip, not DRAM, is the latency) -- kept as a switch
+        if ((p.dbg_flags & 4) && lane == 0)   // measured: no gain (the chunk round trip, not DRAM, is the latency) -- kept as a switch
           for (int c = 0; c < p.n_chunks; ++c) {
             tma_prefetch_4d(&p.yprev_map, c * 32, j0, i0, img);
             tma_prefetch_4d(&p.scprev_map, c * 32, j0, i0, img);
@@ -195,6 +195,8 @@ __global__ void __launch_bounds__(kThreads, 2) conv_tc_kernel(const __grid_const
       }
       int s = 0, ps = 0;
       uint32_t s_par = 1, p_par = 1;          // parity to wait for on the "empty" barriers (first pass: free)
+      long long t_wait_e = 0;
+      const long long t_prod0 = clock64();
       uint8_t* wdst = wring;
       uint8_t* pdst = smem;
       const int n_row0 = n_off;
@@ -204,34 +206,45 @@ __global__ void __launch_bounds__(kThreads, 2) conv_tc_kernel(const __grid_const
           const Group gr = p.groups[g];
           const int cx = j0 + gr.dx0, cy = i0 + gr.dy0;
           mbar_wait(&pempty[ps], p_par);
-          mbar_arrive_expect_tx(&pfull[ps], gr.bytes);
-          if (p.a_rank5)
-            tma_load_5d(pdst, &p.a_map[0], &pfull[ps], 0, cx, cy, gr.plane5, img);
-          else
-            tma_load_4d(pdst, &p.a_map[gr.map], &pfull[ps], c0, cx, cy, img);
+          if (elect_one_sync()) {
+            mbar_arrive_expect_tx(&pfull[ps], gr.bytes);
+            if (p.a_rank5)
+              tma_load_5d(pdst, &p.a_map[0], &pfull[ps], 0, cx, cy, gr.plane5, img);
+            else
+              tma_load_4d(pdst, &p.a_map[gr.map], &pfull[ps], c0, cx, cy, img);
+          }
           if (++ps == P) { ps = 0; p_par ^= 1; pdst = smem; } else { pdst += p.patch_bytes; }
           int wrow = p.tap_wtap[gr.tap_begin] * p.n_total + n_row0;
           for (int t = gr.tap_begin; t < gr.tap_end; ++t) {
             const int wrow_next = (t + 1 < gr.tap_end ? p.tap_wtap[t + 1] : 0) * p.n_total + n_row0;
-            mbar_wait(&empty[s], s_par);
-            mbar_arrive_expect_tx(&full[s], b_bytes);
-            tma_load_2d(wdst, &p.w_map, &full[s], c0, wrow);
+            if (p.dbg != nullptr) { const long long t0 = clock64(); mbar_wait(&empty[s], s_par); t_wait_e += clock64() - t0; }
+            else mbar_wait(&empty[s], s_par);
+            if (elect_one_sync()) {
+              mbar_arrive_expect_tx(&full[s], b_bytes);
+              tma_load_2d(wdst, &p.w_map, &full[s], c0, wrow);
+            }
             wrow = wrow_next;
             if (++s == S) { s = 0; s_par ^= 1; wdst = wring; } else { wdst += b_bytes; }
           }
         }
       }
+      if (p.dbg != nullptr && lane == 0) {
+        long long* q = p.dbg + ((int64_t)blockIdx.y * gridDim.x + blockIdx.x) * 32;
+        q[13] = q[0] + t_wait_e; q[14] = q[0] + (clock64() - t_prod0);   // producer: blocked on empty / whole main loop
+      }
       for (int c = 0; c < gdn_kb; ++c) {
         mbar_wait(&empty[s], s_par);
-        mbar_arrive_expect_tx(&full[s], b_bytes);
-        tma_load_2d(wdst, &p.g_map, &full[s], c * 32, 0);
+        if (elect_one_sync()) {
+          mbar_arrive_expect_tx(&full[s], b_bytes);
+          tma_load_2d(wdst, &p.g_map, &full[s], c * 32, 0);
+        }
         if (++s == S) { s = 0; s_par ^= 1; wdst = wring; } else { wdst += b_bytes; }
       }
     }
     __syncwarp();
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
+    {   // all 32 lanes run the loop (uniform state); one elected lane issues
       const uint32_t idesc = umma_idesc_tf32(kTileM, p.n_ch);
       // shared-memory descriptors: hi word = SBO>>4 | version 1 (bit 14) | SWIZZLE_128B (bit 30); lo word = addr>>4 | LBO 1
       const uint32_t hi_dense = (1024u >> 4) | (1u << 14) | (2u << 29);
@@ -240,51 +253,62 @@ __global__ void __launch_bounds__(kThreads, 2) conv_tc_kernel(const __grid_const
       const uint32_t w_step = b_bytes >> 4, p_step = static_cast<uint32_t>(p.patch_bytes) >> 4;
       int s = 0, ps = 0;
       uint32_t s_par = 0, p_par = 0, w_lo = w_lo0, p_lo = p_lo0, acc = 0;
-      TC_STAMP(2);
+      long long t_wait_w = 0, t_wait_p = 0;   // developer profiling: cycles blocked on the weight / patch rings
+      if (lane == 0) TC_STAMP(2);
       for (int kc = 0; kc < (FROM_IN ? 0 : p.k_chunks); ++kc) {
         for (int g = 0; g < p.num_groups; ++g) {
           const Group gr = p.groups[g];
           const uint32_t a_hi = (static_cast<uint32_t>(gr.sbo_bytes) >> 4) | (1u << 14) | (2u << 29);
           uint32_t aoff = static_cast<uint32_t>(p.tap_aoff[gr.tap_begin]) >> 4;
-          mbar_wait(&pfull[ps], p_par);
+          if (p.dbg != nullptr) { const long long t0 = clock64(); mbar_wait(&pfull[ps], p_par); t_wait_p += clock64() - t0; }
+          else mbar_wait(&pfull[ps], p_par);
           for (int t = gr.tap_begin; t < gr.tap_end; ++t) {
             // tap (dy, dx): same patch, start shifted by whole pixel rows; tile rows are patch_w * 128 bytes apart
             const uint64_t ad = (static_cast<uint64_t>(a_hi) << 32) | (p_lo + aoff);
             const uint64_t bd = (static_cast<uint64_t>(hi_dense) << 32) | w_lo;
             aoff = static_cast<uint32_t>(p.tap_aoff[t + 1 < gr.tap_end ? t + 1 : t]) >> 4;   // next tap, off the critical path
-            mbar_wait(&full[s], s_par);
+            if (p.dbg != nullptr) { const long long t0 = clock64(); mbar_wait(&full[s], s_par); t_wait_w += clock64() - t0; }
+            else mbar_wait(&full[s], s_par);
             tc_fence_after_sync();
-            tc_mma_tf32(tmem, ad, bd, idesc, acc);
-            tc_mma_tf32(tmem, ad + 2, bd + 2, idesc, 1u);
-            tc_mma_tf32(tmem, ad + 4, bd + 4, idesc, 1u);
-            tc_mma_tf32(tmem, ad + 6, bd + 6, idesc, 1u);
-            tc_commit(&empty[s]);
+            if (elect_one_sync()) {
+              tc_mma_tf32(tmem, ad, bd, idesc, acc);
+              tc_mma_tf32(tmem, ad + 2, bd + 2, idesc, 1u);
+              tc_mma_tf32(tmem, ad + 4, bd + 4, idesc, 1u);
+              tc_mma_tf32(tmem, ad + 6, bd + 6, idesc, 1u);
+              tc_commit(&empty[s]);
+            }
             acc = 1u;
             if (++s == S) { s = 0; s_par ^= 1; w_lo = w_lo0; } else { w_lo += w_step; }
           }
-          tc_commit(&pempty[ps]);
+          if (elect_one_sync()) tc_commit(&pempty[ps]);
           if (++ps == P) { ps = 0; p_par ^= 1; p_lo = p_lo0; } else { p_lo += p_step; }
         }
       }
-      if (main_kb > 0) tc_commit(&acc_full[0]);
-      TC_STAMP(3);
+      if (main_kb > 0 && elect_one_sync()) tc_commit(&acc_full[0]);
+      if (lane == 0) TC_STAMP(3);
+      if (p.dbg != nullptr && lane == 0) {
+        long long* q = p.dbg + ((int64_t)blockIdx.y * gridDim.x + blockIdx.x) * 32;
+        q[11] = q[0] + t_wait_w; q[12] = q[0] + t_wait_p;   // stored relative to slot 0 like the stamps
+      }
       for (int c = 0; c < gdn_kb; ++c) {
         const uint64_t ad = (static_cast<uint64_t>(hi_dense) << 32) | p_lo;
         const uint64_t bd = (static_cast<uint64_t>(hi_dense) << 32) | w_lo;
         mbar_wait(&full[s], s_par);
         mbar_wait(&a2_ready[c], 0);
         tc_fence_after_sync();
-        tc_mma_tf32(tmem + p.n_ch, ad, bd, idesc, c > 0 ? 1u : 0u);
-        tc_mma_tf32(tmem + p.n_ch, ad + 2, bd + 2, idesc, 1u);
-        tc_mma_tf32(tmem + p.n_ch, ad + 4, bd + 4, idesc, 1u);
-        tc_mma_tf32(tmem + p.n_ch, ad + 6, bd + 6, idesc, 1u);
-        tc_commit(&empty[s]);
-        tc_commit(&pempty[ps]);
+        if (elect_one_sync()) {
+          tc_mma_tf32(tmem + p.n_ch, ad, bd, idesc, c > 0 ? 1u : 0u);
+          tc_mma_tf32(tmem + p.n_ch, ad + 2, bd + 2, idesc, 1u);
+          tc_mma_tf32(tmem + p.n_ch, ad + 4, bd + 4, idesc, 1u);
+          tc_mma_tf32(tmem + p.n_ch, ad + 6, bd + 6, idesc, 1u);
+          tc_commit(&empty[s]);
+          tc_commit(&pempty[ps]);
+        }
         if (++s == S) { s = 0; s_par ^= 1; w_lo = w_lo0; } else { w_lo += w_step; }
         if (++ps == P) { ps = 0; p_par ^= 1; p_lo = p_lo0; } else { p_lo += p_step; }
       }
-      if (gdn_kb > 0) tc_commit(&acc_full[1]);
-      TC_STAMP(4);
+      if (gdn_kb > 0 && elect_one_sync()) tc_commit(&acc_full[1]);
+      if (lane == 0) TC_STAMP(4);
     }
     __syncwarp();
   } else {
@@ -529,6 +553,449 @@ __global__ void __launch_bounds__(kThreads, 2) conv_tc_kernel(const __grid_const
   if (threadIdx.x == 0) TC_STAMP(10);
 }
 
+// =====================================================================================================
+// Persistent variant: ONE CTA per SM walks a static list of work items (tile x parity class x image).
+//   * the accumulator is double-buffered in TMEM (2 x 256 columns: [acc N | norm N]), so the MMA issuer starts the
+//     next item's main loop while the previous item's epilogue is still reading;
+//   * two epilogue warpgroups (warps 2-5 / 6-9) take alternate items, each with its own 2 x 16 KB staging;
+//   * the four output-parity classes of a stride-2 transposed conv are items of ONE launch (rotated so that every CTA
+//     sees all classes: they differ in length 9/6/6/4 taps);
+//   * gamma (the B operand of the normalisation GEMM) is loaded once per CTA and stays resident;
+//   * normalisation K-blocks are issued by the MMA thread between main-loop K-blocks of the NEXT item, as soon as the
+//     epilogue has written their A operand (polled with mbarrier.test_wait, which never suspends);
+//   * backward epilogues read the saved y / scale rows with plain 128-byte-per-thread loads (L2-prefetched when the
+//     item starts) instead of a TMA staging pair: that shared memory now holds the deeper rings.
+// Reference semantics are those of conv_tc_kernel above (anchors/utils.py:112-130, utils/ops.py:58-97).
+// =====================================================================================================
+constexpr int kPThreads = 320;
+
+struct TcpClass {
+  int16_t g_begin, g_end;   // groups of this class
+  int16_t o_a, o_b;         // output parity (TCONV), else 0
+};
+
+struct TcpParams {
+  CUtensorMap a_map[4];
+  CUtensorMap w_map, g_map;
+  CUtensorMap out_map[4], sc_map[4];   // per class
+  Group groups[kMaxGroups];
+  int32_t tap_aoff[kMaxTaps];
+  int16_t tap_wtap[kMaxTaps];
+  TcpClass cls[4];
+  int n_class, k_chunks, n_ch, n_chunks, n_total;
+  int num_patch, patch_bytes, num_stages;
+  int tiles_x, tiles_y, n_img;
+  int act, round_out, a_rank5;
+  int t_h, t_w, o_h, o_w, o_s;
+  const float* yprev; const float* scprev;
+  const float* bias; const float* beta;
+  const int* active; const int* n_active;
+};
+
+struct TcpItem { int img, i0, j0, cls; };
+
+__device__ __forceinline__ TcpItem tcp_decode(const TcpParams& p, int item) {
+  // class rotates with the tile index so that a CTA's items (stride gridDim.x) cycle through all classes, while the
+  // classes of one tile are adjacent items (their input patch is shared through L2)
+  const int tile_all = item / p.n_class;
+  TcpItem it;
+  it.cls = (item + tile_all) % p.n_class;
+  const int tiles = p.tiles_x * p.tiles_y;
+  const int slot = tile_all / tiles, t = tile_all - slot * tiles;
+  it.img = p.active != nullptr ? p.active[slot] : slot;
+  it.i0 = (t / p.tiles_x) * kTH;
+  it.j0 = (t % p.tiles_x) * kTW;
+  return it;
+}
+
+template <int EPI>
+__global__ void __launch_bounds__(kPThreads, 1) conv_tcp_kernel(const __grid_constant__ TcpParams p) {
+  constexpr bool gdn = EPI >= ICADV_EPI_GDN_FWD && EPI <= ICADV_EPI_IGDN_BWD;
+  constexpr bool bwd = EPI == ICADV_EPI_GDN_BWD || EPI == ICADV_EPI_IGDN_BWD;
+  extern __shared__ uint8_t smem_raw[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int P = p.num_patch, S = p.num_stages, nC = p.n_chunks;
+  const uint32_t b_bytes = static_cast<uint32_t>(p.n_ch) * 128u;
+  uint8_t* wring = smem + P * p.patch_bytes;
+  uint8_t* gmat = wring + S * b_bytes;                              // gdn: nC boxes [32 x n_ch], resident
+  uint8_t* grp0 = gmat + (gdn ? nC * b_bytes : 0u);                 // 2 groups x 2 slots x 16 KB
+  uint64_t* wfull = reinterpret_cast<uint64_t*>(grp0 + 4 * kABytes);
+  uint64_t* wempty = wfull + kMaxStages;
+  uint64_t* pfull = wempty + kMaxStages;
+  uint64_t* pempty = pfull + kMaxPatch;
+  uint64_t* gfull = pempty + kMaxPatch;       // [1]
+  uint64_t* acc_full = gfull + 1;             // [2]
+  uint64_t* norm_full = acc_full + 2;         // [2]
+  uint64_t* tmem_free = norm_full + 2;        // [2]
+  uint64_t* a2_ready = tmem_free + 2;         // [2 groups][2 slots]
+  uint64_t* a2_free = a2_ready + 4;           // [2][2]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(a2_free + 4);
+  float* sbias = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(wfull) + kBarBlock);
+  float* sbeta = sbias + p.n_ch;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < S; ++s) { mbar_init(&wfull[s], 1); mbar_init(&wempty[s], 1); }
+    for (int s = 0; s < P; ++s) { mbar_init(&pfull[s], 1); mbar_init(&pempty[s], 1); }
+    mbar_init(gfull, 1);
+    for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&norm_full[b], 1); mbar_init(&tmem_free[b], 1); }
+    for (int k = 0; k < 4; ++k) { mbar_init(&a2_ready[k], 128); mbar_init(&a2_free[k], 1); }
+    mbar_fence_init();
+  }
+  if (warp == 1) { tmem_alloc(tmem_ptr, 512); tmem_relinquish(); }
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.a_map[0]); tma_prefetch_desc(&p.w_map); tma_prefetch_desc(&p.out_map[0]);
+    if (gdn) tma_prefetch_desc(&p.g_map);
+  }
+  for (int i = threadIdx.x; i < p.n_ch; i += kPThreads) {
+    sbias[i] = p.bias != nullptr ? __ldg(p.bias + i) : 0.f;
+    if (EPI == ICADV_EPI_GDN_FWD || EPI == ICADV_EPI_IGDN_FWD) sbeta[i] = __ldg(p.beta + i);
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem = *tmem_ptr;
+  const int n_slots = p.n_active != nullptr ? *p.n_active : p.n_img;
+  const int total = n_slots * p.tiles_x * p.tiles_y * p.n_class;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    {   // all 32 lanes run the loop (uniform state); one elected lane issues
+      if (gdn && elect_one_sync()) {
+        mbar_arrive_expect_tx(gfull, nC * b_bytes);
+        for (int c = 0; c < nC; ++c) tma_load_2d(gmat + c * b_bytes, &p.g_map, gfull, c * 32, 0);
+      }
+      int s = 0, ps = 0;
+      uint32_t s_par = 1, p_par = 1;
+      uint8_t* wdst = wring;
+      uint8_t* pdst = smem;
+      for (int item = blockIdx.x; item < total; item += gridDim.x) {
+        const TcpItem it = tcp_decode(p, item);
+        const TcpClass cl = p.cls[it.cls];
+        for (int kc = 0; kc < p.k_chunks; ++kc) {
+          const int c0 = kc * 32;
+          for (int g = cl.g_begin; g < cl.g_end; ++g) {
+            const Group gr = p.groups[g];
+            const int cx = it.j0 + gr.dx0, cy = it.i0 + gr.dy0;
+            mbar_wait(&pempty[ps], p_par);
+            if (elect_one_sync()) {
+              mbar_arrive_expect_tx(&pfull[ps], gr.bytes);
+              if (p.a_rank5)
+                tma_load_5d(pdst, &p.a_map[0], &pfull[ps], 0, cx, cy, gr.plane5, it.img);
+              else
+                tma_load_4d(pdst, &p.a_map[gr.map], &pfull[ps], c0, cx, cy, it.img);
+            }
+            if (++ps == P) { ps = 0; p_par ^= 1; pdst = smem; } else { pdst += p.patch_bytes; }
+            int wrow = p.tap_wtap[gr.tap_begin] * p.n_total;
+            for (int t = gr.tap_begin; t < gr.tap_end; ++t) {
+              const int wrow_next = (t + 1 < gr.tap_end ? p.tap_wtap[t + 1] : 0) * p.n_total;
+              mbar_wait(&wempty[s], s_par);
+              if (elect_one_sync()) {
+                mbar_arrive_expect_tx(&wfull[s], b_bytes);
+                tma_load_2d(wdst, &p.w_map, &wfull[s], c0, wrow);
+              }
+              wrow = wrow_next;
+              if (++s == S) { s = 0; s_par ^= 1; wdst = wring; } else { wdst += b_bytes; }
+            }
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    {   // all 32 lanes run the loop (uniform state); one elected lane issues
+      const uint32_t idesc = umma_idesc_tf32(kTileM, p.n_ch);
+      const uint32_t hi_dense = (1024u >> 4) | (1u << 14) | (2u << 29);
+      const uint32_t w_lo0 = ((smem_u32(wring) >> 4) & 0x3FFFu) | (1u << 16);
+      const uint32_t p_lo0 = ((smem_u32(smem) >> 4) & 0x3FFFu) | (1u << 16);
+      const uint32_t g_lo0 = ((smem_u32(gmat) >> 4) & 0x3FFFu) | (1u << 16);
+      const uint32_t a2_lo0 = ((smem_u32(grp0) >> 4) & 0x3FFFu) | (1u << 16);
+      const uint32_t w_step = b_bytes >> 4, p_step = static_cast<uint32_t>(p.patch_bytes) >> 4;
+      int s = 0, ps = 0;
+      uint32_t s_par = 0, p_par = 0, w_lo = w_lo0, p_lo = p_lo0;
+      int pend[2] = {-1, -1};                  // next normalisation chunk to issue per TMEM buffer, -1 = none
+      uint32_t rdy_par[4] = {0, 0, 0, 0};      // a2_ready parity per (buffer, slot)
+      uint32_t free_par[2] = {1, 1};           // tmem_free parity per buffer (first use: free)
+      bool g_loaded = false;
+      // issue every normalisation K-block whose A operand is ready (never blocks)
+      auto service = [&]() {
+#pragma unroll
+        for (int bb = 0; bb < 2; ++bb) {
+          const int c = pend[bb];
+          if (c < 0) continue;
+          const int k = bb * 2 + (c & 1);
+          // the probe is one warp-wide instruction (identical result in every lane); broadcast makes that explicit
+          if (!__shfl_sync(0xffffffffu, (int)mbar_test_wait(&a2_ready[k], rdy_par[k]), 0)) continue;
+          rdy_par[k] ^= 1;
+          if (!g_loaded) { mbar_wait(gfull, 0); g_loaded = true; }
+          tc_fence_after_sync();
+          const uint64_t ad = (static_cast<uint64_t>(hi_dense) << 32) | (a2_lo0 + k * (kABytes >> 4));
+          const uint64_t bd = (static_cast<uint64_t>(hi_dense) << 32) | (g_lo0 + c * w_step);
+          const uint32_t d = tmem + bb * 256 + p.n_ch;
+          if (elect_one_sync()) {
+            tc_mma_tf32(d, ad, bd, idesc, c > 0 ? 1u : 0u);
+            tc_mma_tf32(d, ad + 2, bd + 2, idesc, 1u);
+            tc_mma_tf32(d, ad + 4, bd + 4, idesc, 1u);
+            tc_mma_tf32(d, ad + 6, bd + 6, idesc, 1u);
+            tc_commit(&a2_free[k]);
+            if (c == nC - 1) tc_commit(&norm_full[bb]);
+          }
+          pend[bb] = (c == nC - 1) ? -1 : c + 1;
+        }
+      };
+      int b = 0;
+      for (int item = blockIdx.x; item < total; item += gridDim.x, b ^= 1) {
+        const TcpItem it = tcp_decode(p, item);
+        const TcpClass cl = p.cls[it.cls];
+        // the epilogue of the item that last used TMEM buffer b must have finished reading it
+        if (!__shfl_sync(0xffffffffu, (int)mbar_test_wait(&tmem_free[b], free_par[b]), 0)) {
+          const long long t0 = clock64();
+          while (!__shfl_sync(0xffffffffu, (int)mbar_test_wait(&tmem_free[b], free_par[b]), 0)) {
+            if (gdn) service();
+            if (clock64() - t0 > 4000000000LL) __trap();
+          }
+        }
+        free_par[b] ^= 1;
+        tc_fence_after_sync();
+        const uint32_t d = tmem + b * 256;
+        uint32_t acc = 0;
+        for (int kc = 0; kc < p.k_chunks; ++kc) {
+          for (int g = cl.g_begin; g < cl.g_end; ++g) {
+            const Group gr = p.groups[g];
+            const uint32_t a_hi = (static_cast<uint32_t>(gr.sbo_bytes) >> 4) | (1u << 14) | (2u << 29);
+            uint32_t aoff = static_cast<uint32_t>(p.tap_aoff[gr.tap_begin]) >> 4;
+            mbar_wait(&pfull[ps], p_par);
+            for (int t = gr.tap_begin; t < gr.tap_end; ++t) {
+              const uint64_t ad = (static_cast<uint64_t>(a_hi) << 32) | (p_lo + aoff);
+              const uint64_t bd = (static_cast<uint64_t>(hi_dense) << 32) | w_lo;
+              aoff = static_cast<uint32_t>(p.tap_aoff[t + 1 < gr.tap_end ? t + 1 : t]) >> 4;
+              mbar_wait(&wfull[s], s_par);
+              tc_fence_after_sync();
+              if (elect_one_sync()) {
+                tc_mma_tf32(d, ad, bd, idesc, acc);
+                tc_mma_tf32(d, ad + 2, bd + 2, idesc, 1u);
+                tc_mma_tf32(d, ad + 4, bd + 4, idesc, 1u);
+                tc_mma_tf32(d, ad + 6, bd + 6, idesc, 1u);
+                tc_commit(&wempty[s]);
+              }
+              acc = 1u;
+              if (++s == S) { s = 0; s_par ^= 1; w_lo = w_lo0; } else { w_lo += w_step; }
+              if (gdn && (s & 1) == 0 && (pend[0] >= 0 || pend[1] >= 0)) service();   // poll every other K-block
+            }
+            if (elect_one_sync()) tc_commit(&pempty[ps]);
+            if (++ps == P) { ps = 0; p_par ^= 1; p_lo = p_lo0; } else { p_lo += p_step; }
+          }
+        }
+        if (elect_one_sync()) tc_commit(&acc_full[b]);
+        if (gdn) pend[b] = 0;
+      }
+      if (gdn) {
+        const long long t0 = clock64();
+        while (pend[0] >= 0 || pend[1] >= 0) {
+          service();
+          if (clock64() - t0 > 4000000000LL) __trap();
+        }
+      }
+    }
+    __syncwarp();
+  } else {
+    // ===================== two epilogue warpgroups, alternate items =====================
+    const int grp = (warp - 2) >> 2;           // 0: warps 2-5, 1: warps 6-9
+    const int q = warp & 3;                    // TMEM lane quadrant this warp may touch
+    const int row = q * 32 + lane;
+    const bool leader = (row == 0);
+    const uint32_t bar_id = 1 + grp;
+    uint8_t* gbuf = grp0 + grp * 2 * kABytes;  // two 16 KB slots: normalisation A operand / store staging
+    const uint32_t t_lane = tmem + (static_cast<uint32_t>(q * 32) << 16) + grp * 256;
+    uint32_t acc_par = 0, norm_par = 0;
+    uint32_t slot_par[2] = {1, 1};             // a2_free parity per slot (first use: free)
+
+    for (int item = blockIdx.x + grp * gridDim.x; item < total; item += 2 * gridDim.x) {
+      const TcpItem it = tcp_decode(p, item);
+      const int o_a = p.cls[it.cls].o_a, o_b = p.cls[it.cls].o_b;
+      const int gi = it.i0 + row / kTW, gj = it.j0 + row % kTW;
+      const bool px_ok = gi < p.t_h && gj < p.t_w;
+      const int64_t pix = (((int64_t)it.img * p.o_h + p.o_s * gi + o_a) * p.o_w + p.o_s * gj + o_b) * p.n_ch;
+      if constexpr (bwd) {
+        if (px_ok) {   // saved y / scale of this pixel: pull the rows into L2 while the main loop runs
+          for (int c = 0; c < nC; ++c) { prefetch_l2(p.yprev + pix + c * 32); prefetch_l2(p.scprev + pix + c * 32); }
+        }
+      }
+      mbar_wait(&acc_full[grp], acc_par);
+      acc_par ^= 1;
+      tc_fence_after_sync();
+
+      auto load_acc = [&](int c, float* v) {
+        tmem_ld32(t_lane + c * 32, v);
+        tmem_ld_wait();
+        const float4* b4 = reinterpret_cast<const float4*>(sbias + c * 32);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float4 bb = b4[j];
+          v[4 * j] += bb.x; v[4 * j + 1] += bb.y; v[4 * j + 2] += bb.z; v[4 * j + 3] += bb.w;
+        }
+      };
+      int stores = 0;
+      // double-buffered store of one output chunk through slot (stores & 1)
+      auto store_one = [&](int c, const float* o) {
+        uint8_t* buf = gbuf + (stores & 1) * kABytes;
+        if (stores >= 2) {
+          if (leader) tma_store_wait_read1();
+          __syncwarp();
+          named_bar_sync(bar_id, 128);
+        }
+        if (p.round_out) {
+          float r[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) r[j] = round_tf32(o[j]);
+          write_row32(buf, row, r);
+        } else {
+          write_row32(buf, row, o);
+        }
+        fence_proxy_async_smem();
+        named_bar_sync(bar_id, 128);
+        if (leader) { tma_store_4d(&p.out_map[it.cls], buf, c * 32, it.j0, it.i0, it.img); tma_store_commit(); }
+        __syncwarp();
+        ++stores;
+      };
+
+      if constexpr (!gdn) {
+        for (int c = 0; c < nC; ++c) {
+          float v[32];
+          load_acc(c, v);
+          if (p.act == ICADV_ACT_RELU) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+          } else if (p.act == ICADV_ACT_LEAKY) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = v[j] > 0.f ? v[j] : 0.01f * v[j];
+          } else if (p.act == ICADV_ACT_ABS) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = fabsf(v[j]);
+          }
+          store_one(c, v);
+        }
+      } else {
+        // ---- pass 1: A operand of the normalisation GEMM, chunk c -> slot c & 1 ----
+        for (int c = 0; c < nC; ++c) {
+          float v[32], a2[32];
+          load_acc(c, v);
+          if constexpr (!bwd) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) a2[j] = round_tf32(v[j] * v[j]);
+          } else {
+            float yv[32], sv[32];
+            ldg_row32(p.yprev + pix + c * 32, px_ok, yv);
+            ldg_row32(p.scprev + pix + c * 32, px_ok, sv);
+            if constexpr (EPI == ICADV_EPI_GDN_BWD) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) a2[j] = round_tf32(v[j] * yv[j] * sv[j] * sv[j]);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                const float s2 = sv[j] * sv[j];
+                a2[j] = s2 > 0.f ? round_tf32(__fdividef(v[j] * yv[j], s2)) : 0.f;
+              }
+            }
+          }
+          const int k = c & 1;
+          mbar_wait(&a2_free[grp * 2 + k], slot_par[k]);   // the MMAs that last read this slot are done
+          slot_par[k] ^= 1;
+          write_row32(gbuf + k * kABytes, row, a2);
+          fence_proxy_async_smem();
+          mbar_arrive(&a2_ready[grp * 2 + k]);
+        }
+        // ---- pass 2: normalise ----
+        mbar_wait(&norm_full[grp], norm_par);
+        norm_par ^= 1;
+        tc_fence_after_sync();
+        for (int c = 0; c < nC; ++c) {
+          float v[32], w[32];
+          load_acc(c, v);
+          tmem_ld32(t_lane + p.n_ch + c * 32, w);
+          tmem_ld_wait();
+          if constexpr (!bwd) {
+            float sc[32];
+            const float4* be4 = reinterpret_cast<const float4*>(sbeta + c * 32);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 be = be4[j];
+              const float nn[4] = {be.x + w[4 * j], be.y + w[4 * j + 1], be.z + w[4 * j + 2], be.w + w[4 * j + 3]};
+#pragma unroll
+              for (int t = 0; t < 4; ++t) {
+                const float r = rsqrtf(nn[t]);
+                sc[4 * j + t] = (EPI == ICADV_EPI_GDN_FWD) ? r : nn[t] * r;
+                v[4 * j + t] *= sc[4 * j + t];
+              }
+            }
+            // both outputs of the chunk fill the two slots: single-buffered per chunk
+            if (c > 0) {
+              if (leader) tma_store_wait_read0();
+              __syncwarp();
+              named_bar_sync(bar_id, 128);
+            }
+            if (p.round_out) {
+              float r[32];
+#pragma unroll
+              for (int j = 0; j < 32; ++j) r[j] = round_tf32(v[j]);
+              write_row32(gbuf, row, r);
+            } else {
+              write_row32(gbuf, row, v);
+            }
+            write_row32(gbuf + kABytes, row, sc);
+            fence_proxy_async_smem();
+            named_bar_sync(bar_id, 128);
+            if (leader) {
+              tma_store_4d(&p.out_map[it.cls], gbuf, c * 32, it.j0, it.i0, it.img);
+              tma_store_4d(&p.sc_map[it.cls], gbuf + kABytes, c * 32, it.j0, it.i0, it.img);
+              tma_store_commit();
+            }
+            __syncwarp();
+          } else {
+            float yv[32], sv[32];
+            ldg_row32(p.yprev + pix + c * 32, px_ok, yv);
+            ldg_row32(p.scprev + pix + c * 32, px_ok, sv);
+            constexpr float sign = (EPI == ICADV_EPI_GDN_BWD) ? -1.f : 1.f;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const float xs = sv[j] > 0.f ? __fdividef(yv[j], sv[j]) : 0.f;
+              v[j] = v[j] * sv[j] + sign * xs * w[j];
+            }
+            store_one(c, v);
+          }
+        }
+      }
+      // this item's TMEM reads are over: hand the buffer back to the MMA issuer; the staging slots are reused by
+      // the next item (as normalisation operands or staging) only after every store has finished READING them
+      tc_fence_before_sync();
+      if (leader) tma_store_wait_read0();
+      __syncwarp();
+      named_bar_sync(bar_id, 128);
+      if (leader) mbar_arrive(&tmem_free[grp]);
+    }
+    if (leader) tma_store_wait0();
+    __syncwarp();
+  }
+
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem, 512);
+}
+
+typedef void (*TcpKernelFn)(const TcpParams);
+
+static TcpKernelFn pick_persistent(int epi) {
+  switch (epi) {
+    case ICADV_EPI_LINEAR: return conv_tcp_kernel<ICADV_EPI_LINEAR>;
+    case ICADV_EPI_GDN_FWD: return conv_tcp_kernel<ICADV_EPI_GDN_FWD>;
+    case ICADV_EPI_IGDN_FWD: return conv_tcp_kernel<ICADV_EPI_IGDN_FWD>;
+    case ICADV_EPI_GDN_BWD: return conv_tcp_kernel<ICADV_EPI_GDN_BWD>;
+    case ICADV_EPI_IGDN_BWD: return conv_tcp_kernel<ICADV_EPI_IGDN_BWD>;
+    default: return nullptr;
+  }
+}
+
 typedef void (*TcKernelFn)(const TcParams);
 
 static TcKernelFn pick_kernel(int epi, int from_in) {
@@ -644,6 +1111,11 @@ struct icadv_conv_plan {
   TcParams params[4];
   dim3 grid[4];
   int smem_bytes[4];
+  // persistent variant (one launch covers every parity class)
+  int persistent;
+  TcpKernelFn pfn;
+  TcpParams pp;
+  int pgrid, psmem;
 };
 
 // largest multiple of 32 that divides n and is <= 256 (0 if none)
@@ -686,6 +1158,144 @@ static int tc_mode(const icadv_conv_desc* d, bool report) {
   TC_REQ(d->ksize * d->ksize <= kMaxTaps, "too many taps");
 #undef TC_REQ
   return kModeGeneric;
+}
+
+// ---- persistent variant: eligibility + parameter block.  Returns 1 if built, 0 if this shape stays on the per-tile
+//      kernel, < 0 on error.
+static int build_persistent(const icadv_conv_desc* d, int mode, const Geometry& g, icadv_conv_plan* plan) {
+  // ICADV_TC_PERSIST: 0 = never, 2 = every eligible shape (developer), unset / 1 = where it measured faster on B200
+  // (profiles/r1_step_breakdown_v5_*.json): stride-2 transposed convs with a forward epilogue (four short parity
+  // classes in one launch, epilogue overlapped: 3.96 -> 3.12 ms on g_s.4) and linear epilogues.  A single MMA stream
+  // per SM runs at ~2x the tensor floor, so long stride-2 convs and the backward epilogues (plain-load reads of the
+  // saved y / scale) stay on the two-CTA-per-SM kernel.
+  const char* env = getenv("ICADV_TC_PERSIST");
+  const int level = env != nullptr ? atoi(env) : 1;
+  if (level == 0) return 0;
+  if (!(mode == kModeGeneric || mode == kModeRgbIn) || d->acc_from_in) return 0;
+  const bool gdn = d->epi != ICADV_EPI_LINEAR;
+  const bool bwd = d->epi == ICADV_EPI_GDN_BWD || d->epi == ICADV_EPI_IGDN_BWD;
+  const int N = d->n_ch, K = d->k_ch, s = d->stride;
+  if (N > 256 || (gdn && N > 128)) return 0;            // 2 TMEM buffers x [acc N | norm N] must fit 512 columns
+  const bool tconv2 = d->form == ICADV_FORM_TCONV && s == 2;
+  if (level == 1 && !((tconv2 && !bwd) || (!gdn && mode == kModeGeneric))) return 0;
+  TcpParams& p = plan->pp;
+  memset(&p, 0, sizeof(p));
+  p.n_class = tconv2 ? g.n_launch : 1;
+  if (!tconv2 && g.n_launch != 1) return 0;
+  int rc = 0;
+  int n_groups = 0, n_taps = 0, max_patch = kABytes;
+  if (tconv2) {
+    // one dense input map shared by the classes: a uniform box (the largest halo), per-class origin and tap offsets
+    int pw = kTW, ph = kTH;
+    for (int l = 0; l < p.n_class; ++l) {
+      int dy0 = 1 << 14, dy1 = -(1 << 14), dx0 = 1 << 14, dx1 = -(1 << 14);
+      for (int t = 0; t < g.n_taps[l]; ++t) {
+        const Tap& tp = g.taps[l][t];
+        dy0 = tp.dy < dy0 ? tp.dy : dy0; dy1 = tp.dy > dy1 ? tp.dy : dy1;
+        dx0 = tp.dx < dx0 ? tp.dx : dx0; dx1 = tp.dx > dx1 ? tp.dx : dx1;
+      }
+      pw = kTW + dx1 - dx0 > pw ? kTW + dx1 - dx0 : pw;
+      ph = kTH + dy1 - dy0 > ph ? kTH + dy1 - dy0 : ph;
+    }
+    for (int l = 0; l < p.n_class; ++l) {
+      int dy0 = 1 << 14, dx0 = 1 << 14;
+      for (int t = 0; t < g.n_taps[l]; ++t) {
+        dy0 = g.taps[l][t].dy < dy0 ? g.taps[l][t].dy : dy0;
+        dx0 = g.taps[l][t].dx < dx0 ? g.taps[l][t].dx : dx0;
+      }
+      if (n_groups == kMaxGroups || n_taps + g.n_taps[l] > kMaxTaps) return 0;
+      Group& gr = p.groups[n_groups];
+      gr.map = 0; gr.plane5 = 0; gr.dy0 = (int16_t)dy0; gr.dx0 = (int16_t)dx0;
+      gr.sbo_bytes = pw * 128; gr.bytes = pw * ph * 128;
+      gr.tap_begin = (int16_t)n_taps;
+      for (int t = 0; t < g.n_taps[l]; ++t) {
+        p.tap_aoff[n_taps] = ((g.taps[l][t].dy - dy0) * pw + (g.taps[l][t].dx - dx0)) * 128;
+        p.tap_wtap[n_taps] = g.taps[l][t].wtap;
+        ++n_taps;
+      }
+      gr.tap_end = (int16_t)n_taps;
+      p.cls[l].g_begin = (int16_t)n_groups; p.cls[l].g_end = (int16_t)(n_groups + 1);
+      p.cls[l].o_a = (int16_t)g.out_a[l]; p.cls[l].o_b = (int16_t)g.out_b[l];
+      max_patch = gr.bytes > max_patch ? gr.bytes : max_patch;
+      ++n_groups;
+    }
+    rc = encode_nhwc(&p.a_map[0], d->in, K, d->in_w, d->in_h, d->n_img, K, (int64_t)d->in_w * K,
+                     (int64_t)d->in_h * d->in_w * K, pw, ph);
+    if (rc) return rc;
+    p.a_map[1] = p.a_map[2] = p.a_map[3] = p.a_map[0];
+  } else {
+    // single class: reuse the grouping of the per-tile plan (already built in plan->params[0])
+    const TcParams& q = plan->params[0];
+    n_groups = q.num_groups; n_taps = q.num_taps;
+    for (int i = 0; i < n_groups; ++i) { p.groups[i] = q.groups[i]; max_patch = q.groups[i].bytes > max_patch ? q.groups[i].bytes : max_patch; }
+    for (int i = 0; i < n_taps; ++i) { p.tap_aoff[i] = q.tap_aoff[i]; p.tap_wtap[i] = q.tap_wtap[i]; }
+    for (int i = 0; i < 4; ++i) p.a_map[i] = q.a_map[i];
+    p.cls[0].g_begin = 0; p.cls[0].g_end = (int16_t)n_groups; p.cls[0].o_a = 0; p.cls[0].o_b = 0;
+    p.a_rank5 = q.a_rank5;
+  }
+  // ---- weights, gamma, per-class output maps
+  if (mode == kModeRgbIn) rc = encode_mat(&p.w_map, d->wpack, 32, 5 * N, N);
+  else rc = encode_mat(&p.w_map, d->wpack, K, d->ksize * d->ksize * N, N);
+  if (!rc && gdn) rc = encode_mat(&p.g_map, d->gmat, N, N, N);
+  if (rc) return rc;
+  if (!gdn) p.g_map = p.w_map;
+  for (int l = 0; l < 4; ++l) {
+    const int ll = l < p.n_class ? l : 0;
+    if (tconv2) {
+      rc = encode_plane(&p.out_map[l], d->out, N, g.out_w, g.out_h, d->n_img, 2, g.out_a[ll], g.out_b[ll]);
+      if (!rc && gdn && !bwd) rc = encode_plane(&p.sc_map[l], d->out_scale, N, g.out_w, g.out_h, d->n_img, 2, g.out_a[ll], g.out_b[ll]);
+    } else {
+      rc = encode_nhwc(&p.out_map[l], d->out, N, g.out_w, g.out_h, d->n_img, N, (int64_t)g.out_w * N,
+                       (int64_t)g.out_h * g.out_w * N);
+      if (!rc && gdn && !bwd) rc = encode_nhwc(&p.sc_map[l], d->out_scale, N, g.out_w, g.out_h, d->n_img, N,
+                                                (int64_t)g.out_w * N, (int64_t)g.out_h * g.out_w * N);
+    }
+    if (rc) return rc;
+    if (!(gdn && !bwd)) p.sc_map[l] = p.out_map[l];
+  }
+  p.k_chunks = mode == kModeRgbIn ? 1 : K / 32;
+  p.n_ch = N; p.n_chunks = N / 32; p.n_total = N;
+  p.tiles_x = (g.tile_w + kTW - 1) / kTW; p.tiles_y = (g.tile_h + kTH - 1) / kTH;
+  p.n_img = d->n_img;
+  p.act = d->act; p.round_out = d->round_out_tf32;
+  p.t_h = g.tile_h; p.t_w = g.tile_w; p.o_h = g.out_h; p.o_w = g.out_w; p.o_s = tconv2 ? 2 : 1;
+  p.yprev = d->y_prev; p.scprev = d->sc_prev; p.bias = d->bias; p.beta = d->beta;
+  p.active = d->active; p.n_active = d->n_active;
+  // ---- shared memory: [patch ring | weight ring | gamma | 2 groups x 2 x 16 KB | barriers + bias/beta]
+  p.patch_bytes = (max_patch + 1023) & ~1023;
+  const int wbytes = N * 128;
+  const int gbytes = gdn ? N * N * 4 : 0;
+  const int fixed = 1024 + kBarBlock + 2 * N * 4 + gbytes + 4 * kABytes;
+  int groups_per_item = 0;
+  for (int l = 0; l < p.n_class; ++l) {
+    const int n = (p.cls[l].g_end - p.cls[l].g_begin) * p.k_chunks;
+    groups_per_item = n > groups_per_item ? n : groups_per_item;
+  }
+  int P = (groups_per_item >= 3 && groups_per_item <= 8) ? (groups_per_item > kMaxPatch ? kMaxPatch : groups_per_item) : 2;
+  while (P > 2 && fixed + P * p.patch_bytes + 2 * wbytes > kSmemLimit) --P;
+  int S = (kSmemLimit - fixed - P * p.patch_bytes) / wbytes;
+  if (S > kMaxStages) S = kMaxStages;
+  if (S < 2) return 0;
+  while (P < kMaxPatch - 1 && S > 4 && fixed + (P + 1) * p.patch_bytes + S * wbytes <= kSmemLimit) ++P;
+  p.num_patch = P; p.num_stages = S;
+  plan->psmem = fixed + P * p.patch_bytes + S * wbytes;
+  if (plan->psmem < 120 * 1024) plan->psmem = 120 * 1024;   // one CTA per SM: each allocates all 512 TMEM columns
+  int sms = 148;
+  int dev = 0;
+  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const long long items = (long long)d->n_img * p.tiles_x * p.tiles_y * p.n_class;
+  plan->pgrid = (int)(items < sms ? items : sms);
+  plan->pfn = pick_persistent(d->epi);
+  if (plan->pfn == nullptr) return 0;
+  static std::once_flag once;
+  static cudaError_t err = cudaSuccess;
+  std::call_once(once, [] {
+    for (int e = 0; e <= ICADV_EPI_IGDN_BWD && err == cudaSuccess; ++e)
+      err = cudaFuncSetAttribute(pick_persistent(e), cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
+  });
+  if (err != cudaSuccess) { set_error("cudaFuncSetAttribute(persistent) failed: %s", cudaGetErrorString(err)); return ICADV_ECUDA; }
+  plan->persistent = 1;
+  return 1;
 }
 
 extern "C" {
@@ -898,12 +1508,20 @@ int icadv_conv_plan_create(const icadv_conv_desc* d, icadv_conv_plan** out_plan)
     set_error("cudaFuncSetAttribute(max dynamic smem) failed: %s", cudaGetErrorString(attr_err));
     return ICADV_ECUDA;
   }
+  plan->persistent = 0;
+  rc = build_persistent(d, mode, g, plan);
+  if (rc < 0) { delete plan; return rc; }
   *out_plan = plan;
   return ICADV_OK;
 }
 
 int icadv_conv_plan_launch(const icadv_conv_plan* plan, icadv_stream_t stream) {
   ICADV_REQUIRE(plan != nullptr, "null plan");
+  if (plan->persistent) {
+    plan->pfn<<<plan->pgrid, kPThreads, plan->psmem, as_stream(stream)>>>(plan->pp);
+    ICADV_CUDA_TRY(cudaGetLastError());
+    return ICADV_OK;
+  }
   for (int l = 0; l < plan->n_launch; ++l) {
     plan->fn<<<plan->grid[l], kThreads, plan->smem_bytes[l], as_stream(stream)>>>(plan->params[l]);
     ICADV_CUDA_TRY(cudaGetLastError());
@@ -911,7 +1529,9 @@ int icadv_conv_plan_launch(const icadv_conv_plan* plan, icadv_stream_t stream) {
   return ICADV_OK;
 }
 
-int icadv_conv_plan_num_launches(const icadv_conv_plan* plan) { return plan ? plan->n_launch : 0; }
+int icadv_conv_plan_num_launches(const icadv_conv_plan* plan) {
+  return plan ? (plan->persistent ? 1 : plan->n_launch) : 0;
+}
 
 /* developer profiling: per-CTA phase timestamps (16 x int64 per CTA of launch 0), NULL to disable */
 int icadv_conv_plan_set_debug(icadv_conv_plan* plan, long long* dbg) {

@@ -12,7 +12,7 @@ import ctypes as C  # noqa: E402
 dev = torch.device("cuda:0")
 n = 8
 names = ["start", "setup", "first_full", "main_issued", "gdn_issued", "epi_acc1", "pass1_done", "epi_acc2",
-         "pass2_done", "stores_done", "end", "c0_loaded", "c0_bar1", "c0_written", "c0_bar2", "c0_issued", "c2_loaded",
+         "pass2_done", "stores_done", "end", "mma_wait_w", "mma_wait_p", "prod_wait_empty", "prod_loop", "c0_loaded", "c0_bar1", "c0_written", "c0_bar2", "c0_issued", "c2_loaded",
          "c2_storewait", "c2_bar2", "c2_issued", "-", "-", "-", "-", "acc_q0", "acc_q1", "acc_q2", "acc_q3", "ld_q0", "ld_q1", "ld_q2",
          "ld_q3"]
 
@@ -29,7 +29,7 @@ def run(name, d, keep, grid):
     rel = (t[:, :32] - t[:, :1])
     med = rel.median(0).values
     print(name, "CTAs", t.shape[0])
-    print("   " + "  ".join(f"{nm}={med[i]/1.9e3:6.2f}us" for i, nm in enumerate(names[:11])))
+    print("   " + "  ".join(f"{nm}={med[i]/1.9e3:6.2f}us" for i, nm in enumerate(names[:15])))
 
 
 H, W = 512, 768
