@@ -17,7 +17,12 @@ names = ["start", "setup", "first_full", "main_issued", "gdn_issued", "epi_acc1"
          "ld_q3"]
 
 
+ONLY = sys.argv[1] if len(sys.argv) > 1 else ""
+
+
 def run(name, d, keep, grid):
+    if ONLY and ONLY not in name:
+        return
     plan = ops.ConvPlan(d, keep)
     dbg = torch.zeros(2 * grid * 32, dtype=torch.int64, device=dev)
     L.call("icadv_conv_plan_set_debug", plan._h, C.c_void_p(dbg.data_ptr()))
