@@ -12,10 +12,35 @@ import torch
 
 from . import metrics
 from . import _lib as L
+from . import ops
 from .engine import AttackEngine, GenericAttackEngine, IfgsmEngine, RoiSpec
 from .program import parse_stack
 
 _ENGINES = {}
+
+
+# The scalar metrics of attack_rd.py:402-419 and self_ensemble.py:173-252 through the library's fixed-order reductions
+# (no torch arithmetic on image-sized tensors; what remains in Python is scalar bookkeeping).
+def _clamp01(x):
+    return ops.unary(x.contiguous(memory_format=torch.channels_last), 6)
+
+
+def _mse(a, b):
+    """mean((a - b)^2) over everything, as a Python float (these values are printed / returned as floats)."""
+    ac = a.contiguous(memory_format=torch.channels_last)
+    bc = b.contiguous(memory_format=torch.channels_last)
+    flat = lambda t: t.permute(0, 2, 3, 1).reshape(1, -1)
+    return float(ops.sum_sqdiff(flat(ac), flat(bc))[0]) / ac.numel()
+
+
+def _bpp(likelihoods, num_pixels):
+    """sum_k sum log(lik_k) / (-ln 2 * num_pixels)  (attack_rd.py:419, self_ensemble.py:222), 0-dim device tensor."""
+    total = None
+    for lik in likelihoods.values():
+        lk = lik if (lik.is_contiguous() or lik.is_contiguous(memory_format=torch.channels_last)) else lik.contiguous()
+        t = ops.log_sum(lk, 0.0)
+        total = t if total is None else ops.unary(total, 4, t)
+    return (total * (1.0 / (-math.log(2) * num_pixels))).reshape(())
 
 
 def _fused_stacks(net):
@@ -49,9 +74,9 @@ def clean_pass(im_s, net, args):
     """attack_rd.py:402-419."""
     net.eval()
     result = net(im_s)
-    output_s = torch.clamp(result["x_hat"], 0.0, 1.0) if args.clamp else result["x_hat"]
+    output_s = _clamp01(result["x_hat"]) if args.clamp else result["x_hat"]
     num_pixels = im_s.shape[2] * im_s.shape[3]
-    bpp_ori = sum(torch.log(l).sum() / (-math.log(2) * num_pixels) for l in result["likelihoods"].values())
+    bpp_ori = _bpp(result["likelihoods"], num_pixels)
     return output_s, bpp_ori
 
 
@@ -59,20 +84,20 @@ def clean_pass(im_s, net, args):
 def eval(im_adv, im_s, output_s, net, args):  # noqa: A001 (the reference shadows the builtin too)
     """self_ensemble.py:173-252 (defence branches out of scope)."""
     net.eval()
-    im_ = torch.clamp(im_adv, 0.0, 1.0) if args.clamp else im_adv
+    im_ = _clamp01(im_adv) if args.clamp else im_adv
     result = net(im_)
     x_hat = result["x_hat"]
-    mse_in = torch.mean((im_ - im_s) ** 2)
-    output_ = torch.clamp(x_hat, 0.0, 1.0) if args.clamp else x_hat
+    mse_in = _mse(im_, im_s)
+    output_ = _clamp01(x_hat) if args.clamp else x_hat
     num_pixels = im_adv.shape[2] * im_adv.shape[3]
-    bpp = sum(torch.log(l).sum() / (-math.log(2) * num_pixels) for l in result["likelihoods"].values())
-    mse_out = torch.mean((output_ - output_s) ** 2)
-    mse_results = {"mse_in": mse_in.item(), "mse_out": mse_out.item()}
+    bpp = _bpp(result["likelihoods"], num_pixels)
+    mse_out = _mse(output_, output_s)
+    mse_results = {"mse_in": mse_in, "mse_out": mse_out}
     vi_results = {"vi": None, "vi_msim": None}
     msim_out = metrics.ms_ssim(output_, output_s, data_range=1.0).item()
     msim_in = metrics.ms_ssim(im_, im_s, data_range=1.0).item()
     if mse_in > 1e-20 and mse_out > 1e-20:
-        vi_results["vi"] = 10.0 * math.log10(mse_out.item() / mse_in.item())
+        vi_results["vi"] = 10.0 * math.log10(mse_out / mse_in)
         if not getattr(args, "adv", False) and msim_in < 0.9999:
             vi_results["vi_msim"] = 10.0 * math.log10((1 - msim_out) / (1 - msim_in))
     else:

@@ -156,7 +156,8 @@ __global__ void sum_ws_kernel(const float* __restrict__ ws, float* __restrict__ 
   out[n] = s;
 }
 
-// elementwise helpers at the operator surface: 0 abs, 1 relu, 2 leaky(0.01), 3 round, 4 add (y = x + b), 5 round to TF32
+// elementwise helpers at the operator surface: 0 abs, 1 relu, 2 leaky(0.01), 3 round, 4 add (y = x + b), 5 round to TF32,
+// 6 clamp to [0, 1] (torch.clamp of attack_rd.py:411, self_ensemble.py:182,207)
 __global__ void unary_kernel(const float* __restrict__ x, const float* __restrict__ b, float* __restrict__ y, int64_t n,
                              int op) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
@@ -168,6 +169,7 @@ __global__ void unary_kernel(const float* __restrict__ x, const float* __restric
       case 2: r = v > 0.f ? v : 0.01f * v; break;
       case 3: r = rintf(v); break;
       case 5: r = round_tf32(v); break;
+      case 6: r = fminf(fmaxf(v, 0.f), 1.f); break;
       default: r = v + b[i]; break;
     }
     y[i] = r;
@@ -236,7 +238,7 @@ int icadv_gc_forward(const float* y, const float* scales, const float* means, co
 }
 
 int icadv_unary(const float* x, const float* b, float* y, int64_t n, int op, icadv_stream_t stream) {
-  ICADV_REQUIRE(x && y && op >= 0 && op <= 5 && (op != 4 || b), "bad unary args");
+  ICADV_REQUIRE(x && y && op >= 0 && op <= 6 && (op != 4 || b), "bad unary args");
   int64_t blocks = (n + 255) / 256;
   if (blocks > 148 * 16) blocks = 148 * 16;
   if (blocks < 1) blocks = 1;
