@@ -32,11 +32,11 @@ namespace icadv {
 constexpr int kTH = 16, kTW = 8, kTileM = 128;   // kTW must be 8: one tile row = one 8-row swizzle group
 constexpr int kABytes = kTileM * 128;   // one [128 x 32 fp32] operand / staging tile
 constexpr int kMaxStages = 8;           // weight ring
-constexpr int kMaxPatch = 4;            // patch ring
+constexpr int kMaxPatch = 8;            // patch ring
 constexpr int kMaxGroups = 8;           // patches per 32-channel chunk (parity planes; kernel rows of the RGB form)
 constexpr int kSmemLimit = 232448;      // 227 KB per CTA
 constexpr int kSmemTwoCta = 115712;     // (228 KB per SM) / 2 - 1 KB system reservation per CTA
-constexpr int kBarBlock = 320;          // 35 mbarriers + the TMEM base; followed by per-channel bias / beta copies (2 * n_ch floats)
+constexpr int kBarBlock = 384;          // up to 47 mbarriers + the TMEM base; followed by per-channel bias / beta copies (2 * n_ch floats)
 constexpr int kEpiCol2im = 5;           // internal epilogue code: narrow-output transposed conv via col2im
 constexpr int kZStride = 77;            // floats per row of the col2im staging tile (odd: conflict-free)
 
@@ -164,7 +164,8 @@ __global__ void __launch_bounds__(kThreads, 2) conv_tc_kernel(const __grid_const
   }
   if (threadIdx.x >= 64) {   // parameters the epilogue reads per channel
     for (int i = threadIdx.x - 64; i < p.n_ch; i += kThreads - 64) {
-      sbias[i] = p.bias != nullptr ? __ldg(p.bias + n_off + i) : 0.f;
+      const bool has_bias = p.bias != nullptr && (EPI != kEpiCol2im || i < p.c2i_nch);   // col2im: n_ch is the padded 96
+      sbias[i] = has_bias ? __ldg(p.bias + n_off + i) : 0.f;
       if (EPI == ICADV_EPI_GDN_FWD || EPI == ICADV_EPI_IGDN_FWD) sbeta[i] = __ldg(p.beta + i);
     }
   }
@@ -584,9 +585,13 @@ struct TcpParams {
   TcpClass cls[4];
   int n_class, k_chunks, n_ch, n_chunks, n_total;
   int num_patch, patch_bytes, num_stages;
+  int grp_bytes;                              // per epilogue group: 2 x 16 KB slots, or the col2im scatter tile
   int tiles_x, tiles_y, n_img;
+  int tile_step_y, tile_step_x, tile_off;    // col2im: tiles overlap by a 1-pixel halo
   int act, round_out, a_rank5;
   int t_h, t_w, o_h, o_w, o_s;
+  int c2i_in_h, c2i_in_w, c2i_nch;
+  float* c2i_out;
   const float* yprev; const float* scprev;
   const float* bias; const float* beta;
   const int* active; const int* n_active;
@@ -603,8 +608,8 @@ __device__ __forceinline__ TcpItem tcp_decode(const TcpParams& p, int item) {
   const int tiles = p.tiles_x * p.tiles_y;
   const int slot = tile_all / tiles, t = tile_all - slot * tiles;
   it.img = p.active != nullptr ? p.active[slot] : slot;
-  it.i0 = (t / p.tiles_x) * kTH;
-  it.j0 = (t % p.tiles_x) * kTW;
+  it.i0 = (t / p.tiles_x) * p.tile_step_y + p.tile_off;
+  it.j0 = (t % p.tiles_x) * p.tile_step_x + p.tile_off;
   return it;
 }
 
@@ -619,8 +624,8 @@ __global__ void __launch_bounds__(kPThreads, 1) conv_tcp_kernel(const __grid_con
   const uint32_t b_bytes = static_cast<uint32_t>(p.n_ch) * 128u;
   uint8_t* wring = smem + P * p.patch_bytes;
   uint8_t* gmat = wring + S * b_bytes;                              // gdn: nC boxes [32 x n_ch], resident
-  uint8_t* grp0 = gmat + (gdn ? nC * b_bytes : 0u);                 // 2 groups x 2 slots x 16 KB
-  uint64_t* wfull = reinterpret_cast<uint64_t*>(grp0 + 4 * kABytes);
+  uint8_t* grp0 = gmat + (gdn ? nC * b_bytes : 0u);                 // 2 groups x grp_bytes (2 slots x 16 KB; col2im: Z tile)
+  uint64_t* wfull = reinterpret_cast<uint64_t*>(grp0 + 2 * p.grp_bytes);
   uint64_t* wempty = wfull + kMaxStages;
   uint64_t* pfull = wempty + kMaxStages;
   uint64_t* pempty = pfull + kMaxPatch;
@@ -648,7 +653,7 @@ __global__ void __launch_bounds__(kPThreads, 1) conv_tcp_kernel(const __grid_con
     if (gdn) tma_prefetch_desc(&p.g_map);
   }
   for (int i = threadIdx.x; i < p.n_ch; i += kPThreads) {
-    sbias[i] = p.bias != nullptr ? __ldg(p.bias + i) : 0.f;
+    sbias[i] = (p.bias != nullptr && (EPI != kEpiCol2im || i < p.c2i_nch)) ? __ldg(p.bias + i) : 0.f;
     if (EPI == ICADV_EPI_GDN_FWD || EPI == ICADV_EPI_IGDN_FWD) sbeta[i] = __ldg(p.beta + i);
   }
   tc_fence_before_sync();
@@ -730,7 +735,8 @@ __global__ void __launch_bounds__(kPThreads, 1) conv_tcp_kernel(const __grid_con
           rdy_par[k] ^= 1;
           if (!g_loaded) { mbar_wait(gfull, 0); g_loaded = true; }
           tc_fence_after_sync();
-          const uint64_t ad = (static_cast<uint64_t>(hi_dense) << 32) | (a2_lo0 + k * (kABytes >> 4));
+          const uint64_t ad = (static_cast<uint64_t>(hi_dense) << 32) |
+                              (a2_lo0 + bb * (static_cast<uint32_t>(p.grp_bytes) >> 4) + (c & 1) * (kABytes >> 4));
           const uint64_t bd = (static_cast<uint64_t>(hi_dense) << 32) | (g_lo0 + c * w_step);
           const uint32_t d = tmem + bb * 256 + p.n_ch;
           if (elect_one_sync()) {
@@ -806,7 +812,7 @@ __global__ void __launch_bounds__(kPThreads, 1) conv_tcp_kernel(const __grid_con
     const int row = q * 32 + lane;
     const bool leader = (row == 0);
     const uint32_t bar_id = 1 + grp;
-    uint8_t* gbuf = grp0 + grp * 2 * kABytes;  // two 16 KB slots: normalisation A operand / store staging
+    uint8_t* gbuf = grp0 + grp * p.grp_bytes;  // two 16 KB slots: normalisation A operand / store staging (col2im: Z tile)
     const uint32_t t_lane = tmem + (static_cast<uint32_t>(q * 32) << 16) + grp * 256;
     uint32_t acc_par = 0, norm_par = 0;
     uint32_t slot_par[2] = {1, 1};             // a2_free parity per slot (first use: free)
@@ -825,6 +831,51 @@ __global__ void __launch_bounds__(kPThreads, 1) conv_tcp_kernel(const __grid_con
       mbar_wait(&acc_full[grp], acc_par);
       acc_par ^= 1;
       tc_fence_after_sync();
+
+      if constexpr (EPI == kEpiCol2im) {
+        // Z[128 px][taps * nch] -> this group's shared-memory tile, TMEM handed back at once, then the transposed-conv
+        // outputs of the tile interior are gathered from Z (same arithmetic as conv_tc_kernel<kEpiCol2im>)
+        float* Zs = reinterpret_cast<float*>(gbuf);
+        const int zcols = 25 * p.c2i_nch;
+        for (int c = 0; c < nC; ++c) {
+          float v[32];
+          tmem_ld32(t_lane + c * 32, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (c * 32 + j < zcols) Zs[row * kZStride + c * 32 + j] = v[j];
+        }
+        tc_fence_before_sync();
+        named_bar_sync(bar_id, 128);
+        if (leader) mbar_arrive(&tmem_free[grp]);
+        const int OH = 2 * p.c2i_in_h, OW = 2 * p.c2i_in_w, nch = p.c2i_nch;
+        constexpr int kIy = kTH - 2, kIx = kTW - 2;
+        for (int o = row; o < kIy * kIx * 4; o += 128) {
+          const int cell = o >> 2, a = (o >> 1) & 1, b = o & 1;
+          const int ti = 1 + cell / kIx, tj = 1 + cell % kIx;
+          const int yi = it.i0 + ti, xj = it.j0 + tj;
+          if (yi >= p.c2i_in_h || xj >= p.c2i_in_w) continue;
+          float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+          for (int u = 0; u < 3; ++u) {
+#pragma unroll
+            for (int v = 0; v < 3; ++v) {
+              const int kh = a + 2 * u, kw = b + 2 * v;
+              const bool ok = kh < 5 && kw < 5;
+              const float* z = Zs + ((ti + 1 - u) * kTW + (tj + 1 - v)) * kZStride + (ok ? (kh * 5 + kw) * nch : 0);
+#pragma unroll
+              for (int c = 0; c < 4; ++c)
+                if (c < nch) acc[c] += ok ? z[c] : 0.f;
+            }
+          }
+          float* dst = p.c2i_out + (((int64_t)it.img * OH + 2 * yi + a) * OW + 2 * xj + b) * nch;
+#pragma unroll
+          for (int c = 0; c < 4; ++c)
+            if (c < nch) dst[c] = acc[c] + sbias[c];
+        }
+        named_bar_sync(bar_id, 128);   // Z is rewritten by this group's next item
+        continue;
+      }
 
       auto load_acc = [&](int c, float* v) {
         tmem_ld32(t_lane + c * 32, v);
@@ -992,6 +1043,7 @@ static TcpKernelFn pick_persistent(int epi) {
     case ICADV_EPI_IGDN_FWD: return conv_tcp_kernel<ICADV_EPI_IGDN_FWD>;
     case ICADV_EPI_GDN_BWD: return conv_tcp_kernel<ICADV_EPI_GDN_BWD>;
     case ICADV_EPI_IGDN_BWD: return conv_tcp_kernel<ICADV_EPI_IGDN_BWD>;
+    case kEpiCol2im: return conv_tcp_kernel<kEpiCol2im>;
     default: return nullptr;
   }
 }
@@ -1171,17 +1223,18 @@ static int build_persistent(const icadv_conv_desc* d, int mode, const Geometry& 
   const char* env = getenv("ICADV_TC_PERSIST");
   const int level = env != nullptr ? atoi(env) : 1;
   if (level == 0) return 0;
-  if (!(mode == kModeGeneric || mode == kModeRgbIn) || d->acc_from_in) return 0;
+  if (!(mode == kModeGeneric || mode == kModeRgbIn || mode == kModeCol2im) || d->acc_from_in) return 0;
+  const bool c2i = mode == kModeCol2im;
   const bool gdn = d->epi != ICADV_EPI_LINEAR;
   const bool bwd = d->epi == ICADV_EPI_GDN_BWD || d->epi == ICADV_EPI_IGDN_BWD;
-  const int N = d->n_ch, K = d->k_ch, s = d->stride;
+  const int N = c2i ? 96 : d->n_ch, K = d->k_ch, s = d->stride;   // col2im: Z has 25 * n_ch <= 96 columns
   if (N > 256 || (gdn && N > 128)) return 0;            // 2 TMEM buffers x [acc N | norm N] must fit 512 columns
-  const bool tconv2 = d->form == ICADV_FORM_TCONV && s == 2;
-  if (level == 1 && !((tconv2 && !bwd) || (!gdn && mode == kModeGeneric))) return 0;
+  const bool tconv2 = !c2i && d->form == ICADV_FORM_TCONV && s == 2;
+  if (level == 1 && !((tconv2 && !bwd) || (!gdn && mode == kModeGeneric) || c2i)) return 0;
   TcpParams& p = plan->pp;
   memset(&p, 0, sizeof(p));
   p.n_class = tconv2 ? g.n_launch : 1;
-  if (!tconv2 && g.n_launch != 1) return 0;
+  if (!tconv2 && !c2i && g.n_launch != 1) return 0;
   int rc = 0;
   int n_groups = 0, n_taps = 0, max_patch = kABytes;
   if (tconv2) {
@@ -1235,12 +1288,14 @@ static int build_persistent(const icadv_conv_desc* d, int mode, const Geometry& 
   }
   // ---- weights, gamma, per-class output maps
   if (mode == kModeRgbIn) rc = encode_mat(&p.w_map, d->wpack, 32, 5 * N, N);
+  else if (c2i) rc = encode_mat(&p.w_map, d->wpack, K, d->ksize * d->ksize * d->n_ch, N);   // rows >= 25*n_ch read as zeros
   else rc = encode_mat(&p.w_map, d->wpack, K, d->ksize * d->ksize * N, N);
   if (!rc && gdn) rc = encode_mat(&p.g_map, d->gmat, N, N, N);
   if (rc) return rc;
   if (!gdn) p.g_map = p.w_map;
   for (int l = 0; l < 4; ++l) {
     const int ll = l < p.n_class ? l : 0;
+    if (c2i) { p.out_map[l] = p.sc_map[l] = p.w_map; continue; }   // col2im writes with plain stores
     if (tconv2) {
       rc = encode_plane(&p.out_map[l], d->out, N, g.out_w, g.out_h, d->n_img, 2, g.out_a[ll], g.out_b[ll]);
       if (!rc && gdn && !bwd) rc = encode_plane(&p.sc_map[l], d->out_scale, N, g.out_w, g.out_h, d->n_img, 2, g.out_a[ll], g.out_b[ll]);
@@ -1255,7 +1310,13 @@ static int build_persistent(const icadv_conv_desc* d, int mode, const Geometry& 
   }
   p.k_chunks = mode == kModeRgbIn ? 1 : K / 32;
   p.n_ch = N; p.n_chunks = N / 32; p.n_total = N;
-  p.tiles_x = (g.tile_w + kTW - 1) / kTW; p.tiles_y = (g.tile_h + kTH - 1) / kTH;
+  p.tile_step_y = kTH; p.tile_step_x = kTW; p.tile_off = 0;
+  if (c2i) {
+    const TcParams& q = plan->params[0];
+    p.tile_step_y = q.tile_step_y; p.tile_step_x = q.tile_step_x; p.tile_off = q.tile_off;
+    p.c2i_in_h = q.c2i_in_h; p.c2i_in_w = q.c2i_in_w; p.c2i_nch = q.c2i_nch; p.c2i_out = q.c2i_out;
+  }
+  p.tiles_x = (g.tile_w + p.tile_step_x - 1) / p.tile_step_x; p.tiles_y = (g.tile_h + p.tile_step_y - 1) / p.tile_step_y;
   p.n_img = d->n_img;
   p.act = d->act; p.round_out = d->round_out_tf32;
   p.t_h = g.tile_h; p.t_w = g.tile_w; p.o_h = g.out_h; p.o_w = g.out_w; p.o_s = tconv2 ? 2 : 1;
@@ -1265,18 +1326,28 @@ static int build_persistent(const icadv_conv_desc* d, int mode, const Geometry& 
   p.patch_bytes = (max_patch + 1023) & ~1023;
   const int wbytes = N * 128;
   const int gbytes = gdn ? N * N * 4 : 0;
-  const int fixed = 1024 + kBarBlock + 2 * N * 4 + gbytes + 4 * kABytes;
+  p.grp_bytes = c2i ? ((128 * kZStride * 4 + 1023) & ~1023) : 2 * kABytes;
+  const int fixed = 1024 + kBarBlock + 2 * N * 4 + gbytes + 2 * p.grp_bytes;
   int groups_per_item = 0;
   for (int l = 0; l < p.n_class; ++l) {
     const int n = (p.cls[l].g_end - p.cls[l].g_begin) * p.k_chunks;
     groups_per_item = n > groups_per_item ? n : groups_per_item;
   }
-  int P = (groups_per_item >= 3 && groups_per_item <= 8) ? (groups_per_item > kMaxPatch ? kMaxPatch : groups_per_item) : 2;
-  while (P > 2 && fixed + P * p.patch_bytes + 2 * wbytes > kSmemLimit) --P;
-  int S = (kSmemLimit - fixed - P * p.patch_bytes) / wbytes;
+  int P, S;
+  if (groups_per_item <= 8) {
+    // short main loops (RGB end layers, 1x1): the input is the DRAM stream -> deep patch ring, 3 weight stages
+    S = 3;
+    P = (kSmemLimit - fixed - S * wbytes) / p.patch_bytes;
+    if (P > kMaxPatch) P = kMaxPatch;
+    if (P < 2) { P = 2; S = (kSmemLimit - fixed - P * p.patch_bytes) / wbytes; }
+  } else {
+    P = 2;
+    S = (kSmemLimit - fixed - P * p.patch_bytes) / wbytes;
+    if (S > kMaxStages) S = kMaxStages;
+    while (P < 3 && S > 4 && fixed + (P + 1) * p.patch_bytes + (S - 1) * wbytes <= kSmemLimit) { ++P; --S; }
+  }
   if (S > kMaxStages) S = kMaxStages;
   if (S < 2) return 0;
-  while (P < kMaxPatch - 1 && S > 4 && fixed + (P + 1) * p.patch_bytes + S * wbytes <= kSmemLimit) ++P;
   p.num_patch = P; p.num_stages = S;
   plan->psmem = fixed + P * p.patch_bytes + S * wbytes;
   if (plan->psmem < 120 * 1024) plan->psmem = 120 * 1024;   // one CTA per SM: each allocates all 512 TMEM columns
@@ -1285,12 +1356,12 @@ static int build_persistent(const icadv_conv_desc* d, int mode, const Geometry& 
   if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const long long items = (long long)d->n_img * p.tiles_x * p.tiles_y * p.n_class;
   plan->pgrid = (int)(items < sms ? items : sms);
-  plan->pfn = pick_persistent(d->epi);
+  plan->pfn = pick_persistent(c2i ? kEpiCol2im : d->epi);
   if (plan->pfn == nullptr) return 0;
   static std::once_flag once;
   static cudaError_t err = cudaSuccess;
   std::call_once(once, [] {
-    for (int e = 0; e <= ICADV_EPI_IGDN_BWD && err == cudaSuccess; ++e)
+    for (int e = 0; e <= kEpiCol2im && err == cudaSuccess; ++e)
       err = cudaFuncSetAttribute(pick_persistent(e), cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
   });
   if (err != cudaSuccess) { set_error("cudaFuncSetAttribute(persistent) failed: %s", cudaGetErrorString(err)); return ICADV_ECUDA; }
