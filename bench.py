@@ -275,13 +275,17 @@ def run_ours(args):
     del eng
     torch.cuda.empty_cache()
 
-    def e2e_once():
-        xin = host.to(dev, non_blocking=True)
-        im_adv, output_adv, _, bpp_ori, bpp, mse_r, vi_r = patk.attack_(xin, net, a2)
-        out_host = im_adv.to("cpu", non_blocking=False)
-        return out_host, float(bpp)
+    out_pinned = torch.empty_like(host).pin_memory()
 
-    e2e_once()   # builds the engine for this shape (plans, buffers): not part of the steady-state call
+    def e2e_once():
+        xin = host.to(dev, non_blocking=True)                       # pinned host -> device
+        im_adv, output_adv, _, bpp_ori, bpp, mse_r, vi_r = patk.attack_(xin, net, a2)
+        out_pinned.copy_(im_adv, non_blocking=True)                 # adversarial images -> pinned host
+        torch.cuda.synchronize()
+        return out_pinned, float(bpp)
+
+    e2e_once()   # builds the engine and the cached inference programs for this shape (plans, buffers) ...
+    e2e_once()   # ... and lets the caching allocator settle: the timed call below is a steady-state call
     barrier()
     t0 = time.perf_counter()
     out_host, _ = e2e_once()

@@ -97,8 +97,17 @@ class StackProgram:
                 self.bwd_kind[j] = None
         gdn_ok = lambda j: units[j].gdn is not None and 2 * units[j].cout <= 512
         # ---- forward buffers: y[j] = unit output (after GDN if any); sc[j] = GDN scale; u[j] = pre-GDN (unfused only)
-        self.y = [f(n_img, *self.hw[j + 1], units[j].cout) for j in range(U)]
-        self.sc = [torch.empty_like(self.y[j]) if units[j].gdn is not None else None for j in range(U)]
+        if need_grad:
+            self.y = [f(n_img, *self.hw[j + 1], units[j].cout) for j in range(U)]
+            self.sc = [torch.empty_like(self.y[j]) if units[j].gdn is not None else None for j in range(U)]
+        else:
+            # inference-only program (clean pass, final eval): nothing is saved for a backward pass, so the unit outputs
+            # ping-pong between two flat buffers and every scale goes to one scratch buffer
+            shapes = [(n_img, *self.hw[j + 1], units[j].cout) for j in range(U)]
+            numel = [s[0] * s[1] * s[2] * s[3] for s in shapes]
+            flat = [f(max(numel[0::2])), f(max(numel[1::2]) if U > 1 else 1), f(max(numel))]
+            self.y = [flat[j % 2][:numel[j]].view(shapes[j]) for j in range(U)]
+            self.sc = [flat[2][:numel[j]].view(shapes[j]) if units[j].gdn is not None else None for j in range(U)]
         self.fused_fwd = [gdn_ok(j) and self.fwd_kind[j] in ("generic", "rgb_in") for j in range(U)]
         self.u = [torch.empty_like(self.y[j]) if (units[j].gdn is not None and not self.fused_fwd[j]) else None
                   for j in range(U)]
