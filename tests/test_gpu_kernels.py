@@ -386,3 +386,86 @@ def test_tc_backward_epilogue_is_deterministic(dev):
                              path="tc") for _ in range(5)]
             for o in outs[1:]:
                 assert torch.equal(o, outs[0])
+
+
+@pytest.fixture
+def persist_env():
+    import os
+    old = os.environ.get("ICADV_TC_PERSIST")
+    yield lambda v: os.environ.__setitem__("ICADV_TC_PERSIST", str(v))
+    if old is None:
+        os.environ.pop("ICADV_TC_PERSIST", None)
+    else:
+        os.environ["ICADV_TC_PERSIST"] = old
+
+
+@pytest.mark.parametrize("case", ["sconv_gdn_fwd", "tconv_igdn_fwd", "tconv_gdn_bwd", "sconv_igdn_bwd", "linear_relu",
+                                  "rgb_in_gdn", "col2im"])
+def test_persistent_variant_equals_per_tile_kernel(dev, persist_env, case):
+    """The persistent kernel (one CTA per SM, TMEM double buffer, two epilogue warpgroups, all parity classes in one
+    launch; ICADV_TC_PERSIST=2 forces it for every eligible shape) and the per-tile kernel (=0) run the same K order and
+    the same epilogue arithmetic: results must agree to fp32 round-off, on ragged sizes and with an active-image list."""
+    from imagecompression_adversarial_b200 import _lib as L
+    from imagecompression_adversarial_b200 import ops
+    g = torch.Generator(device=dev).manual_seed(77)
+    C, n = 128, 5
+    gamma, beta = _gdn_params(C, dev, g)
+    act_idx = torch.tensor([4, 0, 2, 0, 0], device=dev, dtype=torch.int32)
+    n_act = torch.tensor([3], device=dev, dtype=torch.int32)
+    outs = []
+    for level in (0, 2):
+        persist_env(level)
+        kw = dict(active=act_idx, n_active=n_act)
+        if case == "sconv_gdn_fwd":
+            x = torch.randn(n, 37, 50, C, device=dev, generator=torch.Generator(device=dev).manual_seed(1))
+            w = ops.pack_weight(torch.randn(C, C, 5, 5, device=dev, generator=torch.Generator(device=dev).manual_seed(2)) / 56, 0)
+            out = torch.zeros(n, 19, 25, C, device=dev); sc = torch.zeros_like(out)
+            ops.conv(x, w, beta, form=L.FORM_SCONV, ksize=5, stride=2, n_ch=C, epi=L.EPI_GDN_FWD, gmat=gamma, beta=beta,
+                     out=out, out_scale=sc, path="tc", round_out=True, **kw)
+            outs.append((out, sc))
+        elif case == "tconv_igdn_fwd":
+            x = torch.randn(n, 11, 19, 192, device=dev, generator=torch.Generator(device=dev).manual_seed(1))
+            w = ops.pack_weight(torch.randn(192, C, 5, 5, device=dev, generator=torch.Generator(device=dev).manual_seed(2)) / 35, 2)
+            out = torch.zeros(n, 22, 38, C, device=dev); sc = torch.zeros_like(out)
+            ops.conv(x, w, beta, form=L.FORM_TCONV, ksize=5, stride=2, n_ch=C, epi=L.EPI_IGDN_FWD, gmat=gamma, beta=beta,
+                     out=out, out_scale=sc, path="tc", **kw)
+            outs.append((out, sc))
+        elif case in ("tconv_gdn_bwd", "sconv_igdn_bwd"):
+            tconv = case == "tconv_gdn_bwd"
+            gsrc = torch.randn(n, 13, 21, C, device=dev, generator=torch.Generator(device=dev).manual_seed(1)) if tconv else \
+                torch.randn(n, 26, 42, C, device=dev, generator=torch.Generator(device=dev).manual_seed(1))
+            oh, ow = (26, 42) if tconv else (13, 21)
+            w = ops.pack_weight(torch.randn(C, C, 5, 5, device=dev, generator=torch.Generator(device=dev).manual_seed(2)) / 56,
+                                1 if tconv else 3)
+            yp = torch.randn(n, oh, ow, C, device=dev, generator=torch.Generator(device=dev).manual_seed(3))
+            sp = 0.5 + torch.rand(n, oh, ow, C, device=dev, generator=torch.Generator(device=dev).manual_seed(4))
+            out = torch.zeros(n, oh, ow, C, device=dev)
+            ops.conv(gsrc, w, None, form=L.FORM_TCONV if tconv else L.FORM_SCONV, ksize=5, stride=2, n_ch=C,
+                     epi=L.EPI_GDN_BWD if tconv else L.EPI_IGDN_BWD, gmat=gamma.t().contiguous(), y_prev=yp, sc_prev=sp,
+                     out=out, path="tc", round_out=True, **kw)
+            outs.append((out,))
+        elif case == "linear_relu":
+            x = torch.randn(n, 12, 20, 192, device=dev, generator=torch.Generator(device=dev).manual_seed(1))
+            w = ops.pack_weight(torch.randn(C, 192, 3, 3, device=dev, generator=torch.Generator(device=dev).manual_seed(2)) / 40, 0)
+            out = torch.zeros(n, 12, 20, C, device=dev)
+            ops.conv(x, w, beta, form=L.FORM_SCONV, ksize=3, stride=1, n_ch=C, act=L.ACT_RELU, out=out, path="tc", **kw)
+            outs.append((out,))
+        elif case == "rgb_in_gdn":
+            x = torch.rand(n, 36, 52, 3, device=dev, generator=torch.Generator(device=dev).manual_seed(1))
+            pad = ops.pad_rgb4(x, ops.alloc_pad4(n, 36, 52, dev))
+            w = ops.pack_weight_rgb(torch.randn(C, 3, 5, 5, device=dev, generator=torch.Generator(device=dev).manual_seed(2)) / 9)
+            out = torch.zeros(n, 18, 26, C, device=dev); sc = torch.zeros_like(out)
+            ops.conv(pad, w, beta, form=L.FORM_SCONV, ksize=5, stride=2, n_ch=C, epi=L.EPI_GDN_FWD, gmat=gamma, beta=beta,
+                     out=out, out_scale=sc, path="tc", in_pad4=True, **kw)
+            outs.append((out, sc))
+        else:
+            x = torch.randn(n, 15, 23, C, device=dev, generator=torch.Generator(device=dev).manual_seed(1))
+            w = ops.pack_weight(torch.randn(C, 3, 5, 5, device=dev, generator=torch.Generator(device=dev).manual_seed(2)) / 30, 2)
+            b3 = torch.randn(3, device=dev, generator=torch.Generator(device=dev).manual_seed(5))
+            out = torch.zeros(n, 30, 46, 3, device=dev)
+            ops.conv(x, w, b3, form=L.FORM_TCONV, ksize=5, stride=2, n_ch=3, out=out, path="tc", **kw)
+            outs.append((out,))
+    for a, b in zip(*outs):
+        assert float(a.abs().max()) > 0
+        assert float(a[1].abs().max()) == 0 and float(b[1].abs().max()) == 0     # images not in the active list stay untouched
+        torch.testing.assert_close(b, a, rtol=1e-5, atol=1e-6)
