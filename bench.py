@@ -286,11 +286,14 @@ def run_ours(args):
 
     e2e_once()   # builds the engine and the cached inference programs for this shape (plans, buffers) ...
     e2e_once()   # ... and lets the caching allocator settle: the timed call below is a steady-state call
-    barrier()
-    t0 = time.perf_counter()
-    out_host, _ = e2e_once()
-    barrier()
-    dt = time.perf_counter() - t0
+    e2e_times = []
+    for _ in range(3):          # three timed calls, the median is reported (all three are listed in the note)
+        barrier()
+        t0 = time.perf_counter()
+        out_host, _ = e2e_once()
+        barrier()
+        e2e_times.append(time.perf_counter() - t0)
+    dt = sorted(e2e_times)[1]
     if world > 1:
         t = torch.tensor([dt], device=dev)
         torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
@@ -298,7 +301,8 @@ def run_ours(args):
     e2e = {"value": GLOBAL_BATCH * e2e_steps / dt, "unit": "image-iterations/s",
            "h2d_bytes_per_step": host.numel() * 4 * world // e2e_steps,
            "d2h_bytes_per_step": out_host.numel() * 4 * world // e2e_steps,
-           "note": f"attack_() with {e2e_steps} iterations: H2D + clean pass + loop + final eval (2x MS-SSIM) + D2H"}
+           "note": f"attack_() with {e2e_steps} iterations: H2D + clean pass + loop + final eval (2x MS-SSIM) + D2H; "
+                   f"median of 3 calls ({', '.join(f'{t:.3f}' for t in e2e_times)} s on rank 0)"}
 
     if rank == 0:
         cpu = cpu_baseline_sample()

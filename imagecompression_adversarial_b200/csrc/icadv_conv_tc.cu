@@ -36,7 +36,7 @@ constexpr int kMaxPatch = 8;            // patch ring
 constexpr int kMaxGroups = 8;           // patches per 32-channel chunk (parity planes; kernel rows of the RGB form)
 constexpr int kSmemLimit = 232448;      // 227 KB per CTA
 constexpr int kSmemTwoCta = 115712;     // (228 KB per SM) / 2 - 1 KB system reservation per CTA
-constexpr int kBarBlock = 384;          // up to 47 mbarriers + the TMEM base; followed by per-channel bias / beta copies (2 * n_ch floats)
+constexpr int kBarBlock = 448;          // up to 49 mbarriers + the TMEM base; followed by per-channel bias / beta copies (2 * n_ch floats)
 constexpr int kEpiCol2im = 5;           // internal epilogue code: narrow-output transposed conv via col2im
 constexpr int kZStride = 77;            // floats per row of the col2im staging tile (odd: conflict-free)
 
@@ -578,7 +578,8 @@ struct TcpClass {
 struct TcpParams {
   CUtensorMap a_map[4];
   CUtensorMap w_map, g_map;
-  CUtensorMap out_map[4], sc_map[4];   // per class
+  CUtensorMap out_map[4], sc_map[4];   // per class; backward epilogues: sc_map = saved scale, yprev_map = saved y
+  CUtensorMap yprev_map[4];
   Group groups[kMaxGroups];
   int32_t tap_aoff[kMaxTaps];
   int16_t tap_wtap[kMaxTaps];
@@ -635,7 +636,8 @@ __global__ void __launch_bounds__(kPThreads, 1) conv_tcp_kernel(const __grid_con
   uint64_t* tmem_free = norm_full + 2;        // [2]
   uint64_t* a2_ready = tmem_free + 2;         // [2 groups][2 slots]
   uint64_t* a2_free = a2_ready + 4;           // [2][2]
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(a2_free + 4);
+  uint64_t* ld_full = a2_free + 4;            // [2] backward: saved y / scale chunk of each epilogue group
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(ld_full + 2);
   float* sbias = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(wfull) + kBarBlock);
   float* sbeta = sbias + p.n_ch;
 
@@ -645,6 +647,7 @@ __global__ void __launch_bounds__(kPThreads, 1) conv_tcp_kernel(const __grid_con
     mbar_init(gfull, 1);
     for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&norm_full[b], 1); mbar_init(&tmem_free[b], 1); }
     for (int k = 0; k < 4; ++k) { mbar_init(&a2_ready[k], 128); mbar_init(&a2_free[k], 1); }
+    mbar_init(&ld_full[0], 1); mbar_init(&ld_full[1], 1);
     mbar_fence_init();
   }
   if (warp == 1) { tmem_alloc(tmem_ptr, 512); tmem_relinquish(); }
@@ -729,14 +732,15 @@ __global__ void __launch_bounds__(kPThreads, 1) conv_tcp_kernel(const __grid_con
         for (int bb = 0; bb < 2; ++bb) {
           const int c = pend[bb];
           if (c < 0) continue;
-          const int k = bb * 2 + (c & 1);
+          const int slot = bwd ? 0 : (c & 1);   // backward: the operand replaces the staged y chunk in place (slot 0)
+          const int k = bb * 2 + slot;
           // the probe is one warp-wide instruction (identical result in every lane); broadcast makes that explicit
           if (!__shfl_sync(0xffffffffu, (int)mbar_test_wait(&a2_ready[k], rdy_par[k]), 0)) continue;
           rdy_par[k] ^= 1;
           if (!g_loaded) { mbar_wait(gfull, 0); g_loaded = true; }
           tc_fence_after_sync();
           const uint64_t ad = (static_cast<uint64_t>(hi_dense) << 32) |
-                              (a2_lo0 + bb * (static_cast<uint32_t>(p.grp_bytes) >> 4) + (c & 1) * (kABytes >> 4));
+                              (a2_lo0 + bb * (static_cast<uint32_t>(p.grp_bytes) >> 4) + slot * (kABytes >> 4));
           const uint64_t bd = (static_cast<uint64_t>(hi_dense) << 32) | (g_lo0 + c * w_step);
           const uint32_t d = tmem + bb * 256 + p.n_ch;
           if (elect_one_sync()) {
@@ -816,6 +820,26 @@ __global__ void __launch_bounds__(kPThreads, 1) conv_tcp_kernel(const __grid_con
     const uint32_t t_lane = tmem + (static_cast<uint32_t>(q * 32) << 16) + grp * 256;
     uint32_t acc_par = 0, norm_par = 0;
     uint32_t slot_par[2] = {1, 1};             // a2_free parity per slot (first use: free)
+    // Backward epilogues stage the saved y / scale of the item one 32-channel chunk at a time in this group's slot pair
+    // [y | scale] (TMA, swizzled rows).  Everything that follows a chunk happens IN PLACE: pass 1 overwrites the y
+    // rows with the normalisation operand (each thread reads and writes only its own row), pass 2 overwrites them
+    // with the output chunk, which is TMA-stored from there.  The next chunk is requested once the tensor core
+    // (pass 1) or the store engine (pass 2) has finished reading the pair.
+    uint32_t ld_par = 0, a2c_par = 0;
+    uint8_t* bufY = gbuf;
+    uint8_t* bufS = gbuf + kABytes;
+    auto fetch = [&](const TcpItem& t, int c) {
+      if (leader) {
+        mbar_arrive_expect_tx(&ld_full[grp], 2 * kABytes);
+        tma_load_4d(bufY, &p.yprev_map[t.cls], &ld_full[grp], c * 32, t.j0, t.i0, t.img);
+        tma_load_4d(bufS, &p.sc_map[t.cls], &ld_full[grp], c * 32, t.j0, t.i0, t.img);
+      }
+      __syncwarp();
+    };
+    if constexpr (bwd) {
+      const int first = blockIdx.x + grp * gridDim.x;
+      if (first < total) fetch(tcp_decode(p, first), 0);
+    }
 
     for (int item = blockIdx.x + grp * gridDim.x; item < total; item += 2 * gridDim.x) {
       const TcpItem it = tcp_decode(p, item);
@@ -823,11 +847,7 @@ __global__ void __launch_bounds__(kPThreads, 1) conv_tcp_kernel(const __grid_con
       const int gi = it.i0 + row / kTW, gj = it.j0 + row % kTW;
       const bool px_ok = gi < p.t_h && gj < p.t_w;
       const int64_t pix = (((int64_t)it.img * p.o_h + p.o_s * gi + o_a) * p.o_w + p.o_s * gj + o_b) * p.n_ch;
-      if constexpr (bwd) {
-        if (px_ok) {   // saved y / scale of this pixel: pull the rows into L2 while the main loop runs
-          for (int c = 0; c < nC; ++c) { prefetch_l2(p.yprev + pix + c * 32); prefetch_l2(p.scprev + pix + c * 32); }
-        }
-      }
+      (void)px_ok; (void)pix;
       mbar_wait(&acc_full[grp], acc_par);
       acc_par ^= 1;
       tc_fence_after_sync();
@@ -937,8 +957,10 @@ __global__ void __launch_bounds__(kPThreads, 1) conv_tcp_kernel(const __grid_con
             for (int j = 0; j < 32; ++j) a2[j] = round_tf32(v[j] * v[j]);
           } else {
             float yv[32], sv[32];
-            ldg_row32(p.yprev + pix + c * 32, px_ok, yv);
-            ldg_row32(p.scprev + pix + c * 32, px_ok, sv);
+            mbar_wait(&ld_full[grp], ld_par);
+            ld_par ^= 1;
+            read_row32(bufY, row, yv);
+            read_row32(bufS, row, sv);
             if constexpr (EPI == ICADV_EPI_GDN_BWD) {
 #pragma unroll
               for (int j = 0; j < 32; ++j) a2[j] = round_tf32(v[j] * yv[j] * sv[j] * sv[j]);
@@ -949,6 +971,14 @@ __global__ void __launch_bounds__(kPThreads, 1) conv_tcp_kernel(const __grid_con
                 a2[j] = s2 > 0.f ? round_tf32(__fdividef(v[j] * yv[j], s2)) : 0.f;
               }
             }
+            write_row32(bufY, row, a2);                 // in place: this thread's own row
+            fence_proxy_async_smem();
+            mbar_arrive(&a2_ready[grp * 2]);
+            // the pair is refilled once the tensor core has read the operand (all 128 threads arrived before that)
+            if (leader) mbar_wait(&a2_free[grp * 2], a2c_par);
+            a2c_par ^= 1;
+            if (c + 1 < nC) fetch(it, c + 1);
+            continue;
           }
           const int k = c & 1;
           mbar_wait(&a2_free[grp * 2 + k], slot_par[k]);   // the MMAs that last read this slot are done
@@ -961,6 +991,7 @@ __global__ void __launch_bounds__(kPThreads, 1) conv_tcp_kernel(const __grid_con
         mbar_wait(&norm_full[grp], norm_par);
         norm_par ^= 1;
         tc_fence_after_sync();
+        if constexpr (bwd) fetch(it, 0);   // every normalisation MMA has completed: the pair is free again
         for (int c = 0; c < nC; ++c) {
           float v[32], w[32];
           load_acc(c, v);
@@ -1005,15 +1036,27 @@ __global__ void __launch_bounds__(kPThreads, 1) conv_tcp_kernel(const __grid_con
             __syncwarp();
           } else {
             float yv[32], sv[32];
-            ldg_row32(p.yprev + pix + c * 32, px_ok, yv);
-            ldg_row32(p.scprev + pix + c * 32, px_ok, sv);
+            mbar_wait(&ld_full[grp], ld_par);
+            ld_par ^= 1;
+            read_row32(bufY, row, yv);
+            read_row32(bufS, row, sv);
             constexpr float sign = (EPI == ICADV_EPI_GDN_BWD) ? -1.f : 1.f;
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
               const float xs = sv[j] > 0.f ? __fdividef(yv[j], sv[j]) : 0.f;
               v[j] = v[j] * sv[j] + sign * xs * w[j];
+              if (p.round_out) v[j] = round_tf32(v[j]);
             }
-            store_one(c, v);
+            write_row32(bufY, row, v);                  // in place, then stored from here
+            fence_proxy_async_smem();
+            named_bar_sync(bar_id, 128);
+            if (leader) {
+              tma_store_4d(&p.out_map[it.cls], bufY, c * 32, it.j0, it.i0, it.img);
+              tma_store_commit();
+              if (c + 1 < nC) tma_store_wait_read0();   // the store engine has read the pair: refill it
+            }
+            __syncwarp();
+            if (c + 1 < nC) fetch(it, c + 1);
           }
         }
       }
@@ -1024,6 +1067,10 @@ __global__ void __launch_bounds__(kPThreads, 1) conv_tcp_kernel(const __grid_con
       __syncwarp();
       named_bar_sync(bar_id, 128);
       if (leader) mbar_arrive(&tmem_free[grp]);
+      if constexpr (bwd) {   // request the first saved chunk of this group's next item while its main loop runs
+        const int nxt = item + 2 * gridDim.x;
+        if (nxt < total) fetch(tcp_decode(p, nxt), 0);
+      }
     }
     if (leader) tma_store_wait0();
     __syncwarp();
@@ -1230,7 +1277,7 @@ static int build_persistent(const icadv_conv_desc* d, int mode, const Geometry& 
   const int N = c2i ? 96 : d->n_ch, K = d->k_ch, s = d->stride;   // col2im: Z has 25 * n_ch <= 96 columns
   if (N > 256 || (gdn && N > 128)) return 0;            // 2 TMEM buffers x [acc N | norm N] must fit 512 columns
   const bool tconv2 = !c2i && d->form == ICADV_FORM_TCONV && s == 2;
-  if (level == 1 && !((tconv2 && !bwd) || (!gdn && mode == kModeGeneric) || c2i)) return 0;
+  if (level == 1 && !(tconv2 || (!gdn && mode == kModeGeneric) || c2i)) return 0;
   TcpParams& p = plan->pp;
   memset(&p, 0, sizeof(p));
   p.n_class = tconv2 ? g.n_launch : 1;
@@ -1295,18 +1342,25 @@ static int build_persistent(const icadv_conv_desc* d, int mode, const Geometry& 
   if (!gdn) p.g_map = p.w_map;
   for (int l = 0; l < 4; ++l) {
     const int ll = l < p.n_class ? l : 0;
-    if (c2i) { p.out_map[l] = p.sc_map[l] = p.w_map; continue; }   // col2im writes with plain stores
+    if (c2i) { p.out_map[l] = p.sc_map[l] = p.yprev_map[l] = p.w_map; continue; }   // col2im writes with plain stores
     if (tconv2) {
       rc = encode_plane(&p.out_map[l], d->out, N, g.out_w, g.out_h, d->n_img, 2, g.out_a[ll], g.out_b[ll]);
       if (!rc && gdn && !bwd) rc = encode_plane(&p.sc_map[l], d->out_scale, N, g.out_w, g.out_h, d->n_img, 2, g.out_a[ll], g.out_b[ll]);
+      if (!rc && bwd) rc = encode_plane(&p.sc_map[l], d->sc_prev, N, g.out_w, g.out_h, d->n_img, 2, g.out_a[ll], g.out_b[ll]);
+      if (!rc && bwd) rc = encode_plane(&p.yprev_map[l], d->y_prev, N, g.out_w, g.out_h, d->n_img, 2, g.out_a[ll], g.out_b[ll]);
     } else {
       rc = encode_nhwc(&p.out_map[l], d->out, N, g.out_w, g.out_h, d->n_img, N, (int64_t)g.out_w * N,
                        (int64_t)g.out_h * g.out_w * N);
       if (!rc && gdn && !bwd) rc = encode_nhwc(&p.sc_map[l], d->out_scale, N, g.out_w, g.out_h, d->n_img, N,
                                                 (int64_t)g.out_w * N, (int64_t)g.out_h * g.out_w * N);
+      if (!rc && bwd) rc = encode_nhwc(&p.sc_map[l], d->sc_prev, N, g.out_w, g.out_h, d->n_img, N,
+                                       (int64_t)g.out_w * N, (int64_t)g.out_h * g.out_w * N);
+      if (!rc && bwd) rc = encode_nhwc(&p.yprev_map[l], d->y_prev, N, g.out_w, g.out_h, d->n_img, N,
+                                       (int64_t)g.out_w * N, (int64_t)g.out_h * g.out_w * N);
     }
     if (rc) return rc;
-    if (!(gdn && !bwd)) p.sc_map[l] = p.out_map[l];
+    if (!gdn) p.sc_map[l] = p.out_map[l];
+    if (!bwd) p.yprev_map[l] = p.out_map[l];
   }
   p.k_chunks = mode == kModeRgbIn ? 1 : K / 32;
   p.n_ch = N; p.n_chunks = N / 32; p.n_total = N;
