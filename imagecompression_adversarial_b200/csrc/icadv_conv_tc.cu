@@ -62,6 +62,8 @@ struct TcParams {
   int tiles_x, tiles_y, tile_step_y, tile_step_x, tile_off;
   int epi, act, acc_from_in, round_out, a_rank5;
   int num_stages, tmem_cols, ld_bufs;       // num_stages: weight ring (n_ch * 128 bytes per stage)
+  int ld_alias;                             // BWD: the saved-chunk staging pair is the LAST 32 KB of the weight ring (idle
+                                            // once the main loop is done); gamma then cycles through stages [0, S-2)
   int t_h, t_w, o_h, o_w, o_s, o_a, o_b;    // tile-space extent; output geometry: pixel (o_s*i + o_a, o_s*j + o_b)
   const float* yprev; const float* scprev; const float* xin;   // epilogue operands read with plain loads
   int c2i_in_h, c2i_in_w, c2i_nch;         // col2im: input extent, real output channels
@@ -135,8 +137,9 @@ __global__ void __launch_bounds__(kThreads, 2) conv_tc_kernel(const __grid_const
   const int P = p.num_patch, S = p.num_stages;
   const uint32_t b_bytes = static_cast<uint32_t>(p.n_ch) * 128u;
   uint8_t* wring = smem + P * p.patch_bytes;               // weight ring behind the patch ring
-  uint8_t* ld_buf = wring + S * b_bytes;                   // BWD: y_prev / sc_prev chunk staging (2 x 16 KB)
-  uint64_t* full = reinterpret_cast<uint64_t*>(ld_buf + p.ld_bufs * kABytes);
+  uint8_t* ring_end = wring + S * b_bytes;
+  uint8_t* ld_buf = p.ld_alias ? ring_end - 2 * kABytes : ring_end;   // BWD: y_prev / sc_prev chunk staging (2 x 16 KB)
+  uint64_t* full = reinterpret_cast<uint64_t*>(ring_end + p.ld_bufs * kABytes);
   uint64_t* empty = full + kMaxStages;
   uint64_t* pfull = empty + kMaxStages;      // [kMaxPatch]
   uint64_t* pempty = pfull + kMaxPatch;      // [kMaxPatch]
@@ -233,6 +236,19 @@ __global__ void __launch_bounds__(kThreads, 2) conv_tc_kernel(const __grid_const
         long long* q = p.dbg + ((int64_t)blockIdx.y * gridDim.x + blockIdx.x) * 32;
         q[13] = q[0] + t_wait_e; q[14] = q[0] + (clock64() - t_prod0);   // producer: blocked on empty / whole main loop
       }
+      if (p.ld_alias) {
+        // gamma chunks cycle through stages [0, S-2) only; slot j has been used ceil((main_kb - j) / S) times so far
+        const int Sg = S - 2;
+        for (int c = 0; c < gdn_kb; ++c) {
+          const int j = c % Sg;
+          const int n = (main_kb > j ? (main_kb - j + S - 1) / S : 0) + c / Sg;   // use index of slot j
+          mbar_wait(&empty[j], ((n & 1) ^ 1));
+          if (elect_one_sync()) {
+            mbar_arrive_expect_tx(&full[j], b_bytes);
+            tma_load_2d(wring + j * b_bytes, &p.g_map, &full[j], c * 32, 0);
+          }
+        }
+      } else
       for (int c = 0; c < gdn_kb; ++c) {
         mbar_wait(&empty[s], s_par);
         if (elect_one_sync()) {
@@ -292,6 +308,13 @@ __global__ void __launch_bounds__(kThreads, 2) conv_tc_kernel(const __grid_const
         q[11] = q[0] + t_wait_w; q[12] = q[0] + t_wait_p;   // stored relative to slot 0 like the stamps
       }
       for (int c = 0; c < gdn_kb; ++c) {
+        if (p.ld_alias) {   // gamma ring = stages [0, S-2): recompute the slot and its use parity (see the producer)
+          const int Sg = S - 2;
+          s = c % Sg;
+          const int n = (main_kb > s ? (main_kb - s + S - 1) / S : 0) + c / Sg;
+          s_par = static_cast<uint32_t>(n & 1);
+          w_lo = w_lo0 + s * w_step;
+        }
         const uint64_t ad = (static_cast<uint64_t>(hi_dense) << 32) | p_lo;
         const uint64_t bd = (static_cast<uint64_t>(hi_dense) << 32) | w_lo;
         mbar_wait(&full[s], s_par);
@@ -305,7 +328,7 @@ __global__ void __launch_bounds__(kThreads, 2) conv_tc_kernel(const __grid_const
           tc_commit(&empty[s]);
           tc_commit(&pempty[ps]);
         }
-        if (++s == S) { s = 0; s_par ^= 1; w_lo = w_lo0; } else { w_lo += w_step; }
+        if (!p.ld_alias) { if (++s == S) { s = 0; s_par ^= 1; w_lo = w_lo0; } else { w_lo += w_step; } }
         if (++ps == P) { ps = 0; p_par ^= 1; p_lo = p_lo0; } else { p_lo += p_step; }
       }
       if (gdn_kb > 0 && elect_one_sync()) tc_commit(&acc_full[1]);
@@ -405,7 +428,7 @@ __global__ void __launch_bounds__(kThreads, 2) conv_tc_kernel(const __grid_const
                      : "memory");
         if (p.dbg_flags & 1) { cur_chunk = next; } else if (next >= 0) fetch(next);
       };
-      if constexpr (bwd) { if (!(p.dbg_flags & 1)) fetch(0); }   // overlaps the main loop
+      if constexpr (bwd) { if (!(p.dbg_flags & 1) && !p.ld_alias) fetch(0); }   // overlaps the main loop
 
       auto load_acc1 = [&](int c, float* v) {
         if constexpr (FROM_IN) {
@@ -454,6 +477,7 @@ __global__ void __launch_bounds__(kThreads, 2) conv_tc_kernel(const __grid_const
         mbar_wait(&acc_full[0], 0);
         tc_fence_after_sync();
       }
+      if constexpr (bwd) { if (!(p.dbg_flags & 1) && p.ld_alias) fetch(0); }   // the weight stages it lands in are idle now
       if (leader) TC_STAMP(5);
 
       if constexpr (!gdn) {
@@ -1581,8 +1605,13 @@ int icadv_conv_plan_create(const icadv_conv_desc* d, icadv_conv_plan** out_plan)
     //      (their prologue / epilogue overlap each other's main loop).
     p.patch_bytes = (max_patch + 1023) & ~1023;
     const int wbytes = N * 128;
-    p.ld_bufs = bwd ? 2 : 0;
-    const int fixed = 1024 + kBarBlock + 2 * N * 4 + p.ld_bufs * kABytes;
+    // long backward main loops: four weight stages matter more than prefetching the first saved chunk, so the staging
+    // pair aliases the tail of the weight ring (measured: g_s.4 dgrad main loop 0.47 -> 0.33 us per K-block)
+    const bool want_alias = bwd && !d->acc_from_in && mode == kModeGeneric && N * 128 >= kABytes &&
+                            K / 32 * g.n_taps[l] >= 16 && getenv("ICADV_TC_NO_ALIAS") == nullptr;
+    p.ld_alias = want_alias ? 1 : 0;
+    p.ld_bufs = bwd && !want_alias ? 2 : 0;
+    int fixed = 1024 + kBarBlock + 2 * N * 4 + p.ld_bufs * kABytes;
     // bytes of ring the epilogue aliases for its store staging (16 KB regions) / the col2im scatter tile
     const int need_ring = mode == kModeCol2im ? 128 * kZStride * 4 : ((gdn && !bwd) ? 4 : 2) * kABytes;
     // a short main loop (the RGB end layers: 4-5 K-blocks) is one DRAM round trip if every patch is in flight at once
@@ -1607,7 +1636,13 @@ int icadv_conv_plan_create(const icadv_conv_desc* d, icadv_conv_plan** out_plan)
     };
     const bool want_two = (gdn ? 2 * N : N) <= 256 && getenv("ICADV_TC_ONE_CTA") == nullptr;
     const int env_s = getenv("ICADV_TC_S") ? atoi(getenv("ICADV_TC_S")) : 0;   // developer override: weight stages
-    if (!(want_two && fit(kSmemTwoCta, 2, env_s > 0 ? env_s : 4)) && !fit(kSmemLimit, 3, env_s > 0 ? env_s : kMaxStages)) {
+    bool ok = (want_two && fit(kSmemTwoCta, 2, env_s > 0 ? env_s : 4)) || fit(kSmemLimit, 3, env_s > 0 ? env_s : kMaxStages);
+    if (ok && p.ld_alias && p.num_stages < 4) {   // not enough stages to give two away: separate staging pair instead
+      p.ld_alias = 0; p.ld_bufs = 2;
+      fixed += 2 * kABytes;
+      ok = (want_two && fit(kSmemTwoCta, 2, env_s > 0 ? env_s : 4)) || fit(kSmemLimit, 3, env_s > 0 ? env_s : kMaxStages);
+    }
+    if (!ok) {
       delete plan; set_error("conv_tc: not enough shared memory for n_ch=%d", N); return ICADV_EINVAL;
     }
     int cols = gdn ? 2 * N : N, pow2 = 32;
