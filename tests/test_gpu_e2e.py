@@ -177,6 +177,8 @@ def test_msssim_gradient_matches_oracle_autograd(dev):
 
 @pytest.mark.parametrize("model,quality,hw,n,steps,metric", [("hyper", 3, (192, 256), 2, 12, "L2"),
                                                              ("factorized", 1, (192, 192), 1, 9, "L2"),
+                                                             ("hyper", 6, (192, 256), 1, 6, "L2"),      # N=192, M=320
+                                                             ("context", 5, (192, 192), 1, 6, "L2"),
                                                              ("hyper", 3, (192, 256), 1, 6, "ms-ssim")])
 def test_attack_trajectory_matches_oracle(dev, model, quality, hw, n, steps, metric):
     """Fused loop vs the oracle's attack_ per image (N=1 semantics): per-step (branch, loss_i, loss)."""
@@ -208,7 +210,9 @@ def test_attack_trajectory_matches_oracle(dev, model, quality, hw, n, steps, met
         if first_div is None:
             # same branch sequence: final metrics within tolerance
             assert abs(psnr(im_adv[i:i + 1], x[i:i + 1]) - psnr(o[0], x[i:i + 1])) < 0.05
-            assert abs(psnr(out_adv[i:i + 1], out_s[i:i + 1]) - psnr(o[1], o[2])) < 0.05
+            # context model: one latent rounding the other way moves the means / x_hat around it (see
+            # test_eval_forward_matches_oracle), so its reconstruction PSNR gets the 0.1 dB bound used there
+            assert abs(psnr(out_adv[i:i + 1], out_s[i:i + 1]) - psnr(o[1], o[2])) < (0.1 if model == "context" else 0.05)
     if n == 1:
         assert abs(float(bpp_ori) - float(o[3])) < max(1e-3, 2e-3 * float(o[3]))
         assert abs(float(bpp) - float(o[4])) < max(1e-3, 5e-3 * float(o[4]))
