@@ -469,3 +469,38 @@ def test_persistent_variant_equals_per_tile_kernel(dev, persist_env, case):
         assert float(a.abs().max()) > 0
         assert float(a[1].abs().max()) == 0 and float(b[1].abs().max()) == 0     # images not in the active list stay untouched
         torch.testing.assert_close(b, a, rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("epi", ["igdn_fwd", "gdn_bwd", "col2im"])
+def test_persistent_kernel_many_items_per_cta(dev, persist_env, epi):
+    """Transposed convs at a size where every persistent CTA walks ~10-20 work items (ring phases, TMEM buffer hand-offs,
+    in-place saved-chunk staging all wrap many times): persistent vs per-tile kernel, and run-to-run bit-identity."""
+    from imagecompression_adversarial_b200 import _lib as L
+    from imagecompression_adversarial_b200 import ops
+    C, n, h, w = 128, 6, 72, 104
+    gen = lambda seed: torch.Generator(device=dev).manual_seed(seed)
+    gamma, beta = _gdn_params(C, dev, gen(3))
+    x = torch.randn(n, h, w, C, device=dev, generator=gen(1))
+    res = {}
+    for level in (0, 2, 2):
+        persist_env(level)
+        if epi == "col2im":
+            wp = ops.pack_weight(torch.randn(C, 3, 5, 5, device=dev, generator=gen(2)) / 30, 2)
+            out = torch.zeros(n, 2 * h, 2 * w, 3, device=dev)
+            ops.conv(x, wp, torch.zeros(3, device=dev), form=L.FORM_TCONV, ksize=5, stride=2, n_ch=3, out=out, path="tc")
+        elif epi == "igdn_fwd":
+            wp = ops.pack_weight(torch.randn(C, C, 5, 5, device=dev, generator=gen(2)) / 28, 2)
+            out = torch.zeros(n, 2 * h, 2 * w, C, device=dev); sc = torch.zeros_like(out)
+            ops.conv(x, wp, beta, form=L.FORM_TCONV, ksize=5, stride=2, n_ch=C, epi=L.EPI_IGDN_FWD, gmat=gamma, beta=beta,
+                     out=out, out_scale=sc, path="tc")
+            out = torch.cat((out, sc))
+        else:
+            wp = ops.pack_weight(torch.randn(C, C, 5, 5, device=dev, generator=gen(2)) / 56, 1)
+            yp = torch.randn(n, 2 * h, 2 * w, C, device=dev, generator=gen(4))
+            sp = 0.5 + torch.rand(n, 2 * h, 2 * w, C, device=dev, generator=gen(5))
+            out = torch.zeros(n, 2 * h, 2 * w, C, device=dev)
+            ops.conv(x, wp, None, form=L.FORM_TCONV, ksize=5, stride=2, n_ch=C, epi=L.EPI_GDN_BWD,
+                     gmat=gamma.t().contiguous(), y_prev=yp, sc_prev=sp, out=out, path="tc")
+        res.setdefault(level, []).append(out)
+    torch.testing.assert_close(res[2][0], res[0][0], rtol=1e-5, atol=1e-6)
+    assert torch.equal(res[2][0], res[2][1])
