@@ -1204,7 +1204,7 @@ static int encode_plane(CUtensorMap* m, const float* base, int C, int W, int H, 
 }
 
 // padded RGB0 input of the first-layer form: [n_img][in_h + 4][in_w + 8][4] floats, pixel (h, w) at (h+2, w+2)
-static int encode_pad4(CUtensorMap* m, const float* base, int W, int H, int N) {
+static int encode_pad4(CUtensorMap* m, const float* base, int W, int H, int N, int box_h = kTH) {
   EncodeTiledFn enc = get_encode();
   if (!enc) { set_error("cuTensorMapEncodeTiled not available"); return ICADV_ECUDA; }
   const int64_t Wp = W + 8, Hp = H + 4;
@@ -1212,7 +1212,7 @@ static int encode_pad4(CUtensorMap* m, const float* base, int W, int H, int N) {
   //       | row parity | image
   cuuint64_t dims[5] = {32, (cuuint64_t)(W / 2), (cuuint64_t)(Hp / 2), 2, (cuuint64_t)N};
   cuuint64_t strides[4] = {32, (cuuint64_t)(2 * Wp * 16), (cuuint64_t)(Wp * 16), (cuuint64_t)(Hp * Wp * 16)};
-  cuuint32_t box[5] = {32, (cuuint32_t)kTW, (cuuint32_t)kTH, 1, 1};
+  cuuint32_t box[5] = {32, (cuuint32_t)kTW, (cuuint32_t)box_h, 1, 1};
   cuuint32_t es[5] = {1, 1, 1, 1, 1};
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, const_cast<float*>(base), dims, strides, box, es,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -1287,10 +1287,11 @@ static int tc_mode(const icadv_conv_desc* d, bool report) {
 //      kernel, < 0 on error.
 static int build_persistent(const icadv_conv_desc* d, int mode, const Geometry& g, icadv_conv_plan* plan) {
   // ICADV_TC_PERSIST: 0 = never, 2 = every eligible shape (developer), unset / 1 = where it measured faster on B200
-  // (profiles/r1_step_breakdown_v5_*.json): stride-2 transposed convs with a forward epilogue (four short parity
-  // classes in one launch, epilogue overlapped: 3.96 -> 3.12 ms on g_s.4) and linear epilogues.  A single MMA stream
-  // per SM runs at ~2x the tensor floor, so long stride-2 convs and the backward epilogues (plain-load reads of the
-  // saved y / scale) stay on the two-CTA-per-SM kernel.
+  // (profiles/r1_step_breakdown_v*.json): stride-2 transposed convs (four short parity classes in one launch, epilogue
+  // overlapped: forward 3.96 -> 3.45 ms on g_s.4, backward 5.07 -> 4.3 ms on the g_a.2 dgrad), linear epilogues, the
+  // col2im end layers (2.1 -> 1.27 ms) and the forward RGB first layer (2.12 -> 1.68 ms).  A single MMA stream per SM
+  // runs at ~2x the tensor floor for N = 128, so long stride-2 convs (forward and backward) and the RGB dgrad layer
+  // stay on the two-CTA-per-SM kernel.
   const char* env = getenv("ICADV_TC_PERSIST");
   const int level = env != nullptr ? atoi(env) : 1;
   if (level == 0) return 0;
@@ -1301,7 +1302,7 @@ static int build_persistent(const icadv_conv_desc* d, int mode, const Geometry& 
   const int N = c2i ? 96 : d->n_ch, K = d->k_ch, s = d->stride;   // col2im: Z has 25 * n_ch <= 96 columns
   if (N > 256 || (gdn && N > 128)) return 0;            // 2 TMEM buffers x [acc N | norm N] must fit 512 columns
   const bool tconv2 = !c2i && d->form == ICADV_FORM_TCONV && s == 2;
-  if (level == 1 && !(tconv2 || (!gdn && mode == kModeGeneric) || c2i)) return 0;
+  if (level == 1 && !(tconv2 || (!gdn && mode == kModeGeneric) || c2i || (mode == kModeRgbIn && !bwd))) return 0;
   TcpParams& p = plan->pp;
   memset(&p, 0, sizeof(p));
   p.n_class = tconv2 ? g.n_launch : 1;
@@ -1486,9 +1487,11 @@ int icadv_conv_plan_create(const icadv_conv_desc* d, icadv_conv_plan** out_plan)
     Tap taps[kMaxTaps];
     int n_taps = 0;
     if (mode == kModeRgbIn) {
-      // one K-block per kernel row kh: padded input row 2*oh + kh -> (parity kh & 1, half-row oh + (kh >> 1))
+      // one K-block per kernel row kh: padded input row 2*oh + kh -> (parity kh & 1, half-row oh + (kh >> 1)).
+      // Kernel rows of the same parity read the same half-rows shifted by kh >> 1: ONE halo patch per row parity
+      // (2 boxes of 18 half-rows per tile instead of 5 boxes of 16)
       for (int kh = 0; kh < 5; ++kh) {
-        Tap t; t.plane = (int16_t)kh; t.dy = (int16_t)(kh >> 1); t.dx = 0; t.wtap = (int16_t)kh;
+        Tap t; t.plane = (int16_t)(kh & 1); t.dy = (int16_t)(kh >> 1); t.dx = 0; t.wtap = (int16_t)kh;
         taps[n_taps++] = t;
       }
     } else if (mode == kModeCol2im) {
@@ -1536,7 +1539,11 @@ int icadv_conv_plan_create(const icadv_conv_desc* d, icadv_conv_plan** out_plan)
     }
     // ---- input maps: one per group, box = tile + halo
     if (mode == kModeRgbIn) {
-      rc = encode_pad4(&p.a_map[0], d->in, d->in_w, d->in_h, d->n_img);
+      int ph_max = kTH;   // both row parities go through one 5-D map: a uniform box (the taller halo)
+      for (int gi = 0; gi < p.num_groups; ++gi) ph_max = box_h[gi] > ph_max ? box_h[gi] : ph_max;
+      for (int gi = 0; gi < p.num_groups; ++gi) p.groups[gi].bytes = kTW * ph_max * 128;
+      max_patch = kTW * ph_max * 128 > max_patch ? kTW * ph_max * 128 : max_patch;
+      rc = encode_pad4(&p.a_map[0], d->in, d->in_w, d->in_h, d->n_img, ph_max);
       if (rc) { delete plan; return rc; }
       p.a_map[1] = p.a_map[2] = p.a_map[3] = p.a_map[0];
       p.a_rank5 = 1;
