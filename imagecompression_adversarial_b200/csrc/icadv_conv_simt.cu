@@ -213,22 +213,33 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, float* __
   }
 }
 
-// dbias[n] = sum over all pixels of gout[px][n]; one block per 32 channels, fixed-order tree.
-__global__ void __launch_bounds__(256) bias_grad_kernel(const float* __restrict__ gout, float* __restrict__ dbias,
+// dbias[n] = sum over all pixels of gout[px][n].  Two stages, both fixed-order: block (x = 32 channels, y = pixel split)
+// writes partial[y][n]; the second kernel adds the splits.
+constexpr int kBiasSplits = 128;
+__global__ void __launch_bounds__(256) bias_grad_kernel(const float* __restrict__ gout, float* __restrict__ partial,
                                                         int64_t npx, int N) {
   __shared__ float red[8][33];
   const int tx = threadIdx.x & 31, tyy = threadIdx.x >> 5;
   const int n = blockIdx.x * 32 + tx;
+  const int64_t per = (npx + gridDim.y - 1) / gridDim.y;
+  const int64_t m0 = (int64_t)blockIdx.y * per, m1 = m0 + per < npx ? m0 + per : npx;
   float s = 0.f;
   if (n < N)
-    for (int64_t m = tyy; m < npx; m += 8) s += __ldg(gout + m * N + n);
+    for (int64_t m = m0 + tyy; m < m1; m += 8) s += __ldg(gout + m * N + n);
   red[tyy][tx] = s;
   __syncthreads();
   if (tyy == 0 && n < N) {
     float a = 0.f;
     for (int r = 0; r < 8; ++r) a += red[r][tx];
-    dbias[n] = a;
+    partial[(int64_t)blockIdx.y * N + n] = a;
   }
+}
+__global__ void bias_grad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dbias, int N, int splits) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  float a = 0.f;
+  for (int y = 0; y < splits; ++y) a += partial[(int64_t)y * N + n];
+  dbias[n] = a;
 }
 
 static int fill_params(const icadv_conv_desc* d, const Geometry& g, int l, SimtParams* p) {
@@ -326,8 +337,13 @@ int icadv_conv_wgrad(const icadv_conv_desc* d, const float* gout, float* dwpack,
   }
   if (dbias != nullptr) {
     const int64_t npx = (int64_t)d->n_img * g.out_h * g.out_w;
-    bias_grad_kernel<<<(d->n_ch + 31) / 32, 256, 0, s>>>(gout, dbias, npx, d->n_ch);
+    float* partial = nullptr;
+    ICADV_CUDA_TRY(cudaMallocAsync(&partial, (size_t)kBiasSplits * d->n_ch * sizeof(float), s));
+    bias_grad_kernel<<<dim3((d->n_ch + 31) / 32, kBiasSplits), 256, 0, s>>>(gout, partial, npx, d->n_ch);
     ICADV_CUDA_TRY(cudaGetLastError());
+    bias_grad_reduce_kernel<<<(d->n_ch + 127) / 128, 128, 0, s>>>(partial, dbias, d->n_ch, kBiasSplits);
+    ICADV_CUDA_TRY(cudaGetLastError());
+    ICADV_CUDA_TRY(cudaFreeAsync(partial, s));
   }
   return ICADV_OK;
 }

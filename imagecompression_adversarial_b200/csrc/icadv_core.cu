@@ -232,14 +232,20 @@ const char* icadv_last_error(void) { return g_err; }
 int icadv_version(void) { return 100; }
 
 int icadv_check_device(void) {
+  // cudaGetDeviceProperties costs milliseconds and this is called from every plan creation: cache the verdict per
+  // device ordinal (0 = unknown, 1 = sm_100, 2 = other); benign race: every thread computes the same value
+  static int verdict[64] = {0};
   int dev = 0;
   ICADV_CUDA_TRY(cudaGetDevice(&dev));
-  cudaDeviceProp prop;
-  ICADV_CUDA_TRY(cudaGetDeviceProperties(&prop, dev));
-  if (prop.major != 10) {
-    set_error("device %s is sm_%d%d; this library is sm_100a only (no fallback)", prop.name, prop.major, prop.minor);
+  if (dev >= 0 && dev < 64 && verdict[dev] == 1) return ICADV_OK;
+  int major = 0, minor = 0;
+  ICADV_CUDA_TRY(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+  ICADV_CUDA_TRY(cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, dev));
+  if (major != 10) {
+    set_error("device %d is sm_%d%d; this library is sm_100a only (no fallback)", dev, major, minor);
     return ICADV_EARCH;
   }
+  if (dev >= 0 && dev < 64) verdict[dev] = 1;
   return ICADV_OK;
 }
 
