@@ -48,3 +48,45 @@ def test_reference_cli_runs_unmodified(tmp_path, fused):
     assert len(nums) >= 4
     bpp_ori, bpp, vi = float(nums[0]), float(nums[1]), float(nums[2])
     assert 0.0 < bpp_ori < 64.0 and 0.0 < bpp < 64.0 and vi > 0.0   # the attack amplifies the distortion
+
+
+def _reference_module(name):
+    """Import a module of the reference copy with the launcher's stand-ins for its missing third-party imports."""
+    import importlib
+    from imagecompression_adversarial_b200 import launch
+    launch.install_shims()
+    if REF not in sys.path:
+        sys.path.insert(0, REF)
+    return importlib.import_module(name)
+
+
+def test_reference_self_ensemble_defence_on_the_operator_surface():
+    """the reference's geometric self-ensemble (self_ensemble.py:34-131: 8 flips / rot90,
+    two batched net(x) calls, best-MSE pick), UNMODIFIED, on this package's codec vs on the oracle codec."""
+    if not os.path.exists(os.path.join(REF, "self_ensemble.py")):
+        pytest.skip("no reference copy under baseline/_ref/reference")
+    import torch
+    from imagecompression_adversarial_b200 import models as pm
+    from oracle import models as om
+    from oracle.attack import synthetic_image
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    se = _reference_module("self_ensemble")
+    dev = torch.device("cuda:0")
+    onet = om.init_model("hyper", 3, seed=0).to(dev).eval()
+    pnet = pm.init_model("hyper", 3, "mse", pretrained=False).to(dev).eval()
+    pnet.load_state_dict(onet.state_dict())
+    x = synthetic_image(3, 128, 192).to(dev)            # non-square: the rot90 members have the transposed shape
+    with torch.no_grad():
+        o_mse, o_x, o_xhat, o_lik = se.self_ensemble(onet, x)
+        p_mse, p_x, p_xhat, p_lik = se.self_ensemble(pnet, x)
+    assert abs(float(p_mse) - float(o_mse)) <= 2e-3 * float(o_mse)
+    assert torch.equal(p_x, o_x)                          # same ensemble member picked
+    assert p_xhat.shape == o_xhat.shape == x.shape
+    # eval mode rounds the latent: a TF32-vs-fp32 near-tie flips isolated symbols, so compare reconstruction quality
+    import math
+    psnr = lambda a: -10.0 * math.log10(float(torch.mean((a - x) ** 2)))
+    assert abs(psnr(p_xhat) - psnr(o_xhat)) < 0.05
+    assert set(p_lik) == set(o_lik) == {"y", "z"}
+    for k in o_lik:
+        assert p_lik[k].shape == o_lik[k].shape
