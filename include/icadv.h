@@ -93,9 +93,12 @@ typedef struct {
 /* output spatial size implied by a descriptor */
 int icadv_conv_out_hw(const icadv_conv_desc* d, int* out_h, int* out_w);
 
-/* tcgen05/TMEM/TMA implicit-GEMM path.  Requires k_ch % 32 == 0, n_ch % 32 == 0, n_ch <= 256
- * (<= 192 for the GDN epilogues unless n_ch == 256 fits 512 TMEM columns).  A plan caches the
- * TMA tensor maps for fixed buffers; launching is stream-ordered. */
+/* tcgen05/TMEM/TMA implicit-GEMM path.  Requires k_ch % 32 == 0, n_ch % 32 == 0 (n_ch > 256 is tiled over N for the
+ * linear epilogue; GDN epilogues need 2 * n_ch <= 512 TMEM columns), or one of the two RGB end-layer forms (in_pad4;
+ * transposed conv with n_ch <= 4).  A plan caches the TMA tensor maps for fixed buffers; launching is stream-ordered and
+ * graph-capturable.  Two kernels sit behind a plan: a per-tile kernel (two CTAs per SM) and a persistent kernel (one CTA
+ * per SM, TMEM double buffer, all parity classes of a transposed conv in one launch); the plan picks per shape
+ * (environment: ICADV_TC_PERSIST = 0 never / 1 default / 2 wherever eligible -- results agree to fp32 round-off). */
 typedef struct icadv_conv_plan icadv_conv_plan;
 int icadv_conv_plan_create(const icadv_conv_desc* d, icadv_conv_plan** plan);
 int icadv_conv_plan_launch(const icadv_conv_plan* plan, icadv_stream_t stream);
