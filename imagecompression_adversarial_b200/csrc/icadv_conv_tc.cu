@@ -620,6 +620,7 @@ struct TcpParams {
   const float* yprev; const float* scprev;
   const float* bias; const float* beta;
   const int* active; const int* n_active;
+  long long* dbg;   // developer profiling: 16 cycle counters per CTA (see scripts/persistent_timeline.py)
 };
 
 struct TcpItem { int img, i0, j0, cls; };
@@ -779,9 +780,13 @@ __global__ void __launch_bounds__(kPThreads, 1) conv_tcp_kernel(const __grid_con
         }
       };
       int b = 0;
+      const bool prof = p.dbg != nullptr;
+      long long c_ring = 0, c_free = 0, n_items = 0;
+      const long long c_start = prof ? clock64() : 0;
       for (int item = blockIdx.x; item < total; item += gridDim.x, b ^= 1) {
         const TcpItem it = tcp_decode(p, item);
         const TcpClass cl = p.cls[it.cls];
+        ++n_items;
         // the epilogue of the item that last used TMEM buffer b must have finished reading it
         if (!__shfl_sync(0xffffffffu, (int)mbar_test_wait(&tmem_free[b], free_par[b]), 0)) {
           const long long t0 = clock64();
@@ -789,6 +794,7 @@ __global__ void __launch_bounds__(kPThreads, 1) conv_tcp_kernel(const __grid_con
             if (gdn) service();
             if (clock64() - t0 > 4000000000LL) __trap();
           }
+          c_free += clock64() - t0;
         }
         free_par[b] ^= 1;
         tc_fence_after_sync();
@@ -799,12 +805,14 @@ __global__ void __launch_bounds__(kPThreads, 1) conv_tcp_kernel(const __grid_con
             const Group gr = p.groups[g];
             const uint32_t a_hi = (static_cast<uint32_t>(gr.sbo_bytes) >> 4) | (1u << 14) | (2u << 29);
             uint32_t aoff = static_cast<uint32_t>(p.tap_aoff[gr.tap_begin]) >> 4;
-            mbar_wait(&pfull[ps], p_par);
+            if (prof) { const long long t0 = clock64(); mbar_wait(&pfull[ps], p_par); c_ring += clock64() - t0; }
+            else mbar_wait(&pfull[ps], p_par);
             for (int t = gr.tap_begin; t < gr.tap_end; ++t) {
               const uint64_t ad = (static_cast<uint64_t>(a_hi) << 32) | (p_lo + aoff);
               const uint64_t bd = (static_cast<uint64_t>(hi_dense) << 32) | w_lo;
               aoff = static_cast<uint32_t>(p.tap_aoff[t + 1 < gr.tap_end ? t + 1 : t]) >> 4;
-              mbar_wait(&wfull[s], s_par);
+              if (prof) { const long long t0 = clock64(); mbar_wait(&wfull[s], s_par); c_ring += clock64() - t0; }
+              else mbar_wait(&wfull[s], s_par);
               tc_fence_after_sync();
               if (elect_one_sync()) {
                 tc_mma_tf32(d, ad, bd, idesc, acc);
@@ -824,12 +832,17 @@ __global__ void __launch_bounds__(kPThreads, 1) conv_tcp_kernel(const __grid_con
         if (elect_one_sync()) tc_commit(&acc_full[b]);
         if (gdn) pend[b] = 0;
       }
+      const long long c_main_end = prof ? clock64() : 0;
       if (gdn) {
         const long long t0 = clock64();
         while (pend[0] >= 0 || pend[1] >= 0) {
           service();
           if (clock64() - t0 > 4000000000LL) __trap();
         }
+      }
+      if (prof && lane == 0) {
+        long long* q = p.dbg + (int64_t)blockIdx.x * 16;
+        q[0] = c_main_end - c_start; q[1] = c_ring; q[2] = c_free; q[7] = n_items; q[8] = clock64() - c_start;
       }
     }
     __syncwarp();
@@ -872,9 +885,13 @@ __global__ void __launch_bounds__(kPThreads, 1) conv_tcp_kernel(const __grid_con
       const bool px_ok = gi < p.t_h && gj < p.t_w;
       const int64_t pix = (((int64_t)it.img * p.o_h + p.o_s * gi + o_a) * p.o_w + p.o_s * gj + o_b) * p.n_ch;
       (void)px_ok; (void)pix;
+      const bool eprof = p.dbg != nullptr && leader;
+      const long long e0 = eprof ? clock64() : 0;
       mbar_wait(&acc_full[grp], acc_par);
       acc_par ^= 1;
       tc_fence_after_sync();
+      const long long e1 = eprof ? clock64() : 0;
+      long long e2 = e1, e3 = e1;
 
       if constexpr (EPI == kEpiCol2im) {
         // Z[128 px][taps * nch] -> this group's shared-memory tile, TMEM handed back at once, then the transposed-conv
@@ -932,15 +949,16 @@ __global__ void __launch_bounds__(kPThreads, 1) conv_tcp_kernel(const __grid_con
         }
       };
       int stores = 0;
-      // double-buffered store of one output chunk through slot (stores & 1)
-      auto store_one = [&](int c, const float* o) {
+      // double-buffered store of one output chunk through slot (stores & 1): a slot is rewritten once the store issued
+      // from it two stores ago has finished reading (each store is its own bulk group)
+      auto store_one = [&](int c, const float* o, const CUtensorMap* map, bool round) {
         uint8_t* buf = gbuf + (stores & 1) * kABytes;
         if (stores >= 2) {
           if (leader) tma_store_wait_read1();
           __syncwarp();
           named_bar_sync(bar_id, 128);
         }
-        if (p.round_out) {
+        if (round) {
           float r[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) r[j] = round_tf32(o[j]);
@@ -950,7 +968,7 @@ __global__ void __launch_bounds__(kPThreads, 1) conv_tcp_kernel(const __grid_con
         }
         fence_proxy_async_smem();
         named_bar_sync(bar_id, 128);
-        if (leader) { tma_store_4d(&p.out_map[it.cls], buf, c * 32, it.j0, it.i0, it.img); tma_store_commit(); }
+        if (leader) { tma_store_4d(map, buf, c * 32, it.j0, it.i0, it.img); tma_store_commit(); }
         __syncwarp();
         ++stores;
       };
@@ -969,7 +987,7 @@ __global__ void __launch_bounds__(kPThreads, 1) conv_tcp_kernel(const __grid_con
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = fabsf(v[j]);
           }
-          store_one(c, v);
+          store_one(c, v, &p.out_map[it.cls], p.round_out != 0);
         }
       } else {
         // ---- pass 1: A operand of the normalisation GEMM, chunk c -> slot c & 1 ----
@@ -1012,9 +1030,11 @@ __global__ void __launch_bounds__(kPThreads, 1) conv_tcp_kernel(const __grid_con
           mbar_arrive(&a2_ready[grp * 2 + k]);
         }
         // ---- pass 2: normalise ----
+        if (eprof) e2 = clock64();
         mbar_wait(&norm_full[grp], norm_par);
         norm_par ^= 1;
         tc_fence_after_sync();
+        if (eprof) e3 = clock64();
         if constexpr (bwd) fetch(it, 0);   // every normalisation MMA has completed: the pair is free again
         for (int c = 0; c < nC; ++c) {
           float v[32], w[32];
@@ -1035,29 +1055,9 @@ __global__ void __launch_bounds__(kPThreads, 1) conv_tcp_kernel(const __grid_con
                 v[4 * j + t] *= sc[4 * j + t];
               }
             }
-            // both outputs of the chunk fill the two slots: single-buffered per chunk
-            if (c > 0) {
-              if (leader) tma_store_wait_read0();
-              __syncwarp();
-              named_bar_sync(bar_id, 128);
-            }
-            if (p.round_out) {
-              float r[32];
-#pragma unroll
-              for (int j = 0; j < 32; ++j) r[j] = round_tf32(v[j]);
-              write_row32(gbuf, row, r);
-            } else {
-              write_row32(gbuf, row, v);
-            }
-            write_row32(gbuf + kABytes, row, sc);
-            fence_proxy_async_smem();
-            named_bar_sync(bar_id, 128);
-            if (leader) {
-              tma_store_4d(&p.out_map[it.cls], gbuf, c * 32, it.j0, it.i0, it.img);
-              tma_store_4d(&p.sc_map[it.cls], gbuf + kABytes, c * 32, it.j0, it.i0, it.img);
-              tma_store_commit();
-            }
-            __syncwarp();
+            // the two outputs of the chunk leave through alternating slots, each store its own bulk group
+            store_one(c, v, &p.out_map[it.cls], p.round_out != 0);
+            store_one(c, sc, &p.sc_map[it.cls], false);
           } else {
             float yv[32], sv[32];
             mbar_wait(&ld_full[grp], ld_par);
@@ -1091,6 +1091,12 @@ __global__ void __launch_bounds__(kPThreads, 1) conv_tcp_kernel(const __grid_con
       __syncwarp();
       named_bar_sync(bar_id, 128);
       if (leader) mbar_arrive(&tmem_free[grp]);
+      if (eprof) {
+        long long* q = p.dbg + (int64_t)blockIdx.x * 16 + 9 + grp * 3;   // per group: wait acc, pass 1 (+ wait norm), pass 2
+        const long long e4 = clock64();
+        q[0] += e1 - e0; q[1] += e3 - e1; q[2] += e4 - e3;
+        if (grp == 0) p.dbg[(int64_t)blockIdx.x * 16 + 3] += e3 - e2;  // of which: waiting for the last normalisation MMA
+      }
       if constexpr (bwd) {   // request the first saved chunk of this group's next item while its main loop runs
         const int nxt = item + 2 * gridDim.x;
         if (nxt < total) fetch(tcp_decode(p, nxt), 0);
@@ -1704,6 +1710,7 @@ int icadv_conv_plan_num_launches(const icadv_conv_plan* plan) {
 int icadv_conv_plan_set_debug(icadv_conv_plan* plan, long long* dbg) {
   ICADV_REQUIRE(plan != nullptr, "null plan");
   plan->params[0].dbg = dbg;
+  plan->pp.dbg = dbg;   // persistent variant: 16 counters per CTA (148 CTAs)
   return ICADV_OK;
 }
 
