@@ -54,7 +54,7 @@ struct TcParams {
   CUtensorMap a_map[4];
   CUtensorMap w_map, g_map, out_map, sc_map, yprev_map, scprev_map;
   Group groups[kMaxGroups];
-  int32_t tap_aoff[kMaxTaps];   // byte offset of the tap's first row inside its patch
+  int32_t tap_aoff[kMaxTaps + 1];   // byte offset of the tap's first row inside its patch (one slack entry: read ahead)
   int16_t tap_wtap[kMaxTaps];   // row block of the packed weight
   int num_groups, num_taps, k_chunks, n_ch, n_chunks;   // n_ch = MMA N (one N-tile); n_chunks = n_ch / 32
   int num_patch, patch_bytes;               // patch ring: slots and bytes per slot (multiple of 1024)
@@ -261,7 +261,7 @@ __global__ void __launch_bounds__(kThreads, 2) conv_tc_kernel(const __grid_const
     __syncwarp();
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    {   // all 32 lanes run the loop (uniform state); one elected lane issues
+    if (elect_one_sync()) {   // ONE thread runs the whole role: no per-K-block reconvergence (see conv_tcp_kernel)
       const uint32_t idesc = umma_idesc_tf32(kTileM, p.n_ch);
       // shared-memory descriptors: hi word = SBO>>4 | version 1 (bit 14) | SWIZZLE_128B (bit 30); lo word = addr>>4 | LBO 1
       const uint32_t hi_dense = (1024u >> 4) | (1u << 14) | (2u << 29);
@@ -270,40 +270,49 @@ __global__ void __launch_bounds__(kThreads, 2) conv_tc_kernel(const __grid_const
       const uint32_t w_step = b_bytes >> 4, p_step = static_cast<uint32_t>(p.patch_bytes) >> 4;
       int s = 0, ps = 0;
       uint32_t s_par = 0, p_par = 0, w_lo = w_lo0, p_lo = p_lo0, acc = 0;
-      long long t_wait_w = 0, t_wait_p = 0;   // developer profiling: cycles blocked on the weight / patch rings
-      if (lane == 0) TC_STAMP(2);
+      long long t_wait_w = 0, t_wait_p = 0;   // developer profiling: cycles blocked on the weight / patch rings (slow paths)
+      bool w_ok = false;                      // early probe of full[s]
+      TC_STAMP(2);
       for (int kc = 0; kc < (FROM_IN ? 0 : p.k_chunks); ++kc) {
         for (int g = 0; g < p.num_groups; ++g) {
-          const Group gr = p.groups[g];
-          const uint32_t a_hi = (static_cast<uint32_t>(gr.sbo_bytes) >> 4) | (1u << 14) | (2u << 29);
-          uint32_t aoff = static_cast<uint32_t>(p.tap_aoff[gr.tap_begin]) >> 4;
-          if (p.dbg != nullptr) { const long long t0 = clock64(); mbar_wait(&pfull[ps], p_par); t_wait_p += clock64() - t0; }
-          else mbar_wait(&pfull[ps], p_par);
-          for (int t = gr.tap_begin; t < gr.tap_end; ++t) {
+          const uint32_t a_hi = (static_cast<uint32_t>(p.groups[g].sbo_bytes) >> 4) | (1u << 14) | (2u << 29);
+          const int t_end = p.groups[g].tap_end;
+          int t = p.groups[g].tap_begin;
+          uint32_t aoff = static_cast<uint32_t>(p.tap_aoff[t]) >> 4;
+          if (!mbar_test_wait(&pfull[ps], p_par)) {
+            const long long t0 = clock64();
+            mbar_wait(&pfull[ps], p_par);
+            t_wait_p += clock64() - t0;
+          }
+          for (; t < t_end; ++t) {
             // tap (dy, dx): same patch, start shifted by whole pixel rows; tile rows are patch_w * 128 bytes apart
             const uint64_t ad = (static_cast<uint64_t>(a_hi) << 32) | (p_lo + aoff);
             const uint64_t bd = (static_cast<uint64_t>(hi_dense) << 32) | w_lo;
-            aoff = static_cast<uint32_t>(p.tap_aoff[t + 1 < gr.tap_end ? t + 1 : t]) >> 4;   // next tap, off the critical path
-            if (p.dbg != nullptr) { const long long t0 = clock64(); mbar_wait(&full[s], s_par); t_wait_w += clock64() - t0; }
-            else mbar_wait(&full[s], s_par);
-            tc_fence_after_sync();
-            if (elect_one_sync()) {
-              tc_mma_tf32(tmem, ad, bd, idesc, acc);
-              tc_mma_tf32(tmem, ad + 2, bd + 2, idesc, 1u);
-              tc_mma_tf32(tmem, ad + 4, bd + 4, idesc, 1u);
-              tc_mma_tf32(tmem, ad + 6, bd + 6, idesc, 1u);
-              tc_commit(&empty[s]);
+            if (!w_ok) {
+              const long long t0 = clock64();
+              mbar_wait(&full[s], s_par);
+              t_wait_w += clock64() - t0;
             }
-            acc = 1u;
+            uint64_t* wdone = &empty[s];
             if (++s == S) { s = 0; s_par ^= 1; w_lo = w_lo0; } else { w_lo += w_step; }
+            tc_fence_after_sync();
+            tc_mma_tf32(tmem, ad, bd, idesc, acc);
+            tc_mma_tf32(tmem, ad + 2, bd + 2, idesc, 1u);
+            tc_mma_tf32(tmem, ad + 4, bd + 4, idesc, 1u);
+            tc_mma_tf32(tmem, ad + 6, bd + 6, idesc, 1u);
+            tc_commit(wdone);
+            acc = 1u;
+            // off the critical path (the MMAs above are draining): next tap's offset, next stage's barrier
+            aoff = static_cast<uint32_t>(p.tap_aoff[t + 1]) >> 4;   // tap_aoff has one slack entry
+            w_ok = mbar_test_wait(&full[s], s_par);
           }
-          if (elect_one_sync()) tc_commit(&pempty[ps]);
+          tc_commit(&pempty[ps]);
           if (++ps == P) { ps = 0; p_par ^= 1; p_lo = p_lo0; } else { p_lo += p_step; }
         }
       }
-      if (main_kb > 0 && elect_one_sync()) tc_commit(&acc_full[0]);
-      if (lane == 0) TC_STAMP(3);
-      if (p.dbg != nullptr && lane == 0) {
+      if (main_kb > 0) tc_commit(&acc_full[0]);
+      TC_STAMP(3);
+      if (p.dbg != nullptr) {
         long long* q = p.dbg + ((int64_t)blockIdx.y * gridDim.x + blockIdx.x) * 32;
         q[11] = q[0] + t_wait_w; q[12] = q[0] + t_wait_p;   // stored relative to slot 0 like the stamps
       }
@@ -320,19 +329,17 @@ __global__ void __launch_bounds__(kThreads, 2) conv_tc_kernel(const __grid_const
         mbar_wait(&full[s], s_par);
         mbar_wait(&a2_ready[c], 0);
         tc_fence_after_sync();
-        if (elect_one_sync()) {
-          tc_mma_tf32(tmem + p.n_ch, ad, bd, idesc, c > 0 ? 1u : 0u);
-          tc_mma_tf32(tmem + p.n_ch, ad + 2, bd + 2, idesc, 1u);
-          tc_mma_tf32(tmem + p.n_ch, ad + 4, bd + 4, idesc, 1u);
-          tc_mma_tf32(tmem + p.n_ch, ad + 6, bd + 6, idesc, 1u);
-          tc_commit(&empty[s]);
-          tc_commit(&pempty[ps]);
-        }
+        tc_mma_tf32(tmem + p.n_ch, ad, bd, idesc, c > 0 ? 1u : 0u);
+        tc_mma_tf32(tmem + p.n_ch, ad + 2, bd + 2, idesc, 1u);
+        tc_mma_tf32(tmem + p.n_ch, ad + 4, bd + 4, idesc, 1u);
+        tc_mma_tf32(tmem + p.n_ch, ad + 6, bd + 6, idesc, 1u);
+        tc_commit(&empty[s]);
+        tc_commit(&pempty[ps]);
         if (!p.ld_alias) { if (++s == S) { s = 0; s_par ^= 1; w_lo = w_lo0; } else { w_lo += w_step; } }
         if (++ps == P) { ps = 0; p_par ^= 1; p_lo = p_lo0; } else { p_lo += p_step; }
       }
-      if (gdn_kb > 0 && elect_one_sync()) tc_commit(&acc_full[1]);
-      if (lane == 0) TC_STAMP(4);
+      if (gdn_kb > 0) tc_commit(&acc_full[1]);
+      TC_STAMP(4);
     }
     __syncwarp();
   } else {
@@ -592,7 +599,8 @@ __global__ void __launch_bounds__(kThreads, 2) conv_tc_kernel(const __grid_const
 //     item starts) instead of a TMA staging pair: that shared memory now holds the deeper rings.
 // Reference semantics are those of conv_tc_kernel above (anchors/utils.py:112-130, utils/ops.py:58-97).
 // =====================================================================================================
-constexpr int kPThreads = 320;
+constexpr int kPThreads = 352;   // warp 0 TMA producer, 1 main MMA issuer, 2-9 two epilogue groups, 10 normalisation MMA issuer
+constexpr int kPNormWarp = 10;
 
 struct TcpClass {
   int16_t g_begin, g_end;   // groups of this class
@@ -605,7 +613,7 @@ struct TcpParams {
   CUtensorMap out_map[4], sc_map[4];   // per class; backward epilogues: sc_map = saved scale, yprev_map = saved y
   CUtensorMap yprev_map[4];
   Group groups[kMaxGroups];
-  int32_t tap_aoff[kMaxTaps];
+  int32_t tap_aoff[kMaxTaps + 1];   // one slack entry: the issuer reads tap t + 1 ahead
   int16_t tap_wtap[kMaxTaps];
   TcpClass cls[4];
   int n_class, k_chunks, n_ch, n_chunks, n_total;
@@ -736,113 +744,117 @@ __global__ void __launch_bounds__(kPThreads, 1) conv_tcp_kernel(const __grid_con
     }
     __syncwarp();
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    {   // all 32 lanes run the loop (uniform state); one elected lane issues
+    // ===================== main-loop MMA issuer =====================
+    // ONE thread runs the whole role (elected once, no per-K-block reconvergence): at N = 128 the tensor core retires
+    // a K-block (4 MMAs) every 256 cycles and a lone warp issues roughly one dependent instruction per 4-6 cycles, so
+    // the issue path has to stay at a few dozen instructions per K-block (a bare issue loop reaches the tensor floor,
+    // scripts/probes/mma_rate_probe.cu; the previous form -- converged warp, elect + reconvergence per K-block,
+    // normalisation hand-off polled in the same loop -- measured ~530 cycles per K-block, ncu source view:
+    // 19 % of it on the reconvergence barrier waiting for the four UTCHMMA to drain).  The normalisation K-blocks have
+    // their own issuing warp (below): they only depend on the epilogue, never on this loop.
+    if (elect_one_sync()) {
       const uint32_t idesc = umma_idesc_tf32(kTileM, p.n_ch);
       const uint32_t hi_dense = (1024u >> 4) | (1u << 14) | (2u << 29);
       const uint32_t w_lo0 = ((smem_u32(wring) >> 4) & 0x3FFFu) | (1u << 16);
       const uint32_t p_lo0 = ((smem_u32(smem) >> 4) & 0x3FFFu) | (1u << 16);
-      const uint32_t g_lo0 = ((smem_u32(gmat) >> 4) & 0x3FFFu) | (1u << 16);
-      const uint32_t a2_lo0 = ((smem_u32(grp0) >> 4) & 0x3FFFu) | (1u << 16);
       const uint32_t w_step = b_bytes >> 4, p_step = static_cast<uint32_t>(p.patch_bytes) >> 4;
       int s = 0, ps = 0;
       uint32_t s_par = 0, p_par = 0, w_lo = w_lo0, p_lo = p_lo0;
-      int pend[2] = {-1, -1};                  // next normalisation chunk to issue per TMEM buffer, -1 = none
-      uint32_t rdy_par[4] = {0, 0, 0, 0};      // a2_ready parity per (buffer, slot)
-      uint32_t free_par[2] = {1, 1};           // tmem_free parity per buffer (first use: free)
-      bool g_loaded = false;
-      // issue every normalisation K-block whose A operand is ready (never blocks)
-      auto service = [&]() {
-#pragma unroll
-        for (int bb = 0; bb < 2; ++bb) {
-          const int c = pend[bb];
-          if (c < 0) continue;
-          const int slot = bwd ? 0 : (c & 1);   // backward: the operand replaces the staged y chunk in place (slot 0)
-          const int k = bb * 2 + slot;
-          // the probe is one warp-wide instruction (identical result in every lane); broadcast makes that explicit
-          if (!__shfl_sync(0xffffffffu, (int)mbar_test_wait(&a2_ready[k], rdy_par[k]), 0)) continue;
-          rdy_par[k] ^= 1;
-          if (!g_loaded) { mbar_wait(gfull, 0); g_loaded = true; }
-          tc_fence_after_sync();
-          const uint64_t ad = (static_cast<uint64_t>(hi_dense) << 32) |
-                              (a2_lo0 + bb * (static_cast<uint32_t>(p.grp_bytes) >> 4) + slot * (kABytes >> 4));
-          const uint64_t bd = (static_cast<uint64_t>(hi_dense) << 32) | (g_lo0 + c * w_step);
-          const uint32_t d = tmem + bb * 256 + p.n_ch;
-          if (elect_one_sync()) {
-            tc_mma_tf32(d, ad, bd, idesc, c > 0 ? 1u : 0u);
-            tc_mma_tf32(d, ad + 2, bd + 2, idesc, 1u);
-            tc_mma_tf32(d, ad + 4, bd + 4, idesc, 1u);
-            tc_mma_tf32(d, ad + 6, bd + 6, idesc, 1u);
-            tc_commit(&a2_free[k]);
-            if (c == nC - 1) tc_commit(&norm_full[bb]);
-          }
-          pend[bb] = (c == nC - 1) ? -1 : c + 1;
-        }
-      };
+      uint32_t free_bits = 3;                  // tmem_free parity per buffer (first use: free)
       int b = 0;
       const bool prof = p.dbg != nullptr;
-      long long c_ring = 0, c_free = 0, n_items = 0;
+      long long c_free = 0, n_items = 0, c_ring = 0, c_ring_p = 0;
       const long long c_start = prof ? clock64() : 0;
+      bool w_ok = false;                       // result of the early probe of wfull[s]
       for (int item = blockIdx.x; item < total; item += gridDim.x, b ^= 1) {
         const TcpItem it = tcp_decode(p, item);
         const TcpClass cl = p.cls[it.cls];
         ++n_items;
         // the epilogue of the item that last used TMEM buffer b must have finished reading it
-        if (!__shfl_sync(0xffffffffu, (int)mbar_test_wait(&tmem_free[b], free_par[b]), 0)) {
+        if (!mbar_test_wait(&tmem_free[b], (free_bits >> b) & 1u)) {
           const long long t0 = clock64();
-          while (!__shfl_sync(0xffffffffu, (int)mbar_test_wait(&tmem_free[b], free_par[b]), 0)) {
-            if (gdn) service();
-            if (clock64() - t0 > 4000000000LL) __trap();
-          }
+          mbar_wait(&tmem_free[b], (free_bits >> b) & 1u);
           c_free += clock64() - t0;
         }
-        free_par[b] ^= 1;
+        free_bits ^= 1u << b;
         tc_fence_after_sync();
         const uint32_t d = tmem + b * 256;
         uint32_t acc = 0;
         for (int kc = 0; kc < p.k_chunks; ++kc) {
           for (int g = cl.g_begin; g < cl.g_end; ++g) {
-            const Group gr = p.groups[g];
-            const uint32_t a_hi = (static_cast<uint32_t>(gr.sbo_bytes) >> 4) | (1u << 14) | (2u << 29);
-            uint32_t aoff = static_cast<uint32_t>(p.tap_aoff[gr.tap_begin]) >> 4;
-            if (prof) { const long long t0 = clock64(); mbar_wait(&pfull[ps], p_par); c_ring += clock64() - t0; }
-            else mbar_wait(&pfull[ps], p_par);
-            for (int t = gr.tap_begin; t < gr.tap_end; ++t) {
+            const uint32_t a_hi = (static_cast<uint32_t>(p.groups[g].sbo_bytes) >> 4) | (1u << 14) | (2u << 29);
+            const int t_end = p.groups[g].tap_end;
+            int t = p.groups[g].tap_begin;
+            uint32_t aoff = static_cast<uint32_t>(p.tap_aoff[t]) >> 4;
+            if (!mbar_test_wait(&pfull[ps], p_par)) {   // slow path (timed for the developer counters)
+              const long long t0 = clock64();
+              mbar_wait(&pfull[ps], p_par);
+              c_ring_p += clock64() - t0;
+            }
+            for (; t < t_end; ++t) {
               const uint64_t ad = (static_cast<uint64_t>(a_hi) << 32) | (p_lo + aoff);
               const uint64_t bd = (static_cast<uint64_t>(hi_dense) << 32) | w_lo;
-              aoff = static_cast<uint32_t>(p.tap_aoff[t + 1 < gr.tap_end ? t + 1 : t]) >> 4;
-              if (prof) { const long long t0 = clock64(); mbar_wait(&wfull[s], s_par); c_ring += clock64() - t0; }
-              else mbar_wait(&wfull[s], s_par);
-              tc_fence_after_sync();
-              if (elect_one_sync()) {
-                tc_mma_tf32(d, ad, bd, idesc, acc);
-                tc_mma_tf32(d, ad + 2, bd + 2, idesc, 1u);
-                tc_mma_tf32(d, ad + 4, bd + 4, idesc, 1u);
-                tc_mma_tf32(d, ad + 6, bd + 6, idesc, 1u);
-                tc_commit(&wempty[s]);
+              if (!w_ok) {
+                const long long t0 = clock64();
+                mbar_wait(&wfull[s], s_par);
+                c_ring += clock64() - t0;
               }
-              acc = 1u;
+              uint64_t* wdone = &wempty[s];
               if (++s == S) { s = 0; s_par ^= 1; w_lo = w_lo0; } else { w_lo += w_step; }
-              if (gdn && (s & 1) == 0 && (pend[0] >= 0 || pend[1] >= 0)) service();   // poll every other K-block
+              tc_fence_after_sync();
+              tc_mma_tf32(d, ad, bd, idesc, acc);
+              tc_mma_tf32(d, ad + 2, bd + 2, idesc, 1u);
+              tc_mma_tf32(d, ad + 4, bd + 4, idesc, 1u);
+              tc_mma_tf32(d, ad + 6, bd + 6, idesc, 1u);
+              tc_commit(wdone);
+              acc = 1u;
+              // off the critical path (the four MMAs above are draining): next tap's offset, next stage's barrier
+              aoff = static_cast<uint32_t>(p.tap_aoff[t + 1]) >> 4;   // tap_aoff has one slack entry
+              w_ok = mbar_test_wait(&wfull[s], s_par);
             }
-            if (elect_one_sync()) tc_commit(&pempty[ps]);
+            tc_commit(&pempty[ps]);
             if (++ps == P) { ps = 0; p_par ^= 1; p_lo = p_lo0; } else { p_lo += p_step; }
           }
         }
-        if (elect_one_sync()) tc_commit(&acc_full[b]);
-        if (gdn) pend[b] = 0;
+        tc_commit(&acc_full[b]);
       }
-      const long long c_main_end = prof ? clock64() : 0;
-      if (gdn) {
-        const long long t0 = clock64();
-        while (pend[0] >= 0 || pend[1] >= 0) {
-          service();
-          if (clock64() - t0 > 4000000000LL) __trap();
-        }
-      }
-      if (prof && lane == 0) {
+      if (prof) {
         long long* q = p.dbg + (int64_t)blockIdx.x * 16;
-        q[0] = c_main_end - c_start; q[1] = c_ring; q[2] = c_free; q[7] = n_items; q[8] = clock64() - c_start;
+        q[0] = clock64() - c_start; q[1] = c_ring + c_ring_p; q[2] = c_free; q[4] = c_ring_p; q[7] = n_items; q[8] = q[0];
+      }
+    }
+    __syncwarp();
+  } else if (warp == kPNormWarp) {
+    // ===================== normalisation MMA issuer (GDN / IGDN epilogues) =====================
+    // Walks the same item sequence; per item nC K-blocks [128 x 32] x gamma chunk -> the item's norm region.  The A
+    // operand is written by the item's epilogue group (a2_ready), which in turn waited for the main accumulator.
+    if (gdn && elect_one_sync()) {
+      const uint32_t idesc = umma_idesc_tf32(kTileM, p.n_ch);
+      const uint32_t hi_dense = (1024u >> 4) | (1u << 14) | (2u << 29);
+      const uint32_t g_lo0 = ((smem_u32(gmat) >> 4) & 0x3FFFu) | (1u << 16);
+      const uint32_t a2_lo0 = ((smem_u32(grp0) >> 4) & 0x3FFFu) | (1u << 16);
+      const uint32_t w_step = b_bytes >> 4;
+      uint32_t rdy_bits = 0;                   // a2_ready parity, bit (buffer * 2 + slot)
+      int b = 0;
+      mbar_wait(gfull, 0);
+      for (int item = blockIdx.x; item < total; item += gridDim.x, b ^= 1) {
+        const uint32_t dn = tmem + b * 256 + p.n_ch;
+        for (int c = 0; c < nC; ++c) {
+          const int slot = bwd ? 0 : (c & 1);   // backward: the operand replaces the staged y chunk in place (slot 0)
+          const int k = b * 2 + slot;
+          const uint64_t ad = (static_cast<uint64_t>(hi_dense) << 32) |
+                              (a2_lo0 + b * (static_cast<uint32_t>(p.grp_bytes) >> 4) + slot * (kABytes >> 4));
+          const uint64_t bd = (static_cast<uint64_t>(hi_dense) << 32) | (g_lo0 + c * w_step);
+          mbar_wait(&a2_ready[k], (rdy_bits >> k) & 1u);
+          rdy_bits ^= 1u << k;
+          tc_fence_after_sync();
+          tc_mma_tf32(dn, ad, bd, idesc, c > 0 ? 1u : 0u);
+          tc_mma_tf32(dn, ad + 2, bd + 2, idesc, 1u);
+          tc_mma_tf32(dn, ad + 4, bd + 4, idesc, 1u);
+          tc_mma_tf32(dn, ad + 6, bd + 6, idesc, 1u);
+          tc_commit(&a2_free[k]);
+          if (c == nC - 1) tc_commit(&norm_full[b]);
+        }
       }
     }
     __syncwarp();

@@ -36,6 +36,7 @@ def run(name, d, keep):
     items = float(t[:, 7].median())
     print(f"{name}: {e0.elapsed_time(e1):.3f} ms, {items:.0f} items/CTA")
     print(f"   MMA warp: main loops {med[0]:8.1f} us (rings {med[1]:7.1f}, TMEM-buffer wait {med[2]:7.1f}), whole {med[8]:8.1f} us")
+    print(f"   of the ring wait: {med[4]:.1f} us on the patch ring")
     for g in range(2):
         print(f"   epilogue group {g}: wait acc {med[9 + 3 * g]:8.1f}  pass1(+norm wait) {med[10 + 3 * g]:8.1f}  pass2 {med[11 + 3 * g]:8.1f} us")
     print(f"   group 0 waiting for the last normalisation MMA: {med[3]:.1f} us")

@@ -1,0 +1,269 @@
+// Developer probe: sustained issue rate of tcgen05.mma kind::tf32 (M = 128 per CTA, K = 8) from ONE issuing thread,
+// as a function of N, of the number of resident CTAs per SM, of the number of accumulators / issuing warps, and of
+// cta_group (1 = one SM, 2 = a CTA pair sharing the B operand).  Operands are static shared-memory tiles (no TMA),
+// rotated over `nbuf` buffers so that consecutive instructions read different addresses, as the conv kernels do.
+// Prints cycles per MMA per SM and the fraction of the 4096 FLOP/cycle/SM TF32 floor.
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O2 -o mma_rate_probe mma_rate_probe.cu
+#include <stdio.h>
+#include <stdlib.h>
+#include <vector>
+#include "../../imagecompression_adversarial_b200/csrc/icadv_ptx.cuh"
+using namespace icadv;
+
+struct Cfg {
+  int n;          // MMA N
+  int nbuf;       // operand buffers rotated through
+  int iters;      // MMAs per issuing warp
+  int issuers;    // 1 or 2 issuing warps (each with its own accumulator)
+  int accs;       // accumulators an issuer alternates between (1 or 2)
+  int cg;         // cta_group
+  int same_a;     // 1: every MMA reads the same A tile
+  int kb;         // > 0: per `kb` MMAs one mbarrier wait (already complete) + fence before and one tcgen05.commit after
+  int same_acc;   // 1: both issuers accumulate into the SAME TMEM region
+};
+
+__device__ __forceinline__ void mma_cg2(uint32_t d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n}\n" ::"r"(d), "l"(a), "l"(b), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void commit_cg2(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_rank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+template <int CG>
+__global__ void __launch_bounds__(128) probe(Cfg c, long long* out) {
+  extern __shared__ uint8_t raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~uintptr_t(1023));
+  const int b_rows = c.n / CG;                      // rows of B this CTA holds
+  const int a_bytes = 128 * 128, b_bytes = b_rows * 128;
+  uint8_t* A = smem;
+  uint8_t* B = smem + c.nbuf * a_bytes;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(B + c.nbuf * b_bytes);
+  uint32_t* tptr = reinterpret_cast<uint32_t*>(bar + 8);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int total = c.nbuf * (a_bytes + b_bytes) / 4;
+  for (int i = threadIdx.x; i < total; i += 128) reinterpret_cast<float*>(smem)[i] = 1e-3f * (float)((i * 37) & 255);
+  if (threadIdx.x == 0) { for (int i = 0; i < 8; ++i) mbar_init(&bar[i], 1); mbar_fence_init(); }
+  int cols = 32;
+  while (cols < c.issuers * c.accs * c.n) cols <<= 1;
+  if (warp == 0) {
+    if (CG == 1) { tmem_alloc(tptr, cols); tmem_relinquish(); }
+    else {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tptr)), "r"(cols) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+  }
+  fence_proxy_async_smem();
+  tc_fence_before_sync();
+  __syncthreads();
+  if (CG == 2) cluster_sync_all();
+  tc_fence_after_sync();
+  const uint32_t tmem = *tptr;
+  const bool leader_cta = CG == 1 || cluster_rank() == 0;
+  if (leader_cta && warp < c.issuers) {
+    const uint32_t idesc = umma_idesc_tf32(128 * CG, c.n);
+    const uint32_t hi = (1024u >> 4) | (1u << 14) | (2u << 29);
+    const uint32_t a_lo0 = ((smem_u32(A) >> 4) & 0x3FFFu) | (1u << 16);
+    const uint32_t b_lo0 = ((smem_u32(B) >> 4) & 0x3FFFu) | (1u << 16);
+    const int acc_cols = c.n;   // accumulators side by side
+    __syncwarp();
+    const long long t0 = clock64();
+    int buf = 0;
+    uint64_t* rdy = &bar[2 + warp];       // a barrier whose phase 0 completes at once: the "full" wait of a K-block
+    uint64_t* done = &bar[4 + warp];      // receives the per-K-block commits (nobody waits on it)
+    if (c.kb > 0 && lane == 0) mbar_arrive(rdy);
+    __syncwarp();
+    for (int i = 0; i < c.iters; i += 4) {
+      if (c.kb > 0 && (i % c.kb) == 0) { mbar_wait(rdy, 0); tc_fence_after_sync(); }
+      const uint64_t ad = (static_cast<uint64_t>(hi) << 32) | (a_lo0 + (c.same_a ? 0 : buf) * (a_bytes >> 4));
+      const uint64_t bd = (static_cast<uint64_t>(hi) << 32) | (b_lo0 + buf * (b_bytes >> 4));
+      const uint32_t d = tmem + ((c.same_acc ? 0 : warp) * c.accs + ((i >> 2) % c.accs)) * acc_cols;
+      if (elect_one_sync()) {
+        if (CG == 1) {
+          tc_mma_tf32(d, ad, bd, idesc, 1u); tc_mma_tf32(d, ad + 2, bd + 2, idesc, 1u);
+          tc_mma_tf32(d, ad + 4, bd + 4, idesc, 1u); tc_mma_tf32(d, ad + 6, bd + 6, idesc, 1u);
+        } else {
+          mma_cg2(d, ad, bd, idesc, 1u); mma_cg2(d, ad + 2, bd + 2, idesc, 1u);
+          mma_cg2(d, ad + 4, bd + 4, idesc, 1u); mma_cg2(d, ad + 6, bd + 6, idesc, 1u);
+        }
+      }
+      if (c.kb > 0 && ((i + 4) % c.kb) == 0 && elect_one_sync()) { if (CG == 1) tc_commit(done); else commit_cg2(done); }
+      if (++buf == c.nbuf) buf = 0;
+    }
+    if (elect_one_sync()) { if (CG == 1) tc_commit(&bar[warp]); else commit_cg2(&bar[warp]); }
+    __syncwarp();
+    const long long t_issue = clock64();
+    mbar_wait(&bar[warp], 0);
+    const long long t1 = clock64();
+    if (lane == 0) {
+      out[(blockIdx.x * 2 + warp) * 2 + 0] = t1 - t0;
+      out[(blockIdx.x * 2 + warp) * 2 + 1] = t_issue - t0;
+    }
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (CG == 2) cluster_sync_all();
+  if (warp == 0) {
+    if (CG == 1) tmem_dealloc(tmem, cols);
+    else asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(cols) : "memory");
+  }
+}
+
+// Minimal issue loops (cg1, N = 128, one accumulator): U MMAs per elect.sync block, or MODE 1 = only lane 0 runs the loop
+template <int U, int MODE, int NN = 128>
+__global__ void __launch_bounds__(128) probe_min(int iters, long long* out) {
+  extern __shared__ uint8_t raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* A = smem;
+  uint8_t* B = smem + 4 * 16384;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(B + 4 * 16384);
+  uint32_t* tptr = reinterpret_cast<uint32_t*>(bar + 8);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < 8 * 16384 / 4; i += 128) reinterpret_cast<float*>(smem)[i] = 1e-3f * (float)((i * 37) & 255);
+  if (threadIdx.x == 0) { mbar_init(&bar[0], 1); mbar_fence_init(); }
+  if (warp == 0) { tmem_alloc(tptr, 128); tmem_relinquish(); }
+  fence_proxy_async_smem();
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem = *tptr;
+  if (warp == 0) {
+    const uint32_t idesc = umma_idesc_tf32(128, NN);
+    const uint32_t hi = (1024u >> 4) | (1u << 14) | (2u << 29);
+    const uint32_t a_lo0 = ((smem_u32(A) >> 4) & 0x3FFFu) | (1u << 16);
+    const uint32_t b_lo0 = ((smem_u32(B) >> 4) & 0x3FFFu) | (1u << 16);
+    __syncwarp();
+    const long long t0 = clock64();
+    if (MODE == 0) {
+      for (int i = 0; i < iters; i += U) {
+        if (elect_one_sync()) {
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            const uint32_t off = ((u >> 2) & 3) * 1024u + (u & 3) * 2u;
+            tc_mma_tf32(tmem, (static_cast<uint64_t>(hi) << 32) | (a_lo0 + off), (static_cast<uint64_t>(hi) << 32) | (b_lo0 + off), idesc, 1u);
+          }
+        }
+      }
+      if (elect_one_sync()) tc_commit(&bar[0]);
+    } else if (lane == 0) {
+      for (int i = 0; i < iters; i += U) {
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const uint32_t off = ((u >> 2) & 3) * 1024u + (u & 3) * 2u;
+          tc_mma_tf32(tmem, (static_cast<uint64_t>(hi) << 32) | (a_lo0 + off), (static_cast<uint64_t>(hi) << 32) | (b_lo0 + off), idesc, 1u);
+        }
+      }
+      tc_commit(&bar[0]);
+    }
+    __syncwarp();
+    mbar_wait(&bar[0], 0);
+    const long long t1 = clock64();
+    if (lane == 0) out[blockIdx.x] = t1 - t0;
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 128);
+}
+
+template <int U, int MODE, int NN = 128>
+static void run_min(const char* name) {
+  const int iters = 2048, smem = 8 * 16384 + 128 + 1024;
+  long long* d_out;
+  cudaMalloc(&d_out, 148 * sizeof(long long));
+  cudaFuncSetAttribute(probe_min<U, MODE, NN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  for (int rep = 0; rep < 2; ++rep) probe_min<U, MODE, NN><<<148, 128, smem>>>(iters, d_out);
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) { printf("%-58s CUDA error: %s\n", name, cudaGetErrorString(e)); exit(1); }
+  std::vector<long long> h(148);
+  cudaMemcpy(h.data(), d_out, 148 * sizeof(long long), cudaMemcpyDeviceToHost);
+  double sum = 0;
+  for (int b = 0; b < 148; ++b) sum += (double)h[b];
+  printf("%-58s %7.1f cyc/MMA/SM  (floor 64.0)\n", name, sum / 148 / iters);
+  cudaFree(d_out);
+}
+
+static void run(const char* name, Cfg c, int ctas_per_sm) {
+  const int b_rows = c.n / c.cg;
+  int smem = c.nbuf * (128 * 128 + b_rows * 128) + 128 + 1024;
+  if (ctas_per_sm == 1 && smem < 120 * 1024) smem = 120 * 1024;   // force one CTA per SM
+  const int grid = 148 * ctas_per_sm;
+  long long* d_out;
+  cudaMalloc(&d_out, grid * 4 * sizeof(long long));
+  cudaMemset(d_out, 0, grid * 4 * sizeof(long long));
+  cudaError_t e;
+  if (c.cg == 1) {
+    cudaFuncSetAttribute(probe<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    for (int rep = 0; rep < 2; ++rep) probe<1><<<grid, 128, smem>>>(c, d_out);
+  } else {
+    cudaFuncSetAttribute(probe<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(128); cfg.dynamicSmemBytes = smem;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    for (int rep = 0; rep < 2; ++rep) cudaLaunchKernelEx(&cfg, probe<2>, c, d_out);
+  }
+  e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) { printf("%-58s CUDA error: %s\n", name, cudaGetErrorString(e)); exit(1); }
+  std::vector<long long> h(grid * 4);
+  cudaMemcpy(h.data(), d_out, grid * 4 * sizeof(long long), cudaMemcpyDeviceToHost);
+  double sum = 0, sum_i = 0; int cnt = 0;
+  for (int b = 0; b < grid; ++b)
+    for (int w = 0; w < 2; ++w)
+      if (h[(b * 2 + w) * 2] > 0) { sum += (double)h[(b * 2 + w) * 2]; sum_i += (double)h[(b * 2 + w) * 2 + 1]; ++cnt; }
+  const double cyc = sum / cnt, cyc_issue = sum_i / cnt;
+  // MMAs retired per SM while one issuer runs: issuers * ctas_per_sm streams in parallel (cg2: one stream feeds 2 SMs)
+  const double streams_per_sm = (c.cg == 1) ? (double)c.issuers * ctas_per_sm : (double)c.issuers * ctas_per_sm;
+  const double per_mma_per_sm = cyc / c.iters / streams_per_sm;   // cg2: each instruction = 128 x N x 8 on EACH SM
+  const double floor_cyc = 128.0 * c.n * 8 / 2048.0;                  // 128 x N x 8 MACs at 2048 MAC/cycle/SM
+  printf("%-58s %7.1f cyc/MMA/SM (issue loop %6.1f)  floor %5.1f  -> %5.1f %% of the tensor floor\n", name, per_mma_per_sm,
+         cyc_issue / c.iters / streams_per_sm, floor_cyc, 100.0 * floor_cyc / per_mma_per_sm);
+  cudaFree(d_out);
+}
+
+int main() {
+  const int L = 2048;
+  run_min<4, 0, 64>("min loop N=64: elect, 4 MMAs per block (floor 32)");
+  run_min<4, 0, 32>("min loop N=32: elect, 4 MMAs per block (floor 16)");
+  run_min<16, 0, 32>("min loop N=32: elect, 16 MMAs per block (floor 16)");
+  run_min<4, 0, 16>("min loop N=16: elect, 4 MMAs per block (floor 8)");
+  run_min<4, 0>("min loop: elect, 4 MMAs per block");
+  run_min<8, 0>("min loop: elect, 8 MMAs per block");
+  run_min<16, 0>("min loop: elect, 16 MMAs per block");
+  run_min<64, 0>("min loop: elect, 64 MMAs per block");
+  run_min<4, 1>("min loop: lane 0 only, 4 MMAs per iteration");
+  run_min<16, 1>("min loop: lane 0 only, 16 MMAs per iteration");
+  run("cg1 N=128 1 CTA/SM, 1 issuer, 4 bufs", Cfg{128, 4, L, 1, 1, 1, 0, 0, 0}, 1);
+  run("cg1 N=128 1 CTA/SM, 1 issuer, same A", Cfg{128, 4, L, 1, 1, 1, 1, 0, 0}, 1);
+  run("cg1 N=128 1 CTA/SM, 1 issuer, 1 buf", Cfg{128, 1, L, 1, 1, 1, 0, 0, 0}, 1);
+  run("cg1 N=128 1 CTA/SM, 1 issuer, 2 accumulators", Cfg{128, 4, L, 1, 2, 1, 0, 0, 0}, 1);
+  run("cg1 N=128 1 CTA/SM, 2 issuers", Cfg{128, 4, L, 2, 1, 1, 0, 0, 0}, 1);
+  run("cg1 N=128 2 CTA/SM, 1 issuer each", Cfg{128, 3, L, 1, 1, 1, 0, 0, 0}, 2);
+  run("cg1 N=64  1 CTA/SM, 1 issuer", Cfg{64, 4, L, 1, 1, 1, 0, 0, 0}, 1);
+  run("cg1 N=192 1 CTA/SM, 1 issuer", Cfg{192, 4, L, 1, 1, 1, 0, 0, 0}, 1);
+  run("cg1 N=256 1 CTA/SM, 1 issuer", Cfg{256, 4, L, 1, 1, 1, 0, 0, 0}, 1);
+  run("cg1 N=256 1 CTA/SM, 1 issuer, 2 accumulators", Cfg{256, 4, L, 1, 2, 1, 0, 0, 0}, 1);
+  run("cg2 M=256 N=128 (B split 64+64), 1 issuer per pair", Cfg{128, 4, L, 1, 1, 2, 0, 0, 0}, 1);
+  run("cg2 M=256 N=256 (B split 128+128), 1 issuer per pair", Cfg{256, 4, L, 1, 1, 2, 0, 0, 0}, 1);
+  run("cg2 M=256 N=128, 2 accumulators", Cfg{128, 4, L, 1, 2, 2, 0, 0, 0}, 1);
+  run("cg1 N=128 1 issuer, wait+commit per 4 MMAs", Cfg{128, 4, L, 1, 1, 1, 0, 4, 0}, 1);
+  run("cg1 N=128 1 issuer, wait+commit per 8 MMAs", Cfg{128, 4, L, 1, 1, 1, 0, 8, 0}, 1);
+  run("cg1 N=128 2 issuers, wait+commit per 4 MMAs", Cfg{128, 4, L, 2, 1, 1, 0, 4, 0}, 1);
+  run("cg1 N=128 2 issuers SAME accumulator", Cfg{128, 4, L, 2, 1, 1, 0, 0, 1}, 1);
+  run("cg1 N=128 2 issuers SAME accumulator, wait+commit per 4", Cfg{128, 4, L, 2, 1, 1, 0, 4, 1}, 1);
+  run("cg1 N=256 1 issuer, wait+commit per 4 MMAs", Cfg{256, 4, L, 1, 1, 1, 0, 4, 0}, 1);
+  run("cg1 N=128 2 CTA/SM, wait+commit per 4 MMAs", Cfg{128, 3, L, 1, 1, 1, 0, 4, 0}, 2);
+  run("cg2 N=128 2 issuers", Cfg{128, 4, L, 2, 1, 2, 0, 0, 0}, 1);
+  return 0;
+}
