@@ -6,7 +6,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libicadv_b200.so")
+LIB_PATH = os.environ.get("ICADV_LIB") or os.path.join(_HERE, "libicadv_b200.so")   # ICADV_LIB: developer A/B of two builds
 
 OK = 0
 FORM_SCONV, FORM_TCONV = 0, 1

@@ -599,8 +599,8 @@ __global__ void __launch_bounds__(kThreads, 2) conv_tc_kernel(const __grid_const
 //     item starts) instead of a TMA staging pair: that shared memory now holds the deeper rings.
 // Reference semantics are those of conv_tc_kernel above (anchors/utils.py:112-130, utils/ops.py:58-97).
 // =====================================================================================================
-constexpr int kPThreads = 352;   // warp 0 TMA producer, 1 main MMA issuer, 2-9 two epilogue groups, 10 normalisation MMA issuer
-constexpr int kPNormWarp = 10;
+constexpr int kPThreads = 384;   // warp 0 weight producer, 1 main MMA issuer, 2-9 two epilogue groups, 10 normalisation MMA issuer, 11 patch producer
+constexpr int kPNormWarp = 10, kPPatchWarp = 11;
 
 struct TcpClass {
   int16_t g_begin, g_end;   // groups of this class
@@ -613,8 +613,8 @@ struct TcpParams {
   CUtensorMap out_map[4], sc_map[4];   // per class; backward epilogues: sc_map = saved scale, yprev_map = saved y
   CUtensorMap yprev_map[4];
   Group groups[kMaxGroups];
-  int32_t tap_aoff[kMaxTaps + 1];   // one slack entry: the issuer reads tap t + 1 ahead
-  int16_t tap_wtap[kMaxTaps];
+  int32_t tap_aoff[kMaxTaps + 2];   // slack entries: the issuer reads up to tap t + 2 ahead
+  int16_t tap_wtap[kMaxTaps + 1];
   TcpClass cls[4];
   int n_class, k_chunks, n_ch, n_chunks, n_total;
   int num_patch, patch_bytes, num_stages;
@@ -700,15 +700,40 @@ __global__ void __launch_bounds__(kPThreads, 1) conv_tcp_kernel(const __grid_con
   const int total = n_slots * p.tiles_x * p.tiles_y * p.n_class;
 
   if (warp == 0) {
-    // ===================== TMA producer =====================
-    {   // all 32 lanes run the loop (uniform state); one elected lane issues
-      if (gdn && elect_one_sync()) {
+    // ===================== TMA producer: weights (+ the resident gamma) =====================
+    // Weights and patches have separate producing threads: a patch is requested as soon as its slot is free (one
+    // whole patch period ahead of its use) instead of queueing behind the weight boxes of the previous patch.
+    if (elect_one_sync()) {
+      if (gdn) {
         mbar_arrive_expect_tx(gfull, nC * b_bytes);
         for (int c = 0; c < nC; ++c) tma_load_2d(gmat + c * b_bytes, &p.g_map, gfull, c * 32, 0);
       }
-      int s = 0, ps = 0;
-      uint32_t s_par = 1, p_par = 1;
+      int s = 0;
+      uint32_t s_par = 1;
       uint8_t* wdst = wring;
+      for (int item = blockIdx.x; item < total; item += gridDim.x) {
+        const TcpItem it = tcp_decode(p, item);
+        const TcpClass cl = p.cls[it.cls];
+        const int t_begin = p.groups[cl.g_begin].tap_begin, t_end = p.groups[cl.g_end - 1].tap_end;   // a class's taps are contiguous
+        for (int kc = 0; kc < p.k_chunks; ++kc) {
+          const int c0 = kc * 32;
+          int wrow = p.tap_wtap[t_begin] * p.n_total;
+          for (int t = t_begin; t < t_end; ++t) {
+            mbar_wait(&wempty[s], s_par);
+            mbar_arrive_expect_tx(&wfull[s], b_bytes);
+            tma_load_2d(wdst, &p.w_map, &wfull[s], c0, wrow);
+            wrow = p.tap_wtap[t + 1] * p.n_total;   // one slack entry
+            if (++s == S) { s = 0; s_par ^= 1; wdst = wring; } else { wdst += b_bytes; }
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == kPPatchWarp) {
+    // ===================== TMA producer: input halo patches =====================
+    if (elect_one_sync()) {
+      int ps = 0;
+      uint32_t p_par = 1;
       uint8_t* pdst = smem;
       for (int item = blockIdx.x; item < total; item += gridDim.x) {
         const TcpItem it = tcp_decode(p, item);
@@ -716,28 +741,14 @@ __global__ void __launch_bounds__(kPThreads, 1) conv_tcp_kernel(const __grid_con
         for (int kc = 0; kc < p.k_chunks; ++kc) {
           const int c0 = kc * 32;
           for (int g = cl.g_begin; g < cl.g_end; ++g) {
-            const Group gr = p.groups[g];
-            const int cx = it.j0 + gr.dx0, cy = it.i0 + gr.dy0;
+            const int cx = it.j0 + p.groups[g].dx0, cy = it.i0 + p.groups[g].dy0;
             mbar_wait(&pempty[ps], p_par);
-            if (elect_one_sync()) {
-              mbar_arrive_expect_tx(&pfull[ps], gr.bytes);
-              if (p.a_rank5)
-                tma_load_5d(pdst, &p.a_map[0], &pfull[ps], 0, cx, cy, gr.plane5, it.img);
-              else
-                tma_load_4d(pdst, &p.a_map[gr.map], &pfull[ps], c0, cx, cy, it.img);
-            }
+            mbar_arrive_expect_tx(&pfull[ps], p.groups[g].bytes);
+            if (p.a_rank5)
+              tma_load_5d(pdst, &p.a_map[0], &pfull[ps], 0, cx, cy, p.groups[g].plane5, it.img);
+            else
+              tma_load_4d(pdst, &p.a_map[p.groups[g].map], &pfull[ps], c0, cx, cy, it.img);
             if (++ps == P) { ps = 0; p_par ^= 1; pdst = smem; } else { pdst += p.patch_bytes; }
-            int wrow = p.tap_wtap[gr.tap_begin] * p.n_total;
-            for (int t = gr.tap_begin; t < gr.tap_end; ++t) {
-              const int wrow_next = (t + 1 < gr.tap_end ? p.tap_wtap[t + 1] : 0) * p.n_total;
-              mbar_wait(&wempty[s], s_par);
-              if (elect_one_sync()) {
-                mbar_arrive_expect_tx(&wfull[s], b_bytes);
-                tma_load_2d(wdst, &p.w_map, &wfull[s], c0, wrow);
-              }
-              wrow = wrow_next;
-              if (++s == S) { s = 0; s_par ^= 1; wdst = wring; } else { wdst += b_bytes; }
-            }
           }
         }
       }
@@ -809,7 +820,7 @@ __global__ void __launch_bounds__(kPThreads, 1) conv_tcp_kernel(const __grid_con
               tc_commit(wdone);
               acc = 1u;
               // off the critical path (the four MMAs above are draining): next tap's offset, next stage's barrier
-              aoff = static_cast<uint32_t>(p.tap_aoff[t + 1]) >> 4;   // tap_aoff has one slack entry
+              aoff = static_cast<uint32_t>(p.tap_aoff[t + 1]) >> 4;   // tap_aoff has slack entries
               w_ok = mbar_test_wait(&wfull[s], s_par);
             }
             tc_commit(&pempty[ps]);

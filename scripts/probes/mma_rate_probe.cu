@@ -20,6 +20,7 @@ struct Cfg {
   int same_a;     // 1: every MMA reads the same A tile
   int kb;         // > 0: per `kb` MMAs one mbarrier wait (already complete) + fence before and one tcgen05.commit after
   int same_acc;   // 1: both issuers accumulate into the SAME TMEM region
+  int kbmode;     // which per-K-block extras run when kb > 0: 1 = mbarrier wait, 2 = tcgen05.fence::after_thread_sync, 4 = tcgen05.commit (0 = all)
 };
 
 __device__ __forceinline__ void mma_cg2(uint32_t d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
@@ -84,7 +85,10 @@ __global__ void __launch_bounds__(128) probe(Cfg c, long long* out) {
     if (c.kb > 0 && lane == 0) mbar_arrive(rdy);
     __syncwarp();
     for (int i = 0; i < c.iters; i += 4) {
-      if (c.kb > 0 && (i % c.kb) == 0) { mbar_wait(rdy, 0); tc_fence_after_sync(); }
+      if (c.kb > 0 && (i % c.kb) == 0) {
+        if (c.kbmode == 0 || (c.kbmode & 1)) mbar_wait(rdy, 0);
+        if (c.kbmode == 0 || (c.kbmode & 2)) tc_fence_after_sync();
+      }
       const uint64_t ad = (static_cast<uint64_t>(hi) << 32) | (a_lo0 + (c.same_a ? 0 : buf) * (a_bytes >> 4));
       const uint64_t bd = (static_cast<uint64_t>(hi) << 32) | (b_lo0 + buf * (b_bytes >> 4));
       const uint32_t d = tmem + ((c.same_acc ? 0 : warp) * c.accs + ((i >> 2) % c.accs)) * acc_cols;
@@ -97,7 +101,7 @@ __global__ void __launch_bounds__(128) probe(Cfg c, long long* out) {
           mma_cg2(d, ad + 4, bd + 4, idesc, 1u); mma_cg2(d, ad + 6, bd + 6, idesc, 1u);
         }
       }
-      if (c.kb > 0 && ((i + 4) % c.kb) == 0 && elect_one_sync()) { if (CG == 1) tc_commit(done); else commit_cg2(done); }
+      if (c.kb > 0 && (c.kbmode == 0 || (c.kbmode & 4)) && ((i + 4) % c.kb) == 0 && elect_one_sync()) { if (CG == 1) tc_commit(done); else commit_cg2(done); }
       if (++buf == c.nbuf) buf = 0;
     }
     if (elect_one_sync()) { if (CG == 1) tc_commit(&bar[warp]); else commit_cg2(&bar[warp]); }
@@ -192,6 +196,87 @@ static void run_min(const char* name) {
   cudaFree(d_out);
 }
 
+
+// Shared-memory contention: warp 0 issues the bare N = 128 MMA stream (64 cycles per MMA alone, all of it operand reads at
+// 128 B/clk); `lsw` other warps stream 16-byte ld.shared (mode 1) or st.shared (mode 2) over a private 32 KB buffer.
+__global__ void __launch_bounds__(288) probe_contend(int iters, int lsw, int mode, long long* out, float* sink) {
+  extern __shared__ uint8_t raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* A = smem;
+  uint8_t* B = smem + 4 * 16384;
+  uint8_t* X = B + 4 * 16384;                       // 32 KB private buffer of the load/store warps
+  uint64_t* bar = reinterpret_cast<uint64_t*>(X + 32768);
+  uint32_t* tptr = reinterpret_cast<uint32_t*>(bar + 8);
+  volatile int* stop = reinterpret_cast<volatile int*>(tptr + 2);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < (8 * 16384 + 32768) / 4; i += blockDim.x) reinterpret_cast<float*>(smem)[i] = 1e-3f * (float)((i * 37) & 255);
+  if (threadIdx.x == 0) { mbar_init(&bar[0], 1); mbar_fence_init(); *stop = 0; }
+  if (warp == 0) { tmem_alloc(tptr, 128); tmem_relinquish(); }
+  fence_proxy_async_smem();
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem = *tptr;
+  if (warp == 0) {
+    const uint32_t idesc = umma_idesc_tf32(128, 128);
+    const uint32_t hi = (1024u >> 4) | (1u << 14) | (2u << 29);
+    const uint32_t a_lo0 = ((smem_u32(A) >> 4) & 0x3FFFu) | (1u << 16);
+    const uint32_t b_lo0 = ((smem_u32(B) >> 4) & 0x3FFFu) | (1u << 16);
+    __syncwarp();
+    const long long t0 = clock64();
+    for (int i = 0; i < iters; i += 16) {
+      if (elect_one_sync()) {
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+          const uint32_t off = ((u >> 2) & 3) * 1024u + (u & 3) * 2u;
+          tc_mma_tf32(tmem, (static_cast<uint64_t>(hi) << 32) | (a_lo0 + off), (static_cast<uint64_t>(hi) << 32) | (b_lo0 + off), idesc, 1u);
+        }
+      }
+    }
+    if (elect_one_sync()) tc_commit(&bar[0]);
+    __syncwarp();
+    mbar_wait(&bar[0], 0);
+    const long long t1 = clock64();
+    if (lane == 0) { out[blockIdx.x * 2] = t1 - t0; *stop = 1; }
+  } else if (warp <= lsw) {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    long long n = 0;
+    float4* xb = reinterpret_cast<float4*>(X) + (warp - 1) * 256 + lane;   // 4 KB per warp, conflict-free 512 B per instruction
+    while (!*stop) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        if (mode == 1) { const float4 v = xb[k * 32]; acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w; }
+        else { xb[k * 32] = acc; acc.x += 1.f; }
+      }
+      n += 8;
+    }
+    if (lane == 0) atomicAdd(reinterpret_cast<unsigned long long*>(&out[blockIdx.x * 2 + 1]), (unsigned long long)n);
+    if (acc.x == 123.456f) sink[0] = acc.y + acc.z + acc.w;
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 128);
+}
+
+static void run_contend(const char* name, int lsw, int mode) {
+  const int iters = 4096, smem = 8 * 16384 + 32768 + 256 + 1024;
+  long long* d_out; float* d_sink;
+  cudaMalloc(&d_out, 148 * 2 * sizeof(long long));
+  cudaMalloc(&d_sink, 16);
+  cudaFuncSetAttribute(probe_contend, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  for (int rep = 0; rep < 2; ++rep) { cudaMemset(d_out, 0, 148 * 2 * sizeof(long long)); probe_contend<<<148, 288, smem>>>(iters, lsw, mode, d_out, d_sink); }
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) { printf("%-58s CUDA error: %s\n", name, cudaGetErrorString(e)); exit(1); }
+  std::vector<long long> h(148 * 2);
+  cudaMemcpy(h.data(), d_out, 148 * 2 * sizeof(long long), cudaMemcpyDeviceToHost);
+  double cyc = 0, ins = 0;
+  for (int b = 0; b < 148; ++b) { cyc += (double)h[2 * b]; ins += (double)h[2 * b + 1]; }
+  cyc /= 148; ins /= 148;
+  printf("%-58s %7.1f cyc/MMA  | other warps: %6.1f B/clk of %s (MMA operand reads: %5.1f B/clk)\n", name, cyc / iters,
+         ins * 512.0 / cyc, mode == 1 ? "ld.shared" : "st.shared", 8192.0 * iters / cyc);
+  cudaFree(d_out); cudaFree(d_sink);
+}
+
 static void run(const char* name, Cfg c, int ctas_per_sm) {
   const int b_rows = c.n / c.cg;
   int smem = c.nbuf * (128 * 128 + b_rows * 128) + 128 + 1024;
@@ -234,6 +319,20 @@ static void run(const char* name, Cfg c, int ctas_per_sm) {
 
 int main() {
   const int L = 2048;
+  run("cg1 N=128 1 issuer, per 4 MMAs: wait only", Cfg{128, 4, L, 1, 1, 1, 0, 4, 0, 1}, 1);
+  run("cg1 N=128 1 issuer, per 4 MMAs: fence only", Cfg{128, 4, L, 1, 1, 1, 0, 4, 0, 2}, 1);
+  run("cg1 N=128 1 issuer, per 4 MMAs: commit only", Cfg{128, 4, L, 1, 1, 1, 0, 4, 0, 4}, 1);
+  run("cg1 N=128 1 issuer, per 4 MMAs: wait + fence", Cfg{128, 4, L, 1, 1, 1, 0, 4, 0, 3}, 1);
+  run("cg1 N=128 1 issuer, per 4 MMAs: none of them (loop only)", Cfg{128, 4, L, 1, 1, 1, 0, 4, 0, 8}, 1);
+  run_contend("MMA stream alone", 0, 1);
+  run_contend("MMA stream + 1 warp ld.shared", 1, 1);
+  run_contend("MMA stream + 2 warps ld.shared", 2, 1);
+  run_contend("MMA stream + 4 warps ld.shared", 4, 1);
+  run_contend("MMA stream + 8 warps ld.shared", 8, 1);
+  run_contend("MMA stream + 1 warp st.shared", 1, 2);
+  run_contend("MMA stream + 2 warps st.shared", 2, 2);
+  run_contend("MMA stream + 4 warps st.shared", 4, 2);
+  run_contend("MMA stream + 8 warps st.shared", 8, 2);
   run_min<4, 0, 64>("min loop N=64: elect, 4 MMAs per block (floor 32)");
   run_min<4, 0, 32>("min loop N=32: elect, 4 MMAs per block (floor 16)");
   run_min<16, 0, 32>("min loop N=32: elect, 16 MMAs per block (floor 16)");
@@ -244,26 +343,26 @@ int main() {
   run_min<64, 0>("min loop: elect, 64 MMAs per block");
   run_min<4, 1>("min loop: lane 0 only, 4 MMAs per iteration");
   run_min<16, 1>("min loop: lane 0 only, 16 MMAs per iteration");
-  run("cg1 N=128 1 CTA/SM, 1 issuer, 4 bufs", Cfg{128, 4, L, 1, 1, 1, 0, 0, 0}, 1);
-  run("cg1 N=128 1 CTA/SM, 1 issuer, same A", Cfg{128, 4, L, 1, 1, 1, 1, 0, 0}, 1);
-  run("cg1 N=128 1 CTA/SM, 1 issuer, 1 buf", Cfg{128, 1, L, 1, 1, 1, 0, 0, 0}, 1);
-  run("cg1 N=128 1 CTA/SM, 1 issuer, 2 accumulators", Cfg{128, 4, L, 1, 2, 1, 0, 0, 0}, 1);
-  run("cg1 N=128 1 CTA/SM, 2 issuers", Cfg{128, 4, L, 2, 1, 1, 0, 0, 0}, 1);
-  run("cg1 N=128 2 CTA/SM, 1 issuer each", Cfg{128, 3, L, 1, 1, 1, 0, 0, 0}, 2);
-  run("cg1 N=64  1 CTA/SM, 1 issuer", Cfg{64, 4, L, 1, 1, 1, 0, 0, 0}, 1);
-  run("cg1 N=192 1 CTA/SM, 1 issuer", Cfg{192, 4, L, 1, 1, 1, 0, 0, 0}, 1);
-  run("cg1 N=256 1 CTA/SM, 1 issuer", Cfg{256, 4, L, 1, 1, 1, 0, 0, 0}, 1);
-  run("cg1 N=256 1 CTA/SM, 1 issuer, 2 accumulators", Cfg{256, 4, L, 1, 2, 1, 0, 0, 0}, 1);
-  run("cg2 M=256 N=128 (B split 64+64), 1 issuer per pair", Cfg{128, 4, L, 1, 1, 2, 0, 0, 0}, 1);
-  run("cg2 M=256 N=256 (B split 128+128), 1 issuer per pair", Cfg{256, 4, L, 1, 1, 2, 0, 0, 0}, 1);
-  run("cg2 M=256 N=128, 2 accumulators", Cfg{128, 4, L, 1, 2, 2, 0, 0, 0}, 1);
-  run("cg1 N=128 1 issuer, wait+commit per 4 MMAs", Cfg{128, 4, L, 1, 1, 1, 0, 4, 0}, 1);
-  run("cg1 N=128 1 issuer, wait+commit per 8 MMAs", Cfg{128, 4, L, 1, 1, 1, 0, 8, 0}, 1);
-  run("cg1 N=128 2 issuers, wait+commit per 4 MMAs", Cfg{128, 4, L, 2, 1, 1, 0, 4, 0}, 1);
-  run("cg1 N=128 2 issuers SAME accumulator", Cfg{128, 4, L, 2, 1, 1, 0, 0, 1}, 1);
-  run("cg1 N=128 2 issuers SAME accumulator, wait+commit per 4", Cfg{128, 4, L, 2, 1, 1, 0, 4, 1}, 1);
-  run("cg1 N=256 1 issuer, wait+commit per 4 MMAs", Cfg{256, 4, L, 1, 1, 1, 0, 4, 0}, 1);
-  run("cg1 N=128 2 CTA/SM, wait+commit per 4 MMAs", Cfg{128, 3, L, 1, 1, 1, 0, 4, 0}, 2);
-  run("cg2 N=128 2 issuers", Cfg{128, 4, L, 2, 1, 2, 0, 0, 0}, 1);
+  run("cg1 N=128 1 CTA/SM, 1 issuer, 4 bufs", Cfg{128, 4, L, 1, 1, 1, 0, 0, 0, 0}, 1);
+  run("cg1 N=128 1 CTA/SM, 1 issuer, same A", Cfg{128, 4, L, 1, 1, 1, 1, 0, 0, 0}, 1);
+  run("cg1 N=128 1 CTA/SM, 1 issuer, 1 buf", Cfg{128, 1, L, 1, 1, 1, 0, 0, 0, 0}, 1);
+  run("cg1 N=128 1 CTA/SM, 1 issuer, 2 accumulators", Cfg{128, 4, L, 1, 2, 1, 0, 0, 0, 0}, 1);
+  run("cg1 N=128 1 CTA/SM, 2 issuers", Cfg{128, 4, L, 2, 1, 1, 0, 0, 0, 0}, 1);
+  run("cg1 N=128 2 CTA/SM, 1 issuer each", Cfg{128, 3, L, 1, 1, 1, 0, 0, 0, 0}, 2);
+  run("cg1 N=64  1 CTA/SM, 1 issuer", Cfg{64, 4, L, 1, 1, 1, 0, 0, 0, 0}, 1);
+  run("cg1 N=192 1 CTA/SM, 1 issuer", Cfg{192, 4, L, 1, 1, 1, 0, 0, 0, 0}, 1);
+  run("cg1 N=256 1 CTA/SM, 1 issuer", Cfg{256, 4, L, 1, 1, 1, 0, 0, 0, 0}, 1);
+  run("cg1 N=256 1 CTA/SM, 1 issuer, 2 accumulators", Cfg{256, 4, L, 1, 2, 1, 0, 0, 0, 0}, 1);
+  run("cg2 M=256 N=128 (B split 64+64), 1 issuer per pair", Cfg{128, 4, L, 1, 1, 2, 0, 0, 0, 0}, 1);
+  run("cg2 M=256 N=256 (B split 128+128), 1 issuer per pair", Cfg{256, 4, L, 1, 1, 2, 0, 0, 0, 0}, 1);
+  run("cg2 M=256 N=128, 2 accumulators", Cfg{128, 4, L, 1, 2, 2, 0, 0, 0, 0}, 1);
+  run("cg1 N=128 1 issuer, wait+commit per 4 MMAs", Cfg{128, 4, L, 1, 1, 1, 0, 4, 0, 0}, 1);
+  run("cg1 N=128 1 issuer, wait+commit per 8 MMAs", Cfg{128, 4, L, 1, 1, 1, 0, 8, 0, 0}, 1);
+  run("cg1 N=128 2 issuers, wait+commit per 4 MMAs", Cfg{128, 4, L, 2, 1, 1, 0, 4, 0, 0}, 1);
+  run("cg1 N=128 2 issuers SAME accumulator", Cfg{128, 4, L, 2, 1, 1, 0, 0, 1, 0}, 1);
+  run("cg1 N=128 2 issuers SAME accumulator, wait+commit per 4", Cfg{128, 4, L, 2, 1, 1, 0, 4, 1, 0}, 1);
+  run("cg1 N=256 1 issuer, wait+commit per 4 MMAs", Cfg{256, 4, L, 1, 1, 1, 0, 4, 0, 0}, 1);
+  run("cg1 N=128 2 CTA/SM, wait+commit per 4 MMAs", Cfg{128, 3, L, 1, 1, 1, 0, 4, 0, 0}, 2);
+  run("cg2 N=128 2 issuers", Cfg{128, 4, L, 2, 1, 2, 0, 0, 0, 0}, 1);
   return 0;
 }
