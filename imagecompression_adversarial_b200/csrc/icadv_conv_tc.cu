@@ -589,7 +589,8 @@ __global__ void __launch_bounds__(kThreads, 2) conv_tc_kernel(const __grid_const
 // Persistent variant: ONE CTA per SM walks a static list of work items (tile x parity class x image).
 //   * the accumulator is double-buffered in TMEM (2 x 256 columns: [acc N | norm N]), so the MMA issuer starts the
 //     next item's main loop while the previous item's epilogue is still reading;
-//   * two epilogue warpgroups (warps 2-5 / 6-9) take alternate items, each with its own 2 x 16 KB staging;
+//   * two epilogue warpgroups (warps 2-5 / 6-9), each with its own 2 x 16 KB staging, share every item (half of the
+//     32-channel chunks each; col2im: alternate items);
 //   * the four output-parity classes of a stride-2 transposed conv are items of ONE launch (rotated so that every CTA
 //     sees all classes: they differ in length 9/6/6/4 taps);
 //   * gamma (the B operand of the normalisation GEMM) is loaded once per CTA and stays resident;
@@ -678,7 +679,10 @@ __global__ void __launch_bounds__(kPThreads, 1) conv_tcp_kernel(const __grid_con
     for (int s = 0; s < S; ++s) { mbar_init(&wfull[s], 1); mbar_init(&wempty[s], 1); }
     for (int s = 0; s < P; ++s) { mbar_init(&pfull[s], 1); mbar_init(&pempty[s], 1); }
     mbar_init(gfull, 1);
-    for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&norm_full[b], 1); mbar_init(&tmem_free[b], 1); }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&acc_full[b], 1); mbar_init(&norm_full[b], 1);
+      mbar_init(&tmem_free[b], bwd ? 2 : 1);   // backward epilogues: both epilogue groups read every item
+    }
     for (int k = 0; k < 4; ++k) { mbar_init(&a2_ready[k], 128); mbar_init(&a2_free[k], 1); }
     mbar_init(&ld_full[0], 1); mbar_init(&ld_full[1], 1);
     mbar_fence_init();
@@ -850,35 +854,54 @@ __global__ void __launch_bounds__(kPThreads, 1) conv_tcp_kernel(const __grid_con
       mbar_wait(gfull, 0);
       for (int item = blockIdx.x; item < total; item += gridDim.x, b ^= 1) {
         const uint32_t dn = tmem + b * 256 + p.n_ch;
-        for (int c = 0; c < nC; ++c) {
-          const int slot = bwd ? 0 : (c & 1);   // backward: the operand replaces the staged y chunk in place (slot 0)
-          const int k = b * 2 + slot;
-          const uint64_t ad = (static_cast<uint64_t>(hi_dense) << 32) |
-                              (a2_lo0 + b * (static_cast<uint32_t>(p.grp_bytes) >> 4) + slot * (kABytes >> 4));
-          const uint64_t bd = (static_cast<uint64_t>(hi_dense) << 32) | (g_lo0 + c * w_step);
-          mbar_wait(&a2_ready[k], (rdy_bits >> k) & 1u);
-          rdy_bits ^= 1u << k;
-          tc_fence_after_sync();
-          tc_mma_tf32(dn, ad, bd, idesc, c > 0 ? 1u : 0u);
-          tc_mma_tf32(dn, ad + 2, bd + 2, idesc, 1u);
-          tc_mma_tf32(dn, ad + 4, bd + 4, idesc, 1u);
-          tc_mma_tf32(dn, ad + 6, bd + 6, idesc, 1u);
-          tc_commit(&a2_free[k]);
-          if (c == nC - 1) tc_commit(&norm_full[b]);
+        // forward: the item belongs to epilogue group b, chunk c in slot c & 1.  backward: chunk c is produced by group g
+        // (first / second half of the channels) in that group's slot 0, and the two groups' chunks are taken alternately
+        // (a fixed order: the accumulation order stays deterministic)
+        const int half = bwd ? (nC + 1) >> 1 : nC;
+        int issued = 0;
+        for (int j = 0; j < half; ++j) {
+          for (int gg = 0; gg < (bwd ? 2 : 1); ++gg) {
+            const int c = gg ? half + j : j;
+            if (c >= nC) continue;
+            const int g = bwd ? gg : b;
+            const int slot = bwd ? 0 : (j & 1);   // backward: the operand replaces the staged y chunk in place (slot 0)
+            const int k = g * 2 + slot;
+            const uint64_t ad = (static_cast<uint64_t>(hi_dense) << 32) |
+                                (a2_lo0 + g * (static_cast<uint32_t>(p.grp_bytes) >> 4) + slot * (kABytes >> 4));
+            const uint64_t bd = (static_cast<uint64_t>(hi_dense) << 32) | (g_lo0 + c * w_step);
+            mbar_wait(&a2_ready[k], (rdy_bits >> k) & 1u);
+            rdy_bits ^= 1u << k;
+            tc_fence_after_sync();
+            tc_mma_tf32(dn, ad, bd, idesc, issued > 0 ? 1u : 0u);
+            tc_mma_tf32(dn, ad + 2, bd + 2, idesc, 1u);
+            tc_mma_tf32(dn, ad + 4, bd + 4, idesc, 1u);
+            tc_mma_tf32(dn, ad + 6, bd + 6, idesc, 1u);
+            tc_commit(&a2_free[k]);
+            if (++issued == nC) tc_commit(&norm_full[b]);
+          }
         }
       }
     }
     __syncwarp();
   } else {
-    // ===================== two epilogue warpgroups, alternate items =====================
+    // ===================== two epilogue warpgroups =====================
+    // Backward epilogues (eight serial saved-chunk round trips per item): BOTH groups work on every item, each on half
+    // of the 32-channel chunks, so an item's TMEM buffer is handed back after half the epilogue latency and the issuer's
+    // next main loop (other buffer) overlaps it; with alternate items per group a group's own next main loop could never
+    // start before its epilogue had ended (g_a.2 dgrad: 20 us per item and group, of which 6 us main loop; 4.08 -> 3.47 ms).
+    // Forward / linear / col2im epilogues keep alternate items: they have no load latency to hide and two items in
+    // flight overlap their normalisation wait and store drain (split measured slower there: RGB layer 1.58 -> 1.96 ms).
+    constexpr bool split = bwd;
     const int grp = (warp - 2) >> 2;           // 0: warps 2-5, 1: warps 6-9
     const int q = warp & 3;                    // TMEM lane quadrant this warp may touch
     const int row = q * 32 + lane;
     const bool leader = (row == 0);
     const uint32_t bar_id = 1 + grp;
     uint8_t* gbuf = grp0 + grp * p.grp_bytes;  // two 16 KB slots: normalisation A operand / store staging (col2im: Z tile)
-    const uint32_t t_lane = tmem + (static_cast<uint32_t>(q * 32) << 16) + grp * 256;
-    uint32_t acc_par = 0, norm_par = 0;
+    const int c_half = (nC + 1) >> 1;
+    const int c_lo = split ? (grp == 0 ? 0 : c_half) : 0;        // this group's chunks [c_lo, c_hi)
+    const int c_hi = split ? (grp == 0 ? c_half : nC) : nC;
+    uint32_t acc_bits = 0, norm_bits = 0;      // acc_full / norm_full parity per TMEM buffer
     uint32_t slot_par[2] = {1, 1};             // a2_free parity per slot (first use: free)
     // Backward epilogues stage the saved y / scale of the item one 32-channel chunk at a time in this group's slot pair
     // [y | scale] (TMA, swizzled rows).  Everything that follows a chunk happens IN PLACE: pass 1 overwrites the y
@@ -896,22 +919,25 @@ __global__ void __launch_bounds__(kPThreads, 1) conv_tcp_kernel(const __grid_con
       }
       __syncwarp();
     };
+    const int item0 = blockIdx.x + (split ? 0 : grp * gridDim.x);
+    const int item_step = (split ? 1 : 2) * gridDim.x;
     if constexpr (bwd) {
-      const int first = blockIdx.x + grp * gridDim.x;
-      if (first < total) fetch(tcp_decode(p, first), 0);
+      if (item0 < total && c_lo < c_hi) fetch(tcp_decode(p, item0), c_lo);
     }
 
-    for (int item = blockIdx.x + grp * gridDim.x; item < total; item += 2 * gridDim.x) {
+    int b = split ? 0 : grp;                   // TMEM buffer of the current item
+    for (int item = item0; item < total; item += item_step, b ^= (split ? 1 : 0)) {
       const TcpItem it = tcp_decode(p, item);
       const int o_a = p.cls[it.cls].o_a, o_b = p.cls[it.cls].o_b;
       const int gi = it.i0 + row / kTW, gj = it.j0 + row % kTW;
       const bool px_ok = gi < p.t_h && gj < p.t_w;
       const int64_t pix = (((int64_t)it.img * p.o_h + p.o_s * gi + o_a) * p.o_w + p.o_s * gj + o_b) * p.n_ch;
       (void)px_ok; (void)pix;
+      const uint32_t t_lane = tmem + (static_cast<uint32_t>(q * 32) << 16) + b * 256;
       const bool eprof = p.dbg != nullptr && leader;
       const long long e0 = eprof ? clock64() : 0;
-      mbar_wait(&acc_full[grp], acc_par);
-      acc_par ^= 1;
+      mbar_wait(&acc_full[b], (acc_bits >> b) & 1u);
+      acc_bits ^= 1u << b;
       tc_fence_after_sync();
       const long long e1 = eprof ? clock64() : 0;
       long long e2 = e1, e3 = e1;
@@ -931,7 +957,7 @@ __global__ void __launch_bounds__(kPThreads, 1) conv_tcp_kernel(const __grid_con
         }
         tc_fence_before_sync();
         named_bar_sync(bar_id, 128);
-        if (leader) mbar_arrive(&tmem_free[grp]);
+        if (leader) mbar_arrive(&tmem_free[b]);
         const int OH = 2 * p.c2i_in_h, OW = 2 * p.c2i_in_w, nch = p.c2i_nch;
         constexpr int kIy = kTH - 2, kIx = kTW - 2;
         for (int o = row; o < kIy * kIx * 4; o += 128) {
@@ -997,7 +1023,7 @@ __global__ void __launch_bounds__(kPThreads, 1) conv_tcp_kernel(const __grid_con
       };
 
       if constexpr (!gdn) {
-        for (int c = 0; c < nC; ++c) {
+        for (int c = c_lo; c < c_hi; ++c) {
           float v[32];
           load_acc(c, v);
           if (p.act == ICADV_ACT_RELU) {
@@ -1013,8 +1039,8 @@ __global__ void __launch_bounds__(kPThreads, 1) conv_tcp_kernel(const __grid_con
           store_one(c, v, &p.out_map[it.cls], p.round_out != 0);
         }
       } else {
-        // ---- pass 1: A operand of the normalisation GEMM, chunk c -> slot c & 1 ----
-        for (int c = 0; c < nC; ++c) {
+        // ---- pass 1: A operand of the normalisation GEMM, this group's chunk c -> slot (c - c_lo) & 1 ----
+        for (int c = c_lo; c < c_hi; ++c) {
           float v[32], a2[32];
           load_acc(c, v);
           if constexpr (!bwd) {
@@ -1042,10 +1068,10 @@ __global__ void __launch_bounds__(kPThreads, 1) conv_tcp_kernel(const __grid_con
             // the pair is refilled once the tensor core has read the operand (all 128 threads arrived before that)
             if (leader) mbar_wait(&a2_free[grp * 2], a2c_par);
             a2c_par ^= 1;
-            if (c + 1 < nC) fetch(it, c + 1);
+            if (c + 1 < c_hi) fetch(it, c + 1);
             continue;
           }
-          const int k = c & 1;
+          const int k = (c - c_lo) & 1;
           mbar_wait(&a2_free[grp * 2 + k], slot_par[k]);   // the MMAs that last read this slot are done
           slot_par[k] ^= 1;
           write_row32(gbuf + k * kABytes, row, a2);
@@ -1054,12 +1080,12 @@ __global__ void __launch_bounds__(kPThreads, 1) conv_tcp_kernel(const __grid_con
         }
         // ---- pass 2: normalise ----
         if (eprof) e2 = clock64();
-        mbar_wait(&norm_full[grp], norm_par);
-        norm_par ^= 1;
+        mbar_wait(&norm_full[b], (norm_bits >> b) & 1u);
+        norm_bits ^= 1u << b;
         tc_fence_after_sync();
         if (eprof) e3 = clock64();
-        if constexpr (bwd) fetch(it, 0);   // every normalisation MMA has completed: the pair is free again
-        for (int c = 0; c < nC; ++c) {
+        if constexpr (bwd) { if (c_lo < c_hi) fetch(it, c_lo); }   // every normalisation MMA has completed: the pair is free again
+        for (int c = c_lo; c < c_hi; ++c) {
           float v[32], w[32];
           load_acc(c, v);
           tmem_ld32(t_lane + p.n_ch + c * 32, w);
@@ -1100,10 +1126,10 @@ __global__ void __launch_bounds__(kPThreads, 1) conv_tcp_kernel(const __grid_con
             if (leader) {
               tma_store_4d(&p.out_map[it.cls], bufY, c * 32, it.j0, it.i0, it.img);
               tma_store_commit();
-              if (c + 1 < nC) tma_store_wait_read0();   // the store engine has read the pair: refill it
+              if (c + 1 < c_hi) tma_store_wait_read0();   // the store engine has read the pair: refill it
             }
             __syncwarp();
-            if (c + 1 < nC) fetch(it, c + 1);
+            if (c + 1 < c_hi) fetch(it, c + 1);
           }
         }
       }
@@ -1113,7 +1139,7 @@ __global__ void __launch_bounds__(kPThreads, 1) conv_tcp_kernel(const __grid_con
       if (leader) tma_store_wait_read0();
       __syncwarp();
       named_bar_sync(bar_id, 128);
-      if (leader) mbar_arrive(&tmem_free[grp]);
+      if (leader) mbar_arrive(&tmem_free[b]);
       if (eprof) {
         long long* q = p.dbg + (int64_t)blockIdx.x * 16 + 9 + grp * 3;   // per group: wait acc, pass 1 (+ wait norm), pass 2
         const long long e4 = clock64();
@@ -1121,8 +1147,8 @@ __global__ void __launch_bounds__(kPThreads, 1) conv_tcp_kernel(const __grid_con
         if (grp == 0) p.dbg[(int64_t)blockIdx.x * 16 + 3] += e3 - e2;  // of which: waiting for the last normalisation MMA
       }
       if constexpr (bwd) {   // request the first saved chunk of this group's next item while its main loop runs
-        const int nxt = item + 2 * gridDim.x;
-        if (nxt < total) fetch(tcp_decode(p, nxt), 0);
+        const int nxt = item + item_step;
+        if (nxt < total && c_lo < c_hi) fetch(tcp_decode(p, nxt), c_lo);
       }
     }
     if (leader) tma_store_wait0();

@@ -177,7 +177,15 @@ def conv(x, wpack, bias=None, *, form, ksize, stride, n_ch, epi=L.EPI_LINEAR, ac
         h, w = h - 4, w - 8
     oh, ow = out_hw(form, ksize, stride, h, w)
     if out is None:
-        out = torch.empty(n, oh, ow, n_ch, device=x.device, dtype=torch.float32)
+        if form == L.FORM_TCONV and ksize < stride:
+            # output pixels no tap reaches (the input gradient of a strided 1x1 conv: 3 of 4 pixels) are not written
+            # by the kernels: they are the bias, or zero.  torch.empty() is NOT zero (under the reference's
+            # torch.use_deterministic_algorithms(True), self_ensemble.py:31, it is NaN-filled).
+            out = torch.zeros(n, oh, ow, n_ch, device=x.device, dtype=torch.float32)
+            if bias is not None:
+                out += bias
+        else:
+            out = torch.empty(n, oh, ow, n_ch, device=x.device, dtype=torch.float32)
     fwd_gdn = epi in (L.EPI_GDN_FWD, L.EPI_IGDN_FWD)
     if fwd_gdn and out_scale is None:
         out_scale = torch.empty_like(out)

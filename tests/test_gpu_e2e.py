@@ -347,6 +347,30 @@ def test_generic_engine_cheng2020_matches_oracle(dev):
     assert abs(psnr(p[0], x) - psnr(o[0], x)) < 0.05
 
 
+def test_no_kernel_leaves_output_unwritten(dev):
+    """The reference runs with torch.use_deterministic_algorithms(True) (self_ensemble.py:31), under which torch.empty()
+    is NaN-filled: an output region a kernel does not write (e.g. the 3 of 4 pixels the input gradient of a strided 1x1
+    conv never reaches) must be produced explicitly.  Forward outputs, input gradients and net(x) of every family."""
+    from imagecompression_adversarial_b200 import models as pm
+    prev = torch.are_deterministic_algorithms_enabled()
+    torch.use_deterministic_algorithms(True, warn_only=True)
+    try:
+        for model, q, hw in (("cheng2020", 1, (64, 64)), ("context", 4, (64, 64)), ("hyper", 3, (64, 96)),
+                             ("factorized", 1, (64, 96))):
+            torch.manual_seed(0)
+            net = pm.init_model(model, q, "mse", pretrained=False).to(dev).train()
+            x = torch.rand(2, 3, *hw, device=dev).requires_grad_(True)
+            out = net.g_s(net.g_a(x))
+            out.backward(torch.rand_like(out))
+            assert bool(torch.isfinite(out).all()) and bool(torch.isfinite(x.grad).all()), model
+            assert all(p.grad is None or bool(torch.isfinite(p.grad).all()) for p in net.parameters()), model
+            full = net(x.detach())
+            assert bool(torch.isfinite(full["x_hat"]).all()), model
+            assert all(bool(torch.isfinite(v).all()) for v in full["likelihoods"].values()), model
+    finally:
+        torch.use_deterministic_algorithms(prev)
+
+
 def test_context_q4_msssim_attack_runs_and_matches(dev):
     """BASELINE config 3 at test size: mbt2018 q4 (N = M = 192), -att_metric ms-ssim, fused loop vs oracle."""
     from imagecompression_adversarial_b200 import attack as patk

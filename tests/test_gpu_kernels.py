@@ -468,7 +468,12 @@ def test_persistent_variant_equals_per_tile_kernel(dev, persist_env, case):
     for a, b in zip(*outs):
         assert float(a.abs().max()) > 0
         assert float(a[1].abs().max()) == 0 and float(b[1].abs().max()) == 0     # images not in the active list stay untouched
-        torch.testing.assert_close(b, a, rtol=1e-5, atol=1e-6)
+        # The persistent kernel's backward epilogue accumulates the normalisation chunks of its two warpgroups
+        # alternately (0, 2, 1, 3), the per-tile kernel in order: fp32 sums differ in the last bit, and where the output
+        # is rounded to TF32 (round_out) that can flip one TF32 ulp (2^-10 relative) on a few elements.
+        exact = torch.isclose(b, a, rtol=1e-5, atol=1e-6)
+        assert float((~exact).float().mean()) < 1e-3, float((~exact).float().mean())
+        torch.testing.assert_close(b, a, rtol=1.2e-3, atol=1e-6)
 
 
 @pytest.mark.parametrize("epi", ["igdn_fwd", "gdn_bwd", "col2im"])
