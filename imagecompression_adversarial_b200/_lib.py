@@ -76,6 +76,7 @@ _SIGS = {
     "icadv_output_loss_roi": (C.c_int, [_fp, _fp, _fp, _fp, _fp, C.c_int, C.c_int64, C.c_int, C.c_float, _fp, _fp, _fp,
                                         C.c_void_p]),
     "icadv_ifgsm_update": (C.c_int, [_fp, _fp, _fp, C.c_int64, C.c_float, C.c_float, C.c_void_p]),
+    "icadv_cw_combine": (C.c_int, [_fp, _fp, _fp, _fp, _fp, _fp, _fp, C.c_int, C.c_int64, C.c_void_p]),
     "icadv_mifgsm_update": (C.c_int, [_fp, _fp, _fp, _fp, _fp, _fp, C.c_int, C.c_int64, C.c_float, C.c_float, C.c_float,
                                       C.c_void_p]),
     "icadv_output_loss": (C.c_int, [_fp, _fp, _fp, _fp, _fp, C.c_int, C.c_int64, C.c_int, C.c_float, _fp, _fp,

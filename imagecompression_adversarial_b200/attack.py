@@ -143,3 +143,62 @@ def attack_ifgsm(im_s, net, args, random_start=False, multi_start=1, momentum=Fa
     im_adv = eng.im_adv_nchw().contiguous()
     im_, output_adv, bpp, mse_results, vi_results = eval(im_adv, im_s, output_s, net, args)
     return im_, output_adv, output_s, bpp_ori, bpp, mse_results["mse_in"], mse_results["mse_out"], vi_results["vi"]
+
+
+def attack_cw(im_s, net, args, record=None):
+    """Same contract as attack_cw.attack_ (attack_cw.py:194-263; inner search :142-192, loss :111-140): a bisection on
+    the reconstruction-error level wrapped around a bisection on the loss weight c, each probe ``args.steps`` Adam
+    iterations through the network.  Returns (im_adv, output_adv, output_s, bpp_ori, bpp, mse_in, mse_out, vi).
+
+    The reference handles one image per call; here every image of the batch carries its own (level, c) search state
+    (host arrays), the iterations of all images run as one fused batch, and one device->host read of 2 floats per image
+    closes each block of ``args.steps`` iterations (the reference synchronises every iteration).  An image whose outer
+    search has converged (:248-249) keeps the adversarial input it had at that point."""
+    import numpy as np
+    from .engine import CwEngine
+    output_s, bpp_ori = clean_pass(im_s, net, args)
+    net.train()                                                            # attack_cw.py:231
+    n, _, h, w = im_s.shape
+    key = ("cw", id(net), n, h, w, float(args.epsilon), float(args.lr_attack), bool(args.clamp))
+    eng = _ENGINES.get(key)
+    if eng is None:
+        eng = CwEngine(net, n, h, w, epsilon=args.epsilon, lr_attack=args.lr_attack, clamp=args.clamp)
+        _ENGINES.clear()
+        _ENGINES[key] = eng
+    else:
+        eng.refresh_parameters()
+    per_img = float(eng.per_img)
+    min_noise = np.full(n, float(args.noise)); max_noise = np.full(n, 0.1)
+    level = max_noise.copy()
+    loss_i = np.zeros(n)
+    done = np.zeros(n, dtype=bool)
+    final_in = torch.zeros_like(im_s)
+    for _ in range(args.search_steps):                                     # attack_cw.py:239
+        loss_i_old = loss_i
+        # ---- search_noise (attack_cw.py:142-192): fresh perturbation and optimiser, bisection on c
+        eng.load(im_s, output_s)
+        c_r = np.full(n, float(args.lamb_attack)); c_l = np.zeros(n); c = c_r.copy()
+        eng.level.copy_(torch.as_tensor(level, dtype=torch.float32))
+        for _ in range(args.search_steps):
+            eng.c.copy_(torch.as_tensor(c, dtype=torch.float32))
+            eng.run(args.steps)
+            got = torch.stack((eng.st.loss_i, eng.loss_o_sum / per_img)).cpu().double().numpy()   # one D2H per block
+            loss_i, mse_o = got[0], got[1]
+            if record is not None:
+                record.append((level.copy(), c.copy(), loss_i.copy(), mse_o.copy()))
+            low = mse_o < 0.99 * level                                     # attack_cw.py:186-189
+            c_l = np.where(low, c, c_l); c_r = np.where(low, c_r, c)
+            c = (c_r + c_l) / 2
+        im_in = eng.im_in_nchw()
+        conv = (np.abs(loss_i - loss_i_old) < args.noise * 0.01) & (np.abs(loss_i - args.noise) < args.noise * 0.1)
+        newly = ~done                                                      # images still searching take this result
+        final_in[torch.as_tensor(newly, device=im_s.device)] = im_in[torch.as_tensor(newly, device=im_s.device)]
+        done |= conv                                                       # attack_cw.py:248-249 (break)
+        if done.all():
+            break
+        over = loss_i > args.noise                                         # attack_cw.py:251-255
+        max_noise = np.where(over & ~done, level, max_noise)
+        min_noise = np.where(~over & ~done, level, min_noise)
+        level = np.where(done, level, (min_noise + max_noise) / 2)
+    im_adv, output_adv, bpp, mse_results, vi_results = eval(final_in.contiguous(), im_s, output_s, net, args)
+    return im_adv, output_adv, output_s, bpp_ori, bpp, mse_results["mse_in"], mse_results["mse_out"], vi_results["vi"]

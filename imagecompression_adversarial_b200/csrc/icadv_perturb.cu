@@ -210,6 +210,26 @@ __global__ void mifgsm_update_kernel(const float* __restrict__ im_s, float* im_a
   }
 }
 
+// ---- C&W loss (attack_cw.py:111-140): loss = loss_i + c (1 - MSE_o), with c = 0 for an image whose reconstruction
+//      error already exceeds 1.1 x its target level.  Gradient wrt im_in = 2 (im_in - im_s) / P + c_n g_net, where g_net
+//      is the network-branch gradient of (1 - MSE_o) the stack backward produced.
+__global__ void __launch_bounds__(256) cw_combine_kernel(const float4* __restrict__ g_net, const float4* __restrict__ im_in,
+                                                         const float4* __restrict__ im_s, float4* __restrict__ g_out,
+                                                         const float* __restrict__ c, const float* __restrict__ level,
+                                                         const float* __restrict__ sum_d2, int64_t per_img4,
+                                                         float inv_per_img) {
+  const int n = blockIdx.y;
+  const int64_t base = (int64_t)n * per_img4;
+  const float mse_o = sum_d2[n] * inv_per_img;
+  const float cn = (mse_o > level[n] * 1.1f) ? 0.f : c[n];          // attack_cw.py:138-139
+  const float a = 2.f * inv_per_img;
+  for (int64_t i = blockIdx.x * 256 + threadIdx.x; i < per_img4; i += (int64_t)gridDim.x * 256) {
+    const float4 g = __ldg(g_net + base + i), x = __ldg(im_in + base + i), s = __ldg(im_s + base + i);
+    g_out[base + i] = make_float4(a * (x.x - s.x) + cn * g.x, a * (x.y - s.y) + cn * g.y, a * (x.z - s.z) + cn * g.z,
+                                  a * (x.w - s.w) + cn * g.w);
+  }
+}
+
 // ---- output clamp + distortion + gradient seed (attack_rd.py:353-364)
 __global__ void __launch_bounds__(256) output_loss_kernel(const float4* __restrict__ x, const float4* __restrict__ ref,
                                                           float4* __restrict__ g_x, float* __restrict__ ws,
@@ -372,6 +392,20 @@ int icadv_mifgsm_update(const float* im_s, float* im_adv, const float* g, float*
   sum_finalize_kernel<<<(n_img + 127) / 128, 128, 0, as_stream(stream)>>>(ws, l1, n_img, nullptr, nullptr);
   ICADV_CUDA_TRY(cudaGetLastError());
   mifgsm_update_kernel<<<grid, 256, 0, as_stream(stream)>>>(im_s, im_adv, g, g_mom, l1, per_img, alpha, eps, mu);
+  ICADV_CUDA_TRY(cudaGetLastError());
+  return ICADV_OK;
+}
+
+int icadv_cw_combine(const float* g_net, const float* im_in, const float* im_s, float* g_out, const float* c,
+                     const float* level, const float* sum_d2, int n_img, int64_t per_img, icadv_stream_t stream) {
+  ICADV_REQUIRE(g_net && im_in && im_s && g_out && c && level && sum_d2, "null pointer");
+  ICADV_REQUIRE(per_img % 4 == 0 && n_img >= 1 && n_img <= 65535, "bad sizes");
+  dim3 grid(kRedBlocks, n_img);
+  cw_combine_kernel<<<grid, 256, 0, as_stream(stream)>>>(reinterpret_cast<const float4*>(g_net),
+                                                        reinterpret_cast<const float4*>(im_in),
+                                                        reinterpret_cast<const float4*>(im_s),
+                                                        reinterpret_cast<float4*>(g_out), c, level, sum_d2, per_img / 4,
+                                                        1.f / (float)per_img);
   ICADV_CUDA_TRY(cudaGetLastError());
   return ICADV_OK;
 }

@@ -272,6 +272,32 @@ class GenericAttackEngine(AttackEngine):
         return Fn.to_nhwc(x_in.grad).contiguous()
 
 
+class CwEngine(AttackEngine):
+    """One step of the C&W-style search of attack_cw.py (:111-140, 149-166): every iteration runs the network,
+    loss = loss_i + c (1 - MSE_o) with a per-image weight c (zeroed on device once the image's reconstruction error exceeds
+    1.1 x its target level), Adam with a CONSTANT learning rate (no scheduler in attack_cw.py).  ``c`` and ``level`` are
+    device vectors the driver (attack.attack_cw) rewrites between blocks of iterations; the iteration itself is the same
+    stream-ordered launch sequence (CUDA graph) as AttackEngine's network branch plus one combine kernel."""
+
+    def __init__(self, net, n_img, height, width, *, epsilon=16.0, lr_attack=0.01, clamp=True, use_graph=True, device=None):
+        super().__init__(net, n_img, height, width, steps=3, epsilon=epsilon, noise_budget=0.0, lr_attack=lr_attack,
+                         clamp=clamp, att_metric="L2", force_branch=1, use_graph=use_graph, device=device)
+        self.c = torch.zeros(n_img, device=self.device, dtype=torch.float32)
+        self.level = torch.zeros(n_img, device=self.device, dtype=torch.float32)
+        self.g_cw = torch.zeros_like(self.im_s)
+
+    def _iteration(self):
+        ops.perturb_forward(self.im_s, self.noise, self.im_in, self.st, eps=self.eps, budget=0.0, force_branch=1,
+                            lr0=self.lr0, lr_gamma=1.0, sched_period=1 << 30)
+        g_net = self._network_pass()       # d(1 - MSE_o)/d im_in; loss_o_sum[n] = sum (output_s - out)^2 of this forward
+        ops.cw_combine(g_net, self.im_in, self.im_s, self.g_cw, self.c, self.level, self.loss_o_sum)
+        ops.perturb_update_adam(self.im_s, self.noise, self.g_cw, self.m, self.v, self.st, eps=self.eps,
+                                gradA_scale=0.0, gradB_scale=1.0)
+
+    def kernels_per_iteration(self):
+        return super().kernels_per_iteration() + 1
+
+
 class IfgsmEngine:
     """I-FGSM / PGD / MI-FGSM loop of attack_ifgsm.py:364-438 on the same launch programs: every step is a network
     step (no budget branch): loss = mean((output_s - g_s(g_a(x)))^2), x += (eps/steps) sign(grad) [or the momentum

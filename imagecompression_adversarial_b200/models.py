@@ -309,7 +309,43 @@ class LowerBound(nn.Module):
         return Fn.Low_bound.apply(x, self.bound)
 
 
-class EntropyBottleneck(nn.Module):
+_CDF_BUFFERS = ("_offset", "_quantized_cdf", "_cdf_length")
+
+
+class _ZooStateDict:
+    """Checkpoint compatibility of the entropy models (reference: coder.py:104-116,
+    anchors/balle.py:57-72, anchors/utils.py:46-109; key names SURVEY.md A.7).
+
+    * The entropy-coder tables a CompressAI checkpoint carries (``_quantized_cdf``, ``_offset``, ``_cdf_length``, and
+      ``scale_table`` for GaussianConditional) are registered EMPTY like CompressAI does, so the reference's
+      ``update_registered_buffers`` can resize them and ``state_dict()`` round-trips them.  On load they take the
+      checkpoint's sizes ("resize" policy) and are optional (a plain / oracle state dict has none).  The likelihood
+      kernels never read them: bpp is estimated from the likelihoods (attack_rd.py:419); entropy coding itself is out
+      of scope (section 8f rank 4).
+    * CompressAI >= 1.2 stores the EntropyBottleneck chain as ParameterLists (``matrices.0`` ...); the reference's era
+      and this package use ``_matrix0`` ...: both spellings load."""
+
+    _zoo_buffers = _CDF_BUFFERS
+
+    def _register_zoo_buffers(self):
+        for name in _CDF_BUFFERS:
+            self.register_buffer(name, torch.zeros(0, dtype=torch.int32))
+
+    def _load_from_state_dict(self, state_dict, prefix, local_metadata, strict, missing_keys, unexpected_keys, error_msgs):
+        for new, old in (("matrices.", "_matrix"), ("biases.", "_bias"), ("factors.", "_factor")):
+            for key in [k for k in state_dict if k.startswith(prefix + new)]:
+                state_dict[prefix + old + key[len(prefix + new):]] = state_dict.pop(key)
+        for name in self._zoo_buffers:
+            key, buf = prefix + name, getattr(self, name)
+            if key in state_dict:
+                if tuple(buf.shape) != tuple(state_dict[key].shape):
+                    setattr(self, name, torch.zeros(state_dict[key].shape, dtype=buf.dtype, device=buf.device))
+            else:
+                state_dict[key] = buf
+        super()._load_from_state_dict(state_dict, prefix, local_metadata, strict, missing_keys, unexpected_keys, error_msgs)
+
+
+class EntropyBottleneck(_ZooStateDict, nn.Module):
     """compressai EntropyBottleneck, forward on the fused likelihood kernel."""
 
     def __init__(self, channels, tail_mass=1e-9, init_scale=10.0, filters=(3, 3, 3, 3)):
@@ -329,6 +365,7 @@ class EntropyBottleneck(nn.Module):
         self.quantiles = nn.Parameter(torch.tensor([-self.init_scale, 0.0, self.init_scale]).repeat(C, 1, 1))
         t = math.log(2 / self.tail_mass - 1)
         self.register_buffer("target", torch.tensor([-t, 0.0, t]))
+        self._register_zoo_buffers()
         self.likelihood_bound = 1e-9
         self.noise_override = None  # test hook: U(-.5,.5) sample shared with the oracle (NCHW)
         self.last_bits = None
@@ -371,12 +408,16 @@ class EntropyBottleneck(nn.Module):
         return Fn.to_nchw(x_hat), Fn.to_nchw(lik)
 
 
-class GaussianConditional(nn.Module):
+class GaussianConditional(_ZooStateDict, nn.Module):
     """compressai GaussianConditional (A.4) on the fused erfc likelihood kernel."""
+    _zoo_buffers = _CDF_BUFFERS + ("scale_table",)
 
     def __init__(self, scale_table=None, scale_bound=0.11, tail_mass=1e-9):
         super().__init__()
         self.scale_bound, self.likelihood_bound = float(scale_bound), 1e-9
+        self._register_zoo_buffers()
+        self.register_buffer("scale_table", torch.tensor(sorted(float(v) for v in scale_table)) if scale_table is not None
+                             else torch.zeros(0))
         self.noise_override = None
         self.last_bits = None
 

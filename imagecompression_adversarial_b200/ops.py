@@ -297,6 +297,14 @@ def ifgsm_update(im_s, im_adv, g, *, alpha, eps):
     L.call("icadv_ifgsm_update", _p(im_s), _p(im_adv), _p(g), im_s.numel(), float(alpha), float(eps), _stream())
 
 
+def cw_combine(g_net, im_in, im_s, g_out, c, level, sum_d2):
+    """C&W gradient wrt im_in (attack_cw.py:111-140): 2 (im_in - im_s) / P + c_n g_net, c_n zeroed per image once its
+    reconstruction error exceeds 1.1 x its target level."""
+    n_img, per_img = im_s.shape[0], im_s[0].numel()
+    L.call("icadv_cw_combine", _p(g_net), _p(im_in), _p(im_s), _p(g_out), _p(c), _p(level), _p(sum_d2), n_img, per_img,
+           _stream())
+
+
 def mifgsm_update(im_s, im_adv, g, g_mom, ws, l1, *, alpha, eps, mu=1.0):
     n_img, per_img = im_s.shape[0], im_s[0].numel()
     L.call("icadv_mifgsm_update", _p(im_s), _p(im_adv), _p(g), _p(g_mom), _p(ws), _p(l1), n_img, per_img, float(alpha),

@@ -159,3 +159,53 @@ def adv_train_step(batch_x, net, args, criterion, optimizer, aux_optimizer, grou
     aux.backward()
     aux_optimizer.step(None)
     return out, aux
+
+
+def test_epoch(epoch, test_dataloader, model, criterion, log_dir, args, group=None):
+    """train.py:196-242.  ``--adv``: every batch is attacked with the input budget forced to 1e-4 (:212-216) and the
+    mean VI (10 log10(mse_out / mse_in)) is returned; otherwise the RD loss, its terms and the auxiliary loss are
+    averaged over the batches (``training=True`` in the reference's criterion call only selects the loss form, :220).
+    One log line is appended to ``log_dir`` (a file path in the reference, :233-235).  Multi-GPU (one process per GPU,
+    each with its shard of the loader): the batch means and counts are summed over ``group`` before the averages form."""
+    from .attack import attack_
+    model.eval()
+    device = next(model.parameters()).device
+    sums = {"loss": 0.0, "bpp": 0.0, "aux": 0.0, "d": 0.0, "vi": 0.0}
+    count = 0
+    for d in test_dataloader:
+        d = d.to(device)
+        if args.adv:
+            noise = args.noise
+            args.noise = 0.0001                                           # :214 force the input perturbation level
+            try:
+                vi_results = attack_(d, model, args)[-1]
+            finally:
+                args.noise = noise
+            sums["vi"] += float(vi_results["vi"])
+        else:
+            with torch.no_grad():
+                out_net = model(d.detach())
+                out = criterion(out_net, d)
+                sums["aux"] += float(model.aux_loss())
+                sums["bpp"] += float(out["bpp_loss"])
+                sums["loss"] += float(out["loss"])
+                sums["d"] += float(out["distortion_loss"])
+        count += 1
+    if group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
+        t = torch.tensor([sums[k] for k in ("loss", "bpp", "aux", "d", "vi")] + [float(count)], device=device,
+                         dtype=torch.float64)
+        torch.distributed.all_reduce(t, group=group)
+        vals = t.tolist()
+        sums = dict(zip(("loss", "bpp", "aux", "d", "vi"), vals[:5]))
+        count = int(vals[5])
+    n = max(count, 1)
+    log = (f"Test epoch {epoch}: Average losses:\tLoss: {sums['loss'] / n:.4f} |\tMSE loss: {sums['d'] / n:.6f} |"
+           f"\tBpp loss: {sums['bpp'] / n:.3f} |\tRecomp loss: {0.0:.3f}\n")
+    if log_dir:
+        with open(log_dir, "a") as f:
+            f.write(log)
+    if args.adv:
+        print(f"Test Loss (VI): {sums['vi'] / n:.4f}")
+        return sums["vi"] / n
+    print(log)
+    return sums["loss"] / n

@@ -216,6 +216,12 @@ int icadv_ifgsm_update(const float* im_s, float* im_adv, const float* g, int64_t
 int icadv_mifgsm_update(const float* im_s, float* im_adv, const float* g, float* g_mom, float* ws, float* l1,
                         int n_img, int64_t per_img, float alpha, float eps, float mu, icadv_stream_t stream);
 
+/* C&W step (attack_cw.py:111-140: loss = loss_i + c (1 - MSE_o); c = 0 once MSE_o > 1.1 x the image's target level):
+ * g_out = 2 (im_in - im_s) / per_img + c_n * g_net, with c_n = (sum_d2[n] / per_img > 1.1 level[n]) ? 0 : c[n].
+ * g_net = gradient of (1 - MSE_o) wrt im_in from the stack backward; c, level, sum_d2: [n_img] device floats. */
+int icadv_cw_combine(const float* g_net, const float* im_in, const float* im_s, float* g_out, const float* c,
+                     const float* level, const float* sum_d2, int n_img, int64_t per_img, icadv_stream_t stream);
+
 /* Output clamp + distortion (attack_rd.py:353-364) and its gradient seed:
  * o = clamp(x,0,1) (if do_clamp); sum_d2[n] = sum (ref - o)^2;
  * g_x = grad_scale * 2 (ref - o) passed through the Low/Up_bound backward rule (g_x may be NULL). */

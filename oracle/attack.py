@@ -24,7 +24,7 @@ def default_args(**kw):
     """Defaults of ``coder.config()`` (coder.py:166-220) for the flags the hot path reads."""
     a = dict(model="hyper", metric="ms-ssim", quality=3, steps=1001, random=1, lamb_attack=0.2,
              noise=1e-4, lr_attack=0.01, att_metric="L2", epsilon=16.0, pad=None, debug=False,
-             clamp=True, defend=False, method="ensemble", adv=False, lr_train=1e-4,
+             clamp=True, defend=False, method="ensemble", adv=False, lr_train=1e-4, search_steps=20,
              target=None, mask_loc=None, lamb_bkg_in=1.0, lamb_bkg_out=1.0, lamb_tar=1.0)
     a.update(kw)
     return SimpleNamespace(**a)
@@ -163,6 +163,62 @@ def attack_(im_s, net, args, record=None, noise_init=None, im_t=None):
     return im_adv, output_adv, output_s, bpp_ori, bpp, mse_results, vi_results
 
 
+def attack_cw(im_s, net, args, record=None):
+    """attack_cw.py:111-263 for ONE image (the reference's unit): outer bisection on the reconstruction-error level
+    (:233-257), inner bisection on the loss weight c (:142-192), loss = loss_i + c (1 - MSE_o) with c zeroed once
+    MSE_o > 1.1 level (:111-140).  ``args.search_steps`` bounds both searches (coder.py flag).  ``record`` receives one
+    ``(level, c, loss_i, mse_o)`` per block of ``args.steps`` iterations.  Returns the reference's tuple
+    (im_adv, output_adv, output_s, bpp_ori, bpp, mse_in, mse_out, vi)."""
+    output_s, bpp_ori, _ = clean_pass(im_s, net, args)                      # :216-230
+    net.train()                                                             # :231
+    noise_range = args.epsilon / 255.0
+
+    def search_noise(noise_level):                                          # :142-192
+        noise = torch.zeros_like(im_s).requires_grad_(True)                 # :145-148
+        optimizer = torch.optim.Adam([noise], lr=args.lr_attack)            # :149
+        c_r, c_l = args.lamb_attack, 0.0
+        c = c_r
+        for _ in range(args.search_steps):                                  # :158
+            for _ in range(args.steps):                                     # :159
+                noise_clipped = up_bound(low_bound(noise, -noise_range), noise_range)
+                im_in = up_bound(low_bound(im_s + noise_clipped, 0.0), 1.0)
+                loss_i = torch.mean((im_s - im_in) ** 2)                    # :114
+                out = up_bound(low_bound(net.g_s(net.g_a(im_in)), 0.0), 1.0)
+                loss_o = 1.0 - torch.mean((output_s - out) * (output_s - out))   # :137
+                cc = 0.0 if float(1.0 - loss_o) > noise_level * 1.1 else c        # :138-139
+                loss = loss_i + cc * loss_o
+                optimizer.zero_grad()
+                loss.backward()
+                optimizer.step()
+            if record is not None:
+                record.append((noise_level, c, float(loss_i.detach()), float(1.0 - loss_o.detach())))
+            if float(1.0 - loss_o) < 0.99 * noise_level:                    # :186
+                c_l = c
+            else:
+                c_r = c
+            c = (c_r + c_l) / 2                                             # :190
+        return float(loss_i.detach()), im_in.detach()
+
+    min_noise, max_noise = args.noise, 0.1                                  # :232-234
+    noise_level = max_noise
+    loss_i = 0.0
+    search_cnt = 0
+    im_in = im_s
+    while search_cnt < args.search_steps:                                   # :239
+        loss_i_old = loss_i
+        loss_i, im_in = search_noise(noise_level)
+        if abs(loss_i - loss_i_old) < args.noise * 0.01 and abs(loss_i - args.noise) < args.noise * 0.1:   # :248
+            break
+        if loss_i > args.noise:
+            max_noise = noise_level
+        else:
+            min_noise = noise_level
+        noise_level = (min_noise + max_noise) / 2
+        search_cnt += 1
+    im_adv, output_adv, bpp, mse_results, vi_results = eval_metrics(im_in, im_s, output_s, net, args)
+    return im_adv, output_adv, output_s, bpp_ori, bpp, mse_results["mse_in"], mse_results["mse_out"], vi_results["vi"]
+
+
 def lr_schedule(steps, lr0=0.01, gamma=0.33):
     """LR used at iteration i under MultiStepLR([1,2,3]) stepped when i % (steps//3) == 0."""
     out, lr, n = [], lr0, 0
@@ -257,6 +313,28 @@ def adv_train_step(batch_x, net, args, criterion, optimizer, aux_optimizer):
     aux.backward()
     aux_optimizer.step()
     return out, aux
+
+
+def test_epoch(test_dataloader, model, criterion, args):
+    """train.py:196-242: mean VI over attacked batches under ``--adv`` (budget forced to 1e-4, :212-216), else the mean
+    RD loss.  Returns (value, dict of the other averages)."""
+    model.eval()
+    device = next(model.parameters()).device
+    vi, loss, bpp, dist, aux, n = 0.0, 0.0, 0.0, 0.0, 0.0, 0
+    for d in test_dataloader:
+        d = d.to(device)
+        if args.adv:
+            noise, args.noise = args.noise, 0.0001
+            vi += attack_(d, model, args)[-1]["vi"]
+            args.noise = noise
+        else:
+            with torch.no_grad():
+                out = criterion(model(d.detach()), d)
+                aux += float(model.aux_loss())
+                loss += float(out["loss"]); bpp += float(out["bpp_loss"]); dist += float(out["distortion_loss"])
+        n += 1
+    avg = {"loss": loss / n, "bpp_loss": bpp / n, "distortion_loss": dist / n, "aux_loss": aux / n, "vi": vi / n}
+    return (avg["vi"] if args.adv else avg["loss"]), avg
 
 
 # ---------------------------------------------------------------- synthetic inputs (SURVEY §8d)

@@ -1,0 +1,100 @@
+"""CompressAI / zoo checkpoint compatibility of the operator surface: host logic only, runs
+on CPU.  Reference: coder.py:104-116 (load), anchors/balle.py:57-72 + anchors/utils.py:46-109 (dynamic buffer resizing),
+train.py:443-454 (save_checkpoint round trip)."""
+import os
+import sys
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = os.path.join(ROOT, "baseline", "_ref", "reference")
+
+
+def _zoo_style(sd, model, new_names):
+    """What a CompressAI checkpoint of this model looks like: the parameters plus filled entropy-coder tables."""
+    out = {}
+    for k, v in sd.items():
+        if new_names:
+            for old, new in (("_matrix", "matrices."), ("_bias", "biases."), ("_factor", "factors.")):
+                k = k.replace("entropy_bottleneck." + old, "entropy_bottleneck." + new)
+        out[k] = v.clone()
+    C = sd["entropy_bottleneck.quantiles"].shape[0]
+    out["entropy_bottleneck._quantized_cdf"] = torch.arange(C * 37, dtype=torch.int32).reshape(C, 37)
+    out["entropy_bottleneck._offset"] = torch.full((C,), -17, dtype=torch.int32)
+    out["entropy_bottleneck._cdf_length"] = torch.full((C,), 37, dtype=torch.int32)
+    if model != "factorized":
+        out["gaussian_conditional._quantized_cdf"] = torch.arange(64 * 99, dtype=torch.int32).reshape(64, 99)
+        out["gaussian_conditional._offset"] = torch.full((64,), -48, dtype=torch.int32)
+        out["gaussian_conditional._cdf_length"] = torch.full((64,), 99, dtype=torch.int32)
+        out["gaussian_conditional.scale_table"] = torch.exp(torch.linspace(-2.2, 5.5, 64))
+    return out
+
+
+@pytest.mark.parametrize("model,quality", [("factorized", 1), ("hyper", 3), ("context", 4), ("cheng2020", 1)])
+@pytest.mark.parametrize("new_names", [False, True])
+def test_zoo_style_state_dict_loads_and_round_trips(model, quality, new_names):
+    from imagecompression_adversarial_b200 import models as pm
+    from oracle import models as om
+    onet = om.init_model(model, quality, seed=3)
+    zoo = _zoo_style(onet.state_dict(), model, new_names)
+    net = pm.init_model(model, quality, "mse", pretrained=False)
+    res = net.load_state_dict(zoo, strict=True)
+    assert not res.missing_keys and not res.unexpected_keys
+    sd = net.state_dict()
+    for k, v in onet.state_dict().items():          # every parameter arrived (old-style names are the canonical ones)
+        assert torch.equal(sd[k], v), k
+    for k, v in zoo.items():
+        if "cdf" in k or "_offset" in k or k.endswith("scale_table"):
+            assert sd[k].shape == v.shape and torch.equal(sd[k], v.to(sd[k].dtype)), k
+    # save_checkpoint / resume round trip (train.py:443-454, coder.py:104-108) into a FRESH model
+    net2 = pm.init_model(model, quality, "mse", pretrained=False)
+    res = net2.load_state_dict({"state_dict": sd}["state_dict"], strict=True)
+    assert not res.missing_keys and not res.unexpected_keys
+    for k, v in sd.items():
+        assert torch.equal(net2.state_dict()[k], v), k
+
+
+def test_plain_state_dict_without_tables_still_loads_strictly():
+    from imagecompression_adversarial_b200 import models as pm
+    from oracle import models as om
+    onet = om.init_model("hyper", 3, seed=0)
+    net = pm.init_model("hyper", 3, "mse", pretrained=False)
+    res = net.load_state_dict(onet.state_dict(), strict=True)
+    assert not res.missing_keys and not res.unexpected_keys
+    assert net.entropy_bottleneck._quantized_cdf.numel() == 0       # still empty: nothing to resize to
+    bad = dict(onet.state_dict())
+    bad.pop("g_a.0.weight")
+    with pytest.raises(RuntimeError):
+        net.load_state_dict(bad, strict=True)                       # real parameters stay mandatory
+
+
+def test_reference_update_registered_buffers_works_on_the_operator_surface():
+    """The reference's own helper (anchors/utils.py:75-109), unmodified, resizes this package's buffers the way
+    anchors/balle.py:57-72 calls it."""
+    if not os.path.exists(os.path.join(REF, "anchors", "utils.py")):
+        pytest.skip("no reference copy under baseline/_ref/reference")
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("_ref_anchor_utils", os.path.join(REF, "anchors", "utils.py"))
+    mod = importlib.util.module_from_spec(spec)
+    try:
+        spec.loader.exec_module(mod)
+    except ImportError as e:                                         # the file imports compressai at module level
+        from imagecompression_adversarial_b200 import launch
+        launch.install_shims()
+        spec.loader.exec_module(mod)
+    from imagecompression_adversarial_b200 import models as pm
+    from oracle import models as om
+    onet = om.init_model("hyper", 3, seed=1)
+    zoo = {"net." + k: v for k, v in _zoo_style(onet.state_dict(), "hyper", False).items()}
+    net = pm.init_model("hyper", 3, "mse", pretrained=False)
+    mod.update_registered_buffers(net.entropy_bottleneck, "net.entropy_bottleneck",
+                                  ["_quantized_cdf", "_offset", "_cdf_length"], zoo)
+    mod.update_registered_buffers(net.gaussian_conditional, "net.gaussian_conditional",
+                                  ["_quantized_cdf", "_offset", "_cdf_length", "scale_table"], zoo)
+    assert tuple(net.entropy_bottleneck._quantized_cdf.shape) == (128, 37)
+    assert tuple(net.gaussian_conditional.scale_table.shape) == (64,)
+    wrapper = torch.nn.Module()
+    wrapper.net = net
+    res = wrapper.load_state_dict(zoo, strict=True)
+    assert not res.missing_keys and not res.unexpected_keys

@@ -385,3 +385,36 @@ def test_context_q4_msssim_attack_runs_and_matches(dev):
         pb, pli, pl = int(rec[k][0][0]), float(rec[k][1][0]), float(rec[k][2][0])
         assert (pb == 1) == (br == "B"), (k, pb, br)
         assert abs(pl - loss) <= 2.5e-3 * abs(loss) + 1e-9, (k, pl, loss)
+
+
+def test_cw_search_matches_oracle(dev):
+    """the C&W-style double bisection of attack_cw.py (:111-263) on the fused engine vs the
+    oracle restatement, per block of iterations: (level, c) probed and (loss_i, MSE_o) reached.  Two images in one
+    batch carry independent search states; each is compared with the oracle run on that image alone."""
+    from imagecompression_adversarial_b200 import attack as patk
+    from oracle import attack as oatk
+    onet, pnet = pair("hyper", 3, dev)
+    x = images(2, 128, 192, dev)
+    args = oatk.default_args(model="hyper", quality=3, metric="mse", steps=6, search_steps=3, lamb_attack=0.2)
+    rec = []
+    p = patk.attack_cw(x, pnet, args, record=rec)
+    assert p[0].shape == x.shape and len(p) == 8
+    for i in range(2):
+        orec = []
+        o = oatk.attack_cw(x[i:i + 1], onet, args, record=orec)
+        diverged = False
+        for k, (lvl, c, loss_i, mse_o) in enumerate(orec):
+            if k >= len(rec):
+                break
+            plvl, pc, pli, pmo = float(rec[k][0][i]), float(rec[k][1][i]), float(rec[k][2][i]), float(rec[k][3][i])
+            if abs(plvl - lvl) > 1e-9 or abs(pc - c) > 1e-9:
+                # a bisection decision went the other way: only legitimate on a near-tie of the previous block
+                _, _, li0, mo0 = orec[k - 1]
+                lv0 = orec[k - 1][0]
+                assert (abs(mo0 - 0.99 * lv0) < 5e-3 * lv0 or abs(li0 - args.noise) < 5e-3 * args.noise), (i, k, orec[k - 1])
+                diverged = True
+                break
+            assert abs(pli - loss_i) <= 5e-3 * max(loss_i, 1e-7) + 1e-9, (i, k, pli, loss_i)
+            assert abs(pmo - mse_o) <= 5e-3 * max(mse_o, 1e-7) + 1e-9, (i, k, pmo, mse_o)
+        if not diverged and i == 0 and len(orec) == len(rec):
+            assert abs(psnr(p[0][i:i + 1], x[i:i + 1]) - psnr(o[0], x[i:i + 1])) < 0.05

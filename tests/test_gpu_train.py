@@ -275,3 +275,27 @@ def test_msssim_distortion_term_matches_oracle(dev):
     assert abs(p[0] - o[0]) <= 1e-4 * abs(o[0]) and abs(p[1] - o[1]) <= 2e-5 and abs(p[2] - o[2]) <= 1e-5 * abs(o[2])
     assert rel(p[3], o[3]) < 3e-3, rel(p[3], o[3])
     assert rel(p[4], o[4]) < 1e-5, rel(p[4], o[4])
+
+
+@pytest.mark.parametrize("adv", [False, True])
+def test_test_epoch_matches_oracle(dev, tmp_path, adv):
+    """train.py:196-242: RD-loss averages without --adv, mean VI of the attacked batches with it."""
+    from imagecompression_adversarial_b200 import models as pm
+    from imagecompression_adversarial_b200 import training as ptr
+    from oracle import attack as oatk
+    from oracle import models as om
+    from oracle.attack import synthetic_image
+    onet = om.init_model("hyper", 1, seed=0).to(dev)
+    pnet = pm.init_model("hyper", 1, "mse", pretrained=False).to(dev)
+    pnet.load_state_dict(onet.state_dict())
+    loader = [torch.cat([synthetic_image(2 * b + i, 192, 192) for i in range(2)]) for b in range(2)]
+    args = oatk.default_args(model="hyper", quality=1, metric="mse", steps=6, adv=adv, noise=1e-3)
+    log = str(tmp_path / "log.txt")
+    p = ptr.test_epoch(0, loader, pnet, ptr.RateDistortionLoss(metric="mse", lmbda=0.0018), log, args)
+    o, avg = oatk.test_epoch(loader, onet, oatk.RateDistortionLoss(metric="mse", lmbda=0.0018), args)
+    assert args.noise == 1e-3                                             # the forced budget is restored (:216)
+    assert "Test epoch 0" in open(log).read()
+    if adv:
+        assert abs(p - o) < 0.1, (p, o)                                   # VI in dB over a 6-step attack
+    else:
+        assert abs(p - o) <= 2e-3 * abs(o), (p, o)
