@@ -394,7 +394,7 @@ def test_cw_search_matches_oracle(dev):
     from imagecompression_adversarial_b200 import attack as patk
     from oracle import attack as oatk
     onet, pnet = pair("hyper", 3, dev)
-    x = images(2, 128, 192, dev)
+    x = images(2, 192, 256, dev)   # > 160: the final eval computes MS-SSIM
     args = oatk.default_args(model="hyper", quality=3, metric="mse", steps=6, search_steps=3, lamb_attack=0.2)
     rec = []
     p = patk.attack_cw(x, pnet, args, record=rec)
