@@ -72,6 +72,7 @@ struct TcParams {
   const float* beta;
   const int* active;
   const int* n_active;
+  int bwd_lookahead;   // backward epilogues: L2-prefetch the saved tensors of the CTA this many launch slots ahead (0 = off)
   int dbg_flags;    // developer switches (env ICADV_TC_DBG): 1 = no prefetch of saved y/scale, 2 = single-buffered stores
   long long* dbg;   // optional per-CTA phase timestamps (16 slots per CTA), developer profiling only
 };
@@ -196,6 +197,22 @@ __global__ void __launch_bounds__(kThreads, 2) conv_tc_kernel(const __grid_const
             tma_prefetch_4d(&p.yprev_map, c * 32, j0, i0, img);
             tma_prefetch_4d(&p.scprev_map, c * 32, j0, i0, img);
           }
+        // Lookahead: the saved y / scale of the tile that will run `bwd_lookahead` CTAs after this one (about two waves
+        // later) are pulled into L2 now, so that tile's pass-1 chunk loads are L2 hits (1.35 us per chunk) instead of DRAM
+        // round trips (2.3 us per chunk; profiles/r1_tile_timeline_bwd_v10.txt)
+        if (p.bwd_lookahead > 0 && lane == 0) {
+          const long long lin = (long long)blockIdx.y * gridDim.x + blockIdx.x + p.bwd_lookahead;
+          const int slot2 = (int)(lin / gridDim.x), tile2 = (int)(lin % gridDim.x);
+          const int n_slots = p.n_active != nullptr ? *p.n_active : (int)gridDim.y;
+          if (slot2 < n_slots) {
+            const int img2 = p.active != nullptr ? p.active[slot2] : slot2;
+            const int i2 = (tile2 / p.tiles_x) * p.tile_step_y + p.tile_off, j2 = (tile2 % p.tiles_x) * p.tile_step_x + p.tile_off;
+            for (int c = 0; c < p.n_chunks; ++c) {
+              tma_prefetch_4d(&p.yprev_map, c * 32, j2, i2, img2);
+              tma_prefetch_4d(&p.scprev_map, c * 32, j2, i2, img2);
+            }
+          }
+        }
       }
       int s = 0, ps = 0;
       uint32_t s_par = 1, p_par = 1;          // parity to wait for on the "empty" barriers (first pass: free)
@@ -1663,6 +1680,7 @@ int icadv_conv_plan_create(const icadv_conv_desc* d, icadv_conv_plan** out_plan)
     else { p.o_s = 1; p.o_a = 0; p.o_b = 0; }
     p.yprev = d->y_prev; p.scprev = d->sc_prev; p.xin = d->in;
     p.dbg_flags = getenv("ICADV_TC_DBG") ? atoi(getenv("ICADV_TC_DBG")) : 0;
+    p.bwd_lookahead = bwd ? (getenv("ICADV_TC_LOOKAHEAD") ? atoi(getenv("ICADV_TC_LOOKAHEAD")) : 0) : 0;
     // ---- shared memory: [patch ring | weight ring | BWD staging | barriers + bias/beta].  Aim for two CTAs per SM
     //      (their prologue / epilogue overlap each other's main loop).
     p.patch_bytes = (max_patch + 1023) & ~1023;

@@ -75,3 +75,17 @@ o5 = torch.empty(n, H, W, 3, device=dev)
 b5 = torch.zeros(3, device=dev)
 d = ops.make_desc(x5, w5, b5, o5, form=L.FORM_TCONV, ksize=5, stride=2, n_ch=3)
 run("g_s.6 col2im", d, (x5, w5, o5, b5), 1204 * n)
+# g_s.6 dgrad: rgb_in conv + IGDN backward (per-tile kernel, two CTAs per SM)
+yp = torch.randn(n, H // 2, W // 2, 128, device=dev)
+sp = 0.5 + torch.rand(n, H // 2, W // 2, 128, device=dev)
+go = torch.empty(n, H // 2, W // 2, 128, device=dev)
+d = ops.make_desc(pad, wp, None, go, form=L.FORM_SCONV, ksize=5, stride=2, n_ch=128, epi=L.EPI_IGDN_BWD, gmat=gm,
+                  y_prev=yp, sc_prev=sp, in_pad4=True)
+run("g_s.6 dgrad rgb_in + IGDN bwd", d, (pad, wp, go, yp, sp), 768 * n)
+# g_s.4 dgrad: stride-2 conv + IGDN backward
+yp2 = torch.randn(n, H // 4, W // 4, 128, device=dev)
+sp2 = 0.5 + torch.rand(n, H // 4, W // 4, 128, device=dev)
+go2 = torch.empty(n, H // 4, W // 4, 128, device=dev)
+d = ops.make_desc(x2, w2, None, go2, form=L.FORM_SCONV, ksize=5, stride=2, n_ch=128, epi=L.EPI_IGDN_BWD, gmat=gm,
+                  y_prev=yp2, sc_prev=sp2)
+run("g_s.4 dgrad conv + IGDN bwd", d, (x2, w2, go2, yp2, sp2), 192 * n)
