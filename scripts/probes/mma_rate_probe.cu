@@ -277,6 +277,76 @@ static void run_contend(const char* name, int lsw, int mode) {
   cudaFree(d_out); cudaFree(d_sink);
 }
 
+// Issue loops of ONE thread (the whole loop inside one elect.sync block, as the kernels run it) with runtime descriptors:
+// FEAT bit 0 = descriptors depend on a per-iteration register value (R2UR), bit 1 = tcgen05.commit per 4 MMAs,
+// bit 2 = mbarrier.test_wait probe per 4 MMAs, bit 3 = tcgen05.fence::after_thread_sync per 4 MMAs.
+template <int FEAT>
+__global__ void __launch_bounds__(128) probe_thread(int iters, int stride_rt, long long* out) {
+  extern __shared__ uint8_t raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* A = smem;
+  uint8_t* B = smem + 4 * 16384;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(B + 4 * 16384);
+  uint32_t* tptr = reinterpret_cast<uint32_t*>(bar + 8);
+  const int warp = threadIdx.x >> 5;
+  for (int i = threadIdx.x; i < 8 * 16384 / 4; i += 128) reinterpret_cast<float*>(smem)[i] = 1e-3f * (float)((i * 37) & 255);
+  if (threadIdx.x == 0) { for (int i = 0; i < 8; ++i) mbar_init(&bar[i], 1); mbar_fence_init(); }
+  if (warp == 0) { tmem_alloc(tptr, 128); tmem_relinquish(); }
+  fence_proxy_async_smem();
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem = *tptr;
+  if (warp == 0) {
+    if (elect_one_sync()) {
+      const uint32_t idesc = umma_idesc_tf32(128, 128);
+      const uint32_t hi = (1024u >> 4) | (1u << 14) | (2u << 29);
+      const uint32_t a_lo0 = ((smem_u32(A) >> 4) & 0x3FFFu) | (1u << 16);
+      const uint32_t b_lo0 = ((smem_u32(B) >> 4) & 0x3FFFu) | (1u << 16);
+      mbar_arrive(&bar[1]);                       // bar[1]: phase 0 complete -> the probes below succeed at once
+      int s = 0;
+      uint32_t seen = 0;
+      const long long t0 = clock64();
+      for (int i = 0; i < iters; i += 4) {
+        const uint32_t off = (FEAT & 1) ? static_cast<uint32_t>(s) * static_cast<uint32_t>(stride_rt) : 0u;
+        const uint64_t ad = (static_cast<uint64_t>(hi) << 32) | (a_lo0 + off);
+        const uint64_t bd = (static_cast<uint64_t>(hi) << 32) | (b_lo0 + off);
+        if (FEAT & 8) tc_fence_after_sync();
+        tc_mma_tf32(tmem, ad, bd, idesc, 1u);
+        tc_mma_tf32(tmem, ad + 2, bd + 2, idesc, 1u);
+        tc_mma_tf32(tmem, ad + 4, bd + 4, idesc, 1u);
+        tc_mma_tf32(tmem, ad + 6, bd + 6, idesc, 1u);
+        if (FEAT & 2) tc_commit(&bar[2 + (s & 1)]);
+        if (FEAT & 4) seen += mbar_test_wait(&bar[1], 0) ? 1u : 0u;
+        if (++s == 4) s = 0;
+      }
+      tc_commit(&bar[0]);
+      mbar_wait(&bar[0], 0);
+      out[blockIdx.x] = clock64() - t0 + (seen == 0xffffffffu ? 1 : 0);
+    }
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 128);
+}
+
+template <int FEAT>
+static void run_thread(const char* name) {
+  const int iters = 2048, smem = 8 * 16384 + 128 + 1024;
+  long long* d_out;
+  cudaMalloc(&d_out, 148 * sizeof(long long));
+  cudaFuncSetAttribute(probe_thread<FEAT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  for (int rep = 0; rep < 2; ++rep) probe_thread<FEAT><<<148, 128, smem>>>(iters, 1024, d_out);
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) { printf("%-58s CUDA error: %s\n", name, cudaGetErrorString(e)); exit(1); }
+  std::vector<long long> h(148);
+  cudaMemcpy(h.data(), d_out, 148 * sizeof(long long), cudaMemcpyDeviceToHost);
+  double sum = 0;
+  for (int b = 0; b < 148; ++b) sum += (double)h[b];
+  printf("%-58s %7.1f cyc/MMA/SM  (floor 64.0)\n", name, sum / 148 / iters);
+  cudaFree(d_out);
+}
+
 static void run(const char* name, Cfg c, int ctas_per_sm) {
   const int b_rows = c.n / c.cg;
   int smem = c.nbuf * (128 * 128 + b_rows * 128) + 128 + 1024;
@@ -319,6 +389,13 @@ static void run(const char* name, Cfg c, int ctas_per_sm) {
 
 int main() {
   const int L = 2048;
+  run_thread<0>("one thread: constant descriptors");
+  run_thread<1>("one thread: runtime descriptors (R2UR)");
+  run_thread<3>("one thread: runtime descriptors + commit per 4");
+  run_thread<5>("one thread: runtime descriptors + test_wait per 4");
+  run_thread<9>("one thread: runtime descriptors + fence per 4");
+  run_thread<15>("one thread: runtime descriptors + commit + test_wait + fence");
+  run_thread<2>("one thread: constant descriptors + commit per 4");
   run("cg1 N=128 1 issuer, per 4 MMAs: wait only", Cfg{128, 4, L, 1, 1, 1, 0, 4, 0, 1}, 1);
   run("cg1 N=128 1 issuer, per 4 MMAs: fence only", Cfg{128, 4, L, 1, 1, 1, 0, 4, 0, 2}, 1);
   run("cg1 N=128 1 issuer, per 4 MMAs: commit only", Cfg{128, 4, L, 1, 1, 1, 0, 4, 0, 4}, 1);
