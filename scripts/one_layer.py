@@ -22,6 +22,9 @@ small = lambda s: torch.randn(n, H // 4, W // 4, Cc, device=dev, generator=gen(s
 if which == "gs4_fwd":     # deconv 128->128 + IGDN forward, 128x192 -> 256x384
     x, out, sc = small(1), big(7), big(8)
     d = ops.make_desc(x, w, beta, out, form=L.FORM_TCONV, ksize=5, stride=2, n_ch=Cc, epi=L.EPI_IGDN_FWD, gmat=gm, beta=beta, out_scale=sc)
+elif which == "gs4_lin":   # deconv 128->128, linear epilogue (developer experiments)
+    x, out = small(1), big(7)
+    d = ops.make_desc(x, w, beta, out, form=L.FORM_TCONV, ksize=5, stride=2, n_ch=Cc, epi=L.EPI_LINEAR)
 elif which == "ga2_bwd":   # dgrad of conv 128->128 (a transposed conv) + GDN backward of the layer below
     x, yp, sp, out = small(1), big(3), 0.5 + torch.rand(n, H // 2, W // 2, Cc, device=dev, generator=gen(4)), big(9)
     d = ops.make_desc(x, w, None, out, form=L.FORM_TCONV, ksize=5, stride=2, n_ch=Cc, epi=L.EPI_GDN_BWD, gmat=gm, y_prev=yp, sc_prev=sp)

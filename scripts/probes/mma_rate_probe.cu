@@ -281,7 +281,7 @@ static void run_contend(const char* name, int lsw, int mode) {
 // FEAT bit 0 = descriptors depend on a per-iteration register value (R2UR), bit 1 = tcgen05.commit per 4 MMAs,
 // bit 2 = mbarrier.test_wait probe per 4 MMAs, bit 3 = tcgen05.fence::after_thread_sync per 4 MMAs.
 template <int FEAT>
-__global__ void __launch_bounds__(128) probe_thread(int iters, int stride_rt, long long* out) {
+__global__ void __launch_bounds__(128) probe_thread(int iters, int stride_rt, int a_sbo, int a_shift_rows, long long* out) {
   extern __shared__ uint8_t raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~uintptr_t(1023));
   uint8_t* A = smem;
@@ -301,7 +301,8 @@ __global__ void __launch_bounds__(128) probe_thread(int iters, int stride_rt, lo
     if (elect_one_sync()) {
       const uint32_t idesc = umma_idesc_tf32(128, 128);
       const uint32_t hi = (1024u >> 4) | (1u << 14) | (2u << 29);
-      const uint32_t a_lo0 = ((smem_u32(A) >> 4) & 0x3FFFu) | (1u << 16);
+      const uint32_t a_hi = (static_cast<uint32_t>(a_sbo) >> 4) | (1u << 14) | (2u << 29);   // halo patch: tile rows a_sbo bytes apart
+      const uint32_t a_lo0 = (((smem_u32(A) + a_shift_rows * 128) >> 4) & 0x3FFFu) | (1u << 16);
       const uint32_t b_lo0 = ((smem_u32(B) >> 4) & 0x3FFFu) | (1u << 16);
       mbar_arrive(&bar[1]);                       // bar[1]: phase 0 complete -> the probes below succeed at once
       int s = 0;
@@ -309,7 +310,7 @@ __global__ void __launch_bounds__(128) probe_thread(int iters, int stride_rt, lo
       const long long t0 = clock64();
       for (int i = 0; i < iters; i += 4) {
         const uint32_t off = (FEAT & 1) ? static_cast<uint32_t>(s) * static_cast<uint32_t>(stride_rt) : 0u;
-        const uint64_t ad = (static_cast<uint64_t>(hi) << 32) | (a_lo0 + off);
+        const uint64_t ad = (static_cast<uint64_t>(a_hi) << 32) | (a_lo0 + ((FEAT & 16) ? static_cast<uint32_t>(s) * 8u : off));
         const uint64_t bd = (static_cast<uint64_t>(hi) << 32) | (b_lo0 + off);
         if (FEAT & 8) tc_fence_after_sync();
         tc_mma_tf32(tmem, ad, bd, idesc, 1u);
@@ -331,12 +332,176 @@ __global__ void __launch_bounds__(128) probe_thread(int iters, int stride_rt, lo
 }
 
 template <int FEAT>
-static void run_thread(const char* name) {
+static void run_thread(const char* name, int a_sbo = 1024, int a_shift = 0) {
   const int iters = 2048, smem = 8 * 16384 + 128 + 1024;
   long long* d_out;
   cudaMalloc(&d_out, 148 * sizeof(long long));
   cudaFuncSetAttribute(probe_thread<FEAT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-  for (int rep = 0; rep < 2; ++rep) probe_thread<FEAT><<<148, 128, smem>>>(iters, 1024, d_out);
+  for (int rep = 0; rep < 2; ++rep) probe_thread<FEAT><<<148, 128, smem>>>(iters, 1024, a_sbo, a_shift, d_out);
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) { printf("%-58s CUDA error: %s\n", name, cudaGetErrorString(e)); exit(1); }
+  std::vector<long long> h(148);
+  cudaMemcpy(h.data(), d_out, 148 * sizeof(long long), cudaMemcpyDeviceToHost);
+  double sum = 0;
+  for (int b = 0; b < 148; ++b) sum += (double)h[b];
+  printf("%-58s %7.1f cyc/MMA/SM  (floor 64.0)\n", name, sum / 148 / iters);
+  cudaFree(d_out);
+}
+
+// TMEM contention: warp 0 issues the bare N = 128 MMA stream into columns [0,128); warps 4-7 (one per lane quadrant) read
+// columns [128,256) with tcgen05.ld 32x32b.x32 in a loop, as the epilogue warpgroups do while the next item's main loop runs.
+__global__ void __launch_bounds__(256) probe_tmem(int iters, int readers, long long* out, float* sink) {
+  extern __shared__ uint8_t raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* A = smem;
+  uint8_t* B = smem + 4 * 16384;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(B + 4 * 16384);
+  uint32_t* tptr = reinterpret_cast<uint32_t*>(bar + 8);
+  volatile int* stop = reinterpret_cast<volatile int*>(tptr + 2);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < 8 * 16384 / 4; i += blockDim.x) reinterpret_cast<float*>(smem)[i] = 1e-3f * (float)((i * 37) & 255);
+  if (threadIdx.x == 0) { mbar_init(&bar[0], 1); mbar_fence_init(); *stop = 0; }
+  if (warp == 0) { tmem_alloc(tptr, 256); tmem_relinquish(); }
+  fence_proxy_async_smem();
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem = *tptr;
+  if (warp == 0) {
+    if (elect_one_sync()) {
+      const uint32_t idesc = umma_idesc_tf32(128, 128);
+      const uint32_t hi = (1024u >> 4) | (1u << 14) | (2u << 29);
+      const uint32_t a_lo0 = ((smem_u32(A) >> 4) & 0x3FFFu) | (1u << 16);
+      const uint32_t b_lo0 = ((smem_u32(B) >> 4) & 0x3FFFu) | (1u << 16);
+      const long long t0 = clock64();
+      for (int i = 0; i < iters; i += 4) {
+        const uint32_t off = static_cast<uint32_t>((i >> 2) & 3) * 1024u;
+        const uint64_t ad = (static_cast<uint64_t>(hi) << 32) | (a_lo0 + off), bd = (static_cast<uint64_t>(hi) << 32) | (b_lo0 + off);
+        tc_mma_tf32(tmem, ad, bd, idesc, 1u); tc_mma_tf32(tmem, ad + 2, bd + 2, idesc, 1u);
+        tc_mma_tf32(tmem, ad + 4, bd + 4, idesc, 1u); tc_mma_tf32(tmem, ad + 6, bd + 6, idesc, 1u);
+      }
+      tc_commit(&bar[0]);
+      mbar_wait(&bar[0], 0);
+      out[blockIdx.x * 2] = clock64() - t0;
+      *stop = 1;
+    }
+  } else if (warp >= 4 && warp < 4 + readers) {
+    const int q = warp & 3;
+    const uint32_t t_lane = tmem + (static_cast<uint32_t>(q * 32) << 16) + 128;
+    float acc = 0.f;
+    long long n = 0;
+    while (!*stop) {
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        float v[32];
+        tmem_ld32(t_lane + c * 32, v);
+        tmem_ld_wait();
+        acc += v[0] + v[31];
+      }
+      n += 4;
+    }
+    if (lane == 0) atomicAdd(reinterpret_cast<unsigned long long*>(&out[blockIdx.x * 2 + 1]), (unsigned long long)n);
+    if (acc == 123.456f) sink[0] = acc;
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 256);
+}
+
+static void run_tmem(const char* name, int readers) {
+  const int iters = 4096, smem = 8 * 16384 + 256 + 1024;
+  long long* d_out; float* d_sink;
+  cudaMalloc(&d_out, 148 * 2 * sizeof(long long));
+  cudaMalloc(&d_sink, 16);
+  cudaFuncSetAttribute(probe_tmem, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  for (int rep = 0; rep < 2; ++rep) { cudaMemset(d_out, 0, 148 * 2 * sizeof(long long)); probe_tmem<<<148, 256, smem>>>(iters, readers, d_out, d_sink); }
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) { printf("%-58s CUDA error: %s\n", name, cudaGetErrorString(e)); exit(1); }
+  std::vector<long long> h(148 * 2);
+  cudaMemcpy(h.data(), d_out, 148 * 2 * sizeof(long long), cudaMemcpyDeviceToHost);
+  double cyc = 0, ins = 0;
+  for (int b = 0; b < 148; ++b) { cyc += (double)h[2 * b]; ins += (double)h[2 * b + 1]; }
+  cyc /= 148; ins /= 148;
+  printf("%-58s %7.1f cyc/MMA  | readers: %6.1f B/clk of tcgen05.ld (32 lanes x 32 columns x 4 B per instruction)\n", name,
+         cyc / iters, ins * 4096.0 / cyc);
+  cudaFree(d_out); cudaFree(d_sink);
+}
+
+// The kernels' issue loop, re-created feature by feature on pre-armed barriers (nobody produces or consumes):
+// FEAT bit 0 = tap offsets from a kernel-parameter table with a register index (LDC), bit 1 = ring bookkeeping with wrap
+// (stage index, parity, descriptor base), bit 2 = a commit to a ROTATING barrier per K-block + early test_wait probe of the
+// next stage (barriers re-armed by the commits themselves), bit 3 = per-group patch wait + commit every 6 K-blocks.
+struct ProbeTable { int32_t aoff[40]; int32_t S; int32_t pad[7]; };
+template <int FEAT>
+__global__ void __launch_bounds__(128) probe_loop(const __grid_constant__ ProbeTable tb, int iters, long long* out) {
+  extern __shared__ uint8_t raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* A = smem;
+  uint8_t* B = smem + 4 * 16384;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(B + 4 * 16384);   // [0] done, [1..8] "full" ring, [9..16] "empty" ring, [17] patch
+  uint32_t* tptr = reinterpret_cast<uint32_t*>(bar + 20);
+  const int warp = threadIdx.x >> 5;
+  for (int i = threadIdx.x; i < 8 * 16384 / 4; i += 128) reinterpret_cast<float*>(smem)[i] = 1e-3f * (float)((i * 37) & 255);
+  if (threadIdx.x == 0) { for (int i = 0; i < 20; ++i) mbar_init(&bar[i], 1); mbar_fence_init(); }
+  if (warp == 0) { tmem_alloc(tptr, 128); tmem_relinquish(); }
+  fence_proxy_async_smem();
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem = *tptr;
+  if (warp == 0) {
+    if (elect_one_sync()) {
+      const uint32_t idesc = umma_idesc_tf32(128, 128);
+      const uint32_t hi = (1024u >> 4) | (1u << 14) | (2u << 29);
+      const uint32_t a_hi = (1280u >> 4) | (1u << 14) | (2u << 29);
+      const uint32_t a_lo0 = ((smem_u32(A) >> 4) & 0x3FFFu) | (1u << 16);
+      const uint32_t w_lo0 = ((smem_u32(B) >> 4) & 0x3FFFu) | (1u << 16);
+      const int S = tb.S;
+      uint64_t* full = bar + 1;
+      uint64_t* empty = bar + 9;
+      // "full" barriers: the commit of iteration k on full[s] re-arms it for the probe of iteration k + S (self-feeding)
+      for (int i = 0; i < S; ++i) mbar_arrive(&full[i]);
+      int s = 0, t = 0;
+      uint32_t s_par = 0, w_lo = w_lo0, aoff = (FEAT & 1) ? static_cast<uint32_t>(tb.aoff[0]) >> 4 : 0u;
+      bool w_ok = false;
+      const long long t0 = clock64();
+      for (int i = 0; i < iters; i += 4) {
+        if ((FEAT & 8) && t == 0) mbar_wait(&full[(s + 1 == S) ? 0 : s + 1], s_par ^ ((s + 1 == S) ? 1u : 0u) ^ 0u) ;
+        const uint64_t ad = (static_cast<uint64_t>(a_hi) << 32) | (a_lo0 + aoff);
+        const uint64_t bd = (static_cast<uint64_t>(hi) << 32) | w_lo;
+        if ((FEAT & 4) && !w_ok) mbar_wait(&full[s], s_par);
+        uint64_t* wdone = (FEAT & 4) ? &full[s] : &empty[s];
+        if (FEAT & 2) { if (++s == S) { s = 0; s_par ^= 1; w_lo = w_lo0; } else { w_lo += 1024u; } }
+        tc_fence_after_sync();
+        tc_mma_tf32(tmem, ad, bd, idesc, 1u);
+        tc_mma_tf32(tmem, ad + 2, bd + 2, idesc, 1u);
+        tc_mma_tf32(tmem, ad + 4, bd + 4, idesc, 1u);
+        tc_mma_tf32(tmem, ad + 6, bd + 6, idesc, 1u);
+        tc_commit(wdone);
+        if (++t == 6) { t = 0; if (FEAT & 8) tc_commit(&bar[17]); }
+        if (FEAT & 1) aoff = static_cast<uint32_t>(tb.aoff[t + 1]) >> 4;
+        if (FEAT & 4) w_ok = mbar_test_wait(&full[s], s_par);
+      }
+      tc_commit(&bar[0]);
+      mbar_wait(&bar[0], 0);
+      out[blockIdx.x] = clock64() - t0;
+    }
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 128);
+}
+
+template <int FEAT>
+static void run_loop(const char* name) {
+  const int iters = 2048, smem = 8 * 16384 + 256 + 1024;
+  ProbeTable tb;
+  for (int i = 0; i < 40; ++i) tb.aoff[i] = ((i % 3) * 10 + (i % 2)) * 128;
+  tb.S = 3;
+  long long* d_out;
+  cudaMalloc(&d_out, 148 * sizeof(long long));
+  cudaFuncSetAttribute(probe_loop<FEAT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  for (int rep = 0; rep < 2; ++rep) probe_loop<FEAT><<<148, 128, smem>>>(tb, iters, d_out);
   cudaError_t e = cudaDeviceSynchronize();
   if (e != cudaSuccess) { printf("%-58s CUDA error: %s\n", name, cudaGetErrorString(e)); exit(1); }
   std::vector<long long> h(148);
@@ -389,6 +554,19 @@ static void run(const char* name, Cfg c, int ctas_per_sm) {
 
 int main() {
   const int L = 2048;
+  run_loop<0>("kernel-like loop: bare (commit per K-block)");
+  run_loop<1>("kernel-like loop: + LDC tap offsets");
+  run_loop<3>("kernel-like loop: + LDC + ring bookkeeping");
+  run_loop<7>("kernel-like loop: + LDC + ring + barrier wait/probe");
+  run_loop<6>("kernel-like loop: ring + barrier wait/probe (no LDC)");
+  run_tmem("MMA stream, no TMEM readers", 0);
+  run_tmem("MMA stream + 1 warp tcgen05.ld", 1);
+  run_tmem("MMA stream + 2 warps tcgen05.ld", 2);
+  run_tmem("MMA stream + 4 warps tcgen05.ld (one epilogue group)", 4);
+  run_thread<31>("one thread: halo-patch A (SBO 1280 B, start +13 rows, shifting)", 1280, 13);
+  run_thread<31>("one thread: halo-patch A (SBO 2304 B, start +19 rows, shifting)", 2304, 19);
+  run_thread<15>("one thread: A with SBO 1280 B, start +0", 1280, 0);
+  run_thread<15>("one thread: A dense (SBO 1024), start +3 rows", 1024, 3);
   run_thread<0>("one thread: constant descriptors");
   run_thread<1>("one thread: runtime descriptors (R2UR)");
   run_thread<3>("one thread: runtime descriptors + commit per 4");

@@ -43,6 +43,71 @@ __global__ void __launch_bounds__(128) probe(const __grid_constant__ CUtensorMap
   }
 }
 
+
+// Shared-memory contention between the tensor core's operand reads and TMA fills: warp 0 issues the bare tcgen05.mma stream
+// (kind::tf32, M = 128, N = 128: 8 KB of operand reads per 64-cycle MMA = 128 B/clk), warps 1..nw stream 16 KB boxes into a
+// separate ring of the same shared memory (each issuing thread ~33 B/clk, see above).
+__global__ void __launch_bounds__(160) probe_mix(const __grid_constant__ CUtensorMap map, int iters, int nw, int n_boxes_total, int nmma,
+                                                 long long* out) {
+  extern __shared__ uint8_t raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* A = smem;                       // 2 x 16 KB
+  uint8_t* B = smem + 2 * 16384;           // 2 x 32 KB (N up to 256)
+  uint8_t* R = smem + 6 * 16384;           // TMA rings: 4 warps x 2 slots x 16 KB
+  uint64_t* bar = reinterpret_cast<uint64_t*>(R + 8 * 16384);
+  uint32_t* tptr = reinterpret_cast<uint32_t*>(bar + 12);
+  volatile int* stop = reinterpret_cast<volatile int*>(tptr + 2);
+  const int warp = threadIdx.x >> 5;
+  for (int i = threadIdx.x; i < 6 * 16384 / 4; i += blockDim.x) reinterpret_cast<float*>(smem)[i] = 1e-3f * (float)((i * 37) & 255);
+  if (threadIdx.x == 0) { for (int i = 0; i < 12; ++i) mbar_init(&bar[i], 1); mbar_fence_init(); *stop = 0; }
+  if (warp == 0) { tmem_alloc(tptr, 256); tmem_relinquish(); }
+  fence_proxy_async_smem();
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem = *tptr;
+  if (warp == 0) {
+    if (elect_one_sync()) {
+      const uint32_t idesc = umma_idesc_tf32(128, nmma);
+      const uint32_t hi = (1024u >> 4) | (1u << 14) | (2u << 29);
+      const uint32_t a_lo0 = ((smem_u32(A) >> 4) & 0x3FFFu) | (1u << 16);
+      const uint32_t b_lo0 = ((smem_u32(B) >> 4) & 0x3FFFu) | (1u << 16);
+      const long long t0 = clock64();
+      for (int i = 0; i < iters; i += 4) {
+        const uint32_t sel = static_cast<uint32_t>((i >> 2) & 1);
+        const uint64_t ad = (static_cast<uint64_t>(hi) << 32) | (a_lo0 + sel * 1024u), bd = (static_cast<uint64_t>(hi) << 32) | (b_lo0 + sel * 2048u);
+        tc_mma_tf32(tmem, ad, bd, idesc, 1u); tc_mma_tf32(tmem, ad + 2, bd + 2, idesc, 1u);
+        tc_mma_tf32(tmem, ad + 4, bd + 4, idesc, 1u); tc_mma_tf32(tmem, ad + 6, bd + 6, idesc, 1u);
+      }
+      tc_commit(&bar[0]);
+      mbar_wait(&bar[0], 0);
+      out[blockIdx.x * 2] = clock64() - t0;
+      *stop = 1;
+    }
+  } else if (warp <= nw) {
+    if (elect_one_sync()) {
+      uint64_t* mybar = bar + 2 + (warp - 1) * 2;
+      uint8_t* ring = R + (warp - 1) * 2 * 16384;
+      long long n = 0;
+      int i = 0;
+      while (!*stop) {
+        const int s = i & 1;
+        if (i >= 2) mbar_wait(&mybar[s], ((i >> 1) - 1) & 1);
+        const int box = (int)(((long long)(blockIdx.x * 4 + warp) * 4096 + i) % n_boxes_total);
+        mbar_arrive_expect_tx(&mybar[s], 16384);
+        tma_load_2d(ring + s * 16384, &map, &mybar[s], 0, box * 128);
+        ++i; ++n;
+      }
+      // drain the loads still in flight before the CTA exits
+      for (int k = i > 2 ? i - 2 : 0; k < i; ++k) mbar_wait(&mybar[k & 1], (k >> 1) & 1);
+      atomicAdd(reinterpret_cast<unsigned long long*>(&out[blockIdx.x * 2 + 1]), (unsigned long long)n);
+    }
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 256);
+}
+
 int main() {
   void* fp = nullptr;
   cudaDriverEntryPointQueryResult q;
@@ -56,6 +121,32 @@ int main() {
   cudaMemset(buf, 0, big);
   long long* d_out;
   cudaMalloc(&d_out, 296 * 8);
+  {
+    const size_t set = (size_t)64 << 20;
+    cuuint64_t dims[2] = {32, set / 512};
+    cuuint64_t strd[1] = {512};
+    cuuint32_t box[2] = {32, 128}, es[2] = {1, 1};
+    CUtensorMap map;
+    enc(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, buf, dims, strd, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    const int smem = 14 * 16384 + 256 + 1024, iters = 8192;
+    cudaFuncSetAttribute(probe_mix, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    for (int nmma : {128, 256})
+      for (int nw = 0; nw <= 4; ++nw) {
+        for (int rep = 0; rep < 2; ++rep) { cudaMemset(d_out, 0, 296 * 8); probe_mix<<<148, 160, smem>>>(map, iters, nw, (int)(set / 512 / 128), nmma, d_out); }
+        cudaError_t e = cudaDeviceSynchronize();
+        if (e != cudaSuccess) { printf("CUDA error: %s\n", cudaGetErrorString(e)); return 1; }
+        e = cudaGetLastError();
+        if (e != cudaSuccess) { printf("launch error: %s\n", cudaGetErrorString(e)); return 1; }
+        std::vector<long long> h(296);
+        cudaMemcpy(h.data(), d_out, 296 * 8, cudaMemcpyDeviceToHost);
+        double cyc = 0, nb = 0;
+        for (int b = 0; b < 148; ++b) { cyc += (double)h[2 * b]; nb += (double)h[2 * b + 1]; }
+        cyc /= 148; nb /= 148;
+        printf("MMA N=%3d stream + %d TMA-issuing warps: %6.1f cycles per MMA (alone: %3d) | TMA fills %5.1f B/clk, operand reads %5.1f B/clk\n",
+               nmma, nw, cyc / iters, nmma == 128 ? 64 : 128, nb * 16384.0 / cyc, (4096.0 + nmma * 32.0) * iters / cyc);
+      }
+  }
   const int strides[] = {128, 512};
   const size_t sets[] = {(size_t)64 << 20};   // L2-resident
   for (size_t set : sets)
