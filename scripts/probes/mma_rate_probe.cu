@@ -432,7 +432,7 @@ static void run_tmem(const char* name, int readers) {
 // (stage index, parity, descriptor base), bit 2 = a commit to a ROTATING barrier per K-block + early test_wait probe of the
 // next stage (barriers re-armed by the commits themselves), bit 3 = per-group patch wait + commit every 6 K-blocks.
 struct ProbeTable { int32_t aoff[40]; int32_t S; int32_t pad[7]; };
-template <int FEAT>
+template <int FEAT, int NN = 128>
 __global__ void __launch_bounds__(128) probe_loop(const __grid_constant__ ProbeTable tb, int iters, long long* out) {
   extern __shared__ uint8_t raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~uintptr_t(1023));
@@ -451,7 +451,7 @@ __global__ void __launch_bounds__(128) probe_loop(const __grid_constant__ ProbeT
   const uint32_t tmem = *tptr;
   if (warp == 0) {
     if (elect_one_sync()) {
-      const uint32_t idesc = umma_idesc_tf32(128, 128);
+      const uint32_t idesc = umma_idesc_tf32(128, NN);
       const uint32_t hi = (1024u >> 4) | (1u << 14) | (2u << 29);
       const uint32_t a_hi = (1280u >> 4) | (1u << 14) | (2u << 29);
       const uint32_t a_lo0 = ((smem_u32(A) >> 4) & 0x3FFFu) | (1u << 16);
@@ -492,7 +492,7 @@ __global__ void __launch_bounds__(128) probe_loop(const __grid_constant__ ProbeT
   if (warp == 0) tmem_dealloc(tmem, 128);
 }
 
-template <int FEAT>
+template <int FEAT, int NN = 128>
 static void run_loop(const char* name) {
   const int iters = 2048, smem = 8 * 16384 + 256 + 1024;
   ProbeTable tb;
@@ -500,8 +500,8 @@ static void run_loop(const char* name) {
   tb.S = 3;
   long long* d_out;
   cudaMalloc(&d_out, 148 * sizeof(long long));
-  cudaFuncSetAttribute(probe_loop<FEAT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-  for (int rep = 0; rep < 2; ++rep) probe_loop<FEAT><<<148, 128, smem>>>(tb, iters, d_out);
+  cudaFuncSetAttribute(probe_loop<FEAT, NN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  for (int rep = 0; rep < 2; ++rep) probe_loop<FEAT, NN><<<148, 128, smem>>>(tb, iters, d_out);
   cudaError_t e = cudaDeviceSynchronize();
   if (e != cudaSuccess) { printf("%-58s CUDA error: %s\n", name, cudaGetErrorString(e)); exit(1); }
   std::vector<long long> h(148);
@@ -554,6 +554,8 @@ static void run(const char* name, Cfg c, int ctas_per_sm) {
 
 int main() {
   const int L = 2048;
+  run_loop<7, 16>("kernel-like loop, N=16 MMAs (tensor time 39 cycles): the issue path itself");
+  run_loop<15, 16>("kernel-like loop + per-group wait/commit, N=16 MMAs");
   run_loop<0>("kernel-like loop: bare (commit per K-block)");
   run_loop<1>("kernel-like loop: + LDC tap offsets");
   run_loop<3>("kernel-like loop: + LDC + ring bookkeeping");
