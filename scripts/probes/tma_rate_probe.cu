@@ -33,7 +33,7 @@ __global__ void __launch_bounds__(128) probe(const __grid_constant__ CUtensorMap
         const int s = i % depth;
         if (i >= depth) mbar_wait(&bar[s], ((i / depth) - 1) & 1);
         if (i < boxes_per_cta) {
-          const int box = ((blockIdx.x * 2 + w) * boxes_per_cta + i) % n_boxes_total;   // every issuer streams its own range
+          const int box = ((blockIdx.x * 2 + w) * boxes_per_cta + i) & (n_boxes_total - 1);   // power of two: no division in the loop
           mbar_arrive_expect_tx(&bar[s], box_rows * 128);
           tma_load_2d(smem + s * 32768, &map, &bar[s], 0, box * box_rows);
         }
@@ -93,7 +93,7 @@ __global__ void __launch_bounds__(160) probe_mix(const __grid_constant__ CUtenso
       while (!*stop) {
         const int s = i & 1;
         if (i >= 2) mbar_wait(&mybar[s], ((i >> 1) - 1) & 1);
-        const int box = (int)(((long long)(blockIdx.x * 4 + warp) * 4096 + i) % n_boxes_total);
+        const int box = ((blockIdx.x * 4 + warp) * 4096 + i) & (n_boxes_total - 1);
         mbar_arrive_expect_tx(&mybar[s], 16384);
         tma_load_2d(ring + s * 16384, &map, &mybar[s], 0, box * 128);
         ++i; ++n;
@@ -106,6 +106,85 @@ __global__ void __launch_bounds__(160) probe_mix(const __grid_constant__ CUtenso
   tc_fence_before_sync();
   __syncthreads();
   if (warp == 0) tmem_dealloc(tmem, 256);
+}
+
+
+// The kernels' core pipeline in miniature: `np` producing threads (alternate stages) fill a ring of S 16 KB stages with
+// weight-like boxes, one issuing thread waits for a stage, issues four 128x128x8 MMAs (static A tile, B = the stage) and
+// commits the stage back.  Reports cycles per K-block (floor 256).
+__global__ void __launch_bounds__(160) probe_pipe(const __grid_constant__ CUtensorMap map, int kblocks, int S, int np, int n_boxes_total,
+                                                  int mode, long long* out) {
+  extern __shared__ uint8_t raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* A = smem;                       // 16 KB static
+  uint8_t* R = smem + 16384;               // S x 16 KB ring
+  uint64_t* full = reinterpret_cast<uint64_t*>(R + S * 16384);
+  uint64_t* empty = full + 8;   // up to 8 stages
+  uint64_t* done = empty + 8;
+  uint32_t* tptr = reinterpret_cast<uint32_t*>(done + 1);
+  const int warp = threadIdx.x >> 5;
+  for (int i = threadIdx.x; i < (S + 1) * 16384 / 4; i += blockDim.x) reinterpret_cast<float*>(smem)[i] = 1e-3f * (float)((i * 37) & 255);
+  if (threadIdx.x == 0) { for (int i = 0; i < 8; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); } mbar_init(done, 1); mbar_fence_init(); }
+  if (warp == 0) { tmem_alloc(tptr, 128); tmem_relinquish(); }
+  fence_proxy_async_smem();
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem = *tptr;
+  if (warp == 0) {
+    if (elect_one_sync()) {
+      const uint32_t idesc = umma_idesc_tf32(128, 128);
+      const uint32_t hi = (1024u >> 4) | (1u << 14) | (2u << 29);
+      const uint32_t a_lo = ((smem_u32(A) >> 4) & 0x3FFFu) | (1u << 16);
+      const uint32_t w_lo0 = ((smem_u32(R) >> 4) & 0x3FFFu) | (1u << 16);
+      int s = 0;
+      uint32_t par = 0, w_lo = w_lo0;
+      bool ok = false;
+      long long waited = 0;
+      const long long t0 = clock64();
+      for (int k = 0; k < kblocks; ++k) {
+        const uint64_t ad = (static_cast<uint64_t>(hi) << 32) | a_lo, bd = (static_cast<uint64_t>(hi) << 32) | w_lo;
+        if (!ok) { const long long w0 = clock64(); mbar_wait(&full[s], par); waited += clock64() - w0; }
+        uint64_t* wdone = &empty[s];
+        if (++s == S) { s = 0; par ^= 1; w_lo = w_lo0; } else { w_lo += 1024u; }
+        tc_fence_after_sync();
+        if (!(mode & 4)) {   // mode 4: no MMAs at all (pure TMA ring with a consumer)
+          tc_mma_tf32(tmem, ad, bd, idesc, 1u); tc_mma_tf32(tmem, ad + 2, bd + 2, idesc, 1u);
+          tc_mma_tf32(tmem, ad + 4, bd + 4, idesc, 1u); tc_mma_tf32(tmem, ad + 6, bd + 6, idesc, 1u);
+          if (mode & 8) {   // mode 8: eight MMAs per stage (floor 512 per stage)
+            tc_mma_tf32(tmem, ad, bd, idesc, 1u); tc_mma_tf32(tmem, ad + 2, bd + 2, idesc, 1u);
+            tc_mma_tf32(tmem, ad + 4, bd + 4, idesc, 1u); tc_mma_tf32(tmem, ad + 6, bd + 6, idesc, 1u);
+          }
+        }
+        if (mode & 2) mbar_arrive(wdone); else tc_commit(wdone);   // mode 2: plain arrive (stage handed back at once: WRONG for real use)
+        ok = mbar_test_wait(&full[s], par);
+      }
+      tc_commit(done);
+      mbar_wait(done, 0);
+      out[blockIdx.x * 2] = clock64() - t0;
+      out[blockIdx.x * 2 + 1] = waited;
+    }
+  } else if (warp <= np) {
+    if (elect_one_sync()) {
+      const int me = warp - 1;
+      int s = 0;
+      uint32_t par = 1;
+      int owner = 0;
+      for (int k = 0; k < kblocks; ++k) {
+        if (owner == me) {
+          if (!(mode & 1)) mbar_wait(&empty[s], par);             // mode 1: never wait for the stage to be free
+          mbar_arrive_expect_tx(&full[s], 16384);
+          const int box = (blockIdx.x * kblocks + k) & (n_boxes_total - 1);
+          tma_load_2d(R + s * 16384, &map, &full[s], 0, box * 128);
+        }
+        if (++s == S) { s = 0; par ^= 1; }
+        if (++owner == np) owner = 0;
+      }
+    }
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 128);
 }
 
 int main() {
@@ -129,6 +208,22 @@ int main() {
     CUtensorMap map;
     enc(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, buf, dims, strd, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    for (int mode : {0, 8, 6})
+    for (int S : {3, 6})
+      for (int np : {1, 2}) {
+        const int smem_p = (S + 1) * 16384 + 256 + 1024, kblocks = 4096;
+        const int smem_use = smem_p < 120 * 1024 ? 120 * 1024 : smem_p;   // one CTA per SM
+        cudaFuncSetAttribute(probe_pipe, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_use);
+        for (int rep = 0; rep < 2; ++rep) probe_pipe<<<148, 160, smem_use>>>(map, kblocks, S, np, (int)(set / 512 / 128), mode, d_out);
+        cudaError_t e = cudaDeviceSynchronize();
+        if (e != cudaSuccess) { printf("CUDA error: %s\n", cudaGetErrorString(e)); return 1; }
+        std::vector<long long> h(296);
+        cudaMemcpy(h.data(), d_out, 296 * 8, cudaMemcpyDeviceToHost);
+        double cyc = 0, wt = 0;
+        for (int b = 0; b < 148; ++b) { cyc += (double)h[2 * b]; wt += (double)h[2 * b + 1]; }
+        printf("mini pipeline (%s): %d stages, %d producing thread(s): %6.1f cycles per K-block (floor 256), of which issuer blocked on the ring %6.1f\n",
+               mode == 0 ? "commit -> empty -> producer" : mode == 8 ? "EIGHT MMAs per stage (floor 512)" : mode == 2 ? "plain arrive instead of commit" : mode == 6 ? "NO MMAs, plain arrive" : "producers never wait for empty", S, np, cyc / 148 / kblocks, wt / 148 / kblocks);
+      }
     const int smem = 14 * 16384 + 256 + 1024, iters = 8192;
     cudaFuncSetAttribute(probe_mix, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     for (int nmma : {128, 256})
@@ -147,14 +242,14 @@ int main() {
                nmma, nw, cyc / iters, nmma == 128 ? 64 : 128, nb * 16384.0 / cyc, (4096.0 + nmma * 32.0) * iters / cyc);
       }
   }
-  const int strides[] = {128, 512};
+  const int strides[] = {512};
   const size_t sets[] = {(size_t)64 << 20};   // L2-resident
   for (size_t set : sets)
     for (int stride : strides)
-     for (int box_rows : {128, 256})
+     for (int box_rows : {64, 128, 256})
      for (int ctas : {1})
      for (int issuers : {1, 2})
-      for (int depth : {2}) {
+      for (int depth : {2, 4}) {
         // 2-D view: dim0 = 32 floats, dim1 = rows `stride` bytes apart
         const cuuint64_t rows = set / stride;
         cuuint64_t dims[2] = {32, rows};
