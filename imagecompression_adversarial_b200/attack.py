@@ -202,3 +202,26 @@ def attack_cw(im_s, net, args, record=None):
         level = np.where(done, level, (min_noise + max_noise) / 2)
     im_adv, output_adv, bpp, mse_results, vi_results = eval(final_in.contiguous(), im_s, output_s, net, args)
     return im_adv, output_adv, output_s, bpp_ori, bpp, mse_results["mse_in"], mse_results["mse_out"], vi_results["vi"]
+
+
+@torch.no_grad()
+def recompression(im_s, net, args, repeat_times=None):
+    """Repeated coding of the same images (recompression.py:21-61; ``coder.code`` :154-164): each round decodes, clamps to
+    [0, 1] and goes through the 8-bit PNG lattice (``write_image`` / ``read_image``, coder.py:20-48: round(x * 255) / 255)
+    before it is coded again.  The whole batch stays on the device between rounds (the reference round-trips a PNG file per
+    image and round).  Returns, for the LAST round as the reference reports it (:46-50): (x_hat, bpp, psnr, ms_ssim) with
+    bpp / psnr / ms_ssim per batch (scalars) against the original images."""
+    n_rounds = int(repeat_times if repeat_times is not None else args.steps)
+    net.eval()
+    x = im_s
+    result = None
+    for _ in range(n_rounds):
+        result = net(x)
+        x = torch.round(_clamp01(result["x_hat"]) * 255.0) / 255.0        # the PNG lattice between rounds
+    x_hat = _clamp01(result["x_hat"])
+    num_pixels = im_s.shape[0] * im_s.shape[2] * im_s.shape[3]            # RateDistortionLoss: N * H * W (train.py:60-64)
+    bpp = float(_bpp(result["likelihoods"], num_pixels))
+    mse = _mse(x_hat, im_s)
+    psnr = -10.0 * math.log10(mse) if mse > 0 else float("inf")
+    msim = float(metrics.ms_ssim(x_hat, im_s, data_range=1.0, size_average=True))
+    return x_hat, bpp, psnr, msim

@@ -337,6 +337,23 @@ def test_epoch(test_dataloader, model, criterion, args):
     return (avg["vi"] if args.adv else avg["loss"]), avg
 
 
+@torch.no_grad()
+def recompression(im_s, net, args, repeat_times):
+    """recompression.py:21-61 without the PNG files: decode, clamp, 8-bit lattice (coder.py:20-48), code again; the last
+    round's bpp (RateDistortionLoss convention, train.py:60-64), PSNR and MS-SSIM against the original."""
+    net.eval()
+    x = im_s
+    for _ in range(repeat_times):
+        result = net(x)
+        x = torch.round(torch.clamp(result["x_hat"], 0.0, 1.0) * 255.0) / 255.0
+    x_hat = torch.clamp(result["x_hat"], 0.0, 1.0)
+    n, _, h, w = im_s.shape
+    bpp = float(sum(torch.log(l).sum() / (-math.log(2) * n * h * w) for l in result["likelihoods"].values()))
+    psnr = -10.0 * math.log10(float(torch.mean((x_hat - im_s) ** 2)))
+    msim = float(ms_ssim(x_hat, im_s, data_range=1.0, size_average=True))
+    return x_hat, bpp, psnr, msim
+
+
 # ---------------------------------------------------------------- synthetic inputs (SURVEY §8d)
 def synthetic_image(i, H=512, W=768, device="cpu"):
     """Seeded Kodak-like image on the k/255 lattice: U[0,1) field -> separable Gaussian blur

@@ -418,3 +418,18 @@ def test_cw_search_matches_oracle(dev):
             assert abs(pmo - mse_o) <= 5e-3 * max(mse_o, 1e-7) + 1e-9, (i, k, pmo, mse_o)
         if not diverged and i == 0 and len(orec) == len(rec):
             assert abs(psnr(p[0][i:i + 1], x[i:i + 1]) - psnr(o[0], x[i:i + 1])) < 0.05
+
+
+def test_recompression_matches_oracle(dev):
+    """repeated coding through the 8-bit lattice (recompression.py:21-61)."""
+    from imagecompression_adversarial_b200 import attack as patk
+    from oracle import attack as oatk
+    onet, pnet = pair("hyper", 3, dev)
+    x = images(2, 192, 256, dev)
+    args = oatk.default_args(model="hyper", quality=3, metric="mse")
+    p = patk.recompression(x, pnet, args, repeat_times=4)
+    o = oatk.recompression(x, onet, args, 4)
+    assert p[0].shape == x.shape
+    assert abs(p[1] - o[1]) <= max(1e-3, 5e-3 * o[1]), (p[1], o[1])       # bpp (rounding near-ties move isolated symbols)
+    assert abs(p[2] - o[2]) < 0.05, (p[2], o[2])                          # PSNR, dB
+    assert abs(p[3] - o[3]) < 2e-3, (p[3], o[3])                          # MS-SSIM
