@@ -252,7 +252,7 @@ def run_ours(args):
     achieved = dom_flops / (best / 1e3) / 1e12
     roof = {"bound": "tensor", "achieved": achieved, "peak": tf32_peak, "unit": "TFLOP/s",
             "frac": achieved / tf32_peak,
-            "traffic": 71.55e6 * n_local,           # ncu --set full on this launch at 8 images: 572.4 MB DRAM (read 414.0 + write 158.4), profiles/r1_ncu_full_g_a2_conv_gdn_v5.txt
+            "traffic": 71.79e6 * n_local,           # ncu --set full on this launch at 8 images: 574.4 MB DRAM (read 414.3 + write 160.1), profiles/r1_ncu_full_g_a2_conv_gdn_v10.txt
             "kernel": "conv_tc_kernel<GDN_FWD> (tcgen05 kind::tf32), g_a.2 conv 128->128 5x5/2 + GDN",
             "kernel_ms": best, "algorithmic_flops_per_launch": dom_flops,
             "algorithmic_bytes_per_launch": n_local * 4.0 * 128 * ((H // 2) * (W // 2) + 2 * (H // 4) * (W // 4)),
