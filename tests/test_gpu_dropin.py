@@ -71,7 +71,15 @@ def test_reference_self_ensemble_defence_on_the_operator_surface():
     from oracle.attack import synthetic_image
     torch.backends.cudnn.allow_tf32 = False
     torch.backends.cuda.matmul.allow_tf32 = False
-    se = _reference_module("self_ensemble")
+    det = torch.are_deterministic_algorithms_enabled()
+    se = _reference_module("self_ensemble")     # the module switches torch.use_deterministic_algorithms on at import (:31)
+    try:
+        _self_ensemble_checks(se, torch, pm, om, synthetic_image)
+    finally:
+        torch.use_deterministic_algorithms(det)  # do not leak the global into the rest of the test session
+
+
+def _self_ensemble_checks(se, torch, pm, om, synthetic_image):
     dev = torch.device("cuda:0")
     onet = om.init_model("hyper", 3, seed=0).to(dev).eval()
     pnet = pm.init_model("hyper", 3, "mse", pretrained=False).to(dev).eval()
