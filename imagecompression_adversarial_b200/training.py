@@ -43,13 +43,13 @@ class _MsssimFn(torch.autograd.Function):
 
 
 class RateDistortionLoss(torch.nn.Module):
-    """train.py:37-96, training branch (``lpips`` is out of scope)."""
+    """train.py:37-96: the training branch and the ``training=False`` evaluation metrics (``lpips`` is out of scope)."""
 
     def __init__(self, metric="mse", lmbda=1e-2):
         super().__init__()
         self.metric, self.lmbda = metric, lmbda
 
-    def forward(self, output, target):
+    def forward(self, output, target, training=True):
         N, _, H, W = target.shape
         num_pixels = N * H * W
         out = {}
@@ -58,6 +58,16 @@ class RateDistortionLoss(torch.nn.Module):
             term = Fn.LogSumFn.apply(lik, 1.0 / 65536) * (1.0 / (-math.log(2) * num_pixels))
             bpp = term if bpp is None else bpp + term
         out["bpp_loss"] = bpp.reshape(())
+        if not training:                                                 # train.py:67-72 (evaluation metrics)
+            from . import metrics
+            with torch.no_grad():
+                x_hat = torch.clamp(output["x_hat"], 0.0, 1.0)
+                output["x_hat"] = x_hat
+                out["mse_loss"] = Fn.MseFn.apply(x_hat, target).reshape(())
+                out["msim_loss"] = metrics.ms_ssim(x_hat, target, data_range=1.0, size_average=True)
+                out["psnr"] = -10.0 * math.log10(float(out["mse_loss"]))
+                out["msim_dB"] = -10.0 * math.log10(1.0 - float(out["msim_loss"]))
+            return out
         lamb_r = 0 if self.lmbda == 100 else 1                           # train.py:77-80
         if self.metric == "mse":
             out["distortion_loss"] = Fn.MseFn.apply(output["x_hat"], target).reshape(())
@@ -209,3 +219,24 @@ def test_epoch(epoch, test_dataloader, model, criterion, log_dir, args, group=No
         return sums["vi"] / n
     print(log)
     return sums["loss"] / n
+
+
+@torch.no_grad()
+def batch_test(images, net, criterion=None):
+    """test.py:28-60 without the file IO: eval-mode ``net(x)`` per image (``coder.code``, coder.py:154-164), the
+    evaluation branch of the criterion, and the four averages of the ``AVG:`` line: (bpp, psnr, ms_ssim, ms_ssim_dB).
+    ``images``: an iterable of [1, 3, H, W] tensors (or one [N, 3, H, W] tensor, taken image by image like the reference)."""
+    criterion = criterion or RateDistortionLoss()
+    net.eval()
+    sums = [0.0, 0.0, 0.0, 0.0]
+    count = 0
+    for im in images:
+        im = im if im.dim() == 4 else im.unsqueeze(0)
+        result = net(im)
+        m = criterion(result, im, training=False)
+        for i, k in enumerate(("bpp_loss", "psnr", "msim_loss", "msim_dB")):
+            sums[i] += float(m[k])
+        count += 1
+    avg = [v / max(count, 1) for v in sums]
+    print("AVG:", *avg)
+    return tuple(avg)

@@ -354,6 +354,26 @@ def recompression(im_s, net, args, repeat_times):
     return x_hat, bpp, psnr, msim
 
 
+@torch.no_grad()
+def batch_test(images, net):
+    """test.py:28-60 + the evaluation branch of RateDistortionLoss (train.py:50-72): per image bpp (likelihoods clamped at
+    1/65536, N*H*W pixels), PSNR and MS-SSIM of the clamped reconstruction; returns the four averages of the AVG: line."""
+    net.eval()
+    sums = [0.0, 0.0, 0.0, 0.0]
+    for im in images:
+        im = im if im.dim() == 4 else im.unsqueeze(0)
+        result = net(im)
+        n, _, h, w = im.shape
+        bpp = float(sum(torch.log(torch.clamp(l, min=1.0 / 65536)).sum() / (-math.log(2) * n * h * w)
+                        for l in result["likelihoods"].values()))
+        x_hat = torch.clamp(result["x_hat"], 0.0, 1.0)
+        mse = float(torch.mean((x_hat - im) ** 2))
+        msim = float(ms_ssim(x_hat, im, data_range=1.0, size_average=True))
+        for i, v in enumerate((bpp, -10.0 * math.log10(mse), msim, -10.0 * math.log10(1.0 - msim))):
+            sums[i] += v
+    return tuple(v / len(images) for v in sums)
+
+
 # ---------------------------------------------------------------- synthetic inputs (SURVEY §8d)
 def synthetic_image(i, H=512, W=768, device="cpu"):
     """Seeded Kodak-like image on the k/255 lattice: U[0,1) field -> separable Gaussian blur

@@ -299,3 +299,23 @@ def test_test_epoch_matches_oracle(dev, tmp_path, adv):
         assert abs(p - o) < 0.1, (p, o)                                   # VI in dB over a 6-step attack
     else:
         assert abs(p - o) <= 2e-3 * abs(o), (p, o)
+
+
+def test_batch_test_matches_oracle(dev):
+    """test.py:28-60: the RD evaluation driver -- per-image eval forward, bpp / PSNR / MS-SSIM,
+    the four averages of its AVG: line."""
+    from imagecompression_adversarial_b200 import models as pm
+    from imagecompression_adversarial_b200 import training as ptr
+    from oracle import attack as oatk
+    from oracle import models as om
+    from oracle.attack import synthetic_image
+    onet = om.init_model("hyper", 3, seed=0).to(dev)
+    pnet = pm.init_model("hyper", 3, "mse", pretrained=False).to(dev)
+    pnet.load_state_dict(onet.state_dict())
+    imgs = [synthetic_image(i, 192, 256).to(dev) for i in range(3)]
+    p = ptr.batch_test(imgs, pnet)
+    o = oatk.batch_test(imgs, onet)
+    assert abs(p[0] - o[0]) <= max(1e-3, 2e-3 * o[0]), (p[0], o[0])      # bpp
+    assert abs(p[1] - o[1]) < 0.05, (p[1], o[1])                          # PSNR, dB
+    assert abs(p[2] - o[2]) < 1e-3, (p[2], o[2])                          # MS-SSIM
+    assert abs(p[3] - o[3]) < 0.05, (p[3], o[3])                          # MS-SSIM, dB
