@@ -13,6 +13,7 @@ import torch
 from . import metrics
 from . import _lib as L
 from . import ops
+from . import precision
 from .engine import AttackEngine, GenericAttackEngine, IfgsmEngine, RoiSpec
 from .program import parse_stack
 
@@ -56,7 +57,7 @@ def _engine_for(net, im_s, args, roi=None):
     n, _, h, w = im_s.shape
     force = getattr(args, "force_branch", -1)
     key = (id(net), n, h, w, args.steps, float(args.epsilon), float(args.noise), float(args.lr_attack),
-           bool(args.clamp), args.att_metric, force, roi.key() if roi is not None else None)
+           bool(args.clamp), args.att_metric, force, roi.key() if roi is not None else None, precision.get())
     eng = _ENGINES.get(key)
     if eng is None:
         cls = AttackEngine if _fused_stacks(net) else GenericAttackEngine
@@ -159,7 +160,7 @@ def attack_cw(im_s, net, args, record=None):
     output_s, bpp_ori = clean_pass(im_s, net, args)
     net.train()                                                            # attack_cw.py:231
     n, _, h, w = im_s.shape
-    key = ("cw", id(net), n, h, w, float(args.epsilon), float(args.lr_attack), bool(args.clamp))
+    key = ("cw", id(net), n, h, w, float(args.epsilon), float(args.lr_attack), bool(args.clamp), precision.get())
     eng = _ENGINES.get(key)
     if eng is None:
         eng = CwEngine(net, n, h, w, epsilon=args.epsilon, lr_attack=args.lr_attack, clamp=args.clamp)

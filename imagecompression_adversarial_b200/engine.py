@@ -86,11 +86,39 @@ class AttackEngine:
         # gradient wrt the latent: written by g_s.backward, seed of g_a.backward (one shared buffer)
         self.g_lat = f(n_img, lat_h, lat_w, ga_units[-1].cout)
         self.ga = StackProgram(ga_units, n_img, height, width, dev, x_in=self.im_in, g_out=self.g_lat, active=act,
-                               n_active=nact, round_final_out=True)
+                               n_active=nact, round_final_out=True, name="g_a")
         self.gs = StackProgram(gs_units, n_img, lat_h, lat_w, dev, x_in=self.ga.out, g_in=self.g_lat, active=act,
-                               n_active=nact, round_final_gin=True)
+                               n_active=nact, round_final_gin=True, name="g_s")
         self.x_out, self.g_x = self.gs.out, self.gs.g_out
         assert self.x_out.shape == self.im_s.shape, (self.x_out.shape, self.im_s.shape)
+
+    def launch_table(self):
+        """Every launch of one L2-attack iteration, in stream order, with its algorithmic work:
+        a list of dicts {name, launch (callable), kernels, flops, bytes, bound}.  ``bytes`` counts every tensor the
+        launch must read or write once in fp32; ``bound`` names the roofline that limits it ("tensor" / "hbm").
+        Used by bench.py's per-launch roofline table and scripts/step_breakdown.py (speed mode only)."""
+        img = 4.0 * self.n_img * self.per_img           # bytes of one RGB tensor of the batch
+        rows = [{"name": "perturb_forward + finalize", "launch": self._perturb_forward, "kernels": 2, "flops": 0.0,
+                 "bytes": 3 * img, "bound": "hbm"}]
+
+        def stack(prog, lst, info):
+            for p, i in zip(lst, info):
+                rows.append({"name": i["name"], "launch": p.launch, "kernels": p.kernels, "flops": i["flops"],
+                             "bytes": i["bytes"], "bound": i["bound"]})
+
+        stack(self.ga, self.ga.fwd, self.ga.fwd_info)
+        stack(self.gs, self.gs.fwd, self.gs.fwd_info)
+        rows.append({"name": "output_loss (clamp + MSE + gradient seed)",
+                     "launch": lambda: self._output_loss(self.x_out, self.g_x), "kernels": 2, "flops": 0.0,
+                     "bytes": 3 * img, "bound": "hbm"})
+        stack(self.gs, self.gs.bwd, self.gs.bwd_info)
+        stack(self.ga, self.ga.bwd, self.ga.bwd_info)
+        rows.append({"name": "perturb_update_adam (clamp backward + Adam)",
+                     "launch": lambda: ops.perturb_update_adam(self.im_s, self.noise, self.ga.g_in, self.m, self.v, self.st,
+                                                               eps=self.eps, gradA_scale=1.0 / self.per_img,
+                                                               gradB_scale=1.0, w_in=self.w_in),
+                     "kernels": 1, "flops": 0.0, "bytes": 8 * img, "bound": "hbm"})
+        return rows
 
     # ------------------------------------------------------------------ state
     def load(self, im_s_nchw, output_s_nchw, noise_init_nchw=None, output_t_nchw=None):

@@ -11,6 +11,7 @@ import torch
 
 from . import _lib as L
 from . import ops
+from . import precision
 
 _PACK_CACHE = {}
 
@@ -40,7 +41,8 @@ def tc_shape(k_ch, n_ch):
 def packed(weight, kind):
     """Packed copy of a layer weight, cached on (storage, version) so it is rebuilt only after an update.
     Weights of tensor-path contractions are rounded to TF32 (nearest) here."""
-    key = (id(weight), kind)
+    split = precision.split()
+    key = (id(weight), kind, split)
     hit = _PACK_CACHE.get(key)
     # the entry must belong to THIS tensor object (ids and addresses are recycled once a model is freed)
     if hit is not None and hit[3]() is weight and hit[0] == weight._version and hit[2] == tuple(weight.shape) \
@@ -52,14 +54,28 @@ def packed(weight, kind):
     a, b = weight.shape[0], weight.shape[1]
     n_ch, k_ch = {L.PACK_CONV_FWD: (a, b), L.PACK_CONV_DGRAD: (b, a), L.PACK_CONVT_FWD: (b, a),
                   L.PACK_CONVT_DGRAD: (a, b)}[kind]
-    wp = ops.pack_weight(weight, kind, round_tf32=tc_shape(k_ch, n_ch))
+    if split and tc_shape(k_ch, n_ch):      # parity mode: [Whi | Whi | Wlo] along K (csrc/icadv_split.cu)
+        wp = ops.split3_weight(ops.pack_weight(weight, kind, round_tf32=False))
+    else:
+        wp = ops.pack_weight(weight, kind, round_tf32=tc_shape(k_ch, n_ch))
     _PACK_CACHE[key] = (weight._version, wp, tuple(weight.shape), weakref.ref(weight), weight.data_ptr())
     return wp
 
 
 def tc_operand(xn, k_ch, n_ch):
-    """Round an activation to TF32 (nearest) when it is about to feed a tensor-path contraction."""
-    return ops.unary(xn, 5) if tc_shape(k_ch, n_ch) else xn
+    """Prepare an activation that is about to feed a tensor-path contraction: round to TF32 (nearest), or -- parity
+    mode -- expand it to the three-term split form [hi | lo | hi] along the channel axis."""
+    if not tc_shape(k_ch, n_ch):
+        return xn
+    return ops.split3(xn.contiguous()) if precision.split() else ops.unary(xn, 5)
+
+
+def _path(k_ch, n_ch):
+    """Parity mode pins the kernel choice to the operand preparation above (split operands <-> tensor path; every
+    other shape runs on the fp32 CUDA-core kernels)."""
+    if not precision.split():
+        return "auto"
+    return "tc" if tc_shape(k_ch, n_ch) else "simt"
 
 
 class Contraction(torch.autograd.Function):
@@ -73,7 +89,7 @@ class Contraction(torch.autograd.Function):
         n_ch = weight.shape[1] if transposed else weight.shape[0]
         out = ops.conv(tc_operand(xn, xn.shape[-1], n_ch), packed(weight, kind),
                        bias.detach() if bias is not None else None, form=form, ksize=ksize, stride=stride, n_ch=n_ch,
-                       act=act)
+                       act=act, path=_path(xn.shape[-1], n_ch))
         ctx.save_for_backward(xn, weight, out if act != L.ACT_NONE else None)
         ctx.cfg = (ksize, stride, transposed, act, param_grads, bias is not None)
         return to_nchw(out)
@@ -90,7 +106,8 @@ class Contraction(torch.autograd.Function):
             kind = L.PACK_CONVT_DGRAD if transposed else L.PACK_CONV_DGRAD
             form = L.FORM_SCONV if transposed else L.FORM_TCONV
             gx = to_nchw(ops.conv(tc_operand(gn.contiguous(), gn.shape[-1], xn.shape[-1]), packed(weight, kind), None,
-                                  form=form, ksize=ksize, stride=stride, n_ch=xn.shape[-1]))
+                                  form=form, ksize=ksize, stride=stride, n_ch=xn.shape[-1],
+                                  path=_path(gn.shape[-1], xn.shape[-1])))
         if param_grads and (ctx.needs_input_grad[1] or (has_bias and ctx.needs_input_grad[2])):
             form = L.FORM_TCONV if transposed else L.FORM_SCONV
             n_ch = weight.shape[1] if transposed else weight.shape[0]
@@ -108,9 +125,13 @@ class GdnFn(torch.autograd.Function):
     def forward(ctx, x, beta_eff, gamma_eff, inverse):
         xn = to_nhwc(x)
         C = xn.shape[-1]
-        y, sc = ops.conv(xn, None, None, form=L.FORM_SCONV, ksize=1, stride=1, n_ch=C,
-                         epi=L.EPI_IGDN_FWD if inverse else L.EPI_GDN_FWD, gmat=gamma_eff.contiguous(),
-                         beta=beta_eff.contiguous(), acc_from_in=True, path="tc")
+        ctx.split = precision.split()
+        if ctx.split:
+            y, sc = ops.gdn_forward_split(xn.contiguous(), beta_eff, gamma_eff, inverse)
+        else:
+            y, sc = ops.conv(xn, None, None, form=L.FORM_SCONV, ksize=1, stride=1, n_ch=C,
+                             epi=L.EPI_IGDN_FWD if inverse else L.EPI_GDN_FWD, gmat=gamma_eff.contiguous(),
+                             beta=beta_eff.contiguous(), acc_from_in=True, path="tc")
         ctx.save_for_backward(y, sc, gamma_eff)
         ctx.inverse = inverse
         return to_nchw(y)
@@ -119,6 +140,8 @@ class GdnFn(torch.autograd.Function):
     def backward(ctx, g):
         y, sc, gamma_eff = ctx.saved_tensors
         C = y.shape[-1]
+        if ctx.split:
+            return to_nchw(ops.gdn_backward_split(to_nhwc(g).contiguous(), y, sc, gamma_eff, ctx.inverse)), None, None, None
         gx = ops.conv(to_nhwc(g), None, None, form=L.FORM_SCONV, ksize=1, stride=1, n_ch=C,
                       epi=L.EPI_IGDN_BWD if ctx.inverse else L.EPI_GDN_BWD, gmat=gamma_eff.t().contiguous(),
                       y_prev=y, sc_prev=sc, acc_from_in=True, path="tc")
@@ -252,12 +275,16 @@ class GdnTrainFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, beta_raw, gamma_raw, inverse, beta_bound, beta_ped, gamma_bound, gamma_ped):
         be = ops.gdn_reparam(beta_raw, beta_bound, beta_ped)
-        ga = ops.gdn_reparam(gamma_raw, gamma_bound, gamma_ped, round_tf32=True)
+        ctx.split = precision.split()
+        ga = ops.gdn_reparam(gamma_raw, gamma_bound, gamma_ped, round_tf32=not ctx.split)
         xn = to_nhwc(x)
         C = xn.shape[-1]
-        y, sc = ops.conv(xn, None, None, form=L.FORM_SCONV, ksize=1, stride=1, n_ch=C,
-                         epi=L.EPI_IGDN_FWD if inverse else L.EPI_GDN_FWD, gmat=ga.contiguous(), beta=be.contiguous(),
-                         acc_from_in=True, path="tc")
+        if ctx.split:
+            y, sc = ops.gdn_forward_split(xn.contiguous(), be, ga, inverse)
+        else:
+            y, sc = ops.conv(xn, None, None, form=L.FORM_SCONV, ksize=1, stride=1, n_ch=C,
+                             epi=L.EPI_IGDN_FWD if inverse else L.EPI_GDN_FWD, gmat=ga.contiguous(), beta=be.contiguous(),
+                             acc_from_in=True, path="tc")
         ctx.save_for_backward(y, sc, ga, beta_raw, gamma_raw)
         ctx.cfg = (inverse, beta_bound, gamma_bound)
         return to_nchw(y)
@@ -268,9 +295,12 @@ class GdnTrainFn(torch.autograd.Function):
         inverse, beta_bound, gamma_bound = ctx.cfg
         C = y.shape[-1]
         gn = to_nhwc(g).contiguous()
-        gx = ops.conv(gn, None, None, form=L.FORM_SCONV, ksize=1, stride=1, n_ch=C,
-                      epi=L.EPI_IGDN_BWD if inverse else L.EPI_GDN_BWD, gmat=ga.t().contiguous(), y_prev=y, sc_prev=sc,
-                      acc_from_in=True, path="tc")
+        if ctx.split:
+            gx = ops.gdn_backward_split(gn, y, sc, ga, inverse)
+        else:
+            gx = ops.conv(gn, None, None, form=L.FORM_SCONV, ksize=1, stride=1, n_ch=C,
+                          epi=L.EPI_IGDN_BWD if inverse else L.EPI_GDN_BWD, gmat=ga.t().contiguous(), y_prev=y, sc_prev=sc,
+                          acc_from_in=True, path="tc")
         gb, gg = ops.gdn_param_grad(gn, y, sc, beta_raw, gamma_raw, inverse=inverse, beta_bound=beta_bound,
                                     gamma_bound=gamma_bound)
         return to_nchw(gx), gb, gg, None, None, None, None, None
@@ -287,7 +317,7 @@ class EbTrainFn(torch.autograd.Function):
         C = xn.shape[-1]
         table = ops.eb_prepare(ms, bs, fs, C)
         if noise_nhwc is None:
-            noise_nhwc = torch.empty_like(xn).uniform_(-0.5, 0.5)
+            noise_nhwc = ops.uniform_noise_like(xn)
         x_hat, lik, _ = ops.eb_forward(xn, table, medians, training=True, noise=noise_nhwc, lik_bound=lik_bound)
         ctx.save_for_backward(x_hat, table, *params)
         ctx.lik_bound = lik_bound
@@ -321,7 +351,7 @@ class GcTrainFn(torch.autograd.Function):
         yn, sn = to_nhwc(y).contiguous(), to_nhwc(scales).contiguous()
         mn = to_nhwc(means).contiguous() if means is not None else None
         if noise_nhwc is None:
-            noise_nhwc = torch.empty_like(yn).uniform_(-0.5, 0.5)
+            noise_nhwc = ops.uniform_noise_like(yn)
         y_hat, lik, _ = ops.gc_forward(yn, sn, mn, training=True, noise=noise_nhwc, scale_bound=scale_bound,
                                        lik_bound=lik_bound)
         ctx.save_for_backward(y_hat, sn, mn)

@@ -17,6 +17,7 @@ import torch.nn as nn
 from . import _lib as L
 from . import functional as Fn
 from . import ops
+from . import precision
 from .program import StackProgram, parse_stack
 
 # compressai.zoo.image.cfgs
@@ -127,8 +128,33 @@ def deconv(cin, cout, kernel_size=5, stride=2):
     return ConvTranspose2d(cin, cout, kernel_size, stride)
 
 
-class NonNegativeParametrizer(nn.Module):
+class _ConstStateKeys:
+    """CompressAI keeps a few constants as persistent 1-element buffers, so its checkpoints (and checkpoints the
+    reference's train.py wrote, train.py:443-454) carry keys such as ``g_a.1.beta_reparam.pedestal``,
+    ``g_a.1.beta_reparam.lower_bound.bound``, ``entropy_bottleneck.likelihood_lower_bound.bound``,
+    ``gaussian_conditional.lower_bound_scale.bound``.  Here those constants are plain floats (kernel arguments); this
+    mixin EMITS them in ``state_dict()`` under CompressAI's names and, on load, accepts them (the checkpoint's value is
+    adopted), so the strict ``net.load_state_dict(checkpoint["state_dict"])`` of coder.py:107 works on real checkpoints
+    and a saved one loads back into CompressAI.  They are optional on load (an oracle / plain state dict has none)."""
+
+    _const_keys = {}   # state-dict key (relative) -> attribute name holding the float
+
+    def _save_to_state_dict(self, destination, prefix, keep_vars):
+        super()._save_to_state_dict(destination, prefix, keep_vars)
+        for key, attr in self._const_keys.items():
+            destination[prefix + key] = torch.tensor([float(getattr(self, attr))], dtype=torch.float32)
+
+    def _load_from_state_dict(self, state_dict, prefix, local_metadata, strict, missing_keys, unexpected_keys, error_msgs):
+        for key, attr in self._const_keys.items():
+            v = state_dict.pop(prefix + key, None)
+            if v is not None:
+                setattr(self, attr, float(v.reshape(-1)[0]))
+        super()._load_from_state_dict(state_dict, prefix, local_metadata, strict, missing_keys, unexpected_keys, error_msgs)
+
+
+class NonNegativeParametrizer(_ConstStateKeys, nn.Module):
     """compressai.ops.NonNegativeParametrizer; exposes ``bound``/``pedestal`` (attack_rd.py:294-295 calls it)."""
+    _const_keys = {"pedestal": "pedestal", "lower_bound.bound": "bound"}
 
     def __init__(self, minimum=0.0, reparam_offset=2 ** -18):
         super().__init__()
@@ -167,7 +193,7 @@ class GDN(nn.Module):
         if torch.is_grad_enabled() and (self.beta.requires_grad or self.gamma.requires_grad) and _PARAM_GRADS[0]:
             return Fn.GdnTrainFn.apply(x, self.beta, self.gamma, self.inverse, self.beta_reparam.bound,
                                        self.beta_reparam.pedestal, self.gamma_reparam.bound, self.gamma_reparam.pedestal)
-        be, ga, _ = self.effective_parameters(round_tf32=True)
+        be, ga, _ = self.effective_parameters(round_tf32=not precision.split())
         return Fn.GdnFn.apply(x, be, ga, self.inverse)
 
 
@@ -241,7 +267,7 @@ _INFER_PROGRAMS = {}
 def _inference_program(stack, n, h, w, device):
     """Cached forward-only StackProgram of ``stack`` for this input shape (at most a few live entries per stack)."""
     import weakref
-    key = (id(stack), n, h, w, str(device))
+    key = (id(stack), n, h, w, str(device), precision.get())
     hit = _INFER_PROGRAMS.get(key)
     if hit is not None and hit[0]() is stack:
         return hit[1]
@@ -312,7 +338,7 @@ class LowerBound(nn.Module):
 _CDF_BUFFERS = ("_offset", "_quantized_cdf", "_cdf_length")
 
 
-class _ZooStateDict:
+class _ZooStateDict(_ConstStateKeys):
     """Checkpoint compatibility of the entropy models (reference: coder.py:104-116,
     anchors/balle.py:57-72, anchors/utils.py:46-109; key names SURVEY.md A.7).
 
@@ -335,6 +361,10 @@ class _ZooStateDict:
         for new, old in (("matrices.", "_matrix"), ("biases.", "_bias"), ("factors.", "_factor")):
             for key in [k for k in state_dict if k.startswith(prefix + new)]:
                 state_dict[prefix + old + key[len(prefix + new):]] = state_dict.pop(key)
+        for key, attr in self._const_keys.items():      # CompressAI's constant buffers (see _ConstStateKeys)
+            v = state_dict.pop(prefix + key, None)
+            if v is not None:
+                setattr(self, attr, float(v.reshape(-1)[0]))
         for name in self._zoo_buffers:
             key, buf = prefix + name, getattr(self, name)
             if key in state_dict:
@@ -342,11 +372,13 @@ class _ZooStateDict:
                     setattr(self, name, torch.zeros(state_dict[key].shape, dtype=buf.dtype, device=buf.device))
             else:
                 state_dict[key] = buf
-        super()._load_from_state_dict(state_dict, prefix, local_metadata, strict, missing_keys, unexpected_keys, error_msgs)
+        nn.Module._load_from_state_dict(self, state_dict, prefix, local_metadata, strict, missing_keys, unexpected_keys,
+                                        error_msgs)
 
 
 class EntropyBottleneck(_ZooStateDict, nn.Module):
     """compressai EntropyBottleneck, forward on the fused likelihood kernel."""
+    _const_keys = {"likelihood_lower_bound.bound": "likelihood_bound"}
 
     def __init__(self, channels, tail_mass=1e-9, init_scale=10.0, filters=(3, 3, 3, 3)):
         super().__init__()
@@ -401,7 +433,7 @@ class EntropyBottleneck(_ZooStateDict, nn.Module):
         noise = None
         if training:
             noise = (Fn.to_nhwc(self.noise_override).contiguous() if self.noise_override is not None
-                     else torch.empty_like(xn).uniform_(-0.5, 0.5))
+                     else ops.uniform_noise_like(xn))
         x_hat, lik, bits = ops.eb_forward(xn, self._table(), med, training=training, noise=noise,
                                           lik_bound=self.likelihood_bound)
         self.last_bits = bits
@@ -411,6 +443,7 @@ class EntropyBottleneck(_ZooStateDict, nn.Module):
 class GaussianConditional(_ZooStateDict, nn.Module):
     """compressai GaussianConditional (A.4) on the fused erfc likelihood kernel."""
     _zoo_buffers = _CDF_BUFFERS + ("scale_table",)
+    _const_keys = {"likelihood_lower_bound.bound": "likelihood_bound", "lower_bound_scale.bound": "scale_bound"}
 
     def __init__(self, scale_table=None, scale_bound=0.11, tail_mass=1e-9):
         super().__init__()
@@ -426,7 +459,11 @@ class GaussianConditional(_ZooStateDict, nn.Module):
         x = inputs.contiguous(memory_format=torch.channels_last)
         if mode == "noise":
             nz = (self.noise_override.contiguous(memory_format=torch.channels_last)
-                  if self.noise_override is not None else torch.empty_like(x).uniform_(-0.5, 0.5))
+                  if self.noise_override is not None else ops.uniform_noise_like(x))
+            if torch.is_grad_enabled() and inputs.requires_grad:
+                # compressai: ``inputs + noise`` is differentiable (identity to the inputs, anchors/model.py:102), so the
+                # distortion gradient through g_s(y_hat) and context_prediction(y_hat) reaches g_a in training
+                return Fn.AddFn.apply(x, nz)
             return ops.unary(x, 4, nz)
         if means is not None:
             m = means.contiguous(memory_format=torch.channels_last)
@@ -450,7 +487,7 @@ class GaussianConditional(_ZooStateDict, nn.Module):
         noise = None
         if training:
             noise = (Fn.to_nhwc(self.noise_override).contiguous() if self.noise_override is not None
-                     else torch.empty_like(y).uniform_(-0.5, 0.5))
+                     else ops.uniform_noise_like(y))
         y_hat, lik, bits = ops.gc_forward(y, s, m, training=training, noise=noise, scale_bound=self.scale_bound,
                                           lik_bound=self.likelihood_bound)
         self.last_bits = bits

@@ -464,3 +464,104 @@ def adam_clip_step(params, grads, m, v, *, sumsq_dev, max_norm, lr, step, grad_s
                    eps=1e-8):
     L.call("icadv_adam_clip_step", _p(params), _p(grads), _p(m), _p(v), params.numel(), _p(sumsq_dev), float(max_norm),
            float(grad_scale), float(lr), float(beta1), float(beta2), float(eps), int(step), _stream())
+
+
+# ------------------------------------------------------------------ 3xTF32 parity mode (csrc/icadv_split.cu)
+def split_width(c):
+    """Channels of the split form of a C-channel operand: roundup(3C, 32)."""
+    return (3 * c + 31) // 32 * 32
+
+
+def split3(x, op=0, out=None):
+    """[..., C] channels-last activation -> [..., Kp] = [hi | lo | hi | 0]; op 1 squares first."""
+    _chk(x, "x")
+    c = x.shape[-1]
+    kp = split_width(c)
+    if out is None:
+        out = torch.empty(*x.shape[:-1], kp, device=x.device, dtype=torch.float32)
+    assert out.shape[-1] == kp and out.numel() == x.numel() // c * kp
+    L.call("icadv_split3", _p(x), _p(out), x.numel() // c, c, kp, int(op), 0, _stream())
+    return out
+
+
+def split3_weight(wpack, out=None):
+    """packed weight [taps][n][k] (or a [n][k] matrix) -> [...][Kp] = [hi | hi | lo | 0]."""
+    _chk(wpack, "wpack")
+    k = wpack.shape[-1]
+    kp = split_width(k)
+    if out is None:
+        out = torch.empty(*wpack.shape[:-1], kp, device=wpack.device, dtype=torch.float32)
+    L.call("icadv_split3", _p(wpack), _p(out), wpack.numel() // k, k, kp, 0, 1, _stream())
+    return out
+
+
+def gdn_bwd_operand_split3(g, y, sc, inverse, out=None):
+    c = y.shape[-1]
+    kp = split_width(c)
+    if out is None:
+        out = torch.empty(*y.shape[:-1], kp, device=y.device, dtype=torch.float32)
+    L.call("icadv_gdn_bwd_operand_split3", _p(g), _p(y), _p(sc), _p(out), y.numel() // c, c, kp, 1 if inverse else 0,
+           _stream())
+    return out
+
+
+def gdn_apply(x, nrm, y, sc, inverse):
+    L.call("icadv_gdn_apply", _p(x), _p(nrm), _p(y), _p(sc), x.numel(), 1 if inverse else 0, _stream())
+
+
+def gdn_bwd_combine(g, y, sc, w, out, inverse):
+    L.call("icadv_gdn_bwd_combine", _p(g), _p(y), _p(sc), _p(w), _p(out), y.numel(), 1 if inverse else 0, _stream())
+
+
+def gdn_forward_split(xn, beta_eff, gamma_eff, inverse):
+    """Unfused GDN / IGDN in the parity mode: (y, sc).  gamma_eff [C][C] unrounded."""
+    c = xn.shape[-1]
+    sq = split3(xn, op=1)
+    nrm = conv(sq, split3_weight(gamma_eff.contiguous().view(1, c, c)), beta_eff.contiguous(), form=L.FORM_SCONV,
+               ksize=1, stride=1, n_ch=c, path="tc")
+    y, sc = torch.empty_like(xn), torch.empty_like(xn)
+    gdn_apply(xn, nrm, y, sc, inverse)
+    return y, sc
+
+
+def gdn_backward_split(gn, y, sc, gamma_eff, inverse):
+    c = y.shape[-1]
+    t = gdn_bwd_operand_split3(gn, y, sc, inverse)
+    w = conv(t, split3_weight(gamma_eff.t().contiguous().view(1, c, c)), None, form=L.FORM_SCONV, ksize=1, stride=1,
+             n_ch=c, path="tc")
+    out = torch.empty_like(y)
+    gdn_bwd_combine(gn, y, sc, w, out, inverse)
+    return out
+
+
+_NOISE_OFFSET = [0, None]   # running Philox block counter, and the seed it belongs to
+
+
+def uniform_noise_like(x, lo=-0.5, hi=0.5):
+    """U[lo, hi) sample shaped (and laid out) like ``x`` from the library's Philox kernel, keyed by torch's CUDA seed
+    (``torch.manual_seed`` reproduces it) and a running block counter."""
+    out = torch.empty_like(x)
+    n = out.numel()
+    seed = torch.cuda.initial_seed() & ((1 << 64) - 1)
+    if _NOISE_OFFSET[1] != seed:            # torch.manual_seed() was called: restart the stream
+        _NOISE_OFFSET[0], _NOISE_OFFSET[1] = 0, seed
+    L.call("icadv_uniform_noise", _p(out), n, C.c_uint64(seed), C.c_uint64(_NOISE_OFFSET[0]), float(lo), float(hi),
+           _stream())
+    _NOISE_OFFSET[0] += (n + 3) // 4
+    return out
+
+
+def probe_tf32_peak(iters=4000, n=256, reps=3):
+    """Measured kind::tf32 tensor-core rate of this GPU in TFLOP/s (csrc/icadv_probe.cu): best of ``reps`` launches of a
+    bare MMA loop, each timed with CUDA events.  ``iters`` sets the launch length (4000 K-blocks ~ 1 ms)."""
+    flops = C.c_double(0.0)
+    best = None
+    for _ in range(reps + 1):                       # first launch: warm-up
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        L.call("icadv_probe_tf32_peak", int(iters), int(n), C.byref(flops), _stream())
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        best = ms if best is None else min(best, ms)
+    return flops.value / (best * 1e-3) / 1e12

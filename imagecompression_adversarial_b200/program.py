@@ -15,6 +15,7 @@ import torch
 
 from . import _lib as L
 from . import ops
+from . import precision
 
 
 class UnitSpec:
@@ -73,10 +74,27 @@ class PadLaunch:
         ops.pad_rgb4(self.src, self.dst, self.active, self.n_active)
 
 
+class FnLaunch:
+    """One elementwise library call with its arguments bound (same interface as ConvPlan)."""
+    kernels = 1
+
+    def __init__(self, fn, *args):
+        self.fn, self.args = fn, args
+
+    def launch(self):
+        self.fn(*self.args)
+
+
 class StackProgram:
     def __init__(self, units, n_img, in_h, in_w, device, *, x_in=None, g_out=None, g_in=None, active=None,
-                 n_active=None, need_grad=True, round_final_out=False, round_final_gin=False):
+                 n_active=None, need_grad=True, round_final_out=False, round_final_gin=False, name="stack"):
         self.units, self.n_img, self.device = units, n_img, device
+        self.name = name
+        self.fwd_info, self.bwd_info = [], []
+        self.split = precision.split()
+        if self.split:
+            self._init_split(in_h, in_w, x_in, g_out, g_in, active, n_active, need_grad)
+            return
         self.round_final_out, self.round_final_gin = round_final_out, round_final_gin
         self.active, self.n_active = active, n_active
         f = lambda *shape: torch.empty(*shape, device=device, dtype=torch.float32)
@@ -136,10 +154,106 @@ class StackProgram:
                            if self.bwd_kind[j] == "rgb_in"}
         self._build()
 
+    # ------------------------------------------------------------------ 3xTF32 parity mode
+    def _init_split(self, in_h, in_w, x_in, g_out, g_in, active, n_active, need_grad):
+        """Launch lists of the parity mode (precision.py, csrc/icadv_split.cu): every contraction is preceded by a
+        split of its input into [hi | lo | hi] along the channels and runs with [Whi | Whi | Wlo] weights on the same
+        tensor-path kernel (linear epilogue); GDN / IGDN are unfused (square -> split -> 1x1 contraction with gamma ->
+        apply; backward: operand -> split -> 1x1 with gamma^T -> combine).  Nothing is rounded to TF32 in memory.
+        Scratch buffers are shared by all units (everything is stream-ordered)."""
+        units, n_img, device = self.units, self.n_img, self.device
+        self.round_final_out = self.round_final_gin = False
+        self.active, self.n_active = active, n_active
+        f = lambda *shape: torch.empty(*shape, device=device, dtype=torch.float32)
+        U = len(units)
+        self.x_in = x_in if x_in is not None else f(n_img, in_h, in_w, units[0].cin)
+        assert tuple(self.x_in.shape) == (n_img, in_h, in_w, units[0].cin), self.x_in.shape
+        self.hw = [(in_h, in_w)]
+        for u in units:
+            self.hw.append(ops.out_hw(u.fwd_form, u.k, u.s, *self.hw[-1]))
+        self.fwd_kind = self.bwd_kind = ["split"] * U
+        self.need_grad = need_grad
+        self.y = [f(n_img, *self.hw[j + 1], units[j].cout) for j in range(U)]
+        self.sc = [torch.empty_like(self.y[j]) if units[j].gdn is not None else None for j in range(U)]
+        self.out = self.y[-1]
+        px = lambda j: n_img * self.hw[j][0] * self.hw[j][1]       # pixels of the INPUT of unit j (px(j+1): its output)
+        n_split = max(max(px(j) * ops.split_width(units[j].cin), px(j + 1) * ops.split_width(units[j].cout))
+                      for j in range(U))
+        n_act = max(self.y[j].numel() for j in range(U))
+        self._s = f(n_split)                                      # split operand of the next contraction
+        self._a, self._b, self._c = f(n_act), f(n_act), f(n_act)  # pre-GDN output / gradient ping-pong / norm
+        self.w_fwd, self.w_bwd, self.bias = [None] * U, [None] * U, [None] * U
+        self.beta, self.gamma, self.gammaT = [None] * U, [None] * U, [None] * U
+        self.refresh_parameters()
+        if need_grad:
+            if g_out is not None:
+                assert g_out.shape == self.y[-1].shape
+            self.g_out = g_out if g_out is not None else torch.empty_like(self.y[-1])
+            self.gu = [None] * (U - 1) + [self.g_out]
+            self.g_in = g_in if g_in is not None else torch.empty_like(self.x_in)
+            assert self.g_in.shape == self.x_in.shape
+        self.fwd, self.bwd = [], []
+        sview = lambda npx, c: self._s[:npx * ops.split_width(c)].view(npx, ops.split_width(c))
+        aview = lambda buf, like: buf[:like.numel()].view(like.shape)
+        x = self.x_in
+        for j, u in enumerate(units):
+            xs = sview(px(j), u.cin).view(n_img, *self.hw[j], -1)
+            self.fwd.append(FnLaunch(ops.split3, x, 0, xs))
+            dst = self.y[j] if u.gdn is None else aview(self._a, self.y[j])
+            self.fwd.append(self._launch(xs, self.w_fwd[j], self.bias[j], dst, form=u.fwd_form, u=u, n_ch=u.cout))
+            if u.gdn is not None:
+                sq = sview(px(j + 1), u.cout).view(n_img, *self.hw[j + 1], -1)
+                nrm = aview(self._c, self.y[j])
+                self.fwd.append(FnLaunch(ops.split3, dst, 1, sq))
+                self.fwd.append(self._launch(sq, self.gamma[j], self.beta[j], nrm, form=L.FORM_SCONV, u=u, n_ch=u.cout,
+                                             ksize=1, stride=1))
+                self.fwd.append(FnLaunch(ops.gdn_apply, dst, nrm, self.y[j], self.sc[j], u.gdn.inverse))
+            x = self.y[j]
+        if not need_grad:
+            return
+        gcur = self.g_out                                          # gradient wrt the OUTPUT y[j] of the current unit
+        for j in range(U - 1, -1, -1):
+            u = units[j]
+            gsrc = gcur
+            if u.gdn is not None:
+                t = sview(px(j + 1), u.cout).view(n_img, *self.hw[j + 1], -1)
+                w = aview(self._c, self.y[j])
+                gsrc = aview(self._a, self.y[j])
+                self.bwd.append(FnLaunch(ops.gdn_bwd_operand_split3, gcur, self.y[j], self.sc[j], u.gdn.inverse, t))
+                self.bwd.append(self._launch(t, self.gammaT[j], None, w, form=L.FORM_SCONV, u=u, n_ch=u.cout, ksize=1,
+                                             stride=1))
+                self.bwd.append(FnLaunch(ops.gdn_bwd_combine, gcur, self.y[j], self.sc[j], w, gsrc, u.gdn.inverse))
+            gs = sview(px(j + 1), u.cout).view(n_img, *self.hw[j + 1], -1)
+            self.bwd.append(FnLaunch(ops.split3, gsrc, 0, gs))
+            dst = self.g_in if j == 0 else aview(self._b, self.y[j - 1])
+            self.bwd.append(self._launch(gs, self.w_bwd[j], None, dst, form=u.bwd_form, u=u, n_ch=u.cin))
+            gcur = dst
+
+    def _refresh_split(self):
+        for j, u in enumerate(self.units):
+            w = u.conv.weight
+            wf = ops.split3_weight(ops.pack_weight(w, L.PACK_CONVT_FWD if u.transposed else L.PACK_CONV_FWD))
+            wb = ops.split3_weight(ops.pack_weight(w, L.PACK_CONVT_DGRAD if u.transposed else L.PACK_CONV_DGRAD))
+            vals = [(self.w_fwd, wf), (self.w_bwd, wb)]
+            if u.conv.bias is not None:
+                vals.append((self.bias, u.conv.bias.detach().contiguous().clone()))
+            if u.gdn is not None:
+                be, ga, gaT = u.gdn.effective_parameters(round_tf32=False)
+                c = u.cout
+                vals += [(self.beta, be), (self.gamma, ops.split3_weight(ga.contiguous().view(1, c, c))),
+                         (self.gammaT, ops.split3_weight(gaT.contiguous().view(1, c, c)))]
+            for store, val in vals:
+                if store[j] is None:      # plans bake these pointers in: later refreshes copy in place
+                    store[j] = val
+                else:
+                    store[j].copy_(val)
+
     # ------------------------------------------------------------------ parameters
     def refresh_parameters(self):
         """(Re)pack weights and reparametrise GDN parameters; call after a codec update.
         Tensor-path operands are rounded to TF32 (nearest) once, here; CUDA-core layers keep fp32 weights."""
+        if self.split:
+            return self._refresh_split()
         for j, u in enumerate(self.units):
             w = u.conv.weight
             if self.fwd_kind[j] == "rgb_in":
@@ -186,33 +300,64 @@ class StackProgram:
         return self._launch(x, None, None, out, form=L.FORM_SCONV, u=u, n_ch=u.cout, ksize=1, stride=1, epi=epi,
                             acc_from_in=True, **kw)
 
+    # ------------------------------------------------------------------ algorithmic work per launch (roofline tables)
+    def _conv_macs(self, j):
+        u = self.units[j]
+        px = self.hw[j][0] * self.hw[j][1] if u.transposed else self.hw[j + 1][0] * self.hw[j + 1][1]
+        return self.n_img * px * u.k * u.k * u.cin * u.cout
+
+    def _act_bytes(self, j):
+        """fp32 bytes of the OUTPUT activation of unit j (j = -1: the stack input)."""
+        c = self.units[0].cin if j < 0 else self.units[j].cout
+        return 4 * self.n_img * self.hw[j + 1][0] * self.hw[j + 1][1] * c
+
+    def _note(self, lst, name, macs, nbytes, bound):
+        """Record the algorithmic work of the launch just appended to ``lst`` (SURVEY.md section 8d accounting:
+        every tensor read once and written once; weights stay in L2)."""
+        info = self.fwd_info if lst is self.fwd else self.bwd_info
+        while len(info) < len(lst) - 1:
+            info.append(None)
+        info.append({"name": name, "flops": 2.0 * macs, "bytes": float(nbytes), "bound": bound})
+
     def _build(self):
         U, units = len(self.units), self.units
         self.fwd, self.bwd = [], []
+        self.fwd_info, self.bwd_info = [], []
+        nm = lambda j, d: f"{self.name}.{j * 2} {'deconv' if units[j].transposed else 'conv'} {units[j].cin}->{units[j].cout} {d}"
+        end = lambda kind: "hbm" if kind in ("rgb_in", "col2im", None) else "tensor"
+        gmacs = lambda j: self.n_img * self.hw[j + 1][0] * self.hw[j + 1][1] * units[j].cout ** 2
         # an activation is rounded to TF32 where it is produced iff its consumer is a tensor-path contraction
         fwd_round = [(self.fwd_kind[j + 1] is not None if j + 1 < U else self.round_final_out) for j in range(U)]
         bwd_round = [self.bwd_kind[j] is not None for j in range(U)]   # gu[j] feeds the input-gradient of unit j
         x = self.x_in
         for j, u in enumerate(units):
             extra = {}
+            in_bytes = self._act_bytes(j - 1)
             if self.fwd_kind[j] == "rgb_in":
                 self.fwd.append(PadLaunch(x, self.x_pad[j], self.active, self.n_active))
+                in_bytes = 4 * self.x_pad[j].numel()
+                self._note(self.fwd, f"{self.name}.{j * 2} pad RGB->RGB0", 0, self._act_bytes(j - 1) + in_bytes, "hbm")
                 x, extra = self.x_pad[j], {"in_pad4": True}
             if u.gdn is None:
                 self.fwd.append(self._launch(x, self.w_fwd[j], self.bias[j], self.y[j], form=u.fwd_form, u=u,
                                              n_ch=u.cout, round_out=fwd_round[j], **extra))
+                self._note(self.fwd, nm(j, "fwd"), self._conv_macs(j), in_bytes + self._act_bytes(j), end(self.fwd_kind[j]))
             else:
                 epi = L.EPI_IGDN_FWD if u.gdn.inverse else L.EPI_GDN_FWD
                 if self.fused_fwd[j]:
                     self.fwd.append(self._launch(x, self.w_fwd[j], self.bias[j], self.y[j], form=u.fwd_form, u=u,
                                                  n_ch=u.cout, epi=epi, gmat=self.gamma[j], beta=self.beta[j],
                                                  out_scale=self.sc[j], round_out=fwd_round[j], **extra))
+                    self._note(self.fwd, nm(j, "fwd + " + ("IGDN" if u.gdn.inverse else "GDN")),
+                               self._conv_macs(j) + gmacs(j), in_bytes + 2 * self._act_bytes(j), end(self.fwd_kind[j]))
                 else:
                     self.fwd.append(self._launch(x, self.w_fwd[j], self.bias[j], self.u[j], form=u.fwd_form, u=u,
                                                  n_ch=u.cout, **extra))
+                    self._note(self.fwd, nm(j, "fwd"), self._conv_macs(j), in_bytes + self._act_bytes(j), end(self.fwd_kind[j]))
                     self.fwd.append(self._gdn_alone(self.u[j], self.y[j], j, epi, gmat=self.gamma[j],
                                                     beta=self.beta[j], out_scale=self.sc[j],
                                                     round_out=fwd_round[j]))
+                    self._note(self.fwd, f"{self.name}.{j * 2 + 1} (I)GDN fwd", gmacs(j), 3 * self._act_bytes(j), "hbm")
             x = self.y[j]
         if not self.need_grad:
             return
@@ -221,32 +366,42 @@ class StackProgram:
             self.bwd.append(self._gdn_alone(self.g_out, self.gu[-1], U - 1,
                                             L.EPI_IGDN_BWD if g.inverse else L.EPI_GDN_BWD, gmat=self.gammaT[-1],
                                             y_prev=self.y[-1], sc_prev=self.sc[-1], round_out=bwd_round[-1]))
+            self._note(self.bwd, f"{self.name}.{2 * U - 1} (I)GDN bwd", gmacs(U - 1), 4 * self._act_bytes(U - 1), "hbm")
         for j in range(U - 1, -1, -1):
             u = units[j]
             gsrc, extra = self.gu[j], {}
+            g_bytes = self._act_bytes(j)
             if self.bwd_kind[j] == "rgb_in":
                 self.bwd.append(PadLaunch(self.gu[j], self.gu_pad[j], self.active, self.n_active))
+                g_bytes = 4 * self.gu_pad[j].numel()
+                self._note(self.bwd, f"{self.name}.{j * 2} pad RGB->RGB0 (gradient)", 0, self._act_bytes(j) + g_bytes, "hbm")
                 gsrc, extra = self.gu_pad[j], {"in_pad4": True}
             if j == 0:
                 self.bwd.append(self._launch(gsrc, self.w_bwd[0], None, self.g_in, form=u.bwd_form, u=u, n_ch=u.cin,
                                              round_out=self.round_final_gin, **extra))
+                self._note(self.bwd, nm(0, "dgrad"), self._conv_macs(0), g_bytes + self._act_bytes(-1), end(self.bwd_kind[0]))
                 continue
             prev = units[j - 1]
             if prev.gdn is None:
                 self.bwd.append(self._launch(gsrc, self.w_bwd[j], None, self.gu[j - 1], form=u.bwd_form, u=u,
                                              n_ch=u.cin, round_out=bwd_round[j - 1], **extra))
+                self._note(self.bwd, nm(j, "dgrad"), self._conv_macs(j), g_bytes + self._act_bytes(j - 1), end(self.bwd_kind[j]))
                 continue
             epi = L.EPI_IGDN_BWD if prev.gdn.inverse else L.EPI_GDN_BWD
             if self.fused_bwd[j]:
                 self.bwd.append(self._launch(gsrc, self.w_bwd[j], None, self.gu[j - 1], form=u.bwd_form, u=u,
                                              n_ch=u.cin, epi=epi, gmat=self.gammaT[j - 1], y_prev=self.y[j - 1],
                                              sc_prev=self.sc[j - 1], round_out=bwd_round[j - 1], **extra))
+                self._note(self.bwd, nm(j, "dgrad + " + ("IGDN" if prev.gdn.inverse else "GDN") + " bwd"),
+                           self._conv_macs(j) + gmacs(j - 1), g_bytes + 3 * self._act_bytes(j - 1), end(self.bwd_kind[j]))
             else:
                 self.bwd.append(self._launch(gsrc, self.w_bwd[j], None, self.gy[j], form=u.bwd_form, u=u,
                                              n_ch=u.cin, **extra))
+                self._note(self.bwd, nm(j, "dgrad"), self._conv_macs(j), g_bytes + self._act_bytes(j - 1), end(self.bwd_kind[j]))
                 self.bwd.append(self._gdn_alone(self.gy[j], self.gu[j - 1], j - 1, epi, gmat=self.gammaT[j - 1],
                                                 y_prev=self.y[j - 1], sc_prev=self.sc[j - 1],
                                                 round_out=bwd_round[j - 1]))
+                self._note(self.bwd, f"{self.name}.{j * 2 - 1} (I)GDN bwd", gmacs(j - 1), 4 * self._act_bytes(j - 1), "hbm")
 
     def forward(self):
         for p in self.fwd:

@@ -92,55 +92,100 @@ def exchange_gradients(flat_grad, group=None):
     return 1.0 / world
 
 
-class FusedAdamClip:
+class FusedAdamClip(torch.optim.Optimizer):
     """Adam over ONE flat parameter buffer with ``clip_grad_norm_(max_norm)`` folded in (train.py:360-361).
 
     ``params`` keep their identity (``state_dict`` keys, shapes) but their storage becomes a view of ``self.flat`` and
-    their ``.grad`` a view of ``self.flat_grad``; ``zero_grad`` zeroes the flat buffer in place."""
+    their ``.grad`` a view of ``self.flat_grad``; ``zero_grad`` zeroes the flat buffer in place.
+
+    A ``torch.optim.Optimizer``: ``param_groups[0]["lr"]`` is the live learning rate (schedulers such as
+    ``ReduceLROnPlateau`` attach to it, coder.py:109-116 reads it back on resume), and ``state_dict()`` /
+    ``load_state_dict()`` use ``torch.optim.Adam``'s layout (per-parameter ``step`` / ``exp_avg`` / ``exp_avg_sq``), so
+    the reference's checkpoint format (train.py:443-454: ``optimizer`` / ``aux_optimizer`` entries) round-trips and a
+    resumed run continues with the same moments."""
 
     def __init__(self, params, lr, max_norm=None, betas=(0.9, 0.999), eps=1e-8):
-        self.params = [p for p in params]
-        assert self.params, "no parameters"
+        params = [p for p in params]
+        assert params, "no parameters"
+        super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=0, amsgrad=False))
+        self.params = params
         dev = self.params[0].device
         total = sum(p.numel() for p in self.params)
         self.flat = torch.empty(total, device=dev, dtype=torch.float32)
         self.flat_grad = torch.zeros(total, device=dev, dtype=torch.float32)
         self.m, self.v = torch.zeros_like(self.flat), torch.zeros_like(self.flat)
         off = 0
+        self._spans = []
         for p in self.params:
             n = p.numel()
             self.flat[off:off + n].copy_(p.detach().reshape(-1))
             p.data = self.flat[off:off + n].view(p.shape)
             p.grad = self.flat_grad[off:off + n].view(p.shape)
+            self._spans.append((off, n))
             off += n
-        self.lr, self.max_norm, self.betas, self.eps = lr, max_norm, betas, eps
+        self.max_norm = max_norm
         self.steps = 0
         self.last_sumsq = None
 
+    @property
+    def lr(self):
+        return self.param_groups[0]["lr"]
+
+    @lr.setter
+    def lr(self, value):
+        self.param_groups[0]["lr"] = value
+
     def zero_grad(self, set_to_none=False):
         self.flat_grad.zero_()
-        off = 0
-        for p in self.params:      # autograd may have replaced a view: re-attach
-            n = p.numel()
+        for p, (off, n) in zip(self.params, self._spans):      # autograd may have replaced a view: re-attach
             if p.grad is None or p.grad.data_ptr() != self.flat_grad[off:off + n].data_ptr():
                 p.grad = self.flat_grad[off:off + n].view(p.shape)
-            off += n
 
-    def step(self, group=None):
-        off = 0
-        for p in self.params:      # a gradient that autograd re-allocated is copied back into the flat buffer
-            n = p.numel()
+    def step(self, group=None, exchange=True):
+        """``exchange=False`` skips the data-parallel all-reduce (the auxiliary optimiser: ``aux_loss`` depends on the
+        parameters only, so its gradient is already identical on every rank)."""
+        for p, (off, n) in zip(self.params, self._spans):      # a gradient that autograd re-allocated is copied back
             if p.grad is not None and p.grad.data_ptr() != self.flat_grad[off:off + n].data_ptr():
                 self.flat_grad[off:off + n].copy_(p.grad.reshape(-1))
-            off += n
-        scale = exchange_gradients(self.flat_grad, group)
+        scale = exchange_gradients(self.flat_grad, group) if exchange else 1.0
         self.steps += 1
         sumsq = ops.sumsq(self.flat_grad) if self.max_norm is not None else None
         self.last_sumsq = sumsq
+        g = self.param_groups[0]
         ops.adam_clip_step(self.flat, self.flat_grad, self.m, self.v, sumsq_dev=sumsq,
-                           max_norm=self.max_norm if self.max_norm is not None else 0.0, lr=self.lr, step=self.steps,
-                           grad_scale=scale, beta1=self.betas[0], beta2=self.betas[1], eps=self.eps)
+                           max_norm=self.max_norm if self.max_norm is not None else 0.0, lr=g["lr"], step=self.steps,
+                           grad_scale=scale, beta1=g["betas"][0], beta2=g["betas"][1], eps=g["eps"])
         Fn.invalidate_pack_cache()   # the kernel updated weights behind autograd's version counters
+
+    def state_dict(self):
+        """torch.optim.Adam layout: {"state": {i: {"step", "exp_avg", "exp_avg_sq"}}, "param_groups": [...]}."""
+        state = {}
+        if self.steps > 0:
+            for i, (p, (off, n)) in enumerate(zip(self.params, self._spans)):
+                state[i] = {"step": torch.tensor(float(self.steps)),
+                            "exp_avg": self.m[off:off + n].view(p.shape).clone(),
+                            "exp_avg_sq": self.v[off:off + n].view(p.shape).clone()}
+        group = {k: v for k, v in self.param_groups[0].items() if k != "params"}
+        group["params"] = list(range(len(self.params)))
+        return {"state": state, "param_groups": [group]}
+
+    def load_state_dict(self, state_dict):
+        groups = state_dict["param_groups"]
+        if len(groups) != 1 or len(groups[0]["params"]) != len(self.params):
+            raise ValueError("loaded state dict does not match this optimiser's parameters")
+        for k, v in groups[0].items():
+            if k != "params":
+                self.param_groups[0][k] = v
+        self.m.zero_(); self.v.zero_()
+        steps = 0
+        for i, st in state_dict["state"].items():
+            p, (off, n) = self.params[int(i)], self._spans[int(i)]
+            if tuple(st["exp_avg"].shape) != tuple(p.shape):
+                raise ValueError(f"optimizer state {i}: shape {tuple(st['exp_avg'].shape)} != {tuple(p.shape)}")
+            self.m[off:off + n].copy_(st["exp_avg"].reshape(-1))
+            self.v[off:off + n].copy_(st["exp_avg_sq"].reshape(-1))
+            steps = max(steps, int(float(st["step"])))
+        self.steps = steps
 
 
 def configure_optimizers(net, args):
@@ -153,10 +198,18 @@ def configure_optimizers(net, args):
             FusedAdamClip([named[n] for n in aux], lr=1e-3, max_norm=None))
 
 
-def adv_train_step(batch_x, net, args, criterion, optimizer, aux_optimizer, group=None):
-    """One iteration of train.py:335-366 with N_ADV = 0.  Returns (out_criterion, aux_loss)."""
+def adv_train_step(batch_x, net, args, criterion, optimizer, aux_optimizer, group=None, timings=None):
+    """One iteration of train.py:335-366 with N_ADV = 0.  Returns (out_criterion, aux_loss).
+    ``timings`` (a dict of lists, benchmark use): receives the CUDA-event times in ms of the attack part
+    (``attack_ms``), the codec update (``update_ms``) and, inside it, the gradient all-reduce (``allreduce_ms``);
+    measuring them synchronises the stream three times per step."""
     from .attack import attack_
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)] if timings is not None else None
+    if ev:
+        ev[0].record()
     batch_adv = attack_(batch_x, net, args)[0].detach()                  # :342-343
+    if ev:
+        ev[1].record()
     net.train()                                                          # :346
     batch = batch_adv.clone()                                            # :347
     result = net(batch)                                                  # :351
@@ -164,10 +217,20 @@ def adv_train_step(batch_x, net, args, criterion, optimizer, aux_optimizer, grou
     optimizer.zero_grad()
     aux_optimizer.zero_grad()
     out["loss"].backward()                                               # :359
+    if ev:
+        ev[2].record()
     optimizer.step(group)                                                # all-reduce + clip_grad_norm_(1.0) + Adam (:360-361)
+    if ev:
+        ev[3].record()
     aux = net.aux_loss()                                                 # :363 (parameter-only math: identical on all ranks)
     aux.backward()
-    aux_optimizer.step(None)
+    aux_optimizer.step(exchange=False)
+    if ev:
+        ev[4].record()
+        torch.cuda.synchronize()
+        timings.setdefault("attack_ms", []).append(ev[0].elapsed_time(ev[1]))
+        timings.setdefault("update_ms", []).append(ev[1].elapsed_time(ev[4]))
+        timings.setdefault("allreduce_ms", []).append(ev[2].elapsed_time(ev[3]))   # all-reduce + sumsq + clip/Adam kernel
     return out, aux
 
 

@@ -326,6 +326,38 @@ int icadv_ssim_level_backward(const float* X, const float* Y, const float* coef_
 int icadv_avgpool2(const float* x, float* y, int planes, int h, int w, int pad_h, int pad_w,
                    icadv_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------
+ * 3xTF32 parity mode (csrc/icadv_split.cu).  The contractions of the codec stacks
+ * (anchors/utils.py:112-130; compressai GDN, utils/ops.py:58-97) stay on the tcgen05 kernels, but every fp32
+ * operand is split x = hi + lo (both TF32) and the product is hi*Whi + lo*Whi + hi*Wlo, accumulated in fp32 in
+ * TMEM.  The split is a layout: activations [px][C] -> [px][Kp] = [hi | lo | hi | 0] (layout 0), packed weights
+ * [rows][C] -> [rows][Kp] = [hi | hi | lo | 0] (layout 1), Kp = roundup(3C, 32); the contraction is then launched
+ * with k_ch = Kp.  op 1 squares the input first (operand of the GDN normalisation).  GDN / IGDN run unfused in this
+ * mode: split3(op 1) -> 1x1 contraction with gamma, bias beta -> icadv_gdn_apply; backward: icadv_gdn_bwd_operand_split3
+ * -> 1x1 contraction with gamma^T -> icadv_gdn_bwd_combine.  Purpose: per-step losses of attack_rd.py:332-379,506-560
+ * within 1e-3 of the fp32 reference.
+ * ------------------------------------------------------------------------------------------ */
+int icadv_split3(const float* x, float* out, int64_t n_px, int C, int Kp, int op, int layout, icadv_stream_t stream);
+int icadv_gdn_bwd_operand_split3(const float* g, const float* y, const float* sc, float* out, int64_t n_px, int C, int Kp,
+                                 int inverse, icadv_stream_t stream);
+/* sc = norm^(-1/2) (inverse: ^(+1/2)); y = x * sc */
+int icadv_gdn_apply(const float* x, const float* nrm, float* y, float* sc, int64_t n, int inverse,
+                    icadv_stream_t stream);
+/* out = g sc - (y/sc) w   (inverse: +) */
+int icadv_gdn_bwd_combine(const float* g, const float* y, const float* sc, const float* w, float* out, int64_t n,
+                          int inverse, icadv_stream_t stream);
+
+/* U[lo, hi) noise of the training-mode quantiser (compressai quantize(x, "noise"): x + U(-.5,.5), call site
+ * anchors/model.py:102; EntropyBottleneck / GaussianConditional in train mode): Philox4x32-10 keyed by `seed`,
+ * counter `offset` + element block, so a (seed, offset) pair reproduces the sample on any launch geometry. */
+int icadv_uniform_noise(float* out, int64_t n, uint64_t seed, uint64_t offset, float lo, float hi,
+                        icadv_stream_t stream);
+
+/* Roofline denominator for the contraction kernels (bench.py): one launch of a bare tcgen05.mma kind::tf32 loop
+ * (128 x n x 8 instructions on static shared-memory operands, one CTA per SM, `iters` K-blocks of four MMAs each).
+ * The caller times the launch with CUDA events; *flops_out receives the FLOP it performs. */
+int icadv_probe_tf32_peak(int iters, int n, double* flops_out, icadv_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

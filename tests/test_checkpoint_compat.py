@@ -28,6 +28,27 @@ def _zoo_style(sd, model, new_names):
         out["gaussian_conditional._offset"] = torch.full((64,), -48, dtype=torch.int32)
         out["gaussian_conditional._cdf_length"] = torch.full((64,), 99, dtype=torch.int32)
         out["gaussian_conditional.scale_table"] = torch.exp(torch.linspace(-2.2, 5.5, 64))
+    out.update(_compressai_constant_buffers(sd, model))
+    return out
+
+
+def _compressai_constant_buffers(sd, model):
+    """The persistent 1-element buffers a CompressAI (1.1.x - 1.2.x) state_dict carries next to the parameters:
+    NonNegativeParametrizer.pedestal, LowerBound.bound (GDN reparametrisers, likelihood bounds, scale bound).
+    Key list written from CompressAI's source (compressai/ops/parametrizers.py, ops/bound_ops.py, entropy_models.py);
+    the package itself is not installable here, so this list -- not a real checkpoint file -- is what pins it."""
+    out = {}
+    pedestal = (2.0 ** -18) ** 2
+    for k in sd:
+        if k.endswith(".beta") and k[:-5] + ".gamma" in sd:          # a GDN module
+            base = k[:-5]
+            for rep, minimum in (("beta_reparam", 1e-6), ("gamma_reparam", 0.0)):
+                out[f"{base}.{rep}.pedestal"] = torch.tensor([pedestal])
+                out[f"{base}.{rep}.lower_bound.bound"] = torch.tensor([(minimum + pedestal) ** 0.5])
+    out["entropy_bottleneck.likelihood_lower_bound.bound"] = torch.tensor([1e-9])
+    if model != "factorized":
+        out["gaussian_conditional.likelihood_lower_bound.bound"] = torch.tensor([1e-9])
+        out["gaussian_conditional.lower_bound_scale.bound"] = torch.tensor([0.11])
     return out
 
 
@@ -42,6 +63,11 @@ def test_zoo_style_state_dict_loads_and_round_trips(model, quality, new_names):
     res = net.load_state_dict(zoo, strict=True)
     assert not res.missing_keys and not res.unexpected_keys
     sd = net.state_dict()
+    # what this package writes has exactly the key set of a CompressAI checkpoint of the model (old-style names)
+    canon = _zoo_style(onet.state_dict(), model, False)
+    assert set(sd.keys()) == set(canon.keys()), set(sd.keys()) ^ set(canon.keys())
+    for k, v in _compressai_constant_buffers(onet.state_dict(), model).items():
+        assert sd[k].shape == (1,) and abs(float(sd[k]) - float(v)) <= 1e-6 * abs(float(v)), k
     for k, v in onet.state_dict().items():          # every parameter arrived (old-style names are the canonical ones)
         assert torch.equal(sd[k], v), k
     for k, v in zoo.items():

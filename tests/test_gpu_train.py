@@ -33,7 +33,9 @@ def share_noise(onet, pnet, x, dev, seed=5):
     with torch.no_grad():
         onet.eval()
         y = onet.g_a(x)
-        z = onet.h_a(torch.abs(y)) if hasattr(onet, "h_a") else None
+        z = None
+        if hasattr(onet, "h_a"):                       # hyper: h_a(|y|); context / cheng2020: h_a(y) (anchors/model.py:92,98)
+            z = onet.h_a(y if hasattr(onet, "context_prediction") else torch.abs(y))
     ny = torch.rand(y.shape, device=dev, generator=g) - 0.5
     for net in (onet, pnet):
         if z is not None:
@@ -45,6 +47,82 @@ def share_noise(onet, pnet, x, dev, seed=5):
 
 def rel(a, b):
     return float((a - b).pow(2).sum().sqrt() / b.pow(2).sum().sqrt().clamp(min=1e-30))
+
+
+@pytest.mark.parametrize("model,quality", [("context", 1), ("cheng2020", 1)])
+def test_autoregressive_families_train_g_a_through_the_distortion_term(dev, model, quality):
+    """The train-mode quantiser ``y + noise`` is differentiable (compressai quantize(.,"noise"), anchors/model.py:102):
+    the distortion gradient through g_s(y_hat) and context_prediction(y_hat) must reach g_a.  Every g_a parameter
+    gradient of one RD-loss backward against the oracle, plus a direct check that the distortion term alone
+    (lambda-weighted MSE, no rate) produces a non-zero g_a gradient."""
+    from imagecompression_adversarial_b200 import training as ptr
+    from oracle import attack as oatk
+    from oracle.attack import synthetic_image
+    onet, pnet = pair(model, quality, dev)
+    x = torch.cat([synthetic_image(i, 128, 128) for i in range(2)]).to(dev)
+    share_noise(onet, pnet, x, dev)
+    lm = ptr.LAMBDA_MSE[quality]
+    ocrit, pcrit = oatk.RateDistortionLoss("mse", lm).to(dev), ptr.RateDistortionLoss("mse", lm)
+    onet.train(); pnet.train()
+    oout = ocrit(onet(x), x)
+    onet.zero_grad(); oout["loss"].backward()
+    pout = pcrit(pnet(x), x)
+    pnet.zero_grad(); pout["loss"].backward()
+    og = {n: q.grad.detach().clone() for n, q in onet.named_parameters() if q.grad is not None}
+    pg = {n: q.grad.detach().clone() for n, q in pnet.named_parameters() if q.grad is not None}
+    ga = [n for n in og if n.startswith("g_a.") and float(og[n].abs().max()) > 0]
+    assert ga and set(ga) <= set(pg)
+    bound = 2e-2 if model == "cheng2020" else 1e-2        # TF32 contractions, 8 / 20 layers deep
+    worst = max((rel(pg[n], og[n]), n) for n in ga)
+    assert worst[0] < bound, worst
+    assert abs(float(pout["loss"]) - float(oout["loss"])) <= 3e-3 * abs(float(oout["loss"]))
+    # distortion term alone
+    pnet.zero_grad()
+    (pcrit(pnet(x), x)["distortion_loss"]).backward()
+    assert float(pnet.g_a[0].conv1.weight.grad.abs().max() if model == "cheng2020" else
+                 pnet.g_a[0].weight.grad.abs().max()) > 0
+
+
+def test_optimizer_checkpoint_resume_continues_identically(dev):
+    """train.py:443-454 / coder.py:104-116: save {state_dict, optimizer, aux_optimizer} after two steps, resume in a
+    fresh model + optimisers, take a third step in both -- bit-identical weights."""
+    import io
+    from imagecompression_adversarial_b200 import models as pm
+    from imagecompression_adversarial_b200 import training as ptr
+    from oracle import attack as oatk
+    from oracle.attack import synthetic_image
+    torch.manual_seed(0)
+    net = pm.init_model("hyper", 1, "mse", pretrained=False).to(dev)
+    x = torch.cat([synthetic_image(i, 64, 64) for i in range(2)]).to(dev)
+    args = oatk.default_args(model="hyper", quality=1, metric="mse", lr_train=1e-4)
+    crit = ptr.RateDistortionLoss("mse", ptr.LAMBDA_MSE[1])
+    opt, aux = ptr.configure_optimizers(net, args)
+
+    def step(net, opt, aux, seed):
+        g = torch.Generator(device=dev).manual_seed(seed)
+        net.train()
+        net.gaussian_conditional.noise_override = torch.rand(2, 192, 4, 4, device=dev, generator=g) - 0.5
+        net.entropy_bottleneck.noise_override = torch.rand(2, 128, 1, 1, device=dev, generator=g) - 0.5
+        out = crit(net(x), x)
+        opt.zero_grad(); aux.zero_grad()
+        out["loss"].backward()
+        opt.step()
+        a = net.aux_loss(); a.backward(); aux.step(exchange=False)
+
+    step(net, opt, aux, 1); step(net, opt, aux, 2)
+    buf = io.BytesIO()
+    torch.save({"epoch": 0, "step": 2, "state_dict": net.state_dict(), "optimizer": opt.state_dict(),
+                "aux_optimizer": aux.state_dict()}, buf)
+    buf.seek(0)
+    ck = torch.load(buf, map_location=dev, weights_only=False)
+    net2 = pm.init_model("hyper", 1, "mse", pretrained=False).to(dev)
+    net2.load_state_dict(ck["state_dict"], strict=True)
+    opt2, aux2 = ptr.configure_optimizers(net2, args)
+    opt2.load_state_dict(ck["optimizer"]); aux2.load_state_dict(ck["aux_optimizer"])
+    assert opt2.steps == 2 and opt2.param_groups[0]["lr"] == args.lr_train
+    step(net, opt, aux, 3); step(net2, opt2, aux2, 3)
+    for (n, a), (_, b) in zip(net.named_parameters(), net2.named_parameters()):
+        assert torch.equal(a.detach(), b.detach()), n
 
 
 @pytest.mark.parametrize("model,quality,metric", [("hyper", 1, "mse"), ("factorized", 1, "mse"), ("hyper", 3, "ms-ssim")])
