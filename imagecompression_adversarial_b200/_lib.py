@@ -107,12 +107,13 @@ _SIGS = {
     "icadv_ssim_level": (C.c_int, [_fp, _fp, _fp, _fp, _fp, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float), C.c_int,
                                    C.c_int, C.c_float, C.c_float, C.c_void_p]),
     "icadv_ssim_level_backward": (C.c_int, [_fp, _fp, _fp, _fp, _fp, _fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
-                                            C.c_int, C.c_int, C.POINTER(C.c_float), C.c_int, C.c_float, C.c_float,
+                                            C.c_int, C.c_int, C.POINTER(C.c_float), C.c_int, C.c_int, C.c_float, C.c_float,
                                             C.c_void_p]),
     "icadv_avgpool2": (C.c_int, [_fp, _fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "icadv_sum_sqdiff": (C.c_int, [_fp, _fp, _fp, _fp, C.c_int, C.c_int64, C.c_void_p]),
-    "icadv_split3": (C.c_int, [_fp, _fp, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
-    "icadv_gdn_bwd_operand_split3": (C.c_int, [_fp, _fp, _fp, _fp, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "icadv_split3": (C.c_int, [_fp, _fp, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "icadv_gdn_bwd_operand_split3": (C.c_int, [_fp, _fp, _fp, _fp, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "icadv_sum_slices": (C.c_int, [_fp, _fp, C.c_int64, C.c_int, C.c_void_p]),
     "icadv_gdn_apply": (C.c_int, [_fp, _fp, _fp, _fp, C.c_int64, C.c_int, C.c_void_p]),
     "icadv_gdn_bwd_combine": (C.c_int, [_fp, _fp, _fp, _fp, _fp, C.c_int64, C.c_int, C.c_void_p]),
     "icadv_probe_tf32_peak": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_double), C.c_void_p]),

@@ -115,7 +115,8 @@ __global__ void avgpool2_kernel(const float* __restrict__ x, float* __restrict__
 
 
 // ---------------------------------------------------------------------------------------------------------
-// Backward of one MS-SSIM level (variant 1, valid separable window) with respect to X.
+// Backward of one MS-SSIM level with respect to X: variant 1 (valid separable window) and variant 2 (zero "same"
+// padding, utils/torch_msssim.py:26-52 -- its 2-D window is the outer product of the 1-D taps, so it is separable too).
 //   value_l[plane] = mean_px map(X, Y),  map = cs (levels 0..3) or ssim (last level)
 //   dX = coef_cs[plane] * d(sum cs)/dX + coef_ss[plane] * d(sum ssim)/dX + 0.25 * dXnext[pool parent]
 // One block produces a 32x32 tile of dX.  The filtered statistics are RECOMPUTED from a 52x52 input tile (no
@@ -130,6 +131,7 @@ constexpr int kBX = kBA + kMaxWin - 1;  // 52: input tile
 struct SsimBwdParams {
   const float* X; const float* Y; const float* coef_cs; const float* coef_ss; const float* dXnext; float* dX;
   int h, w, oh, ow, win, nh, nw, ph, pw;
+  int so;   // statistics-map position of tile row 0 relative to the dX tile: win-1 (valid window) or win/2 (zero "same" padding)
   float c1, c2;
   float taps[kMaxWin];
 };
@@ -173,7 +175,9 @@ __global__ void __launch_bounds__(256) ssim_level_bwd_kernel(const SsimBwdParams
   __syncthreads();
   for (int i = threadIdx.x; i < as * as; i += 256) {   // vertical forward filter + per-position coefficients
     const int r = i / as, c = i % as;
-    const int oy = ty0 - R + r, ox = tx0 - R + c;      // position in the valid statistics map
+    // position in the statistics map.  Valid window: map position o reads inputs o .. o+R; "same" padding (R = 2 pad):
+    // o-pad .. o+pad -- in both cases the 52x52 input tile starts R before the dX tile, only this origin differs
+    const int oy = ty0 - p.so + r, ox = tx0 - p.so + c;
     float A12 = 0.f, A11 = 0.f, B = 0.f;
     if (oy >= 0 && oy < p.oh && ox >= 0 && ox < p.ow) {
       float m1 = 0.f, m2 = 0.f, s11 = 0.f, s22 = 0.f, s12 = 0.f;
@@ -270,13 +274,16 @@ int icadv_avgpool2(const float* x, float* y, int planes, int h, int w, int pad_h
 
 int icadv_ssim_level_backward(const float* X, const float* Y, const float* coef_cs, const float* coef_ss,
                               const float* dXnext, float* dX, int planes, int h, int w, int next_h, int next_w,
-                              int pad_h, int pad_w, const float* win_taps_host, int win, float c1, float c2,
-                              icadv_stream_t stream) {
+                              int pad_h, int pad_w, const float* win_taps_host, int win, int same_pad, float c1,
+                              float c2, icadv_stream_t stream) {
   ICADV_REQUIRE(X && Y && coef_cs && coef_ss && dX && win_taps_host, "null pointer");
   ICADV_REQUIRE(win >= 1 && win <= kMaxWin && h >= win && w >= win, "bad window / image size");
+  ICADV_REQUIRE(!same_pad || win % 2 == 1, "same padding needs an odd window");
   SsimBwdParams p;
   p.X = X; p.Y = Y; p.coef_cs = coef_cs; p.coef_ss = coef_ss; p.dXnext = dXnext; p.dX = dX;
-  p.h = h; p.w = w; p.oh = h - win + 1; p.ow = w - win + 1; p.win = win;
+  p.h = h; p.w = w; p.win = win;
+  p.oh = same_pad ? h : h - win + 1; p.ow = same_pad ? w : w - win + 1;
+  p.so = same_pad ? win / 2 : win - 1;
   p.nh = next_h; p.nw = next_w; p.ph = pad_h; p.pw = pad_w; p.c1 = c1; p.c2 = c2;
   for (int k = 0; k < kMaxWin; ++k) p.taps[k] = k < win ? win_taps_host[k] : 0.f;
   const size_t smem = sizeof(float) * (2 * kBX * (kBX + 1) + 5 * kBX * (kBA + 1) + 3 * kBA * (kBA + 1) + 3 * kBA * (kBT + 1));

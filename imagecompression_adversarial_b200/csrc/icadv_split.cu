@@ -24,13 +24,15 @@ __device__ __forceinline__ float split_pick(float v, int seg, int layout) {
   return want_lo ? round_tf32(v - hi) : hi;
 }
 
-// out[px][Kp]: layout 0 (activation) [hi | lo | hi | 0], layout 1 (weight) [hi | hi | lo | 0]; op 1: v = x^2
-__global__ void split3_kernel(const float* __restrict__ x, float* __restrict__ out, int64_t n_px, int C, int Kp, int op,
-                              int layout) {
-  const int64_t total = n_px * Kp;
+// out[G][px][Ks] holding split channel kk = g * Ks + k of [hi | lo | hi | 0] (layout 0, activation) or
+// [hi | hi | lo | 0] (layout 1, weight); op 1: v = x^2
+__global__ void split3_kernel(const float* __restrict__ x, float* __restrict__ out, int64_t n_px, int C, int Ks, int G,
+                              int op, int layout) {
+  const int64_t total = n_px * Ks * G;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int k = (int)(i % Kp);
-    const int64_t px = i / Kp;
+    const int kl = (int)(i % Ks);
+    const int64_t px = (i / Ks) % n_px;
+    const int k = (int)(i / ((int64_t)Ks * n_px)) * Ks + kl;
     const int seg = k / C, c = k - seg * C;
     float v = seg < 3 ? x[px * C + c] : 0.f;
     if (op == 1) v = v * v;
@@ -40,12 +42,13 @@ __global__ void split3_kernel(const float* __restrict__ x, float* __restrict__ o
 
 // operand of the normalisation GEMM of the GDN / IGDN backward, split: t = g y sc^2 (GDN) or g y / sc^2 (IGDN)
 __global__ void gdn_bwd_operand_kernel(const float* __restrict__ g, const float* __restrict__ y,
-                                       const float* __restrict__ sc, float* __restrict__ out, int64_t n_px, int C, int Kp,
-                                       int inverse) {
-  const int64_t total = n_px * Kp;
+                                       const float* __restrict__ sc, float* __restrict__ out, int64_t n_px, int C, int Ks,
+                                       int G, int inverse) {
+  const int64_t total = n_px * Ks * G;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int k = (int)(i % Kp);
-    const int64_t px = i / Kp;
+    const int kl = (int)(i % Ks);
+    const int64_t px = (i / Ks) % n_px;
+    const int k = (int)(i / ((int64_t)Ks * n_px)) * Ks + kl;
     const int seg = k / C, c = k - seg * C;
     float t = 0.f;
     if (seg < 3) {
@@ -76,6 +79,15 @@ __global__ void gdn_bwd_combine_kernel(const float* __restrict__ g, const float*
     const float s = sc[i];
     const float xs = s > 0.f ? y[i] / s : 0.f;
     out[i] = inverse ? g[i] * s + xs * w[i] : g[i] * s - xs * w[i];
+  }
+}
+
+// out = sum over the G partial outputs of the K-slices, added in order in round-to-nearest fp32
+__global__ void sum_slices_kernel(const float* __restrict__ parts, float* __restrict__ out, int64_t n, int G) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    float acc = parts[i];
+    for (int g = 1; g < G; ++g) acc += parts[(int64_t)g * n + i];
+    out[i] = acc;
   }
 }
 
@@ -120,18 +132,28 @@ using namespace icadv;
 
 extern "C" {
 
-int icadv_split3(const float* x, float* out, int64_t n_px, int C, int Kp, int op, int layout, icadv_stream_t stream) {
-  ICADV_REQUIRE(x && out && n_px > 0 && C > 0 && Kp >= 3 * C && Kp % 32 == 0, "split3: need Kp >= 3C, Kp %% 32 == 0");
+int icadv_split3(const float* x, float* out, int64_t n_px, int C, int Ks, int G, int op, int layout,
+                 icadv_stream_t stream) {
+  ICADV_REQUIRE(x && out && n_px > 0 && C > 0 && G >= 1 && Ks % 32 == 0 && (int64_t)Ks * G >= 3 * (int64_t)C,
+                "split3: need Ks %% 32 == 0 and Ks * G >= 3C");
   ICADV_REQUIRE((op == 0 || op == 1) && (layout == 0 || layout == 1), "split3: bad op / layout");
-  split3_kernel<<<grid_for(n_px * Kp), 256, 0, as_stream(stream)>>>(x, out, n_px, C, Kp, op, layout);
+  split3_kernel<<<grid_for(n_px * Ks * G), 256, 0, as_stream(stream)>>>(x, out, n_px, C, Ks, G, op, layout);
   ICADV_CUDA_TRY(cudaGetLastError());
   return ICADV_OK;
 }
 
-int icadv_gdn_bwd_operand_split3(const float* g, const float* y, const float* sc, float* out, int64_t n_px, int C, int Kp,
-                                 int inverse, icadv_stream_t stream) {
-  ICADV_REQUIRE(g && y && sc && out && n_px > 0 && C > 0 && Kp >= 3 * C && Kp % 32 == 0, "gdn_bwd_operand: bad args");
-  gdn_bwd_operand_kernel<<<grid_for(n_px * Kp), 256, 0, as_stream(stream)>>>(g, y, sc, out, n_px, C, Kp, inverse);
+int icadv_gdn_bwd_operand_split3(const float* g, const float* y, const float* sc, float* out, int64_t n_px, int C, int Ks,
+                                 int G, int inverse, icadv_stream_t stream) {
+  ICADV_REQUIRE(g && y && sc && out && n_px > 0 && C > 0 && G >= 1 && Ks % 32 == 0 && (int64_t)Ks * G >= 3 * (int64_t)C,
+                "gdn_bwd_operand: bad args");
+  gdn_bwd_operand_kernel<<<grid_for(n_px * Ks * G), 256, 0, as_stream(stream)>>>(g, y, sc, out, n_px, C, Ks, G, inverse);
+  ICADV_CUDA_TRY(cudaGetLastError());
+  return ICADV_OK;
+}
+
+int icadv_sum_slices(const float* parts, float* out, int64_t n, int G, icadv_stream_t stream) {
+  ICADV_REQUIRE(parts && out && n > 0 && G >= 1, "sum_slices: bad args");
+  sum_slices_kernel<<<grid_for(n), 256, 0, as_stream(stream)>>>(parts, out, n, G);
   ICADV_CUDA_TRY(cudaGetLastError());
   return ICADV_OK;
 }

@@ -38,11 +38,11 @@ def tc_shape(k_ch, n_ch):
     return n_ch <= 256 or any(n_ch % t == 0 for t in range(256, 31, -32))   # wider outputs are tiled over N
 
 
-def packed(weight, kind):
+def packed(weight, kind, split_geom=None):
     """Packed copy of a layer weight, cached on (storage, version) so it is rebuilt only after an update.
-    Weights of tensor-path contractions are rounded to TF32 (nearest) here."""
-    split = precision.split()
-    key = (id(weight), kind, split)
+    Weights of tensor-path contractions are rounded to TF32 (nearest) here; with ``split_geom = (Ks, G)`` (parity mode)
+    they are returned as G slices of [Whi | Whi | Wlo] instead (csrc/icadv_split.cu)."""
+    key = (id(weight), kind, split_geom)
     hit = _PACK_CACHE.get(key)
     # the entry must belong to THIS tensor object (ids and addresses are recycled once a model is freed)
     if hit is not None and hit[3]() is weight and hit[0] == weight._version and hit[2] == tuple(weight.shape) \
@@ -54,28 +54,29 @@ def packed(weight, kind):
     a, b = weight.shape[0], weight.shape[1]
     n_ch, k_ch = {L.PACK_CONV_FWD: (a, b), L.PACK_CONV_DGRAD: (b, a), L.PACK_CONVT_FWD: (b, a),
                   L.PACK_CONVT_DGRAD: (a, b)}[kind]
-    if split and tc_shape(k_ch, n_ch):      # parity mode: [Whi | Whi | Wlo] along K (csrc/icadv_split.cu)
-        wp = ops.split3_weight(ops.pack_weight(weight, kind, round_tf32=False))
+    if split_geom is not None:
+        wp = ops.split3_weight(ops.pack_weight(weight, kind, round_tf32=False), *split_geom)
     else:
-        wp = ops.pack_weight(weight, kind, round_tf32=tc_shape(k_ch, n_ch))
+        wp = ops.pack_weight(weight, kind, round_tf32=tc_shape(k_ch, n_ch) and not precision.split())
     _PACK_CACHE[key] = (weight._version, wp, tuple(weight.shape), weakref.ref(weight), weight.data_ptr())
     return wp
 
 
-def tc_operand(xn, k_ch, n_ch):
-    """Prepare an activation that is about to feed a tensor-path contraction: round to TF32 (nearest), or -- parity
-    mode -- expand it to the three-term split form [hi | lo | hi] along the channel axis."""
+def contract(xn, weight, kind, bias, *, form, ksize, stride, n_ch, act=L.ACT_NONE):
+    """One contraction of the module-by-module path on a channels-last activation, in the current precision mode:
+    speed mode -- operand rounded to TF32 (nearest), one launch; parity mode -- operand and weight in the K-sliced
+    three-term split form, one tensor-path launch per slice, partial outputs added in fp32.  Shapes the tensor path does
+    not take run on the fp32 CUDA-core kernels in both modes."""
+    k_ch = xn.shape[-1]
     if not tc_shape(k_ch, n_ch):
-        return xn
-    return ops.split3(xn.contiguous()) if precision.split() else ops.unary(xn, 5)
-
-
-def _path(k_ch, n_ch):
-    """Parity mode pins the kernel choice to the operand preparation above (split operands <-> tensor path; every
-    other shape runs on the fp32 CUDA-core kernels)."""
-    if not precision.split():
-        return "auto"
-    return "tc" if tc_shape(k_ch, n_ch) else "simt"
+        return ops.conv(xn, packed(weight, kind), bias, form=form, ksize=ksize, stride=stride, n_ch=n_ch, act=act,
+                        path="simt" if precision.split() else "auto")
+    if precision.split():
+        geom = ops.split_geom(k_ch, form, ksize, stride)
+        return ops.conv_sliced(ops.split3(xn.contiguous(), *geom), packed(weight, kind, geom), bias, form=form,
+                               ksize=ksize, stride=stride, n_ch=n_ch, act=act)
+    return ops.conv(ops.unary(xn, 5), packed(weight, kind), bias, form=form, ksize=ksize, stride=stride, n_ch=n_ch,
+                    act=act)
 
 
 class Contraction(torch.autograd.Function):
@@ -87,9 +88,8 @@ class Contraction(torch.autograd.Function):
         kind = L.PACK_CONVT_FWD if transposed else L.PACK_CONV_FWD
         form = L.FORM_TCONV if transposed else L.FORM_SCONV
         n_ch = weight.shape[1] if transposed else weight.shape[0]
-        out = ops.conv(tc_operand(xn, xn.shape[-1], n_ch), packed(weight, kind),
-                       bias.detach() if bias is not None else None, form=form, ksize=ksize, stride=stride, n_ch=n_ch,
-                       act=act, path=_path(xn.shape[-1], n_ch))
+        out = contract(xn, weight, kind, bias.detach() if bias is not None else None, form=form, ksize=ksize,
+                       stride=stride, n_ch=n_ch, act=act)
         ctx.save_for_backward(xn, weight, out if act != L.ACT_NONE else None)
         ctx.cfg = (ksize, stride, transposed, act, param_grads, bias is not None)
         return to_nchw(out)
@@ -105,9 +105,8 @@ class Contraction(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             kind = L.PACK_CONVT_DGRAD if transposed else L.PACK_CONV_DGRAD
             form = L.FORM_SCONV if transposed else L.FORM_TCONV
-            gx = to_nchw(ops.conv(tc_operand(gn.contiguous(), gn.shape[-1], xn.shape[-1]), packed(weight, kind), None,
-                                  form=form, ksize=ksize, stride=stride, n_ch=xn.shape[-1],
-                                  path=_path(gn.shape[-1], xn.shape[-1])))
+            gx = to_nchw(contract(gn.contiguous(), weight, kind, None, form=form, ksize=ksize, stride=stride,
+                                  n_ch=xn.shape[-1]))
         if param_grads and (ctx.needs_input_grad[1] or (has_bias and ctx.needs_input_grad[2])):
             form = L.FORM_TCONV if transposed else L.FORM_SCONV
             n_ch = weight.shape[1] if transposed else weight.shape[0]

@@ -2,7 +2,9 @@
 
 ``ms_ssim`` / ``MS_SSIM`` mirror ``pytorch_msssim`` (attack_rd.py:19; train.py:18,44) -- variant 1;
 ``MS_SSIM_v2`` mirrors ``utils/torch_msssim.MS_SSIM`` (utils/torch_msssim.py:18-76) -- variant 2.
-Forward only for now (final metrics run under no_grad: self_ensemble.py:172).
+All three are differentiable with respect to BOTH images (autograd Functions whose backward is
+``ssim_level_backward_kernel``): the unmodified ``attack_our`` ms-ssim branches (``1 - ms_ssim(im_s, im_in)``,
+``ms_ssim(output_, output_s)``, attack_rd.py:336,362) and the ms-ssim RD loss (train.py:44,88) differentiate through them.
 """
 import ctypes as C
 import math
@@ -42,12 +44,41 @@ def _pool(X, ph, pw):
     return out
 
 
+class _MsSsimFn(torch.autograd.Function):
+    """Variant 1 with gradients to both images.  The forward is the plain kernel composition; the backward recomputes
+    the pyramid (nothing image-sized is saved except the two inputs) through ``ms_ssim_value_and_grad``."""
+
+    @staticmethod
+    def forward(ctx, X, Y, size_average, kw):
+        ctx.save_for_backward(X.detach(), Y.detach())
+        ctx.size_average, ctx.kw = size_average, kw
+        return _ms_ssim_forward(X, Y, size_average=size_average, **kw)
+
+    @staticmethod
+    def backward(ctx, g):
+        X, Y = ctx.saved_tensors
+        B = X.shape[0]
+        up = (g.reshape(1).expand(B) / B) if ctx.size_average else g.reshape(B)
+        up = up.to(torch.float32).contiguous()
+        kw = ctx.kw
+        gX = ms_ssim_value_and_grad(X, Y, up, **kw)[1] if ctx.needs_input_grad[0] else None
+        gY = ms_ssim_value_and_grad(Y, X, up, **kw)[1] if ctx.needs_input_grad[1] else None   # SSIM is symmetric
+        return gX, gY, None, None
+
+
 def ms_ssim(X, Y, data_range=1.0, size_average=True, win_size=11, win_sigma=1.5, weights=WEIGHTS, K=(0.01, 0.03)):
-    """pytorch_msssim.ms_ssim (variant 1)."""
+    """pytorch_msssim.ms_ssim (variant 1); differentiable w.r.t. X and Y."""
     if X.shape != Y.shape or X.dim() != 4:
         raise ValueError("Input images should be 4-d tensors of the same shape")
     assert min(X.shape[-2:]) > (win_size - 1) * 2 ** 4, \
         "Image size should be larger than %d due to the 4 downsamplings in ms-ssim" % ((win_size - 1) * 2 ** 4)
+    kw = dict(data_range=data_range, win_size=win_size, win_sigma=win_sigma, weights=tuple(weights), K=tuple(K))
+    if torch.is_grad_enabled() and (X.requires_grad or Y.requires_grad):
+        return _MsSsimFn.apply(X, Y, size_average, kw)
+    return _ms_ssim_forward(X, Y, size_average=size_average, **kw)
+
+
+def _ms_ssim_forward(X, Y, data_range=1.0, size_average=True, win_size=11, win_sigma=1.5, weights=WEIGHTS, K=(0.01, 0.03)):
     X, Y = X.detach().contiguous().float(), Y.detach().contiguous().float()
     taps = _taps(win_size, win_sigma)
     c1, c2 = (K[0] * data_range) ** 2, (K[1] * data_range) ** 2
@@ -64,13 +95,13 @@ def ms_ssim(X, Y, data_range=1.0, size_average=True, win_size=11, win_sigma=1.5,
     return val.mean() if size_average else val.mean(1)
 
 
-def _level_bwd(X, Y, coef_cs, coef_ss, dXnext, pads, taps, c1, c2):
+def _level_bwd(X, Y, coef_cs, coef_ss, dXnext, pads, taps, c1, c2, same_pad=False):
     n, c, h, w = X.shape
     dX = torch.empty_like(X)
     nh, nw = (dXnext.shape[2], dXnext.shape[3]) if dXnext is not None else (0, 0)
     arr = (C.c_float * len(taps))(*taps)
     L.call("icadv_ssim_level_backward", _p(X), _p(Y), _p(coef_cs), _p(coef_ss), _p(dXnext), _p(dX), n * c, h, w, nh, nw,
-           pads[0], pads[1], arr, len(taps), float(c1), float(c2), _stream())
+           pads[0], pads[1], arr, len(taps), 1 if same_pad else 0, float(c1), float(c2), _stream())
     return dX
 
 
@@ -120,24 +151,73 @@ class MS_SSIM(torch.nn.Module):
         return ms_ssim(X, Y, **self.kw)
 
 
+def _v2_levels(X, Y, max_val, levels):
+    """Variant 2 pyramid: per level (X, Y, taps, global mean ssim, global mean cs)."""
+    c1, c2 = (0.01 * max_val) ** 2, (0.03 * max_val) ** 2
+    out = []
+    for _ in range(levels):
+        wsz = min(X.shape[2], X.shape[3], 11)
+        taps = _taps(wsz, 1.5 * wsz / 11)
+        ss, cs = _level(X, Y, taps, True, c1, c2)
+        out.append((X, Y, taps, ss.mean(), cs.mean()))   # global mean over N, C, H, W (planes have equal size)
+        X, Y = _pool(X, 0, 0), _pool(Y, 0, 0)
+    return out, c1, c2
+
+
+def _v2_value(lv, levels):
+    w = torch.tensor(WEIGHTS, device=lv[0][0].device, dtype=torch.float32)
+    mcs_t, ms_t = torch.stack([l[4] for l in lv]), torch.stack([l[3] for l in lv])
+    return torch.prod(mcs_t[:levels - 1] ** w[:levels - 1]) * (ms_t[levels - 1] ** w[levels - 1])
+
+
+class _MsSsimV2Fn(torch.autograd.Function):
+    """utils/torch_msssim.MS_SSIM.forward with gradients to both images (the 2-D window is an outer product of the
+    1-D taps, so the separable backward kernel applies with the "same" padding origin)."""
+
+    @staticmethod
+    def forward(ctx, X, Y, max_val, levels):
+        ctx.save_for_backward(X.detach(), Y.detach())
+        ctx.cfg = (max_val, levels)
+        lv, _, _ = _v2_levels(X.detach().contiguous().float(), Y.detach().contiguous().float(), max_val, levels)
+        return _v2_value(lv, levels)
+
+    @staticmethod
+    def _grad(A, Bimg, g, max_val, levels):
+        lv, c1, c2 = _v2_levels(A, Bimg, max_val, levels)
+        value = _v2_value(lv, levels)
+        planes = A.shape[0] * A.shape[1]
+        dnext = None
+        zero = torch.zeros(planes, device=A.device, dtype=torch.float32)
+        for l in range(levels - 1, -1, -1):
+            Xl, Yl, taps, ms_l, mcs_l = lv[l]
+            last = l == levels - 1
+            base = ms_l if last else mcs_l
+            # d value / d (global mean of this level's map), spread over the planes * H * W positions of the mean
+            coef = (g * WEIGHTS[l] * value / base / (planes * Xl.shape[2] * Xl.shape[3])).reshape(1).expand(planes).contiguous()
+            dnext = _level_bwd(Xl, Yl, zero if last else coef, coef if last else zero, dnext, (0, 0), taps, c1, c2,
+                               same_pad=True)
+        return dnext
+
+    @staticmethod
+    def backward(ctx, g):
+        X, Y = ctx.saved_tensors
+        max_val, levels = ctx.cfg
+        Xc, Yc = X.contiguous().float(), Y.contiguous().float()
+        g = g.to(torch.float32)
+        gX = _MsSsimV2Fn._grad(Xc, Yc, g, max_val, levels) if ctx.needs_input_grad[0] else None
+        gY = _MsSsimV2Fn._grad(Yc, Xc, g, max_val, levels) if ctx.needs_input_grad[1] else None
+        return gX, gY, None, None
+
+
 class MS_SSIM_v2(torch.nn.Module):
-    """utils/torch_msssim.MS_SSIM(size_average=True, max_val=255)."""
+    """utils/torch_msssim.MS_SSIM(size_average=True, max_val=255); differentiable w.r.t. both images."""
 
     def __init__(self, size_average=True, max_val=255, device_id=0):
         super().__init__()
         self.max_val = max_val
 
     def forward(self, img1, img2, levels=5):
-        X, Y = img1.detach().contiguous().float(), img2.detach().contiguous().float()
-        c1, c2 = (0.01 * self.max_val) ** 2, (0.03 * self.max_val) ** 2
-        ms, mcs = [], []
-        for _ in range(levels):
-            wsz = min(X.shape[2], X.shape[3], 11)
-            taps = _taps(wsz, 1.5 * wsz / 11)
-            ss, cs = _level(X, Y, taps, True, c1, c2)
-            ms.append(ss.mean())   # global mean over N, C, H, W (planes have equal size)
-            mcs.append(cs.mean())
-            X, Y = _pool(X, 0, 0), _pool(Y, 0, 0)
-        w = torch.tensor(WEIGHTS, device=X.device, dtype=torch.float32)
-        mcs_t, ms_t = torch.stack(mcs), torch.stack(ms)
-        return torch.prod(mcs_t[:levels - 1] ** w[:levels - 1]) * (ms_t[levels - 1] ** w[levels - 1])
+        if torch.is_grad_enabled() and (img1.requires_grad or img2.requires_grad):
+            return _MsSsimV2Fn.apply(img1, img2, self.max_val, levels)
+        lv, _, _ = _v2_levels(img1.detach().contiguous().float(), img2.detach().contiguous().float(), self.max_val, levels)
+        return _v2_value(lv, levels)

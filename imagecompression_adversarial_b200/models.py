@@ -278,6 +278,26 @@ def _inference_program(stack, n, h, w, device):
     return prog
 
 
+_GRAD_PROGRAMS = {}
+
+
+def _grad_program(stack, n, h, w, device):
+    """Cached forward + input-gradient StackProgram of ``stack`` for this input shape: the unmodified reference loop calls
+    ``net.g_a(im_in)`` / ``net.g_s(y)`` once per iteration (attack_rd.py:344,349), and building a program (buffers,
+    weight packing, TMA plans) per call costs more than running it.  One program per stack is kept."""
+    import weakref
+    key = (id(stack), n, h, w, str(device), precision.get())
+    hit = _GRAD_PROGRAMS.get(key)
+    if hit is not None and hit[0]() is stack:
+        return hit[1]
+    for k in [k for k, v in _GRAD_PROGRAMS.items() if v[0]() is None or (k[0] == id(stack) and k != key)]:
+        del _GRAD_PROGRAMS[k]
+    prog = StackProgram(parse_stack(stack), n, h, w, device, need_grad=True)
+    prog.version = 0
+    _GRAD_PROGRAMS[key] = (weakref.ref(stack), prog)
+    return prog
+
+
 class _StackFn(torch.autograd.Function):
     """Whole g_a / g_s stack as ONE autograd node running a fused StackProgram."""
 
@@ -294,16 +314,28 @@ class _StackFn(torch.autograd.Function):
             prog.refresh_parameters()
             ctx.prog = None
             return Fn.to_nchw(prog.forward().clone())
-        prog = StackProgram(parse_stack(stack), n, h, w, x.device, x_in=xn, need_grad=True)
-        out = prog.forward()
-        ctx.prog = prog
-        return Fn.to_nchw(out)
+        # grad-enabled call: the cached program of this (stack, shape); its buffers hold the saved activations until the
+        # matching backward.  The input is kept so that a backward that arrives after the stack has been run again (two
+        # forwards, then two backwards) can replay its forward first.
+        prog = _grad_program(stack, n, h, w, x.device)
+        prog.x_in.copy_(xn)
+        prog.refresh_parameters()
+        prog.version += 1
+        ctx.prog, ctx.version = prog, prog.version
+        ctx.save_for_backward(xn)
+        return Fn.to_nchw(prog.forward().clone())
 
     @staticmethod
     def backward(ctx, g):
         prog = ctx.prog
+        if prog.version != ctx.version:        # the stack ran forward again since: restore this call's activations
+            (xn,) = ctx.saved_tensors
+            prog.x_in.copy_(xn)
+            prog.forward()
+            prog.version += 1
+            ctx.version = prog.version
         prog.g_out.copy_(Fn.to_nhwc(g))
-        return Fn.to_nchw(prog.backward()), None
+        return Fn.to_nchw(prog.backward().clone()), None
 
 
 class CodecStack(nn.Sequential):

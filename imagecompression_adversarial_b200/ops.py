@@ -467,41 +467,54 @@ def adam_clip_step(params, grads, m, v, *, sumsq_dev, max_norm, lr, step, grad_s
 
 
 # ------------------------------------------------------------------ 3xTF32 parity mode (csrc/icadv_split.cu)
-def split_width(c):
-    """Channels of the split form of a C-channel operand: roundup(3C, 32)."""
-    return (3 * c + 31) // 32 * 32
+def split_geom(c, form=None, ksize=1, stride=1):
+    """(Ks, G) of the K-sliced split form of a C-channel operand feeding a contraction with this geometry: G slices of
+    Ks channels, Ks * G >= 3C, with at most ~128 sequential tensor-core accumulations per slice (taps x Ks/8) -- the
+    accumulator truncates after every instruction, so the chain length bounds the bias (csrc/icadv_split.cu)."""
+    if form == L.FORM_TCONV:
+        taps = ((ksize + stride - 1) // stride) ** 2       # taps per output-parity class
+    else:
+        taps = ksize * ksize
+    chunks = max(1, 32 // taps)
+    total = (3 * c + 31) // 32                              # 32-channel chunks of the whole split form
+    chunks = min(chunks, total)
+    g = (total + chunks - 1) // chunks
+    return 32 * chunks, g
 
 
-def split3(x, op=0, out=None):
-    """[..., C] channels-last activation -> [..., Kp] = [hi | lo | hi | 0]; op 1 squares first."""
+def split3(x, ks, g, op=0, out=None):
+    """[..., C] channels-last activation -> [G, ..., Ks] slices of [hi | lo | hi | 0]; op 1 squares first."""
     _chk(x, "x")
     c = x.shape[-1]
-    kp = split_width(c)
     if out is None:
-        out = torch.empty(*x.shape[:-1], kp, device=x.device, dtype=torch.float32)
-    assert out.shape[-1] == kp and out.numel() == x.numel() // c * kp
-    L.call("icadv_split3", _p(x), _p(out), x.numel() // c, c, kp, int(op), 0, _stream())
+        out = torch.empty(g, *x.shape[:-1], ks, device=x.device, dtype=torch.float32)
+    assert out.numel() == x.numel() // c * ks * g, (out.shape, x.shape, ks, g)
+    L.call("icadv_split3", _p(x), _p(out), x.numel() // c, c, ks, g, int(op), 0, _stream())
     return out
 
 
-def split3_weight(wpack, out=None):
-    """packed weight [taps][n][k] (or a [n][k] matrix) -> [...][Kp] = [hi | hi | lo | 0]."""
+def split3_weight(wpack, ks, g, out=None):
+    """packed weight [taps][n][k] (or [1][n][k] for a matrix) -> [G][taps][n][Ks] slices of [hi | hi | lo | 0]."""
     _chk(wpack, "wpack")
     k = wpack.shape[-1]
-    kp = split_width(k)
     if out is None:
-        out = torch.empty(*wpack.shape[:-1], kp, device=wpack.device, dtype=torch.float32)
-    L.call("icadv_split3", _p(wpack), _p(out), wpack.numel() // k, k, kp, 0, 1, _stream())
+        out = torch.empty(g, *wpack.shape[:-1], ks, device=wpack.device, dtype=torch.float32)
+    L.call("icadv_split3", _p(wpack), _p(out), wpack.numel() // k, k, ks, g, 0, 1, _stream())
     return out
 
 
-def gdn_bwd_operand_split3(g, y, sc, inverse, out=None):
+def gdn_bwd_operand_split3(g_out, y, sc, inverse, ks, g, out=None):
     c = y.shape[-1]
-    kp = split_width(c)
     if out is None:
-        out = torch.empty(*y.shape[:-1], kp, device=y.device, dtype=torch.float32)
-    L.call("icadv_gdn_bwd_operand_split3", _p(g), _p(y), _p(sc), _p(out), y.numel() // c, c, kp, 1 if inverse else 0,
-           _stream())
+        out = torch.empty(g, *y.shape[:-1], ks, device=y.device, dtype=torch.float32)
+    L.call("icadv_gdn_bwd_operand_split3", _p(g_out), _p(y), _p(sc), _p(out), y.numel() // c, c, ks, g,
+           1 if inverse else 0, _stream())
+    return out
+
+
+def sum_slices(parts, out):
+    """out = parts[0] + parts[1] + ... in round-to-nearest fp32 (parts: [G, ...] contiguous)."""
+    L.call("icadv_sum_slices", _p(parts), _p(out), out.numel(), parts.shape[0], _stream())
     return out
 
 
@@ -513,12 +526,34 @@ def gdn_bwd_combine(g, y, sc, w, out, inverse):
     L.call("icadv_gdn_bwd_combine", _p(g), _p(y), _p(sc), _p(w), _p(out), y.numel(), 1 if inverse else 0, _stream())
 
 
+def conv_sliced(xs, ws, bias, *, form, ksize, stride, n_ch, act=L.ACT_NONE):
+    """Parity-mode contraction from prepared slices: xs [G, N, H, W, Ks], ws [G, taps, n_ch, Ks].  One tensor-path
+    launch per slice (the bias rides in slice 0), partial outputs added in fp32, activation applied after the sum."""
+    g = xs.shape[0]
+    n, h, w = xs.shape[1], xs.shape[2], xs.shape[3]
+    oh, ow = out_hw(form, ksize, stride, h, w)
+    if form == L.FORM_TCONV and ksize < stride:
+        parts = torch.zeros(g, n, oh, ow, n_ch, device=xs.device, dtype=torch.float32)
+        if bias is not None:
+            parts[0] += bias
+    else:
+        parts = torch.empty(g, n, oh, ow, n_ch, device=xs.device, dtype=torch.float32)
+    for i in range(g):
+        conv(xs[i], ws[i], bias if i == 0 else None, form=form, ksize=ksize, stride=stride, n_ch=n_ch, out=parts[i],
+             path="tc")
+    out = parts[0] if g == 1 else sum_slices(parts, torch.empty_like(parts[0]))
+    if act != L.ACT_NONE:
+        out = unary(out, _UNARY[act])
+    return out
+
+
 def gdn_forward_split(xn, beta_eff, gamma_eff, inverse):
     """Unfused GDN / IGDN in the parity mode: (y, sc).  gamma_eff [C][C] unrounded."""
     c = xn.shape[-1]
-    sq = split3(xn, op=1)
-    nrm = conv(sq, split3_weight(gamma_eff.contiguous().view(1, c, c)), beta_eff.contiguous(), form=L.FORM_SCONV,
-               ksize=1, stride=1, n_ch=c, path="tc")
+    ks, g = split_geom(c)
+    sq = split3(xn, ks, g, op=1)
+    nrm = conv_sliced(sq, split3_weight(gamma_eff.contiguous().view(1, c, c), ks, g), beta_eff.contiguous(),
+                      form=L.FORM_SCONV, ksize=1, stride=1, n_ch=c)
     y, sc = torch.empty_like(xn), torch.empty_like(xn)
     gdn_apply(xn, nrm, y, sc, inverse)
     return y, sc
@@ -526,28 +561,25 @@ def gdn_forward_split(xn, beta_eff, gamma_eff, inverse):
 
 def gdn_backward_split(gn, y, sc, gamma_eff, inverse):
     c = y.shape[-1]
-    t = gdn_bwd_operand_split3(gn, y, sc, inverse)
-    w = conv(t, split3_weight(gamma_eff.t().contiguous().view(1, c, c)), None, form=L.FORM_SCONV, ksize=1, stride=1,
-             n_ch=c, path="tc")
+    ks, g = split_geom(c)
+    t = gdn_bwd_operand_split3(gn, y, sc, inverse, ks, g)
+    w = conv_sliced(t, split3_weight(gamma_eff.t().contiguous().view(1, c, c), ks, g), None, form=L.FORM_SCONV, ksize=1,
+                    stride=1, n_ch=c)
     out = torch.empty_like(y)
     gdn_bwd_combine(gn, y, sc, w, out, inverse)
     return out
 
 
-_NOISE_OFFSET = [0, None]   # running Philox block counter, and the seed it belongs to
-
-
 def uniform_noise_like(x, lo=-0.5, hi=0.5):
-    """U[lo, hi) sample shaped (and laid out) like ``x`` from the library's Philox kernel, keyed by torch's CUDA seed
-    (``torch.manual_seed`` reproduces it) and a running block counter."""
+    """U[lo, hi) sample shaped (and laid out) like ``x`` from the library's Philox kernel.  Seed and counter are those
+    of torch's CUDA generator of the device (``torch.manual_seed`` restarts the stream, every draw advances it), so
+    runs reproduce exactly like runs that draw from torch."""
     out = torch.empty_like(x)
     n = out.numel()
-    seed = torch.cuda.initial_seed() & ((1 << 64) - 1)
-    if _NOISE_OFFSET[1] != seed:            # torch.manual_seed() was called: restart the stream
-        _NOISE_OFFSET[0], _NOISE_OFFSET[1] = 0, seed
-    L.call("icadv_uniform_noise", _p(out), n, C.c_uint64(seed), C.c_uint64(_NOISE_OFFSET[0]), float(lo), float(hi),
-           _stream())
-    _NOISE_OFFSET[0] += (n + 3) // 4
+    gen = torch.cuda.default_generators[x.device.index if x.device.index is not None else torch.cuda.current_device()]
+    seed, offset = gen.initial_seed() & ((1 << 64) - 1), gen.get_offset()
+    L.call("icadv_uniform_noise", _p(out), n, C.c_uint64(seed), C.c_uint64(offset // 4), float(lo), float(hi), _stream())
+    gen.set_offset(offset + 4 * ((n + 3) // 4))      # torch keeps the Philox offset in units of 4 (one 128-bit block)
     return out
 
 

@@ -156,11 +156,12 @@ class StackProgram:
 
     # ------------------------------------------------------------------ 3xTF32 parity mode
     def _init_split(self, in_h, in_w, x_in, g_out, g_in, active, n_active, need_grad):
-        """Launch lists of the parity mode (precision.py, csrc/icadv_split.cu): every contraction is preceded by a
-        split of its input into [hi | lo | hi] along the channels and runs with [Whi | Whi | Wlo] weights on the same
-        tensor-path kernel (linear epilogue); GDN / IGDN are unfused (square -> split -> 1x1 contraction with gamma ->
-        apply; backward: operand -> split -> 1x1 with gamma^T -> combine).  Nothing is rounded to TF32 in memory.
-        Scratch buffers are shared by all units (everything is stream-ordered)."""
+        """Launch lists of the parity mode (precision.py, csrc/icadv_split.cu): every contraction input is expanded to
+        the three-term split form [hi | lo | hi] along the channels, cut into K-slices, and contracted slice by slice
+        with [Whi | Whi | Wlo] weights on the same tensor-path kernel (linear epilogue); the partial outputs are added in
+        fp32.  GDN / IGDN are unfused (square -> split -> 1x1 contraction with gamma -> apply; backward: operand ->
+        split -> 1x1 with gamma^T -> combine).  Nothing is rounded to TF32 in memory.  Scratch buffers are shared by all
+        units (everything is stream-ordered)."""
         units, n_img, device = self.units, self.n_img, self.device
         self.round_final_out = self.round_final_gin = False
         self.active, self.n_active = active, n_active
@@ -177,10 +178,19 @@ class StackProgram:
         self.sc = [torch.empty_like(self.y[j]) if units[j].gdn is not None else None for j in range(U)]
         self.out = self.y[-1]
         px = lambda j: n_img * self.hw[j][0] * self.hw[j][1]       # pixels of the INPUT of unit j (px(j+1): its output)
-        n_split = max(max(px(j) * ops.split_width(units[j].cin), px(j + 1) * ops.split_width(units[j].cout))
-                      for j in range(U))
-        n_act = max(self.y[j].numel() for j in range(U))
+        width = lambda geom: geom[0] * geom[1]
+        self.geom_f = [ops.split_geom(u.cin, u.fwd_form, u.k, u.s) for u in units]       # forward contraction of unit j
+        self.geom_b = [ops.split_geom(u.cout, u.bwd_form, u.k, u.s) for u in units]      # its input gradient
+        self.geom_n = [ops.split_geom(u.cout) if u.gdn is not None else None for u in units]   # 1x1 normalisation GEMM
+        n_split, n_parts = 0, 0
+        for j, u in enumerate(units):
+            n_split = max(n_split, px(j) * width(self.geom_f[j]), px(j + 1) * width(self.geom_b[j]),
+                          px(j + 1) * width(self.geom_n[j]) if u.gdn is not None else 0)
+            n_parts = max(n_parts, self.geom_f[j][1] * px(j + 1) * u.cout, self.geom_b[j][1] * px(j) * u.cin,
+                          self.geom_n[j][1] * px(j + 1) * u.cout if u.gdn is not None else 0)
+        n_act = max([self.y[j].numel() for j in range(U)] + [self.x_in.numel()])
         self._s = f(n_split)                                      # split operand of the next contraction
+        self._p = f(n_parts)                                      # partial outputs of the K-slices
         self._a, self._b, self._c = f(n_act), f(n_act), f(n_act)  # pre-GDN output / gradient ping-pong / norm
         self.w_fwd, self.w_bwd, self.bias = [None] * U, [None] * U, [None] * U
         self.beta, self.gamma, self.gammaT = [None] * U, [None] * U, [None] * U
@@ -193,20 +203,34 @@ class StackProgram:
             self.g_in = g_in if g_in is not None else torch.empty_like(self.x_in)
             assert self.g_in.shape == self.x_in.shape
         self.fwd, self.bwd = [], []
-        sview = lambda npx, c: self._s[:npx * ops.split_width(c)].view(npx, ops.split_width(c))
         aview = lambda buf, like: buf[:like.numel()].view(like.shape)
+
+        def sview(geom, j_px, hw):
+            ks, g = geom
+            return self._s[:g * j_px * ks].view(g, n_img, hw[0], hw[1], ks)
+
+        def contraction(lst, xs, ws, bias, dst, form, u, n_ch, **kw):
+            """G slice launches + the fp32 sum of their partial outputs into dst."""
+            g = xs.shape[0]
+            if g == 1:
+                lst.append(self._launch(xs[0], ws[0], bias, dst, form=form, u=u, n_ch=n_ch, **kw))
+                return
+            parts = self._p[:g * dst.numel()].view(g, *dst.shape)
+            for i in range(g):
+                lst.append(self._launch(xs[i], ws[i], bias if i == 0 else None, parts[i], form=form, u=u, n_ch=n_ch, **kw))
+            lst.append(FnLaunch(ops.sum_slices, parts, dst))
+
         x = self.x_in
         for j, u in enumerate(units):
-            xs = sview(px(j), u.cin).view(n_img, *self.hw[j], -1)
-            self.fwd.append(FnLaunch(ops.split3, x, 0, xs))
+            xs = sview(self.geom_f[j], px(j), self.hw[j])
+            self.fwd.append(FnLaunch(ops.split3, x, *self.geom_f[j], 0, xs))
             dst = self.y[j] if u.gdn is None else aview(self._a, self.y[j])
-            self.fwd.append(self._launch(xs, self.w_fwd[j], self.bias[j], dst, form=u.fwd_form, u=u, n_ch=u.cout))
+            contraction(self.fwd, xs, self.w_fwd[j], self.bias[j], dst, u.fwd_form, u, u.cout)
             if u.gdn is not None:
-                sq = sview(px(j + 1), u.cout).view(n_img, *self.hw[j + 1], -1)
+                sq = sview(self.geom_n[j], px(j + 1), self.hw[j + 1])
                 nrm = aview(self._c, self.y[j])
-                self.fwd.append(FnLaunch(ops.split3, dst, 1, sq))
-                self.fwd.append(self._launch(sq, self.gamma[j], self.beta[j], nrm, form=L.FORM_SCONV, u=u, n_ch=u.cout,
-                                             ksize=1, stride=1))
+                self.fwd.append(FnLaunch(ops.split3, dst, *self.geom_n[j], 1, sq))
+                contraction(self.fwd, sq, self.gamma[j], self.beta[j], nrm, L.FORM_SCONV, u, u.cout, ksize=1, stride=1)
                 self.fwd.append(FnLaunch(ops.gdn_apply, dst, nrm, self.y[j], self.sc[j], u.gdn.inverse))
             x = self.y[j]
         if not need_grad:
@@ -216,32 +240,33 @@ class StackProgram:
             u = units[j]
             gsrc = gcur
             if u.gdn is not None:
-                t = sview(px(j + 1), u.cout).view(n_img, *self.hw[j + 1], -1)
+                t = sview(self.geom_n[j], px(j + 1), self.hw[j + 1])
                 w = aview(self._c, self.y[j])
                 gsrc = aview(self._a, self.y[j])
-                self.bwd.append(FnLaunch(ops.gdn_bwd_operand_split3, gcur, self.y[j], self.sc[j], u.gdn.inverse, t))
-                self.bwd.append(self._launch(t, self.gammaT[j], None, w, form=L.FORM_SCONV, u=u, n_ch=u.cout, ksize=1,
-                                             stride=1))
+                self.bwd.append(FnLaunch(ops.gdn_bwd_operand_split3, gcur, self.y[j], self.sc[j], u.gdn.inverse,
+                                         *self.geom_n[j], t))
+                contraction(self.bwd, t, self.gammaT[j], None, w, L.FORM_SCONV, u, u.cout, ksize=1, stride=1)
                 self.bwd.append(FnLaunch(ops.gdn_bwd_combine, gcur, self.y[j], self.sc[j], w, gsrc, u.gdn.inverse))
-            gs = sview(px(j + 1), u.cout).view(n_img, *self.hw[j + 1], -1)
-            self.bwd.append(FnLaunch(ops.split3, gsrc, 0, gs))
+            gs = sview(self.geom_b[j], px(j + 1), self.hw[j + 1])
+            self.bwd.append(FnLaunch(ops.split3, gsrc, *self.geom_b[j], 0, gs))
             dst = self.g_in if j == 0 else aview(self._b, self.y[j - 1])
-            self.bwd.append(self._launch(gs, self.w_bwd[j], None, dst, form=u.bwd_form, u=u, n_ch=u.cin))
+            contraction(self.bwd, gs, self.w_bwd[j], None, dst, u.bwd_form, u, u.cin)
             gcur = dst
 
     def _refresh_split(self):
         for j, u in enumerate(self.units):
             w = u.conv.weight
-            wf = ops.split3_weight(ops.pack_weight(w, L.PACK_CONVT_FWD if u.transposed else L.PACK_CONV_FWD))
-            wb = ops.split3_weight(ops.pack_weight(w, L.PACK_CONVT_DGRAD if u.transposed else L.PACK_CONV_DGRAD))
+            wf = ops.split3_weight(ops.pack_weight(w, L.PACK_CONVT_FWD if u.transposed else L.PACK_CONV_FWD), *self.geom_f[j])
+            wb = ops.split3_weight(ops.pack_weight(w, L.PACK_CONVT_DGRAD if u.transposed else L.PACK_CONV_DGRAD),
+                                   *self.geom_b[j])
             vals = [(self.w_fwd, wf), (self.w_bwd, wb)]
             if u.conv.bias is not None:
                 vals.append((self.bias, u.conv.bias.detach().contiguous().clone()))
             if u.gdn is not None:
                 be, ga, gaT = u.gdn.effective_parameters(round_tf32=False)
                 c = u.cout
-                vals += [(self.beta, be), (self.gamma, ops.split3_weight(ga.contiguous().view(1, c, c))),
-                         (self.gammaT, ops.split3_weight(gaT.contiguous().view(1, c, c)))]
+                vals += [(self.beta, be), (self.gamma, ops.split3_weight(ga.contiguous().view(1, c, c), *self.geom_n[j])),
+                         (self.gammaT, ops.split3_weight(gaT.contiguous().view(1, c, c), *self.geom_n[j]))]
             for store, val in vals:
                 if store[j] is None:      # plans bake these pointers in: later refreshes copy in place
                     store[j] = val

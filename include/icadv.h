@@ -314,14 +314,15 @@ int icadv_ssim_workspace_floats(int planes, int h, int w, int win, int same_pad)
 int icadv_ssim_level(const float* X, const float* Y, float* ws, float* ssim_sum, float* cs_sum, int planes,
                      int h, int w, const float* win_taps_host, int win, int same_pad, float c1, float c2,
                      icadv_stream_t stream);
-/* Backward of one level (variant 1) w.r.t. X.  coef_cs / coef_ss [planes]: upstream weights on the per-plane SUMS of
- * the cs / ssim maps; dXnext (nullable): gradient w.r.t. the 2x2-average-pooled next level, folded in.  Statistics are
- * recomputed in shared memory (nothing saved by the forward).  Used by the ms-ssim attack metric
- * (attack_rd.py:336,362 under autograd). */
+/* Backward of one level w.r.t. X (same_pad as above: 0 = variant 1, 1 = variant 2).  coef_cs / coef_ss [planes]:
+ * upstream weights on the per-plane SUMS of the cs / ssim maps; dXnext (nullable): gradient w.r.t. the
+ * 2x2-average-pooled next level, folded in.  Statistics are recomputed in shared memory (nothing saved by the forward).
+ * The SSIM map is symmetric in (X, Y): the gradient w.r.t. Y is this call with the two images swapped.  Used by the
+ * ms-ssim attack metric and the ms-ssim RD loss (attack_rd.py:336,362 and train.py:44,88 under autograd). */
 int icadv_ssim_level_backward(const float* X, const float* Y, const float* coef_cs, const float* coef_ss,
                               const float* dXnext, float* dX, int planes, int h, int w, int next_h, int next_w,
-                              int pad_h, int pad_w, const float* win_taps_host, int win, float c1, float c2,
-                              icadv_stream_t stream);
+                              int pad_h, int pad_w, const float* win_taps_host, int win, int same_pad, float c1,
+                              float c2, icadv_stream_t stream);
 /* F.avg_pool2d(x, 2, stride 2, padding (pad_h, pad_w)) between levels */
 int icadv_avgpool2(const float* x, float* y, int planes, int h, int w, int pad_h, int pad_w,
                    icadv_stream_t stream);
@@ -330,16 +331,22 @@ int icadv_avgpool2(const float* x, float* y, int planes, int h, int w, int pad_h
  * 3xTF32 parity mode (csrc/icadv_split.cu).  The contractions of the codec stacks
  * (anchors/utils.py:112-130; compressai GDN, utils/ops.py:58-97) stay on the tcgen05 kernels, but every fp32
  * operand is split x = hi + lo (both TF32) and the product is hi*Whi + lo*Whi + hi*Wlo, accumulated in fp32 in
- * TMEM.  The split is a layout: activations [px][C] -> [px][Kp] = [hi | lo | hi | 0] (layout 0), packed weights
- * [rows][C] -> [rows][Kp] = [hi | hi | lo | 0] (layout 1), Kp = roundup(3C, 32); the contraction is then launched
- * with k_ch = Kp.  op 1 squares the input first (operand of the GDN normalisation).  GDN / IGDN run unfused in this
+ * TMEM.  The split is a layout: activations [px][C] -> [hi | lo | hi | 0] along the channels (layout 0), packed
+ * weights [rows][C] -> [hi | hi | lo | 0] (layout 1), written as G slices of Ks channels (Ks * G >= 3C); the contraction
+ * is then launched once per slice with k_ch = Ks (see icadv_sum_slices).  op 1 squares the input first (operand of the GDN normalisation).  GDN / IGDN run unfused in this
  * mode: split3(op 1) -> 1x1 contraction with gamma, bias beta -> icadv_gdn_apply; backward: icadv_gdn_bwd_operand_split3
  * -> 1x1 contraction with gamma^T -> icadv_gdn_bwd_combine.  Purpose: per-step losses of attack_rd.py:332-379,506-560
  * within 1e-3 of the fp32 reference.
  * ------------------------------------------------------------------------------------------ */
-int icadv_split3(const float* x, float* out, int64_t n_px, int C, int Kp, int op, int layout, icadv_stream_t stream);
-int icadv_gdn_bwd_operand_split3(const float* g, const float* y, const float* sc, float* out, int64_t n_px, int C, int Kp,
-                                 int inverse, icadv_stream_t stream);
+int icadv_split3(const float* x, float* out, int64_t n_px, int C, int Ks, int G, int op, int layout,
+                 icadv_stream_t stream);
+int icadv_gdn_bwd_operand_split3(const float* g, const float* y, const float* sc, float* out, int64_t n_px, int C, int Ks,
+                                 int G, int inverse, icadv_stream_t stream);
+/* K-slicing (the tensor core truncates its fp32 accumulator after every instruction, so long accumulation chains come
+ * out low by ~2^-24 per step): the split form is cut into G slices of Ks channels -- activations [G][px][Ks], weights
+ * [G][rows][Ks] -- each slice is contracted by its own launch (k_ch = Ks) into its own partial output, and the partials
+ * [G][n] are added in round-to-nearest fp32: */
+int icadv_sum_slices(const float* parts, float* out, int64_t n, int G, icadv_stream_t stream);
 /* sc = norm^(-1/2) (inverse: ^(+1/2)); y = x * sc */
 int icadv_gdn_apply(const float* x, const float* nrm, float* y, float* sc, int64_t n, int inverse,
                     icadv_stream_t stream);

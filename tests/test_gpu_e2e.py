@@ -175,6 +175,51 @@ def test_msssim_gradient_matches_oracle_autograd(dev):
         assert err < 2e-3, err
 
 
+def test_msssim_operator_surface_is_differentiable_in_both_images(dev):
+    """The calls the unmodified reference makes under autograd: ``1 - ms_ssim(im_s, im_in)`` (gradient to the SECOND
+    image, attack_rd.py:336), ``ms_ssim(output_, output_s)`` (:362), ``MS_SSIM(...)(x_hat, target)`` (train.py:44,88),
+    and ``utils/torch_msssim.MS_SSIM`` (variant 2) -- values and gradients against the oracle's autograd."""
+    from imagecompression_adversarial_b200 import metrics
+    from oracle import msssim as oms
+    g = torch.Generator(device=dev).manual_seed(33)
+    for hw in ((192, 256), (181, 207)):
+        a = torch.rand(2, 3, *hw, device=dev, generator=g)
+        b = (a + 0.05 * torch.randn(2, 3, *hw, device=dev, generator=g)).clamp(0, 1)
+        for size_average in (True, False):
+            res = []
+            for fn in (oms.ms_ssim, metrics.ms_ssim):
+                x, y = a.clone().requires_grad_(True), b.clone().requires_grad_(True)
+                v = fn(x, y, data_range=1.0, size_average=size_average)
+                loss = (1.0 - v).sum() if size_average else ((1.0 - v) * torch.tensor([1.0, -2.0], device=dev)).sum()
+                loss.backward()
+                res.append((v.detach(), x.grad, y.grad))
+            (ov, ogx, ogy), (pv, pgx, pgy) = res
+            torch.testing.assert_close(pv, ov, rtol=0, atol=2e-5)
+            assert float((pgx - ogx).abs().max() / ogx.abs().max()) < 2e-3
+            assert float((pgy - ogy).abs().max() / ogy.abs().max()) < 2e-3
+        # gradient to one side only (the other does not require grad)
+        y = b.clone().requires_grad_(True)
+        (1.0 - metrics.ms_ssim(a, y, data_range=1.0)).backward()
+        assert bool(torch.isfinite(y.grad).all()) and float(y.grad.abs().max()) > 0
+    # module form
+    x = a.clone().requires_grad_(True)
+    v = metrics.MS_SSIM(data_range=1.0, size_average=True, channel=3)(x, b)
+    v.backward()
+    assert x.grad is not None and float(x.grad.abs().max()) > 0
+    # variant 2
+    res = []
+    a2, b2 = a[:, :, :176, :192].contiguous(), b[:, :, :176, :192].contiguous()
+    for which in ("oracle", "product"):
+        x, y = a2.clone().requires_grad_(True), b2.clone().requires_grad_(True)
+        v = oms.ms_ssim_v2(x, y, max_val=1.0) if which == "oracle" else metrics.MS_SSIM_v2(max_val=1.0)(x, y)
+        v.backward()
+        res.append((float(v), x.grad, y.grad))
+    (ov, ogx, ogy), (pv, pgx, pgy) = res
+    assert abs(pv - ov) < 2e-5
+    assert float((pgx - ogx).abs().max() / ogx.abs().max()) < 2e-3, float((pgx - ogx).abs().max() / ogx.abs().max())
+    assert float((pgy - ogy).abs().max() / ogy.abs().max()) < 2e-3
+
+
 @pytest.mark.parametrize("model,quality,hw,n,steps,metric", [("hyper", 3, (192, 256), 2, 12, "L2"),
                                                              ("factorized", 1, (192, 192), 1, 9, "L2"),
                                                              ("hyper", 6, (192, 256), 1, 6, "L2"),      # N=192, M=320
