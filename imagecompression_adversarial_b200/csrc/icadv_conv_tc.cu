@@ -647,6 +647,8 @@ struct TcpParams {
   const float* bias; const float* beta;
   const int* active; const int* n_active;
   long long* dbg;   // developer profiling: 16 cycle counters per CTA (see scripts/persistent_timeline.py)
+  int ys_slots;     // streaming backward kernel: slots of the saved-tensor ring (each [y chunk | scale chunk] = 32 KB)
+  float* out;       // streaming backward kernel: dense output base (plain 128-byte stores per pixel and chunk)
 };
 
 struct TcpItem { int img, i0, j0, cls; };
@@ -1177,6 +1179,343 @@ __global__ void __launch_bounds__(kPThreads, 1) conv_tcp_kernel(const __grid_con
   if (warp == 1) tmem_dealloc(tmem, 512);
 }
 
+// =====================================================================================================
+// Streaming backward variant (GDN / IGDN backward epilogues): conv_tcp_kernel's item walk, rings and TMEM double buffer,
+// with the saved tensors of the matching forward treated as what they are -- the HBM stream that bounds these launches
+// (y + scale in, gradient out: 3 x N x 4 bytes per pixel against a main loop that is short on the RGB layer and
+// tensor-bound by a small margin on the 128-channel ones).
+//   * the saved y / scale chunks of successive items stream through their own ring of [y | scale] slots, requested by a
+//     producing thread as soon as a slot is free -- across item boundaries, so the epilogue of item i finds its chunks
+//     already in shared memory and the ring keeps HBM requests in flight while the epilogue computes (the per-tile and
+//     the persistent kernel above fetch one pair per epilogue group on demand: eight serial round trips per tile);
+//   * pass 1 leaves its per-element products in TMEM instead of re-reading y and scale in pass 2: g*sc overwrites the
+//     accumulator chunk in place and y/sc goes to a stash region (tcgen05.st), so every saved byte crosses the SM once;
+//     TMEM: [acc 0 | acc 1 | norm | stash] x 128 columns;
+//   * a slot is handed back by the tcgen05.commit of the normalisation MMAs that read its operand (written in place
+//     over the y rows), i.e. without any epilogue-side wait;
+//   * the output leaves with plain 128-byte stores (one pixel row of 32 channels per thread and chunk: whole lines), so
+//     no staging buffers and no store-drain waits; gamma^T stays resident.
+// Patches and saved chunks are produced by ONE polling thread (two cursors, mbarrier.test_wait, no blocking wait: a
+// blocked patch request must not hold back the saved-tensor stream and vice versa).
+// Arithmetic and accumulation order are those of conv_tcp_kernel (bit-identical results).
+// =====================================================================================================
+constexpr int kMaxYs = 4;
+
+template <int EPI>
+__global__ void __launch_bounds__(kPThreads, 1) conv_tcb_kernel(const __grid_constant__ TcpParams p) {
+  static_assert(EPI == ICADV_EPI_GDN_BWD || EPI == ICADV_EPI_IGDN_BWD, "backward epilogues only");
+  extern __shared__ uint8_t smem_raw[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int P = p.num_patch, S = p.num_stages, nC = p.n_chunks, R = p.ys_slots;
+  const int half = nC >> 1;                                          // chunks per epilogue group (nC is even)
+  const uint32_t b_bytes = static_cast<uint32_t>(p.n_ch) * 128u;
+  uint8_t* wring = smem + P * p.patch_bytes;
+  uint8_t* gmat = wring + S * b_bytes;                               // nC boxes [32 x n_ch] of gamma^T, resident
+  uint8_t* ysr = gmat + nC * b_bytes;                                // R slots x [y chunk 16 KB | scale chunk 16 KB]
+  uint64_t* wfull = reinterpret_cast<uint64_t*>(ysr + R * 2 * kABytes);
+  uint64_t* wempty = wfull + kMaxStages;
+  uint64_t* pfull = wempty + kMaxStages;
+  uint64_t* pempty = pfull + kMaxPatch;
+  uint64_t* gfull = pempty + kMaxPatch;       // [1]
+  uint64_t* acc_full = gfull + 1;             // [2]
+  uint64_t* tmem_free = acc_full + 2;         // [2]  both epilogue groups have finished with accumulator b
+  uint64_t* norm_full = tmem_free + 2;        // [1]
+  uint64_t* norm_free = norm_full + 1;        // [1]  both groups have read the norm region
+  uint64_t* ys_full = norm_free + 1;          // [kMaxYs]  TMA arrival of a [y | scale] pair
+  uint64_t* ys_empty = ys_full + kMaxYs;      // [kMaxYs]  the normalisation MMAs that read the slot have completed
+  uint64_t* a2_ready = ys_empty + kMaxYs;     // [kMaxYs]  128 epilogue threads have written the operand
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(a2_ready + kMaxYs);
+  float* sbias = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(wfull) + kBarBlock);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < S; ++s) { mbar_init(&wfull[s], 1); mbar_init(&wempty[s], 1); }
+    for (int s = 0; s < P; ++s) { mbar_init(&pfull[s], 1); mbar_init(&pempty[s], 1); }
+    mbar_init(gfull, 1);
+    for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&tmem_free[b], 2); }
+    mbar_init(norm_full, 1); mbar_init(norm_free, 2);
+    for (int k = 0; k < R; ++k) { mbar_init(&ys_full[k], 1); mbar_init(&ys_empty[k], 1); mbar_init(&a2_ready[k], 128); }
+    mbar_fence_init();
+  }
+  if (warp == 1) { tmem_alloc(tmem_ptr, 512); tmem_relinquish(); }
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.a_map[0]); tma_prefetch_desc(&p.w_map); tma_prefetch_desc(&p.g_map);
+    tma_prefetch_desc(&p.yprev_map[0]); tma_prefetch_desc(&p.sc_map[0]);
+  }
+  for (int i = threadIdx.x; i < p.n_ch; i += kPThreads) sbias[i] = p.bias != nullptr ? __ldg(p.bias + i) : 0.f;
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem = *tmem_ptr;
+  const int n_slots = p.n_active != nullptr ? *p.n_active : p.n_img;
+  const int total = n_slots * p.tiles_x * p.tiles_y * p.n_class;
+  // TMEM columns: accumulator b at b * 128, norm at 256, stash (y / sc) at 384
+
+  if (warp == 0) {
+    // ===================== TMA producer: weights (+ the resident gamma^T) =====================
+    if (elect_one_sync()) {
+      mbar_arrive_expect_tx(gfull, nC * b_bytes);
+      for (int c = 0; c < nC; ++c) tma_load_2d(gmat + c * b_bytes, &p.g_map, gfull, c * 32, 0);
+      int s = 0;
+      uint32_t s_par = 1;
+      uint8_t* wdst = wring;
+      for (int item = blockIdx.x; item < total; item += gridDim.x) {
+        const TcpItem it = tcp_decode(p, item);
+        const TcpClass cl = p.cls[it.cls];
+        const int t_begin = p.groups[cl.g_begin].tap_begin, t_end = p.groups[cl.g_end - 1].tap_end;
+        for (int kc = 0; kc < p.k_chunks; ++kc) {
+          const int c0 = kc * 32;
+          int wrow = p.tap_wtap[t_begin] * p.n_total;
+          for (int t = t_begin; t < t_end; ++t) {
+            mbar_wait(&wempty[s], s_par);
+            mbar_arrive_expect_tx(&wfull[s], b_bytes);
+            tma_load_2d(wdst, &p.w_map, &wfull[s], c0, wrow);
+            wrow = p.tap_wtap[t + 1] * p.n_total;   // one slack entry
+            if (++s == S) { s = 0; s_par ^= 1; wdst = wring; } else { wdst += b_bytes; }
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == kPPatchWarp) {
+    // ===================== TMA producer: input halo patches AND the saved-tensor stream (two cursors, polled) ==========
+    if (elect_one_sync()) {
+      int p_item = blockIdx.x, p_kc = 0, p_g = 0, p_gend = 0;
+      TcpItem pit = {0, 0, 0, 0};
+      bool p_live = p_item < total;
+      if (p_live) { pit = tcp_decode(p, p_item); p_g = p.cls[pit.cls].g_begin; p_gend = p.cls[pit.cls].g_end; }
+      int ps = 0;
+      uint32_t p_par = 1;
+      int y_item = blockIdx.x, y_q = 0;
+      TcpItem yit = {0, 0, 0, 0};
+      bool y_live = y_item < total;
+      if (y_live) yit = tcp_decode(p, y_item);
+      int ys = 0;
+      uint32_t y_par = 1;
+      while (p_live || y_live) {
+        if (y_live && mbar_test_wait(&ys_empty[ys], y_par)) {
+          const int c = (y_q & 1) * half + (y_q >> 1);               // the two groups' chunks alternate (fixed order)
+          uint8_t* dst = ysr + ys * 2 * kABytes;
+          mbar_arrive_expect_tx(&ys_full[ys], 2 * kABytes);
+          tma_load_4d(dst, &p.yprev_map[yit.cls], &ys_full[ys], c * 32, yit.j0, yit.i0, yit.img);
+          tma_load_4d(dst + kABytes, &p.sc_map[yit.cls], &ys_full[ys], c * 32, yit.j0, yit.i0, yit.img);
+          if (++ys == R) { ys = 0; y_par ^= 1; }
+          if (++y_q == nC) {
+            y_q = 0;
+            y_item += gridDim.x;
+            y_live = y_item < total;
+            if (y_live) yit = tcp_decode(p, y_item);
+          }
+        }
+        if (p_live && mbar_test_wait(&pempty[ps], p_par)) {
+          const int cx = pit.j0 + p.groups[p_g].dx0, cy = pit.i0 + p.groups[p_g].dy0;
+          uint8_t* pdst = smem + ps * p.patch_bytes;
+          mbar_arrive_expect_tx(&pfull[ps], p.groups[p_g].bytes);
+          if (p.a_rank5)
+            tma_load_5d(pdst, &p.a_map[0], &pfull[ps], 0, cx, cy, p.groups[p_g].plane5, pit.img);
+          else
+            tma_load_4d(pdst, &p.a_map[p.groups[p_g].map], &pfull[ps], p_kc * 32, cx, cy, pit.img);
+          if (++ps == P) { ps = 0; p_par ^= 1; }
+          if (++p_g == p_gend) {
+            if (++p_kc == p.k_chunks) {
+              p_kc = 0;
+              p_item += gridDim.x;
+              p_live = p_item < total;
+              if (p_live) { pit = tcp_decode(p, p_item); p_gend = p.cls[pit.cls].g_end; }
+            }
+            if (p_live) p_g = p.cls[pit.cls].g_begin;
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ===================== main-loop MMA issuer (as conv_tcp_kernel) =====================
+    if (elect_one_sync()) {
+      const uint32_t idesc = umma_idesc_tf32(kTileM, p.n_ch);
+      const uint32_t hi_dense = (1024u >> 4) | (1u << 14) | (2u << 29);
+      const uint32_t w_lo0 = ((smem_u32(wring) >> 4) & 0x3FFFu) | (1u << 16);
+      const uint32_t p_lo0 = ((smem_u32(smem) >> 4) & 0x3FFFu) | (1u << 16);
+      const uint32_t w_step = b_bytes >> 4, p_step = static_cast<uint32_t>(p.patch_bytes) >> 4;
+      int s = 0, ps = 0;
+      uint32_t s_par = 0, p_par = 0, w_lo = w_lo0, p_lo = p_lo0;
+      uint32_t free_bits = 3;
+      int b = 0;
+      bool w_ok = false;
+      for (int item = blockIdx.x; item < total; item += gridDim.x, b ^= 1) {
+        const TcpItem it = tcp_decode(p, item);
+        const TcpClass cl = p.cls[it.cls];
+        mbar_wait(&tmem_free[b], (free_bits >> b) & 1u);
+        free_bits ^= 1u << b;
+        tc_fence_after_sync();
+        const uint32_t d = tmem + b * 128;
+        uint32_t acc = 0;
+        for (int kc = 0; kc < p.k_chunks; ++kc) {
+          for (int g = cl.g_begin; g < cl.g_end; ++g) {
+            const uint32_t a_hi = (static_cast<uint32_t>(p.groups[g].sbo_bytes) >> 4) | (1u << 14) | (2u << 29);
+            const int t_end = p.groups[g].tap_end;
+            int t = p.groups[g].tap_begin;
+            uint32_t aoff = static_cast<uint32_t>(p.tap_aoff[t]) >> 4;
+            mbar_wait(&pfull[ps], p_par);
+            for (; t < t_end; ++t) {
+              const uint64_t ad = (static_cast<uint64_t>(a_hi) << 32) | (p_lo + aoff);
+              const uint64_t bd = (static_cast<uint64_t>(hi_dense) << 32) | w_lo;
+              if (!w_ok) mbar_wait(&wfull[s], s_par);
+              uint64_t* wdone = &wempty[s];
+              if (++s == S) { s = 0; s_par ^= 1; w_lo = w_lo0; } else { w_lo += w_step; }
+              tc_fence_after_sync();
+              tc_mma_tf32(d, ad, bd, idesc, acc);
+              tc_mma_tf32(d, ad + 2, bd + 2, idesc, 1u);
+              tc_mma_tf32(d, ad + 4, bd + 4, idesc, 1u);
+              tc_mma_tf32(d, ad + 6, bd + 6, idesc, 1u);
+              tc_commit(wdone);
+              acc = 1u;
+              aoff = static_cast<uint32_t>(p.tap_aoff[t + 1]) >> 4;
+              w_ok = mbar_test_wait(&wfull[s], s_par);
+            }
+            tc_commit(&pempty[ps]);
+            if (++ps == P) { ps = 0; p_par ^= 1; p_lo = p_lo0; } else { p_lo += p_step; }
+          }
+        }
+        tc_commit(&acc_full[b]);
+      }
+    }
+    __syncwarp();
+  } else if (warp == kPNormWarp) {
+    // ===================== normalisation MMA issuer =====================
+    // per item: nC K-blocks [128 x 32] (operand written in place over the y rows of a ring slot) x gamma^T chunk -> norm
+    // region, in the fixed chunk order of the stream; each K-block's commit hands its slot back to the producer
+    if (elect_one_sync()) {
+      const uint32_t idesc = umma_idesc_tf32(kTileM, p.n_ch);
+      const uint32_t hi_dense = (1024u >> 4) | (1u << 14) | (2u << 29);
+      const uint32_t g_lo0 = ((smem_u32(gmat) >> 4) & 0x3FFFu) | (1u << 16);
+      const uint32_t y_lo0 = ((smem_u32(ysr) >> 4) & 0x3FFFu) | (1u << 16);
+      const uint32_t w_step = b_bytes >> 4;
+      const uint32_t dn = tmem + 256;
+      int ys = 0;
+      uint32_t y_par = 0, nf_par = 1;
+      mbar_wait(gfull, 0);
+      for (int item = blockIdx.x; item < total; item += gridDim.x) {
+        mbar_wait(norm_free, nf_par);            // both groups have read the previous item's norm region
+        nf_par ^= 1;
+        for (int q = 0; q < nC; ++q) {
+          const int c = (q & 1) * half + (q >> 1);
+          const uint64_t ad = (static_cast<uint64_t>(hi_dense) << 32) | (y_lo0 + ys * ((2 * kABytes) >> 4));
+          const uint64_t bd = (static_cast<uint64_t>(hi_dense) << 32) | (g_lo0 + c * w_step);
+          mbar_wait(&a2_ready[ys], y_par);
+          tc_fence_after_sync();
+          tc_mma_tf32(dn, ad, bd, idesc, q > 0 ? 1u : 0u);
+          tc_mma_tf32(dn, ad + 2, bd + 2, idesc, 1u);
+          tc_mma_tf32(dn, ad + 4, bd + 4, idesc, 1u);
+          tc_mma_tf32(dn, ad + 6, bd + 6, idesc, 1u);
+          tc_commit(&ys_empty[ys]);
+          if (q == nC - 1) tc_commit(norm_full);
+          if (++ys == R) { ys = 0; y_par ^= 1; }
+        }
+      }
+    }
+    __syncwarp();
+  } else {
+    // ===================== two epilogue warpgroups: both work on every item, half of the chunks each =====================
+    const int grp = (warp - 2) >> 2;           // 0: warps 2-5, 1: warps 6-9
+    const int q4 = warp & 3;                   // TMEM lane quadrant this warp may touch
+    const int row = q4 * 32 + lane;
+    const bool leader = (row == 0);
+    const uint32_t bar_id = 1 + grp;
+    constexpr float sign = (EPI == ICADV_EPI_GDN_BWD) ? -1.f : 1.f;
+    uint32_t acc_bits = 0, nfull_par = 0;
+    int b = 0;
+    uint32_t seq0 = 0;                         // stream position of this item's first chunk
+    for (int item = blockIdx.x; item < total; item += gridDim.x, b ^= 1, seq0 += nC) {
+      const TcpItem it = tcp_decode(p, item);
+      const int o_a = p.cls[it.cls].o_a, o_b = p.cls[it.cls].o_b;
+      const int gi = it.i0 + row / kTW, gj = it.j0 + row % kTW;
+      const bool px_ok = gi < p.t_h && gj < p.t_w;
+      float* orow = p.out + (((int64_t)it.img * p.o_h + p.o_s * gi + o_a) * p.o_w + p.o_s * gj + o_b) * p.n_ch;
+      const uint32_t t_lane = tmem + (static_cast<uint32_t>(q4 * 32) << 16);
+      const uint32_t t_acc = t_lane + b * 128, t_norm = t_lane + 256, t_stash = t_lane + 384;
+      mbar_wait(&acc_full[b], (acc_bits >> b) & 1u);
+      acc_bits ^= 1u << b;
+      tc_fence_after_sync();
+      // ---- pass 1: this group's chunks, in stream order
+      for (int j = 0; j < half; ++j) {
+        const int c = grp * half + j;
+        const uint32_t seq = seq0 + 2 * j + grp;
+        const uint32_t slot = seq % R, par = (seq / R) & 1u;
+        uint8_t* bufY = ysr + slot * 2 * kABytes;
+        uint8_t* bufS = bufY + kABytes;
+        float v[32], yv[32], sv[32];
+        tmem_ld32(t_acc + c * 32, v);
+        tmem_ld_wait();
+        const float4* b4 = reinterpret_cast<const float4*>(sbias + c * 32);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const float4 bb = b4[k];
+          v[4 * k] += bb.x; v[4 * k + 1] += bb.y; v[4 * k + 2] += bb.z; v[4 * k + 3] += bb.w;
+        }
+        mbar_wait(&ys_full[slot], par);
+        read_row32(bufY, row, yv);
+        read_row32(bufS, row, sv);
+        // operand of the normalisation GEMM, written in place over this thread's own y row (16 bytes at a time)
+#pragma unroll
+        for (int k4 = 0; k4 < 8; ++k4) {
+          float a2[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int k = 4 * k4 + e;
+            const float s2 = sv[k] * sv[k];
+            if constexpr (EPI == ICADV_EPI_GDN_BWD) a2[e] = round_tf32(v[k] * yv[k] * s2);
+            else a2[e] = s2 > 0.f ? round_tf32(__fdividef(v[k] * yv[k], s2)) : 0.f;
+          }
+          *reinterpret_cast<float4*>(bufY + sw128_off(row, k4)) = make_float4(a2[0], a2[1], a2[2], a2[3]);
+        }
+        fence_proxy_async_smem();
+        // the products pass 2 needs: g * sc over the accumulator chunk, y / sc in the stash
+#pragma unroll
+        for (int k = 0; k < 32; ++k) {
+          const float xs = sv[k] > 0.f ? __fdividef(yv[k], sv[k]) : 0.f;
+          v[k] = v[k] * sv[k];
+          yv[k] = xs;
+        }
+        tmem_st32(t_acc + c * 32, v);
+        tmem_st32(t_stash + c * 32, yv);
+        tmem_st_wait();
+        mbar_arrive(&a2_ready[slot]);
+      }
+      // ---- pass 2: out = g sc -+ (y / sc) (gamma^T t), from TMEM only
+      mbar_wait(norm_full, nfull_par);
+      nfull_par ^= 1;
+      tc_fence_after_sync();
+      for (int j = 0; j < half; ++j) {
+        const int c = grp * half + j;
+        float v[32], xs[32], w[32];
+        tmem_ld32(t_acc + c * 32, v);
+        tmem_ld32(t_stash + c * 32, xs);
+        tmem_ld32(t_norm + c * 32, w);
+        tmem_ld_wait();
+#pragma unroll
+        for (int k = 0; k < 32; ++k) {
+          v[k] = v[k] + sign * xs[k] * w[k];
+          if (p.round_out) v[k] = round_tf32(v[k]);
+        }
+        if (px_ok) {
+          float4* dst = reinterpret_cast<float4*>(orow + c * 32);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) dst[k] = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+        }
+      }
+      // this item's TMEM reads are over: accumulator b goes back to the main issuer, the norm region to its issuer
+      tc_fence_before_sync();
+      named_bar_sync(bar_id, 128);
+      if (leader) { mbar_arrive(&tmem_free[b]); mbar_arrive(norm_free); }
+    }
+  }
+
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem, 512);
+}
+
 typedef void (*TcpKernelFn)(const TcpParams);
 
 static TcpKernelFn pick_persistent(int epi) {
@@ -1187,6 +1526,14 @@ static TcpKernelFn pick_persistent(int epi) {
     case ICADV_EPI_GDN_BWD: return conv_tcp_kernel<ICADV_EPI_GDN_BWD>;
     case ICADV_EPI_IGDN_BWD: return conv_tcp_kernel<ICADV_EPI_IGDN_BWD>;
     case kEpiCol2im: return conv_tcp_kernel<kEpiCol2im>;
+    default: return nullptr;
+  }
+}
+
+static TcpKernelFn pick_streaming(int epi) {
+  switch (epi) {
+    case ICADV_EPI_GDN_BWD: return conv_tcb_kernel<ICADV_EPI_GDN_BWD>;
+    case ICADV_EPI_IGDN_BWD: return conv_tcb_kernel<ICADV_EPI_IGDN_BWD>;
     default: return nullptr;
   }
 }
@@ -1374,7 +1721,12 @@ static int build_persistent(const icadv_conv_desc* d, int mode, const Geometry& 
   const int N = c2i ? 96 : d->n_ch, K = d->k_ch, s = d->stride;   // col2im: Z has 25 * n_ch <= 96 columns
   if (N > 256 || (gdn && N > 128)) return 0;            // 2 TMEM buffers x [acc N | norm N] must fit 512 columns
   const bool tconv2 = !c2i && d->form == ICADV_FORM_TCONV && s == 2;
-  if (level == 1 && !(tconv2 || (!gdn && mode == kModeGeneric) || c2i || (mode == kModeRgbIn && !bwd))) return 0;
+  // ICADV_TC_STREAM_BWD: 0 = never, unset / 1 = every GDN / IGDN backward epilogue the streaming kernel takes
+  const char* senv = getenv("ICADV_TC_STREAM_BWD");
+  const int stream_level = senv != nullptr ? atoi(senv) : 1;
+  const bool stream = bwd && stream_level > 0 && N <= 128 && (N / 32) % 2 == 0 &&
+                      (mode == kModeGeneric || mode == kModeRgbIn);
+  if (level == 1 && !stream && !(tconv2 || (!gdn && mode == kModeGeneric) || c2i || (mode == kModeRgbIn && !bwd))) return 0;
   TcpParams& p = plan->pp;
   memset(&p, 0, sizeof(p));
   p.n_class = tconv2 ? g.n_launch : 1;
@@ -1473,6 +1825,45 @@ static int build_persistent(const icadv_conv_desc* d, int mode, const Geometry& 
   p.t_h = g.tile_h; p.t_w = g.tile_w; p.o_h = g.out_h; p.o_w = g.out_w; p.o_s = tconv2 ? 2 : 1;
   p.yprev = d->y_prev; p.scprev = d->sc_prev; p.bias = d->bias; p.beta = d->beta;
   p.active = d->active; p.n_active = d->n_active;
+  p.out = d->out;
+  if (stream) {
+    // ---- streaming backward kernel: [patch ring | weight ring | gamma^T | saved-tensor ring R x 32 KB | barriers + bias]
+    p.patch_bytes = (max_patch + 1023) & ~1023;
+    const int wbytes = N * 128, pair = 2 * kABytes;
+    const int fixed = 1024 + kBarBlock + 2 * N * 4 + N * N * 4;
+    int per_item = 0;   // patches of one item
+    for (int l = 0; l < p.n_class; ++l) {
+      const int n = (p.cls[l].g_end - p.cls[l].g_begin) * p.k_chunks;
+      per_item = n > per_item ? n : per_item;
+    }
+    int P = 2, S = per_item <= 8 ? 2 : 3;
+    int R = (kSmemLimit - fixed - P * p.patch_bytes - S * wbytes) / pair;
+    if (R > kMaxYs) R = kMaxYs;
+    if (R >= 2) {
+      // left-over shared memory: more weight stages (long main loops), then a third patch slot
+      while (S < 4 && fixed + P * p.patch_bytes + (S + 1) * wbytes + R * pair <= kSmemLimit) ++S;
+      if (fixed + (P + 1) * p.patch_bytes + S * wbytes + R * pair <= kSmemLimit) ++P;
+      p.num_patch = P; p.num_stages = S; p.ys_slots = R; p.grp_bytes = 0;
+      plan->psmem = fixed + P * p.patch_bytes + S * wbytes + R * pair;
+      if (plan->psmem < 120 * 1024) plan->psmem = 120 * 1024;
+      int sms = 148, dev = 0;
+      if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+      const long long items = (long long)d->n_img * p.tiles_x * p.tiles_y * p.n_class;
+      plan->pgrid = (int)(items < sms ? items : sms);
+      plan->pfn = pick_streaming(d->epi);
+      static std::once_flag sonce;
+      static cudaError_t serr = cudaSuccess;
+      std::call_once(sonce, [] {
+        serr = cudaFuncSetAttribute(conv_tcb_kernel<ICADV_EPI_GDN_BWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
+        if (serr == cudaSuccess)
+          serr = cudaFuncSetAttribute(conv_tcb_kernel<ICADV_EPI_IGDN_BWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
+      });
+      if (serr != cudaSuccess) { set_error("cudaFuncSetAttribute(streaming) failed: %s", cudaGetErrorString(serr)); return ICADV_ECUDA; }
+      plan->persistent = 1;
+      return 1;
+    }
+    if (level == 1 && !(tconv2 || (mode == kModeRgbIn && !bwd))) return 0;   // not enough shared memory: previous policy
+  }
   // ---- shared memory: [patch ring | weight ring | gamma | 2 groups x 2 x 16 KB | barriers + bias/beta]
   p.patch_bytes = (max_patch + 1023) & ~1023;
   const int wbytes = N * 128;

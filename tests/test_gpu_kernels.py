@@ -4,6 +4,7 @@ bit-exact for clamps and layout moves, 1e-5 relative for CUDA-core fp32 contract
 bound (inputs truncated to 10 mantissa bits, fp32 accumulate) for the tcgen05 path.
 """
 import math
+import os
 
 import pytest
 import torch
@@ -400,7 +401,7 @@ def persist_env():
 
 
 @pytest.mark.parametrize("case", ["sconv_gdn_fwd", "tconv_igdn_fwd", "tconv_gdn_bwd", "sconv_igdn_bwd", "linear_relu",
-                                  "rgb_in_gdn", "col2im"])
+                                  "rgb_in_gdn", "rgb_in_igdn_bwd", "col2im"])
 def test_persistent_variant_equals_per_tile_kernel(dev, persist_env, case):
     """The persistent kernel (one CTA per SM, TMEM double buffer, two epilogue warpgroups, all parity classes in one
     launch; ICADV_TC_PERSIST=2 forces it for every eligible shape) and the per-tile kernel (=0) run the same K order and
@@ -450,6 +451,19 @@ def test_persistent_variant_equals_per_tile_kernel(dev, persist_env, case):
             out = torch.zeros(n, 12, 20, C, device=dev)
             ops.conv(x, w, beta, form=L.FORM_SCONV, ksize=3, stride=1, n_ch=C, act=L.ACT_RELU, out=out, path="tc", **kw)
             outs.append((out,))
+        elif case == "rgb_in_igdn_bwd":
+            # input gradient of the last synthesis layer (deconv N -> 3) with the IGDN backward in its epilogue: the
+            # HBM-bound launch the streaming backward kernel exists for
+            gx = torch.randn(n, 36, 52, 3, device=dev, generator=torch.Generator(device=dev).manual_seed(1))
+            pad = ops.pad_rgb4(gx, ops.alloc_pad4(n, 36, 52, dev))
+            w = ops.pack_weight_rgb(torch.randn(C, 3, 5, 5, device=dev, generator=torch.Generator(device=dev).manual_seed(2)) / 9)
+            yp = torch.randn(n, 18, 26, C, device=dev, generator=torch.Generator(device=dev).manual_seed(3))
+            sp = 0.5 + torch.rand(n, 18, 26, C, device=dev, generator=torch.Generator(device=dev).manual_seed(4))
+            out = torch.zeros(n, 18, 26, C, device=dev)
+            ops.conv(pad, w, None, form=L.FORM_SCONV, ksize=5, stride=2, n_ch=C, epi=L.EPI_IGDN_BWD,
+                     gmat=gamma.t().contiguous(), y_prev=yp, sc_prev=sp, out=out, path="tc", in_pad4=True, round_out=True,
+                     **kw)
+            outs.append((out,))
         elif case == "rgb_in_gdn":
             x = torch.rand(n, 36, 52, 3, device=dev, generator=torch.Generator(device=dev).manual_seed(1))
             pad = ops.pad_rgb4(x, ops.alloc_pad4(n, 36, 52, dev))
@@ -474,6 +488,38 @@ def test_persistent_variant_equals_per_tile_kernel(dev, persist_env, case):
         exact = torch.isclose(b, a, rtol=1e-5, atol=1e-6)
         assert float((~exact).float().mean()) < 1e-3, float((~exact).float().mean())
         torch.testing.assert_close(b, a, rtol=1.2e-3, atol=1e-6)
+
+
+def test_streaming_backward_kernel_matches_the_in_place_persistent_kernel(dev):
+    """ICADV_TC_STREAM_BWD=0 (saved chunks fetched per epilogue group, re-read in pass 2) vs =1 (saved-tensor ring, pass-1
+    products stashed in TMEM, plain stores): same chunk order, same arithmetic -> bit-identical, and both bit-reproducible;
+    ~17 items per CTA so every ring and the TMEM buffers wrap many times, ragged tile edges included."""
+    from imagecompression_adversarial_b200 import _lib as L
+    from imagecompression_adversarial_b200 import ops
+    C, n, h, w = 128, 6, 75, 101
+    gen = lambda seed: torch.Generator(device=dev).manual_seed(seed)
+    gamma, _ = _gdn_params(C, dev, gen(3))
+    x = torch.randn(n, h, w, C, device=dev, generator=gen(1))
+    wp = ops.pack_weight(torch.randn(C, C, 5, 5, device=dev, generator=gen(2)) / 56, 1)
+    yp = torch.randn(n, 2 * h, 2 * w, C, device=dev, generator=gen(4))
+    sp = 0.5 + torch.rand(n, 2 * h, 2 * w, C, device=dev, generator=gen(5))
+    old = os.environ.get("ICADV_TC_STREAM_BWD")
+    res = []
+    try:
+        for level in ("0", "1", "1"):
+            os.environ["ICADV_TC_STREAM_BWD"] = level
+            out = torch.zeros(n, 2 * h, 2 * w, C, device=dev)
+            ops.conv(x, wp, None, form=L.FORM_TCONV, ksize=5, stride=2, n_ch=C, epi=L.EPI_GDN_BWD,
+                     gmat=gamma.t().contiguous(), y_prev=yp, sc_prev=sp, out=out, path="tc", round_out=True)
+            res.append(out)
+    finally:
+        if old is None:
+            os.environ.pop("ICADV_TC_STREAM_BWD", None)
+        else:
+            os.environ["ICADV_TC_STREAM_BWD"] = old
+    assert float(res[0].abs().max()) > 0
+    assert torch.equal(res[1], res[2])
+    assert torch.equal(res[1], res[0])
 
 
 @pytest.mark.parametrize("epi", ["igdn_fwd", "gdn_bwd", "col2im"])

@@ -59,12 +59,21 @@ def test_autoregressive_families_train_g_a_through_the_distortion_term(dev, mode
     from oracle import attack as oatk
     from oracle.attack import synthetic_image
     onet, pnet = pair(model, quality, dev)
+    if model == "cheng2020":
+        # a random-init cheng2020 (20 contractions with residual adds and IGDN) blows its reconstruction up to ~1e10 and
+        # the RD loss to ~1e21, where fp32 comparisons mean nothing: damp the synthesis weights in BOTH implementations
+        with torch.no_grad():
+            for n, q in onet.named_parameters():
+                if n.startswith("g_s.") and n.endswith(".weight"):
+                    q.mul_(0.5)
+        pnet.load_state_dict(onet.state_dict(), strict=True)
     x = torch.cat([synthetic_image(i, 128, 128) for i in range(2)]).to(dev)
     share_noise(onet, pnet, x, dev)
     lm = ptr.LAMBDA_MSE[quality]
     ocrit, pcrit = oatk.RateDistortionLoss("mse", lm).to(dev), ptr.RateDistortionLoss("mse", lm)
     onet.train(); pnet.train()
     oout = ocrit(onet(x), x)
+    assert float(oout["loss"]) < 1e8, float(oout["loss"])
     onet.zero_grad(); oout["loss"].backward()
     pout = pcrit(pnet(x), x)
     pnet.zero_grad(); pout["loss"].backward()
