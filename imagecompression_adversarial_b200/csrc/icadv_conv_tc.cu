@@ -1463,9 +1463,14 @@ __global__ void __launch_bounds__(kPThreads, 1) conv_tcb_kernel(const __grid_con
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
             const int k = 4 * k4 + e;
-            const float s2 = sv[k] * sv[k];
-            if constexpr (EPI == ICADV_EPI_GDN_BWD) a2[e] = round_tf32(v[k] * yv[k] * s2);
-            else a2[e] = s2 > 0.f ? round_tf32(__fdividef(v[k] * yv[k], s2)) : 0.f;
+            // same expression order as conv_tc_kernel / conv_tcp_kernel: the operand is re-rounded to TF32, so a last-bit
+            // difference here would show up as a TF32 ulp in the normalisation GEMM
+            if constexpr (EPI == ICADV_EPI_GDN_BWD) {
+              a2[e] = round_tf32(v[k] * yv[k] * sv[k] * sv[k]);
+            } else {
+              const float s2 = sv[k] * sv[k];
+              a2[e] = s2 > 0.f ? round_tf32(__fdividef(v[k] * yv[k], s2)) : 0.f;
+            }
           }
           *reinterpret_cast<float4*>(bufY + sw128_off(row, k4)) = make_float4(a2[0], a2[1], a2[2], a2[3]);
         }

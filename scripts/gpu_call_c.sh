@@ -1,7 +1,7 @@
 #!/bin/bash
 cd "$GRAFT_REPO_ROOT" 2>/dev/null || true
 rm -f gpurun_out/c_status.txt
-timeout 900 python -m pytest tests/test_gpu_kernels.py -q --maxfail=30 -k "persistent or streaming or deterministic or fused" > gpurun_out/c_kernels.log 2>&1
+timeout 900 python -m pytest tests/test_gpu_kernels.py -q --maxfail=30 -k "persistent or streaming or deterministic or fused or active" > gpurun_out/c_kernels.log 2>&1
 echo "kernels exit $?" >> gpurun_out/c_status.txt
 if grep -q "passed" gpurun_out/c_kernels.log && ! grep -q "failed" gpurun_out/c_kernels.log; then
   ICADV_TC_STREAM_BWD=0 timeout 600 python scripts/launch_table.py 64 gpurun_out/c_table_stream0.json > gpurun_out/c_table_stream0.log 2>&1

@@ -49,16 +49,27 @@ def rel(a, b):
     return float((a - b).pow(2).sum().sqrt() / b.pow(2).sum().sqrt().clamp(min=1e-30))
 
 
+@pytest.mark.parametrize("mode", ["3xtf32", "tf32"])
 @pytest.mark.parametrize("model,quality", [("context", 1), ("cheng2020", 1)])
-def test_autoregressive_families_train_g_a_through_the_distortion_term(dev, model, quality):
+def test_autoregressive_families_train_g_a_through_the_distortion_term(dev, model, quality, mode):
     """The train-mode quantiser ``y + noise`` is differentiable (compressai quantize(.,"noise"), anchors/model.py:102):
     the distortion gradient through g_s(y_hat) and context_prediction(y_hat) must reach g_a.  Every g_a parameter
     gradient of one RD-loss backward against the oracle, plus a direct check that the distortion term alone
     (lambda-weighted MSE, no rate) produces a non-zero g_a gradient."""
+    from imagecompression_adversarial_b200 import precision
     from imagecompression_adversarial_b200 import training as ptr
     from oracle import attack as oatk
     from oracle.attack import synthetic_image
     onet, pnet = pair(model, quality, dev)
+    prev_mode = precision.get()
+    precision.set(mode)
+    try:
+        _autoregressive_train_check(dev, model, quality, mode, onet, pnet, ptr, oatk, synthetic_image)
+    finally:
+        precision.set(prev_mode)
+
+
+def _autoregressive_train_check(dev, model, quality, mode, onet, pnet, ptr, oatk, synthetic_image):
     if model == "cheng2020":
         # a random-init cheng2020 (20 contractions with residual adds and IGDN) blows its reconstruction up to ~1e10 and
         # the RD loss to ~1e21, where fp32 comparisons mean nothing: damp the synthesis weights in BOTH implementations
@@ -81,10 +92,14 @@ def test_autoregressive_families_train_g_a_through_the_distortion_term(dev, mode
     pg = {n: q.grad.detach().clone() for n, q in pnet.named_parameters() if q.grad is not None}
     ga = [n for n in og if n.startswith("g_a.") and float(og[n].abs().max()) > 0]
     assert ga and set(ga) <= set(pg)
-    bound = 2e-2 if model == "cheng2020" else 1e-2        # TF32 contractions, 8 / 20 layers deep
+    # parity mode: fp32-accurate contractions -> every g_a gradient tensor to 2e-3.  Speed mode: TF32 contractions; the
+    # rate gradient reaching y depends on the scales through GaussianConditional's LowerBound(0.11) gate, which flips for
+    # scales on the bound (Precision) -- context (8 layers) stays within 1e-2, cheng2020 (20 layers, damped
+    # synthesis so the rate term dominates) is only bounded loosely there and pinned by the parity-mode run.
+    bound = 2e-3 if mode == "3xtf32" else (0.5 if model == "cheng2020" else 1e-2)
     worst = max((rel(pg[n], og[n]), n) for n in ga)
     assert worst[0] < bound, worst
-    assert abs(float(pout["loss"]) - float(oout["loss"])) <= 3e-3 * abs(float(oout["loss"]))
+    assert abs(float(pout["loss"]) - float(oout["loss"])) <= (1e-4 if mode == "3xtf32" else 3e-3) * abs(float(oout["loss"]))
     # distortion term alone
     pnet.zero_grad()
     (pcrit(pnet(x), x)["distortion_loss"]).backward()
