@@ -50,8 +50,6 @@ class AttackEngine:
         self.roi = roi
         if roi is not None and att_metric != "L2":
             raise L.IcadvError("AttackEngine: the targeted / ROI loss is defined for -att_metric L2 only")
-        if att_metric == "ms-ssim":
-            use_graph = False   # the MS-SSIM composition allocates its pyramid per call; runs eagerly for now
         if steps < 3:
             raise ZeroDivisionError("integer division or modulo by zero")  # attack_rd.py:553 with steps//3 == 0
         dev = device or next(net.parameters()).device
@@ -74,6 +72,10 @@ class AttackEngine:
         self._graph = None
         self.iterations_done = 0
         self.im_s_nchw = self.output_s_nchw = None
+        self._ones = torch.ones(n_img, device=dev, dtype=torch.float32)
+        if att_metric == "ms-ssim":
+            from . import metrics
+            metrics._weights_tensor(dev, metrics.WEIGHTS)   # created outside any graph capture
         self.last_loss_A = f(n_img)   # loss of the budget branch per image (loss_i, or 1 - ms_ssim(im_s, im_in))
         self.last_loss_B = f(n_img)   # loss of the network branch per image (1 - MSE, ms_ssim(out, output_s), or loss_o)
 
@@ -100,6 +102,14 @@ class AttackEngine:
         img = 4.0 * self.n_img * self.per_img           # bytes of one RGB tensor of the batch
         rows = [{"name": "perturb_forward + finalize", "launch": self._perturb_forward, "kernels": 2, "flops": 0.0,
                  "bytes": 3 * img, "bound": "hbm"}]
+        msssim = self.att_metric == "ms-ssim"
+        # MS-SSIM value + gradient: both images' 5-level pyramids (4/3 of the image) read by the forward and again by
+        # the backward (statistics are recomputed, nothing is saved), the gradient pyramid written once, + layout copies
+        ms_bytes = (4.0 / 3.0) * (2 + 2 + 1) * img + 4 * img
+        if msssim:
+            rows.append({"name": "1 - ms_ssim(im_s, im_in) value + gradient (11 launches + layout copies)",
+                         "launch": self._msssim_budget_branch, "kernels": 24, "flops": 0.0, "bytes": ms_bytes,
+                         "bound": "hbm"})
 
         def stack(prog, lst, info):
             for p, i in zip(lst, info):
@@ -108,11 +118,20 @@ class AttackEngine:
 
         stack(self.ga, self.ga.fwd, self.ga.fwd_info)
         stack(self.gs, self.gs.fwd, self.gs.fwd_info)
-        rows.append({"name": "output_loss (clamp + MSE + gradient seed)",
-                     "launch": lambda: self._output_loss(self.x_out, self.g_x), "kernels": 2, "flops": 0.0,
-                     "bytes": 3 * img, "bound": "hbm"})
+        if msssim:
+            rows.append({"name": "ms_ssim(clamp(x_out), output_s) value + gradient + clamp rules",
+                         "launch": self._msssim_output_loss, "kernels": 30, "flops": 0.0, "bytes": ms_bytes + 6 * img,
+                         "bound": "hbm"})
+        else:
+            rows.append({"name": "output_loss (clamp + MSE + gradient seed)",
+                         "launch": lambda: self._output_loss(self.x_out, self.g_x), "kernels": 2, "flops": 0.0,
+                         "bytes": 3 * img, "bound": "hbm"})
         stack(self.gs, self.gs.bwd, self.gs.bwd_info)
         stack(self.ga, self.ga.bwd, self.ga.bwd_info)
+        if msssim:
+            rows.append({"name": "perturb_update_adam (clamp backward + Adam, external budget-branch gradient)",
+                         "launch": self._update_msssim, "kernels": 1, "flops": 0.0, "bytes": 9 * img, "bound": "hbm"})
+            return rows
         rows.append({"name": "perturb_update_adam (clamp backward + Adam)",
                      "launch": lambda: ops.perturb_update_adam(self.im_s, self.noise, self.ga.g_in, self.m, self.v, self.st,
                                                                eps=self.eps, gradA_scale=1.0 / self.per_img,
@@ -177,36 +196,50 @@ class AttackEngine:
         ops.perturb_update_adam(self.im_s, self.noise, g_in, self.m, self.v, self.st, eps=self.eps,
                                 gradA_scale=1.0 / self.per_img, gradB_scale=1.0, w_in=self.w_in)
 
-    def _iteration_msssim(self):
-        """-att_metric ms-ssim (attack_rd.py:335-336, 360-362): budget branch loss = 1 - ms_ssim(im_s, im_in),
-        network branch loss = ms_ssim(output_, output_s); the branch test itself stays on the L2 budget (:333-334)."""
+    def _msssim_budget_branch(self):
+        """Budget branch of -att_metric ms-ssim: loss = 1 - ms_ssim(im_s, im_in) (attack_rd.py:335-336) and its gradient
+        with respect to im_in (channels-last), for every image."""
         from . import metrics
-        ops.perturb_forward(self.im_s, self.noise, self.im_in, self.st, eps=self.eps, budget=self.budget,
-                            force_branch=self.force_branch, lr0=self.lr0, lr_gamma=0.33,
-                            sched_period=self.steps // 3)
-        ones = torch.ones(self.n_img, device=self.device)
-        ms_a, g_a = metrics.ms_ssim_value_and_grad(ops.nhwc_to_nchw(self.im_in), self.im_s_nchw, -ones)
-        g_a_nhwc = ops.nchw_to_nhwc(g_a)
+        ms_a, g_a = metrics.ms_ssim_value_and_grad(ops.nhwc_to_nchw(self.im_in), self.im_s_nchw, -self._ones)
         self.last_loss_A = 1.0 - ms_a
-        self.ga.forward()
-        self.gs.forward()
+        self._g_a_ext = ops.nchw_to_nhwc(g_a)
+
+    def _msssim_output_loss(self):
+        """Network branch: loss = ms_ssim(clamp(x_out), output_s) (attack_rd.py:353-362); writes the gradient seed g_x."""
+        from . import metrics
         x = self.x_out
         if self.clamp:
             lo = ops.bound_forward(x.view(-1), 0.0, False)
             out = ops.bound_forward(lo, 1.0, True).view_as(x)
         else:
             out = x
-        ms_b, g_o = metrics.ms_ssim_value_and_grad(ops.nhwc_to_nchw(out), self.output_s_nchw, ones)
+        ms_b, g_o = metrics.ms_ssim_value_and_grad(ops.nhwc_to_nchw(out), self.output_s_nchw, self._ones)
         g = ops.nchw_to_nhwc(g_o).view(-1)
         if self.clamp:
             g = ops.bound_backward(lo, g, 1.0, True)
             g = ops.bound_backward(x.view(-1), g, 0.0, False)
         self.g_x.copy_(g.view_as(self.g_x))
         self.last_loss_B = ms_b
+
+    def _update_msssim(self):
+        ops.perturb_update_adam(self.im_s, self.noise, self.ga.g_in, self.m, self.v, self.st, eps=self.eps,
+                                gradA_scale=1.0, gradB_scale=1.0, g_a_ext=self._g_a_ext)
+
+    def _iteration_msssim(self):
+        """-att_metric ms-ssim (attack_rd.py:335-336, 360-362): budget branch loss = 1 - ms_ssim(im_s, im_in),
+        network branch loss = ms_ssim(output_, output_s); the branch test itself stays on the L2 budget (:333-334).
+        Every tensor this composition allocates (the two 5-level pyramids, the per-level sums, the layout copies) comes
+        from the CUDA graph's private pool during capture and is reused by every replay."""
+        ops.perturb_forward(self.im_s, self.noise, self.im_in, self.st, eps=self.eps, budget=self.budget,
+                            force_branch=self.force_branch, lr0=self.lr0, lr_gamma=0.33,
+                            sched_period=self.steps // 3)
+        self._msssim_budget_branch()
+        self.ga.forward()
+        self.gs.forward()
+        self._msssim_output_loss()
         self.gs.backward()
         self.ga.backward()
-        ops.perturb_update_adam(self.im_s, self.noise, self.ga.g_in, self.m, self.v, self.st, eps=self.eps,
-                                gradA_scale=1.0, gradB_scale=1.0, g_a_ext=g_a_nhwc)
+        self._update_msssim()
 
     def kernels_per_iteration(self):
         fa, ba = self.ga.n_kernels()

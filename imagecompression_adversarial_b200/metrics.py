@@ -15,6 +15,18 @@ from . import _lib as L
 from .ops import _p, _stream
 
 WEIGHTS = (0.0448, 0.2856, 0.3001, 0.2363, 0.1333)
+_CONST = {}
+
+
+def _weights_tensor(device, weights):
+    """[levels, 1, 1] device tensor of the level weights, created once per device (a host -> device copy from pageable
+    memory is not allowed while a CUDA graph is being captured; the attack loop captures this composition)."""
+    key = (str(device), tuple(weights))
+    t = _CONST.get(key)
+    if t is None:
+        t = torch.tensor(weights, device=device, dtype=torch.float32).view(-1, 1, 1)
+        _CONST[key] = t
+    return t
 
 
 def _taps(size, sigma):
@@ -90,7 +102,7 @@ def _ms_ssim_forward(X, Y, data_range=1.0, size_average=True, win_size=11, win_s
             ph, pw = X.shape[2] % 2, X.shape[3] % 2
             X, Y = _pool(X, ph, pw), _pool(Y, ph, pw)
     vals.append(torch.relu(ss))
-    w = torch.tensor(weights, device=X.device, dtype=torch.float32).view(-1, 1, 1)
+    w = _weights_tensor(X.device, weights)
     val = torch.prod(torch.stack(vals, 0) ** w, dim=0)
     return val.mean() if size_average else val.mean(1)
 
@@ -124,7 +136,7 @@ def ms_ssim_value_and_grad(X, Y, upstream, data_range=1.0, win_size=11, win_sigm
             pads.append((ph, pw))
             xs.append(_pool(xs[-1], ph, pw))
             ys.append(_pool(ys[-1], ph, pw))
-    w = torch.tensor(weights, device=X.device, dtype=torch.float32).view(-1, 1, 1)
+    w = _weights_tensor(X.device, weights)
     V = torch.stack(vals, 0)                       # [levels, B, C]
     P = torch.prod(V ** w, dim=0)                  # [B, C]
     value = P.mean(1)
@@ -165,7 +177,7 @@ def _v2_levels(X, Y, max_val, levels):
 
 
 def _v2_value(lv, levels):
-    w = torch.tensor(WEIGHTS, device=lv[0][0].device, dtype=torch.float32)
+    w = _weights_tensor(lv[0][0].device, WEIGHTS).view(-1)
     mcs_t, ms_t = torch.stack([l[4] for l in lv]), torch.stack([l[3] for l in lv])
     return torch.prod(mcs_t[:levels - 1] ** w[:levels - 1]) * (ms_t[levels - 1] ** w[levels - 1])
 

@@ -263,15 +263,20 @@ def test_attack_trajectory_matches_oracle(dev, model, quality, hw, n, steps, met
         assert abs(float(bpp) - float(o[4])) < max(1e-3, 5e-3 * float(o[4]))
 
 
-def test_graph_replay_equals_eager(dev):
+@pytest.mark.parametrize("metric,hw", [("L2", (64, 64)), ("ms-ssim", (192, 192))])
+def test_graph_replay_equals_eager(dev, metric, hw):
+    """The whole iteration -- for -att_metric ms-ssim including both 5-level MS-SSIM value-and-gradient compositions --
+    replayed from one CUDA graph equals the eager launches bit for bit."""
     from imagecompression_adversarial_b200.engine import AttackEngine
     _, pnet = pair("factorized", 1, dev)
     pnet.train()
-    x = images(2, 64, 64, dev)
-    ref = torch.rand_like(x)
+    x = images(2, *hw, dev)
+    ref = (x + 0.05 * torch.rand_like(x)).clamp(0, 1) if metric == "ms-ssim" else torch.rand_like(x)
     res = []
     for use_graph in (False, True):
-        eng = AttackEngine(pnet, 2, 64, 64, steps=6, use_graph=use_graph)
+        eng = AttackEngine(pnet, 2, *hw, steps=6, use_graph=use_graph, att_metric=metric,
+                           noise_budget=1e-4 if metric == "L2" else 2e-5)
+        assert eng.use_graph == use_graph
         eng.load(x, ref)
         eng.run(6)
         torch.cuda.synchronize()

@@ -492,8 +492,11 @@ def test_persistent_variant_equals_per_tile_kernel(dev, persist_env, case):
 
 def test_streaming_backward_kernel_matches_the_in_place_persistent_kernel(dev):
     """ICADV_TC_STREAM_BWD=0 (saved chunks fetched per epilogue group, re-read in pass 2) vs =1 (saved-tensor ring, pass-1
-    products stashed in TMEM, plain stores): same chunk order, same arithmetic -> bit-identical, and both bit-reproducible;
-    ~17 items per CTA so every ring and the TMEM buffers wrap many times, ragged tile edges included."""
+    products stashed in TMEM, plain stores): same chunk order and the same normalisation operand; the last step differs in
+    one rounding (g*sc is rounded to fp32 when it is stashed, the other kernel fuses it into the final multiply-add), so
+    results agree to fp32 round-off, with a TF32 ulp on the few elements where that crosses the output rounding.  The
+    streaming kernel itself is bit-reproducible.  ~17 items per CTA so every ring and the TMEM buffers wrap many times,
+    ragged tile edges included."""
     from imagecompression_adversarial_b200 import _lib as L
     from imagecompression_adversarial_b200 import ops
     C, n, h, w = 128, 6, 75, 101
@@ -519,7 +522,9 @@ def test_streaming_backward_kernel_matches_the_in_place_persistent_kernel(dev):
             os.environ["ICADV_TC_STREAM_BWD"] = old
     assert float(res[0].abs().max()) > 0
     assert torch.equal(res[1], res[2])
-    assert torch.equal(res[1], res[0])
+    exact = torch.isclose(res[1], res[0], rtol=1e-5, atol=1e-6)
+    assert float((~exact).float().mean()) < 1e-3, float((~exact).float().mean())
+    torch.testing.assert_close(res[1], res[0], rtol=1.2e-3, atol=1e-6)
 
 
 @pytest.mark.parametrize("epi", ["igdn_fwd", "gdn_bwd", "col2im"])

@@ -99,7 +99,7 @@ def _autoregressive_train_check(dev, model, quality, mode, onet, pnet, ptr, oatk
     bound = 2e-3 if mode == "3xtf32" else (0.5 if model == "cheng2020" else 1e-2)
     worst = max((rel(pg[n], og[n]), n) for n in ga)
     assert worst[0] < bound, worst
-    assert abs(float(pout["loss"]) - float(oout["loss"])) <= (1e-4 if mode == "3xtf32" else 3e-3) * abs(float(oout["loss"]))
+    assert abs(float(pout["loss"]) - float(oout["loss"])) <= (5e-4 if mode == "3xtf32" else 3e-3) * abs(float(oout["loss"]))
     # distortion term alone
     pnet.zero_grad()
     (pcrit(pnet(x), x)["distortion_loss"]).backward()
