@@ -1342,10 +1342,18 @@ __global__ void __launch_bounds__(kPThreads, 1) conv_tcb_kernel(const __grid_con
       uint32_t free_bits = 3;
       int b = 0;
       bool w_ok = false;
+      const bool prof = p.dbg != nullptr;
+      long long c_free = 0, c_ring = 0, c_ring_p = 0, n_items = 0;
+      const long long c_start = prof ? clock64() : 0;
       for (int item = blockIdx.x; item < total; item += gridDim.x, b ^= 1) {
         const TcpItem it = tcp_decode(p, item);
         const TcpClass cl = p.cls[it.cls];
-        mbar_wait(&tmem_free[b], (free_bits >> b) & 1u);
+        ++n_items;
+        if (!mbar_test_wait(&tmem_free[b], (free_bits >> b) & 1u)) {
+          const long long t0 = clock64();
+          mbar_wait(&tmem_free[b], (free_bits >> b) & 1u);
+          c_free += clock64() - t0;
+        }
         free_bits ^= 1u << b;
         tc_fence_after_sync();
         const uint32_t d = tmem + b * 128;
@@ -1356,11 +1364,19 @@ __global__ void __launch_bounds__(kPThreads, 1) conv_tcb_kernel(const __grid_con
             const int t_end = p.groups[g].tap_end;
             int t = p.groups[g].tap_begin;
             uint32_t aoff = static_cast<uint32_t>(p.tap_aoff[t]) >> 4;
-            mbar_wait(&pfull[ps], p_par);
+            if (!mbar_test_wait(&pfull[ps], p_par)) {
+              const long long t0 = clock64();
+              mbar_wait(&pfull[ps], p_par);
+              c_ring_p += clock64() - t0;
+            }
             for (; t < t_end; ++t) {
               const uint64_t ad = (static_cast<uint64_t>(a_hi) << 32) | (p_lo + aoff);
               const uint64_t bd = (static_cast<uint64_t>(hi_dense) << 32) | w_lo;
-              if (!w_ok) mbar_wait(&wfull[s], s_par);
+              if (!w_ok) {
+                const long long t0 = clock64();
+                mbar_wait(&wfull[s], s_par);
+                c_ring += clock64() - t0;
+              }
               uint64_t* wdone = &wempty[s];
               if (++s == S) { s = 0; s_par ^= 1; w_lo = w_lo0; } else { w_lo += w_step; }
               tc_fence_after_sync();
@@ -1378,6 +1394,10 @@ __global__ void __launch_bounds__(kPThreads, 1) conv_tcb_kernel(const __grid_con
           }
         }
         tc_commit(&acc_full[b]);
+      }
+      if (prof) {
+        long long* q = p.dbg + (int64_t)blockIdx.x * 16;
+        q[0] = clock64() - c_start; q[1] = c_ring + c_ring_p; q[2] = c_free; q[4] = c_ring_p; q[7] = n_items; q[8] = q[0];
       }
     }
     __syncwarp();
@@ -1434,9 +1454,13 @@ __global__ void __launch_bounds__(kPThreads, 1) conv_tcb_kernel(const __grid_con
       float* orow = p.out + (((int64_t)it.img * p.o_h + p.o_s * gi + o_a) * p.o_w + p.o_s * gj + o_b) * p.n_ch;
       const uint32_t t_lane = tmem + (static_cast<uint32_t>(q4 * 32) << 16);
       const uint32_t t_acc = t_lane + b * 128, t_norm = t_lane + 256, t_stash = t_lane + 384;
+      const bool eprof = p.dbg != nullptr && leader;
+      const long long e0 = eprof ? clock64() : 0;
+      long long e_ys = 0;
       mbar_wait(&acc_full[b], (acc_bits >> b) & 1u);
       acc_bits ^= 1u << b;
       tc_fence_after_sync();
+      const long long e1 = eprof ? clock64() : 0;
       // ---- pass 1: this group's chunks, in stream order
       for (int j = 0; j < half; ++j) {
         const int c = grp * half + j;
@@ -1453,7 +1477,8 @@ __global__ void __launch_bounds__(kPThreads, 1) conv_tcb_kernel(const __grid_con
           const float4 bb = b4[k];
           v[4 * k] += bb.x; v[4 * k + 1] += bb.y; v[4 * k + 2] += bb.z; v[4 * k + 3] += bb.w;
         }
-        mbar_wait(&ys_full[slot], par);
+        if (eprof) { const long long t0 = clock64(); mbar_wait(&ys_full[slot], par); e_ys += clock64() - t0; }
+        else mbar_wait(&ys_full[slot], par);
         read_row32(bufY, row, yv);
         read_row32(bufS, row, sv);
         // operand of the normalisation GEMM, written in place over this thread's own y row (16 bytes at a time)
@@ -1488,9 +1513,11 @@ __global__ void __launch_bounds__(kPThreads, 1) conv_tcb_kernel(const __grid_con
         mbar_arrive(&a2_ready[slot]);
       }
       // ---- pass 2: out = g sc -+ (y / sc) (gamma^T t), from TMEM only
+      const long long e2 = eprof ? clock64() : 0;
       mbar_wait(norm_full, nfull_par);
       nfull_par ^= 1;
       tc_fence_after_sync();
+      const long long e3 = eprof ? clock64() : 0;
       for (int j = 0; j < half; ++j) {
         const int c = grp * half + j;
         float v[32], xs[32], w[32];
@@ -1513,6 +1540,13 @@ __global__ void __launch_bounds__(kPThreads, 1) conv_tcb_kernel(const __grid_con
       tc_fence_before_sync();
       named_bar_sync(bar_id, 128);
       if (leader) { mbar_arrive(&tmem_free[b]); mbar_arrive(norm_free); }
+      if (eprof) {   // per group: wait acc, pass 1 (+ norm wait), pass 2; slots 5 / 6: of pass 1, blocked on the saved-tensor ring
+        long long* q = p.dbg + (int64_t)blockIdx.x * 16;
+        const long long e4 = clock64();
+        q[9 + grp * 3] += e1 - e0; q[10 + grp * 3] += e3 - e1; q[11 + grp * 3] += e4 - e3;
+        q[5 + grp] += e_ys;
+        if (grp == 0) q[3] += e3 - e2;
+      }
     }
   }
 

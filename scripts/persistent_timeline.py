@@ -39,7 +39,8 @@ def run(name, d, keep):
     print(f"   of the ring wait: {med[4]:.1f} us on the patch ring")
     for g in range(2):
         print(f"   epilogue group {g}: wait acc {med[9 + 3 * g]:8.1f}  pass1(+norm wait) {med[10 + 3 * g]:8.1f}  pass2 {med[11 + 3 * g]:8.1f} us")
-    print(f"   group 0 waiting for the last normalisation MMA: {med[3]:.1f} us")
+    print(f"   group 0 waiting for the last normalisation MMA: {med[3]:.1f} us;  blocked on the saved-tensor ring (streaming "
+          f"backward kernel): group 0 {med[5]:.1f} us, group 1 {med[6]:.1f} us")
 
 
 # g_s.4: deconv 128->128 + IGDN forward at 128x192 -> 256x384
@@ -59,3 +60,14 @@ pad = ops.pad_rgb4(xi, ops.alloc_pad4(n, H, W, dev))
 wr = ops.pack_weight_rgb(torch.randn(Cc, 3, 5, 5, device=dev, generator=gen(6)) / 9)
 d = ops.make_desc(pad, wr, beta, out, form=L.FORM_SCONV, ksize=5, stride=2, n_ch=Cc, epi=L.EPI_GDN_FWD, gmat=gm, beta=beta, out_scale=sc, in_pad4=True)
 run("g_a.0 rgb_in + GDN fwd (persistent)", d, (pad, wr, out, sc))
+# g_s.6 dgrad: rgb_in + IGDN backward (the HBM-bound launch the streaming backward kernel exists for)
+gx = torch.randn(n, H, W, 3, device=dev, generator=gen(7))
+padg = ops.pad_rgb4(gx, ops.alloc_pad4(n, H, W, dev))
+d = ops.make_desc(padg, wr, None, gin, form=L.FORM_SCONV, ksize=5, stride=2, n_ch=Cc, epi=L.EPI_IGDN_BWD, gmat=gm, y_prev=yp, sc_prev=sp, in_pad4=True)
+run("g_s.6 dgrad rgb_in + IGDN bwd", d, (padg, wr, gin, yp, sp))
+# g_s.4 dgrad: conv 5x5/2 + IGDN backward
+g4 = torch.randn(n, H // 2, W // 2, Cc, device=dev, generator=gen(8))
+yq = torch.randn(n, H // 4, W // 4, Cc, device=dev, generator=gen(9)); sq = 0.5 + torch.rand(n, H // 4, W // 4, Cc, device=dev, generator=gen(10))
+go = torch.empty_like(yq)
+d = ops.make_desc(g4, w, None, go, form=L.FORM_SCONV, ksize=5, stride=2, n_ch=Cc, epi=L.EPI_IGDN_BWD, gmat=gm, y_prev=yq, sc_prev=sq)
+run("g_s.4 dgrad conv + IGDN bwd", d, (g4, w, go, yq, sq))
