@@ -541,7 +541,7 @@ __global__ void __launch_bounds__(kThreads, 2) conv_tc_kernel(const __grid_const
               for (int j = 0; j < 32; ++j) {
                 // pixels outside the image read as zeros (sc = 0): keep them finite
                 const float s2 = sv[j] * sv[j];
-                a2[j] = s2 > 0.f ? round_tf32(__fdividef(v[j] * yv[j], s2)) : 0.f;
+                a2[j] = s2 > 0.f ? round_tf32(fast_div(v[j] * yv[j], s2)) : 0.f;
               }
             }
           }
@@ -582,7 +582,7 @@ __global__ void __launch_bounds__(kThreads, 2) conv_tc_kernel(const __grid_const
             constexpr float sign = (EPI == ICADV_EPI_GDN_BWD) ? -1.f : 1.f;
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
-              const float xs = sv[j] > 0.f ? __fdividef(yv[j], sv[j]) : 0.f;   // x = y / sc
+              const float xs = sv[j] > 0.f ? fast_div(yv[j], sv[j]) : 0.f;   // x = y / sc
               v[j] = v[j] * sv[j] + sign * xs * w[j];
             }
             store_chunk(c, v, nullptr);
@@ -1078,7 +1078,7 @@ __global__ void __launch_bounds__(kPThreads, 1) conv_tcp_kernel(const __grid_con
 #pragma unroll
               for (int j = 0; j < 32; ++j) {
                 const float s2 = sv[j] * sv[j];
-                a2[j] = s2 > 0.f ? round_tf32(__fdividef(v[j] * yv[j], s2)) : 0.f;
+                a2[j] = s2 > 0.f ? round_tf32(fast_div(v[j] * yv[j], s2)) : 0.f;
               }
             }
             write_row32(bufY, row, a2);                 // in place: this thread's own row
@@ -1135,7 +1135,7 @@ __global__ void __launch_bounds__(kPThreads, 1) conv_tcp_kernel(const __grid_con
             constexpr float sign = (EPI == ICADV_EPI_GDN_BWD) ? -1.f : 1.f;
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
-              const float xs = sv[j] > 0.f ? __fdividef(yv[j], sv[j]) : 0.f;
+              const float xs = sv[j] > 0.f ? fast_div(yv[j], sv[j]) : 0.f;
               v[j] = v[j] * sv[j] + sign * xs * w[j];
               if (p.round_out) v[j] = round_tf32(v[j]);
             }
@@ -1293,7 +1293,9 @@ __global__ void __launch_bounds__(kPThreads, 1) conv_tcb_kernel(const __grid_con
       int ys = 0;
       uint32_t y_par = 1;
       while (p_live || y_live) {
+        bool idle = true;
         if (y_live && mbar_test_wait(&ys_empty[ys], y_par)) {
+          idle = false;
           const int c = (y_q & 1) * half + (y_q >> 1);               // the two groups' chunks alternate (fixed order)
           uint8_t* dst = ysr + ys * 2 * kABytes;
           mbar_arrive_expect_tx(&ys_full[ys], 2 * kABytes);
@@ -1308,6 +1310,7 @@ __global__ void __launch_bounds__(kPThreads, 1) conv_tcb_kernel(const __grid_con
           }
         }
         if (p_live && mbar_test_wait(&pempty[ps], p_par)) {
+          idle = false;
           const int cx = pit.j0 + p.groups[p_g].dx0, cy = pit.i0 + p.groups[p_g].dy0;
           uint8_t* pdst = smem + ps * p.patch_bytes;
           mbar_arrive_expect_tx(&pfull[ps], p.groups[p_g].bytes);
@@ -1326,6 +1329,7 @@ __global__ void __launch_bounds__(kPThreads, 1) conv_tcb_kernel(const __grid_con
             if (p_live) p_g = p.cls[pit.cls].g_begin;
           }
         }
+        if (idle) __nanosleep(64);   // both rings full: leave the issue slots of this scheduler to its epilogue warps
       }
     }
     __syncwarp();
@@ -1446,6 +1450,7 @@ __global__ void __launch_bounds__(kPThreads, 1) conv_tcb_kernel(const __grid_con
     uint32_t acc_bits = 0, nfull_par = 0;
     int b = 0;
     uint32_t seq0 = 0;                         // stream position of this item's first chunk
+    const uint32_t r_log2 = R == 4 ? 2u : 1u;
     for (int item = blockIdx.x; item < total; item += gridDim.x, b ^= 1, seq0 += nC) {
       const TcpItem it = tcp_decode(p, item);
       const int o_a = p.cls[it.cls].o_a, o_b = p.cls[it.cls].o_b;
@@ -1465,17 +1470,19 @@ __global__ void __launch_bounds__(kPThreads, 1) conv_tcb_kernel(const __grid_con
       for (int j = 0; j < half; ++j) {
         const int c = grp * half + j;
         const uint32_t seq = seq0 + 2 * j + grp;
-        const uint32_t slot = seq % R, par = (seq / R) & 1u;
+        const uint32_t slot = seq & (R - 1), par = (seq >> r_log2) & 1u;    // R is a power of two
         uint8_t* bufY = ysr + slot * 2 * kABytes;
         uint8_t* bufS = bufY + kABytes;
         float v[32], yv[32], sv[32];
         tmem_ld32(t_acc + c * 32, v);
         tmem_ld_wait();
-        const float4* b4 = reinterpret_cast<const float4*>(sbias + c * 32);
+        if (p.bias != nullptr) {                    // an input-gradient contraction has no bias: uniform, normally skipped
+          const float4* b4 = reinterpret_cast<const float4*>(sbias + c * 32);
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          const float4 bb = b4[k];
-          v[4 * k] += bb.x; v[4 * k + 1] += bb.y; v[4 * k + 2] += bb.z; v[4 * k + 3] += bb.w;
+          for (int k = 0; k < 8; ++k) {
+            const float4 bb = b4[k];
+            v[4 * k] += bb.x; v[4 * k + 1] += bb.y; v[4 * k + 2] += bb.z; v[4 * k + 3] += bb.w;
+          }
         }
         if (eprof) { const long long t0 = clock64(); mbar_wait(&ys_full[slot], par); e_ys += clock64() - t0; }
         else mbar_wait(&ys_full[slot], par);
@@ -1494,7 +1501,7 @@ __global__ void __launch_bounds__(kPThreads, 1) conv_tcb_kernel(const __grid_con
               a2[e] = round_tf32(v[k] * yv[k] * sv[k] * sv[k]);
             } else {
               const float s2 = sv[k] * sv[k];
-              a2[e] = s2 > 0.f ? round_tf32(__fdividef(v[k] * yv[k], s2)) : 0.f;
+              a2[e] = s2 > 0.f ? round_tf32(fast_div(v[k] * yv[k], s2)) : 0.f;
             }
           }
           *reinterpret_cast<float4*>(bufY + sw128_off(row, k4)) = make_float4(a2[0], a2[1], a2[2], a2[3]);
@@ -1503,7 +1510,7 @@ __global__ void __launch_bounds__(kPThreads, 1) conv_tcb_kernel(const __grid_con
         // the products pass 2 needs: g * sc over the accumulator chunk, y / sc in the stash
 #pragma unroll
         for (int k = 0; k < 32; ++k) {
-          const float xs = sv[k] > 0.f ? __fdividef(yv[k], sv[k]) : 0.f;
+          const float xs = sv[k] > 0.f ? fast_div(yv[k], sv[k]) : 0.f;
           v[k] = v[k] * sv[k];
           yv[k] = xs;
         }
@@ -1877,7 +1884,7 @@ static int build_persistent(const icadv_conv_desc* d, int mode, const Geometry& 
     }
     int P = 2, S = per_item <= 8 ? 2 : 3;
     int R = (kSmemLimit - fixed - P * p.patch_bytes - S * wbytes) / pair;
-    if (R > kMaxYs) R = kMaxYs;
+    R = R >= 4 ? 4 : (R >= 2 ? 2 : 0);   // power of two (slot = sequence number & (R - 1) in the kernel)
     if (R >= 2) {
       // left-over shared memory: more weight stages (long main loops), then a third patch slot
       while (S < 4 && fixed + P * p.patch_bytes + (S + 1) * wbytes + R * pair <= kSmemLimit) ++S;

@@ -233,6 +233,14 @@ __device__ __forceinline__ float round_tf32(float x) {
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
   return __uint_as_float(u);
 }
+// a / b as a * rcp.approx(b): one MUFU and one multiply.  (__fdividef / div.approx computes the same product for
+// |b| in [2^-126, 2^126] but carries a dozen instructions of range scaling per call; the divisors here are GDN scales,
+// O(0.1 .. 100).)
+__device__ __forceinline__ float fast_div(float a, float b) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(b));
+  return a * r;
+}
 // byte offset of 16-byte chunk j of row r inside a [rows x 128 B] SWIZZLE_128B tile (1024 B aligned)
 __device__ __forceinline__ uint32_t sw128_off(int r, int j) { return (r << 7) + (((j ^ (r & 7)) & 7) << 4); }
 
