@@ -1193,10 +1193,12 @@ __global__ void __launch_bounds__(kPThreads, 1) conv_tcp_kernel(const __grid_con
 //     TMEM: [acc 0 | acc 1 | norm | stash] x 128 columns;
 //   * a slot is handed back by the tcgen05.commit of the normalisation MMAs that read its operand (written in place
 //     over the y rows), i.e. without any epilogue-side wait;
-//   * the output leaves with plain 128-byte stores (one pixel row of 32 channels per thread and chunk: whole lines), so
-//     no staging buffers and no store-drain waits; gamma^T stays resident.
-// Patches and saved chunks are produced by ONE polling thread (two cursors, mbarrier.test_wait, no blocking wait: a
-// blocked patch request must not hold back the saved-tensor stream and vice versa).
+//   * gamma^T is streamed (two 16 KB stages, one chunk per normalisation K-block, L2-resident) instead of held resident:
+//     the 32 KB that frees pay for one 16 KB output staging tile per epilogue group -- the output leaves through TMA
+//     stores (per-thread 128-byte rows written with plain stores were tried: the LSU needs 32 line transactions per
+//     instruction, 2 us per item).
+// Patches, saved chunks and gamma^T chunks are produced by ONE polling thread (three cursors, mbarrier.test_wait, no
+// blocking wait: a blocked patch request must not hold back the saved-tensor stream and vice versa).
 // Arithmetic and accumulation order are those of conv_tcp_kernel (bit-identical results).
 // =====================================================================================================
 constexpr int kMaxYs = 4;
@@ -1211,14 +1213,16 @@ __global__ void __launch_bounds__(kPThreads, 1) conv_tcb_kernel(const __grid_con
   const int half = nC >> 1;                                          // chunks per epilogue group (nC is even)
   const uint32_t b_bytes = static_cast<uint32_t>(p.n_ch) * 128u;
   uint8_t* wring = smem + P * p.patch_bytes;
-  uint8_t* gmat = wring + S * b_bytes;                               // nC boxes [32 x n_ch] of gamma^T, resident
-  uint8_t* ysr = gmat + nC * b_bytes;                                // R slots x [y chunk 16 KB | scale chunk 16 KB]
-  uint64_t* wfull = reinterpret_cast<uint64_t*>(ysr + R * 2 * kABytes);
+  uint8_t* gring = wring + S * b_bytes;                              // 2 stages [32 x n_ch] of gamma^T chunks (streamed from L2)
+  uint8_t* ysr = gring + 2 * b_bytes;                                // R slots x [y chunk 16 KB | scale chunk 16 KB]
+  uint8_t* ostage = ysr + R * 2 * kABytes;                           // one 16 KB output staging tile per epilogue group
+  uint64_t* wfull = reinterpret_cast<uint64_t*>(ostage + 2 * kABytes);
   uint64_t* wempty = wfull + kMaxStages;
   uint64_t* pfull = wempty + kMaxStages;
   uint64_t* pempty = pfull + kMaxPatch;
-  uint64_t* gfull = pempty + kMaxPatch;       // [1]
-  uint64_t* acc_full = gfull + 1;             // [2]
+  uint64_t* g_full = pempty + kMaxPatch;      // [2]
+  uint64_t* g_empty = g_full + 2;             // [2]
+  uint64_t* acc_full = g_empty + 2;           // [2]
   uint64_t* tmem_free = acc_full + 2;         // [2]  both epilogue groups have finished with accumulator b
   uint64_t* norm_full = tmem_free + 2;        // [1]
   uint64_t* norm_free = norm_full + 1;        // [1]  both groups have read the norm region
@@ -1231,8 +1235,10 @@ __global__ void __launch_bounds__(kPThreads, 1) conv_tcb_kernel(const __grid_con
   if (threadIdx.x == 0) {
     for (int s = 0; s < S; ++s) { mbar_init(&wfull[s], 1); mbar_init(&wempty[s], 1); }
     for (int s = 0; s < P; ++s) { mbar_init(&pfull[s], 1); mbar_init(&pempty[s], 1); }
-    mbar_init(gfull, 1);
-    for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&tmem_free[b], 2); }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&acc_full[b], 1); mbar_init(&tmem_free[b], 2);
+      mbar_init(&g_full[b], 1); mbar_init(&g_empty[b], 1);
+    }
     mbar_init(norm_full, 1); mbar_init(norm_free, 2);
     for (int k = 0; k < R; ++k) { mbar_init(&ys_full[k], 1); mbar_init(&ys_empty[k], 1); mbar_init(&a2_ready[k], 128); }
     mbar_fence_init();
@@ -1240,7 +1246,7 @@ __global__ void __launch_bounds__(kPThreads, 1) conv_tcb_kernel(const __grid_con
   if (warp == 1) { tmem_alloc(tmem_ptr, 512); tmem_relinquish(); }
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&p.a_map[0]); tma_prefetch_desc(&p.w_map); tma_prefetch_desc(&p.g_map);
-    tma_prefetch_desc(&p.yprev_map[0]); tma_prefetch_desc(&p.sc_map[0]);
+    tma_prefetch_desc(&p.yprev_map[0]); tma_prefetch_desc(&p.sc_map[0]); tma_prefetch_desc(&p.out_map[0]);
   }
   for (int i = threadIdx.x; i < p.n_ch; i += kPThreads) sbias[i] = p.bias != nullptr ? __ldg(p.bias + i) : 0.f;
   tc_fence_before_sync();
@@ -1252,10 +1258,8 @@ __global__ void __launch_bounds__(kPThreads, 1) conv_tcb_kernel(const __grid_con
   // TMEM columns: accumulator b at b * 128, norm at 256, stash (y / sc) at 384
 
   if (warp == 0) {
-    // ===================== TMA producer: weights (+ the resident gamma^T) =====================
+    // ===================== TMA producer: weights =====================
     if (elect_one_sync()) {
-      mbar_arrive_expect_tx(gfull, nC * b_bytes);
-      for (int c = 0; c < nC; ++c) tma_load_2d(gmat + c * b_bytes, &p.g_map, gfull, c * 32, 0);
       int s = 0;
       uint32_t s_par = 1;
       uint8_t* wdst = wring;
@@ -1292,8 +1296,20 @@ __global__ void __launch_bounds__(kPThreads, 1) conv_tcb_kernel(const __grid_con
       if (y_live) yit = tcp_decode(p, y_item);
       int ys = 0;
       uint32_t y_par = 1;
-      while (p_live || y_live) {
+      // third cursor: the gamma^T chunk of every normalisation K-block, in the stream's chunk order (L2-resident, 64 KB)
+      int g_item = blockIdx.x, g_q = 0, gs = 0;
+      uint32_t g_par = 1;
+      bool g_live = g_item < total;
+      while (p_live || y_live || g_live) {
         bool idle = true;
+        if (g_live && mbar_test_wait(&g_empty[gs], g_par)) {
+          idle = false;
+          const int c = (g_q & 1) * half + (g_q >> 1);
+          mbar_arrive_expect_tx(&g_full[gs], b_bytes);
+          tma_load_2d(gring + gs * b_bytes, &p.g_map, &g_full[gs], c * 32, 0);
+          if (++gs == 2) { gs = 0; g_par ^= 1; }
+          if (++g_q == nC) { g_q = 0; g_item += gridDim.x; g_live = g_item < total; }
+        }
         if (y_live && mbar_test_wait(&ys_empty[ys], y_par)) {
           idle = false;
           const int c = (y_q & 1) * half + (y_q >> 1);               // the two groups' chunks alternate (fixed order)
@@ -1412,20 +1428,19 @@ __global__ void __launch_bounds__(kPThreads, 1) conv_tcb_kernel(const __grid_con
     if (elect_one_sync()) {
       const uint32_t idesc = umma_idesc_tf32(kTileM, p.n_ch);
       const uint32_t hi_dense = (1024u >> 4) | (1u << 14) | (2u << 29);
-      const uint32_t g_lo0 = ((smem_u32(gmat) >> 4) & 0x3FFFu) | (1u << 16);
+      const uint32_t g_lo0 = ((smem_u32(gring) >> 4) & 0x3FFFu) | (1u << 16);
       const uint32_t y_lo0 = ((smem_u32(ysr) >> 4) & 0x3FFFu) | (1u << 16);
       const uint32_t w_step = b_bytes >> 4;
       const uint32_t dn = tmem + 256;
-      int ys = 0;
-      uint32_t y_par = 0, nf_par = 1;
-      mbar_wait(gfull, 0);
+      int ys = 0, gs = 0;
+      uint32_t y_par = 0, g_par = 0, nf_par = 1;
       for (int item = blockIdx.x; item < total; item += gridDim.x) {
         mbar_wait(norm_free, nf_par);            // both groups have read the previous item's norm region
         nf_par ^= 1;
         for (int q = 0; q < nC; ++q) {
-          const int c = (q & 1) * half + (q >> 1);
           const uint64_t ad = (static_cast<uint64_t>(hi_dense) << 32) | (y_lo0 + ys * ((2 * kABytes) >> 4));
-          const uint64_t bd = (static_cast<uint64_t>(hi_dense) << 32) | (g_lo0 + c * w_step);
+          const uint64_t bd = (static_cast<uint64_t>(hi_dense) << 32) | (g_lo0 + gs * w_step);
+          mbar_wait(&g_full[gs], g_par);
           mbar_wait(&a2_ready[ys], y_par);
           tc_fence_after_sync();
           tc_mma_tf32(dn, ad, bd, idesc, q > 0 ? 1u : 0u);
@@ -1433,8 +1448,10 @@ __global__ void __launch_bounds__(kPThreads, 1) conv_tcb_kernel(const __grid_con
           tc_mma_tf32(dn, ad + 4, bd + 4, idesc, 1u);
           tc_mma_tf32(dn, ad + 6, bd + 6, idesc, 1u);
           tc_commit(&ys_empty[ys]);
+          tc_commit(&g_empty[gs]);
           if (q == nC - 1) tc_commit(norm_full);
           if (++ys == R) { ys = 0; y_par ^= 1; }
+          if (++gs == 2) { gs = 0; g_par ^= 1; }
         }
       }
     }
@@ -1446,6 +1463,7 @@ __global__ void __launch_bounds__(kPThreads, 1) conv_tcb_kernel(const __grid_con
     const int row = q4 * 32 + lane;
     const bool leader = (row == 0);
     const uint32_t bar_id = 1 + grp;
+    uint8_t* obuf = ostage + grp * kABytes;
     constexpr float sign = (EPI == ICADV_EPI_GDN_BWD) ? -1.f : 1.f;
     uint32_t acc_bits = 0, nfull_par = 0;
     int b = 0;
@@ -1456,7 +1474,7 @@ __global__ void __launch_bounds__(kPThreads, 1) conv_tcb_kernel(const __grid_con
       const int o_a = p.cls[it.cls].o_a, o_b = p.cls[it.cls].o_b;
       const int gi = it.i0 + row / kTW, gj = it.j0 + row % kTW;
       const bool px_ok = gi < p.t_h && gj < p.t_w;
-      float* orow = p.out + (((int64_t)it.img * p.o_h + p.o_s * gi + o_a) * p.o_w + p.o_s * gj + o_b) * p.n_ch;
+      (void)o_a; (void)o_b; (void)px_ok;
       const uint32_t t_lane = tmem + (static_cast<uint32_t>(q4 * 32) << 16);
       const uint32_t t_acc = t_lane + b * 128, t_norm = t_lane + 256, t_stash = t_lane + 384;
       const bool eprof = p.dbg != nullptr && leader;
@@ -1537,16 +1555,22 @@ __global__ void __launch_bounds__(kPThreads, 1) conv_tcb_kernel(const __grid_con
           v[k] = v[k] + sign * xs[k] * w[k];
           if (p.round_out) v[k] = round_tf32(v[k]);
         }
-        if (px_ok) {
-          float4* dst = reinterpret_cast<float4*>(orow + c * 32);
-#pragma unroll
-          for (int k = 0; k < 8; ++k) dst[k] = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
-        }
+        // out through this group's staging tile and one TMA store (a per-thread 128-byte row written with plain
+        // stores costs the LSU 32 line transactions per instruction: measured 2 us per item)
+        if (leader) tma_store_wait_read0();        // the previous chunk's store has finished reading the tile
+        __syncwarp();
+        named_bar_sync(bar_id, 128);
+        write_row32(obuf, row, v);
+        fence_proxy_async_smem();
+        named_bar_sync(bar_id, 128);
+        if (leader) { tma_store_4d(&p.out_map[it.cls], obuf, c * 32, it.j0, it.i0, it.img); tma_store_commit(); }
+        __syncwarp();
       }
       // this item's TMEM reads are over: accumulator b goes back to the main issuer, the norm region to its issuer
       tc_fence_before_sync();
       named_bar_sync(bar_id, 128);
       if (leader) { mbar_arrive(&tmem_free[b]); mbar_arrive(norm_free); }
+      __syncwarp();
       if (eprof) {   // per group: wait acc, pass 1 (+ norm wait), pass 2; slots 5 / 6: of pass 1, blocked on the saved-tensor ring
         long long* q = p.dbg + (int64_t)blockIdx.x * 16;
         const long long e4 = clock64();
@@ -1555,6 +1579,8 @@ __global__ void __launch_bounds__(kPThreads, 1) conv_tcb_kernel(const __grid_con
         if (grp == 0) q[3] += e3 - e2;
       }
     }
+    if (leader) tma_store_wait0();
+    __syncwarp();
   }
 
   tc_fence_before_sync();
@@ -1873,10 +1899,10 @@ static int build_persistent(const icadv_conv_desc* d, int mode, const Geometry& 
   p.active = d->active; p.n_active = d->n_active;
   p.out = d->out;
   if (stream) {
-    // ---- streaming backward kernel: [patch ring | weight ring | gamma^T | saved-tensor ring R x 32 KB | barriers + bias]
+    // ---- streaming backward kernel: [patch ring | weight ring | gamma^T ring | saved-tensor ring R x 32 KB | staging | barriers + bias]
     p.patch_bytes = (max_patch + 1023) & ~1023;
     const int wbytes = N * 128, pair = 2 * kABytes;
-    const int fixed = 1024 + kBarBlock + 2 * N * 4 + N * N * 4;
+    const int fixed = 1024 + kBarBlock + 2 * N * 4 + 2 * wbytes + 2 * kABytes;   // + gamma^T ring (2 stages) + 2 staging tiles
     int per_item = 0;   // patches of one item
     for (int l = 0; l < p.n_class; ++l) {
       const int n = (p.cls[l].g_end - p.cls[l].g_begin) * p.k_chunks;
