@@ -1191,8 +1191,8 @@ __global__ void __launch_bounds__(kPThreads, 1) conv_tcp_kernel(const __grid_con
 //   * pass 1 leaves its per-element products in TMEM instead of re-reading y and scale in pass 2: g*sc overwrites the
 //     accumulator chunk in place and y/sc goes to a stash region (tcgen05.st), so every saved byte crosses the SM once;
 //     TMEM: [acc 0 | acc 1 | norm | stash] x 128 columns;
-//   * a slot is handed back by the tcgen05.commit of the normalisation MMAs that read its operand (written in place
-//     over the y rows), i.e. without any epilogue-side wait;
+//   * a slot is handed back as soon as its 128 consumer threads hold the pair in registers (the normalisation operand
+//     goes to the group's staging tile, not in place), so the next pair of the stream is in flight during the arithmetic;
 //   * gamma^T is streamed (two 16 KB stages, one chunk per normalisation K-block, L2-resident) instead of held resident:
 //     the 32 KB that frees pay for one 16 KB output staging tile per epilogue group -- the output leaves through TMA
 //     stores (per-thread 128-byte rows written with plain stores were tried: the LSU needs 32 line transactions per
@@ -1227,9 +1227,10 @@ __global__ void __launch_bounds__(kPThreads, 1) conv_tcb_kernel(const __grid_con
   uint64_t* norm_full = tmem_free + 2;        // [1]
   uint64_t* norm_free = norm_full + 1;        // [1]  both groups have read the norm region
   uint64_t* ys_full = norm_free + 1;          // [kMaxYs]  TMA arrival of a [y | scale] pair
-  uint64_t* ys_empty = ys_full + kMaxYs;      // [kMaxYs]  the normalisation MMAs that read the slot have completed
-  uint64_t* a2_ready = ys_empty + kMaxYs;     // [kMaxYs]  128 epilogue threads have written the operand
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(a2_ready + kMaxYs);
+  uint64_t* ys_empty = ys_full + kMaxYs;      // [kMaxYs]  the 128 threads of the consuming group hold the pair in registers
+  uint64_t* a2_ready = ys_empty + kMaxYs;     // [2]  per group: 128 threads have written the normalisation operand
+  uint64_t* a2_free = a2_ready + 2;           // [2]  per group: the MMAs that read the operand have completed
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(a2_free + 2);
   float* sbias = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(wfull) + kBarBlock);
 
   if (threadIdx.x == 0) {
@@ -1240,7 +1241,8 @@ __global__ void __launch_bounds__(kPThreads, 1) conv_tcb_kernel(const __grid_con
       mbar_init(&g_full[b], 1); mbar_init(&g_empty[b], 1);
     }
     mbar_init(norm_full, 1); mbar_init(norm_free, 2);
-    for (int k = 0; k < R; ++k) { mbar_init(&ys_full[k], 1); mbar_init(&ys_empty[k], 1); mbar_init(&a2_ready[k], 128); }
+    for (int k = 0; k < R; ++k) { mbar_init(&ys_full[k], 1); mbar_init(&ys_empty[k], 128); }
+    for (int g = 0; g < 2; ++g) { mbar_init(&a2_ready[g], 128); mbar_init(&a2_free[g], 1); }
     mbar_fence_init();
   }
   if (warp == 1) { tmem_alloc(tmem_ptr, 512); tmem_relinquish(); }
@@ -1429,28 +1431,29 @@ __global__ void __launch_bounds__(kPThreads, 1) conv_tcb_kernel(const __grid_con
       const uint32_t idesc = umma_idesc_tf32(kTileM, p.n_ch);
       const uint32_t hi_dense = (1024u >> 4) | (1u << 14) | (2u << 29);
       const uint32_t g_lo0 = ((smem_u32(gring) >> 4) & 0x3FFFu) | (1u << 16);
-      const uint32_t y_lo0 = ((smem_u32(ysr) >> 4) & 0x3FFFu) | (1u << 16);
+      const uint32_t o_lo0 = ((smem_u32(ostage) >> 4) & 0x3FFFu) | (1u << 16);
       const uint32_t w_step = b_bytes >> 4;
       const uint32_t dn = tmem + 256;
-      int ys = 0, gs = 0;
-      uint32_t y_par = 0, g_par = 0, nf_par = 1;
+      int gs = 0;
+      uint32_t g_par = 0, nf_par = 1, a2_par = 0;   // a2_par: bit g = parity of group g's next operand hand-off
       for (int item = blockIdx.x; item < total; item += gridDim.x) {
         mbar_wait(norm_free, nf_par);            // both groups have read the previous item's norm region
         nf_par ^= 1;
         for (int q = 0; q < nC; ++q) {
-          const uint64_t ad = (static_cast<uint64_t>(hi_dense) << 32) | (y_lo0 + ys * ((2 * kABytes) >> 4));
+          const int g = q & 1;                   // the stream alternates the two groups' chunks
+          const uint64_t ad = (static_cast<uint64_t>(hi_dense) << 32) | (o_lo0 + g * (kABytes >> 4));
           const uint64_t bd = (static_cast<uint64_t>(hi_dense) << 32) | (g_lo0 + gs * w_step);
           mbar_wait(&g_full[gs], g_par);
-          mbar_wait(&a2_ready[ys], y_par);
+          mbar_wait(&a2_ready[g], (a2_par >> g) & 1u);
+          a2_par ^= 1u << g;
           tc_fence_after_sync();
           tc_mma_tf32(dn, ad, bd, idesc, q > 0 ? 1u : 0u);
           tc_mma_tf32(dn, ad + 2, bd + 2, idesc, 1u);
           tc_mma_tf32(dn, ad + 4, bd + 4, idesc, 1u);
           tc_mma_tf32(dn, ad + 6, bd + 6, idesc, 1u);
-          tc_commit(&ys_empty[ys]);
+          tc_commit(&a2_free[g]);
           tc_commit(&g_empty[gs]);
           if (q == nC - 1) tc_commit(norm_full);
-          if (++ys == R) { ys = 0; y_par ^= 1; }
           if (++gs == 2) { gs = 0; g_par ^= 1; }
         }
       }
@@ -1465,7 +1468,7 @@ __global__ void __launch_bounds__(kPThreads, 1) conv_tcb_kernel(const __grid_con
     const uint32_t bar_id = 1 + grp;
     uint8_t* obuf = ostage + grp * kABytes;
     constexpr float sign = (EPI == ICADV_EPI_GDN_BWD) ? -1.f : 1.f;
-    uint32_t acc_bits = 0, nfull_par = 0;
+    uint32_t acc_bits = 0, nfull_par = 0, a2f_par = 1;   // a2_free: first use free
     int b = 0;
     uint32_t seq0 = 0;                         // stream position of this item's first chunk
     const uint32_t r_log2 = R == 4 ? 2u : 1u;
@@ -1484,6 +1487,10 @@ __global__ void __launch_bounds__(kPThreads, 1) conv_tcb_kernel(const __grid_con
       acc_bits ^= 1u << b;
       tc_fence_after_sync();
       const long long e1 = eprof ? clock64() : 0;
+      // the staging tile doubles as the operand buffer of pass 1: the last TMA store of the previous item must have read it
+      if (leader) tma_store_wait_read0();
+      __syncwarp();
+      named_bar_sync(bar_id, 128);
       // ---- pass 1: this group's chunks, in stream order
       for (int j = 0; j < half; ++j) {
         const int c = grp * half + j;
@@ -1506,7 +1513,21 @@ __global__ void __launch_bounds__(kPThreads, 1) conv_tcb_kernel(const __grid_con
         else mbar_wait(&ys_full[slot], par);
         read_row32(bufY, row, yv);
         read_row32(bufS, row, sv);
-        // operand of the normalisation GEMM, written in place over this thread's own y row (16 bytes at a time)
+        {
+          // The pair is in registers: hand the slot back to the producer NOW, so that the next pair of the stream is in
+          // flight while this one is being processed.  Every shared-memory load above must have RETURNED before the
+          // arrival (the slot is overwritten through the async proxy): one word of each 16-byte load feeds the address
+          // of the arrive instruction, so the scoreboard holds it until the data is here.
+          uint32_t dep = 0;
+#pragma unroll
+          for (int k4 = 0; k4 < 8; ++k4) dep |= __float_as_uint(yv[4 * k4]) | __float_as_uint(sv[4 * k4]);
+          fence_proxy_async_smem();
+          asm volatile("{\n.reg .b32 t;\nand.b32 t, %1, 0;\nadd.u32 t, t, %0;\nmbarrier.arrive.shared::cta.b64 _, [t];\n}"
+                       ::"r"(smem_u32(&ys_empty[slot])), "r"(dep) : "memory");
+        }
+        mbar_wait(&a2_free[grp], a2f_par);          // the MMAs that read this group's previous operand are done
+        a2f_par ^= 1;
+        // operand of the normalisation GEMM -> this group's staging tile (16 bytes at a time)
 #pragma unroll
         for (int k4 = 0; k4 < 8; ++k4) {
           float a2[4];
@@ -1522,7 +1543,7 @@ __global__ void __launch_bounds__(kPThreads, 1) conv_tcb_kernel(const __grid_con
               a2[e] = s2 > 0.f ? round_tf32(fast_div(v[k] * yv[k], s2)) : 0.f;
             }
           }
-          *reinterpret_cast<float4*>(bufY + sw128_off(row, k4)) = make_float4(a2[0], a2[1], a2[2], a2[3]);
+          *reinterpret_cast<float4*>(obuf + sw128_off(row, k4)) = make_float4(a2[0], a2[1], a2[2], a2[3]);
         }
         fence_proxy_async_smem();
         // the products pass 2 needs: g * sc over the accumulator chunk, y / sc in the stash
@@ -1535,7 +1556,7 @@ __global__ void __launch_bounds__(kPThreads, 1) conv_tcb_kernel(const __grid_con
         tmem_st32(t_acc + c * 32, v);
         tmem_st32(t_stash + c * 32, yv);
         tmem_st_wait();
-        mbar_arrive(&a2_ready[slot]);
+        mbar_arrive(&a2_ready[grp]);
       }
       // ---- pass 2: out = g sc -+ (y / sc) (gamma^T t), from TMEM only
       const long long e2 = eprof ? clock64() : 0;
@@ -1793,11 +1814,15 @@ static int build_persistent(const icadv_conv_desc* d, int mode, const Geometry& 
   const int N = c2i ? 96 : d->n_ch, K = d->k_ch, s = d->stride;   // col2im: Z has 25 * n_ch <= 96 columns
   if (N > 256 || (gdn && N > 128)) return 0;            // 2 TMEM buffers x [acc N | norm N] must fit 512 columns
   const bool tconv2 = !c2i && d->form == ICADV_FORM_TCONV && s == 2;
-  // ICADV_TC_STREAM_BWD: 0 = never, unset / 1 = every GDN / IGDN backward epilogue the streaming kernel takes
+  // ICADV_TC_STREAM_BWD: 0 = never; unset / 1 = where it measured faster on B200 (profiles/r2_stream_bwd_ab.txt): the
+  // HBM-bound backward epilogues -- the RGB first-layer form (g_s.6 input gradient + IGDN backward: 2.84 -> 2.3 ms at 64
+  // images) and stride-2 transposed convs (g_a.2 / g_a.4 input gradients + GDN backward: 3.29 -> 2.9 ms); 2 = every
+  // GDN / IGDN backward epilogue it takes (stride-2 convs with their long main loops stay faster on the two-CTA kernel)
   const char* senv = getenv("ICADV_TC_STREAM_BWD");
   const int stream_level = senv != nullptr ? atoi(senv) : 1;
   const bool stream = bwd && stream_level > 0 && N <= 128 && (N / 32) % 2 == 0 &&
-                      (mode == kModeGeneric || mode == kModeRgbIn);
+                      (mode == kModeGeneric || mode == kModeRgbIn) &&
+                      (stream_level >= 2 || mode == kModeRgbIn || tconv2);
   if (level == 1 && !stream && !(tconv2 || (!gdn && mode == kModeGeneric) || c2i || (mode == kModeRgbIn && !bwd))) return 0;
   TcpParams& p = plan->pp;
   memset(&p, 0, sizeof(p));
