@@ -1487,10 +1487,7 @@ __global__ void __launch_bounds__(kPThreads, 1) conv_tcb_kernel(const __grid_con
       acc_bits ^= 1u << b;
       tc_fence_after_sync();
       const long long e1 = eprof ? clock64() : 0;
-      // the staging tile doubles as the operand buffer of pass 1: the last TMA store of the previous item must have read it
-      if (leader) tma_store_wait_read0();
-      __syncwarp();
-      named_bar_sync(bar_id, 128);
+      long long e_drain = 0;
       // ---- pass 1: this group's chunks, in stream order
       for (int j = 0; j < half; ++j) {
         const int c = grp * half + j;
@@ -1527,6 +1524,15 @@ __global__ void __launch_bounds__(kPThreads, 1) conv_tcb_kernel(const __grid_con
         }
         mbar_wait(&a2_free[grp], a2f_par);          // the MMAs that read this group's previous operand are done
         a2f_par ^= 1;
+        if (j == 0) {
+          // the staging tile doubles as the operand buffer: the last TMA store of the previous item must have read it
+          // (waited for here, after this chunk's loads and hand-back, so the drain overlaps them)
+          const long long t0 = eprof ? clock64() : 0;
+          if (leader) tma_store_wait_read0();
+          __syncwarp();
+          named_bar_sync(bar_id, 128);
+          if (eprof) e_drain = clock64() - t0;
+        }
         // operand of the normalisation GEMM -> this group's staging tile (16 bytes at a time)
 #pragma unroll
         for (int k4 = 0; k4 < 8; ++k4) {
@@ -1597,6 +1603,7 @@ __global__ void __launch_bounds__(kPThreads, 1) conv_tcb_kernel(const __grid_con
         const long long e4 = clock64();
         q[9 + grp * 3] += e1 - e0; q[10 + grp * 3] += e3 - e1; q[11 + grp * 3] += e4 - e3;
         q[5 + grp] += e_ys;
+        if (grp == 0) q[15] += e_drain;
         if (grp == 0) q[3] += e3 - e2;
       }
     }

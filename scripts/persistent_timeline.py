@@ -40,7 +40,8 @@ def run(name, d, keep):
     for g in range(2):
         print(f"   epilogue group {g}: wait acc {med[9 + 3 * g]:8.1f}  pass1(+norm wait) {med[10 + 3 * g]:8.1f}  pass2 {med[11 + 3 * g]:8.1f} us")
     print(f"   group 0 waiting for the last normalisation MMA: {med[3]:.1f} us;  blocked on the saved-tensor ring (streaming "
-          f"backward kernel): group 0 {med[5]:.1f} us, group 1 {med[6]:.1f} us")
+          f"backward kernel): group 0 {med[5]:.1f} us, group 1 {med[6]:.1f} us; store drain before the first operand write: "
+          f"group 0 {med[15]:.1f} us")
 
 
 # g_s.4: deconv 128->128 + IGDN forward at 128x192 -> 256x384
