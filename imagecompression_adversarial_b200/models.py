@@ -580,6 +580,28 @@ class ScaleHyperprior(CompressionModel):
             return {"x_hat": self.g_s(y_hat), "likelihoods": {"y": y_lik, "z": z_lik}}
 
 
+class MeanScaleHyperprior(ScaleHyperprior):
+    """compressai MeanScaleHyperprior (mbt2018_mean): the base class of the reference's ``debug`` model
+    (anchors/model.py:9-35), whose own forward (:22-35) is what runs there; this forward is CompressAI's."""
+
+    def __init__(self, N, M, **kwargs):
+        super().__init__(N, M)
+        self.h_a = nn.Sequential(conv(M, N, 3, 1), LeakyReLU(), conv(N, N), LeakyReLU(), conv(N, N))
+        self.h_s = nn.Sequential(deconv(N, M), LeakyReLU(), deconv(M, M * 3 // 2), LeakyReLU(),
+                                 conv(M * 3 // 2, M * 2, 3, 1))
+
+    def forward(self, x):
+        with _param_grads_on(self.training):
+            y = self.g_a(x)
+            z = self.h_a(y)
+            z_hat, z_lik = self.entropy_bottleneck(z)
+            gp = self.h_s(z_hat)
+            half = gp.shape[1] // 2
+            scales_hat, means_hat = Fn.NarrowFn.apply(gp, 0, half), Fn.NarrowFn.apply(gp, half, half)
+            y_hat, y_lik = self.gaussian_conditional(y, scales_hat, means=means_hat)
+            return {"x_hat": self.g_s(y_hat), "likelihoods": {"y": y_lik, "z": z_lik}}
+
+
 class JointAutoregressiveHierarchicalPriors(CompressionModel):
     """compressai mbt2018 (widths pinned by InvCompress/ours.py:22-32); forward of anchors/model.py:96-108."""
 

@@ -124,3 +124,18 @@ def test_reference_update_registered_buffers_works_on_the_operator_surface():
     wrapper.net = net
     res = wrapper.load_state_dict(zoo, strict=True)
     assert not res.missing_keys and not res.unexpected_keys
+
+
+def test_image_folder_stand_in(tmp_path):
+    """compressai.datasets.ImageFolder as train.py:114-123 constructs it (root / split / files, transform)."""
+    import numpy as np
+    from PIL import Image
+    from imagecompression_adversarial_b200.shims.compressai.datasets import ImageFolder
+    (tmp_path / "train").mkdir()
+    for i in range(3):
+        Image.fromarray((np.random.RandomState(i).rand(20, 24, 3) * 255).astype("uint8")).save(tmp_path / "train" / f"{i}.png")
+    (tmp_path / "train" / "notes.txt").write_text("not an image")
+    ds = ImageFolder(str(tmp_path), split="train", transform=lambda im: np.asarray(im).shape)
+    assert len(ds) == 3 and ds[1] == (20, 24, 3)
+    with pytest.raises(RuntimeError):
+        ImageFolder(str(tmp_path), split="test")

@@ -488,3 +488,85 @@ def test_recompression_matches_oracle(dev):
         assert abs(p[1] - o[1]) <= max(1e-3, bpp_tol * o[1]), (rounds, p[1], o[1])   # bpp
         assert abs(p[2] - o[2]) < psnr_tol, (rounds, p[2], o[2])                     # PSNR, dB
         assert abs(p[3] - o[3]) < msim_tol, (rounds, p[3], o[3])                     # MS-SSIM
+
+
+def test_quantize_modes_match_oracle(dev):
+    """compressai ``quantize(x, mode, means)`` (call site anchors/model.py:102): noise / dequantize / symbols, with and
+    without means; symbols are the int32 latent indices (bit-exact)."""
+    from imagecompression_adversarial_b200 import models as pm
+    from oracle import layers as ol
+    g = torch.Generator(device=dev).manual_seed(9)
+    y = torch.randn(2, 192, 8, 12, device=dev, generator=g) * 4
+    mu = torch.randn(2, 192, 8, 12, device=dev, generator=g)
+    nz = torch.rand(2, 192, 8, 12, device=dev, generator=g) - 0.5
+    pg = pm.GaussianConditional().to(dev)
+    for means in (None, mu):
+        for mode in ("dequantize", "symbols"):
+            want = ol.quantize(y, mode, means)
+            got = pg.quantize(y, mode, means)
+            assert got.dtype == want.dtype and torch.equal(got, want), (mode, means is None)
+    pg.noise_override = nz
+    assert torch.equal(pg.quantize(y, "noise"), ol.quantize(y, "noise", noise=nz))
+    # train-mode quantiser is differentiable with an identity gradient (compressai: inputs + noise)
+    yr = y.clone().requires_grad_(True)
+    out = pg.quantize(yr, "noise")
+    out.backward(torch.ones_like(out) * 2.0)
+    assert torch.equal(yr.grad, torch.full_like(y, 2.0))
+
+
+def test_compressai_format_checkpoint_file_loads_and_runs(dev, tmp_path):
+    """SURVEY 8(f) rank 1 on the GPU: a checkpoint FILE in the layout train.py:443-454 writes and coder.py:104-116 reads
+    ({"epoch", "step", "state_dict", "optimizer", ...}) with every key a CompressAI state_dict carries -- parameters, the
+    entropy-coder tables, the constant 1-element buffers (pedestal / bound) -- loads strictly and the loaded model
+    reproduces the oracle's eval forward."""
+    from imagecompression_adversarial_b200 import models as pm
+    from oracle import models as om
+    onet = om.init_model("hyper", 3, seed=4).to(dev)
+    sd = {k: v.detach().cpu().clone() for k, v in onet.state_dict().items()}
+    C = sd["entropy_bottleneck.quantiles"].shape[0]
+    sd["entropy_bottleneck._quantized_cdf"] = torch.arange(C * 37, dtype=torch.int32).reshape(C, 37)
+    sd["entropy_bottleneck._offset"] = torch.full((C,), -17, dtype=torch.int32)
+    sd["entropy_bottleneck._cdf_length"] = torch.full((C,), 37, dtype=torch.int32)
+    sd["gaussian_conditional._quantized_cdf"] = torch.arange(64 * 99, dtype=torch.int32).reshape(64, 99)
+    sd["gaussian_conditional._offset"] = torch.full((64,), -48, dtype=torch.int32)
+    sd["gaussian_conditional._cdf_length"] = torch.full((64,), 99, dtype=torch.int32)
+    sd["gaussian_conditional.scale_table"] = torch.exp(torch.linspace(-2.2, 5.5, 64))
+    ped = (2.0 ** -18) ** 2
+    for k in list(sd):
+        if k.endswith(".beta"):
+            base = k[:-5]
+            for rep, minimum in (("beta_reparam", 1e-6), ("gamma_reparam", 0.0)):
+                sd[f"{base}.{rep}.pedestal"] = torch.tensor([ped])
+                sd[f"{base}.{rep}.lower_bound.bound"] = torch.tensor([(minimum + ped) ** 0.5])
+    sd["entropy_bottleneck.likelihood_lower_bound.bound"] = torch.tensor([1e-9])
+    sd["gaussian_conditional.likelihood_lower_bound.bound"] = torch.tensor([1e-9])
+    sd["gaussian_conditional.lower_bound_scale.bound"] = torch.tensor([0.11])
+    path = tmp_path / "checkpoint_best_loss.pth.tar"
+    torch.save({"epoch": 7, "step": 1234, "state_dict": sd, "optimizer": {}, "aux_optimizer": {}, "lr_scheduler": {}}, path)
+    ck = torch.load(path, map_location=dev, weights_only=False)                     # coder.py:104-105
+    pnet = pm.init_model("hyper", 3, "mse", pretrained=False).to(dev)
+    res = pnet.load_state_dict(ck["state_dict"], strict=True)                       # coder.py:107
+    assert not res.missing_keys and not res.unexpected_keys
+    assert tuple(pnet.gaussian_conditional.scale_table.shape) == (64,)
+    x = images(1, 128, 192, dev)
+    onet.eval(); pnet.eval()
+    with torch.no_grad():
+        o, p = onet(x), pnet(x)
+    assert abs(psnr(p["x_hat"], x) - psnr(o["x_hat"], x)) < 0.05
+    bo = sum(float(torch.log(l).sum()) for l in o["likelihoods"].values())
+    bp = sum(float(torch.log(l).sum()) for l in p["likelihoods"].values())
+    assert abs(bo - bp) < 2e-3 * abs(bo)
+
+
+def test_mean_scale_hyperprior_runs(dev):
+    """The base class of the reference's ``debug`` model (anchors/model.py:9-35): forward, likelihood ranges, gradients."""
+    from imagecompression_adversarial_b200 import models as pm
+    torch.manual_seed(0)
+    net = pm.MeanScaleHyperprior(128, 192).to(dev).train()
+    x = torch.rand(2, 3, 64, 64, device=dev, requires_grad=True)
+    out = net(x)
+    assert out["x_hat"].shape == x.shape and set(out["likelihoods"]) == {"y", "z"}
+    for l in out["likelihoods"].values():
+        assert float(l.min()) >= 1e-9 and float(l.max()) <= 1.0 + 1e-6
+    (out["x_hat"].mean() + sum(torch.log(l).mean() for l in out["likelihoods"].values())).backward()
+    assert bool(torch.isfinite(x.grad).all()) and float(x.grad.abs().max()) > 0
