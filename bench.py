@@ -312,7 +312,7 @@ def launch_table(eng, pk, tf32_burst):
 def build_attack(cfg, net, n_local, x, dev, steps_for_sched):
     """(engine, args namespace, output_s) for the attack configs."""
     from imagecompression_adversarial_b200 import attack as patk
-    from imagecompression_adversarial_b200.engine import AttackEngine, GenericAttackEngine, RoiSpec
+    from imagecompression_adversarial_b200.engine import AttackEngine, RoiSpec, TapeAttackEngine
     a = argparse.Namespace(model=cfg["model"], quality=cfg["quality"], metric="mse", steps=steps_for_sched, random=1,
                            noise=1e-4, lr_attack=0.01, att_metric=cfg["att_metric"], epsilon=16.0, clamp=True, adv=False,
                            force_branch=1, mask_loc=None, lamb_bkg_in=1.0, lamb_bkg_out=1.0, lamb_tar=1.0)
@@ -324,7 +324,7 @@ def build_attack(cfg, net, n_local, x, dev, steps_for_sched):
         roi = RoiSpec(a.mask_loc, a.lamb_bkg_in, a.lamb_bkg_out, a.lamb_tar)
         output_t, _ = patk.clean_pass(torch.roll(x, 1, 0) if x.shape[0] > 1 else torch.flip(x, (3,)), net, a)
     net.train()
-    cls = AttackEngine if patk._fused_stacks(net) else GenericAttackEngine
+    cls = AttackEngine if patk._fused_stacks(net) else TapeAttackEngine
     eng = cls(net, n_local, cfg["H"], cfg["W"], steps=cfg["sched_steps"], force_branch=1, att_metric=cfg["att_metric"], roi=roi)
     eng.load(x, output_s, None, output_t)
     return eng, a, output_s, output_t

@@ -14,7 +14,7 @@ from . import metrics
 from . import _lib as L
 from . import ops
 from . import precision
-from .engine import AttackEngine, GenericAttackEngine, IfgsmEngine, RoiSpec
+from .engine import AttackEngine, GenericAttackEngine, IfgsmEngine, RoiSpec, TapeAttackEngine
 from .program import parse_stack
 
 _ENGINES = {}
@@ -60,7 +60,9 @@ def _engine_for(net, im_s, args, roi=None):
            bool(args.clamp), args.att_metric, force, roi.key() if roi is not None else None, precision.get())
     eng = _ENGINES.get(key)
     if eng is None:
-        cls = AttackEngine if _fused_stacks(net) else GenericAttackEngine
+        # plain conv/GDN stacks: fused launch programs; anything else: traced into a static launch program (speed mode) or
+        # walked module by module through autograd (parity mode: every contraction K-sliced and split, precision.py)
+        cls = AttackEngine if _fused_stacks(net) else (GenericAttackEngine if precision.split() else TapeAttackEngine)
         eng = cls(net, n, h, w, steps=args.steps, epsilon=args.epsilon, noise_budget=args.noise,
                   lr_attack=args.lr_attack, clamp=args.clamp, att_metric=args.att_metric, force_branch=force, roi=roi)
         _ENGINES.clear()  # one live engine: its buffers are sized for the batch

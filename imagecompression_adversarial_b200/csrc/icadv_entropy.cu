@@ -170,6 +170,7 @@ __global__ void unary_kernel(const float* __restrict__ x, const float* __restric
       case 3: r = rintf(v); break;
       case 5: r = round_tf32(v); break;
       case 6: r = fminf(fmaxf(v, 0.f), 1.f); break;
+      case 7: r = v; break;
       default: r = v + b[i]; break;
     }
     y[i] = r;
@@ -238,7 +239,7 @@ int icadv_gc_forward(const float* y, const float* scales, const float* means, co
 }
 
 int icadv_unary(const float* x, const float* b, float* y, int64_t n, int op, icadv_stream_t stream) {
-  ICADV_REQUIRE(x && y && op >= 0 && op <= 6 && (op != 4 || b), "bad unary args");
+  ICADV_REQUIRE(x && y && op >= 0 && op <= 7 && (op != 4 || b), "bad unary args");
   int64_t blocks = (n + 255) / 256;
   if (blocks > 148 * 16) blocks = 148 * 16;
   if (blocks < 1) blocks = 1;

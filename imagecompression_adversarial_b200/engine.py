@@ -333,6 +333,30 @@ class GenericAttackEngine(AttackEngine):
         return Fn.to_nhwc(x_in.grad).contiguous()
 
 
+class TapeAttackEngine(AttackEngine):
+    """The same device-resident loop for codecs whose ``g_a`` / ``g_s`` are not plain conv/GDN stacks (cheng2020_anchor:
+    residual blocks, sub-pixel convolutions; BASELINE config 4): the two stacks are traced once into static launch
+    programs (``tape.TapeProgram``: pre-allocated buffers, cached TMA plans, activations fused into contraction
+    epilogues), so the iteration is the same stream-ordered launch sequence as AttackEngine's and replays from one CUDA
+    graph -- no autograd walk, no per-call plan creation."""
+
+    def _build_network(self, net, n_img, height, width, dev, act, nact):
+        from .tape import TapeProgram
+        f = lambda *s: torch.zeros(*s, device=dev, dtype=torch.float32)
+        with torch.no_grad():
+            probe = torch.zeros(1, 3, height, width, device=dev).contiguous(memory_format=torch.channels_last)
+            lat = net.g_a(probe)
+        lat_c, lat_h, lat_w = lat.shape[1], lat.shape[2], lat.shape[3]
+        del probe, lat
+        self.g_lat = f(n_img, lat_h, lat_w, lat_c)
+        self.ga = TapeProgram(net.g_a, n_img, height, width, dev, x_in=self.im_in, g_out=self.g_lat, active=act,
+                              n_active=nact, name="g_a")
+        self.gs = TapeProgram(net.g_s, n_img, lat_h, lat_w, dev, x_in=self.ga.out, g_in=self.g_lat, active=act,
+                              n_active=nact, name="g_s")
+        self.x_out, self.g_x = self.gs.out, self.gs.g_out
+        assert self.x_out.shape == self.im_s.shape, (self.x_out.shape, self.im_s.shape)
+
+
 class CwEngine(AttackEngine):
     """One step of the C&W-style search of attack_cw.py (:111-140, 149-166): every iteration runs the network,
     loss = loss_i + c (1 - MSE_o) with a per-image weight c (zeroed on device once the image's reconstruction error exceeds

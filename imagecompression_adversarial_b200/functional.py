@@ -14,6 +14,7 @@ from . import ops
 from . import precision
 
 _PACK_CACHE = {}
+_REC = None   # tape.Recorder while a stack is being traced into a static launch program (tape.py)
 
 
 def invalidate_pack_cache():
@@ -92,6 +93,9 @@ class Contraction(torch.autograd.Function):
                        stride=stride, n_ch=n_ch, act=act)
         ctx.save_for_backward(xn, weight, out if act != L.ACT_NONE else None)
         ctx.cfg = (ksize, stride, transposed, act, param_grads, bias is not None)
+        if _REC is not None:
+            _REC.note("conv", [xn], out, weight=weight, bias=bias, ksize=ksize, stride=stride, transposed=transposed,
+                      act=act, n_ch=n_ch)
         return to_nchw(out)
 
     @staticmethod
@@ -133,6 +137,8 @@ class GdnFn(torch.autograd.Function):
                              beta=beta_eff.contiguous(), acc_from_in=True, path="tc")
         ctx.save_for_backward(y, sc, gamma_eff)
         ctx.inverse = inverse
+        if _REC is not None:
+            _REC.note("gdn", [xn], y, module=_REC.current_gdn, inverse=inverse)
         return to_nchw(y)
 
     @staticmethod
@@ -187,6 +193,8 @@ class ActFn(torch.autograd.Function):
         y = ops.unary(xc, {L.ACT_ABS: 0, L.ACT_RELU: 1, L.ACT_LEAKY: 2}[act])
         ctx.save_for_backward(xc)
         ctx.act = act
+        if _REC is not None and xc.dim() == 4:
+            _REC.note("act", [to_nhwc(xc)], to_nhwc(y), act=act)
         return y
 
     @staticmethod
@@ -203,7 +211,10 @@ class AddFn(torch.autograd.Function):
     def forward(ctx, a, b):
         ac = a.contiguous(memory_format=torch.channels_last)
         bc = b.contiguous(memory_format=torch.channels_last)
-        return ops.unary(ac, 4, bc)
+        y = ops.unary(ac, 4, bc)
+        if _REC is not None:
+            _REC.note("add", [to_nhwc(ac), to_nhwc(bc)], to_nhwc(y))
+        return y
 
     @staticmethod
     def backward(ctx, g):
@@ -216,7 +227,11 @@ class PixelShuffleFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, r):
         ctx.r = r
-        return to_nchw(ops.pixel_shuffle(to_nhwc(x).contiguous(), r))
+        xn = to_nhwc(x).contiguous()
+        y = ops.pixel_shuffle(xn, r)
+        if _REC is not None:
+            _REC.note("shuffle", [xn], y, r=r)
+        return to_nchw(y)
 
     @staticmethod
     def backward(ctx, g):

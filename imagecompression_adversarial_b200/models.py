@@ -194,6 +194,8 @@ class GDN(nn.Module):
             return Fn.GdnTrainFn.apply(x, self.beta, self.gamma, self.inverse, self.beta_reparam.bound,
                                        self.beta_reparam.pedestal, self.gamma_reparam.bound, self.gamma_reparam.pedestal)
         be, ga, _ = self.effective_parameters(round_tf32=not precision.split())
+        if Fn._REC is not None:
+            Fn._REC.current_gdn = self          # a trace records which module owns this normalisation (tape.py)
         return Fn.GdnFn.apply(x, be, ga, self.inverse)
 
 

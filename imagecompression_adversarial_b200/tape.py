@@ -1,0 +1,327 @@
+"""Static launch programs for codecs whose ``g_a`` / ``g_s`` are not plain conv/GDN stacks (cheng2020_anchor: residual
+blocks, sub-pixel convolutions, skip connections; anchors/model.py:77).
+
+The module graph is TRACED once (one forward through the operator surface with a recorder in ``functional``), then
+compiled into two launch lists -- forward, and backward to the input -- over pre-allocated buffers with cached TMA
+plans.  What the trace buys over walking the modules through autograd every iteration (the previous
+``GenericAttackEngine``): no per-call plan creation / destruction, no autograd bookkeeping or allocation, the whole
+attack iteration is capturable in ONE CUDA graph, and three peephole fusions:
+
+  * LeakyReLU / ReLU following a contraction (directly, or behind a PixelShuffle: an activation commutes with a
+    permutation) runs in that contraction's epilogue;
+  * an activation that feeds only tensor-path contractions is rounded to TF32 where it is produced (``round_out``) instead
+    of by a separate rounding pass in front of every contraction;
+  * the gradient of a tensor with several consumers (block input: first conv + skip) is summed by one add launch.
+
+Weight gradients are not produced (the attack never reads them: attack_rd.py:546-548).  Reference semantics:
+``x_ = net.g_s(net.g_a(im_in))`` and autograd to ``im_in`` (attack_rd.py:344-349,547).
+"""
+import torch
+
+from . import _lib as L
+from . import functional as Fn
+from . import ops
+from .ops import _p, _stream
+from .program import FnLaunch
+
+_UN = {L.ACT_ABS: 0, L.ACT_RELU: 1, L.ACT_LEAKY: 2}
+
+
+class Recorder:
+    """Receives one ``note()`` per operator-surface call while a trace is active (``functional._REC``).  Tensors are
+    identified by the allocation behind them (channels-last buffers; NCHW views of one buffer share its id)."""
+
+    def __init__(self):
+        self.nodes, self.keep, self.ids = [], [], {}
+        self.current_gdn = None
+
+    def tid(self, t_nhwc):
+        key = (t_nhwc.data_ptr(), tuple(t_nhwc.shape))
+        if key not in self.ids:
+            self.ids[key] = len(self.ids)
+            self.keep.append(t_nhwc)     # keep the allocation alive so data_ptr stays unique for the whole trace
+        return self.ids[key]
+
+    def note(self, kind, inputs, output, **attrs):
+        """``inputs`` / ``output``: channels-last [N,H,W,C] tensors (views are fine)."""
+        self.nodes.append({"kind": kind, "in": [self.tid(t) for t in inputs], "out": self.tid(output),
+                           "shape": tuple(output.shape), **attrs})
+
+
+def trace(stack, x_nchw):
+    """Run ``stack(x)`` once under the recorder; returns (nodes, id of the input buffer, id of the output buffer)."""
+    rec = Recorder()
+    x = x_nchw.contiguous(memory_format=torch.channels_last)
+    in_id = rec.tid(Fn.to_nhwc(x))
+    Fn._REC = rec
+    try:
+        with torch.no_grad():
+            out = stack(x)
+    finally:
+        Fn._REC = None
+    return rec.nodes, in_id, rec.tid(Fn.to_nhwc(out))
+
+
+def _unary(x, b, y, op):
+    L.call("icadv_unary", _p(x), _p(b), _p(y), x.numel(), int(op), _stream())
+
+
+def _act_bwd(x, g, gx, act):
+    L.call("icadv_act_backward", _p(x), _p(g), _p(gx), x.numel(), _UN[act], _stream())
+
+
+def _shuffle(src, dst, n, lo_h, lo_w, c_out, r, inverse):
+    L.call("icadv_pixel_shuffle", _p(src), _p(dst), n, lo_h, lo_w, c_out, r, 1 if inverse else 0, _stream())
+
+
+class TapeProgram:
+    """Forward + input-gradient launch lists of one traced stack; same interface as ``program.StackProgram``."""
+
+    def __init__(self, stack, n_img, in_h, in_w, device, *, x_in=None, g_out=None, g_in=None, active=None, n_active=None,
+                 name="stack"):
+        self.name, self.n_img, self.device = name, n_img, device
+        self.active, self.n_active = active, n_active
+        f = lambda *shape: torch.empty(*shape, device=device, dtype=torch.float32)
+        cin = self._first_in_channels(stack)
+        self.x_in = x_in if x_in is not None else f(n_img, in_h, in_w, cin)
+        probe = torch.zeros(n_img, cin, in_h, in_w, device=device).contiguous(memory_format=torch.channels_last)
+        nodes, in_id, out_id = trace(stack, probe)
+        del probe
+        self.nodes, alias = self._fuse_activations(nodes)
+        out_id = alias.get(out_id, out_id)
+        # ---- buffers: one per node output; the input buffer is the caller's
+        self.buf = {in_id: self.x_in}
+        for nd in self.nodes:
+            self.buf[nd["out"]] = f(*nd["shape"])
+        self.out = self.buf[out_id]
+        self.consumers = {}
+        for i, nd in enumerate(self.nodes):
+            for t in nd["in"]:
+                self.consumers.setdefault(t, []).append(i)
+        self.producer = {nd["out"]: i for i, nd in enumerate(self.nodes)}
+        self._keep = []
+        self.fwd, self.bwd = [], []
+        self.fwd_info, self.bwd_info = [], []
+        self._weights = []           # (module weight, kind, packed buffer) for refresh_parameters
+        self._gdn = []               # (gdn module, beta buffer, gamma buffer, gammaT buffer)
+        self._build_forward(in_id)
+        self.g_out = g_out if g_out is not None else torch.empty_like(self.out)
+        assert self.g_out.shape == self.out.shape
+        self.g_in = g_in if g_in is not None else torch.empty_like(self.x_in)
+        self._build_backward(in_id, out_id)
+
+    @staticmethod
+    def _first_in_channels(stack):
+        for m in stack.modules():
+            if hasattr(m, "in_channels"):
+                return int(m.in_channels)
+        raise L.IcadvError("tape program: no contraction in the stack")
+
+    # ------------------------------------------------------------------ peephole: activations into epilogues
+    @staticmethod
+    def _fuse_activations(nodes):
+        """conv -> act and conv -> shuffle -> act (each link the only consumer) become conv(act) [-> shuffle]."""
+        uses = {}
+        for nd in nodes:
+            for t in nd["in"]:
+                uses[t] = uses.get(t, 0) + 1
+        prod = {nd["out"]: nd for nd in nodes}
+        drop, alias = set(), {}
+        for nd in nodes:
+            if nd["kind"] != "act":
+                continue
+            src = prod.get(nd["in"][0])
+            via = None
+            if src is not None and src["kind"] == "shuffle" and uses[src["out"]] == 1:
+                via, src = src, prod.get(src["in"][0])
+            if src is None or src["kind"] != "conv" or src["act"] != L.ACT_NONE or uses[src["out"]] != 1:
+                continue
+            src["act"] = nd["act"]
+            drop.add(id(nd))
+            alias[nd["out"]] = via["out"] if via is not None else src["out"]
+        out = []
+        for nd in nodes:
+            if id(nd) in drop:
+                continue
+            nd["in"] = [alias.get(t, t) for t in nd["in"]]
+            out.append(nd)
+        return out, alias
+
+    # ------------------------------------------------------------------ helpers
+    def _tc(self, k_ch, n_ch):
+        return Fn.tc_shape(k_ch, n_ch)
+
+    def _plan(self, x, w, bias, out, **kw):
+        d = ops.make_desc(x, w, bias, out, active=self.active, n_active=self.n_active, **kw)
+        keep = (x, w, bias, out) + tuple(v for v in kw.values() if torch.is_tensor(v))
+        import ctypes as C
+        if L.lib().icadv_conv_tc_supported(C.byref(d)) == 1:
+            return ops.ConvPlan(d, keep)
+        if kw.get("epi", L.EPI_LINEAR) != L.EPI_LINEAR or kw.get("acc_from_in"):
+            raise L.IcadvError("tape program: normalisation on a shape the tensor path does not take")
+        return ops.SimtLaunch(d, keep)
+
+    def _rounded_source(self, lst, src, rounded_cache):
+        """Buffer holding ``src`` rounded to TF32 for a tensor-path consumer: ``src`` itself when its producer rounds on
+        store, else one rounding launch into a scratch copy (shared by all consumers)."""
+        if src in self._round_at_producer:
+            return self.buf[src]
+        if src not in rounded_cache:
+            r = torch.empty_like(self.buf[src])
+            lst.append(FnLaunch(_unary, self.buf[src], None, r, 5))
+            rounded_cache[src] = r
+        return rounded_cache[src]
+
+    def _pack(self, weight, kind, tc):
+        w = ops.pack_weight(weight, kind, round_tf32=tc)
+        self._weights.append((weight, kind, tc, w))
+        return w
+
+    def refresh_parameters(self):
+        """Re-pack weights / re-parametrise GDN in place after a codec update (plans bake the pointers in)."""
+        for weight, kind, tc, w in self._weights:
+            w.copy_(ops.pack_weight(weight, kind, round_tf32=tc))
+        for nd in self.nodes:
+            if nd["kind"] == "conv" and nd.get("bias_buf") is not None:
+                nd["bias_buf"].copy_(nd["bias"].detach())
+        for gdn, be, ga, gaT in self._gdn:
+            b2, g2, gT2 = gdn.effective_parameters(round_tf32=True)
+            be.copy_(b2); ga.copy_(g2); gaT.copy_(gT2)
+
+    # ------------------------------------------------------------------ forward
+    def _build_forward(self, in_id):
+        # a tensor is rounded where it is produced iff its producer is a contraction / GDN launch and EVERY consumer is a
+        # tensor-path contraction
+        self._round_at_producer = set()
+        for t, cons in self.consumers.items():
+            pi = self.producer.get(t)
+            if pi is None or self.nodes[pi]["kind"] not in ("conv", "gdn"):
+                continue
+            if all(self.nodes[c]["kind"] == "conv" and self._tc(self.buf[t].shape[-1], self.nodes[c]["n_ch"]) for c in cons):
+                self._round_at_producer.add(t)
+        # (a shuffle is a permutation: rounding its source conv covers its consumers)
+        for nd in self.nodes:
+            if nd["kind"] == "shuffle":
+                t = nd["out"]
+                cons = self.consumers.get(t, [])
+                src = nd["in"][0]
+                if cons and self.producer.get(src) is not None and self.nodes[self.producer[src]]["kind"] == "conv" and \
+                        len(self.consumers.get(src, [])) == 1 and \
+                        all(self.nodes[c]["kind"] == "conv" and self._tc(self.buf[t].shape[-1], self.nodes[c]["n_ch"]) for c in cons):
+                    self._round_at_producer.add(src)
+                    self._round_at_producer.add(t)
+        rounded = {}
+        for nd in self.nodes:
+            out = self.buf[nd["out"]]
+            if nd["kind"] == "conv":
+                src = nd["in"][0]
+                k_ch, n_ch = self.buf[src].shape[-1], nd["n_ch"]
+                tc = self._tc(k_ch, n_ch)
+                x = self._rounded_source(self.fwd, src, rounded) if tc else self.buf[src]
+                w = self._pack(nd["weight"], L.PACK_CONVT_FWD if nd["transposed"] else L.PACK_CONV_FWD, tc)
+                bias = nd["bias"].detach().contiguous().clone() if nd["bias"] is not None else None
+                nd["bias_buf"] = bias
+                self.fwd.append(self._plan(x, w, bias, out, form=L.FORM_TCONV if nd["transposed"] else L.FORM_SCONV,
+                                           ksize=nd["ksize"], stride=nd["stride"], n_ch=n_ch, act=nd["act"],
+                                           round_out=nd["out"] in self._round_at_producer))
+            elif nd["kind"] == "gdn":
+                g = nd["module"]
+                be, ga, gaT = g.effective_parameters(round_tf32=True)
+                self._gdn.append((g, be, ga, gaT))
+                nd["gaT"] = gaT
+                nd["sc"] = torch.empty_like(out)
+                c = out.shape[-1]
+                self.fwd.append(self._plan(self.buf[nd["in"][0]], None, None, out, form=L.FORM_SCONV, ksize=1, stride=1,
+                                           n_ch=c, epi=L.EPI_IGDN_FWD if g.inverse else L.EPI_GDN_FWD, gmat=ga, beta=be,
+                                           out_scale=nd["sc"], acc_from_in=True,
+                                           round_out=nd["out"] in self._round_at_producer))
+            elif nd["kind"] == "act":
+                self.fwd.append(FnLaunch(_unary, self.buf[nd["in"][0]], None, out, _UN[nd["act"]]))
+            elif nd["kind"] == "add":
+                self.fwd.append(FnLaunch(_unary, self.buf[nd["in"][0]], self.buf[nd["in"][1]], out, 4))
+            elif nd["kind"] == "shuffle":
+                n, h, w, c = self.buf[nd["in"][0]].shape
+                r = nd["r"]
+                self.fwd.append(FnLaunch(_shuffle, self.buf[nd["in"][0]], out, n, h, w, c // (r * r), r, False))
+            else:
+                raise L.IcadvError(f"tape program: unsupported operator '{nd['kind']}'")
+
+    # ------------------------------------------------------------------ backward (to the input)
+    def _build_backward(self, in_id, out_id):
+        contrib = {out_id: [self.g_out]}            # gradient contributions per tensor, one per consumer
+
+        def grad_of(t):
+            """One buffer holding dL/dt: the contributions of several consumers are summed by add launches."""
+            parts = contrib.get(t)
+            if not parts:
+                raise L.IcadvError("tape program: a tensor of the stack has no path to the output")
+            acc = parts[0]
+            for extra in parts[1:]:
+                dst = torch.empty_like(acc)
+                self.bwd.append(FnLaunch(_unary, acc, extra, dst, 4))
+                acc = dst
+            return acc
+
+        single_input_use = len(self.consumers.get(in_id, [])) == 1
+        for nd in reversed(self.nodes):
+            g = grad_of(nd["out"])
+            src = nd["in"][0]
+            if nd["kind"] == "conv":
+                k_ch = self.buf[src].shape[-1]
+                if nd["act"] != L.ACT_NONE:         # activation fused into the forward epilogue: its gradient from the output
+                    gz = torch.empty_like(g)
+                    self.bwd.append(FnLaunch(_act_bwd, self.buf[nd["out"]], g, gz, nd["act"]))
+                    g = gz
+                tc = self._tc(g.shape[-1], k_ch)
+                if tc:
+                    gr = torch.empty_like(g)
+                    self.bwd.append(FnLaunch(_unary, g, None, gr, 5))
+                    g = gr
+                w = self._pack(nd["weight"], L.PACK_CONVT_DGRAD if nd["transposed"] else L.PACK_CONV_DGRAD, tc)
+                if not nd["transposed"] and nd["ksize"] < nd["stride"]:
+                    # input gradient of a strided 1x1 conv: the pixels no tap reaches are never written and stay zero
+                    dst = torch.zeros_like(self.buf[src])
+                elif src == in_id and single_input_use:
+                    dst = self.g_in
+                else:
+                    dst = torch.empty_like(self.buf[src])
+                self.bwd.append(self._plan(g, w, None, dst, form=L.FORM_SCONV if nd["transposed"] else L.FORM_TCONV,
+                                           ksize=nd["ksize"], stride=nd["stride"], n_ch=k_ch))
+                contrib.setdefault(src, []).append(dst)
+            elif nd["kind"] == "gdn":
+                dst = torch.empty_like(self.buf[src])
+                gm = nd["module"]
+                self.bwd.append(self._plan(g, None, None, dst, form=L.FORM_SCONV, ksize=1, stride=1, n_ch=dst.shape[-1],
+                                           epi=L.EPI_IGDN_BWD if gm.inverse else L.EPI_GDN_BWD, gmat=nd["gaT"],
+                                           y_prev=self.buf[nd["out"]], sc_prev=nd["sc"], acc_from_in=True))
+                contrib.setdefault(src, []).append(dst)
+            elif nd["kind"] == "act":
+                dst = torch.empty_like(g)
+                self.bwd.append(FnLaunch(_act_bwd, self.buf[src], g, dst, nd["act"]))
+                contrib.setdefault(src, []).append(dst)
+            elif nd["kind"] == "add":
+                for t in nd["in"]:
+                    contrib.setdefault(t, []).append(g)
+            elif nd["kind"] == "shuffle":
+                n, h, w, c = self.buf[src].shape
+                r = nd["r"]
+                dst = torch.empty_like(self.buf[src])
+                self.bwd.append(FnLaunch(_shuffle, g, dst, n, h, w, c // (r * r), r, True))
+                contrib.setdefault(src, []).append(dst)
+        gin = grad_of(in_id)
+        if gin is not self.g_in:
+            self.bwd.append(FnLaunch(_unary, gin, None, self.g_in, 7))      # op 7: copy
+
+    # ------------------------------------------------------------------ run
+    def forward(self):
+        for p in self.fwd:
+            p.launch()
+        return self.out
+
+    def backward(self):
+        for p in self.bwd:
+            p.launch()
+        return self.g_in
+
+    def n_kernels(self):
+        return sum(p.kernels for p in self.fwd), sum(p.kernels for p in self.bwd)

@@ -371,9 +371,10 @@ def test_roi_targeted_attack_matches_oracle(dev):
 
 
 def test_generic_engine_cheng2020_matches_oracle(dev):
-    """cheng2020_anchor (residual blocks, sub-pixel convs) through the module-by-module engine vs the oracle loop."""
+    """cheng2020_anchor (residual blocks, sub-pixel convs) through the traced static launch program (CUDA graph) vs the
+    oracle loop."""
     from imagecompression_adversarial_b200 import attack as patk
-    from imagecompression_adversarial_b200.engine import GenericAttackEngine
+    from imagecompression_adversarial_b200.engine import TapeAttackEngine as GenericAttackEngine
     from oracle import attack as oatk
     onet, pnet = pair("cheng2020", 1, dev)
     x = images(1, 192, 192, dev)   # > 160: the final eval computes MS-SSIM (pytorch_msssim asserts on smaller images)
@@ -570,3 +571,44 @@ def test_mean_scale_hyperprior_runs(dev):
         assert float(l.min()) >= 1e-9 and float(l.max()) <= 1.0 + 1e-6
     (out["x_hat"].mean() + sum(torch.log(l).mean() for l in out["likelihoods"].values())).backward()
     assert bool(torch.isfinite(x.grad).all()) and float(x.grad.abs().max()) > 0
+
+
+def test_traced_program_equals_module_walk(dev):
+    """cheng2020_anchor g_s(g_a(x)) and its input gradient: the traced static launch program (activations fused into
+    contraction epilogues, rounding at the producer, summed skip gradients) against the same modules walked through
+    autograd -- the same kernels in a different arrangement, so they agree to fp32 round-off; and the engine built on it
+    replays from a CUDA graph bit for bit."""
+    from imagecompression_adversarial_b200 import models as pm
+    from imagecompression_adversarial_b200.engine import TapeAttackEngine
+    from imagecompression_adversarial_b200.tape import TapeProgram
+    torch.manual_seed(0)
+    net = pm.init_model("cheng2020", 1, "mse", pretrained=False).to(dev).train()
+    n, h, w = 2, 64, 96
+    x = torch.rand(n, 3, h, w, device=dev)
+    xi = x.clone().requires_grad_(True)
+    y = net.g_a(xi)
+    out = net.g_s(y)
+    gout = torch.randn_like(out)
+    out.backward(gout)
+    ga = TapeProgram(net.g_a, n, h, w, dev)
+    gs = TapeProgram(net.g_s, n, y.shape[2], y.shape[3], dev, x_in=ga.out, g_in=ga.g_out)
+    ga.x_in.copy_(x.permute(0, 2, 3, 1))
+    ga.forward(); gs.forward()
+    gs.g_out.copy_(gout.permute(0, 2, 3, 1))
+    gs.backward(); ga.backward()
+    rel = lambda a, b: float((a - b).pow(2).sum().sqrt() / b.pow(2).sum().sqrt())
+    assert rel(ga.out.permute(0, 3, 1, 2), y.detach()) < 1e-5
+    assert rel(gs.out.permute(0, 3, 1, 2), out.detach()) < 1e-5
+    assert rel(ga.g_in.permute(0, 3, 1, 2), xi.grad) < 1e-5
+    # fewer launches than operators: every LeakyReLU of the blocks rides in a contraction epilogue
+    kinds = [nd["kind"] for nd in ga.nodes + gs.nodes]
+    assert "act" not in kinds, kinds
+    ref = torch.rand_like(x)
+    res = []
+    for use_graph in (False, True):
+        eng = TapeAttackEngine(net, n, h, w, steps=6, use_graph=use_graph, force_branch=1)
+        eng.load(x, ref)
+        eng.run(5)
+        torch.cuda.synchronize()
+        res.append(eng.noise.clone())
+    assert torch.equal(res[0], res[1])
