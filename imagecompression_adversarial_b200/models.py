@@ -501,13 +501,16 @@ class GaussianConditional(_ZooStateDict, nn.Module):
             return ops.unary(x, 4, nz)
         if means is not None:
             m = means.contiguous(memory_format=torch.channels_last)
-            out = ops.unary(ops.unary(x - m, 3), 4, m)
-        else:
-            out = ops.unary(x, 3)
+            r = ops.unary(x - m, 3)                      # round(x - mean): the integer symbols
+            if mode == "symbols":
+                return r.int()
+            assert mode == "dequantize", mode
+            return ops.unary(r, 4, m)
+        out = ops.unary(x, 3)
         if mode == "dequantize":
             return out
         assert mode == "symbols", mode
-        return (out - means if means is not None else out).int()
+        return out.int()
 
     def forward(self, inputs, scales, means=None, training=None):
         if training is None:

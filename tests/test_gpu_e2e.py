@@ -568,7 +568,7 @@ def test_mean_scale_hyperprior_runs(dev):
     out = net(x)
     assert out["x_hat"].shape == x.shape and set(out["likelihoods"]) == {"y", "z"}
     for l in out["likelihoods"].values():
-        assert float(l.min()) >= 1e-9 and float(l.max()) <= 1.0 + 1e-6
+        assert float(l.min()) >= 1e-9 * (1 - 1e-6) and float(l.max()) <= 1.0 + 1e-6     # bound held as float32
     (out["x_hat"].mean() + sum(torch.log(l).mean() for l in out["likelihoods"].values())).backward()
     assert bool(torch.isfinite(x.grad).all()) and float(x.grad.abs().max()) > 0
 
