@@ -221,9 +221,16 @@ class TapeProgram:
                 w = self._pack(nd["weight"], L.PACK_CONVT_FWD if nd["transposed"] else L.PACK_CONV_FWD, tc)
                 bias = nd["bias"].detach().contiguous().clone() if nd["bias"] is not None else None
                 nd["bias_buf"] = bias
-                self.fwd.append(self._plan(x, w, bias, out, form=L.FORM_TCONV if nd["transposed"] else L.FORM_SCONV,
-                                           ksize=nd["ksize"], stride=nd["stride"], n_ch=n_ch, act=nd["act"],
-                                           round_out=nd["out"] in self._round_at_producer))
+                plan = self._plan(x, w, bias, out, form=L.FORM_TCONV if nd["transposed"] else L.FORM_SCONV,
+                                  ksize=nd["ksize"], stride=nd["stride"], n_ch=n_ch, act=nd["act"],
+                                  round_out=nd["out"] in self._round_at_producer)
+                if not isinstance(plan, ops.ConvPlan):
+                    # the CUDA-core kernels do not round on store: consumers of this tensor get a rounding launch
+                    self._round_at_producer.discard(nd["out"])
+                    for c in self.consumers.get(nd["out"], []):
+                        if self.nodes[c]["kind"] == "shuffle":
+                            self._round_at_producer.discard(self.nodes[c]["out"])
+                self.fwd.append(plan)
             elif nd["kind"] == "gdn":
                 g = nd["module"]
                 be, ga, gaT = g.effective_parameters(round_tf32=True)
