@@ -2034,6 +2034,23 @@ int icadv_conv_plan_create(const icadv_conv_desc* d, icadv_conv_plan** out_plan)
   Geometry g;
   int rc = make_geometry(d, &g);
   if (rc) return rc;
+  if (d->form == ICADV_FORM_TCONV && !d->acc_from_in && g.n_launch > 1) {
+    // Output-parity classes no tap reaches (the input gradient of a strided 1x1 conv: 3 of its 4 classes) are dropped:
+    // their pixels are NOT written (the caller pre-fills them with the bias / zero, see icadv.h).  Left in, such a class
+    // would run an epilogue on an accumulator no MMA ever wrote.
+    int keep = 0;
+    for (int l = 0; l < g.n_launch; ++l) {
+      if (g.n_taps[l] == 0) continue;
+      if (keep != l) {
+        g.n_taps[keep] = g.n_taps[l]; g.out_a[keep] = g.out_a[l]; g.out_b[keep] = g.out_b[l];
+        for (int t = 0; t < g.n_taps[l]; ++t) g.taps[keep][t] = g.taps[l][t];
+      }
+      ++keep;
+    }
+    ICADV_REQUIRE(keep > 0, "conv_tc: no output class has a tap");
+    for (int l = keep; l < 4; ++l) g.n_taps[l] = 0;
+    g.n_launch = keep;
+  }
   int dev_rc = icadv_check_device();
   if (dev_rc) return dev_rc;
 

@@ -207,6 +207,7 @@ class ConvPlan:
 
     def __init__(self, desc, keep):
         self._keep = keep  # tensors whose pointers are baked into the tensor maps
+        self.desc = desc
         h = C.c_void_p()
         L.call("icadv_conv_plan_create", C.byref(desc), C.byref(h))
         self._h = h

@@ -109,6 +109,7 @@ class TapeProgram:
         assert self.g_out.shape == self.out.shape
         self.g_in = g_in if g_in is not None else torch.empty_like(self.x_in)
         self._build_backward(in_id, out_id)
+        self._describe()
 
     @staticmethod
     def _first_in_channels(stack):
@@ -318,6 +319,31 @@ class TapeProgram:
         gin = grad_of(in_id)
         if gin is not self.g_in:
             self.bwd.append(FnLaunch(_unary, gin, None, self.g_in, 7))      # op 7: copy
+
+    # ------------------------------------------------------------------ algorithmic work per launch (roofline tables)
+    def _describe(self):
+        """fwd_info / bwd_info for engine.launch_table(): every tensor a launch touches read or written once (fp32),
+        FLOPs = 2 x MACs of the contraction (GDN: the C x C normalisation GEMM)."""
+        def info(p, direction, k):
+            if isinstance(p, (ops.ConvPlan, ops.SimtLaunch)):
+                d = p._d if isinstance(p, ops.SimtLaunch) else p.desc
+                oh, ow = ops.out_hw(d.form, d.ksize, d.stride, d.in_h, d.in_w)
+                px = d.in_h * d.in_w if d.form == L.FORM_TCONV else oh * ow
+                if d.acc_from_in:
+                    macs, nbytes = d.n_img * oh * ow * d.n_ch * d.n_ch, 4.0 * d.n_img * oh * ow * d.n_ch * (3 if d.epi <= L.EPI_IGDN_FWD else 4)
+                    name = "(I)GDN " + ("fwd" if d.epi <= L.EPI_IGDN_FWD else "bwd")
+                else:
+                    macs = d.n_img * px * d.ksize * d.ksize * d.k_ch * d.n_ch
+                    nbytes = 4.0 * d.n_img * (d.in_h * d.in_w * d.k_ch + oh * ow * d.n_ch)
+                    name = f"{'deconv' if (d.form == L.FORM_TCONV) == (direction == 'fwd') else 'conv'} {d.ksize}x{d.ksize}/{d.stride} " \
+                           f"{d.k_ch}->{d.n_ch} {'' if direction == 'fwd' else 'dgrad'}"
+                bound = "tensor" if Fn.tc_shape(d.k_ch, d.n_ch) or d.acc_from_in else "hbm"
+                return {"name": f"{self.name}[{k}] {name}", "flops": 2.0 * macs, "bytes": nbytes, "bound": bound}
+            t = [a for a in p.args if torch.is_tensor(a)]
+            return {"name": f"{self.name}[{k}] elementwise ({p.fn.__name__.strip('_')})", "flops": 0.0,
+                    "bytes": 4.0 * sum(a.numel() for a in t), "bound": "hbm"}
+        self.fwd_info = [info(p, "fwd", k) for k, p in enumerate(self.fwd)]
+        self.bwd_info = [info(p, "bwd", k) for k, p in enumerate(self.bwd)]
 
     # ------------------------------------------------------------------ run
     def forward(self):

@@ -46,7 +46,8 @@ int icadv_check_device(void);
  *   ICADV_FORM_SCONV  out[n,oh,ow,:] = sum_taps in[n, s*oh+kh-p, s*ow+kw-p, :] * W[tap]
  *                     (Conv2d forward; ConvTranspose2d input-gradient)
  *   ICADV_FORM_TCONV  out[n, s*i+kh-p, s*j+kw-p, :] += in[n,i,j,:] * W[tap]      (output_padding s-1)
- *                     (ConvTranspose2d forward; Conv2d input-gradient)
+ *                     (ConvTranspose2d forward; Conv2d input-gradient).  Output pixels no tap reaches (k < s: the
+ *                     input gradient of a strided 1x1 conv) are NOT written: the caller pre-fills them (bias / zero).
  * W is pre-packed [k*k taps][n_ch][k_ch] fp32 (icadv_pack_weight).
  * ------------------------------------------------------------------------------------------ */
 #define ICADV_FORM_SCONV 0

@@ -110,6 +110,10 @@ TC_CASES = [
     (3, 192, 128, 5, 2, (16, 24), 1), (0, 128, 192, 5, 2, (32, 48), 1), (0, 128, 128, 5, 2, (20, 36), 1),
     (2, 128, 128, 5, 2, (5, 9), 2), (0, 128, 128, 3, 1, (12, 20), 1), (0, 64, 32, 1, 1, (8, 16), 1),
     (0, 192, 128, 3, 1, (9, 17), 1), (2, 128, 128, 5, 2, (16, 16), 3),
+    # strided 1x1 (the skip of compressai's ResidualBlockWithStride) and its input gradient, where 3 of the 4 output
+    # parity classes have no tap: those pixels are the caller's pre-fill (zero), not an epilogue on an unwritten accumulator
+    (0, 128, 128, 1, 2, (16, 24), 2), (1, 128, 128, 1, 2, (8, 12), 2), (1, 128, 128, 1, 2, (40, 56), 3),
+    (0, 128, 128, 3, 2, (16, 24), 1), (1, 128, 128, 3, 2, (8, 12), 2),
 ]
 
 
