@@ -370,7 +370,7 @@ def run_ours(args, cfg):
 
     pk, pk_kind = peaks()
     roof, table, tf32 = None, None, None
-    if rank == 0 and type(eng) is AttackEngine:
+    if rank == 0 and isinstance(eng, AttackEngine) and (eng.ga.fwd_info or type(eng) is AttackEngine):
         burst, sustained = measured_tf32_peak()
         tf32 = {"burst_tflops": round(burst, 1), "sustained_tflops": round(sustained, 1),
                 "how": "bare tcgen05.mma kind::tf32 128x256x8 loop, one CTA per SM (icadv_probe_tf32_peak): best single "
