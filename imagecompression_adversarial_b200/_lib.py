@@ -50,6 +50,8 @@ _SIGS = {
     "icadv_conv_tc_supported": (C.c_int, [C.POINTER(ConvDesc)]),
     "icadv_conv_simt": (C.c_int, [C.POINTER(ConvDesc), C.c_void_p]),
     "icadv_conv_wgrad": (C.c_int, [C.POINTER(ConvDesc), _fp, _fp, _fp, C.c_void_p]),
+    "icadv_conv_wgrad_ex": (C.c_int, [C.POINTER(ConvDesc), _fp, _fp, _fp, C.c_int, C.c_void_p]),
+    "icadv_conv_wgrad_tc_supported": (C.c_int, [C.POINTER(ConvDesc)]),
     "icadv_pack_weight": (C.c_int, [_fp, _fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "icadv_pack_weight_rgb": (C.c_int, [_fp, _fp, C.c_int, C.c_int, C.c_void_p]),
     "icadv_pad_rgb4": (C.c_int, [_fp, _fp, C.c_int, C.c_int, C.c_int, C.c_int, _fp, _fp, C.c_void_p]),

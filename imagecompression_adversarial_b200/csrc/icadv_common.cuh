@@ -55,4 +55,8 @@ struct Geometry {
 // Fills g from the descriptor; returns 0 or ICADV_EINVAL.
 int make_geometry(const icadv_conv_desc* d, Geometry* g);
 
+// tcgen05 weight gradient (icadv_wgrad_tc.cu): eligibility and launch; dwpack [taps][n_ch][k_ch] is overwritten
+int wgrad_tc_supported(const icadv_conv_desc* d);
+int wgrad_tc(const icadv_conv_desc* d, const Geometry& g, const float* gout, float* dwpack, cudaStream_t stream);
+
 }  // namespace icadv

@@ -304,8 +304,11 @@ int icadv_conv_simt(const icadv_conv_desc* d, icadv_stream_t stream) {
 // `d` describes the FORWARD contraction (in, geometry); gout has the shape of d->out.
 // dwpack: [taps][n_ch][k_ch] (overwritten), dbias: [n_ch] or NULL.  Workspace is allocated
 // stream-ordered (cudaMallocAsync) -- this entry point is not on the attack path.
-int icadv_conv_wgrad(const icadv_conv_desc* d, const float* gout, float* dwpack, float* dbias,
-                     icadv_stream_t stream) {
+// path: ICADV_WGRAD_AUTO = tcgen05 kernel where the shape is eligible (icadv_wgrad_tc.cu; operands read as TF32),
+// ICADV_WGRAD_SIMT = fp32 CUDA-core kernel (parity mode; shapes the tensor path does not take), ICADV_WGRAD_TC = tensor
+// path or an error.
+int icadv_conv_wgrad_ex(const icadv_conv_desc* d, const float* gout, float* dwpack, float* dbias, int path,
+                        icadv_stream_t stream) {
   ICADV_REQUIRE(d && d->in && gout && dwpack, "null pointer");
   ICADV_REQUIRE(d->active == nullptr, "wgrad does not take an image indirection");
   Geometry g;
@@ -313,6 +316,11 @@ int icadv_conv_wgrad(const icadv_conv_desc* d, const float* gout, float* dwpack,
   if (rc) return rc;
   cudaStream_t s = as_stream(stream);
   const int taps_total = d->ksize * d->ksize;
+  const bool tc = path == ICADV_WGRAD_TC || (path == ICADV_WGRAD_AUTO && wgrad_tc_supported(d));
+  if (tc) {
+    rc = wgrad_tc(d, g, gout, dwpack, s);
+    if (rc) return rc;
+  } else {
   ICADV_CUDA_TRY(cudaMemsetAsync(dwpack, 0, (size_t)taps_total * d->n_ch * d->k_ch * sizeof(float), s));
   for (int l = 0; l < g.n_launch; ++l) {
     SimtParams p;
@@ -335,6 +343,7 @@ int icadv_conv_wgrad(const icadv_conv_desc* d, const float* gout, float* dwpack,
     ICADV_CUDA_TRY(cudaGetLastError());
     ICADV_CUDA_TRY(cudaFreeAsync(partial, s));
   }
+  }
   if (dbias != nullptr) {
     const int64_t npx = (int64_t)d->n_img * g.out_h * g.out_w;
     float* partial = nullptr;
@@ -347,5 +356,12 @@ int icadv_conv_wgrad(const icadv_conv_desc* d, const float* gout, float* dwpack,
   }
   return ICADV_OK;
 }
+
+int icadv_conv_wgrad(const icadv_conv_desc* d, const float* gout, float* dwpack, float* dbias,
+                     icadv_stream_t stream) {
+  return icadv_conv_wgrad_ex(d, gout, dwpack, dbias, ICADV_WGRAD_AUTO, stream);
+}
+
+int icadv_conv_wgrad_tc_supported(const icadv_conv_desc* d) { return d != nullptr && wgrad_tc_supported(d) ? 1 : 0; }
 
 }  // extern "C"

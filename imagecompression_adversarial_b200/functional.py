@@ -63,11 +63,19 @@ def packed(weight, kind, split_geom=None):
     return wp
 
 
-def contract(xn, weight, kind, bias, *, form, ksize, stride, n_ch, act=L.ACT_NONE):
+def round_operand(xn, n_ch):
+    """The TF32 (round-to-nearest) copy of an activation that feeds tensor-path contractions in the speed mode; the
+    tensor itself where no rounding applies (parity mode, shapes on the CUDA-core kernels)."""
+    if precision.split() or not tc_shape(xn.shape[-1], n_ch):
+        return xn
+    return ops.unary(xn, 5)
+
+
+def contract(xn, weight, kind, bias, *, form, ksize, stride, n_ch, act=L.ACT_NONE, rounded=False):
     """One contraction of the module-by-module path on a channels-last activation, in the current precision mode:
-    speed mode -- operand rounded to TF32 (nearest), one launch; parity mode -- operand and weight in the K-sliced
-    three-term split form, one tensor-path launch per slice, partial outputs added in fp32.  Shapes the tensor path does
-    not take run on the fp32 CUDA-core kernels in both modes."""
+    speed mode -- operand rounded to TF32 (nearest; ``rounded`` = the caller already did), one launch; parity mode --
+    operand and weight in the K-sliced three-term split form, one tensor-path launch per slice, partial outputs added in
+    fp32.  Shapes the tensor path does not take run on the fp32 CUDA-core kernels in both modes."""
     k_ch = xn.shape[-1]
     if not tc_shape(k_ch, n_ch):
         return ops.conv(xn, packed(weight, kind), bias, form=form, ksize=ksize, stride=stride, n_ch=n_ch, act=act,
@@ -76,8 +84,8 @@ def contract(xn, weight, kind, bias, *, form, ksize, stride, n_ch, act=L.ACT_NON
         geom = ops.split_geom(k_ch, form, ksize, stride)
         return ops.conv_sliced(ops.split3(xn.contiguous(), *geom), packed(weight, kind, geom), bias, form=form,
                                ksize=ksize, stride=stride, n_ch=n_ch, act=act)
-    return ops.conv(ops.unary(xn, 5), packed(weight, kind), bias, form=form, ksize=ksize, stride=stride, n_ch=n_ch,
-                    act=act)
+    return ops.conv(xn if rounded else ops.unary(xn, 5), packed(weight, kind), bias, form=form, ksize=ksize,
+                    stride=stride, n_ch=n_ch, act=act)
 
 
 class Contraction(torch.autograd.Function):
@@ -89,9 +97,15 @@ class Contraction(torch.autograd.Function):
         kind = L.PACK_CONVT_FWD if transposed else L.PACK_CONV_FWD
         form = L.FORM_TCONV if transposed else L.FORM_SCONV
         n_ch = weight.shape[1] if transposed else weight.shape[0]
-        out = contract(xn, weight, kind, bias.detach() if bias is not None else None, form=form, ksize=ksize,
-                       stride=stride, n_ch=n_ch, act=act)
-        ctx.save_for_backward(xn, weight, out if act != L.ACT_NONE else None)
+        # speed mode: the operand is rounded to TF32 once; that copy feeds this contraction and, saved, the tensor-core
+        # weight gradient (both read their operands as TF32: rounding where produced keeps them unbiased)
+        xr = round_operand(xn, n_ch)
+        out = contract(xr, weight, kind, bias.detach() if bias is not None else None, form=form, ksize=ksize,
+                       stride=stride, n_ch=n_ch, act=act, rounded=True)
+        if param_grads and xr is xn and not precision.split() and \
+                ops.conv_wgrad_tc_supported(xn.shape[-1], n_ch, ksize, stride, form, xn.shape[1:3]):
+            xr = ops.unary(xn, 5)          # RGB end-layer forms: rounded copy for the weight gradient only
+        ctx.save_for_backward(xr if param_grads else xn, weight, out if act != L.ACT_NONE else None)
         ctx.cfg = (ksize, stride, transposed, act, param_grads, bias is not None)
         if _REC is not None:
             _REC.note("conv", [xn], out, weight=weight, bias=bias, ksize=ksize, stride=stride, transposed=transposed,
@@ -105,17 +119,26 @@ class Contraction(torch.autograd.Function):
         gn = to_nhwc(g)
         if act != L.ACT_NONE:
             gn = ops.act_backward(out, gn, act)
+        gn = gn.contiguous()
         gx = gw = gb = None
+        want_w = param_grads and (ctx.needs_input_grad[1] or (has_bias and ctx.needs_input_grad[2]))
+        gr = round_operand(gn, xn.shape[-1]) if (ctx.needs_input_grad[0] or want_w) else gn
         if ctx.needs_input_grad[0]:
             kind = L.PACK_CONVT_DGRAD if transposed else L.PACK_CONV_DGRAD
             form = L.FORM_SCONV if transposed else L.FORM_TCONV
-            gx = to_nchw(contract(gn.contiguous(), weight, kind, None, form=form, ksize=ksize, stride=stride,
-                                  n_ch=xn.shape[-1]))
-        if param_grads and (ctx.needs_input_grad[1] or (has_bias and ctx.needs_input_grad[2])):
+            gx = to_nchw(contract(gr, weight, kind, None, form=form, ksize=ksize, stride=stride, n_ch=xn.shape[-1],
+                                  rounded=True))
+        if want_w:
             form = L.FORM_TCONV if transposed else L.FORM_SCONV
             n_ch = weight.shape[1] if transposed else weight.shape[0]
-            dwp, db = ops.conv_wgrad(xn, gn.contiguous(), form=form, ksize=ksize, stride=stride, n_ch=n_ch,
-                                     want_bias=has_bias)
+            # K6: tcgen05 weight gradient on the TF32-rounded operands in the speed mode; fp32 CUDA-core kernel in the
+            # parity mode and for the 3-channel end layers
+            tc = not precision.split() and ops.conv_wgrad_tc_supported(xn.shape[-1], n_ch, ksize, stride, form,
+                                                                       xn.shape[1:3])
+            if tc and gr is gn:
+                gr = ops.unary(gn, 5)
+            dwp, db = ops.conv_wgrad(xn, gr if tc else gn, form=form, ksize=ksize, stride=stride, n_ch=n_ch,
+                                     want_bias=has_bias, path="tc" if tc else "simt")
             gw = ops.unpack_weight_grad(dwp, weight, L.PACK_CONVT_FWD if transposed else L.PACK_CONV_FWD)
             gb = db
         return gx, gw, gb, None, None, None, None, None

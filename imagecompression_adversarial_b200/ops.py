@@ -235,16 +235,29 @@ class SimtLaunch:
         L.call("icadv_conv_simt", C.byref(self._d), _stream())
 
 
-def conv_wgrad(x, gout, *, form, ksize, stride, n_ch, want_bias=True):
-    """dW (packed) and dbias of a contraction whose forward input was ``x`` and output gradient ``gout``."""
+_WGRAD_PATH = {"auto": 0, "simt": 1, "tc": 2}
+
+
+def conv_wgrad(x, gout, *, form, ksize, stride, n_ch, want_bias=True, path="auto"):
+    """dW (packed) and dbias of a contraction whose forward input was ``x`` and output gradient ``gout``.
+    ``path``: "tc" = tcgen05 kernel (pixel axis as the reduction axis; operands are read as TF32, so callers round them),
+    "simt" = fp32 CUDA-core kernel, "auto" = tensor path where the shape is eligible (channel counts multiples of 32)."""
     _chk(x, "x")
     _chk(gout, "gout")
     k_ch = x.shape[-1]
     dw = torch.empty(ksize * ksize, n_ch, k_ch, device=x.device, dtype=torch.float32)
     db = torch.empty(n_ch, device=x.device, dtype=torch.float32) if want_bias else None
     d = make_desc(x, dw, None, gout, form=form, ksize=ksize, stride=stride, n_ch=n_ch)
-    L.call("icadv_conv_wgrad", C.byref(d), _p(gout), _p(dw), _p(db), _stream())
+    L.call("icadv_conv_wgrad_ex", C.byref(d), _p(gout), _p(dw), _p(db), _WGRAD_PATH[path], _stream())
     return dw, db
+
+
+def conv_wgrad_tc_supported(k_ch, n_ch, ksize, stride, form=L.FORM_SCONV, in_hw=(2, 2)):
+    """Whether icadv_conv_wgrad takes the tcgen05 kernel for this contraction (channel counts multiples of 32, or one of
+    the two RGB end-layer forms: 3 -> N conv / N -> 3 transposed conv, 5x5 stride 2)."""
+    d = L.ConvDesc()
+    d.form, d.k_ch, d.n_ch, d.ksize, d.stride, d.in_h, d.in_w = form, k_ch, n_ch, ksize, stride, in_hw[0], in_hw[1]
+    return bool(L.lib().icadv_conv_wgrad_tc_supported(C.byref(d)))
 
 
 # ------------------------------------------------------------------ perturbation step

@@ -114,10 +114,21 @@ int icadv_conv_tc_supported(const icadv_conv_desc* d);             /* 1 / 0 */
  * Same descriptor; only ICADV_EPI_LINEAR. */
 int icadv_conv_simt(const icadv_conv_desc* d, icadv_stream_t stream);
 
-/* weight gradient of a contraction (train.py:359 only; the attack never reads parameter grads):
- * dW[tap][n][k] = sum_px gout[px,n] * in[tap-shifted px,k]; deterministic split reduction. */
+/* weight gradient of a contraction (train.py:357-359 `out_criterion["loss"].backward()` -- Conv2d / ConvTranspose2d
+ * .weight.grad; the attack never reads parameter grads):
+ * dW[tap][n][k] = sum_px gout[px,n] * in[tap-shifted px,k]; `d` describes the forward contraction (d->in = its input),
+ * gout has the shape of its output; dwpack [taps][n_ch][k_ch] is overwritten; deterministic (fixed-order split reduction).
+ * Two kernels: tcgen05 kind::tf32 with the pixel axis as the reduction axis (both operands MN-major straight from the
+ * channels-last tensors; k_ch % 32 == 0 and n_ch % 32 == 0; operands are read as TF32, round them where produced) and an
+ * fp32 CUDA-core kernel for every other shape and for the parity mode. */
+#define ICADV_WGRAD_AUTO 0
+#define ICADV_WGRAD_SIMT 1
+#define ICADV_WGRAD_TC 2
 int icadv_conv_wgrad(const icadv_conv_desc* d, const float* gout, float* dwpack, float* dbias,
-                     icadv_stream_t stream);
+                     icadv_stream_t stream); /* = _ex with ICADV_WGRAD_AUTO */
+int icadv_conv_wgrad_ex(const icadv_conv_desc* d, const float* gout, float* dwpack, float* dbias, int path,
+                        icadv_stream_t stream);
+int icadv_conv_wgrad_tc_supported(const icadv_conv_desc* d); /* 1 / 0 */
 
 /* torch layouts -> packed [taps][n_ch][k_ch].  kind: 0 Conv2d.weight [Co,Ci,k,k] for its forward,
  * 1 Conv2d.weight for its input-gradient, 2 ConvTranspose2d.weight [Ci,Co,k,k] for its forward,

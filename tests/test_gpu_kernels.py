@@ -292,6 +292,50 @@ def test_conv_wgrad_matches_autograd(dev, kind, cin, cout, k, s, hw):
     assert rel_err(db, gb_ref) < 5e-5
 
 
+# K6: the tcgen05 weight gradient (pixel axis as the reduction axis, MN-major operands).  Operands are pre-rounded to
+# TF32 so the comparison against fp32 autograd isolates the kernel (what remains is the tensor core's fp32 accumulate).
+@pytest.mark.parametrize("kind,cin,cout,k,s,hw,n", [
+    (0, 128, 128, 5, 2, (32, 48), 2),     # g_a.2
+    (2, 128, 128, 5, 2, (16, 24), 2),     # g_s.2
+    (0, 128, 192, 5, 2, (16, 16), 3),     # g_a.6: second M block is half empty
+    (2, 192, 128, 5, 2, (8, 8), 3),       # g_s.0: 192-column accumulators, two taps per CTA
+    (0, 192, 128, 3, 1, (16, 16), 2),     # h_a.0
+    (0, 128, 192, 3, 1, (13, 21), 1),     # ragged tiles
+    (0, 64, 32, 1, 1, (9, 9), 2),
+    (0, 64, 64, 3, 2, (17, 12), 2),       # cheng2020 strided 3x3
+    (0, 64, 96, 1, 2, (16, 16), 2),       # cheng2020 strided 1x1 skip
+    (0, 192, 384, 5, 1, (8, 12), 1),      # context model (5x5 stride 1), three M blocks
+    (0, 320, 192, 5, 2, (8, 8), 1),       # two column blocks (256 + 64)
+    (2, 32, 320, 5, 2, (4, 4), 1),
+    (0, 128, 128, 5, 2, (128, 128), 8),   # config-5 size: many tiles per split
+    (0, 3, 128, 5, 2, (64, 96), 2),       # g_a.0: RGB form (overlapping 128-byte windows of the padded RGB0 image)
+    (2, 128, 3, 5, 2, (32, 48), 2),       # g_s.6: RGB form
+    (0, 3, 192, 5, 2, (20, 12), 1),       # RGB form, two M blocks, ragged tiles
+    (2, 192, 3, 5, 2, (5, 7), 3),
+])
+def test_conv_wgrad_tensor_core_matches_autograd(dev, kind, cin, cout, k, s, hw, n):
+    from imagecompression_adversarial_b200 import _lib as L
+    from imagecompression_adversarial_b200 import ops
+    g = torch.Generator(device=dev).manual_seed(900 + kind + cin)
+    w, xc = make_w(kind, cin, cout, k, dev, g)
+    w.requires_grad_(True)
+    x = ops.unary(torch.randn(n, xc, *hw, device=dev, generator=g), 5)
+    out = ref_contraction(kind, x, w, None, k, s)
+    gout = ops.unary(torch.randn_like(out), 5)
+    (gw_ref,) = torch.autograd.grad(out, (w,), gout)
+    form = L.FORM_SCONV if kind == 0 else L.FORM_TCONV
+    assert ops.conv_wgrad_tc_supported(cin, cout, k, s, form, hw)
+    res = {}
+    for path in ("tc", "simt"):
+        dwp, _ = ops.conv_wgrad(nhwc(x), nhwc(gout), form=form, ksize=k, stride=s, n_ch=cout, want_bias=False, path=path)
+        res[path] = ops.unpack_weight_grad(dwp, w, kind)
+    assert rel_err(res["simt"], gw_ref) < 5e-5
+    assert rel_err(res["tc"], gw_ref) < 2e-4, rel_err(res["tc"], gw_ref)
+    # deterministic: the split reduction has a fixed order
+    dwp2, _ = ops.conv_wgrad(nhwc(x), nhwc(gout), form=form, ksize=k, stride=s, n_ch=cout, want_bias=False, path="tc")
+    assert torch.equal(ops.unpack_weight_grad(dwp2, w, kind), res["tc"])
+
+
 def test_bounds_match_oracle(dev):
     from imagecompression_adversarial_b200 import ops
     from oracle import layers as ol
