@@ -15,6 +15,7 @@ import torch
 import torch.nn as nn
 
 from . import _lib as L
+from . import entropy_coding as ec
 from . import functional as Fn
 from . import ops
 from . import precision
@@ -454,6 +455,65 @@ class EntropyBottleneck(_ZooStateDict, nn.Module):
                 v = v + torch.tanh(fa) * torch.tanh(v)
         return torch.abs(v - self.target).sum()
 
+    # ---- entropy coding (compressai EntropyBottleneck.update / compress / decompress)
+    lanes = ec.DEFAULT_LANES          # independent rANS streams per image (1 = compressai's single stream)
+
+    def _logits_cumulative_host(self, v):
+        for i in range(5):
+            m = getattr(self, f"_matrix{i}").detach().float().cpu()
+            b = getattr(self, f"_bias{i}").detach().float().cpu()
+            v = torch.matmul(torch.nn.functional.softplus(m), v) + b
+            if i < 4:
+                fa = getattr(self, f"_factor{i}").detach().float().cpu()
+                v = v + torch.tanh(fa) * torch.tanh(v)
+        return v
+
+    def update(self, force=False):
+        """Builds ``_quantized_cdf`` / ``_cdf_length`` / ``_offset`` from the learned density (host, parameter-sized)."""
+        if self._offset.numel() > 0 and not force:
+            return False
+        dev = self.quantiles.device
+        q = self.quantiles.detach().float().cpu()
+        medians = q[:, 0, 1]
+        minima = torch.ceil(medians - q[:, 0, 0]).int().clamp(min=0)
+        maxima = torch.ceil(q[:, 0, 2] - medians).int().clamp(min=0)
+        pmf_start = medians - minima
+        pmf_length = maxima + minima + 1
+        max_length = int(pmf_length.max())
+        samples = torch.arange(max_length)[None, :] + pmf_start[:, None, None]
+        lower = self._logits_cumulative_host(samples - 0.5)
+        upper = self._logits_cumulative_host(samples + 0.5)
+        sign = -torch.sign(lower + upper)
+        pmf = torch.abs(torch.sigmoid(sign * upper) - torch.sigmoid(sign * lower))[:, 0, :]
+        tail_mass = torch.sigmoid(lower[:, 0, :1]) + torch.sigmoid(-upper[:, 0, -1:])
+        self._quantized_cdf = ec.pmf_to_cdf(pmf, tail_mass, pmf_length, max_length).to(dev)
+        self._cdf_length = (pmf_length + 2).int().to(dev)
+        self._offset = (-minima).int().to(dev)
+        return True
+
+    def _coder_tables(self):
+        if self._offset.numel() == 0:
+            raise L.IcadvError("Uninitialized CDFs. Run update() first")
+        return ec.CoderTables(self._quantized_cdf, self._cdf_length, self._offset, self.quantiles.device)
+
+    def _channel_indexes(self, n, h, w):
+        c = self.channels
+        return torch.arange(c, device=self.quantiles.device, dtype=torch.int32).expand(n, h, w, c).contiguous()
+
+    def compress(self, x):
+        """-> one byte string per image (symbol order (c, h, w) as compressai's)."""
+        xn = Fn.to_nhwc(x.detach()).contiguous()
+        med = self.quantiles.detach()[:, 0, 1]
+        sym = ops.unary(xn - med, 3).int()
+        return ec.rans_encode(sym, self._channel_indexes(*xn.shape[:3]), self._coder_tables(), mode=0, lanes=self.lanes)
+
+    def decompress(self, strings, size):
+        n, (h, w) = len(strings), size
+        idx = self._channel_indexes(n, h, w)
+        med = self.quantiles.detach()[:, 0, 1].expand(n, h, w, self.channels).contiguous()
+        out = ec.rans_decode(strings, idx, self._coder_tables(), means=med, mode=0, lanes=self.lanes)
+        return Fn.to_nchw(out)
+
     def forward(self, x, training=None):
         if training is None:
             training = self.training
@@ -487,6 +547,53 @@ class GaussianConditional(_ZooStateDict, nn.Module):
                              else torch.zeros(0))
         self.noise_override = None
         self.last_bits = None
+
+    # ---- entropy coding (compressai GaussianConditional.update_scale_table / update / build_indexes / compress /
+    #      decompress)
+    lanes = ec.DEFAULT_LANES
+    tail_mass = 1e-9
+
+    def update_scale_table(self, scale_table, force=False):
+        if self._offset.numel() > 0 and not force:
+            return False
+        dev = self._offset.device
+        self.scale_table = torch.tensor(sorted(float(v) for v in scale_table), device=dev)
+        self.update()
+        return True
+
+    def update(self):
+        from scipy.stats import norm
+        dev = self._offset.device
+        st = self.scale_table.detach().float().cpu()
+        multiplier = -norm.ppf(self.tail_mass / 2)
+        pmf_center = torch.ceil(st * multiplier).int()
+        pmf_length = 2 * pmf_center + 1
+        max_length = int(pmf_length.max())
+        samples = torch.abs(torch.arange(max_length).int() - pmf_center[:, None]).float()
+        sc = st[:, None]
+        cum = lambda t: 0.5 * torch.erfc(-(2 ** -0.5) * t)
+        upper, lower = cum((0.5 - samples) / sc), cum((-0.5 - samples) / sc)
+        self._quantized_cdf = ec.pmf_to_cdf(upper - lower, 2 * lower[:, :1], pmf_length, max_length).to(dev)
+        self._cdf_length = (pmf_length + 2).int().to(dev)
+        self._offset = (-pmf_center).int().to(dev)
+
+    def _coder_tables(self):
+        if self._offset.numel() == 0:
+            raise L.IcadvError("Uninitialized CDFs. Run update() first")
+        return ec.CoderTables(self._quantized_cdf, self._cdf_length, self._offset, self._offset.device)
+
+    def build_indexes(self, scales):
+        return ec.build_indexes(scales.detach(), self.scale_table, self.scale_bound)
+
+    def compress(self, inputs, indexes, means=None):
+        sym = Fn.to_nhwc(self.quantize(inputs.detach(), "symbols", means)).contiguous()
+        return ec.rans_encode(sym, Fn.to_nhwc(indexes).contiguous(), self._coder_tables(), mode=0, lanes=self.lanes)
+
+    def decompress(self, strings, indexes, dtype=torch.float, means=None):
+        m = Fn.to_nhwc(means.detach()).contiguous() if means is not None else None
+        out = ec.rans_decode(strings, Fn.to_nhwc(indexes).contiguous(), self._coder_tables(), means=m, mode=0,
+                             lanes=self.lanes)
+        return Fn.to_nchw(out)
 
     def quantize(self, inputs, mode, means=None):
         """compressai ``quantize`` (call site anchors/model.py:102)."""
@@ -543,6 +650,18 @@ class CompressionModel(nn.Module):
     def to(self, *args, **kwargs):
         return super().to(*args, **kwargs)
 
+    def update(self, scale_table=None, force=False):
+        """compressai ``CompressionModel.update`` (+ the scale table of the conditional model where there is one):
+        builds the entropy coder's CDF tables; call before ``compress`` / ``decompress`` (InvCompress/train.py:452)."""
+        updated = False
+        gc = getattr(self, "gaussian_conditional", None)
+        if gc is not None:
+            updated |= gc.update_scale_table(ec.get_scale_table() if scale_table is None else scale_table, force=force)
+        for m in self.modules():
+            if isinstance(m, EntropyBottleneck):
+                updated |= m.update(force=force)
+        return updated
+
 
 def _g_a(N, M):
     return CodecStack(conv(3, N), GDN(N), conv(N, N), GDN(N), conv(N, N), GDN(N), conv(N, M))
@@ -566,6 +685,19 @@ class FactorizedPrior(CompressionModel):
             return {"x_hat": self.g_s(y_hat), "likelihoods": {"y": y_lik}}
 
 
+    @torch.no_grad()
+    def compress(self, x):
+        """compressai FactorizedPrior.compress."""
+        y = self.g_a(x)
+        return {"strings": [self.entropy_bottleneck.compress(y)], "shape": y.size()[-2:]}
+
+    @torch.no_grad()
+    def decompress(self, strings, shape):
+        assert isinstance(strings, list) and len(strings) == 1
+        y_hat = self.entropy_bottleneck.decompress(strings[0], shape)
+        return {"x_hat": self.g_s(y_hat).clamp_(0, 1)}
+
+
 class ScaleHyperprior(CompressionModel):
     def __init__(self, N, M):
         super().__init__(N)
@@ -583,6 +715,26 @@ class ScaleHyperprior(CompressionModel):
             scales_hat = self.h_s(z_hat)
             y_hat, y_lik = self.gaussian_conditional(y, scales_hat)
             return {"x_hat": self.g_s(y_hat), "likelihoods": {"y": y_lik, "z": z_lik}}
+
+
+    @torch.no_grad()
+    def compress(self, x):
+        """compressai ScaleHyperprior.compress: z string, then y coded with the scale indexes h_s(z_hat) gives."""
+        y = self.g_a(x)
+        z = self.h_a(Fn.ActFn.apply(y, L.ACT_ABS))
+        z_strings = self.entropy_bottleneck.compress(z)
+        z_hat = self.entropy_bottleneck.decompress(z_strings, z.size()[-2:])
+        indexes = self.gaussian_conditional.build_indexes(self.h_s(z_hat))
+        y_strings = self.gaussian_conditional.compress(y, indexes)
+        return {"strings": [y_strings, z_strings], "shape": z.size()[-2:]}
+
+    @torch.no_grad()
+    def decompress(self, strings, shape):
+        assert isinstance(strings, list) and len(strings) == 2
+        z_hat = self.entropy_bottleneck.decompress(strings[1], shape)
+        indexes = self.gaussian_conditional.build_indexes(self.h_s(z_hat))
+        y_hat = self.gaussian_conditional.decompress(strings[0], indexes, z_hat.dtype)
+        return {"x_hat": self.g_s(y_hat).clamp_(0, 1)}
 
 
 class MeanScaleHyperprior(ScaleHyperprior):
@@ -605,6 +757,31 @@ class MeanScaleHyperprior(ScaleHyperprior):
             scales_hat, means_hat = Fn.NarrowFn.apply(gp, 0, half), Fn.NarrowFn.apply(gp, half, half)
             y_hat, y_lik = self.gaussian_conditional(y, scales_hat, means=means_hat)
             return {"x_hat": self.g_s(y_hat), "likelihoods": {"y": y_lik, "z": z_lik}}
+
+
+    @torch.no_grad()
+    def compress(self, x):
+        y = self.g_a(x)
+        z = self.h_a(y)
+        z_strings = self.entropy_bottleneck.compress(z)
+        z_hat = self.entropy_bottleneck.decompress(z_strings, z.size()[-2:])
+        gp = self.h_s(z_hat)
+        half = gp.shape[1] // 2
+        scales_hat, means_hat = gp[:, :half], gp[:, half:]
+        indexes = self.gaussian_conditional.build_indexes(scales_hat.contiguous(memory_format=torch.channels_last))
+        y_strings = self.gaussian_conditional.compress(y, indexes, means=means_hat)
+        return {"strings": [y_strings, z_strings], "shape": z.size()[-2:]}
+
+    @torch.no_grad()
+    def decompress(self, strings, shape):
+        assert isinstance(strings, list) and len(strings) == 2
+        z_hat = self.entropy_bottleneck.decompress(strings[1], shape)
+        gp = self.h_s(z_hat)
+        half = gp.shape[1] // 2
+        scales_hat, means_hat = gp[:, :half], gp[:, half:]
+        indexes = self.gaussian_conditional.build_indexes(scales_hat.contiguous(memory_format=torch.channels_last))
+        y_hat = self.gaussian_conditional.decompress(strings[0], indexes, means=means_hat)
+        return {"x_hat": self.g_s(y_hat).clamp_(0, 1)}
 
 
 class JointAutoregressiveHierarchicalPriors(CompressionModel):

@@ -372,6 +372,50 @@ int icadv_gdn_bwd_combine(const float* g, const float* y, const float* sc, const
 int icadv_uniform_noise(float* out, int64_t n, uint64_t seed, uint64_t offset, float lo, float hi,
                         icadv_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Entropy coding: what compressai's CPU coder does behind
+ * EntropyBottleneck / GaussianConditional .compress() / .decompress() and model.compress() / .decompress()
+ * (compressai/cpp_exts/rans/rans_interface.cpp encode_with_indexes / decode_with_indexes on ryg_rans rans64.h;
+ * compressai/cpp_exts/ops/ops.cpp pmf_to_quantized_cdf; reference call sites attack_TIC.py:106-110,
+ * InvCompress/attack_inv.py:112-116, InvCompress/ours.py:100-175, InvCompress/train.py:452 net.update()).
+ * Per-symbol arithmetic is compressai's bit for bit (64-bit state, 32-bit renormalisation, 16-bit probabilities, 4-bit
+ * bypass digits for out-of-range symbols).  An image's symbol sequence is dealt round-robin to `lanes` independent
+ * coders (one GPU thread each); the string of an image is [lane word counts: lanes x u32 | lane 0 words | lane 1 ...],
+ * little-endian u32 words; with lanes == 1 the header is omitted and the string is compressai's.
+ * symbols / indexes / means / out: channels-last [n_img][hw][C].  mode 0: flat (c, h, w) sequence order (compressai's
+ * order outside the autoregressive models), lane l takes flat indexes l, l + lanes, ...; mode 1: position-major over
+ * `order` (n_pos hw-indexes, NULL = raster 0 .. n_pos - 1), lane l takes channels l, l + lanes, ... of every position
+ * (lanes == 1 + raster = compressai's _compress_ar order; a wavefront list makes the autoregressive decode parallel).
+ * cdf: [n_cdf][cdf_stride] int32 rows as built by icadv_pmf_to_quantized_cdf, cdf_sizes = entries per row (pmf
+ * length + 2), offsets = symbol value of slot 0.
+ * ------------------------------------------------------------------------------------------ */
+/* HOST function (parameter-sized): cdf[0 .. n] from pmf[0 .. n-1], total 2^precision, no zero-width slot */
+int icadv_pmf_to_quantized_cdf(const float* pmf, int n, int precision, int* cdf);
+/* words of scratch per (image, lane) that icadv_rans_encode needs */
+int icadv_rans_lane_capacity(int n_img, int hw, int C, int mode, int n_pos, int lanes);
+/* scratch: n_img * lanes * capacity words; lane_words: n_img * lanes ints; packed: n_img rows of packed_stride words
+ * (>= lanes * capacity + lanes); total_words[n_img] = length of each string in words */
+int icadv_rans_encode(const int* symbols, const int* indexes, int n_img, int hw, int C, const int* cdf,
+                      const int* cdf_sizes, const int* offsets, int cdf_stride, int mode, const int* order, int n_pos,
+                      int lanes, uint32_t* scratch, int* lane_words, uint32_t* packed, int packed_stride,
+                      int* total_words, icadv_stream_t stream);
+/* out = decoded symbol (+ means when given) */
+int icadv_rans_decode(const uint32_t* packed, int packed_stride, const int* indexes, const float* means, float* out,
+                      int n_img, int hw, int C, const int* cdf, const int* cdf_sizes, const int* offsets,
+                      int cdf_stride, int mode, const int* order, int n_pos, int lanes, icadv_stream_t stream);
+/* incremental decoding (mode 1) for the autoregressive models, whose indexes depend on symbols decoded earlier: the
+ * per-lane coder state (state, cursor: n_img * lanes each) lives in device memory between steps; each step decodes the
+ * channels of `n_positions` listed positions */
+int icadv_rans_decode_init(const uint32_t* packed, int packed_stride, int n_img, int lanes, uint64_t* state,
+                           int* cursor, icadv_stream_t stream);
+int icadv_rans_decode_step(const uint32_t* packed, int packed_stride, uint64_t* state, int* cursor, const int* indexes,
+                           const float* means, float* out, int n_img, int hw, int C, const int* cdf,
+                           const int* cdf_sizes, const int* offsets, int cdf_stride, const int* positions,
+                           int n_positions, int lanes, icadv_stream_t stream);
+/* compressai GaussianConditional.build_indexes: out = #(table[0 .. levels-2] < max(scale, bound)) */
+int icadv_build_indexes(const float* scales, const float* table, int levels, float bound, int* out, long long n,
+                        icadv_stream_t stream);
+
 /* Roofline denominator for the contraction kernels (bench.py): one launch of a bare tcgen05.mma kind::tf32 loop
  * (128 x n x 8 instructions on static shared-memory operands, one CTA per SM, `iters` K-blocks of four MMAs each).
  * The caller times the launch with CUDA events; *flops_out receives the FLOP it performs. */

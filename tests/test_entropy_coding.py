@@ -1,0 +1,204 @@
+"""entropy coding (compress / decompress / update).
+
+CPU tests: the host-side table construction against the oracle restatement of compressai's (oracle/entropy_coding.py).
+GPU tests (-m gpu): the rANS kernels against the oracle coder -- with one lane the strings must be the oracle's BYTES
+(integer work: bit-exact), with many lanes every lane's stream must be the oracle's string of that lane's
+sub-sequence -- and the model-level round trips.  compressai itself is absent (unpinned third-party dependency), so the
+oracle is a restatement of its published algorithm: parity unpinned, stated in oracle/entropy_coding.py."""
+import random
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import entropy_coding as oec
+from oracle import layers as ol
+from oracle import models as om
+
+
+@pytest.fixture(scope="module")
+def dev():
+    from imagecompression_adversarial_b200 import ops
+    ops.require_device()
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    return torch.device("cuda:0")
+
+
+def test_pmf_to_quantized_cdf_matches_oracle():
+    from imagecompression_adversarial_b200 import entropy_coding as ec
+    rng = np.random.default_rng(0)
+    for n in (1, 2, 7, 64, 500):
+        for trial in range(6):
+            pmf = rng.random(n).astype(np.float32) ** (1 + 3 * trial)      # later trials: many near-zero slots
+            pmf /= pmf.sum()
+            got = ec.pmf_to_quantized_cdf(pmf).tolist()
+            assert got == oec.pmf_to_quantized_cdf(pmf.tolist())
+            assert got[0] == 0 and got[-1] == 65536 and all(b > a for a, b in zip(got, got[1:]))
+
+
+def test_entropy_bottleneck_tables_match_oracle():
+    from imagecompression_adversarial_b200 import models as pm
+    torch.manual_seed(3)
+    o = ol.EntropyBottleneck(24)
+    with torch.no_grad():          # spread the quantiles as a trained model would have them
+        o.quantiles[:, 0, 0] -= torch.rand(24) * 20
+        o.quantiles[:, 0, 2] += torch.rand(24) * 30
+        o.quantiles[:, 0, 1] += torch.randn(24)
+    p = pm.EntropyBottleneck(24)
+    p.load_state_dict(o.state_dict(), strict=False)
+    assert p.update() is True and p.update() is False
+    cdf, length, offset = oec.eb_tables(o)
+    assert torch.equal(p._quantized_cdf, cdf) and torch.equal(p._cdf_length, length) and torch.equal(p._offset, offset)
+
+
+def test_gaussian_conditional_tables_match_oracle():
+    from imagecompression_adversarial_b200 import entropy_coding as ec
+    from imagecompression_adversarial_b200 import models as pm
+    g = pm.GaussianConditional()
+    assert g.update_scale_table(ec.get_scale_table()) is True
+    cdf, length, offset = oec.gc_tables(oec.get_scale_table())
+    assert torch.equal(g._quantized_cdf, cdf) and torch.equal(g._cdf_length, length) and torch.equal(g._offset, offset)
+    assert g._quantized_cdf.shape[0] == 64
+
+
+def test_oracle_coder_round_trips_and_tracks_the_entropy():
+    st = oec.get_scale_table()
+    cdf, ln, off = oec._lists(oec.gc_tables(st))
+    rnd = random.Random(1)
+    idx = [rnd.randrange(40) for _ in range(4000)]
+    sym = [int(round(rnd.gauss(0, float(st[i])))) for i in idx]
+    data = oec.rans_encode_with_indexes(sym, idx, cdf, ln, off)
+    assert oec.rans_decode_with_indexes(data, idx, cdf, ln, off) == sym
+    bits = 0.0
+    for s, i in zip(sym, idx):
+        v = s - off[i]
+        assert 0 <= v < ln[i] - 2
+        bits -= np.log2((cdf[i][v + 1] - cdf[i][v]) / 65536.0)
+    assert abs(len(data) * 8 - bits) < 0.002 * bits + 64
+
+
+# ------------------------------------------------------------------------------------------------- GPU
+def _random_case(dev, n, h, w, c, seed, escapes=True):
+    from imagecompression_adversarial_b200 import entropy_coding as ec
+    st = oec.get_scale_table()
+    tables = oec.gc_tables(st)
+    g = torch.Generator().manual_seed(seed)
+    idx = torch.randint(0, 48, (n, h, w, c), generator=g, dtype=torch.int32)
+    sym = torch.round(torch.randn(n, h, w, c, generator=g) * st[idx.long()] * (2.5 if escapes else 0.8)).int()
+    if escapes:   # far outliers: multi-digit bypass codes, both signs
+        sym.view(-1)[::97] = torch.randint(-70000, 70000, sym.view(-1)[::97].shape, generator=g, dtype=torch.int32)
+    return sym.to(dev), idx.to(dev), tables, ec.CoderTables(*tables, dev)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode", [0, 1])
+def test_single_lane_strings_are_the_oracle_bytes(dev, mode):
+    from imagecompression_adversarial_b200 import entropy_coding as ec
+    n, h, w, c = 3, 5, 7, 12
+    sym, idx, tables, dt = _random_case(dev, n, h, w, c, 10 + mode)
+    strings = ec.rans_encode(sym, idx, dt, mode=mode, lanes=1)
+    cdf, ln, off = oec._lists(tables)
+    for i in range(n):
+        if mode == 0:   # (c, h, w) order
+            s = sym[i].permute(2, 0, 1).reshape(-1).tolist()
+            x = idx[i].permute(2, 0, 1).reshape(-1).tolist()
+        else:           # (h, w, c) order
+            s, x = sym[i].reshape(-1).tolist(), idx[i].reshape(-1).tolist()
+        assert strings[i] == oec.rans_encode_with_indexes(s, x, cdf, ln, off)
+    out = ec.rans_decode(strings, idx, dt, mode=mode, lanes=1)
+    assert torch.equal(out.int(), sym)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode,lanes", [(0, 8), (0, 64), (1, 4), (1, 12)])
+def test_lane_streams_are_oracle_strings_of_the_lane_subsequences(dev, mode, lanes):
+    from imagecompression_adversarial_b200 import entropy_coding as ec
+    n, h, w, c = 2, 6, 5, 12
+    sym, idx, tables, dt = _random_case(dev, n, h, w, c, 20 + lanes)
+    means = torch.randn(n, h, w, c, device=dev)
+    order = torch.randperm(h * w, generator=torch.Generator().manual_seed(4)).int() if mode == 1 else None
+    strings = ec.rans_encode(sym, idx, dt, mode=mode, order=order, lanes=lanes)
+    cdf, ln, off = oec._lists(tables)
+    for i in range(n):
+        words = np.frombuffer(strings[i], dtype=np.uint32)
+        counts = words[:lanes].tolist()
+        assert sum(counts) + lanes == words.size
+        pos = lanes
+        if mode == 0:
+            seq_s = sym[i].permute(2, 0, 1).reshape(-1).tolist()
+            seq_x = idx[i].permute(2, 0, 1).reshape(-1).tolist()
+        for l in range(lanes):
+            if mode == 0:
+                s, x = seq_s[l::lanes], seq_x[l::lanes]
+            else:
+                s = sym[i].view(h * w, c)[order.long().to(dev)][:, l::lanes].reshape(-1).tolist()
+                x = idx[i].view(h * w, c)[order.long().to(dev)][:, l::lanes].reshape(-1).tolist()
+            assert words[pos: pos + counts[l]].tobytes() == oec.rans_encode_with_indexes(s, x, cdf, ln, off)
+            pos += counts[l]
+    out = ec.rans_decode(strings, idx, dt, means=means, mode=mode, order=order, lanes=lanes)
+    assert torch.equal(out, sym.float() + means)
+
+
+@pytest.mark.gpu
+def test_incremental_decoder_equals_one_shot(dev):
+    from imagecompression_adversarial_b200 import entropy_coding as ec
+    n, h, w, c = 2, 4, 9, 16
+    sym, idx, tables, dt = _random_case(dev, n, h, w, c, 31)
+    steps = ec.ar_schedule(h, w)
+    order = torch.cat(steps)
+    assert sorted(order.tolist()) == list(range(h * w))
+    strings = ec.rans_encode(sym, idx, dt, mode=1, order=order, lanes=8)
+    dec = ec.StepDecoder(strings, dt, c, dev, lanes=8)
+    out = torch.zeros(n, h, w, c, device=dev)
+    for st in steps:
+        dec.step(idx, None, out, st.to(dev))
+    assert torch.equal(out.int(), sym)
+
+
+@pytest.mark.gpu
+def test_build_indexes_matches_oracle(dev):
+    from imagecompression_adversarial_b200 import entropy_coding as ec
+    st = oec.get_scale_table()
+    g = torch.Generator().manual_seed(5)
+    scales = torch.cat((torch.rand(5000, generator=g) * 300 - 1, st, st * (1 + 1e-6), st * (1 - 1e-6)))
+    got = ec.build_indexes(scales.to(dev), st.to(dev), 0.11)
+    assert torch.equal(got.cpu(), oec.build_indexes(scales, st))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("family,quality,hw", [("factorized", 1, (64, 96)), ("hyper", 3, (128, 64)),
+                                               ("mean_scale", 1, (64, 64))])
+def test_model_compress_decompress_round_trip(dev, family, quality, hw):
+    """decompress(compress(x)) reproduces the eval-mode forward's reconstruction; the strings are as long as the
+    likelihoods say; the oracle's strings for the same weights have the same length to within a percent."""
+    from imagecompression_adversarial_b200 import models as pm
+    from oracle import attack as oatk
+    torch.manual_seed(0)
+    if family == "mean_scale":
+        pnet = pm.MeanScaleHyperprior(128, 192).to(dev).eval()
+        onet = None
+    else:
+        onet = om.init_model(family, quality, seed=0).eval()
+        pnet = pm.init_model(family, quality, "mse", pretrained=False).to(dev)
+        pnet.load_state_dict(onet.state_dict())
+        pnet.eval()
+    x = torch.cat([oatk.synthetic_image(i, *hw) for i in range(2)]).to(dev)
+    assert pnet.update() is True
+    with torch.no_grad():
+        ref = pnet(x)
+    for lanes in (1, 64):
+        for m in pnet.modules():
+            if hasattr(m, "lanes"):
+                m.lanes = lanes
+        enc = pnet.compress(x)
+        dec = pnet.decompress(enc["strings"], enc["shape"])
+        assert float((dec["x_hat"] - ref["x_hat"].clamp(0, 1)).abs().max()) < 1e-6
+        bits = sum(len(s) for ss in enc["strings"] for s in ss) * 8
+        est = float(sum((-torch.log2(l)).sum() for l in ref["likelihoods"].values()))
+        overhead = 0 if lanes == 1 else len(enc["strings"]) * x.shape[0] * lanes * (32 + 64)
+        assert abs(bits - est) < 0.03 * est + overhead + 256, (bits, est)
+        if lanes == 1 and onet is not None:
+            oenc = oec.compress(onet, x.cpu(), family)
+            obits = sum(len(s) for ss in oenc["strings"] for s in ss) * 8
+            assert abs(bits - obits) < 0.01 * obits + 64, (bits, obits)
