@@ -819,6 +819,100 @@ class JointAutoregressiveHierarchicalPriors(CompressionModel):
         return {"x_hat": self.g_s(y_hat), "likelihoods": {"y": y_lik, "z": z_lik}}
 
 
+    # ---- entropy coding (compressai JointAutoregressiveHierarchicalPriors.compress / decompress with _compress_ar /
+    #      _decompress_ar; model-level shape InvCompress/ours.py:100-175).  Every position's (scale, mean) depends on the
+    #      latents already coded through the masked 5x5 context, in the encoder as in the decoder.  compressai walks
+    #      the positions in raster order on the CPU (H*W sequential steps per image); here the positions that are
+    #      mutually independent under the type-A mask form a wavefront (j + 3 i = const), so W + 3(H - 1) steps code
+    #      a whole batch, each step = one gathered 1x1 contraction for the context model, the entropy-parameter
+    #      network, a quantiser / index kernel and (decoder) one rANS step kernel.  ``wavefront=False`` keeps raster
+    #      order; with ``gaussian_conditional.lanes = 1`` that string is the one compressai's coder emits.
+    def _ar_pass(self, y, params, decoder, wavefront):
+        """y: channels-last latent [N,H,W,M] (encoder) or None (decoder); params: channels-last h_s output.
+        Returns (y_hat [N,H,W,M], symbols, indexes, order)."""
+        gc = self.gaussian_conditional
+        n, h, w, cp = params.shape
+        m = self.context_prediction.in_channels
+        dev = params.device
+        hp, wp = h + 4, w + 4
+        y_pad = torch.zeros(n, hp * wp, m, device=dev)
+        with torch.no_grad():
+            self.context_prediction.weight.mul_(self.context_prediction.mask)
+        wt = self.context_prediction.weight.detach()
+        live = [(dy, dx) for dy in range(5) for dx in range(5) if dy < 2 or (dy == 2 and dx < 2)]
+        # gathered form of the masked conv: one 1x1 contraction over the 12 live taps, in-channel = tap * M + c
+        w1 = torch.stack([wt[:, :, dy, dx] for dy, dx in live], dim=1).reshape(wt.shape[0], len(live) * m, 1, 1).contiguous()
+        tap_off = torch.tensor([dy * wp + dx for dy, dx in live], device=dev)
+        bias = self.context_prediction.bias.detach()
+        steps = ec.ar_schedule(h, w, wavefront)
+        params = params.reshape(n, h * w, cp)
+        sym = torch.zeros(n, h * w, m, device=dev, dtype=torch.int32)
+        idx = torch.zeros(n, h * w, m, device=dev, dtype=torch.int32)
+        mean_full = torch.zeros(n, h * w, m, device=dev)
+        out_full = torch.zeros(n, h * w, m, device=dev)
+        if y is not None:
+            if tuple(y.shape) != (n, h, w, m):
+                raise L.IcadvError(f"autoregressive coding needs image sides that are multiples of 64 (latent "
+                                   f"{tuple(y.shape[1:3])} vs hyper-decoder output {(h, w)}); pad the input as "
+                                   "attack_TIC.py:95-104 does")
+            y = y.reshape(n, h * w, m)
+        for st in steps:
+            st = st.to(dev)
+            pos = st.long()
+            base = (pos // w) * wp + (pos % w)
+            r = n * pos.numel()
+            rows = (r + 15) // 16 * 16
+            taps = torch.zeros(rows, len(live) * m, device=dev)
+            taps[:r] = y_pad[:, base[:, None] + tap_off[None, :]].reshape(r, -1)
+            ctx = Fn.Contraction.apply(taps.view(1, rows // 16, 16, -1).permute(0, 3, 1, 2), w1, bias, 1, 1, False,
+                                       L.ACT_NONE, False)
+            feat = torch.zeros(rows, cp + ctx.shape[1], device=dev)
+            feat[:r, :cp] = params[:, pos].reshape(r, cp)
+            feat[:, cp:] = Fn.to_nhwc(ctx).reshape(rows, -1)
+            gp = Fn.to_nhwc(self.entropy_parameters(feat.view(1, rows // 16, 16, -1).permute(0, 3, 1, 2)))
+            gp = gp.reshape(rows, -1)[:r]
+            scales, means = gp[:, :m].contiguous(), gp[:, m:].contiguous()
+            ind = gc.build_indexes(scales).view(n, -1, m)
+            if decoder is None:
+                q = ops.unary(y[:, pos].reshape(r, m) - means, 3)
+                sym[:, pos] = q.int().view(n, -1, m)
+                idx[:, pos] = ind
+                y_hat = q + means
+            else:
+                idx[:, pos] = ind
+                mean_full[:, pos] = means.view(n, -1, m)
+                decoder.step(idx, mean_full, out_full, st)
+                y_hat = out_full[:, pos].reshape(r, m)
+            y_pad[:, base + 2 * wp + 2] = y_hat.view(n, -1, m)
+        y_hat = y_pad.view(n, hp, wp, m)[:, 2:-2, 2:-2].contiguous()
+        return y_hat, sym.view(n, h, w, m), idx.view(n, h, w, m), torch.cat(steps)
+
+    @torch.no_grad()
+    def compress(self, x, wavefront=True):
+        gc = self.gaussian_conditional
+        y = self.g_a(x)
+        z = self.h_a(y)
+        z_strings = self.entropy_bottleneck.compress(z)
+        z_hat = self.entropy_bottleneck.decompress(z_strings, z.size()[-2:])
+        params = Fn.to_nhwc(self.h_s(z_hat)).contiguous()
+        y_hat, sym, idx, order = self._ar_pass(Fn.to_nhwc(y).contiguous(), params, None, wavefront)
+        y_strings = ec.rans_encode(sym, idx, gc._coder_tables(), mode=1, order=order, lanes=gc.lanes)
+        self._coded_y_hat = y_hat          # what the decoder must reproduce (tests)
+        return {"strings": [y_strings, z_strings], "shape": z.size()[-2:]}
+
+    @torch.no_grad()
+    def decompress(self, strings, shape, wavefront=True):
+        assert isinstance(strings, list) and len(strings) == 2
+        gc = self.gaussian_conditional
+        z_hat = self.entropy_bottleneck.decompress(strings[1], shape)
+        params = Fn.to_nhwc(self.h_s(z_hat)).contiguous()
+        dec = ec.StepDecoder(strings[0], gc._coder_tables(), self.context_prediction.in_channels, params.device,
+                             lanes=gc.lanes)
+        y_hat, _, _, _ = self._ar_pass(None, params, dec, wavefront)
+        self._decoded_y_hat = y_hat
+        return {"x_hat": self.g_s(Fn.to_nchw(y_hat)).clamp_(0, 1)}
+
+
 class Cheng2020Anchor(JointAutoregressiveHierarchicalPriors):
     """compressai cheng2020_anchor (anchors/model.py:77; widths pinned by InvCompress/ours.py:33-55): residual blocks,
     sub-pixel convolutions, no attention, single Gaussian with mean."""

@@ -197,8 +197,44 @@ def test_model_compress_decompress_round_trip(dev, family, quality, hw):
         bits = sum(len(s) for ss in enc["strings"] for s in ss) * 8
         est = float(sum((-torch.log2(l)).sum() for l in ref["likelihoods"].values()))
         overhead = 0 if lanes == 1 else len(enc["strings"]) * x.shape[0] * lanes * (32 + 64)
-        assert abs(bits - est) < 0.03 * est + overhead + 256, (bits, est)
+        # random-init hyperpriors put much of y outside the table's support, where the likelihood floor (30 bits)
+        # over-estimates the 4-bit bypass digits the coder really spends: an upper bound there, a match for the
+        # factorised prior
+        assert bits < 1.03 * est + overhead + 256, (bits, est)
+        if family == "factorized":
+            assert abs(bits - est) < 0.03 * est + overhead + 256, (bits, est)
         if lanes == 1 and onet is not None:
             oenc = oec.compress(onet, x.cpu(), family)
             obits = sum(len(s) for ss in oenc["strings"] for s in ss) * 8
             assert abs(bits - obits) < 0.01 * obits + 64, (bits, obits)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("family,quality,hw,wavefront,lanes", [("context", 1, (64, 128), True, 64),
+                                                               ("context", 1, (64, 64), False, 1),
+                                                               ("cheng2020", 1, (128, 64), True, 32)])
+def test_autoregressive_compress_decompress_round_trip(dev, family, quality, hw, wavefront, lanes):
+    """The decoder rebuilds exactly the latents the encoder coded (bit-exact: every (scale, mean) it derives from the
+    decoded neighbourhood is the encoder's), in raster order and on the wavefront schedule, for a batch."""
+    from imagecompression_adversarial_b200 import models as pm
+    from oracle import attack as oatk
+    onet = om.init_model(family, quality, seed=0).eval()
+    pnet = pm.init_model(family, quality, "mse", pretrained=False).to(dev)
+    pnet.load_state_dict(onet.state_dict())
+    pnet.eval()
+    pnet.update()
+    pnet.gaussian_conditional.lanes = lanes
+    x = torch.cat([oatk.synthetic_image(i, *hw) for i in range(2)]).to(dev)
+    enc = pnet.compress(x, wavefront=wavefront)
+    dec = pnet.decompress(enc["strings"], enc["shape"], wavefront=wavefront)
+    assert torch.equal(pnet._decoded_y_hat, pnet._coded_y_hat)
+    assert dec["x_hat"].shape == x.shape and float(dec["x_hat"].min()) >= 0 and float(dec["x_hat"].max()) <= 1
+    # each image alone gives the same strings (the batch is only a scheduling unit)
+    one = pnet.compress(x[1:2], wavefront=wavefront)
+    assert one["strings"][0][0] == enc["strings"][0][1] and one["strings"][1][0] == enc["strings"][1][1]
+    if not wavefront and lanes == 1:
+        # compressai's order and single stream: same string length as the oracle's coder to within a percent (the
+        # symbols themselves differ where TF32 moves a latent across a rounding boundary)
+        oenc = oec.compress(onet, x.cpu(), "context")
+        for a, b in zip(enc["strings"][0], oenc["strings"][0]):
+            assert abs(len(a) - len(b)) <= 0.01 * len(b) + 16, (len(a), len(b))
