@@ -192,11 +192,46 @@ __global__ void act_backward_kernel(const float* __restrict__ x, const float* __
   }
 }
 
+// compressai.layers.AttentionBlock gate (cheng2020_attn): y = a * sigmoid(b) + x and its gradients
+__global__ void attention_gate_kernel(const float* __restrict__ a, const float* __restrict__ b,
+                                      const float* __restrict__ x, float* __restrict__ y, int64_t n) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    y[i] = a[i] * (1.f / (1.f + expf(-b[i]))) + x[i];
+}
+__global__ void attention_gate_backward_kernel(const float* __restrict__ a, const float* __restrict__ b,
+                                               const float* __restrict__ g, float* __restrict__ ga,
+                                               float* __restrict__ gb, int64_t n) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float s = 1.f / (1.f + expf(-b[i])), gv = g[i];
+    ga[i] = gv * s;
+    gb[i] = gv * a[i] * s * (1.f - s);
+  }
+}
+
 }  // namespace icadv
 
 using namespace icadv;
 
 extern "C" {
+
+int icadv_attention_gate(const float* a, const float* b, const float* x, float* y, int64_t n, icadv_stream_t stream) {
+  ICADV_REQUIRE(a && b && x && y && n > 0, "bad attention_gate args");
+  int64_t blocks = (n + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  attention_gate_kernel<<<(int)blocks, 256, 0, as_stream(stream)>>>(a, b, x, y, n);
+  ICADV_CUDA_TRY(cudaGetLastError());
+  return ICADV_OK;
+}
+
+int icadv_attention_gate_backward(const float* a, const float* b, const float* g, float* ga, float* gb, int64_t n,
+                                  icadv_stream_t stream) {
+  ICADV_REQUIRE(a && b && g && ga && gb && n > 0, "bad attention_gate_backward args");
+  int64_t blocks = (n + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  attention_gate_backward_kernel<<<(int)blocks, 256, 0, as_stream(stream)>>>(a, b, g, ga, gb, n);
+  ICADV_CUDA_TRY(cudaGetLastError());
+  return ICADV_OK;
+}
 
 int icadv_eb_prepare(const float* const* matrices, const float* const* biases, const float* const* factors,
                      float* table, int C, icadv_stream_t stream) {

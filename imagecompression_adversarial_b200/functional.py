@@ -244,6 +244,27 @@ class AddFn(torch.autograd.Function):
         return g, g
 
 
+class GateFn(torch.autograd.Function):
+    """a * sigmoid(b) + x: the gate of compressai.layers.AttentionBlock (cheng2020_attn)."""
+
+    @staticmethod
+    def forward(ctx, a, b, x):
+        cl = torch.channels_last
+        ac, bc, xc = a.contiguous(memory_format=cl), b.contiguous(memory_format=cl), x.contiguous(memory_format=cl)
+        y = ops.attention_gate(ac, bc, xc)
+        ctx.save_for_backward(ac, bc)
+        if _REC is not None:
+            _REC.note("gate", [to_nhwc(ac), to_nhwc(bc), to_nhwc(xc)], to_nhwc(y))
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        ac, bc = ctx.saved_tensors
+        gc = g.contiguous(memory_format=torch.channels_last)
+        ga, gb = ops.attention_gate_backward(ac, bc, gc)
+        return ga, gb, g
+
+
 class PixelShuffleFn(torch.autograd.Function):
     """nn.PixelShuffle(r) (compressai subpel_conv3x3)."""
 

@@ -27,6 +27,7 @@ ZOO = {
     "hyper": {q: (128, 192) if q <= 5 else (192, 320) for q in range(1, 9)},
     "context": {q: (192, 192) if q <= 4 else (192, 320) for q in range(1, 9)},
     "cheng2020": {q: (128,) if q <= 3 else (192,) for q in range(1, 7)},
+    "cheng2020_attn": {q: (128,) if q <= 3 else (192,) for q in range(1, 7)},
 }
 
 
@@ -935,6 +936,46 @@ class Cheng2020Anchor(JointAutoregressiveHierarchicalPriors):
             ResidualBlock(N, N), subpel_conv3x3(N, 3, 2))
 
 
+class ResidualUnit(nn.Module):
+    """compressai.layers.AttentionBlock.ResidualUnit: 1x1 (N -> N/2), ReLU, 3x3, ReLU, 1x1 (N/2 -> N), + x, ReLU."""
+
+    def __init__(self, N):
+        super().__init__()
+        self.conv = nn.Sequential(conv1x1(N, N // 2), ReLU(), conv3x3(N // 2, N // 2), ReLU(), conv1x1(N // 2, N))
+
+    def forward(self, x):
+        return Fn.ActFn.apply(Fn.AddFn.apply(self.conv(x), x), L.ACT_RELU)
+
+
+class AttentionBlock(nn.Module):
+    """compressai.layers.AttentionBlock (the simplified, non-local-free attention of cheng2020_attn):
+    ``conv_a(x) * sigmoid(conv_b(x)) + x`` with three residual units per branch and a closing 1x1 on the gate."""
+
+    def __init__(self, N):
+        super().__init__()
+        self.conv_a = nn.Sequential(ResidualUnit(N), ResidualUnit(N), ResidualUnit(N))
+        self.conv_b = nn.Sequential(ResidualUnit(N), ResidualUnit(N), ResidualUnit(N), conv1x1(N, N))
+
+    def forward(self, x):
+        return Fn.GateFn.apply(self.conv_a(x), self.conv_b(x), x)
+
+
+class Cheng2020Attention(Cheng2020Anchor):
+    """compressai cheng2020_attn (BASELINE config 4 names it): the anchor with an AttentionBlock after
+    the second strided block and at the end of ``g_a``, mirrored in ``g_s``."""
+
+    def __init__(self, N):
+        super().__init__(N)
+        self.g_a = nn.Sequential(
+            ResidualBlockWithStride(3, N, 2), ResidualBlock(N, N),
+            ResidualBlockWithStride(N, N, 2), AttentionBlock(N), ResidualBlock(N, N),
+            ResidualBlockWithStride(N, N, 2), ResidualBlock(N, N), conv3x3(N, N, 2), AttentionBlock(N))
+        self.g_s = nn.Sequential(
+            AttentionBlock(N), ResidualBlock(N, N), ResidualBlockUpsample(N, N, 2), ResidualBlock(N, N),
+            ResidualBlockUpsample(N, N, 2), AttentionBlock(N), ResidualBlock(N, N), ResidualBlockUpsample(N, N, 2),
+            ResidualBlock(N, N), subpel_conv3x3(N, 3, 2))
+
+
 def _build(model, quality):
     cfg = ZOO[model][quality]
     if model == "factorized":
@@ -945,6 +986,8 @@ def _build(model, quality):
         return JointAutoregressiveHierarchicalPriors(*cfg)
     if model == "cheng2020":
         return Cheng2020Anchor(*cfg)
+    if model == "cheng2020_attn":
+        return Cheng2020Attention(*cfg)
     raise L.IcadvError(f"unknown model family '{model}'")
 
 
@@ -973,10 +1016,16 @@ def cheng2020_anchor(quality, metric="mse", pretrained=False, **kw):
     return _build("cheng2020", quality)
 
 
+def cheng2020_attn(quality, metric="mse", pretrained=False, **kw):
+    _no_zoo(pretrained)
+    return _build("cheng2020_attn", quality)
+
+
 def init_model(MODEL, quality, metric="mse", pretrained=False):
-    """Same dispatch as anchors/model.py:60-78."""
+    """Same dispatch as anchors/model.py:60-78 (+ ``cheng2020_attn``, the zoo entry the reference leaves commented
+    out next to ``cheng2020_anchor``)."""
     table = {"factorized": bmshj2018_factorized, "hyper": bmshj2018_hyperprior, "context": mbt2018,
-             "cheng2020": cheng2020_anchor}
+             "cheng2020": cheng2020_anchor, "cheng2020_attn": cheng2020_attn}
     if MODEL not in table:
         raise L.IcadvError(f"unknown model '{MODEL}'")
     return table[MODEL](quality=quality, metric=metric, pretrained=pretrained)

@@ -350,6 +350,23 @@ def unary(x, op, b=None):
     return y
 
 
+def attention_gate(a, b, x):
+    """a * sigmoid(b) + x on three tensors sharing shape and memory layout."""
+    if not (a.stride() == b.stride() == x.stride() and a.shape == b.shape == x.shape):
+        raise L.IcadvError("attention_gate: operands must share shape and memory layout")
+    y = torch.empty_like(a)
+    L.call("icadv_attention_gate", _p(a), _p(b), _p(x), _p(y), a.numel(), _stream())
+    return y
+
+
+def attention_gate_backward(a, b, g):
+    if not (a.stride() == b.stride() == g.stride() and a.shape == g.shape):
+        raise L.IcadvError("attention_gate_backward: operands must share shape and memory layout")
+    ga, gb = torch.empty_like(a), torch.empty_like(a)
+    L.call("icadv_attention_gate_backward", _p(a), _p(b), _p(g), _p(ga), _p(gb), a.numel(), _stream())
+    return ga, gb
+
+
 def act_backward(x, g, act):
     if x.stride() != g.stride() or x.shape != g.shape:
         raise L.IcadvError("act_backward: operands must share shape and memory layout")

@@ -70,6 +70,14 @@ def _act_bwd(x, g, gx, act):
     L.call("icadv_act_backward", _p(x), _p(g), _p(gx), x.numel(), _UN[act], _stream())
 
 
+def _gate(a, b, x, y):
+    L.call("icadv_attention_gate", _p(a), _p(b), _p(x), _p(y), a.numel(), _stream())
+
+
+def _gate_bwd(a, b, g, ga, gb):
+    L.call("icadv_attention_gate_backward", _p(a), _p(b), _p(g), _p(ga), _p(gb), a.numel(), _stream())
+
+
 def _shuffle(src, dst, n, lo_h, lo_w, c_out, r, inverse):
     L.call("icadv_pixel_shuffle", _p(src), _p(dst), n, lo_h, lo_w, c_out, r, 1 if inverse else 0, _stream())
 
@@ -251,6 +259,9 @@ class TapeProgram:
                 n, h, w, c = self.buf[nd["in"][0]].shape
                 r = nd["r"]
                 self.fwd.append(FnLaunch(_shuffle, self.buf[nd["in"][0]], out, n, h, w, c // (r * r), r, False))
+            elif nd["kind"] == "gate":       # AttentionBlock: a * sigmoid(b) + x
+                a, b, x = (self.buf[t] for t in nd["in"])
+                self.fwd.append(FnLaunch(_gate, a, b, x, out))
             else:
                 raise L.IcadvError(f"tape program: unsupported operator '{nd['kind']}'")
 
@@ -316,6 +327,13 @@ class TapeProgram:
                 dst = torch.empty_like(self.buf[src])
                 self.bwd.append(FnLaunch(_shuffle, g, dst, n, h, w, c // (r * r), r, True))
                 contrib.setdefault(src, []).append(dst)
+            elif nd["kind"] == "gate":
+                ta, tb, tx = nd["in"]
+                ga, gb = torch.empty_like(g), torch.empty_like(g)
+                self.bwd.append(FnLaunch(_gate_bwd, self.buf[ta], self.buf[tb], g, ga, gb))
+                contrib.setdefault(ta, []).append(ga)
+                contrib.setdefault(tb, []).append(gb)
+                contrib.setdefault(tx, []).append(g)
         gin = grad_of(in_id)
         if gin is not self.g_in:
             self.bwd.append(FnLaunch(_unary, gin, None, self.g_in, 7))      # op 7: copy

@@ -416,6 +416,12 @@ int icadv_rans_decode_step(const uint32_t* packed, int packed_stride, uint64_t* 
 int icadv_build_indexes(const float* scales, const float* table, int levels, float bound, int* out, long long n,
                         icadv_stream_t stream);
 
+/* compressai.layers.AttentionBlock gate (cheng2020_attn): y = a * sigmoid(b) + x; backward:
+ * ga = g * sigmoid(b), gb = g * a * sigmoid(b) * (1 - sigmoid(b)) (the gradient to x is g itself) */
+int icadv_attention_gate(const float* a, const float* b, const float* x, float* y, int64_t n, icadv_stream_t stream);
+int icadv_attention_gate_backward(const float* a, const float* b, const float* g, float* ga, float* gb, int64_t n,
+                                  icadv_stream_t stream);
+
 /* Roofline denominator for the contraction kernels (bench.py): one launch of a bare tcgen05.mma kind::tf32 loop
  * (128 x n x 8 instructions on static shared-memory operands, one CTA per SM, `iters` K-blocks of four MMAs each).
  * The caller times the launch with CUDA events; *flops_out receives the FLOP it performs. */

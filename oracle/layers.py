@@ -188,6 +188,30 @@ class ResidualBlock(nn.Module):
         return out + idt
 
 
+class AttentionBlock(nn.Module):
+    """compressai.layers.AttentionBlock (cheng2020_attn): the simplified attention of
+    Cheng 2020 -- ``conv_a(x) * sigmoid(conv_b(x)) + x``, three residual units (1x1 N->N/2, ReLU, 3x3, ReLU, 1x1
+    N/2->N, + x, ReLU) per branch, a closing 1x1 on the gate branch.  20.5 N^2 + 13 N parameters."""
+
+    class ResidualUnit(nn.Module):
+        def __init__(self, N):
+            super().__init__()
+            self.conv = nn.Sequential(conv1x1(N, N // 2), nn.ReLU(inplace=True), conv3x3(N // 2, N // 2),
+                                      nn.ReLU(inplace=True), conv1x1(N // 2, N))
+
+        def forward(self, x):
+            return F.relu(self.conv(x) + x)
+
+    def __init__(self, N):
+        super().__init__()
+        U = AttentionBlock.ResidualUnit
+        self.conv_a = nn.Sequential(U(N), U(N), U(N))
+        self.conv_b = nn.Sequential(U(N), U(N), U(N), conv1x1(N, N))
+
+    def forward(self, x):
+        return self.conv_a(x) * torch.sigmoid(self.conv_b(x)) + x
+
+
 # --------------------------------------------------------------------------------------
 # entropy models (A.3 / A.4)
 # --------------------------------------------------------------------------------------

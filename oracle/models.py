@@ -8,7 +8,7 @@ own spelled-out versions: ``anchors/model.py:86-108`` (``entropy_estimator``) an
 import torch
 import torch.nn as nn
 
-from .layers import (GDN, EntropyBottleneck, GaussianConditional, MaskedConv2d, ResidualBlock,
+from .layers import (GDN, AttentionBlock, EntropyBottleneck, GaussianConditional, MaskedConv2d, ResidualBlock,
                      ResidualBlockUpsample, ResidualBlockWithStride, conv, conv3x3, deconv,
                      subpel_conv3x3)
 
@@ -18,6 +18,7 @@ ZOO = {
     "hyper": {q: (128, 192) if q <= 5 else (192, 320) for q in range(1, 9)},
     "context": {q: (192, 192) if q <= 4 else (192, 320) for q in range(1, 9)},
     "cheng2020": {q: (128,) if q <= 3 else (192,) for q in range(1, 7)},
+    "cheng2020_attn": {q: (128,) if q <= 3 else (192,) for q in range(1, 7)},
 }
 
 # CompressAI's published parameter counts (A.8) -- structural checksum of this restatement
@@ -26,6 +27,7 @@ PARAM_COUNTS = {
     ("hyper", 128, 192): 5_075_843, ("hyper", 192, 320): 11_816_323,
     ("context", 192, 192): 14_130_467, ("context", 192, 320): 25_504_596,
     ("cheng2020", 128): 11_833_149, ("cheng2020", 192): 26_598_956,
+    ("cheng2020_attn", 128): 13_183_293,      # published; N=192 follows from the same layer list (29 631 788)
 }
 
 
@@ -147,6 +149,22 @@ class Cheng2020Anchor(JointAutoregressiveHierarchicalPriors):
         self._init_weights()
 
 
+class Cheng2020Attention(Cheng2020Anchor):
+    """cheng2020_attn (the zoo entry BASELINE config 4 names): the anchor plus four AttentionBlocks."""
+
+    def __init__(self, N):
+        super().__init__(N)
+        self.g_a = nn.Sequential(
+            ResidualBlockWithStride(3, N, 2), ResidualBlock(N, N),
+            ResidualBlockWithStride(N, N, 2), AttentionBlock(N), ResidualBlock(N, N),
+            ResidualBlockWithStride(N, N, 2), ResidualBlock(N, N), conv3x3(N, N, 2), AttentionBlock(N))
+        self.g_s = nn.Sequential(
+            AttentionBlock(N), ResidualBlock(N, N), ResidualBlockUpsample(N, N, 2), ResidualBlock(N, N),
+            ResidualBlockUpsample(N, N, 2), AttentionBlock(N), ResidualBlock(N, N), ResidualBlockUpsample(N, N, 2),
+            ResidualBlock(N, N), subpel_conv3x3(N, 3, 2))
+        self._init_weights()
+
+
 def init_model(model, quality, metric="mse", pretrained=False, seed=None):
     """Mirror of ``anchors.model.init_model`` (anchors/model.py:60-78) on the oracle classes.
 
@@ -164,6 +182,8 @@ def init_model(model, quality, metric="mse", pretrained=False, seed=None):
         return JointAutoregressiveHierarchicalPriors(*cfg)
     if model == "cheng2020":
         return Cheng2020Anchor(*cfg)
+    if model == "cheng2020_attn":
+        return Cheng2020Attention(*cfg)
     raise ValueError(model)
 
 

@@ -27,6 +27,14 @@ def pair(model, quality, dev, seed=0):
     from imagecompression_adversarial_b200 import models as pm
     from oracle import models as om
     onet = om.init_model(model, quality, seed=seed).to(dev)
+    if model == "cheng2020_attn":
+        # kaiming-initialised attention blocks (three un-normalised residual units per branch, four blocks per stack)
+        # amplify a random-init network's activations to 1e18-1e22 in BOTH implementations (fp32 overflow in the PSNR);
+        # 0.6 x the g_a / g_s conv weights keeps them O(1), like trained weights
+        with torch.no_grad():
+            for name, m in onet.named_modules():
+                if isinstance(m, torch.nn.Conv2d) and name.startswith(("g_a", "g_s")):
+                    m.weight.mul_(0.6)
     pnet = pm.init_model(model, quality, "mse", pretrained=False).to(dev)
     missing = pnet.load_state_dict(onet.state_dict(), strict=True)
     assert not missing.missing_keys and not missing.unexpected_keys
@@ -370,15 +378,16 @@ def test_roi_targeted_attack_matches_oracle(dev):
     assert abs(psnr(p[0], x) - psnr(o[0], x)) < 0.05
 
 
-def test_generic_engine_cheng2020_matches_oracle(dev):
-    """cheng2020_anchor (residual blocks, sub-pixel convs) through the traced static launch program (CUDA graph) vs the
-    oracle loop."""
+@pytest.mark.parametrize("model", ["cheng2020", "cheng2020_attn"])
+def test_generic_engine_cheng2020_matches_oracle(dev, model):
+    """cheng2020_anchor (residual blocks, sub-pixel convs) and cheng2020_attn (+ attention blocks) through the traced
+    static launch program (CUDA graph) vs the oracle loop."""
     from imagecompression_adversarial_b200 import attack as patk
     from imagecompression_adversarial_b200.engine import TapeAttackEngine as GenericAttackEngine
     from oracle import attack as oatk
-    onet, pnet = pair("cheng2020", 1, dev)
+    onet, pnet = pair(model, 1, dev)
     x = images(1, 192, 192, dev)   # > 160: the final eval computes MS-SSIM (pytorch_msssim asserts on smaller images)
-    args = oatk.default_args(model="cheng2020", quality=1, metric="mse", steps=6)
+    args = oatk.default_args(model=model, quality=1, metric="mse", steps=6)
     rec, orec = [], []
     p = patk.attack_(x, pnet, args, record=rec)
     assert isinstance(next(iter(patk._ENGINES.values())), GenericAttackEngine)

@@ -40,6 +40,14 @@ def pair(model, quality, dev, seed=0):
     from imagecompression_adversarial_b200 import models as pm
     from oracle import models as om
     onet = om.init_model(model, quality, seed=seed).to(dev)
+    if model == "cheng2020_attn":
+        # kaiming-initialised attention blocks (three un-normalised residual units per branch, four blocks per stack)
+        # amplify a random-init network's activations to 1e18-1e22 in BOTH implementations (fp32 overflow in the PSNR);
+        # 0.6 x the g_a / g_s conv weights keeps them O(1), like trained weights
+        with torch.no_grad():
+            for name, m in onet.named_modules():
+                if isinstance(m, torch.nn.Conv2d) and name.startswith(("g_a", "g_s")):
+                    m.weight.mul_(0.6)
     pnet = pm.init_model(model, quality, "mse", pretrained=False).to(dev)
     pnet.load_state_dict(onet.state_dict(), strict=True)
     return onet, pnet
@@ -170,9 +178,11 @@ def test_split_stack_program_matches_oracle(dev, model, quality):
 
 
 @pytest.mark.parametrize("model,quality,hw", [("factorized", 1, (128, 192)), ("hyper", 3, (128, 192)),
-                                              ("context", 4, (128, 192)), ("cheng2020", 6, (128, 128))])
+                                              ("context", 4, (128, 192)), ("cheng2020", 6, (128, 128)),
+                                              ("cheng2020_attn", 1, (128, 128))])
 def test_eval_forward_parity(dev, model, quality, hw):
-    """net(x) in eval mode: latent indices, bpp, PSNR at the literal tolerances for all four families."""
+    """net(x) in eval mode: latent indices, bpp, PSNR at the literal tolerances for all four families (+ the attention
+    variant of cheng2020)."""
     onet, pnet = pair(model, quality, dev)
     x = images(2, *hw, dev)
     onet.eval(); pnet.eval()
@@ -394,3 +404,26 @@ def test_config5_adv_train_step_300_attack_steps(dev):
     # first Adam step = lr * g / (|g| + 1e-8): parameters whose gradient is ~1e-8 (dead units of a random-init codec)
     # move by an amount that depends on the last digits of g; measured ~3 % of lr on average
     assert tot / cnt < 0.05 * lr, tot / cnt / lr
+
+
+def test_attention_block_matches_oracle(dev):
+    """compressai.layers.AttentionBlock (cheng2020_attn): forward, input gradient and every parameter gradient."""
+    from imagecompression_adversarial_b200 import models as pm
+    from oracle import layers as ol
+    torch.manual_seed(11)
+    o = ol.AttentionBlock(64).to(dev)
+    p = pm.AttentionBlock(64).to(dev)
+    p.load_state_dict(o.state_dict())
+    x = torch.randn(2, 64, 24, 40, device=dev)
+    gout = torch.randn(2, 64, 24, 40, device=dev)
+    res = []
+    for net in (o, p):
+        xi = x.clone().requires_grad_(True)
+        with pm._param_grads_on(True):
+            out = net(xi)
+        out.backward(gout)
+        res.append((out.detach(), xi.grad.detach(), {k: v.grad.detach() for k, v in net.named_parameters()}))
+    (oo, og, ow), (po, pg, pw) = res
+    assert relerr(po, oo) < 2e-5 and relerr(pg, og) < 1e-4, (relerr(po, oo), relerr(pg, og))
+    for k in ow:
+        assert relerr(pw[k], ow[k]) < 2e-4, (k, relerr(pw[k], ow[k]))
