@@ -39,6 +39,8 @@ constexpr int kSmemTwoCta = 115712;     // (228 KB per SM) / 2 - 1 KB system res
 constexpr int kBarBlock = 448;          // up to 49 mbarriers + the TMEM base; followed by per-channel bias / beta copies (2 * n_ch floats)
 constexpr int kEpiCol2im = 5;           // internal epilogue code: narrow-output transposed conv via col2im
 constexpr int kZStride = 77;            // floats per row of the col2im staging tile (odd: conflict-free)
+constexpr int kZStride4 = 100;          // persistent col2im, 3 output channels: rows of 25 taps x float4 (stride = 4 mod 32 words:
+                                        // quarter-warp 16-byte accesses of consecutive rows hit distinct bank groups)
 
 // One halo patch of the input: everything the taps [tap_begin, tap_end) read for one 32-channel chunk.
 struct Group {
@@ -649,6 +651,7 @@ struct TcpParams {
   long long* dbg;   // developer profiling: 16 cycle counters per CTA (see scripts/persistent_timeline.py)
   int ys_slots;     // streaming backward kernel: slots of the saved-tensor ring (each [y chunk | scale chunk] = 32 KB)
   float* out;       // streaming backward kernel: dense output base (plain 128-byte stores per pixel and chunk)
+  int w_resident;   // col2im: the k_chunks weight boxes of the 1x1 GEMM are loaded once and stay in shared memory
 };
 
 struct TcpItem { int img, i0, j0, cls; };
@@ -722,48 +725,19 @@ __global__ void __launch_bounds__(kPThreads, 1) conv_tcp_kernel(const __grid_con
   const int n_slots = p.n_active != nullptr ? *p.n_active : p.n_img;
   const int total = n_slots * p.tiles_x * p.tiles_y * p.n_class;
 
-  if (warp == 0) {
-    // ===================== TMA producer: weights (+ the resident gamma) =====================
-    // Weights and patches have separate producing threads: a patch is requested as soon as its slot is free (one
-    // whole patch period ahead of its use) instead of queueing behind the weight boxes of the previous patch.
-    if (elect_one_sync()) {
-      if (gdn) {
-        mbar_arrive_expect_tx(gfull, nC * b_bytes);
-        for (int c = 0; c < nC; ++c) tma_load_2d(gmat + c * b_bytes, &p.g_map, gfull, c * 32, 0);
-      }
-      int s = 0;
-      uint32_t s_par = 1;
-      uint8_t* wdst = wring;
-      for (int item = blockIdx.x; item < total; item += gridDim.x) {
-        const TcpItem it = tcp_decode(p, item);
-        const TcpClass cl = p.cls[it.cls];
-        const int t_begin = p.groups[cl.g_begin].tap_begin, t_end = p.groups[cl.g_end - 1].tap_end;   // a class's taps are contiguous
-        for (int kc = 0; kc < p.k_chunks; ++kc) {
-          const int c0 = kc * 32;
-          int wrow = p.tap_wtap[t_begin] * p.n_total;
-          for (int t = t_begin; t < t_end; ++t) {
-            mbar_wait(&wempty[s], s_par);
-            mbar_arrive_expect_tx(&wfull[s], b_bytes);
-            tma_load_2d(wdst, &p.w_map, &wfull[s], c0, wrow);
-            wrow = p.tap_wtap[t + 1] * p.n_total;   // one slack entry
-            if (++s == S) { s = 0; s_par ^= 1; wdst = wring; } else { wdst += b_bytes; }
-          }
-        }
-      }
-    }
-    __syncwarp();
-  } else if (warp == kPPatchWarp) {
-    // ===================== TMA producer: input halo patches =====================
-    if (elect_one_sync()) {
-      int ps = 0;
-      uint32_t p_par = 1;
-      uint8_t* pdst = smem;
-      for (int item = blockIdx.x; item < total; item += gridDim.x) {
-        const TcpItem it = tcp_decode(p, item);
-        const TcpClass cl = p.cls[it.cls];
-        for (int kc = 0; kc < p.k_chunks; ++kc) {
-          const int c0 = kc * 32;
-          for (int g = cl.g_begin; g < cl.g_end; ++g) {
+  // Patch stream of this CTA: patches q = 0, 1, 2, ... in (item, channel chunk, group) order go to ring slot q % P.
+  // `mask` = 0: the calling thread produces all of them; 1: those with (q & 1) == first (two producing threads).
+  auto produce_patches = [&](int first, int mask) {
+    int ps = 0, q = 0;
+    uint32_t p_par = 1;
+    uint8_t* pdst = smem;
+    for (int item = blockIdx.x; item < total; item += gridDim.x) {
+      const TcpItem it = tcp_decode(p, item);
+      const TcpClass cl = p.cls[it.cls];
+      for (int kc = 0; kc < p.k_chunks; ++kc) {
+        const int c0 = kc * 32;
+        for (int g = cl.g_begin; g < cl.g_end; ++g, ++q) {
+          if ((q & mask) == first) {
             const int cx = it.j0 + p.groups[g].dx0, cy = it.i0 + p.groups[g].dy0;
             mbar_wait(&pempty[ps], p_par);
             mbar_arrive_expect_tx(&pfull[ps], p.groups[g].bytes);
@@ -771,11 +745,58 @@ __global__ void __launch_bounds__(kPThreads, 1) conv_tcp_kernel(const __grid_con
               tma_load_5d(pdst, &p.a_map[0], &pfull[ps], 0, cx, cy, p.groups[g].plane5, it.img);
             else
               tma_load_4d(pdst, &p.a_map[p.groups[g].map], &pfull[ps], c0, cx, cy, it.img);
-            if (++ps == P) { ps = 0; p_par ^= 1; pdst = smem; } else { pdst += p.patch_bytes; }
+          }
+          if (++ps == P) { ps = 0; p_par ^= 1; pdst = smem; } else { pdst += p.patch_bytes; }
+        }
+      }
+    }
+  };
+
+  if (warp == 0) {
+    // ===================== TMA producer: weights (+ the resident gamma) =====================
+    // Weights and patches have separate producing threads: a patch is requested as soon as its slot is free (one
+    // whole patch period ahead of its use) instead of queueing behind the weight boxes of the previous patch.
+    if (elect_one_sync()) {
+      if constexpr (EPI == kEpiCol2im) {
+        // the 1x1 GEMM's weights (k_chunks boxes, the same for every item) are loaded once; this thread then takes every
+        // other patch of the input stream (one thread issues one box per ~343 cycles: four boxes per item from one thread
+        // would sit right at the HBM time of an item)
+        const int wrow0 = p.tap_wtap[p.groups[p.cls[0].g_begin].tap_begin] * p.n_total;
+        for (int kc = 0; kc < p.k_chunks; ++kc) {
+          mbar_arrive_expect_tx(&wfull[kc], b_bytes);
+          tma_load_2d(wring + kc * b_bytes, &p.w_map, &wfull[kc], kc * 32, wrow0);
+        }
+        produce_patches(1, 1);
+      } else {
+        if (gdn) {
+          mbar_arrive_expect_tx(gfull, nC * b_bytes);
+          for (int c = 0; c < nC; ++c) tma_load_2d(gmat + c * b_bytes, &p.g_map, gfull, c * 32, 0);
+        }
+        int s = 0;
+        uint32_t s_par = 1;
+        uint8_t* wdst = wring;
+        for (int item = blockIdx.x; item < total; item += gridDim.x) {
+          const TcpItem it = tcp_decode(p, item);
+          const TcpClass cl = p.cls[it.cls];
+          const int t_begin = p.groups[cl.g_begin].tap_begin, t_end = p.groups[cl.g_end - 1].tap_end;   // a class's taps are contiguous
+          for (int kc = 0; kc < p.k_chunks; ++kc) {
+            const int c0 = kc * 32;
+            int wrow = p.tap_wtap[t_begin] * p.n_total;
+            for (int t = t_begin; t < t_end; ++t) {
+              mbar_wait(&wempty[s], s_par);
+              mbar_arrive_expect_tx(&wfull[s], b_bytes);
+              tma_load_2d(wdst, &p.w_map, &wfull[s], c0, wrow);
+              wrow = p.tap_wtap[t + 1] * p.n_total;   // one slack entry
+              if (++s == S) { s = 0; s_par ^= 1; wdst = wring; } else { wdst += b_bytes; }
+            }
           }
         }
       }
     }
+    __syncwarp();
+  } else if (warp == kPPatchWarp) {
+    // ===================== TMA producer: input halo patches =====================
+    if (elect_one_sync()) produce_patches(0, EPI == kEpiCol2im ? 1 : 0);
     __syncwarp();
   } else if (warp == 1) {
     // ===================== main-loop MMA issuer =====================
@@ -800,6 +821,43 @@ __global__ void __launch_bounds__(kPThreads, 1) conv_tcp_kernel(const __grid_con
       long long c_free = 0, n_items = 0, c_ring = 0, c_ring_p = 0;
       const long long c_start = prof ? clock64() : 0;
       bool w_ok = false;                       // result of the early probe of wfull[s]
+      if constexpr (EPI == kEpiCol2im) {
+        // Resident weights, one class, one patch per K-block: the loop needs no item geometry at all.  Per K-block: the
+        // patch wait (normally complete: the ring is deep), four MMAs, one commit.
+        const int g0 = p.cls[0].g_begin;
+        const uint32_t a_hi = (static_cast<uint32_t>(p.groups[g0].sbo_bytes) >> 4) | (1u << 14) | (2u << 29);
+        const uint32_t aoff = static_cast<uint32_t>(p.tap_aoff[p.groups[g0].tap_begin]) >> 4;
+        for (int kc = 0; kc < p.k_chunks; ++kc) mbar_wait(&wfull[kc], 0);
+        for (int item = blockIdx.x; item < total; item += gridDim.x, b ^= 1) {
+          ++n_items;
+          if (!mbar_test_wait(&tmem_free[b], (free_bits >> b) & 1u)) {
+            const long long t0 = clock64();
+            mbar_wait(&tmem_free[b], (free_bits >> b) & 1u);
+            c_free += clock64() - t0;
+          }
+          free_bits ^= 1u << b;
+          const uint32_t d = tmem + b * 256;
+          w_lo = w_lo0;
+          for (int kc = 0; kc < p.k_chunks; ++kc) {
+            const uint64_t ad = (static_cast<uint64_t>(a_hi) << 32) | (p_lo + aoff);
+            const uint64_t bd = (static_cast<uint64_t>(hi_dense) << 32) | w_lo;
+            if (!mbar_test_wait(&pfull[ps], p_par)) {
+              const long long t0 = clock64();
+              mbar_wait(&pfull[ps], p_par);
+              c_ring_p += clock64() - t0;
+            }
+            tc_fence_after_sync();
+            tc_mma_tf32(d, ad, bd, idesc, kc > 0 ? 1u : 0u);
+            tc_mma_tf32(d, ad + 2, bd + 2, idesc, 1u);
+            tc_mma_tf32(d, ad + 4, bd + 4, idesc, 1u);
+            tc_mma_tf32(d, ad + 6, bd + 6, idesc, 1u);
+            tc_commit(&pempty[ps]);
+            w_lo += w_step;
+            if (++ps == P) { ps = 0; p_par ^= 1; p_lo = p_lo0; } else { p_lo += p_step; }
+          }
+          tc_commit(&acc_full[b]);
+        }
+      } else
       for (int item = blockIdx.x; item < total; item += gridDim.x, b ^= 1) {
         const TcpItem it = tcp_decode(p, item);
         const TcpClass cl = p.cls[it.cls];
@@ -966,6 +1024,58 @@ __global__ void __launch_bounds__(kPThreads, 1) conv_tcp_kernel(const __grid_con
         // outputs of the tile interior are gathered from Z (same arithmetic as conv_tc_kernel<kEpiCol2im>)
         float* Zs = reinterpret_cast<float*>(gbuf);
         const int zcols = 25 * p.c2i_nch;
+        const int OH = 2 * p.c2i_in_h, OW = 2 * p.c2i_in_w, nch = p.c2i_nch;
+        constexpr int kIy = kTH - 2, kIx = kTW - 2;
+        if (nch == 3) {
+          // RGB fast path.  The scalar form below measured 5600 cycles per item and group for the gather (27 LDS.32 with
+          // their address arithmetic per output pixel, 128 threads) against ~1900 cycles of HBM time per item: Z rows are
+          // written as 25 x float4 (one STS.128 per tap) and every tap of an output pixel is ONE LDS.128 at a
+          // compile-time offset from a per-thread base.  Same summation order (u outer, v inner) = same bits.
+          {
+            float v[96];
+            tmem_ld32(t_lane, v); tmem_ld32(t_lane + 32, v + 32); tmem_ld32(t_lane + 64, v + 64);
+            tmem_ld_wait();
+            float4* zr = reinterpret_cast<float4*>(Zs + row * kZStride4);
+#pragma unroll
+            for (int t = 0; t < 25; ++t) zr[t] = make_float4(v[3 * t], v[3 * t + 1], v[3 * t + 2], 0.f);
+          }
+          tc_fence_before_sync();
+          named_bar_sync(bar_id, 128);
+          if (leader) mbar_arrive(&tmem_free[b]);
+          if (eprof) e2 = clock64();
+          const int a = (row >> 1) & 1, bb = row & 1;      // o = row + 128 k: the output parity is the thread's own
+          const float b0 = sbias[0], b1 = sbias[1], b2 = sbias[2];
+#pragma unroll
+          for (int k = 0; k < (kIy * kIx * 4 + 127) / 128; ++k) {
+            const int o = row + k * 128;
+            if (o >= kIy * kIx * 4) break;
+            const int cell = o >> 2;
+            const int ti = 1 + cell / kIx, tj = 1 + cell % kIx;
+            const int yi = it.i0 + ti, xj = it.j0 + tj;
+            if (yi >= p.c2i_in_h || xj >= p.c2i_in_w) continue;
+            const float* zb = Zs + ((ti + 1) * kTW + (tj + 1)) * kZStride4 + (a * 5 + bb) * 4;
+            float ax = 0.f, ay = 0.f, az = 0.f;
+#pragma unroll
+            for (int u = 0; u < 3; ++u) {
+#pragma unroll
+              for (int v = 0; v < 3; ++v) {
+                if ((u < 2 || a == 0) && (v < 2 || bb == 0)) {   // kh = a + 2u < 5, kw = b + 2v < 5
+                  const float4 z = *reinterpret_cast<const float4*>(zb - (u * kTW + v) * kZStride4 + (10 * u + 2 * v) * 4);
+                  ax += z.x; ay += z.y; az += z.z;
+                }
+              }
+            }
+            float* dst = p.c2i_out + (((int64_t)it.img * OH + 2 * yi + a) * OW + 2 * xj + bb) * 3;
+            dst[0] = ax + b0; dst[1] = ay + b1; dst[2] = az + b2;
+          }
+          named_bar_sync(bar_id, 128);   // Z is rewritten by this group's next item
+          if (eprof) {
+            long long* q = p.dbg + (int64_t)blockIdx.x * 16 + 9 + grp * 3;   // per group: wait acc, Z tile, gather + stores
+            const long long e4 = clock64();
+            q[0] += e1 - e0; q[1] += e2 - e1; q[2] += e4 - e2;
+          }
+          continue;
+        }
         for (int c = 0; c < nC; ++c) {
           float v[32];
           tmem_ld32(t_lane + c * 32, v);
@@ -977,8 +1087,7 @@ __global__ void __launch_bounds__(kPThreads, 1) conv_tcp_kernel(const __grid_con
         tc_fence_before_sync();
         named_bar_sync(bar_id, 128);
         if (leader) mbar_arrive(&tmem_free[b]);
-        const int OH = 2 * p.c2i_in_h, OW = 2 * p.c2i_in_w, nch = p.c2i_nch;
-        constexpr int kIy = kTH - 2, kIx = kTW - 2;
+        if (eprof) e2 = clock64();
         for (int o = row; o < kIy * kIx * 4; o += 128) {
           const int cell = o >> 2, a = (o >> 1) & 1, b = o & 1;
           const int ti = 1 + cell / kIx, tj = 1 + cell % kIx;
@@ -1003,6 +1112,11 @@ __global__ void __launch_bounds__(kPThreads, 1) conv_tcp_kernel(const __grid_con
             if (c < nch) dst[c] = acc[c] + sbias[c];
         }
         named_bar_sync(bar_id, 128);   // Z is rewritten by this group's next item
+        if (eprof) {
+          long long* q = p.dbg + (int64_t)blockIdx.x * 16 + 9 + grp * 3;   // per group: wait acc, Z tile, gather + stores
+          const long long e4 = clock64();
+          q[0] += e1 - e0; q[1] += e2 - e1; q[2] += e4 - e2;
+        }
         continue;
       }
 
@@ -1818,7 +1932,9 @@ static int build_persistent(const icadv_conv_desc* d, int mode, const Geometry& 
   const bool c2i = mode == kModeCol2im;
   const bool gdn = d->epi != ICADV_EPI_LINEAR;
   const bool bwd = d->epi == ICADV_EPI_GDN_BWD || d->epi == ICADV_EPI_IGDN_BWD;
-  const int N = c2i ? 96 : d->n_ch, K = d->k_ch, s = d->stride;   // col2im: Z has 25 * n_ch <= 96 columns
+  // col2im: Z has 25 * n_ch columns; 80 (the next multiple of 16 above 75) for the RGB case keeps the resident weights
+  // at 10 KB per K-block, which pays for a fifth patch slot
+  const int N = c2i ? (25 * d->n_ch <= 80 && 25 * d->n_ch > 64 ? 80 : 96) : d->n_ch, K = d->k_ch, s = d->stride;
   if (N > 256 || (gdn && N > 128)) return 0;            // 2 TMEM buffers x [acc N | norm N] must fit 512 columns
   const bool tconv2 = !c2i && d->form == ICADV_FORM_TCONV && s == 2;
   // ICADV_TC_STREAM_BWD: 0 = never; unset / 1 = where it measured faster on B200 (profiles/r2_stream_bwd_ab.txt): the
@@ -1972,7 +2088,7 @@ static int build_persistent(const icadv_conv_desc* d, int mode, const Geometry& 
   p.patch_bytes = (max_patch + 1023) & ~1023;
   const int wbytes = N * 128;
   const int gbytes = gdn ? N * N * 4 : 0;
-  p.grp_bytes = c2i ? ((128 * kZStride * 4 + 1023) & ~1023) : 2 * kABytes;
+  p.grp_bytes = c2i ? ((128 * kZStride4 * 4 + 1023) & ~1023) : 2 * kABytes;
   const int fixed = 1024 + kBarBlock + 2 * N * 4 + gbytes + 2 * p.grp_bytes;
   int groups_per_item = 0;
   for (int l = 0; l < p.n_class; ++l) {
@@ -1994,6 +2110,15 @@ static int build_persistent(const icadv_conv_desc* d, int mode, const Geometry& 
   }
   if (S > kMaxStages) S = kMaxStages;
   if (S < 2) return 0;
+  if (c2i) {
+    // the weights of the 1x1 GEMM (k_chunks boxes) stay resident; everything else goes to the patch ring
+    if (n_groups != 1 || n_taps != 1 || p.k_chunks > kMaxStages) return 0;
+    S = p.k_chunks;
+    P = (kSmemLimit - fixed - S * wbytes) / p.patch_bytes;
+    if (P > kMaxPatch) P = kMaxPatch;
+    if (P < 3) return 0;
+    p.w_resident = 1;
+  }
   p.num_patch = P; p.num_stages = S;
   plan->psmem = fixed + P * p.patch_bytes + S * wbytes;
   if (plan->psmem < 120 * 1024) plan->psmem = 120 * 1024;   // one CTA per SM: each allocates all 512 TMEM columns

@@ -72,3 +72,10 @@ yq = torch.randn(n, H // 4, W // 4, Cc, device=dev, generator=gen(9)); sq = 0.5 
 go = torch.empty_like(yq)
 d = ops.make_desc(g4, w, None, go, form=L.FORM_SCONV, ksize=5, stride=2, n_ch=Cc, epi=L.EPI_IGDN_BWD, gmat=gm, y_prev=yq, sc_prev=sq)
 run("g_s.4 dgrad conv + IGDN bwd", d, (g4, w, go, yq, sq))
+# g_s.6 fwd: deconv 128->3 5x5/2 (col2im epilogue) at 256x384 -> 512x768
+x6 = torch.randn(n, H // 2, W // 2, Cc, device=dev, generator=gen(11))
+w6 = torch.randn(25, 3, Cc, device=dev, generator=gen(12)) / 56
+b6 = torch.zeros(3, device=dev)
+o6 = torch.empty(n, H, W, 3, device=dev)
+d = ops.make_desc(x6, w6, b6, o6, form=L.FORM_TCONV, ksize=5, stride=2, n_ch=3)
+run("g_s.6 deconv 128->3 fwd (col2im, persistent)", d, (x6, w6, b6, o6))
