@@ -174,18 +174,49 @@ __global__ void gdn_reparam_kernel(const float* __restrict__ raw, float* __restr
 }
 
 // nn.PixelShuffle(r) on channels-last tensors (compressai subpel_conv3x3): out[n, h*r+i, w*r+j, c] = in[n, h, w, c*r*r + i*r + j]
-// inverse != 0 runs the permutation backwards (its gradient).  One thread per element of the LOW-resolution tensor.
-__global__ void pixel_shuffle_kernel(const float* __restrict__ src, float* __restrict__ dst, int64_t total, int h, int w,
+// inverse != 0 runs the permutation backwards (its gradient).
+// Both sides coalesced: a block takes kShufT consecutive LOW-resolution pixels of one row (one contiguous run of
+// kShufT * c_in floats) through shared memory; each of the r HIGH-resolution rows they map to is again one contiguous run
+// (r * kShufT pixels x c_out floats).  The previous form (one thread per LOW element, 4-byte accesses c_out floats apart on
+// the HIGH side) measured 1.0 TB/s on the cheng2020 upsampling blocks (profiles/r2_bench_config4.json).
+constexpr int kShufT = 8;
+__global__ void pixel_shuffle_kernel(const float* __restrict__ src, float* __restrict__ dst, int n_seg, int h, int w,
                                      int c_out, int r, int inverse) {
+  extern __shared__ float tile[];   // [kShufT][c_in]
   const int c_in = c_out * r * r;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int ci = (int)(i % c_in);
-    const int64_t px = i / c_in;
-    const int x = (int)(px % w), y = (int)((px / w) % h);
-    const int64_t n = px / ((int64_t)w * h);
-    const int c = ci / (r * r), ij = ci % (r * r), di = ij / r, dj = ij % r;
-    const int64_t hi = ((n * h * r + (int64_t)y * r + di) * ((int64_t)w * r) + (int64_t)x * r + dj) * c_out + c;
-    if (inverse) dst[i] = src[hi]; else dst[hi] = src[i];
+  const int segs_x = (w + kShufT - 1) / kShufT;
+  const float* lo_src = inverse ? nullptr : src;
+  const float* hi_src = inverse ? src : nullptr;
+  for (int seg = blockIdx.x; seg < n_seg; seg += gridDim.x) {
+    const int sx = seg % segs_x, y = (seg / segs_x) % h;
+    const int64_t n = seg / ((int64_t)segs_x * h);
+    const int x0 = sx * kShufT, nx = min(kShufT, w - x0);
+    const int64_t lo = ((n * h + y) * (int64_t)w + x0) * c_in;              // first LOW element of the segment
+    const int run = nx * r * c_out;                                          // floats of one HIGH row of the segment
+    if (!inverse) {
+      for (int i = threadIdx.x; i < nx * c_in; i += blockDim.x) tile[i] = lo_src[lo + i];
+      __syncthreads();
+      for (int di = 0; di < r; ++di) {
+        const int64_t hi = ((n * h * r + (int64_t)y * r + di) * ((int64_t)w * r) + (int64_t)x0 * r) * c_out;
+        for (int o = threadIdx.x; o < run; o += blockDim.x) {
+          const int xl = o / c_out, c = o - xl * c_out;
+          const int x = xl / r, dj = xl - x * r;
+          dst[hi + o] = tile[x * c_in + c * r * r + di * r + dj];
+        }
+      }
+    } else {
+      for (int di = 0; di < r; ++di) {
+        const int64_t hi = ((n * h * r + (int64_t)y * r + di) * ((int64_t)w * r) + (int64_t)x0 * r) * c_out;
+        for (int o = threadIdx.x; o < run; o += blockDim.x) {
+          const int xl = o / c_out, c = o - xl * c_out;
+          const int x = xl / r, dj = xl - x * r;
+          tile[x * c_in + c * r * r + di * r + dj] = hi_src[hi + o];
+        }
+      }
+      __syncthreads();
+      for (int i = threadIdx.x; i < nx * c_in; i += blockDim.x) dst[lo + i] = tile[i];
+    }
+    __syncthreads();
   }
 }
 
@@ -209,10 +240,21 @@ extern "C" {
 int icadv_pixel_shuffle(const float* src, float* dst, int n, int h, int w, int c_out, int r, int inverse,
                         icadv_stream_t stream) {
   ICADV_REQUIRE(src && dst && n > 0 && h > 0 && w > 0 && c_out > 0 && r >= 1, "bad pixel_shuffle args");
-  const int64_t total = (int64_t)n * h * w * c_out * r * r;
-  int64_t blocks = (total + 255) / 256;
-  if (blocks > 148 * 16) blocks = 148 * 16;
-  pixel_shuffle_kernel<<<(int)blocks, 256, 0, as_stream(stream)>>>(src, dst, total, h, w, c_out, r, inverse);
+  const int c_in = c_out * r * r;
+  const size_t smem = (size_t)kShufT * c_in * sizeof(float);
+  ICADV_REQUIRE(smem <= 96 * 1024, "pixel_shuffle: c_out * r * r too large");
+  const int64_t n_seg = (int64_t)n * h * ((w + kShufT - 1) / kShufT);
+  ICADV_REQUIRE(n_seg < (1ll << 31), "pixel_shuffle: tensor too large");
+  if (smem > 48 * 1024) {
+    static std::once_flag once;
+    static cudaError_t err = cudaSuccess;
+    std::call_once(once, [] {
+      err = cudaFuncSetAttribute(pixel_shuffle_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+    });
+    if (err != cudaSuccess) { set_error("cudaFuncSetAttribute(pixel_shuffle) failed: %s", cudaGetErrorString(err)); return ICADV_ECUDA; }
+  }
+  int64_t blocks = n_seg < 148 * 8 ? n_seg : 148 * 8;
+  pixel_shuffle_kernel<<<(int)blocks, 256, smem, as_stream(stream)>>>(src, dst, (int)n_seg, h, w, c_out, r, inverse);
   ICADV_CUDA_TRY(cudaGetLastError());
   return ICADV_OK;
 }

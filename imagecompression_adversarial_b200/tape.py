@@ -78,6 +78,16 @@ def _gate_bwd(a, b, g, ga, gb):
     L.call("icadv_attention_gate_backward", _p(a), _p(b), _p(g), _p(ga), _p(gb), a.numel(), _stream())
 
 
+def _copy_ch(src, dst, count):
+    """dst[..., :count] = src[..., :count] (channels-last tensors of any channel counts)."""
+    L.call("icadv_copy_channels", _p(src), _p(dst), src.numel() // src.shape[-1], src.shape[-1], dst.shape[-1], 0, 0, count,
+           _stream())
+
+
+def _pad32(c):
+    return (c + 31) // 32 * 32
+
+
 def _shuffle(src, dst, n, lo_h, lo_w, c_out, r, inverse):
     L.call("icadv_pixel_shuffle", _p(src), _p(dst), n, lo_h, lo_w, c_out, r, 1 if inverse else 0, _stream())
 
@@ -102,6 +112,7 @@ class TapeProgram:
         for nd in self.nodes:
             self.buf[nd["out"]] = f(*nd["shape"])
         self.out = self.buf[out_id]
+        self._out_id = out_id
         self.consumers = {}
         for i, nd in enumerate(self.nodes):
             for t in nd["in"]:
@@ -181,18 +192,38 @@ class TapeProgram:
             rounded_cache[src] = r
         return rounded_cache[src]
 
-    def _pack(self, weight, kind, tc):
-        w = ops.pack_weight(weight, kind, round_tf32=tc)
-        self._weights.append((weight, kind, tc, w))
+    def _pack(self, weight, kind, tc, pad_to=None):
+        """Packed weight [taps][n][k]; ``pad_to = (n32, k32)``: zero-padded to channel counts the tensor path takes."""
+        pk = ops.pack_weight(weight, kind, round_tf32=tc)
+        if pad_to is None:
+            self._weights.append((weight, kind, tc, pk, None))
+            return pk
+        w = torch.zeros(pk.shape[0], pad_to[0], pad_to[1], device=pk.device, dtype=torch.float32)
+        w[:, :pk.shape[1], :pk.shape[2]].copy_(pk)
+        self._weights.append((weight, kind, tc, w, (pk.shape[1], pk.shape[2])))
         return w
+
+    def _padded(self, k_ch, n_ch):
+        """Channel counts the tensor path does not take as they are (RGB ends, the 12-channel sub-pixel conv) but does
+        once zero-padded to multiples of 32: the padded contraction costs a few MB of extra traffic; the CUDA-core
+        kernel it replaces ran at 1 - 5 % of its HBM bound (profiles/r2_bench_config4.json: 8.3 ms for conv 192 -> 12)."""
+        return not self._tc(k_ch, n_ch) and self._tc(_pad32(k_ch), _pad32(n_ch))
+
+    def _padded_input(self, lst, x, k_ch):
+        """[.., k_ch] -> zero-padded, TF32-rounded [.., pad32(k_ch)] copy (the padding channels are written once, here)."""
+        xp = torch.zeros(*x.shape[:-1], _pad32(k_ch), device=x.device, dtype=torch.float32)
+        lst.append(FnLaunch(_copy_ch, x, xp, k_ch))
+        lst.append(FnLaunch(_unary, xp, None, xp, 5))
+        return xp
 
     def refresh_parameters(self):
         """Re-pack weights / re-parametrise GDN in place after a codec update (plans bake the pointers in)."""
-        for weight, kind, tc, w in self._weights:
-            w.copy_(ops.pack_weight(weight, kind, round_tf32=tc))
+        for weight, kind, tc, w, sub in self._weights:
+            pk = ops.pack_weight(weight, kind, round_tf32=tc)
+            (w if sub is None else w[:, :sub[0], :sub[1]]).copy_(pk)
         for nd in self.nodes:
             if nd["kind"] == "conv" and nd.get("bias_buf") is not None:
-                nd["bias_buf"].copy_(nd["bias"].detach())
+                nd["bias_buf"][:nd["bias"].numel()].copy_(nd["bias"].detach())
         for gdn, be, ga, gaT in self._gdn:
             b2, g2, gT2 = gdn.effective_parameters(round_tf32=True)
             be.copy_(b2); ga.copy_(g2); gaT.copy_(gT2)
@@ -226,10 +257,58 @@ class TapeProgram:
                 src = nd["in"][0]
                 k_ch, n_ch = self.buf[src].shape[-1], nd["n_ch"]
                 tc = self._tc(k_ch, n_ch)
+                kind = L.PACK_CONVT_FWD if nd["transposed"] else L.PACK_CONV_FWD
+                if self._padded(k_ch, n_ch):
+                    kp, npad = _pad32(k_ch), _pad32(n_ch)
+                    if kp != k_ch:
+                        x = self._padded_input(self.fwd, self.buf[src], k_ch)
+                    else:
+                        x = self._rounded_source(self.fwd, src, rounded)
+                    w = self._pack(nd["weight"], kind, True, pad_to=(npad, kp))
+                    bias = None
+                    if nd["bias"] is not None:
+                        bias = torch.zeros(npad, device=out.device, dtype=torch.float32)
+                        bias[:n_ch].copy_(nd["bias"].detach())
+                    nd["bias_buf"] = bias
+                    outp = out if npad == n_ch else torch.empty(*out.shape[:-1], npad, device=out.device, dtype=torch.float32)
+                    plan = self._plan(x, w, bias, outp, form=L.FORM_TCONV if nd["transposed"] else L.FORM_SCONV,
+                                      ksize=nd["ksize"], stride=nd["stride"], n_ch=npad, act=nd["act"],
+                                      round_out=npad == n_ch and nd["out"] in self._round_at_producer)
+                    if not isinstance(plan, ops.ConvPlan):
+                        raise L.IcadvError("tape program: padded contraction not taken by the tensor path")
+                    self.fwd.append(plan)
+                    if outp is not out:
+                        self.fwd.append(FnLaunch(_copy_ch, outp, out, n_ch))
+                        self._round_at_producer.discard(nd["out"])
+                        for c in self.consumers.get(nd["out"], []):
+                            if self.nodes[c]["kind"] == "shuffle":
+                                self._round_at_producer.discard(self.nodes[c]["out"])
+                    continue
                 x = self._rounded_source(self.fwd, src, rounded) if tc else self.buf[src]
-                w = self._pack(nd["weight"], L.PACK_CONVT_FWD if nd["transposed"] else L.PACK_CONV_FWD, tc)
+                w = self._pack(nd["weight"], kind, tc)
                 bias = nd["bias"].detach().contiguous().clone() if nd["bias"] is not None else None
                 nd["bias_buf"] = bias
+                # conv -> (I)GDN with nothing else reading the conv output: the normalisation rides in the contraction's
+                # epilogue (the same fused form program.StackProgram uses); the GDN node keeps only its backward launch
+                cons = self.consumers.get(nd["out"], [])
+                gnd = self.nodes[cons[0]] if len(cons) == 1 and self.nodes[cons[0]]["kind"] == "gdn" else None
+                if tc and gnd is not None and nd["act"] == L.ACT_NONE and n_ch <= 256 and nd["out"] != self._out_id:
+                    g = gnd["module"]
+                    be, ga, gaT = g.effective_parameters(round_tf32=True)
+                    gout = self.buf[gnd["out"]]
+                    sc = torch.empty_like(gout)
+                    try:
+                        plan = self._plan(x, w, bias, gout, form=L.FORM_TCONV if nd["transposed"] else L.FORM_SCONV,
+                                          ksize=nd["ksize"], stride=nd["stride"], n_ch=n_ch,
+                                          epi=L.EPI_IGDN_FWD if g.inverse else L.EPI_GDN_FWD, gmat=ga, beta=be, out_scale=sc,
+                                          round_out=gnd["out"] in self._round_at_producer)
+                    except L.IcadvError:
+                        plan = None
+                    if isinstance(plan, ops.ConvPlan):
+                        self._gdn.append((g, be, ga, gaT))
+                        gnd["gaT"], gnd["sc"], gnd["fused_fwd"] = gaT, sc, True
+                        self.fwd.append(plan)
+                        continue
                 plan = self._plan(x, w, bias, out, form=L.FORM_TCONV if nd["transposed"] else L.FORM_SCONV,
                                   ksize=nd["ksize"], stride=nd["stride"], n_ch=n_ch, act=nd["act"],
                                   round_out=nd["out"] in self._round_at_producer)
@@ -241,6 +320,8 @@ class TapeProgram:
                             self._round_at_producer.discard(self.nodes[c]["out"])
                 self.fwd.append(plan)
             elif nd["kind"] == "gdn":
+                if nd.get("fused_fwd"):
+                    continue
                 g = nd["module"]
                 be, ga, gaT = g.effective_parameters(round_tf32=True)
                 self._gdn.append((g, be, ga, gaT))
@@ -292,11 +373,16 @@ class TapeProgram:
                     self.bwd.append(FnLaunch(_act_bwd, self.buf[nd["out"]], g, gz, nd["act"]))
                     g = gz
                 tc = self._tc(g.shape[-1], k_ch)
-                if tc:
+                padded = self._padded(g.shape[-1], k_ch)
+                if padded and g.shape[-1] % 32:
+                    g = self._padded_input(self.bwd, g, g.shape[-1])
+                elif tc or padded:
                     gr = torch.empty_like(g)
                     self.bwd.append(FnLaunch(_unary, g, None, gr, 5))
                     g = gr
-                w = self._pack(nd["weight"], L.PACK_CONVT_DGRAD if nd["transposed"] else L.PACK_CONV_DGRAD, tc)
+                dkind = L.PACK_CONVT_DGRAD if nd["transposed"] else L.PACK_CONV_DGRAD
+                w = self._pack(nd["weight"], dkind, True, pad_to=(_pad32(k_ch), g.shape[-1])) if padded else \
+                    self._pack(nd["weight"], dkind, tc)
                 if not nd["transposed"] and nd["ksize"] < nd["stride"]:
                     # input gradient of a strided 1x1 conv: the pixels no tap reaches are never written and stay zero
                     dst = torch.zeros_like(self.buf[src])
@@ -304,8 +390,17 @@ class TapeProgram:
                     dst = self.g_in
                 else:
                     dst = torch.empty_like(self.buf[src])
-                self.bwd.append(self._plan(g, w, None, dst, form=L.FORM_SCONV if nd["transposed"] else L.FORM_TCONV,
-                                           ksize=nd["ksize"], stride=nd["stride"], n_ch=k_ch))
+                if padded and k_ch % 32:
+                    dstp = torch.zeros(*dst.shape[:-1], _pad32(k_ch), device=dst.device, dtype=torch.float32)
+                    plan = self._plan(g, w, None, dstp, form=L.FORM_SCONV if nd["transposed"] else L.FORM_TCONV,
+                                      ksize=nd["ksize"], stride=nd["stride"], n_ch=_pad32(k_ch))
+                    if not isinstance(plan, ops.ConvPlan):
+                        raise L.IcadvError("tape program: padded contraction not taken by the tensor path")
+                    self.bwd.append(plan)
+                    self.bwd.append(FnLaunch(_copy_ch, dstp, dst, k_ch))
+                else:
+                    self.bwd.append(self._plan(g, w, None, dst, form=L.FORM_SCONV if nd["transposed"] else L.FORM_TCONV,
+                                               ksize=nd["ksize"], stride=nd["stride"], n_ch=k_ch))
                 contrib.setdefault(src, []).append(dst)
             elif nd["kind"] == "gdn":
                 dst = torch.empty_like(self.buf[src])
