@@ -20,7 +20,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
 // register set, 3 pipelined order with two register sets, 4 no waits (producers off) but commits, 5 bare (no waits, no
 // commits), 6 two K-blocks per pass (two waits, eight MMAs, two commits), 7 as 1 with the wait AFTER the descriptors are
 // in uniform registers (asm barrier), 8 as 6 with four K-blocks per pass
-template <int V>
+template <int V, int ONEWARP = 0>
 __global__ void __launch_bounds__(160) probe(const __grid_constant__ CUtensorMap map, int kblocks, int S, int np, int n_boxes_total,
                                              long long* out) {
   extern __shared__ uint8_t raw[];
@@ -155,7 +155,24 @@ __global__ void __launch_bounds__(160) probe(const __grid_constant__ CUtensorMap
       out[blockIdx.x * 2] = clock64() - t0;
       out[blockIdx.x * 2 + 1] = 0;
     }
-  } else if (warp <= np && producers) {
+  } else if (ONEWARP && warp == 1 && producers) {
+    // both producing threads live in ONE warp (lanes 0 .. np - 1 on divergent paths)
+    const int me = threadIdx.x & 31;
+    if (me < np) {
+      int s = 0, owner = 0;
+      uint32_t par = 1;
+      for (int k = 0; k < kblocks; ++k) {
+        if (owner == me) {
+          mbar_wait(&empty[s], par);
+          mbar_arrive_expect_tx(&full[s], 16384);
+          const int box = (blockIdx.x * kblocks + k) & (n_boxes_total - 1);
+          tma_load_2d(R + s * 16384, &map, &full[s], 0, box * 128);
+        }
+        if (++s == S) { s = 0; par ^= 1; }
+        if (++owner == np) owner = 0;
+      }
+    }
+  } else if (!ONEWARP && warp <= np && producers) {
     if (elect_one_sync()) {
       const int me = warp - 1;
       int s = 0, owner = 0;
@@ -177,14 +194,14 @@ __global__ void __launch_bounds__(160) probe(const __grid_constant__ CUtensorMap
   if (warp == 0) tmem_dealloc(tmem, 128);
 }
 
-template <int V>
+template <int V, int ONEWARP = 0>
 void run(const CUtensorMap& map, int n_boxes, long long* d_out, const char* name) {
   for (int S : {3, 5, 8})
     for (int np : {1, 2}) {
       const int smem_p = (S + 1) * 16384 + 256 + 1024, kblocks = 4096;
       const int smem_use = smem_p < 120 * 1024 ? 120 * 1024 : smem_p;
-      cudaFuncSetAttribute(probe<V>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_use);
-      for (int rep = 0; rep < 2; ++rep) probe<V><<<148, 160, smem_use>>>(map, kblocks, S, np, n_boxes, d_out);
+      cudaFuncSetAttribute(probe<V, ONEWARP>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_use);
+      for (int rep = 0; rep < 2; ++rep) probe<V, ONEWARP><<<148, 160, smem_use>>>(map, kblocks, S, np, n_boxes, d_out);
       cudaError_t e = cudaDeviceSynchronize();
       if (e != cudaSuccess) { printf("CUDA error: %s\n", cudaGetErrorString(e)); exit(1); }
       std::vector<long long> h(296);
@@ -222,6 +239,7 @@ int main() {
   run<2>(map, nb, d_out, "pipelined order, one register set");
   run<3>(map, nb, d_out, "pipelined order, two register sets");
   run<6>(map, nb, d_out, "two K-blocks per pass (2 waits, 8 MMAs, 2 commits)");
-  run<8>(map, nb, d_out, "four K-blocks per pass (4 waits, 16 MMAs, 4 commits)");
+  run<0, 1>(map, nb, d_out, "naive, producers = lanes of ONE warp");
+  run<7, 1>(map, nb, d_out, "bare try_wait spin, producers = lanes of ONE warp");
   return 0;
 }
