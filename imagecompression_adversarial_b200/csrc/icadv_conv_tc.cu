@@ -75,7 +75,8 @@ struct TcParams {
   const int* active;
   const int* n_active;
   int bwd_lookahead;   // backward epilogues: L2-prefetch the saved tensors of the CTA this many launch slots ahead (0 = off)
-  int dbg_flags;    // developer switches (env ICADV_TC_DBG): 1 = no prefetch of saved y/scale, 2 = single-buffered stores
+  int dbg_flags;    // developer switches (env ICADV_TC_DBG): 1 = no prefetch of saved y/scale, 2 = single-buffered stores,
+                    // 16 = weight boxes not loaded (timing experiment: what the weight stream costs; results are garbage)
   long long* dbg;   // optional per-CTA phase timestamps (16 slots per CTA), developer profiling only
 };
 
@@ -243,8 +244,12 @@ __global__ void __launch_bounds__(kThreads, 2) conv_tc_kernel(const __grid_const
             if (p.dbg != nullptr) { const long long t0 = clock64(); mbar_wait(&empty[s], s_par); t_wait_e += clock64() - t0; }
             else mbar_wait(&empty[s], s_par);
             if (elect_one_sync()) {
-              mbar_arrive_expect_tx(&full[s], b_bytes);
-              tma_load_2d(wdst, &p.w_map, &full[s], c0, wrow);
+              if (p.dbg_flags & 16) {   // developer experiment: the stage is handed over without loading the weights
+                mbar_arrive(&full[s]);
+              } else {
+                mbar_arrive_expect_tx(&full[s], b_bytes);
+                tma_load_2d(wdst, &p.w_map, &full[s], c0, wrow);
+              }
             }
             wrow = wrow_next;
             if (++s == S) { s = 0; s_par ^= 1; wdst = wring; } else { wdst += b_bytes; }
