@@ -657,6 +657,7 @@ struct TcpParams {
   int ys_slots;     // streaming backward kernel: slots of the saved-tensor ring (each [y chunk | scale chunk] = 32 KB)
   float* out;       // streaming backward kernel: dense output base (plain 128-byte stores per pixel and chunk)
   int w_resident;   // col2im: the k_chunks weight boxes of the 1x1 GEMM are loaded once and stay in shared memory
+  int dbg_skip_w;   // developer experiment (ICADV_TC_DBG bit 16): weight boxes are not loaded (timing only, results garbage)
 };
 
 struct TcpItem { int img, i0, j0, cls; };
@@ -1393,8 +1394,12 @@ __global__ void __launch_bounds__(kPThreads, 1) conv_tcb_kernel(const __grid_con
           int wrow = p.tap_wtap[t_begin] * p.n_total;
           for (int t = t_begin; t < t_end; ++t) {
             mbar_wait(&wempty[s], s_par);
-            mbar_arrive_expect_tx(&wfull[s], b_bytes);
-            tma_load_2d(wdst, &p.w_map, &wfull[s], c0, wrow);
+            if (p.dbg_skip_w) {   // developer experiment (ICADV_TC_DBG bit 16): stage handed over without loading the weights
+              mbar_arrive(&wfull[s]);
+            } else {
+              mbar_arrive_expect_tx(&wfull[s], b_bytes);
+              tma_load_2d(wdst, &p.w_map, &wfull[s], c0, wrow);
+            }
             wrow = p.tap_wtap[t + 1] * p.n_total;   // one slack entry
             if (++s == S) { s = 0; s_par ^= 1; wdst = wring; } else { wdst += b_bytes; }
           }
@@ -2051,6 +2056,7 @@ static int build_persistent(const icadv_conv_desc* d, int mode, const Geometry& 
   p.yprev = d->y_prev; p.scprev = d->sc_prev; p.bias = d->bias; p.beta = d->beta;
   p.active = d->active; p.n_active = d->n_active;
   p.out = d->out;
+  p.dbg_skip_w = (getenv("ICADV_TC_DBG") != nullptr && (atoi(getenv("ICADV_TC_DBG")) & 16)) ? 1 : 0;
   if (stream) {
     // ---- streaming backward kernel: [patch ring | weight ring | gamma^T ring | saved-tensor ring R x 32 KB | staging | barriers + bias]
     p.patch_bytes = (max_patch + 1023) & ~1023;
