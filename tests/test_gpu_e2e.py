@@ -582,16 +582,49 @@ def test_mean_scale_hyperprior_runs(dev):
     assert bool(torch.isfinite(x.grad).all()) and float(x.grad.abs().max()) > 0
 
 
+def test_traced_program_pads_small_channel_contractions(dev):
+    """3 -> 64 (3x3/2) and 64 -> 12 (+ PixelShuffle): channel counts the tensor path does not take as they are run
+    zero-padded to 32 on it inside a traced program; forward and input gradient against the module walk (fp32 CUDA-core
+    kernels for these shapes) at the TF32 level."""
+    import torch.nn as nn
+    from imagecompression_adversarial_b200 import models as pm
+    from imagecompression_adversarial_b200 import ops
+    from imagecompression_adversarial_b200.tape import TapeProgram
+    torch.manual_seed(0)
+    stack = nn.Sequential(pm.conv3x3(3, 64, 2), pm.subpel_conv3x3(64, 3, 2)).to(dev).train()
+    n, h, w = 2, 64, 96
+    x = torch.rand(n, 3, h, w, device=dev)
+    xi = x.clone().requires_grad_(True)
+    out = stack(xi)
+    gout = torch.randn_like(out)
+    out.backward(gout)
+    tp = TapeProgram(stack, n, h, w, dev)
+    assert all(isinstance(p, ops.ConvPlan) for p in tp.fwd + tp.bwd if hasattr(p, "desc") or hasattr(p, "_d"))
+    tp.x_in.copy_(x.permute(0, 2, 3, 1))
+    tp.forward()
+    tp.g_out.copy_(gout.permute(0, 2, 3, 1))
+    tp.backward()
+    rel = lambda a, b: float((a - b).pow(2).sum().sqrt() / b.pow(2).sum().sqrt())
+    assert rel(tp.out.permute(0, 3, 1, 2), out.detach()) < 2e-3
+    assert rel(tp.g_in.permute(0, 3, 1, 2), xi.grad) < 2e-3
+
+
 def test_traced_program_equals_module_walk(dev):
     """cheng2020_anchor g_s(g_a(x)) and its input gradient: the traced static launch program (activations fused into
     contraction epilogues, rounding at the producer, summed skip gradients) against the same modules walked through
-    autograd -- the same kernels in a different arrangement, so they agree to fp32 round-off; and the engine built on it
-    replays from a CUDA graph bit for bit."""
+    autograd.  The traced program runs the small-channel contractions (the 3x3/2 RGB ends, the 12-channel sub-pixel conv)
+    zero-padded on the tensor path (TF32-rounded operands) and fuses conv -> (I)GDN into the contraction epilogue, where
+    the module walk uses the fp32 CUDA-core kernel and a stand-alone GDN launch: the two agree to the speed mode's TF32
+    level (the bound below), not to fp32 round-off; the engine built on it replays from a CUDA graph bit for bit."""
     from imagecompression_adversarial_b200 import models as pm
     from imagecompression_adversarial_b200.engine import TapeAttackEngine
     from imagecompression_adversarial_b200.tape import TapeProgram
     torch.manual_seed(0)
     net = pm.init_model("cheng2020", 1, "mse", pretrained=False).to(dev).train()
+    with torch.no_grad():   # 0.6 x the kaiming weights keeps the activations O(1) (a random-init cheng2020 amplifies to 1e9,
+        for name, m in net.named_modules():   # and with it every rounding difference of the input gradient)
+            if getattr(m, "weight", None) is not None and m.weight.dim() == 4 and name.startswith(("g_a", "g_s")):
+                m.weight.mul_(0.6)
     n, h, w = 2, 64, 96
     x = torch.rand(n, 3, h, w, device=dev)
     xi = x.clone().requires_grad_(True)
@@ -606,9 +639,12 @@ def test_traced_program_equals_module_walk(dev):
     gs.g_out.copy_(gout.permute(0, 2, 3, 1))
     gs.backward(); ga.backward()
     rel = lambda a, b: float((a - b).pow(2).sum().sqrt() / b.pow(2).sum().sqrt())
-    assert rel(ga.out.permute(0, 3, 1, 2), y.detach()) < 1e-5
-    assert rel(gs.out.permute(0, 3, 1, 2), out.detach()) < 1e-5
-    assert rel(ga.g_in.permute(0, 3, 1, 2), xi.grad) < 1e-5
+    assert rel(ga.out.permute(0, 3, 1, 2), y.detach()) < 3e-3
+    assert rel(gs.out.permute(0, 3, 1, 2), out.detach()) < 3e-3
+    # input gradient through ~35 TF32 contractions and six (I)GDN layers: measured 4.1 % between the two arrangements over
+    # both stacks (1.8 % over g_a alone, where each is 1.4 - 1.8 % from the fp32 oracle: scripts/debug_pad_tape.py); the
+    # padded contractions themselves are pinned at 2e-3 by test_traced_program_pads_small_channel_contractions
+    assert rel(ga.g_in.permute(0, 3, 1, 2), xi.grad) < 8e-2
     # fewer launches than operators: every LeakyReLU of the blocks rides in a contraction epilogue
     kinds = [nd["kind"] for nd in ga.nodes + gs.nodes]
     assert "act" not in kinds, kinds
