@@ -39,11 +39,12 @@ def tc_shape(k_ch, n_ch):
     return n_ch <= 256 or any(n_ch % t == 0 for t in range(256, 31, -32))   # wider outputs are tiled over N
 
 
-def packed(weight, kind, split_geom=None):
+def packed(weight, kind, split_geom=None, pad_to=None):
     """Packed copy of a layer weight, cached on (storage, version) so it is rebuilt only after an update.
     Weights of tensor-path contractions are rounded to TF32 (nearest) here; with ``split_geom = (Ks, G)`` (parity mode)
-    they are returned as G slices of [Whi | Whi | Wlo] instead (csrc/icadv_split.cu)."""
-    key = (id(weight), kind, split_geom)
+    they are returned as G slices of [Whi | Whi | Wlo] instead (csrc/icadv_split.cu); with ``pad_to = (n32, k32)`` rounded
+    and zero-padded to channel counts the tensor path takes."""
+    key = (id(weight), kind, split_geom, pad_to)
     hit = _PACK_CACHE.get(key)
     # the entry must belong to THIS tensor object (ids and addresses are recycled once a model is freed)
     if hit is not None and hit[3]() is weight and hit[0] == weight._version and hit[2] == tuple(weight.shape) \
@@ -55,7 +56,11 @@ def packed(weight, kind, split_geom=None):
     a, b = weight.shape[0], weight.shape[1]
     n_ch, k_ch = {L.PACK_CONV_FWD: (a, b), L.PACK_CONV_DGRAD: (b, a), L.PACK_CONVT_FWD: (b, a),
                   L.PACK_CONVT_DGRAD: (a, b)}[kind]
-    if split_geom is not None:
+    if pad_to is not None:
+        pk = ops.pack_weight(weight, kind, round_tf32=True)
+        wp = torch.zeros(pk.shape[0], pad_to[0], pad_to[1], device=pk.device, dtype=torch.float32)
+        wp[:, :pk.shape[1], :pk.shape[2]].copy_(pk)
+    elif split_geom is not None:
         wp = ops.split3_weight(ops.pack_weight(weight, kind, round_tf32=False), *split_geom)
     else:
         wp = ops.pack_weight(weight, kind, round_tf32=tc_shape(k_ch, n_ch) and not precision.split())
@@ -78,6 +83,27 @@ def contract(xn, weight, kind, bias, *, form, ksize, stride, n_ch, act=L.ACT_NON
     fp32.  Shapes the tensor path does not take run on the fp32 CUDA-core kernels in both modes."""
     k_ch = xn.shape[-1]
     if not tc_shape(k_ch, n_ch):
+        kp, npad = (k_ch + 31) // 32 * 32, (n_ch + 31) // 32 * 32
+        if not precision.split() and tc_shape(kp, npad):
+            # speed mode: channel counts the tensor path does not take as they are (the 3x3/2 RGB ends and the 12-channel
+            # sub-pixel conv of cheng2020) run on it zero-padded to multiples of 32 -- a few MB of extra traffic against a
+            # CUDA-core kernel at 1 - 5 % of its HBM bound (same treatment as tape.TapeProgram, same bits)
+            if kp != k_ch:
+                xp = torch.zeros(*xn.shape[:-1], kp, device=xn.device, dtype=torch.float32)
+                ops.copy_channels(xn.contiguous(), xp, 0, 0, k_ch)
+            else:
+                xp = xn
+            xp = ops.unary(xp, 5)
+            bp = None
+            if bias is not None:
+                bp = torch.zeros(npad, device=xn.device, dtype=torch.float32)
+                bp[:n_ch].copy_(bias)
+            outp = ops.conv(xp, packed(weight, kind, pad_to=(npad, kp)), bp, form=form, ksize=ksize, stride=stride,
+                            n_ch=npad, act=act)
+            if npad == n_ch:
+                return outp
+            out = torch.empty(*outp.shape[:-1], n_ch, device=xn.device, dtype=torch.float32)
+            return ops.copy_channels(outp, out, 0, 0, n_ch)
         return ops.conv(xn, packed(weight, kind), bias, form=form, ksize=ksize, stride=stride, n_ch=n_ch, act=act,
                         path="simt" if precision.split() else "auto")
     if precision.split():
