@@ -157,38 +157,63 @@ __global__ void sum_ws_kernel(const float* __restrict__ ws, float* __restrict__ 
 }
 
 // elementwise helpers at the operator surface: 0 abs, 1 relu, 2 leaky(0.01), 3 round, 4 add (y = x + b), 5 round to TF32,
-// 6 clamp to [0, 1] (torch.clamp of attack_rd.py:411, self_ensemble.py:182,207)
-__global__ void unary_kernel(const float* __restrict__ x, const float* __restrict__ b, float* __restrict__ y, int64_t n,
-                             int op) {
+// 6 clamp to [0, 1] (torch.clamp of attack_rd.py:411, self_ensemble.py:182,207), 7 copy; + 256: the result is rounded to TF32
+// on store (its only readers are tensor-path contractions: saves their separate rounding pass)
+template <int OP, bool RND>
+__device__ __forceinline__ void unary_loop(const float* __restrict__ x, const float* __restrict__ b, float* __restrict__ y,
+                                           int64_t n) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     const float v = x[i];
     float r;
-    switch (op) {
-      case 0: r = fabsf(v); break;
-      case 1: r = fmaxf(v, 0.f); break;
-      case 2: r = v > 0.f ? v : 0.01f * v; break;
-      case 3: r = rintf(v); break;
-      case 5: r = round_tf32(v); break;
-      case 6: r = fminf(fmaxf(v, 0.f), 1.f); break;
-      case 7: r = v; break;
-      default: r = v + b[i]; break;
-    }
-    y[i] = r;
+    if (OP == 0) r = fabsf(v);
+    else if (OP == 1) r = fmaxf(v, 0.f);
+    else if (OP == 2) r = v > 0.f ? v : 0.01f * v;
+    else if (OP == 3) r = rintf(v);
+    else if (OP == 5) r = round_tf32(v);
+    else if (OP == 6) r = fminf(fmaxf(v, 0.f), 1.f);
+    else if (OP == 7) r = v;
+    else r = v + b[i];
+    y[i] = RND ? round_tf32(r) : r;
+  }
+}
+// the operation is resolved OUTSIDE the element loop (one specialised loop per op: a switch inside the loop cost 1.6x on
+// these bandwidth-bound passes)
+__global__ void unary_kernel(const float* __restrict__ x, const float* __restrict__ b, float* __restrict__ y, int64_t n,
+                             int op) {
+  const bool rnd = (op & 256) != 0;
+  switch (op & 255) {
+    case 0: rnd ? unary_loop<0, true>(x, b, y, n) : unary_loop<0, false>(x, b, y, n); break;
+    case 1: rnd ? unary_loop<1, true>(x, b, y, n) : unary_loop<1, false>(x, b, y, n); break;
+    case 2: rnd ? unary_loop<2, true>(x, b, y, n) : unary_loop<2, false>(x, b, y, n); break;
+    case 3: unary_loop<3, false>(x, b, y, n); break;
+    case 5: unary_loop<5, false>(x, b, y, n); break;
+    case 6: rnd ? unary_loop<6, true>(x, b, y, n) : unary_loop<6, false>(x, b, y, n); break;
+    case 7: rnd ? unary_loop<7, true>(x, b, y, n) : unary_loop<7, false>(x, b, y, n); break;
+    default: rnd ? unary_loop<4, true>(x, b, y, n) : unary_loop<4, false>(x, b, y, n); break;
   }
 }
 
-// gradient of abs / relu / leaky given the forward INPUT (or, for relu/leaky, equivalently the output)
-__global__ void act_backward_kernel(const float* __restrict__ x, const float* __restrict__ g, float* __restrict__ gx,
-                                    int64_t n, int op) {
+template <int OP, bool RND>
+__device__ __forceinline__ void act_backward_loop(const float* __restrict__ x, const float* __restrict__ g,
+                                                  float* __restrict__ gx, int64_t n) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     const float v = x[i], gv = g[i];
     float r;
-    switch (op) {
-      case 0: r = v > 0.f ? gv : (v < 0.f ? -gv : 0.f); break;
-      case 1: r = v > 0.f ? gv : 0.f; break;
-      default: r = v > 0.f ? gv : 0.01f * gv; break;
-    }
-    gx[i] = r;
+    if (OP == 0) r = v > 0.f ? gv : (v < 0.f ? -gv : 0.f);
+    else if (OP == 1) r = v > 0.f ? gv : 0.f;
+    else r = v > 0.f ? gv : 0.01f * gv;
+    gx[i] = RND ? round_tf32(r) : r;
+  }
+}
+// gradient of abs / relu / leaky given the forward INPUT (or, for relu/leaky, equivalently the output); + 256: gradient
+// rounded to TF32 on store (it feeds a tensor-path input gradient)
+__global__ void act_backward_kernel(const float* __restrict__ x, const float* __restrict__ g, float* __restrict__ gx,
+                                    int64_t n, int op) {
+  const bool rnd = (op & 256) != 0;
+  switch (op & 255) {
+    case 0: rnd ? act_backward_loop<0, true>(x, g, gx, n) : act_backward_loop<0, false>(x, g, gx, n); break;
+    case 1: rnd ? act_backward_loop<1, true>(x, g, gx, n) : act_backward_loop<1, false>(x, g, gx, n); break;
+    default: rnd ? act_backward_loop<2, true>(x, g, gx, n) : act_backward_loop<2, false>(x, g, gx, n); break;
   }
 }
 
@@ -274,7 +299,7 @@ int icadv_gc_forward(const float* y, const float* scales, const float* means, co
 }
 
 int icadv_unary(const float* x, const float* b, float* y, int64_t n, int op, icadv_stream_t stream) {
-  ICADV_REQUIRE(x && y && op >= 0 && op <= 7 && (op != 4 || b), "bad unary args");
+  ICADV_REQUIRE(x && y && op >= 0 && (op & 255) <= 7 && (op & ~511) == 0 && ((op & 255) != 4 || b), "bad unary args");
   int64_t blocks = (n + 255) / 256;
   if (blocks > 148 * 16) blocks = 148 * 16;
   if (blocks < 1) blocks = 1;
@@ -284,7 +309,7 @@ int icadv_unary(const float* x, const float* b, float* y, int64_t n, int op, ica
 }
 
 int icadv_act_backward(const float* x, const float* g, float* gx, int64_t n, int op, icadv_stream_t stream) {
-  ICADV_REQUIRE(x && g && gx && op >= 0 && op <= 2, "bad act_backward args");
+  ICADV_REQUIRE(x && g && gx && op >= 0 && (op & 255) <= 2 && (op & ~511) == 0, "bad act_backward args");
   int64_t blocks = (n + 255) / 256;
   if (blocks > 148 * 16) blocks = 148 * 16;
   if (blocks < 1) blocks = 1;

@@ -66,8 +66,8 @@ def _unary(x, b, y, op):
     L.call("icadv_unary", _p(x), _p(b), _p(y), x.numel(), int(op), _stream())
 
 
-def _act_bwd(x, g, gx, act):
-    L.call("icadv_act_backward", _p(x), _p(g), _p(gx), x.numel(), _UN[act], _stream())
+def _act_bwd(x, g, gx, act, rnd=False):
+    L.call("icadv_act_backward", _p(x), _p(g), _p(gx), x.numel(), _UN[act] | (256 if rnd else 0), _stream())
 
 
 def _gate(a, b, x, y):
@@ -349,34 +349,50 @@ class TapeProgram:
     # ------------------------------------------------------------------ backward (to the input)
     def _build_backward(self, in_id, out_id):
         contrib = {out_id: [self.g_out]}            # gradient contributions per tensor, one per consumer
+        rounded_g = set()                           # gradient buffers whose producer already rounded them to TF32
 
-        def grad_of(t):
-            """One buffer holding dL/dt: the contributions of several consumers are summed by add launches."""
+        def grad_of(t, want_round=False):
+            """One buffer holding dL/dt: the contributions of several consumers are summed by add launches (the last one
+            rounds to TF32 on store when the only reader is a tensor-path input gradient)."""
             parts = contrib.get(t)
             if not parts:
                 raise L.IcadvError("tape program: a tensor of the stack has no path to the output")
             acc = parts[0]
-            for extra in parts[1:]:
+            for i, extra in enumerate(parts[1:]):
                 dst = torch.empty_like(acc)
-                self.bwd.append(FnLaunch(_unary, acc, extra, dst, 4))
+                last = want_round and i == len(parts) - 2
+                self.bwd.append(FnLaunch(_unary, acc, extra, dst, 4 | (256 if last else 0)))
+                if last:
+                    rounded_g.add(dst.data_ptr())
                 acc = dst
             return acc
 
+        def rounds_its_gradient(nd):
+            """A conv node whose input-gradient launch reads dL/d(out) as a plain TF32-rounded tensor (no activation
+            gradient in between, no channel padding of the gradient)."""
+            if nd["kind"] != "conv" or nd["act"] != L.ACT_NONE:
+                return False
+            n_out, k_in = self.buf[nd["out"]].shape[-1], self.buf[nd["in"][0]].shape[-1]
+            return self._tc(n_out, k_in) or (self._padded(n_out, k_in) and n_out % 32 == 0)
+
         single_input_use = len(self.consumers.get(in_id, [])) == 1
         for nd in reversed(self.nodes):
-            g = grad_of(nd["out"])
+            g = grad_of(nd["out"], want_round=rounds_its_gradient(nd))
             src = nd["in"][0]
             if nd["kind"] == "conv":
                 k_ch = self.buf[src].shape[-1]
-                if nd["act"] != L.ACT_NONE:         # activation fused into the forward epilogue: its gradient from the output
-                    gz = torch.empty_like(g)
-                    self.bwd.append(FnLaunch(_act_bwd, self.buf[nd["out"]], g, gz, nd["act"]))
-                    g = gz
                 tc = self._tc(g.shape[-1], k_ch)
                 padded = self._padded(g.shape[-1], k_ch)
+                plain_round = tc or (padded and g.shape[-1] % 32 == 0)
+                if nd["act"] != L.ACT_NONE:         # activation fused into the forward epilogue: its gradient from the output,
+                    gz = torch.empty_like(g)        # rounded on store when the input gradient reads it as it is
+                    self.bwd.append(FnLaunch(_act_bwd, self.buf[nd["out"]], g, gz, nd["act"], plain_round))
+                    if plain_round:
+                        rounded_g.add(gz.data_ptr())
+                    g = gz
                 if padded and g.shape[-1] % 32:
                     g = self._padded_input(self.bwd, g, g.shape[-1])
-                elif tc or padded:
+                elif plain_round and g.data_ptr() not in rounded_g:
                     gr = torch.empty_like(g)
                     self.bwd.append(FnLaunch(_unary, g, None, gr, 5))
                     g = gr
@@ -405,9 +421,14 @@ class TapeProgram:
             elif nd["kind"] == "gdn":
                 dst = torch.empty_like(self.buf[src])
                 gm = nd["module"]
+                # dL/d(conv out) goes straight into that conv's input-gradient launch: rounded on store
+                pi = self.producer.get(src)
+                rnd = pi is not None and len(self.consumers.get(src, [])) == 1 and rounds_its_gradient(self.nodes[pi])
                 self.bwd.append(self._plan(g, None, None, dst, form=L.FORM_SCONV, ksize=1, stride=1, n_ch=dst.shape[-1],
                                            epi=L.EPI_IGDN_BWD if gm.inverse else L.EPI_GDN_BWD, gmat=nd["gaT"],
-                                           y_prev=self.buf[nd["out"]], sc_prev=nd["sc"], acc_from_in=True))
+                                           y_prev=self.buf[nd["out"]], sc_prev=nd["sc"], acc_from_in=True, round_out=rnd))
+                if rnd:
+                    rounded_g.add(dst.data_ptr())
                 contrib.setdefault(src, []).append(dst)
             elif nd["kind"] == "act":
                 dst = torch.empty_like(g)

@@ -269,9 +269,11 @@ int icadv_gc_forward(const float* y, const float* scales, const float* means, co
                      float scale_bound, float lik_bound, float bits_floor, icadv_stream_t stream);
 /* elementwise helpers: op 0 abs (h_a(|y|), anchors/balle.py:38), 1 relu, 2 leaky 0.01, 3 round, 4 y = x + b,
  * 5 round-to-nearest TF32 (operand preparation for the tensor path), 6 clamp to [0,1] (attack_rd.py:411,
- * self_ensemble.py:182,207), 7 copy */
+ * self_ensemble.py:182,207), 7 copy; op + 256: the result is rounded to TF32 on store (its readers are tensor-path
+ * contractions) */
 int icadv_unary(const float* x, const float* b, float* y, int64_t n, int op, icadv_stream_t stream);
-/* gradient of op 0 abs / 1 relu / 2 leaky given the forward input (relu/leaky: or the output) */
+/* gradient of op 0 abs / 1 relu / 2 leaky given the forward input (relu/leaky: or the output); op + 256: rounded to TF32
+ * on store */
 int icadv_act_backward(const float* x, const float* g, float* gx, int64_t n, int op, icadv_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
