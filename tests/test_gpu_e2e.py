@@ -618,6 +618,37 @@ def test_small_channel_contractions_run_padded_on_the_tensor_path(dev):
     assert torch.equal(tp.out.permute(0, 3, 1, 2), res[1][0]) and torch.equal(tp.g_in.permute(0, 3, 1, 2), res[1][1])
 
 
+def test_traced_program_follows_weight_updates(dev):
+    """A cached traced program (padded end-layer weights, fused conv + GDN, packed copies baked into the plans) is refreshed
+    in place when the codec's parameters change: a second attack_() on the cached engine equals one on a fresh engine."""
+    from imagecompression_adversarial_b200 import attack as patk
+    from imagecompression_adversarial_b200 import models as pm
+    from oracle import attack as oatk
+    torch.manual_seed(3)
+    net = pm.init_model("cheng2020", 1, "mse", pretrained=False).to(dev)
+    with torch.no_grad():
+        for name, m in net.named_modules():
+            if getattr(m, "weight", None) is not None and m.weight.dim() == 4 and name.startswith(("g_a", "g_s")):
+                m.weight.mul_(0.6)
+    x = images(1, 192, 192, dev)
+    args = oatk.default_args(model="cheng2020", quality=1, metric="mse", steps=5)
+    args.force_branch = 1
+    patk._ENGINES.clear()
+    patk.attack_(x, net, args)
+    cached = next(iter(patk._ENGINES.values()))
+    with torch.no_grad():      # every kind of parameter the program bakes in: padded RGB conv, 12-channel conv, GDN, bias
+        for p in net.g_a.parameters():
+            p.mul_(0.9)
+        for p in net.g_s.parameters():
+            p.mul_(1.1)
+    a = patk.attack_(x, net, args)
+    assert next(iter(patk._ENGINES.values())) is cached
+    patk._ENGINES.clear()
+    b = patk.attack_(x, net, args)
+    assert next(iter(patk._ENGINES.values())) is not cached
+    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
+
+
 def test_traced_program_equals_module_walk(dev):
     """cheng2020_anchor g_s(g_a(x)) and its input gradient: the traced static launch program (activations fused into
     contraction epilogues, rounding at the producer, summed skip gradients) against the same modules walked through
