@@ -120,6 +120,8 @@ _SIGS = {
     "icadv_gdn_bwd_combine": (C.c_int, [_fp, _fp, _fp, _fp, _fp, C.c_int64, C.c_int, C.c_void_p]),
     "icadv_probe_tf32_peak": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_double), C.c_void_p]),
     "icadv_uniform_noise": (C.c_int, [_fp, C.c_int64, C.c_uint64, C.c_uint64, C.c_float, C.c_float, C.c_void_p]),
+    "icadv_graph_if_begin": (C.c_int, [_fp, C.c_void_p, C.c_void_p]),
+    "icadv_graph_if_end": (C.c_int, [C.c_void_p]),
     "icadv_attention_gate": (C.c_int, [_fp, _fp, _fp, _fp, C.c_int64, C.c_void_p]),
     "icadv_attention_gate_backward": (C.c_int, [_fp, _fp, _fp, _fp, _fp, C.c_int64, C.c_void_p]),
     "icadv_pmf_to_quantized_cdf": (C.c_int, [C.POINTER(C.c_float), C.c_int, C.c_int, C.POINTER(C.c_int)]),

@@ -5,7 +5,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 SOURCES = ["icadv_core.cu", "icadv_conv_tc.cu", "icadv_conv_simt.cu", "icadv_perturb.cu", "icadv_entropy.cu", "icadv_msssim.cu",
-           "icadv_train.cu", "icadv_split.cu", "icadv_probe.cu", "icadv_wgrad_tc.cu", "icadv_rans.cu"]
+           "icadv_train.cu", "icadv_split.cu", "icadv_probe.cu", "icadv_wgrad_tc.cu", "icadv_rans.cu", "icadv_graph.cu"]
 OUT = os.path.join(os.path.dirname(HERE), "libicadv_b200.so")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
          "--use_fast_math" if False else "-DICADV_NO_FAST_MATH", "-Xptxas", "-v"]

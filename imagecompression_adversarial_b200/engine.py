@@ -10,6 +10,9 @@ Per iteration, all stream-ordered and captured in one CUDA graph:
   4. g_s backward, g_a backward to the input  (attack_rd.py:547, input gradient only)
   5. perturb_update     clamp backward rule + Adam on the perturbation  (attack_rd.py:546-548)
 """
+import ctypes as C
+import os
+
 import torch
 
 from . import _lib as L
@@ -70,6 +73,8 @@ class AttackEngine:
         act, nact = self.st.active, self.st.n_active
         self._build_network(net, n_img, height, width, dev, act, nact)
         self._graph = None
+        self._if_capture, self._if_stream = False, None
+        self._graph_if_ok = True           # engines whose network pass allocates (autograd walk) switch it off
         self.iterations_done = 0
         self.im_s_nchw = self.output_s_nchw = None
         self._ones = torch.ones(n_img, device=dev, dtype=torch.float32)
@@ -192,7 +197,17 @@ class AttackEngine:
         if self.att_metric == "ms-ssim":
             return self._iteration_msssim()
         self._perturb_forward()
-        g_in = self._network_pass()
+        if self._if_capture:
+            # graph capture of an un-forced loop: the network launches go into the body of an IF node on the device-side
+            # count of images that take the network branch (csrc/icadv_graph.cu); nothing in the pass allocates
+            cur = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+            body = C.c_void_p(self._if_stream.cuda_stream)
+            L.call("icadv_graph_if_begin", C.c_void_p(self.st.n_active.data_ptr()), cur, body)
+            with torch.cuda.stream(self._if_stream):
+                g_in = self._network_pass()
+            L.call("icadv_graph_if_end", body)
+        else:
+            g_in = self._network_pass()
         ops.perturb_update_adam(self.im_s, self.noise, g_in, self.m, self.v, self.st, eps=self.eps,
                                 gradA_scale=1.0 / self.per_img, gradB_scale=1.0, w_in=self.w_in)
 
@@ -278,8 +293,17 @@ class AttackEngine:
         for t, c in zip((self.noise, self.m, self.v, self.st.step), state):
             t.copy_(c)
         g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g):
-            self._iteration()
+        # un-forced L2 loops skip the network launches of iterations in which no image takes the network branch
+        # (ICADV_GRAPH_IF=0 keeps them unconditional); a forced branch needs no test
+        self._if_capture = (self.att_metric == "L2" and self.force_branch != 1 and self._graph_if_ok and
+                            os.environ.get("ICADV_GRAPH_IF", "1") != "0")
+        if self._if_capture:
+            self._if_stream = torch.cuda.Stream()
+        try:
+            with torch.cuda.graph(g):
+                self._iteration()
+        finally:
+            self._if_capture = False
         for t, c in zip((self.noise, self.m, self.v, self.st.step), state):
             t.copy_(c)
         self._graph = g

@@ -424,6 +424,14 @@ int icadv_attention_gate(const float* a, const float* b, const float* x, float* 
 int icadv_attention_gate_backward(const float* a, const float* b, const float* g, float* ga, float* gb, int64_t n,
                                   icadv_stream_t stream);
 
+/* Conditional section of a captured launch sequence (CUDA graph IF node; replaces the reference's per-step host branch
+ * `if loss_i >= noise_thres` of attack_rd.py:333-334 for the launches only one branch needs).  Call while
+ * `capture_stream` is capturing: launches made on `body_stream` between begin and end become the body of an IF node of
+ * the capturing graph and run at replay time only if *flag > 0 (read on the device when the graph reaches that point);
+ * work captured on `capture_stream` after begin depends on the IF node.  The body must not allocate. */
+int icadv_graph_if_begin(const int* flag, icadv_stream_t capture_stream, icadv_stream_t body_stream);
+int icadv_graph_if_end(icadv_stream_t body_stream);
+
 /* Roofline denominator for the contraction kernels (bench.py): one launch of a bare tcgen05.mma kind::tf32 loop
  * (128 x n x 8 instructions on static shared-memory operands, one CTA per SM, `iters` K-blocks of four MMAs each).
  * The caller times the launch with CUDA events; *flops_out receives the FLOP it performs. */

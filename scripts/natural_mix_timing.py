@@ -21,3 +21,17 @@ for force, name in ((1, "network branch forced (B)"), (0, "budget branch forced 
     e0.record(); eng.run(50); e1.record()
     torch.cuda.synchronize()
     print(f"{n} images, {name}: {e0.elapsed_time(e1) / 50:.3f} ms per iteration")
+
+# un-forced loop: the graph's IF node skips the network section of budget-branch iterations (csrc/icadv_graph.cu)
+import os
+for flag in ("0", "1"):
+    os.environ["ICADV_GRAPH_IF"] = flag
+    eng = AttackEngine(net, n, 512, 768, steps=1001, use_graph=True)
+    eng.load(x, ref)
+    eng.run(20)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(); eng.run(200); e1.record()
+    torch.cuda.synchronize()
+    print(f"{n} images, un-forced loop (iterations 20..219 of a 1001-step schedule), ICADV_GRAPH_IF={flag}: "
+          f"{e0.elapsed_time(e1) / 200:.3f} ms per iteration")
