@@ -618,25 +618,26 @@ def test_small_channel_contractions_run_padded_on_the_tensor_path(dev):
     assert torch.equal(tp.out.permute(0, 3, 1, 2), res[1][0]) and torch.equal(tp.g_in.permute(0, 3, 1, 2), res[1][1])
 
 
-def test_unforced_graph_loop_with_conditional_network_section_equals_eager(dev):
+@pytest.mark.parametrize("model,quality", [("hyper", 3), ("cheng2020", 1)])
+def test_unforced_graph_loop_with_conditional_network_section_equals_eager(dev, model, quality):
     """An un-forced L2 loop captured in a CUDA graph puts the network launches into an IF node on the device-side count of
     network-branch images (csrc/icadv_graph.cu): replay equals the eager launch sequence bit for bit over a trajectory that
     takes both branches, and equals the capture with the section unconditional (ICADV_GRAPH_IF=0)."""
     import os
     from imagecompression_adversarial_b200 import models as pm
-    from imagecompression_adversarial_b200.engine import AttackEngine
+    from imagecompression_adversarial_b200.engine import AttackEngine, TapeAttackEngine
     torch.manual_seed(0)
-    net = pm.init_model("hyper", 3, "mse", pretrained=False).to(dev).train()
-    n, h, w = 3, 64, 96
+    net = pm.init_model(model, quality, "mse", pretrained=False).to(dev).train()
+    Engine = AttackEngine if model == "hyper" else TapeAttackEngine      # fused stack programs / traced program
+    n, h, w = 3, 64, 128
     x = images(n, h, w, dev)
     with torch.no_grad():
-        ref = net(x)["x_hat"].clamp(0, 1)
-    net.train()
+        ref = net.g_s(net.g_a(x)).clamp(0, 1)
     res, branches = [], None
     for mode in ("eager", "graph", "graph-unconditional"):
         os.environ["ICADV_GRAPH_IF"] = "0" if mode == "graph-unconditional" else "1"
         try:
-            eng = AttackEngine(net, n, h, w, steps=12, use_graph=mode != "eager")
+            eng = Engine(net, n, h, w, steps=12, use_graph=mode != "eager")
             eng.load(x, ref)
             if mode == "eager":
                 rec = []
@@ -649,7 +650,8 @@ def test_unforced_graph_loop_with_conditional_network_section_equals_eager(dev):
             os.environ.pop("ICADV_GRAPH_IF", None)
         torch.cuda.synchronize()
         res.append((eng.noise.clone(), eng.m.clone(), eng.v.clone(), eng.im_in.clone()))
-    assert any(b == 0 for b in branches) and any(b > 0 for b in branches), branches   # both kinds of iteration occurred
+    if model == "hyper":
+        assert any(b == 0 for b in branches) and any(b > 0 for b in branches), branches   # both kinds of iteration occurred
     for other in res[1:]:
         for a, b in zip(res[0], other):
             assert torch.equal(a, b)
