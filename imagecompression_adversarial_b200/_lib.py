@@ -29,7 +29,8 @@ class ConvDesc(C.Structure):
 
 class PerturbState(C.Structure):
     _fields_ = [("sum_d2", _fp), ("loss_i", _fp), ("branch", _fp), ("active", _fp), ("n_active", _fp),
-                ("step", _fp), ("lr", _fp), ("step_size", _fp), ("bc2_sqrt", _fp)]
+                ("step", _fp), ("lr", _fp), ("step_size", _fp), ("bc2_sqrt", _fp), ("counter", _fp),
+                ("cond_handle", C.c_uint64)]
 
 
 class IcadvError(RuntimeError):
@@ -122,6 +123,8 @@ _SIGS = {
     "icadv_uniform_noise": (C.c_int, [_fp, C.c_int64, C.c_uint64, C.c_uint64, C.c_float, C.c_float, C.c_void_p]),
     "icadv_graph_if_begin": (C.c_int, [_fp, C.c_void_p, C.c_void_p]),
     "icadv_graph_if_end": (C.c_int, [C.c_void_p]),
+    "icadv_graph_if_create": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64)]),
+    "icadv_graph_if_begin_handle": (C.c_int, [C.c_uint64, C.c_void_p, C.c_void_p]),
     "icadv_attention_gate": (C.c_int, [_fp, _fp, _fp, _fp, C.c_int64, C.c_void_p]),
     "icadv_attention_gate_backward": (C.c_int, [_fp, _fp, _fp, _fp, _fp, C.c_int64, C.c_void_p]),
     "icadv_pmf_to_quantized_cdf": (C.c_int, [C.POINTER(C.c_float), C.c_int, C.c_int, C.POINTER(C.c_int)]),

@@ -49,6 +49,44 @@ int icadv_graph_if_begin(const int* flag, icadv_stream_t capture_stream, icadv_s
   return ICADV_OK;
 }
 
+int icadv_graph_if_create(icadv_stream_t capture_stream, unsigned long long* handle_out) {
+  ICADV_REQUIRE(capture_stream && handle_out, "bad graph_if_create args");
+  cudaStreamCaptureStatus status;
+  unsigned long long id;
+  cudaGraph_t graph;
+  const cudaGraphNode_t* deps;
+  size_t n_deps;
+  ICADV_CUDA_TRY(cudaStreamGetCaptureInfo(as_stream(capture_stream), &status, &id, &graph, &deps, &n_deps));
+  ICADV_REQUIRE(status == cudaStreamCaptureStatusActive, "graph_if_create: the stream is not capturing");
+  cudaGraphConditionalHandle handle;
+  ICADV_CUDA_TRY(cudaGraphConditionalHandleCreate(&handle, graph, 0, cudaGraphCondAssignDefault));
+  *handle_out = (unsigned long long)handle;
+  return ICADV_OK;
+}
+
+int icadv_graph_if_begin_handle(unsigned long long handle, icadv_stream_t capture_stream, icadv_stream_t body_stream) {
+  ICADV_REQUIRE(handle && capture_stream && body_stream && capture_stream != body_stream, "bad graph_if_begin_handle args");
+  cudaStream_t cap = as_stream(capture_stream), body = as_stream(body_stream);
+  cudaStreamCaptureStatus status;
+  unsigned long long id;
+  cudaGraph_t graph;
+  const cudaGraphNode_t* deps;
+  size_t n_deps;
+  ICADV_CUDA_TRY(cudaStreamGetCaptureInfo(cap, &status, &id, &graph, &deps, &n_deps));
+  ICADV_REQUIRE(status == cudaStreamCaptureStatusActive, "graph_if_begin_handle: the stream is not capturing");
+  cudaGraphNodeParams params = {};
+  params.type = cudaGraphNodeTypeConditional;
+  params.conditional.handle = (cudaGraphConditionalHandle)handle;
+  params.conditional.type = cudaGraphCondTypeIf;
+  params.conditional.size = 1;
+  cudaGraphNode_t node;
+  ICADV_CUDA_TRY(cudaGraphAddNode(&node, graph, deps, n_deps, &params));
+  ICADV_CUDA_TRY(cudaStreamUpdateCaptureDependencies(cap, &node, 1, cudaStreamSetCaptureDependencies));
+  ICADV_CUDA_TRY(cudaStreamBeginCaptureToGraph(body, params.conditional.phGraph_out[0], nullptr, nullptr, 0,
+                                               cudaStreamCaptureModeRelaxed));
+  return ICADV_OK;
+}
+
 int icadv_graph_if_end(icadv_stream_t body_stream) {
   ICADV_REQUIRE(body_stream != nullptr, "bad graph_if_end args");
   cudaGraph_t g = nullptr;

@@ -26,13 +26,64 @@ __device__ __forceinline__ float block_sum_256(float v, float* red) {
 
 __device__ __forceinline__ float clampf(float x, float lo, float hi) { return fminf(fmaxf(x, lo), hi); }
 
-// ---- forward: noise -> im_in, partial sums of (im_s - im_in)^2
+// ---- forward: noise -> im_in, partial sums of (im_s - im_in)^2; the LAST block to finish finalises: per-image loss_i,
+// branch, compaction, LR schedule, Adam bias corrections (and the condition of the loop's graph IF node).  Until round 2
+// session 3 the finalisation was its own one-block launch (and the condition a third): three dependent launches ahead of
+// every iteration, which is what a budget-branch iteration of a small batch consists of.  The per-image sums run over
+// the blocks' partials in fixed order, so the result does not depend on which block comes last.
+struct FinalizeArgs {
+  int n_img, force_branch, sched_period, ge_test;
+  double inv_per_img, lr0, lr_gamma, beta1, beta2;
+  float budget;
+};
+
+__device__ __forceinline__ void perturb_finalize(const float* ws, const icadv_perturb_state& st, const FinalizeArgs& fa,
+                                                 int* s_branch) {
+  for (int n = threadIdx.x; n < fa.n_img; n += blockDim.x) {
+    float s = 0.f;
+    for (int b = 0; b < kRedBlocks; ++b) s += __ldcg(ws + (int64_t)n * kRedBlocks + b);   // written by other blocks
+    const float loss_i = (float)((double)s * fa.inv_per_img);
+    st.sum_d2[n] = s;
+    st.loss_i[n] = loss_i;
+    // attack_rd.py:334 -- A when over budget (">"); the ROI variant switches on ">=" (attack_data.py:219)
+    int br = (fa.ge_test ? (loss_i >= fa.budget) : (loss_i > fa.budget)) ? 0 : 1;
+    if (fa.force_branch >= 0) br = fa.force_branch;
+    st.branch[n] = br;
+    s_branch[n] = br;
+    const int i = st.step[n];  // 0-based iteration index
+    // MultiStepLR([1,2,3], gamma) stepped when i % period == 0 (attack_rd.py:503,553-554)
+    int nsched = (i == 0) ? 0 : 1 + (i - 1) / fa.sched_period;
+    if (nsched > 3) nsched = 3;
+    double lr = fa.lr0;
+    for (int k = 0; k < nsched; ++k) lr *= fa.lr_gamma;
+    const int t = i + 1;
+    const double bc1 = 1.0 - pow(fa.beta1, (double)t), bc2 = 1.0 - pow(fa.beta2, (double)t);
+    st.lr[n] = (float)lr;
+    st.step_size[n] = (float)(lr / bc1);
+    st.bc2_sqrt[n] = (float)sqrt(bc2);
+    st.step[n] = t;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int cnt = 0;
+    for (int k = 0; k < fa.n_img; ++k)
+      if (s_branch[k]) st.active[cnt++] = k;
+    *st.n_active = cnt;
+    for (int k = cnt; k < fa.n_img; ++k) st.active[k] = 0;
+    if (st.cond_handle != 0ull) cudaGraphSetConditional((cudaGraphConditionalHandle)st.cond_handle, cnt > 0 ? 1u : 0u);
+    *st.counter = 0u;           // ready for the next launch (launches on one state are stream-ordered)
+  }
+}
+
 __global__ void __launch_bounds__(256) perturb_forward_kernel(const float4* __restrict__ im_s,
                                                               const float4* __restrict__ noise,
                                                               float4* __restrict__ im_in, float* __restrict__ ws,
                                                               int64_t per_img4, float eps,
-                                                              const float4* __restrict__ w_in) {
+                                                              const float4* __restrict__ w_in, icadv_perturb_state st,
+                                                              FinalizeArgs fa) {
   __shared__ float red[8];
+  __shared__ int s_branch[1024];
+  __shared__ int s_last;
   const int n = blockIdx.y;
   const int64_t base = (int64_t)n * per_img4;
   float acc = 0.f;
@@ -50,47 +101,16 @@ __global__ void __launch_bounds__(256) perturb_forward_kernel(const float4* __re
     acc += w.x * dx * dx + w.y * dy * dy + w.z * dz * dz + w.w * dw * dw;
   }
   const float s = block_sum_256(acc, red);
-  if (threadIdx.x == 0) ws[(int64_t)n * kRedBlocks + blockIdx.x] = s;
-}
-
-// ---- finalize: per-image loss_i, branch, compaction, LR schedule, Adam bias corrections
-__global__ void perturb_finalize_kernel(const float* __restrict__ ws, icadv_perturb_state st, int n_img,
-                                        double inv_per_img, float budget, int force_branch, double lr0,
-                                        double lr_gamma, int sched_period, double beta1, double beta2, int ge_test) {
-  __shared__ int s_branch[1024];
-  const int n = threadIdx.x;
-  if (n < n_img) {
-    float s = 0.f;
-    for (int b = 0; b < kRedBlocks; ++b) s += ws[(int64_t)n * kRedBlocks + b];
-    const float loss_i = (float)((double)s * inv_per_img);
-    st.sum_d2[n] = s;
-    st.loss_i[n] = loss_i;
-    // attack_rd.py:334 -- A when over budget (">"); the ROI variant switches on ">=" (attack_data.py:219)
-    int br = (ge_test ? (loss_i >= budget) : (loss_i > budget)) ? 0 : 1;
-    if (force_branch >= 0) br = force_branch;
-    st.branch[n] = br;
-    s_branch[n] = br;
-    const int i = st.step[n];  // 0-based iteration index
-    // MultiStepLR([1,2,3], gamma) stepped when i % period == 0 (attack_rd.py:503,553-554)
-    int nsched = (i == 0) ? 0 : 1 + (i - 1) / sched_period;
-    if (nsched > 3) nsched = 3;
-    double lr = lr0;
-    for (int k = 0; k < nsched; ++k) lr *= lr_gamma;
-    const int t = i + 1;
-    const double bc1 = 1.0 - pow(beta1, (double)t), bc2 = 1.0 - pow(beta2, (double)t);
-    st.lr[n] = (float)lr;
-    st.step_size[n] = (float)(lr / bc1);
-    st.bc2_sqrt[n] = (float)sqrt(bc2);
-    st.step[n] = t;
+  if (threadIdx.x == 0) {
+    ws[(int64_t)n * kRedBlocks + blockIdx.x] = s;
+    __threadfence();                                           // the partial is visible before the arrival is counted
+    const unsigned int arrived = atomicAdd(st.counter, 1u);
+    s_last = (arrived == gridDim.x * gridDim.y - 1u) ? 1 : 0;
   }
   __syncthreads();
-  if (threadIdx.x == 0) {
-    int cnt = 0;
-    for (int k = 0; k < n_img; ++k)
-      if (s_branch[k]) st.active[cnt++] = k;
-    *st.n_active = cnt;
-    for (int k = cnt; k < n_img; ++k) st.active[k] = 0;
-  }
+  if (!s_last) return;
+  __threadfence();
+  perturb_finalize(ws, st, fa, s_branch);
 }
 
 // ---- backward of both clamp pairs + Adam, fused
@@ -335,14 +355,15 @@ int icadv_perturb_forward_roi(const float* im_s, const float* noise, float* im_i
   ICADV_REQUIRE(per_img % 4 == 0, "per_img must be a multiple of 4");
   ICADV_REQUIRE(n_img >= 1 && n_img <= 1024, "n_img must be in [1,1024]");
   ICADV_REQUIRE(sched_period >= 1, "sched_period (steps//3) must be >= 1 (ZeroDivisionError in the reference)");
+  ICADV_REQUIRE(st->counter != nullptr, "perturb state without an arrival counter");
   dim3 grid(kRedBlocks, n_img);
+  FinalizeArgs fa;
+  fa.n_img = n_img; fa.force_branch = force_branch; fa.sched_period = sched_period; fa.ge_test = ge_test;
+  fa.inv_per_img = 1.0 / (double)per_img; fa.lr0 = lr0; fa.lr_gamma = lr_gamma; fa.beta1 = beta1; fa.beta2 = beta2;
+  fa.budget = noise_budget;
   perturb_forward_kernel<<<grid, 256, 0, as_stream(stream)>>>(
       reinterpret_cast<const float4*>(im_s), reinterpret_cast<const float4*>(noise),
-      reinterpret_cast<float4*>(im_in), ws, per_img / 4, eps, reinterpret_cast<const float4*>(w_in));
-  ICADV_CUDA_TRY(cudaGetLastError());
-  perturb_finalize_kernel<<<1, 1024, 0, as_stream(stream)>>>(ws, *st, n_img, 1.0 / (double)per_img, noise_budget,
-                                                              force_branch, lr0, lr_gamma, sched_period, beta1, beta2,
-                                                              ge_test);
+      reinterpret_cast<float4*>(im_in), ws, per_img / 4, eps, reinterpret_cast<const float4*>(w_in), *st, fa);
   ICADV_CUDA_TRY(cudaGetLastError());
   return ICADV_OK;
 }

@@ -105,7 +105,7 @@ class AttackEngine:
         launch must read or write once in fp32; ``bound`` names the roofline that limits it ("tensor" / "hbm").
         Used by bench.py's per-launch roofline table and scripts/step_breakdown.py (speed mode only)."""
         img = 4.0 * self.n_img * self.per_img           # bytes of one RGB tensor of the batch
-        rows = [{"name": "perturb_forward + finalize", "launch": self._perturb_forward, "kernels": 2, "flops": 0.0,
+        rows = [{"name": "perturb_forward + finalize", "launch": self._perturb_forward, "kernels": 1, "flops": 0.0,
                  "bytes": 3 * img, "bound": "hbm"}]
         msssim = self.att_metric == "ms-ssim"
         # MS-SSIM value + gradient: both images' 5-level pyramids (4/3 of the image) read by the forward and again by
@@ -196,17 +196,25 @@ class AttackEngine:
     def _iteration(self):
         if self.att_metric == "ms-ssim":
             return self._iteration_msssim()
-        self._perturb_forward()
         if self._if_capture:
             # graph capture of an un-forced loop: the network launches go into the body of an IF node on the device-side
-            # count of images that take the network branch (csrc/icadv_graph.cu); nothing in the pass allocates
+            # count of images that take the network branch (csrc/icadv_graph.cu); perturb_forward sets the node's condition
+            # itself (handle in the state it is launched with); nothing in the pass allocates
             cur = C.c_void_p(torch.cuda.current_stream().cuda_stream)
             body = C.c_void_p(self._if_stream.cuda_stream)
-            L.call("icadv_graph_if_begin", C.c_void_p(self.st.n_active.data_ptr()), cur, body)
+            handle = C.c_uint64(0)
+            L.call("icadv_graph_if_create", cur, C.byref(handle))
+            self.st.c.cond_handle = handle.value
+            try:
+                self._perturb_forward()
+            finally:
+                self.st.c.cond_handle = 0
+            L.call("icadv_graph_if_begin_handle", handle, cur, body)
             with torch.cuda.stream(self._if_stream):
                 g_in = self._network_pass()
             L.call("icadv_graph_if_end", body)
         else:
+            self._perturb_forward()
             g_in = self._network_pass()
         ops.perturb_update_adam(self.im_s, self.noise, g_in, self.m, self.v, self.st, eps=self.eps,
                                 gradA_scale=1.0 / self.per_img, gradB_scale=1.0, w_in=self.w_in)
@@ -259,7 +267,7 @@ class AttackEngine:
     def kernels_per_iteration(self):
         fa, ba = self.ga.n_kernels()
         fs, bs = self.gs.n_kernels()
-        return 2 + fa + fs + 2 + bs + ba + 1  # perturb fwd (2) + stacks + output_loss (2) + update (1)
+        return 1 + fa + fs + 2 + bs + ba + 1  # perturb fwd (1) + stacks + output_loss (2) + update (1)
 
     def run(self, iterations, record=None):
         """Run ``iterations`` loop iterations.  ``record`` (list) receives per-iteration

@@ -271,9 +271,11 @@ class PerturbState:
         self.sum_d2, self.loss_i, self.lr, self.step_size, self.bc2_sqrt = f(), f(), f(), f(), f()
         self.branch, self.active, self.step, self.n_active = i(), i(), i(), i(1)
         self.ws = torch.zeros(n_img * L.RED_BLOCKS, device=device, dtype=torch.float32)
+        self.counter = i(1)             # arrival counter of perturb_forward's blocks (reset by the kernel itself)
         s = L.PerturbState()
-        for name in ("sum_d2", "loss_i", "branch", "active", "n_active", "step", "lr", "step_size", "bc2_sqrt"):
+        for name in ("sum_d2", "loss_i", "branch", "active", "n_active", "step", "lr", "step_size", "bc2_sqrt", "counter"):
             setattr(s, name, _p(getattr(self, name)))
+        s.cond_handle = 0               # set by the engine while it captures the loop's IF node
         self.c = s
 
 

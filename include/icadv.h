@@ -181,6 +181,10 @@ typedef struct {
   float* lr;        /* lr used at this iteration (MultiStepLR([1,2,3]) stepped every steps//3) */
   float* step_size; /* lr / (1 - beta1^t) */
   float* bc2_sqrt;  /* sqrt(1 - beta2^t) */
+  unsigned int* counter;          /* [1], zero before the first call: arrival counter of perturb_forward's blocks (the last
+                                   * one finalises the state) */
+  unsigned long long cond_handle; /* 0, or the handle of a CUDA-graph IF node (icadv_graph_if_create) whose condition
+                                   * perturb_forward sets to n_active > 0 */
 } icadv_perturb_state;
 
 /* noise -> clamp(+-eps) -> im_in = clamp(im_s + noise_clipped, 0, 1); loss_i; branch (force_branch
@@ -431,6 +435,10 @@ int icadv_attention_gate_backward(const float* a, const float* b, const float* g
  * work captured on `capture_stream` after begin depends on the IF node.  The body must not allocate. */
 int icadv_graph_if_begin(const int* flag, icadv_stream_t capture_stream, icadv_stream_t body_stream);
 int icadv_graph_if_end(icadv_stream_t body_stream);
+/* Two-step form: the handle is created first and handed to the launch that computes the condition (perturb_forward, through
+ * icadv_perturb_state.cond_handle), which saves the one-thread launch icadv_graph_if_begin makes to set it. */
+int icadv_graph_if_create(icadv_stream_t capture_stream, unsigned long long* handle_out);
+int icadv_graph_if_begin_handle(unsigned long long handle, icadv_stream_t capture_stream, icadv_stream_t body_stream);
 
 /* Roofline denominator for the contraction kernels (bench.py): one launch of a bare tcgen05.mma kind::tf32 loop
  * (128 x n x 8 instructions on static shared-memory operands, one CTA per SM, `iters` K-blocks of four MMAs each).
