@@ -179,42 +179,54 @@ __global__ void gdn_reparam_kernel(const float* __restrict__ raw, float* __restr
 // kShufT * c_in floats) through shared memory; each of the r HIGH-resolution rows they map to is again one contiguous run
 // (r * kShufT pixels x c_out floats).  The previous form (one thread per LOW element, 4-byte accesses c_out floats apart on
 // the HIGH side) measured 1.0 TB/s on the cheng2020 upsampling blocks (profiles/r2_bench_config4.json).
-constexpr int kShufT = 8;
-__global__ void pixel_shuffle_kernel(const float* __restrict__ src, float* __restrict__ dst, int n_seg, int h, int w,
-                                     int c_out, int r, int inverse) {
-  extern __shared__ float tile[];   // [kShufT][c_in]
+// A block takes T consecutive LOW pixels (T chosen by the host so that a tile is ~24 KB whatever the channel count) --
+// element indexes are stepped without divisions (the first form spent ~40 integer instructions per element on o / c_out and
+// xl / r: 2.4 TB/s on the 768-channel blocks, 0.3 TB/s on the 12-channel one).
+__global__ void __launch_bounds__(256) pixel_shuffle_kernel(const float* __restrict__ src, float* __restrict__ dst, int n_seg,
+                                                            int h, int w, int c_out, int r, int inverse, int T) {
+  extern __shared__ float tile[];   // [T][c_in]
   const int c_in = c_out * r * r;
-  const int segs_x = (w + kShufT - 1) / kShufT;
-  const float* lo_src = inverse ? nullptr : src;
-  const float* hi_src = inverse ? src : nullptr;
+  const int segs_x = (w + T - 1) / T;
+  const int dq = 256 / c_out, dr = 256 % c_out;          // element step of a thread: (xl, c) += (dq, dr) with carry
+  const int xl0 = threadIdx.x / c_out, c0 = threadIdx.x % c_out;
   for (int seg = blockIdx.x; seg < n_seg; seg += gridDim.x) {
     const int sx = seg % segs_x, y = (seg / segs_x) % h;
     const int64_t n = seg / ((int64_t)segs_x * h);
-    const int x0 = sx * kShufT, nx = min(kShufT, w - x0);
+    const int x0 = sx * T, nx = min(T, w - x0);
     const int64_t lo = ((n * h + y) * (int64_t)w + x0) * c_in;              // first LOW element of the segment
     const int run = nx * r * c_out;                                          // floats of one HIGH row of the segment
+    const int n_lo = nx * c_in;
+    const bool v4 = (c_in & 3) == 0;                                         // then lo and n_lo are multiples of 4
     if (!inverse) {
-      for (int i = threadIdx.x; i < nx * c_in; i += blockDim.x) tile[i] = lo_src[lo + i];
-      __syncthreads();
-      for (int di = 0; di < r; ++di) {
-        const int64_t hi = ((n * h * r + (int64_t)y * r + di) * ((int64_t)w * r) + (int64_t)x0 * r) * c_out;
-        for (int o = threadIdx.x; o < run; o += blockDim.x) {
-          const int xl = o / c_out, c = o - xl * c_out;
-          const int x = xl / r, dj = xl - x * r;
-          dst[hi + o] = tile[x * c_in + c * r * r + di * r + dj];
-        }
-      }
-    } else {
-      for (int di = 0; di < r; ++di) {
-        const int64_t hi = ((n * h * r + (int64_t)y * r + di) * ((int64_t)w * r) + (int64_t)x0 * r) * c_out;
-        for (int o = threadIdx.x; o < run; o += blockDim.x) {
-          const int xl = o / c_out, c = o - xl * c_out;
-          const int x = xl / r, dj = xl - x * r;
-          tile[x * c_in + c * r * r + di * r + dj] = hi_src[hi + o];
-        }
+      if (v4) {
+        const float4* s4 = reinterpret_cast<const float4*>(src + lo);
+        float4* t4 = reinterpret_cast<float4*>(tile);
+        for (int i = threadIdx.x; i < n_lo / 4; i += 256) t4[i] = s4[i];
+      } else {
+        for (int i = threadIdx.x; i < n_lo; i += 256) tile[i] = src[lo + i];
       }
       __syncthreads();
-      for (int i = threadIdx.x; i < nx * c_in; i += blockDim.x) dst[lo + i] = tile[i];
+    }
+    for (int di = 0; di < r; ++di) {
+      const int64_t hi = ((n * h * r + (int64_t)y * r + di) * ((int64_t)w * r) + (int64_t)x0 * r) * c_out;
+      int xl = xl0, c = c0;
+      for (int o = threadIdx.x; o < run; o += 256) {
+        const int x = r == 2 ? (xl >> 1) : xl / r, dj = r == 2 ? (xl & 1) : xl - (xl / r) * r;
+        const int t = x * c_in + c * r * r + di * r + dj;
+        if (!inverse) dst[hi + o] = tile[t]; else tile[t] = src[hi + o];
+        xl += dq; c += dr;
+        if (c >= c_out) { c -= c_out; ++xl; }
+      }
+    }
+    if (inverse) {
+      __syncthreads();
+      if (v4) {
+        float4* d4 = reinterpret_cast<float4*>(dst + lo);
+        const float4* t4 = reinterpret_cast<const float4*>(tile);
+        for (int i = threadIdx.x; i < n_lo / 4; i += 256) d4[i] = t4[i];
+      } else {
+        for (int i = threadIdx.x; i < n_lo; i += 256) dst[lo + i] = tile[i];
+      }
     }
     __syncthreads();
   }
@@ -241,9 +253,12 @@ int icadv_pixel_shuffle(const float* src, float* dst, int n, int h, int w, int c
                         icadv_stream_t stream) {
   ICADV_REQUIRE(src && dst && n > 0 && h > 0 && w > 0 && c_out > 0 && r >= 1, "bad pixel_shuffle args");
   const int c_in = c_out * r * r;
-  const size_t smem = (size_t)kShufT * c_in * sizeof(float);
-  ICADV_REQUIRE(smem <= 96 * 1024, "pixel_shuffle: c_out * r * r too large");
-  const int64_t n_seg = (int64_t)n * h * ((w + kShufT - 1) / kShufT);
+  ICADV_REQUIRE(c_in <= 12288, "pixel_shuffle: c_out * r * r too large");
+  int T = 6144 / c_in;                       // ~24 KB of LOW pixels per block iteration
+  if (T < 2) T = 2;
+  if (T > w) T = w;
+  const size_t smem = (size_t)T * c_in * sizeof(float);
+  const int64_t n_seg = (int64_t)n * h * ((w + T - 1) / T);
   ICADV_REQUIRE(n_seg < (1ll << 31), "pixel_shuffle: tensor too large");
   if (smem > 48 * 1024) {
     static std::once_flag once;
@@ -254,7 +269,7 @@ int icadv_pixel_shuffle(const float* src, float* dst, int n, int h, int w, int c
     if (err != cudaSuccess) { set_error("cudaFuncSetAttribute(pixel_shuffle) failed: %s", cudaGetErrorString(err)); return ICADV_ECUDA; }
   }
   int64_t blocks = n_seg < 148 * 8 ? n_seg : 148 * 8;
-  pixel_shuffle_kernel<<<(int)blocks, 256, smem, as_stream(stream)>>>(src, dst, (int)n_seg, h, w, c_out, r, inverse);
+  pixel_shuffle_kernel<<<(int)blocks, 256, smem, as_stream(stream)>>>(src, dst, (int)n_seg, h, w, c_out, r, inverse, T);
   ICADV_CUDA_TRY(cudaGetLastError());
   return ICADV_OK;
 }

@@ -474,7 +474,12 @@ class TapeProgram:
                 bound = "tensor" if Fn.tc_shape(d.k_ch, d.n_ch) or d.acc_from_in else "hbm"
                 return {"name": f"{self.name}[{k}] {name}", "flops": 2.0 * macs, "bytes": nbytes, "bound": bound}
             t = [a for a in p.args if torch.is_tensor(a)]
-            return {"name": f"{self.name}[{k}] elementwise ({p.fn.__name__.strip('_')})", "flops": 0.0,
+            fn = p.fn.__name__.strip('_')
+            if fn == "unary":       # which elementwise pass: add / round / copy ... (+ "r": rounds on store)
+                op = int(p.args[3])
+                fn = {0: "abs", 1: "relu", 2: "leaky", 3: "rint", 4: "add", 5: "round", 6: "clamp", 7: "copy"}[op & 255] + \
+                    ("+r" if op & 256 else "")
+            return {"name": f"{self.name}[{k}] elementwise ({fn})", "flops": 0.0,
                     "bytes": 4.0 * sum(a.numel() for a in t), "bound": "hbm"}
         self.fwd_info = [info(p, "fwd", k) for k, p in enumerate(self.fwd)]
         self.bwd_info = [info(p, "bwd", k) for k, p in enumerate(self.bwd)]
