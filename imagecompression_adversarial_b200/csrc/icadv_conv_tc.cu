@@ -353,10 +353,12 @@ __global__ void __launch_bounds__(kThreads, 2) conv_tc_kernel(const __grid_const
         mbar_wait(&full[s], s_par);
         mbar_wait(&a2_ready[c], 0);
         tc_fence_after_sync();
-        tc_mma_tf32(tmem + p.n_ch, ad, bd, idesc, c > 0 ? 1u : 0u);
-        tc_mma_tf32(tmem + p.n_ch, ad + 2, bd + 2, idesc, 1u);
-        tc_mma_tf32(tmem + p.n_ch, ad + 4, bd + 4, idesc, 1u);
-        tc_mma_tf32(tmem + p.n_ch, ad + 6, bd + 6, idesc, 1u);
+        // accumulator from global memory (FROM_IN): TMEM holds the normalisation product only, at column 0
+        const uint32_t dn = tmem + (FROM_IN ? 0u : static_cast<uint32_t>(p.n_ch));
+        tc_mma_tf32(dn, ad, bd, idesc, c > 0 ? 1u : 0u);
+        tc_mma_tf32(dn, ad + 2, bd + 2, idesc, 1u);
+        tc_mma_tf32(dn, ad + 4, bd + 4, idesc, 1u);
+        tc_mma_tf32(dn, ad + 6, bd + 6, idesc, 1u);
         tc_commit(&empty[s]);
         tc_commit(&pempty[ps]);
         if (!p.ld_alias) { if (++s == S) { s = 0; s_par ^= 1; w_lo = w_lo0; } else { w_lo += w_step; } }
@@ -566,7 +568,7 @@ __global__ void __launch_bounds__(kThreads, 2) conv_tc_kernel(const __grid_const
         for (int c = 0; c < nC; ++c) {
           float v[32], w[32];
           load_acc1(c, v);
-          tmem_ld32(t_lane + p.n_ch + c * 32, w);
+          tmem_ld32(t_lane + (FROM_IN ? 0 : p.n_ch) + c * 32, w);
           tmem_ld_wait();
           if constexpr (!bwd) {
             float sc[32];
@@ -2362,7 +2364,10 @@ int icadv_conv_plan_create(const icadv_conv_desc* d, icadv_conv_plan** out_plan)
       p.num_patch = P; p.num_stages = S;
       return true;
     };
-    const bool want_two = (gdn ? 2 * N : N) <= 256 && getenv("ICADV_TC_ONE_CTA") == nullptr;
+    // TMEM columns: accumulator N (+ normalisation product N); a stand-alone (I)GDN launch (accumulator read from global
+    // memory) keeps only the normalisation product there, so N = 192 still leaves room for a second CTA on the SM
+    const int tm_cols = d->acc_from_in ? N : (gdn ? 2 * N : N);
+    const bool want_two = tm_cols <= 256 && getenv("ICADV_TC_ONE_CTA") == nullptr;
     const int env_s = getenv("ICADV_TC_S") ? atoi(getenv("ICADV_TC_S")) : 0;   // developer override: weight stages
     bool ok = (want_two && fit(kSmemTwoCta, 2, env_s > 0 ? env_s : 4)) || fit(kSmemLimit, 3, env_s > 0 ? env_s : kMaxStages);
     if (ok && p.ld_alias && p.num_stages < 4) {   // not enough stages to give two away: separate staging pair instead
@@ -2373,7 +2378,7 @@ int icadv_conv_plan_create(const icadv_conv_desc* d, icadv_conv_plan** out_plan)
     if (!ok) {
       delete plan; set_error("conv_tc: not enough shared memory for n_ch=%d", N); return ICADV_EINVAL;
     }
-    int cols = gdn ? 2 * N : N, pow2 = 32;
+    int cols = tm_cols, pow2 = 32;
     while (pow2 < cols) pow2 <<= 1;
     p.tmem_cols = pow2;
     p.bias = d->bias; p.beta = d->beta; p.active = d->active; p.n_active = d->n_active;
