@@ -235,6 +235,37 @@ class Up_bound:
         return BoundFn.apply(x, up_bound, True)
 
 
+class Round_STE(torch.autograd.Function):
+    """``ops.Round_STE`` (utils/ops.py:8-15): round to nearest (ties to even, as ``torch.round``) forward, identity backward."""
+
+    @staticmethod
+    def forward(ctx, x):
+        xc = x.contiguous()
+        return ops.unary(xc.view(-1), 3).view_as(xc)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g
+
+
+class UniverseQuant(torch.autograd.Function):
+    """``ops.UniverseQuant`` (utils/ops.py:17-25): ``round(x + u) - u`` with ``u ~ U(-1/2, 1/2)`` per element, identity
+    backward.  The sample comes from the library's Philox kernel on torch's CUDA generator (the reference draws on the CPU
+    and copies: a different stream of the same distribution)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        xc = x.contiguous()
+        u = ops.uniform_noise_like(xc)
+        q = ops.unary(ops.unary(xc.view(-1), 4, u.view(-1)), 3)          # round(x + u)
+        u.neg_()
+        return ops.unary(q, 4, u.view(-1)).view_as(xc)                   # - u
+
+    @staticmethod
+    def backward(ctx, g):
+        return g
+
+
 class ActFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, act):

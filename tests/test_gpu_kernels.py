@@ -608,3 +608,27 @@ def test_persistent_kernel_many_items_per_cta(dev, persist_env, epi):
         res.setdefault(level, []).append(out)
     torch.testing.assert_close(res[2][0], res[0][0], rtol=1e-5, atol=1e-6)
     assert torch.equal(res[2][0], res[2][1])
+
+
+def test_round_ste_and_universal_quantiser(dev):
+    """utils/ops.py:8-25 on the operator surface: Round_STE = torch.round forward / identity backward; UniverseQuant =
+    round(x + u) - u with u ~ U(-1/2, 1/2): error in [-1/2, 1/2], unbiased, identity backward, reproducible from the seed."""
+    from imagecompression_adversarial_b200 import functional as Fn
+    g = torch.Generator(device=dev).manual_seed(5)
+    x = (torch.randn(3, 7, 33, 20, device=dev, generator=g) * 4).requires_grad_(True)
+    y = Fn.Round_STE.apply(x)
+    assert torch.equal(y.detach(), torch.round(x.detach()))
+    go = torch.randn_like(y)
+    y.backward(go)
+    assert torch.equal(x.grad, go)
+    x.grad = None
+    torch.manual_seed(11)
+    q1 = Fn.UniverseQuant.apply(x)
+    torch.manual_seed(11)
+    q2 = Fn.UniverseQuant.apply(x)
+    assert torch.equal(q1, q2)
+    err = (q1 - x).detach()
+    assert float(err.abs().max()) <= 0.5 + 1e-6 and abs(float(err.mean())) < 0.02
+    assert 0.07 < float(err.var()) < 0.10                    # U(-1/2, 1/2): variance 1/12
+    q1.backward(go)
+    assert torch.equal(x.grad, go)
