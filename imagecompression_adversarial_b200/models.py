@@ -28,6 +28,7 @@ ZOO = {
     "context": {q: (192, 192) if q <= 4 else (192, 320) for q in range(1, 9)},
     "cheng2020": {q: (128,) if q <= 3 else (192,) for q in range(1, 7)},
     "cheng2020_attn": {q: (128,) if q <= 3 else (192,) for q in range(1, 7)},
+    "debug": {q: (3, 192) for q in range(1, 9)},      # anchors/model.py:61-68: ae_onelayer(N=3, M=192) at every quality
 }
 
 
@@ -936,6 +937,28 @@ class Cheng2020Anchor(JointAutoregressiveHierarchicalPriors):
             ResidualBlock(N, N), subpel_conv3x3(N, 3, 2))
 
 
+class ae_onelayer(MeanScaleHyperprior):
+    """The reference's ``debug`` model (anchors/model.py:9-35): one 3x3 stride-1 conv as ``g_a``, one 3x3 stride-1
+    transposed conv as ``g_s``; its forward decodes the UNQUANTISED latent (``x_hat = g_s(y)``, :31-32) while the
+    likelihoods come from the mean-scale hyperprior."""
+
+    def __init__(self, N, M, **kwargs):
+        super().__init__(N, M)
+        self.g_a = CodecStack(conv(3, M, kernel_size=3, stride=1))
+        self.g_s = CodecStack(deconv(M, 3, kernel_size=3, stride=1))
+
+    def forward(self, x):
+        with _param_grads_on(self.training):
+            y = self.g_a(x)
+            z = self.h_a(y)
+            z_hat, z_lik = self.entropy_bottleneck(z)
+            gp = self.h_s(z_hat)
+            half = gp.shape[1] // 2
+            scales_hat, means_hat = Fn.NarrowFn.apply(gp, 0, half), Fn.NarrowFn.apply(gp, half, half)
+            _, y_lik = self.gaussian_conditional(y, scales_hat, means=means_hat)
+            return {"x_hat": self.g_s(y), "likelihoods": {"y": y_lik, "z": z_lik}}
+
+
 class ResidualUnit(nn.Module):
     """compressai.layers.AttentionBlock.ResidualUnit: 1x1 (N -> N/2), ReLU, 3x3, ReLU, 1x1 (N/2 -> N), + x, ReLU."""
 
@@ -988,6 +1011,8 @@ def _build(model, quality):
         return Cheng2020Anchor(*cfg)
     if model == "cheng2020_attn":
         return Cheng2020Attention(*cfg)
+    if model == "debug":
+        return ae_onelayer(*cfg)
     raise L.IcadvError(f"unknown model family '{model}'")
 
 
@@ -1024,6 +1049,10 @@ def cheng2020_attn(quality, metric="mse", pretrained=False, **kw):
 def init_model(MODEL, quality, metric="mse", pretrained=False):
     """Same dispatch as anchors/model.py:60-78 (+ ``cheng2020_attn``, the zoo entry the reference leaves commented
     out next to ``cheng2020_anchor``)."""
+    if MODEL == "debug":                      # anchors/model.py:61-68: no zoo entry, --new only
+        if pretrained:
+            raise L.IcadvError("No download-able model available!")
+        return _build("debug", quality)
     table = {"factorized": bmshj2018_factorized, "hyper": bmshj2018_hyperprior, "context": mbt2018,
              "cheng2020": cheng2020_anchor, "cheng2020_attn": cheng2020_attn}
     if MODEL not in table:

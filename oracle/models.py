@@ -19,6 +19,7 @@ ZOO = {
     "context": {q: (192, 192) if q <= 4 else (192, 320) for q in range(1, 9)},
     "cheng2020": {q: (128,) if q <= 3 else (192,) for q in range(1, 7)},
     "cheng2020_attn": {q: (128,) if q <= 3 else (192,) for q in range(1, 7)},
+    "debug": {q: (3, 192) for q in range(1, 9)},      # anchors/model.py:61-68: ae_onelayer(N=3, M=192) at every quality
 }
 
 # CompressAI's published parameter counts (A.8) -- structural checksum of this restatement
@@ -125,6 +126,45 @@ class JointAutoregressiveHierarchicalPriors(CompressionModel):
         return {"x_hat": self.g_s(y_hat), "likelihoods": {"y": y_lik, "z": z_lik}}
 
 
+class MeanScaleHyperprior(ScaleHyperprior):
+    """compressai MeanScaleHyperprior (mbt2018_mean): the base class of the reference's ``debug`` model."""
+
+    def __init__(self, N, M):
+        super().__init__(N, M)
+        lr = lambda: nn.LeakyReLU(inplace=True)
+        self.h_a = nn.Sequential(conv(M, N, 3, 1), lr(), conv(N, N), lr(), conv(N, N))
+        self.h_s = nn.Sequential(deconv(N, M), lr(), deconv(M, M * 3 // 2), lr(), conv(M * 3 // 2, M * 2, 3, 1))
+        self._init_weights()
+
+    def forward(self, x):
+        y = self.g_a(x)
+        z = self.h_a(y)
+        z_hat, z_lik = self.entropy_bottleneck(z)
+        scales_hat, means_hat = self.h_s(z_hat).chunk(2, 1)
+        y_hat, y_lik = self.gaussian_conditional(y, scales_hat, means=means_hat)
+        return {"x_hat": self.g_s(y_hat), "likelihoods": {"y": y_lik, "z": z_lik}}
+
+
+class AeOneLayer(MeanScaleHyperprior):
+    """The reference's ``debug`` model (anchors/model.py:9-35): one 3x3 stride-1 conv as ``g_a``, one 3x3 stride-1
+    transposed conv as ``g_s``; its forward decodes the UNQUANTISED latent (``x_hat = g_s(y)``, :31-32) while the
+    likelihoods come from the mean-scale hyperprior."""
+
+    def __init__(self, N, M):
+        super().__init__(N, M)
+        self.g_a = nn.Sequential(conv(3, M, kernel_size=3, stride=1))
+        self.g_s = nn.Sequential(deconv(M, 3, kernel_size=3, stride=1))
+        self._init_weights()
+
+    def forward(self, x):
+        y = self.g_a(x)
+        z = self.h_a(y)
+        z_hat, z_lik = self.entropy_bottleneck(z)
+        scales_hat, means_hat = self.h_s(z_hat).chunk(2, 1)
+        _, y_lik = self.gaussian_conditional(y, scales_hat, means=means_hat)
+        return {"x_hat": self.g_s(y), "likelihoods": {"y": y_lik, "z": z_lik}}
+
+
 class Cheng2020Anchor(JointAutoregressiveHierarchicalPriors):
     """cheng2020_anchor: residual blocks + sub-pixel convs, no attention, single Gaussian
     (anchors/model.py:77; widths pinned by InvCompress/ours.py:33-55)."""
@@ -184,6 +224,8 @@ def init_model(model, quality, metric="mse", pretrained=False, seed=None):
         return Cheng2020Anchor(*cfg)
     if model == "cheng2020_attn":
         return Cheng2020Attention(*cfg)
+    if model == "debug":
+        return AeOneLayer(*cfg)
     raise ValueError(model)
 
 

@@ -407,6 +407,36 @@ def test_generic_engine_cheng2020_matches_oracle(dev, model):
     assert abs(psnr(p[0], x) - psnr(o[0], x)) < 0.05
 
 
+def test_debug_model_attack_matches_oracle(dev):
+    """The reference's ``debug`` codec (anchors/model.py:9-35,61-68: one 3x3 conv each way on a mean-scale hyperprior, the
+    reconstruction decoded from the unquantised latent) through the fused loop vs the oracle loop."""
+    from imagecompression_adversarial_b200 import attack as patk
+    from oracle import attack as oatk
+    onet, pnet = pair("debug", 1, dev)
+    with torch.no_grad():   # a kaiming-initialised one-layer decoder saturates the output clamp everywhere (zero gradient in
+        onet.g_s[0].weight.mul_(0.02)          # both implementations): scale it into (0, 1)
+        onet.g_s[0].bias.fill_(0.5)
+    pnet.load_state_dict(onet.state_dict())
+    x = images(1, 192, 192, dev)
+    args = oatk.default_args(model="debug", quality=1, metric="mse", steps=6)
+    # this codec decodes the unquantised latent in train AND eval mode, so from a zero perturbation the reconstruction equals
+    # output_s and the gradient is exactly zero: the attack needs the reference's random start (-random > 1,
+    # attack_rd.py:498-499), shared by the two implementations here
+    noise0 = torch.empty_like(x).uniform_(-3e-3, 3e-3)
+    rec, orec = [], []
+    p = patk.attack_(x, pnet, args, record=rec, noise_init=noise0)
+    o = oatk.attack_(x, onet, args, record=orec, noise_init=noise0)
+    for k, (br, loss, loss_i) in enumerate(orec):
+        pb, pli, pl = int(rec[k][0][0]), float(rec[k][1][0]), float(rec[k][2][0])
+        if (pb == 1) != (br == "B"):
+            assert abs(loss_i - args.noise) < 4e-3 * args.noise, (k, pb, br, loss_i, pli)
+            return
+        assert abs(pli - loss_i) <= 4e-3 * max(loss_i, 1e-7) + 1e-9, (k, pli, loss_i)
+        assert abs(pl - loss) <= (1e-3 if pb == 1 else 4e-3) * abs(loss) + 1e-9, (k, pl, loss)
+    assert abs(p[3] - o[3]) < max(1e-3, 5e-3 * abs(o[3])), (p[3], o[3])      # clean-pass bpp
+    assert abs(psnr(p[0], x) - psnr(o[0], x)) < 0.05
+
+
 def test_no_kernel_leaves_output_unwritten(dev):
     """The reference runs with torch.use_deterministic_algorithms(True) (self_ensemble.py:31), under which torch.empty()
     is NaN-filled: an output region a kernel does not write (e.g. the 3 of 4 pixels the input gradient of a strided 1x1

@@ -185,7 +185,7 @@ def test_split_stack_program_matches_oracle(dev, model, quality):
 
 @pytest.mark.parametrize("model,quality,hw", [("factorized", 1, (128, 192)), ("hyper", 3, (128, 192)),
                                               ("context", 4, (128, 192)), ("cheng2020", 6, (128, 128)),
-                                              ("cheng2020_attn", 1, (128, 128))])
+                                              ("cheng2020_attn", 1, (128, 128)), ("debug", 1, (128, 128))])
 def test_eval_forward_parity(dev, model, quality, hw):
     """net(x) in eval mode: latent indices, bpp, PSNR at the literal tolerances for all four families (+ the attention
     variant of cheng2020)."""
