@@ -460,6 +460,193 @@ __global__ void __launch_bounds__(256) ssim_level_bwd_kernel11(const SsimBwdPara
   }
 }
 
+
+
+// ---------------------------------------------------------------------------------------------------------
+// Fused value + unit gradient of one level (11-tap window), row-marching form.  The tile kernels above recompute the
+// statistics of a 32x32 tile from a 52x52 input tile (288 multiply-adds per pixel, one shared-memory load per 1-4 of
+// them); here a block owns a strip of kVgT columns and walks down the rows, every thread keeping the last eleven rows
+// of ITS column in registers:
+//     input row n -> horizontal filter (shared-memory row) -> ring of 11 x 4 row-filtered statistics
+//                 -> vertical filter = statistics of row n-10 -> per-position coefficients A12, A11, B -> ring of 11 x 3
+//                 -> vertical transposed filter (registers) -> shared-memory row -> horizontal transposed filter
+//                 -> U[n-10] = Y * T[A12] + 2 X * T[A11] + T[B]
+// so the vertical passes read registers only and no statistic is computed twice (about 190 multiply-adds and 55 shared
+// loads per pixel, forward value included).  Four statistics suffice: X^2 and Y^2 only occur summed.
+//   U = d(sum over the level's map)/dX with unit upstream weight: the map is cs (levels 0..3: ccs = 1, css = 0) or
+//   ssim = lum * cs (last level: ccs = 0, css = 1).  The per-plane weights depend on ALL levels' values, so they are
+//   applied afterwards by ssim_combine_kernel together with the 2x2-average-pool chain between levels.
+// Coordinates are those of the zero-padded frame (pad = 0: valid window, variant 1; pad = 5: zero "same" padding,
+// variant 2): frame (hp, wp) = (h + 2 pad, w + 2 pad), statistics positions (oh, ow) = (hp - 10, wp - 10), position o
+// reads frame rows / columns o .. o+10, the gradient of frame pixel i collects positions i-10 .. i.
+// A block computes statistics columns c0 .. c0+kVgT-1 and the kVgT-10 output columns that need only those; a row
+// segment [i0, i1) of outputs costs 20 extra rows of warm-up.  Per-block partial sums (fixed order) go to ws.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int kVgT = 128;      // threads = statistics columns per strip
+constexpr int kVgR = kMaxWin - 1;
+
+struct SsimVgParams {
+  const float* X; const float* Y; float* U; float* ws;
+  int h, w, pad, hp, wp, oh, ow, seg_rows;
+  float c1, c2, ccs, css;
+  float taps[kMaxWin];
+};
+
+__global__ void __launch_bounds__(kVgT, 4) ssim_level_vg_kernel(const SsimVgParams p) {
+  constexpr int W = kMaxWin, R = kVgR, T = kVgT;
+  __shared__ float s_in[2][2][T + R];
+  __shared__ float s_v[2][3][T];
+  __shared__ float s_red[2][T / 32];
+  const int t = threadIdx.x;
+  const int plane = blockIdx.z;
+  const int c0 = -R + (int)blockIdx.x * (T - R);
+  const int i0 = (int)blockIdx.y * p.seg_rows, i1 = min(i0 + p.seg_rows, p.hp);
+  const float* __restrict__ X = p.X + (int64_t)plane * p.h * p.w;
+  const float* __restrict__ Y = p.Y + (int64_t)plane * p.h * p.w;
+  float* __restrict__ U = p.U + (int64_t)plane * p.h * p.w;
+  const int ox = c0 + t;                       // statistics column = output column (frame coordinates)
+  const bool ox_valid = ox >= 0 && ox < p.ow;
+  const bool own_col = t >= R && ox_valid;     // counted in the sums by this strip
+  const int gx0 = ox - p.pad;                  // image column of frame column ox
+  const bool gx0_in = gx0 >= 0 && gx0 < p.w;
+  const int gx1 = gx0 + T;                     // the R extra columns right of the strip (threads 0..R-1)
+  const bool gx1_in = t < R && gx1 >= 0 && gx1 < p.w;
+  const bool out_col = t >= R && gx0_in;
+
+  float hr[W][4], ar[W][3];
+#pragma unroll
+  for (int k = 0; k < W; ++k) {
+    hr[k][0] = hr[k][1] = hr[k][2] = hr[k][3] = 0.f;
+    ar[k][0] = ar[k][1] = ar[k][2] = 0.f;
+  }
+  float acc_s = 0.f, acc_c = 0.f;
+  float a0 = 0.f, b0 = 0.f, a1 = 0.f, b1 = 0.f;
+  // running offsets inside the plane (h * w < 2^31): the input row being fetched and the output row being produced
+  int gy_in = i0 - R - p.pad, off_in = gy_in * p.w + gx0;
+  if (gy_in >= 0 && gy_in < p.h) {
+    if (gx0_in) { a0 = __ldg(X + off_in); b0 = __ldg(Y + off_in); }
+    if (gx1_in) { a1 = __ldg(X + off_in + T); b1 = __ldg(Y + off_in + T); }
+  }
+  // One barrier per row: the row-filtered V of iteration n is consumed (horizontal transposed filter, output row n-11)
+  // by iteration n+1, after that iteration's barrier; both shared rows are double-buffered.
+  const int n_last = i1 + R;                   // consumer-only iteration that drains the last V row
+  for (int base = i0 - R; base <= n_last; base += W) {
+#pragma unroll
+    for (int s = 0; s < W; ++s) {
+      const int n = base + s;                  // frame row entering the pipeline
+      if (n > n_last) break;
+      const int b = n & 1;
+      const bool produce = n < n_last;         // block-uniform
+      s_in[b][0][t] = a0; s_in[b][1][t] = b0;
+      if (t < R) { s_in[b][0][T + t] = a1; s_in[b][1][T + t] = b1; }
+      // next input row and the operands of the output row drained in this iteration: issued ahead of the arithmetic
+      ++gy_in; off_in += p.w;
+      a0 = b0 = a1 = b1 = 0.f;
+      if (n + 1 < n_last && gy_in >= 0 && gy_in < p.h) {
+        if (gx0_in) { a0 = __ldg(X + off_in); b0 = __ldg(Y + off_in); }
+        if (gx1_in) { a1 = __ldg(X + off_in + T); b1 = __ldg(Y + off_in + T); }
+      }
+      const int io = n - R - 1;                // output row drained by this iteration
+      const int gyo = io - p.pad;
+      const bool drain = io >= i0;             // block-uniform
+      const bool do_out = drain && out_col && gyo >= 0 && gyo < p.h;
+      const int off_o = gyo * p.w + gx0;
+      float xo = 0.f, yo = 0.f;
+      if (do_out) { xo = __ldg(X + off_o); yo = __ldg(Y + off_o); }
+      __syncthreads();
+      if (produce) {
+        {
+          float h0 = 0.f, h1 = 0.f, h2 = 0.f, h3 = 0.f;
+#pragma unroll
+          for (int k = 0; k < W; ++k) {
+            const float g = p.taps[k], u = s_in[b][0][t + k], v = s_in[b][1][t + k];
+            h0 = fmaf(g, u, h0); h1 = fmaf(g, v, h1);
+            h2 = fmaf(g, fmaf(u, u, v * v), h2); h3 = fmaf(g, u * v, h3);
+          }
+          hr[s][0] = h0; hr[s][1] = h1; hr[s][2] = h2; hr[s][3] = h3;
+        }
+        if (n >= i0) {                         // block-uniform: statistics rows i0-R .. are the ones outputs need
+          const int i = n - R;                 // statistics row finished by this iteration
+          float m1 = 0.f, m2 = 0.f, sq = 0.f, s12 = 0.f;
+#pragma unroll
+          for (int k = 0; k < W; ++k) {        // k = 0 is the oldest ring row (frame row n-10)
+            const int q = (s + 1 + k) % W;
+            const float g = p.taps[k];
+            m1 = fmaf(g, hr[q][0], m1); m2 = fmaf(g, hr[q][1], m2);
+            sq = fmaf(g, hr[q][2], sq); s12 = fmaf(g, hr[q][3], s12);
+          }
+          float A12 = 0.f, A11 = 0.f, B = 0.f;
+          if (ox_valid && i >= 0 && i < p.oh) {
+            const float m11 = m1 * m1, m22 = m2 * m2, m12 = m1 * m2;
+            const float rD = 1.f / ((sq - m11 - m22) + p.c2);
+            const float cs = (2.f * (s12 - m12) + p.c2) * rD;
+            const float rDl = 1.f / (m11 + m22 + p.c1);
+            const float lum = (2.f * m12 + p.c1) * rDl;
+            if (own_col && i >= i0) { acc_c += cs; acc_s += lum * cs; }
+            const float a_cs = p.ccs + p.css * lum;
+            A12 = a_cs * 2.f * rD;
+            A11 = -a_cs * cs * rD;
+            B = -m2 * A12 - 2.f * m1 * A11 + p.css * cs * 2.f * (m2 - lum * m1) * rDl;
+          }
+          ar[s][0] = A12; ar[s][1] = A11; ar[s][2] = B;
+          float v0 = 0.f, v1 = 0.f, v2 = 0.f;
+#pragma unroll
+          for (int k = 0; k < W; ++k) {        // V[i] = sum_k g[k] A[i-k]; A[i-k] sits k slots back
+            const int q = (s - k + W) % W;
+            const float g = p.taps[k];
+            v0 = fmaf(g, ar[q][0], v0); v1 = fmaf(g, ar[q][1], v1); v2 = fmaf(g, ar[q][2], v2);
+          }
+          s_v[b][0][t] = v0; s_v[b][1][t] = v1; s_v[b][2][t] = v2;
+        }
+      }
+      if (drain && t >= R) {                   // V row io was written by the previous iteration, buffer b^1
+        float t0 = 0.f, t1 = 0.f, t2 = 0.f;
+#pragma unroll
+        for (int k = 0; k < W; ++k) {
+          const float g = p.taps[k];
+          t0 = fmaf(g, s_v[b ^ 1][0][t - k], t0); t1 = fmaf(g, s_v[b ^ 1][1][t - k], t1);
+          t2 = fmaf(g, s_v[b ^ 1][2][t - k], t2);
+        }
+        if (do_out) U[off_o] = yo * t0 + 2.f * xo * t1 + t2;
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    acc_s += __shfl_xor_sync(0xffffffffu, acc_s, o);
+    acc_c += __shfl_xor_sync(0xffffffffu, acc_c, o);
+  }
+  if ((t & 31) == 0) { s_red[0][t >> 5] = acc_s; s_red[1][t >> 5] = acc_c; }
+  __syncthreads();
+  if (t == 0) {
+    float s = 0.f, c = 0.f;
+    for (int k = 0; k < T / 32; ++k) { s += s_red[0][k]; c += s_red[1][k]; }
+    const int nb = gridDim.x * gridDim.y, blk = blockIdx.y * gridDim.x + blockIdx.x;
+    p.ws[((int64_t)plane * nb + blk) * 2 + 0] = s;
+    p.ws[((int64_t)plane * nb + blk) * 2 + 1] = c;
+  }
+}
+
+// D_l = coef[plane] * U_l + 0.25 * D_{l+1}[pool parent], in place, coarse to fine: the chain rule through
+// value = prod_l relu(level value)^w_l and through F.avg_pool2d(2, padding (ph, pw)) between levels.
+__global__ void __launch_bounds__(256) ssim_combine_kernel(float* __restrict__ U, const float* __restrict__ coef,
+                                                           const float* __restrict__ Dnext, int h, int w, int nh, int nw,
+                                                           int ph, int pw) {
+  const int plane = blockIdx.z, gy = blockIdx.y;
+  const float c = coef[plane];
+  float* row = U + ((int64_t)plane * h + gy) * w;
+  const int py = (gy + ph) >> 1;
+  const float* nrow = (Dnext != nullptr && py < nh) ? Dnext + ((int64_t)plane * nh + py) * nw : nullptr;
+  for (int gx = blockIdx.x * 256 + threadIdx.x; gx < w; gx += gridDim.x * 256) {
+    float d = c * row[gx];
+    if (nrow != nullptr) {
+      const int px = (gx + pw) >> 1;
+      if (px < nw) d = fmaf(0.25f, __ldg(nrow + px), d);
+    }
+    row[gx] = d;
+  }
+}
+
 }  // namespace icadv
 
 using namespace icadv;
@@ -531,6 +718,58 @@ int icadv_ssim_level_backward(const float* X, const float* Y, const float* coef_
   ICADV_REQUIRE(planes <= 65535 && grid.y <= 65535, "grid too large");
   if (win == kMaxWin) ssim_level_bwd_kernel11<<<grid, 256, smem, as_stream(stream)>>>(p);
   else ssim_level_bwd_kernel<<<grid, 256, smem, as_stream(stream)>>>(p);
+  ICADV_CUDA_TRY(cudaGetLastError());
+  return ICADV_OK;
+}
+
+
+static int vg_segments(int planes, int hp, int wp, int* seg_rows) {
+  const int strips = (wp + (kVgT - kVgR) - 1) / (kVgT - kVgR);
+  // enough blocks for ~2 waves of 4 blocks per SM, rows per segment >= 32 (20 warm-up rows per segment)
+  int nseg = (148 * 4 * 2 + planes * strips - 1) / (planes * strips);
+  const int max_seg = (hp + 31) / 32;
+  if (nseg > max_seg) nseg = max_seg;
+  if (nseg < 1) nseg = 1;
+  *seg_rows = (hp + nseg - 1) / nseg;
+  return (hp + *seg_rows - 1) / *seg_rows;
+}
+
+int icadv_ssim_vg_workspace_floats(int planes, int h, int w, int same_pad) {
+  const int pad = same_pad ? kMaxWin / 2 : 0, hp = h + 2 * pad, wp = w + 2 * pad;
+  if (hp < kMaxWin || wp < kMaxWin || planes <= 0) return 0;
+  int seg_rows;
+  const int nseg = vg_segments(planes, hp, wp, &seg_rows);
+  return planes * ((wp + (kVgT - kVgR) - 1) / (kVgT - kVgR)) * nseg * 2;
+}
+
+int icadv_ssim_level_value_grad(const float* X, const float* Y, float* U, float* ws, float* ssim_sum, float* cs_sum,
+                                int planes, int h, int w, const float* win_taps_host, int win, int same_pad, float c1,
+                                float c2, int last_level, icadv_stream_t stream) {
+  ICADV_REQUIRE(X && Y && U && ws && ssim_sum && cs_sum && win_taps_host, "null pointer");
+  ICADV_REQUIRE(win == kMaxWin, "the fused value + gradient level kernel takes the 11-tap window only");
+  SsimVgParams p;
+  p.X = X; p.Y = Y; p.U = U; p.ws = ws; p.h = h; p.w = w; p.pad = same_pad ? win / 2 : 0;
+  p.hp = h + 2 * p.pad; p.wp = w + 2 * p.pad; p.oh = p.hp - kVgR; p.ow = p.wp - kVgR;
+  ICADV_REQUIRE(planes > 0 && p.oh > 0 && p.ow > 0, "image smaller than the window");
+  p.c1 = c1; p.c2 = c2; p.ccs = last_level ? 0.f : 1.f; p.css = last_level ? 1.f : 0.f;
+  for (int k = 0; k < kMaxWin; ++k) p.taps[k] = win_taps_host[k];
+  const int strips = (p.wp + (kVgT - kVgR) - 1) / (kVgT - kVgR);
+  const int nseg = vg_segments(planes, p.hp, p.wp, &p.seg_rows);
+  ICADV_REQUIRE(planes <= 65535 && nseg <= 65535, "grid too large");
+  dim3 grid(strips, nseg, planes);
+  ssim_level_vg_kernel<<<grid, kVgT, 0, as_stream(stream)>>>(p);
+  ICADV_CUDA_TRY(cudaGetLastError());
+  ssim_finalize_kernel<<<(planes + 127) / 128, 128, 0, as_stream(stream)>>>(ws, ssim_sum, cs_sum, planes, strips * nseg);
+  ICADV_CUDA_TRY(cudaGetLastError());
+  return ICADV_OK;
+}
+
+int icadv_ssim_combine(float* U, const float* coef, const float* Dnext, int planes, int h, int w, int next_h, int next_w,
+                       int pad_h, int pad_w, icadv_stream_t stream) {
+  ICADV_REQUIRE(U && coef && planes > 0 && h > 0 && w > 0, "bad ssim_combine args");
+  ICADV_REQUIRE(planes <= 65535 && h <= 65535, "grid too large");
+  dim3 grid((w + 1023) / 1024, h, planes);
+  ssim_combine_kernel<<<grid, 256, 0, as_stream(stream)>>>(U, coef, Dnext, h, w, next_h, next_w, pad_h, pad_w);
   ICADV_CUDA_TRY(cudaGetLastError());
   return ICADV_OK;
 }

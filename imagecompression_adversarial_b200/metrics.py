@@ -117,11 +117,43 @@ def _level_bwd(X, Y, coef_cs, coef_ss, dXnext, pads, taps, c1, c2, same_pad=Fals
     return dX
 
 
+def _level_value_grad(X, Y, taps, same_pad, c1, c2, last):
+    """One level through the row-marching kernel: (mean ssim, mean cs) per plane and the unit gradient U of the level's
+    summed map (cs, or ssim at the last level) with respect to X."""
+    planes, h, w = X.shape[0] * X.shape[1], X.shape[2], X.shape[3]
+    n = L.lib().icadv_ssim_vg_workspace_floats(planes, h, w, 1 if same_pad else 0)
+    ws = torch.empty(max(n, 1), device=X.device, dtype=torch.float32)
+    ss = torch.empty(planes, device=X.device, dtype=torch.float32)
+    cs = torch.empty(planes, device=X.device, dtype=torch.float32)
+    U = torch.empty_like(X)
+    arr = (C.c_float * len(taps))(*taps)
+    L.call("icadv_ssim_level_value_grad", _p(X), _p(Y), _p(U), _p(ws), _p(ss), _p(cs), planes, h, w, arr, len(taps),
+           1 if same_pad else 0, float(c1), float(c2), 1 if last else 0, _stream())
+    oh, ow = (h, w) if same_pad else (h - len(taps) + 1, w - len(taps) + 1)
+    return ss.view(X.shape[0], X.shape[1]) / (oh * ow), cs.view(X.shape[0], X.shape[1]) / (oh * ow), U
+
+
+def _combine(U, coef, Dnext, pads):
+    planes, h, w = U.shape[0] * U.shape[1], U.shape[2], U.shape[3]
+    nh, nw = (Dnext.shape[2], Dnext.shape[3]) if Dnext is not None else (0, 0)
+    L.call("icadv_ssim_combine", _p(U), _p(coef), _p(Dnext), planes, h, w, nh, nw, pads[0], pads[1], _stream())
+    return U
+
+
+FUSED_VALUE_GRAD = True   # False: the two-pass tile kernels (level forward, then level backward) -- kept for A/B tests
+
+
 def ms_ssim_value_and_grad(X, Y, upstream, data_range=1.0, win_size=11, win_sigma=1.5, weights=WEIGHTS, K=(0.01, 0.03)):
     """Per-image MS-SSIM (variant 1, mean over channels) and the gradient of ``sum_b upstream[b] * value[b]`` with
-    respect to X.  This is what autograd of ``ms_ssim(X, Y)`` delivers in attack_rd.py:336,362, one image per row."""
+    respect to X.  This is what autograd of ``ms_ssim(X, Y)`` delivers in attack_rd.py:336,362, one image per row.
+
+    11-tap window (the reference's): ONE pass per level produces the level value and the unit gradient of its map
+    (``icadv_ssim_level_value_grad``); the per-plane chain-rule weights and the pooling chain are applied afterwards,
+    coarse to fine, by ``icadv_ssim_combine``."""
     assert X.shape == Y.shape and X.dim() == 4 and min(X.shape[-2:]) > (win_size - 1) * 2 ** 4
     X, Y = X.detach().contiguous().float(), Y.detach().contiguous().float()
+    if win_size == 11 and FUSED_VALUE_GRAD:
+        return _value_and_grad_fused(X, Y, upstream, data_range, win_size, win_sigma, weights, K)
     B, Cc = X.shape[0], X.shape[1]
     taps = _taps(win_size, win_sigma)
     c1, c2 = (K[0] * data_range) ** 2, (K[1] * data_range) ** 2
@@ -149,6 +181,36 @@ def ms_ssim_value_and_grad(X, Y, upstream, data_range=1.0, win_size=11, win_sigm
         last = lvl == nl - 1
         dnext = _level_bwd(xs[lvl], ys[lvl], zero if last else coef, coef if last else zero, dnext,
                            pads[lvl] if lvl < nl - 1 else (0, 0), taps, c1, c2)
+    return value, dnext
+
+
+def _value_and_grad_fused(X, Y, upstream, data_range, win_size, win_sigma, weights, K):
+    B, Cc = X.shape[0], X.shape[1]
+    taps = _taps(win_size, win_sigma)
+    c1, c2 = (K[0] * data_range) ** 2, (K[1] * data_range) ** 2
+    nl = len(weights)
+    x, y, pads, vals, npx, us = X, Y, [], [], [], []
+    for lvl in range(nl):
+        last = lvl == nl - 1
+        ss, cs, U = _level_value_grad(x, y, taps, False, c1, c2, last)
+        vals.append(torch.relu(ss if last else cs))
+        us.append(U)
+        npx.append((x.shape[2] - win_size + 1) * (x.shape[3] - win_size + 1))
+        if not last:
+            ph, pw = x.shape[2] % 2, x.shape[3] % 2
+            pads.append((ph, pw))
+            x, y = _pool(x, ph, pw), _pool(y, ph, pw)
+    w = _weights_tensor(X.device, weights)
+    V = torch.stack(vals, 0)                       # [levels, B, C]
+    P = torch.prod(V ** w, dim=0)                  # [B, C]
+    value = P.mean(1)
+    dP = (upstream.view(B, 1).to(torch.float32) / Cc).expand(B, Cc)
+    dV = torch.where(V > 0, dP.unsqueeze(0) * w * P.unsqueeze(0) / V.clamp(min=1e-30), torch.zeros_like(V))
+    scale = [1.0 / n for n in npx]
+    dnext = None
+    for lvl in range(nl - 1, -1, -1):
+        coef = (dV[lvl] * scale[lvl]).reshape(-1).contiguous()
+        dnext = _combine(us[lvl], coef, dnext, pads[lvl] if lvl < nl - 1 else (0, 0))
     return value, dnext
 
 

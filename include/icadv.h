@@ -341,6 +341,18 @@ int icadv_ssim_level_backward(const float* X, const float* Y, const float* coef_
                               const float* dXnext, float* dX, int planes, int h, int w, int next_h, int next_w,
                               int pad_h, int pad_w, const float* win_taps_host, int win, int same_pad, float c1,
                               float c2, icadv_stream_t stream);
+/* Value AND gradient of one level in one pass (11-tap window; csrc/icadv_msssim.cu, row-marching kernel): the per-plane
+ * sums as icadv_ssim_level, plus U = d(sum of the level's map)/dX at unit upstream weight -- the cs map, or the ssim map
+ * when last_level != 0.  The upstream weights depend on every level's value (ms_ssim = prod_l relu(v_l)^w_l,
+ * pytorch_msssim.ms_ssim at attack_rd.py:336,362), so the host applies them afterwards, coarse to fine, with
+ * icadv_ssim_combine: U_l <- coef[plane] * U_l + 0.25 * D_{l+1}[pool parent] (Dnext nullable at the coarsest level;
+ * pad_h / pad_w = the padding of the avg_pool2d that produced level l+1). */
+int icadv_ssim_vg_workspace_floats(int planes, int h, int w, int same_pad);
+int icadv_ssim_level_value_grad(const float* X, const float* Y, float* U, float* ws, float* ssim_sum, float* cs_sum,
+                                int planes, int h, int w, const float* win_taps_host, int win, int same_pad, float c1,
+                                float c2, int last_level, icadv_stream_t stream);
+int icadv_ssim_combine(float* U, const float* coef, const float* Dnext, int planes, int h, int w, int next_h, int next_w,
+                       int pad_h, int pad_w, icadv_stream_t stream);
 /* F.avg_pool2d(x, 2, stride 2, padding (pad_h, pad_w)) between levels */
 int icadv_avgpool2(const float* x, float* y, int planes, int h, int w, int pad_h, int pad_w,
                    icadv_stream_t stream);

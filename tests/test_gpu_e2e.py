@@ -183,6 +183,50 @@ def test_msssim_gradient_matches_oracle_autograd(dev):
         assert err < 2e-3, err
 
 
+@pytest.mark.parametrize("shape", [(2, 3, 192, 256), (1, 3, 177, 203), (3, 1, 400, 181), (1, 3, 512, 768)])
+def test_msssim_fused_value_grad_equals_two_pass_kernels(dev, shape):
+    """The row-marching value + gradient kernel (one pass per level, icadv_ssim_level_value_grad + icadv_ssim_combine)
+    against the two-pass tile kernels (icadv_ssim_level, then icadv_ssim_level_backward): same values and gradients up
+    to fp32 summation order; odd sizes exercise the padded 2x2 pooling chain, strips and row segments."""
+    from imagecompression_adversarial_b200 import metrics
+    g = torch.Generator(device=dev).manual_seed(5)
+    a = torch.rand(*shape, device=dev, generator=g)
+    b = (a + 0.05 * torch.randn(*shape, device=dev, generator=g)).clamp(0, 1)
+    up = torch.linspace(1.0, -0.5, shape[0], device=dev)
+    v1, g1 = metrics.ms_ssim_value_and_grad(a, b, up)
+    metrics.FUSED_VALUE_GRAD = False
+    try:
+        v0, g0 = metrics.ms_ssim_value_and_grad(a, b, up)
+    finally:
+        metrics.FUSED_VALUE_GRAD = True
+    torch.testing.assert_close(v1, v0, rtol=0, atol=2e-6)
+    assert torch.isfinite(g1).all()
+    err = float((g1 - g0).abs().max() / g0.abs().max())
+    assert err < 2e-4, err
+
+
+@pytest.mark.parametrize("same_pad,last", [(False, False), (False, True), (True, False), (True, True)])
+def test_msssim_level_value_grad_kernel_matches_level_kernels(dev, same_pad, last):
+    """One level, both paddings (valid window = pytorch_msssim; zero "same" padding = utils/torch_msssim.py:26-52) and
+    both maps (cs; ssim at the last level): sums against icadv_ssim_level, unit gradient against
+    icadv_ssim_level_backward with unit coefficients."""
+    from imagecompression_adversarial_b200 import metrics
+    g = torch.Generator(device=dev).manual_seed(9)
+    a = torch.rand(2, 3, 150, 331, device=dev, generator=g)
+    b = (a + 0.1 * torch.randn(2, 3, 150, 331, device=dev, generator=g)).clamp(0, 1)
+    taps = metrics._taps(11, 1.5)
+    c1, c2 = 1e-4, 9e-4
+    ss, cs, U = metrics._level_value_grad(a, b, taps, same_pad, c1, c2, last)
+    ss0, cs0 = metrics._level(a, b, taps, same_pad, c1, c2)
+    torch.testing.assert_close(ss, ss0, rtol=0, atol=2e-6)
+    torch.testing.assert_close(cs, cs0, rtol=0, atol=2e-6)
+    one, zero = torch.ones(6, device=dev), torch.zeros(6, device=dev)
+    U0 = metrics._level_bwd(a, b, zero if last else one, one if last else zero, None, (0, 0), taps, c1, c2,
+                            same_pad=same_pad)
+    err = float((U - U0).abs().max() / U0.abs().max())
+    assert err < 2e-4, err
+
+
 def test_msssim_operator_surface_is_differentiable_in_both_images(dev):
     """The calls the unmodified reference makes under autograd: ``1 - ms_ssim(im_s, im_in)`` (gradient to the SECOND
     image, attack_rd.py:336), ``ms_ssim(output_, output_s)`` (:362), ``MS_SSIM(...)(x_hat, target)`` (train.py:44,88),

@@ -69,9 +69,12 @@ def make_w(kind, cin_layer, cout_layer, k, dev, g):
     return w, x_ch
 
 
-def test_layout_roundtrip(dev):
+@pytest.mark.parametrize("shape", [(3, 5, 37, 41), (2, 3, 37, 41), (2, 3, 512, 768), (1, 1, 9, 300), (2, 2, 16, 16),
+                                   (3, 4, 33, 65), (1, 192, 8, 12)])
+def test_layout_roundtrip(dev, shape):
+    """32x32-tile transpose (C > 4) and the few-channel form (RGB images)."""
     from imagecompression_adversarial_b200 import ops
-    x = torch.randn(3, 5, 37, 41, device=dev)
+    x = torch.randn(*shape, device=dev)
     y = ops.nchw_to_nhwc(x)
     assert torch.equal(y, x.permute(0, 2, 3, 1).contiguous())
     assert torch.equal(ops.nhwc_to_nchw(y), x)
