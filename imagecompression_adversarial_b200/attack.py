@@ -2,8 +2,10 @@
 (self_ensemble.py:173-252) on the fused device-resident loop.
 
 ``attack_(im_s, net, args)`` keeps the reference's signature and return tuple.  Differences, all stated:
-  * a batch is attacked with PER-IMAGE budget tests (each image behaves like an N=1 call); the reference's
-    batch-mean test is recovered with N=1 (the CLI path);
+  * a batch is attacked with PER-IMAGE budget tests by default (each image behaves like an N=1 call = the CLI path,
+    which attacks one image at a time); ``args.budget_scope = "batch"`` selects the reference's literal batch semantics
+    (loss_i / loss_o are means over the batch, one shared branch per iteration: attack_rd.py:333-364 on a batch), which
+    is what ``training.adv_train_step`` uses because train.py:342 hands ``attack_`` a whole training batch;
   * no host synchronisation inside the loop (the reference syncs every step at attack_rd.py:334).
 """
 import math
@@ -56,15 +58,17 @@ def _fused_stacks(net):
 def _engine_for(net, im_s, args, roi=None):
     n, _, h, w = im_s.shape
     force = getattr(args, "force_branch", -1)
+    scope = getattr(args, "budget_scope", "image")
     key = (id(net), n, h, w, args.steps, float(args.epsilon), float(args.noise), float(args.lr_attack),
-           bool(args.clamp), args.att_metric, force, roi.key() if roi is not None else None, precision.get())
+           bool(args.clamp), args.att_metric, force, roi.key() if roi is not None else None, precision.get(), scope)
     eng = _ENGINES.get(key)
     if eng is None:
         # plain conv/GDN stacks: fused launch programs; anything else: traced into a static launch program (speed mode) or
         # walked module by module through autograd (parity mode: every contraction K-sliced and split, precision.py)
         cls = AttackEngine if _fused_stacks(net) else (GenericAttackEngine if precision.split() else TapeAttackEngine)
         eng = cls(net, n, h, w, steps=args.steps, epsilon=args.epsilon, noise_budget=args.noise,
-                  lr_attack=args.lr_attack, clamp=args.clamp, att_metric=args.att_metric, force_branch=force, roi=roi)
+                  lr_attack=args.lr_attack, clamp=args.clamp, att_metric=args.att_metric, force_branch=force, roi=roi,
+                  budget_scope=scope)
         _ENGINES.clear()  # one live engine: its buffers are sized for the batch
         _ENGINES[key] = eng
     else:

@@ -38,15 +38,31 @@ struct FinalizeArgs {
 };
 
 __device__ __forceinline__ void perturb_finalize(const float* ws, const icadv_perturb_state& st, const FinalizeArgs& fa,
-                                                 int* s_branch) {
+                                                 int* s_branch, float* s_loss) {
   for (int n = threadIdx.x; n < fa.n_img; n += blockDim.x) {
     float s = 0.f;
     for (int b = 0; b < kRedBlocks; ++b) s += __ldcg(ws + (int64_t)n * kRedBlocks + b);   // written by other blocks
     const float loss_i = (float)((double)s * fa.inv_per_img);
     st.sum_d2[n] = s;
     st.loss_i[n] = loss_i;
+    s_loss[n] = loss_i;
+  }
+  __syncthreads();
+  // budget test on the BATCH mean (ge_test bit 1): the reference's attack_our takes torch.mean over the whole batch
+  // (attack_rd.py:333-334), which is what train.py:342 runs on a training batch -- one shared branch per iteration
+  const bool batch_budget = (fa.ge_test & 2) != 0;
+  if (batch_budget) {
+    if (threadIdx.x == 0) {
+      double acc = 0.0;
+      for (int k = 0; k < fa.n_img; ++k) acc += (double)s_loss[k];
+      s_loss[1024] = (float)(acc / (double)fa.n_img);
+    }
+    __syncthreads();
+  }
+  for (int n = threadIdx.x; n < fa.n_img; n += blockDim.x) {
+    const float loss_i = batch_budget ? s_loss[1024] : s_loss[n];
     // attack_rd.py:334 -- A when over budget (">"); the ROI variant switches on ">=" (attack_data.py:219)
-    int br = (fa.ge_test ? (loss_i >= fa.budget) : (loss_i > fa.budget)) ? 0 : 1;
+    int br = ((fa.ge_test & 1) ? (loss_i >= fa.budget) : (loss_i > fa.budget)) ? 0 : 1;
     if (fa.force_branch >= 0) br = fa.force_branch;
     st.branch[n] = br;
     s_branch[n] = br;
@@ -83,6 +99,7 @@ __global__ void __launch_bounds__(256) perturb_forward_kernel(const float4* __re
                                                               FinalizeArgs fa) {
   __shared__ float red[8];
   __shared__ int s_branch[1024];
+  __shared__ float s_loss[1025];
   __shared__ int s_last;
   const int n = blockIdx.y;
   const int64_t base = (int64_t)n * per_img4;
@@ -110,7 +127,7 @@ __global__ void __launch_bounds__(256) perturb_forward_kernel(const float4* __re
   __syncthreads();
   if (!s_last) return;
   __threadfence();
-  perturb_finalize(ws, st, fa, s_branch);
+  perturb_finalize(ws, st, fa, s_branch, s_loss);
 }
 
 // ---- backward of both clamp pairs + Adam, fused

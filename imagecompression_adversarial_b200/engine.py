@@ -45,8 +45,18 @@ class RoiSpec:
 
 class AttackEngine:
     def __init__(self, net, n_img, height, width, *, steps, epsilon=16.0, noise_budget=1e-4, lr_attack=0.01,
-                 clamp=True, att_metric="L2", force_branch=-1, use_graph=True, device=None, roi=None):
+                 clamp=True, att_metric="L2", force_branch=-1, use_graph=True, device=None, roi=None,
+                 budget_scope="image"):
+        """``budget_scope``: "image" = every image tests its own loss_i against the budget (N independent runs of the
+        reference CLI, which attacks one image at a time); "batch" = the reference's literal batch semantics -- loss_i,
+        loss_o and the ms-ssim terms are means over the whole batch and ONE branch is taken per iteration
+        (attack_rd.py:333-364 on a batch, i.e. what train.py:342 runs)."""
         ops.require_device()
+        if budget_scope not in ("image", "batch"):
+            raise L.IcadvError(f"AttackEngine: budget_scope {budget_scope!r} (image, batch)")
+        self.batch_budget = budget_scope == "batch"
+        # a batch-mean loss spreads its gradient: every per-image seed carries 1 / n_img (Adam's eps makes the scale matter)
+        self._bscale = 1.0 / n_img if self.batch_budget else 1.0
         if att_metric not in ("L2", "ms-ssim"):
             raise L.IcadvError(f"AttackEngine: -att_metric {att_metric} is not supported (L2, ms-ssim)")
         self.att_metric = att_metric
@@ -77,7 +87,7 @@ class AttackEngine:
         self._graph_if_ok = True           # engines whose network pass allocates (autograd walk) switch it off
         self.iterations_done = 0
         self.im_s_nchw = self.output_s_nchw = None
-        self._ones = torch.ones(n_img, device=dev, dtype=torch.float32)
+        self._ones = torch.full((n_img,), self._bscale, device=dev, dtype=torch.float32)   # upstream of the ms-ssim terms
         if att_metric == "ms-ssim":
             from . import metrics
             metrics._weights_tensor(dev, metrics.WEIGHTS)   # created outside any graph capture
@@ -140,7 +150,7 @@ class AttackEngine:
             return rows
         rows.append({"name": "perturb_update_adam (clamp backward + Adam)",
                      "launch": lambda: ops.perturb_update_adam(self.im_s, self.noise, self.ga.g_in, self.m, self.v, self.st,
-                                                               eps=self.eps, gradA_scale=1.0 / self.per_img,
+                                                               eps=self.eps, gradA_scale=self._bscale / self.per_img,
                                                                gradB_scale=1.0, w_in=self.w_in),
                      "kernels": 1, "flops": 0.0, "bytes": 8 * img, "bound": "hbm"})
         return rows
@@ -177,13 +187,14 @@ class AttackEngine:
     def _perturb_forward(self):
         ops.perturb_forward(self.im_s, self.noise, self.im_in, self.st, eps=self.eps, budget=self.budget,
                             force_branch=self.force_branch, lr0=self.lr0, lr_gamma=0.33,
-                            sched_period=self.steps // 3, w_in=self.w_in, ge_test=self.roi is not None)
+                            sched_period=self.steps // 3, w_in=self.w_in, ge_test=self.roi is not None,
+                            batch_budget=self.batch_budget)
 
     def _output_loss(self, x_out, g_x):
         # untargeted: loss = 1 - mean(d^2) (attack_rd.py:364), seed +2d/P; ROI: loss = +mean(w d^2), seed -2wd/P
         sign = -1.0 if self.roi is not None else 1.0
         ops.output_loss(x_out, self.output_s, g_x, self.ws_out, self.loss_o_sum, do_clamp=self.clamp,
-                        grad_scale=sign / self.per_img, active=self.st.active, n_active=self.st.n_active,
+                        grad_scale=sign * self._bscale / self.per_img, active=self.st.active, n_active=self.st.n_active,
                         w_out=self.w_out)
 
     def _network_pass(self):
@@ -218,7 +229,7 @@ class AttackEngine:
             self._perturb_forward()
             g_in = self._network_pass()
         ops.perturb_update_adam(self.im_s, self.noise, g_in, self.m, self.v, self.st, eps=self.eps,
-                                gradA_scale=1.0 / self.per_img, gradB_scale=1.0, w_in=self.w_in)
+                                gradA_scale=self._bscale / self.per_img, gradB_scale=1.0, w_in=self.w_in)
 
     def _msssim_budget_branch(self):
         """Budget branch of -att_metric ms-ssim: loss = 1 - ms_ssim(im_s, im_in) (attack_rd.py:335-336) and its gradient
@@ -256,7 +267,7 @@ class AttackEngine:
         from the CUDA graph's private pool during capture and is reused by every replay."""
         ops.perturb_forward(self.im_s, self.noise, self.im_in, self.st, eps=self.eps, budget=self.budget,
                             force_branch=self.force_branch, lr0=self.lr0, lr_gamma=0.33,
-                            sched_period=self.steps // 3)
+                            sched_period=self.steps // 3, batch_budget=self.batch_budget)
         self._msssim_budget_branch()
         self.ga.forward()
         self.gs.forward()

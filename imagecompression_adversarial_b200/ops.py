@@ -280,11 +280,12 @@ class PerturbState:
 
 
 def perturb_forward(im_s, noise, im_in, st, *, eps, budget, force_branch=-1, lr0=0.01, lr_gamma=0.33, sched_period,
-                    beta1=0.9, beta2=0.999, w_in=None, ge_test=False):
+                    beta1=0.9, beta2=0.999, w_in=None, ge_test=False, batch_budget=False):
+    """``batch_budget``: one budget test on the batch mean of loss_i (attack_rd.py:333 on a batch, train.py:342)."""
     per_img = im_s[0].numel()
     L.call("icadv_perturb_forward_roi", _p(im_s), _p(noise), _p(im_in), _p(st.ws), C.byref(st.c), st.n_img, per_img,
            float(eps), float(budget), int(force_branch), float(lr0), float(lr_gamma), int(sched_period), float(beta1),
-           float(beta2), _p(w_in), 1 if ge_test else 0, _stream())
+           float(beta2), _p(w_in), (1 if ge_test else 0) | (2 if batch_budget else 0), _stream())
 
 
 def perturb_update_adam(im_s, noise, g_in, m, v, st, *, eps, beta1=0.9, beta2=0.999, adam_eps=1e-8, gradA_scale,

@@ -198,8 +198,12 @@ def configure_optimizers(net, args):
             FusedAdamClip([named[n] for n in aux], lr=1e-3, max_norm=None))
 
 
-def adv_train_step(batch_x, net, args, criterion, optimizer, aux_optimizer, group=None, timings=None):
+def adv_train_step(batch_x, net, args, criterion, optimizer, aux_optimizer, group=None, timings=None,
+                   budget_scope="batch"):
     """One iteration of train.py:335-366 with N_ADV = 0.  Returns (out_criterion, aux_loss).
+    ``budget_scope``: "batch" (default) = the reference's semantics on this path -- train.py:342 passes the whole batch
+    to ``attack_``, whose ``attack_our`` tests the budget on the batch mean (attack_rd.py:333-334) and takes one branch
+    for all images; "image" = every image tests its own budget (what the sharded CLI attack does).
     ``timings`` (a dict of lists, benchmark use): receives the CUDA-event times in ms of the attack part
     (``attack_ms``), the codec update (``update_ms``) and, inside it, the gradient all-reduce (``allreduce_ms``);
     measuring them synchronises the stream three times per step."""
@@ -207,6 +211,10 @@ def adv_train_step(batch_x, net, args, criterion, optimizer, aux_optimizer, grou
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)] if timings is not None else None
     if ev:
         ev[0].record()
+    if getattr(args, "budget_scope", None) != budget_scope:
+        import copy
+        args = copy.copy(args)
+        args.budget_scope = budget_scope
     batch_adv = attack_(batch_x, net, args)[0].detach()                  # :342-343
     if ev:
         ev[1].record()

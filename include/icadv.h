@@ -210,7 +210,10 @@ int icadv_perturb_update_adam(const float* im_s, float* noise, const float* g_in
  *   loss_i = mean(w_in d_in^2),  w_in = mask_tar + lamb_bkg_in * mask_bkg;  branch A iff loss_i >= budget (ge_test);
  *   loss_o = mean(w_out (ref - o)^2), ref = output_t inside the ROI / output_s outside (mixed by the caller),
  *            w_out = lamb_tar * mask_tar + lamb_bkg_out * mask_bkg; minimised: pass grad_scale = -1/per_img.
- * w_in / w_out: [per_img] floats in the image layout, shared by all images of the batch; NULL = all ones. */
+ * w_in / w_out: [per_img] floats in the image layout, shared by all images of the batch; NULL = all ones.
+ * ge_test is a flag word: bit 0 = switch on ">=" (ROI) instead of ">" (attack_rd.py:334); bit 1 = test the budget on the
+ * BATCH mean of loss_i, one shared branch for all images -- torch.mean over the batch at attack_rd.py:333, the semantics
+ * train.py:342 gets on a training batch (the per-image test, bit 1 clear, is N independent CLI runs). */
 int icadv_perturb_forward_roi(const float* im_s, const float* noise, float* im_in, float* ws,
                               const icadv_perturb_state* st, int n_img, int64_t per_img, float eps,
                               float noise_budget, int force_branch, double lr0, double lr_gamma, int sched_period,

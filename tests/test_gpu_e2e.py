@@ -315,6 +315,44 @@ def test_attack_trajectory_matches_oracle(dev, model, quality, hw, n, steps, met
         assert abs(float(bpp) - float(o[4])) < max(1e-3, 5e-3 * float(o[4]))
 
 
+@pytest.mark.parametrize("metric,force,steps", [("L2", -1, 12), ("L2", 1, 8), ("ms-ssim", -1, 6)])
+def test_batch_budget_scope_matches_the_reference_batch_semantics(dev, metric, force, steps):
+    """``args.budget_scope = "batch"`` (what training.adv_train_step uses): the reference's attack_our on a BATCH --
+    loss_i and the loss are torch.mean over all images, one branch per iteration for the whole batch
+    (attack_rd.py:333-364 as train.py:342 calls it) -- against the oracle's attack_ run on the same batch.  The batch
+    mean also scales every per-image gradient by 1/B, which Adam's eps makes visible; forced network branch included."""
+    from imagecompression_adversarial_b200 import attack as patk
+    from oracle import attack as oatk
+    onet, pnet = pair("hyper", 1, dev)
+    x = images(3, 192, 256, dev)    # the final eval computes MS-SSIM: > 160 pixels a side
+    args = oatk.default_args(model="hyper", quality=1, metric="mse", steps=steps, att_metric=metric,
+                             noise=1e-4 if metric == "L2" else 2e-5)
+    args.force_branch = force
+    args.budget_scope = "batch"
+    rec, orec = [], []
+    im_adv, out_adv, out_s, bpp_ori, bpp, mse, vi = patk.attack_(x, pnet, args, record=rec)
+    o = oatk.attack_(x, onet, args, record=orec)
+    assert len(rec) == len(orec) == steps
+    for t, (br, loss, loss_i) in enumerate(orec):
+        pb = [int(v) for v in rec[t][0]]
+        assert len(set(pb)) == 1, (t, pb)                       # one shared branch
+        pli, pl = float(rec[t][1].mean()), float(rec[t][2].mean())
+        if (pb[0] == 1) != (br == "B"):
+            assert abs(loss_i - args.noise) < 2e-3 * args.noise, (t, loss_i, pli)   # near-tie at the budget boundary
+            break
+        assert abs(pli - loss_i) <= 2.5e-3 * max(loss_i, 1e-7) + 1e-9, (t, pli, loss_i)
+        tol = 1e-3 if pb[0] == 1 else 2.5e-3
+        assert abs(pl - loss) <= tol * abs(loss) + 1e-9, (t, pl, loss)
+    else:
+        assert abs(psnr(im_adv, x) - psnr(o[0], x)) < 0.05
+        assert abs(psnr(out_adv, out_s) - psnr(o[1], o[2])) < 0.05
+    # and the per-image scope on the same batch is a different trajectory as soon as the images disagree about the budget
+    args.budget_scope = "image"
+    rec_i = []
+    patk.attack_(x, pnet, args, record=rec_i)
+    assert len(rec_i) == steps
+
+
 @pytest.mark.parametrize("metric,hw", [("L2", (64, 64)), ("ms-ssim", (192, 192))])
 def test_graph_replay_equals_eager(dev, metric, hw):
     """The whole iteration -- for -att_metric ms-ssim including both 5-level MS-SSIM value-and-gradient compositions --
