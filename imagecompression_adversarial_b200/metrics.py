@@ -2,8 +2,8 @@
 
 ``ms_ssim`` / ``MS_SSIM`` mirror ``pytorch_msssim`` (attack_rd.py:19; train.py:18,44) -- variant 1;
 ``MS_SSIM_v2`` mirrors ``utils/torch_msssim.MS_SSIM`` (utils/torch_msssim.py:18-76) -- variant 2.
-All three are differentiable with respect to BOTH images (autograd Functions whose backward is
-``ssim_level_backward_kernel``): the unmodified ``attack_our`` ms-ssim branches (``1 - ms_ssim(im_s, im_in)``,
+All three are differentiable with respect to BOTH images (autograd Functions on the one-pass value-and-gradient level
+kernel for the 11-tap window, on ``ssim_level_backward_kernel`` otherwise): the unmodified ``attack_our`` ms-ssim branches (``1 - ms_ssim(im_s, im_in)``,
 ``ms_ssim(output_, output_s)``, attack_rd.py:336,362) and the ms-ssim RD loss (train.py:44,88) differentiate through them.
 """
 import ctypes as C
@@ -57,25 +57,34 @@ def _pool(X, ph, pw):
 
 
 class _MsSsimFn(torch.autograd.Function):
-    """Variant 1 with gradients to both images.  The forward is the plain kernel composition; the backward recomputes
-    the pyramid (nothing image-sized is saved except the two inputs) through ``ms_ssim_value_and_grad``."""
+    """Variant 1 with gradients to both images.  The per-image value is linear in nothing but its own upstream weight,
+    so the forward runs the one-pass value-and-gradient composition once per differentiable argument with UNIT upstream
+    and keeps that gradient; the backward only scales it (the reference's autograd walks the pyramid twice).  SSIM is
+    symmetric in (X, Y): the gradient with respect to Y is the same composition with the images swapped."""
 
     @staticmethod
     def forward(ctx, X, Y, size_average, kw):
-        ctx.save_for_backward(X.detach(), Y.detach())
-        ctx.size_average, ctx.kw = size_average, kw
-        return _ms_ssim_forward(X, Y, size_average=size_average, **kw)
+        B = X.shape[0]
+        ones = torch.ones(B, device=X.device, dtype=torch.float32)
+        Xd, Yd = X.detach(), Y.detach()
+        val = gX = gY = None
+        if X.requires_grad:
+            val, gX = ms_ssim_value_and_grad(Xd, Yd, ones, **kw)
+        if Y.requires_grad:
+            val, gY = ms_ssim_value_and_grad(Yd, Xd, ones, **kw)
+        ctx.size_average, ctx.has = size_average, (gX is not None, gY is not None)
+        ctx.save_for_backward(*[g for g in (gX, gY) if g is not None])
+        return val.mean() if size_average else val
 
     @staticmethod
     def backward(ctx, g):
-        X, Y = ctx.saved_tensors
-        B = X.shape[0]
+        saved = list(ctx.saved_tensors)
+        gX = saved.pop(0) if ctx.has[0] else None
+        gY = saved.pop(0) if ctx.has[1] else None
+        B = (gX if gX is not None else gY).shape[0]
         up = (g.reshape(1).expand(B) / B) if ctx.size_average else g.reshape(B)
-        up = up.to(torch.float32).contiguous()
-        kw = ctx.kw
-        gX = ms_ssim_value_and_grad(X, Y, up, **kw)[1] if ctx.needs_input_grad[0] else None
-        gY = ms_ssim_value_and_grad(Y, X, up, **kw)[1] if ctx.needs_input_grad[1] else None   # SSIM is symmetric
-        return gX, gY, None, None
+        up = up.to(torch.float32).view(B, 1, 1, 1)
+        return (gX * up if gX is not None else None), (gY * up if gY is not None else None), None, None
 
 
 def ms_ssim(X, Y, data_range=1.0, size_average=True, win_size=11, win_sigma=1.5, weights=WEIGHTS, K=(0.01, 0.03)):
