@@ -61,6 +61,8 @@ _SIGS = {
     "icadv_unpack_weight": (C.c_int, [_fp, _fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "icadv_nchw_to_nhwc": (C.c_int, [_fp, _fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "icadv_nhwc_to_nchw": (C.c_int, [_fp, _fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "icadv_clamp01_nhwc_to_nchw": (C.c_int, [_fp, _fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "icadv_clamp01_backward_nchw_to_nhwc": (C.c_int, [_fp, _fp, _fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "icadv_pixel_shuffle": (C.c_int, [_fp, _fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "icadv_copy_channels": (C.c_int, [_fp, _fp, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "icadv_gdn_reparam": (C.c_int, [_fp, _fp, C.c_int, C.c_int, C.c_float, C.c_float, C.c_int, C.c_int, C.c_void_p]),

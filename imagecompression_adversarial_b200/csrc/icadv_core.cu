@@ -166,16 +166,31 @@ __global__ void transpose_cp_kernel(const float* __restrict__ src, float* __rest
 // 0.44 TB/s on the 151 MB images of the ms-ssim attack loop, scripts/msssim_profile.py).  Here a block moves 256 pixels:
 // the interleaved side is one contiguous run of 256*C floats (coalesced), the planar side C runs of 256 floats; the
 // shared-memory side reads at stride C, conflict-free for C = 1, 3 (odd) and 2-way for C = 2, 4.
-template <int C, bool TO_PLANAR>
+// FUSE: the [0, 1] clamp of the reconstruction (attack_rd.py:353-356, Up_bound(Low_bound(x, 0), 1)) rides on the copy --
+// forward on the way to planes, and its backward (utils/ops.py:28-56: a gradient passes a bound it sits on only if it
+// points back inside) on the way back, gated by the unclamped interleaved x.  The ms-ssim attack loop then has one launch
+// on each side of the value-and-gradient pyramid instead of three and a copy.
+__device__ __forceinline__ float clamp01_grad(float g, float x) {
+  const float lo = fmaxf(x, 0.f);
+  g = ((lo <= 1.f) || (g > 0.f)) ? g : 0.f;     // Up_bound(., 1) backward, evaluated at Low_bound(x, 0)
+  g = ((x >= 0.f) || (g < 0.f)) ? g : 0.f;      // Low_bound(., 0) backward
+  return g;
+}
+
+template <int C, bool TO_PLANAR, bool FUSE>
 __global__ void __launch_bounds__(256) interleave_small_kernel(const float* __restrict__ src, float* __restrict__ dst,
-                                                               int hw) {
+                                                               const float* __restrict__ gate_x, int hw) {
   __shared__ float tile[256 * C];
   const int64_t img = (int64_t)blockIdx.y * hw * C;
   const int p0 = blockIdx.x * 256, np = min(256, hw - p0), t = threadIdx.x;
   if (TO_PLANAR) {
     const float* in = src + img + (int64_t)p0 * C;
 #pragma unroll
-    for (int k = 0; k < C; ++k) if (t + k * 256 < np * C) tile[t + k * 256] = in[t + k * 256];
+    for (int k = 0; k < C; ++k)
+      if (t + k * 256 < np * C) {
+        const float v = in[t + k * 256];
+        tile[t + k * 256] = FUSE ? fminf(fmaxf(v, 0.f), 1.f) : v;
+      }
     __syncthreads();
     if (t < np) {
 #pragma unroll
@@ -188,20 +203,25 @@ __global__ void __launch_bounds__(256) interleave_small_kernel(const float* __re
     }
     __syncthreads();
     float* out = dst + img + (int64_t)p0 * C;
+    const float* gx = FUSE ? gate_x + img + (int64_t)p0 * C : nullptr;
 #pragma unroll
-    for (int k = 0; k < C; ++k) if (t + k * 256 < np * C) out[t + k * 256] = tile[t + k * 256];
+    for (int k = 0; k < C; ++k)
+      if (t + k * 256 < np * C) {
+        const float v = tile[t + k * 256];
+        out[t + k * 256] = FUSE ? clamp01_grad(v, gx[t + k * 256]) : v;
+      }
   }
 }
 
-template <bool TO_PLANAR>
-static int launch_interleave_small(const float* src, float* dst, int n, int c, int hw, cudaStream_t s) {
+template <bool TO_PLANAR, bool FUSE>
+static int launch_interleave_small(const float* src, float* dst, const float* gate_x, int n, int c, int hw, cudaStream_t s) {
   dim3 grid((hw + 255) / 256, n);
   ICADV_REQUIRE(n <= 65535, "transpose grid too large");
   switch (c) {
-    case 1: interleave_small_kernel<1, TO_PLANAR><<<grid, 256, 0, s>>>(src, dst, hw); break;
-    case 2: interleave_small_kernel<2, TO_PLANAR><<<grid, 256, 0, s>>>(src, dst, hw); break;
-    case 3: interleave_small_kernel<3, TO_PLANAR><<<grid, 256, 0, s>>>(src, dst, hw); break;
-    default: interleave_small_kernel<4, TO_PLANAR><<<grid, 256, 0, s>>>(src, dst, hw); break;
+    case 1: interleave_small_kernel<1, TO_PLANAR, FUSE><<<grid, 256, 0, s>>>(src, dst, gate_x, hw); break;
+    case 2: interleave_small_kernel<2, TO_PLANAR, FUSE><<<grid, 256, 0, s>>>(src, dst, gate_x, hw); break;
+    case 3: interleave_small_kernel<3, TO_PLANAR, FUSE><<<grid, 256, 0, s>>>(src, dst, gate_x, hw); break;
+    default: interleave_small_kernel<4, TO_PLANAR, FUSE><<<grid, 256, 0, s>>>(src, dst, gate_x, hw); break;
   }
   ICADV_CUDA_TRY(cudaGetLastError());
   return ICADV_OK;
@@ -412,14 +432,27 @@ static int launch_transpose(const float* src, float* dst, int batch, int rows, i
 
 int icadv_nchw_to_nhwc(const float* src, float* dst, int n, int c, int h, int w, icadv_stream_t stream) {
   ICADV_REQUIRE(src && dst, "null pointer");
-  if (c <= 4) return launch_interleave_small<false>(src, dst, n, c, h * w, as_stream(stream));
+  if (c <= 4) return launch_interleave_small<false, false>(src, dst, nullptr, n, c, h * w, as_stream(stream));
   return launch_transpose(src, dst, n, c, h * w, as_stream(stream));  // [n][c][hw] -> [n][hw][c]
 }
 
 int icadv_nhwc_to_nchw(const float* src, float* dst, int n, int c, int h, int w, icadv_stream_t stream) {
   ICADV_REQUIRE(src && dst, "null pointer");
-  if (c <= 4) return launch_interleave_small<true>(src, dst, n, c, h * w, as_stream(stream));
+  if (c <= 4) return launch_interleave_small<true, false>(src, dst, nullptr, n, c, h * w, as_stream(stream));
   return launch_transpose(src, dst, n, h * w, c, as_stream(stream));  // [n][hw][c] -> [n][c][hw]
+}
+
+int icadv_clamp01_nhwc_to_nchw(const float* x_nhwc, float* y_nchw, int n, int c, int h, int w, icadv_stream_t stream) {
+  ICADV_REQUIRE(x_nhwc && y_nchw, "null pointer");
+  ICADV_REQUIRE(c >= 1 && c <= 4, "clamp01_nhwc_to_nchw takes images (1..4 channels)");
+  return launch_interleave_small<true, true>(x_nhwc, y_nchw, nullptr, n, c, h * w, as_stream(stream));
+}
+
+int icadv_clamp01_backward_nchw_to_nhwc(const float* g_nchw, const float* x_nhwc, float* gx_nhwc, int n, int c, int h,
+                                        int w, icadv_stream_t stream) {
+  ICADV_REQUIRE(g_nchw && x_nhwc && gx_nhwc, "null pointer");
+  ICADV_REQUIRE(c >= 1 && c <= 4, "clamp01_backward_nchw_to_nhwc takes images (1..4 channels)");
+  return launch_interleave_small<false, true>(g_nchw, gx_nhwc, x_nhwc, n, c, h * w, as_stream(stream));
 }
 
 int icadv_gdn_reparam(const float* raw, float* eff, int rows, int cols, float bound, float pedestal, int transpose,

@@ -635,6 +635,26 @@ __global__ void __launch_bounds__(kVgT, 4) ssim_level_vg_kernel(const SsimVgPara
 
 // D_l = coef[plane] * U_l + 0.25 * D_{l+1}[pool parent], in place, coarse to fine: the chain rule through
 // value = prod_l relu(level value)^w_l and through F.avg_pool2d(2, padding (ph, pw)) between levels.
+// w % 4 == 0 and an unpadded pool (pw = 0): four pixels per thread, one float4 of U and one float2 of parents
+__global__ void __launch_bounds__(256) ssim_combine4_kernel(float* __restrict__ U, const float* __restrict__ coef,
+                                                            const float* __restrict__ Dnext, int h, int w4, int nh, int nw,
+                                                            int ph) {
+  const int plane = blockIdx.y;
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  if (i >= h * w4) return;
+  const int gy = i / w4, g4 = i - gy * w4;
+  const float c = coef[plane];
+  float4* row = reinterpret_cast<float4*>(U + ((int64_t)plane * h + gy) * (w4 * 4));
+  float4 u = row[g4];
+  float2 par = make_float2(0.f, 0.f);
+  const int py = (gy + ph) >> 1;
+  if (Dnext != nullptr && py < nh)
+    par = __ldg(reinterpret_cast<const float2*>(Dnext + ((int64_t)plane * nh + py) * nw) + g4);
+  u.x = fmaf(0.25f, par.x, c * u.x); u.y = fmaf(0.25f, par.x, c * u.y);
+  u.z = fmaf(0.25f, par.y, c * u.z); u.w = fmaf(0.25f, par.y, c * u.w);
+  row[g4] = u;
+}
+
 __global__ void __launch_bounds__(256) ssim_combine_kernel(float* __restrict__ U, const float* __restrict__ coef,
                                                            const float* __restrict__ Dnext, int h, int w, int nh, int nw,
                                                            int ph, int pw) {
@@ -774,6 +794,14 @@ int icadv_ssim_combine(float* U, const float* coef, const float* Dnext, int plan
                        int pad_h, int pad_w, icadv_stream_t stream) {
   ICADV_REQUIRE(U && coef && planes > 0 && h > 0 && w > 0, "bad ssim_combine args");
   ICADV_REQUIRE(planes <= 65535 && h <= 65535, "grid too large");
+  // the vector form needs 16-byte rows of U and 8-byte rows of parents that cover every pixel pair (nw = w / 2)
+  const bool vec = w % 4 == 0 && (Dnext == nullptr || (pad_w == 0 && next_w == w / 2));
+  if (vec) {
+    dim3 grid4((h * (w / 4) + 255) / 256, planes);
+    ssim_combine4_kernel<<<grid4, 256, 0, as_stream(stream)>>>(U, coef, Dnext, h, w / 4, next_h, next_w, pad_h);
+    ICADV_CUDA_TRY(cudaGetLastError());
+    return ICADV_OK;
+  }
   dim3 grid((w + 1023) / 1024, h, planes);
   ssim_combine_kernel<<<grid, 256, 0, as_stream(stream)>>>(U, coef, Dnext, h, w, next_h, next_w, pad_h, pad_w);
   ICADV_CUDA_TRY(cudaGetLastError());

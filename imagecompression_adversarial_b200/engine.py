@@ -136,7 +136,7 @@ class AttackEngine:
         stack(self.gs, self.gs.fwd, self.gs.fwd_info)
         if msssim:
             rows.append({"name": "ms_ssim(clamp(x_out), output_s) value + gradient + clamp rules",
-                         "launch": self._msssim_output_loss, "kernels": 29, "flops": 0.0, "bytes": ms_bytes + 6 * img,
+                         "launch": self._msssim_output_loss, "kernels": 25, "flops": 0.0, "bytes": ms_bytes + img,
                          "bound": "hbm"})
         else:
             rows.append({"name": "output_loss (clamp + MSE + gradient seed)",
@@ -243,17 +243,16 @@ class AttackEngine:
         """Network branch: loss = ms_ssim(clamp(x_out), output_s) (attack_rd.py:353-362); writes the gradient seed g_x."""
         from . import metrics
         x = self.x_out
+        # the clamp and its gradient rules ride on the two layout copies around the pyramid (one launch each side)
+        out = ops.clamp01_nhwc_to_nchw(x) if self.clamp else ops.nhwc_to_nchw(x)
+        ms_b, g_o = metrics.ms_ssim_value_and_grad(out, self.output_s_nchw, self._ones)
+        direct = self.g_x.is_contiguous() and self.g_x.shape == x.shape
         if self.clamp:
-            lo = ops.bound_forward(x.view(-1), 0.0, False)
-            out = ops.bound_forward(lo, 1.0, True).view_as(x)
+            g = ops.clamp01_backward_nchw_to_nhwc(g_o, x, out=self.g_x if direct else None)
         else:
-            out = x
-        ms_b, g_o = metrics.ms_ssim_value_and_grad(ops.nhwc_to_nchw(out), self.output_s_nchw, self._ones)
-        g = ops.nchw_to_nhwc(g_o).view(-1)
-        if self.clamp:
-            g = ops.bound_backward(lo, g, 1.0, True)
-            g = ops.bound_backward(x.view(-1), g, 0.0, False)
-        self.g_x.copy_(g.view_as(self.g_x))
+            g = ops.nchw_to_nhwc(g_o)
+        if not (direct and self.clamp):
+            self.g_x.copy_(g.view_as(self.g_x))
         self.last_loss_B = ms_b
 
     def _update_msssim(self):
@@ -280,7 +279,7 @@ class AttackEngine:
         fa, ba = self.ga.n_kernels()
         fs, bs = self.gs.n_kernels()
         if self.att_metric == "ms-ssim":   # the two value-and-gradient compositions: library kernels only (launch_table)
-            return 1 + 25 + fa + fs + 29 + bs + ba + 1
+            return 1 + 25 + fa + fs + 25 + bs + ba + 1
         return 1 + fa + fs + 2 + bs + ba + 1  # perturb fwd (1) + stacks + output_loss (2) + update (1)
 
     def run(self, iterations, record=None):

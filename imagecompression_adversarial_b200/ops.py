@@ -102,6 +102,26 @@ def nhwc_to_nchw(x):
     return out
 
 
+def clamp01_nhwc_to_nchw(x):
+    """Up_bound(Low_bound(x, 0), 1) of a channels-last image batch, written as planes (one launch)."""
+    _chk(x, "x")
+    n, h, w, c = x.shape
+    out = torch.empty(n, c, h, w, device=x.device, dtype=torch.float32)
+    L.call("icadv_clamp01_nhwc_to_nchw", _p(x), _p(out), n, c, h, w, _stream())
+    return out
+
+
+def clamp01_backward_nchw_to_nhwc(g_nchw, x_nhwc, out=None):
+    """Gradient of ``clamp01_nhwc_to_nchw`` (utils/ops.py:28-56 rules at the unclamped x), written channels-last."""
+    _chk(g_nchw, "g"); _chk(x_nhwc, "x")
+    n, h, w, c = x_nhwc.shape
+    if out is None:
+        out = torch.empty_like(x_nhwc)
+    _chk(out, "out")
+    L.call("icadv_clamp01_backward_nchw_to_nhwc", _p(g_nchw), _p(x_nhwc), _p(out), n, c, h, w, _stream())
+    return out
+
+
 def pixel_shuffle(x_nhwc, r, inverse=False):
     """nn.PixelShuffle(r) on a channels-last tensor [N,H,W,C*r*r] -> [N,H*r,W*r,C] (inverse: the other way)."""
     _chk(x_nhwc, "x")

@@ -148,6 +148,13 @@ int icadv_unpack_weight(const float* dwpack, float* dw, int kind, int c_out, int
 /* layout conversion at the operator surface: NCHW <-> NHWC fp32 */
 int icadv_nchw_to_nhwc(const float* src, float* dst, int n, int c, int h, int w, icadv_stream_t stream);
 int icadv_nhwc_to_nchw(const float* src, float* dst, int n, int c, int h, int w, icadv_stream_t stream);
+/* The [0, 1] clamp of the reconstruction fused into the image layout copies around the MS-SSIM terms (attack_rd.py:353-362;
+ * bounds and their gradient rules: utils/ops.py:28-56).  Forward: y = Up_bound(Low_bound(x, 0), 1) written as planes.
+ * Backward: the gradient arriving as planes goes back through both bounds, gated by the unclamped interleaved x, and is
+ * written interleaved.  Images only (c <= 4). */
+int icadv_clamp01_nhwc_to_nchw(const float* x_nhwc, float* y_nchw, int n, int c, int h, int w, icadv_stream_t stream);
+int icadv_clamp01_backward_nchw_to_nhwc(const float* g_nchw, const float* x_nhwc, float* gx_nhwc, int n, int c, int h,
+                                        int w, icadv_stream_t stream);
 
 /* nn.PixelShuffle(r) on channels-last tensors (compressai subpel_conv3x3, cheng2020_anchor g_s / h_s):
  * dst[n, h*r+i, w*r+j, c] = src[n, h, w, c*r*r + i*r + j]; inverse != 0 applies the inverse permutation (its gradient).

@@ -1,5 +1,5 @@
 """Kernel table (torch.profiler) of one ms-ssim network-branch loss composition as the attack engine runs it:
-layout copy, clamp, value + gradient pyramid, clamp backward, layout copy.  Usage: python scripts/msssim_profile.py [images]"""
+clamp fused into the layout copy, value + gradient pyramid, layout copy with the clamp's gradient rules.  Usage: python scripts/msssim_profile.py [images]"""
 import sys
 import os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -16,13 +16,9 @@ ones = torch.ones(n, device=dev)
 
 
 def comp():
-    lo = ops.bound_forward(x.view(-1), 0.0, False)
-    out = ops.bound_forward(lo, 1.0, True).view_as(x)
-    v, go = metrics.ms_ssim_value_and_grad(ops.nhwc_to_nchw(out), ref, ones)
-    gg = ops.nchw_to_nhwc(go).view(-1)
-    gg = ops.bound_backward(lo, gg, 1.0, True)
-    gg = ops.bound_backward(x.view(-1), gg, 0.0, False)
-    return v, gg
+    out = ops.clamp01_nhwc_to_nchw(x)
+    v, go = metrics.ms_ssim_value_and_grad(out, ref, ones)
+    return v, ops.clamp01_backward_nchw_to_nhwc(go, x)
 
 
 for _ in range(3):

@@ -80,6 +80,28 @@ def test_layout_roundtrip(dev, shape):
     assert torch.equal(ops.nhwc_to_nchw(y), x)
 
 
+@pytest.mark.parametrize("shape", [(2, 37, 41, 3), (1, 512, 768, 3), (3, 16, 16, 1)])
+def test_clamp01_fused_into_the_layout_copies(dev, shape):
+    """clamp01_nhwc_to_nchw / clamp01_backward_nchw_to_nhwc against the separate launches they replace in the ms-ssim
+    loop (bound_forward x2 + layout copy; layout copy + bound_backward x2): bit-identical, values on and outside both
+    bounds included."""
+    from imagecompression_adversarial_b200 import ops
+    g = torch.Generator(device=dev).manual_seed(3)
+    x = torch.rand(*shape, device=dev, generator=g) * 1.6 - 0.3
+    x.view(-1)[::7] = 0.0
+    x.view(-1)[3::11] = 1.0
+    lo = ops.bound_forward(x.view(-1), 0.0, False)
+    ref = ops.nhwc_to_nchw(ops.bound_forward(lo, 1.0, True).view_as(x))
+    assert torch.equal(ops.clamp01_nhwc_to_nchw(x), ref)
+    gy = torch.randn(ref.shape, device=dev, generator=g)
+    gr = ops.nchw_to_nhwc(gy).view(-1)
+    gr = ops.bound_backward(lo, gr, 1.0, True)
+    gr = ops.bound_backward(x.view(-1), gr, 0.0, False).view_as(x)
+    assert torch.equal(ops.clamp01_backward_nchw_to_nhwc(gy, x), gr)
+    out = torch.empty_like(x)
+    assert ops.clamp01_backward_nchw_to_nhwc(gy, x, out=out) is out and torch.equal(out, gr)
+
+
 @pytest.mark.parametrize("kind", [0, 1, 2, 3])
 def test_pack_unpack_weight(dev, kind):
     from imagecompression_adversarial_b200 import ops
