@@ -498,10 +498,25 @@ struct SsimVgParams {
   float taps[kMaxWin];
 };
 
+// Arithmetic is packed two-wide (sm_100 FFMA2, __ffma2_rn: one instruction = two fp32 fused multiply-adds, the tap a
+// broadcast uniform-register operand): the statistics travel as the pairs (mu_x, mu_y) and (x^2 + y^2, xy), the gradient
+// coefficients as (A12, A11) + B, and the shared rows hold (x, y, x^2 + y^2, xy) as float4 -- the products are made once per pixel, not once per tap --
+// and (V12, V11) as float2.  The kernel is issue bound
+// (ncu: FMA pipe 34 % busy at 64 % of the issue slots), so halving the multiply-add and shared-load instruction counts
+// is what counts; every component is still one IEEE fma, bit-identical to the scalar form.
+// 1 / x for the two SSIM denominators (both >= C1 or C2 > 0 up to rounding of the variance): MUFU.RCP + one Newton step,
+// no slow-path branch -- an IEEE division would split the row body into several basic blocks.  <= 1 ulp from 1.f / x.
+__device__ __forceinline__ float vg_rcp(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return fmaf(r, fmaf(-x, r, 1.f), r);
+}
+
 __global__ void __launch_bounds__(kVgT, 4) ssim_level_vg_kernel(const SsimVgParams p) {
   constexpr int W = kMaxWin, R = kVgR, T = kVgT;
-  __shared__ float s_in[2][2][T + R];
-  __shared__ float s_v[2][3][T];
+  __shared__ float4 s_in[2][T + R];            // (x, y, x^2 + y^2, xy) of the frame row: products made once per pixel
+  __shared__ float2 s_va[2][R + T];            // vertically filtered (A12, A11); R pad entries in front
+  __shared__ float s_vb[2][R + T];             // vertically filtered B
   __shared__ float s_red[2][T / 32];
   const int t = threadIdx.x;
   const int plane = blockIdx.z;
@@ -519,19 +534,24 @@ __global__ void __launch_bounds__(kVgT, 4) ssim_level_vg_kernel(const SsimVgPara
   const bool gx1_in = t < R && gx1 >= 0 && gx1 < p.w;
   const bool out_col = t >= R && gx0_in;
 
-  float hr[W][4], ar[W][3];
+  float2 hm[W], hs[W], aa[W];                  // rings: (mu_x, mu_y), (x^2 + y^2, xy) row-filtered; (A12, A11)
+  float ab[W];                                 //        B
 #pragma unroll
   for (int k = 0; k < W; ++k) {
-    hr[k][0] = hr[k][1] = hr[k][2] = hr[k][3] = 0.f;
-    ar[k][0] = ar[k][1] = ar[k][2] = 0.f;
+    hm[k] = hs[k] = aa[k] = make_float2(0.f, 0.f);
+    ab[k] = 0.f;
+  }
+  if (t < R) {
+    s_va[0][t] = s_va[1][t] = make_float2(0.f, 0.f);
+    s_vb[0][t] = s_vb[1][t] = 0.f;
   }
   float acc_s = 0.f, acc_c = 0.f;
-  float a0 = 0.f, b0 = 0.f, a1 = 0.f, b1 = 0.f;
+  float2 in0 = make_float2(0.f, 0.f), in1 = make_float2(0.f, 0.f);
   // running offsets inside the plane (h * w < 2^31): the input row being fetched and the output row being produced
   int gy_in = i0 - R - p.pad, off_in = gy_in * p.w + gx0;
   if (gy_in >= 0 && gy_in < p.h) {
-    if (gx0_in) { a0 = __ldg(X + off_in); b0 = __ldg(Y + off_in); }
-    if (gx1_in) { a1 = __ldg(X + off_in + T); b1 = __ldg(Y + off_in + T); }
+    if (gx0_in) { in0.x = __ldg(X + off_in); in0.y = __ldg(Y + off_in); }
+    if (gx1_in) { in1.x = __ldg(X + off_in + T); in1.y = __ldg(Y + off_in + T); }
   }
   // One barrier per row: the row-filtered V of iteration n is consumed (horizontal transposed filter, output row n-11)
   // by iteration n+1, after that iteration's barrier; both shared rows are double-buffered.
@@ -543,14 +563,14 @@ __global__ void __launch_bounds__(kVgT, 4) ssim_level_vg_kernel(const SsimVgPara
       if (n > n_last) break;
       const int b = n & 1;
       const bool produce = n < n_last;         // block-uniform
-      s_in[b][0][t] = a0; s_in[b][1][t] = b0;
-      if (t < R) { s_in[b][0][T + t] = a1; s_in[b][1][T + t] = b1; }
+      s_in[b][t] = make_float4(in0.x, in0.y, fmaf(in0.x, in0.x, in0.y * in0.y), in0.x * in0.y);
+      if (t < R) s_in[b][T + t] = make_float4(in1.x, in1.y, fmaf(in1.x, in1.x, in1.y * in1.y), in1.x * in1.y);
       // next input row and the operands of the output row drained in this iteration: issued ahead of the arithmetic
       ++gy_in; off_in += p.w;
-      a0 = b0 = a1 = b1 = 0.f;
+      in0 = in1 = make_float2(0.f, 0.f);
       if (n + 1 < n_last && gy_in >= 0 && gy_in < p.h) {
-        if (gx0_in) { a0 = __ldg(X + off_in); b0 = __ldg(Y + off_in); }
-        if (gx1_in) { a1 = __ldg(X + off_in + T); b1 = __ldg(Y + off_in + T); }
+        if (gx0_in) { in0.x = __ldg(X + off_in); in0.y = __ldg(Y + off_in); }
+        if (gx1_in) { in1.x = __ldg(X + off_in + T); in1.y = __ldg(Y + off_in + T); }
       }
       const int io = n - R - 1;                // output row drained by this iteration
       const int gyo = io - p.pad;
@@ -560,61 +580,60 @@ __global__ void __launch_bounds__(kVgT, 4) ssim_level_vg_kernel(const SsimVgPara
       float xo = 0.f, yo = 0.f;
       if (do_out) { xo = __ldg(X + off_o); yo = __ldg(Y + off_o); }
       __syncthreads();
-      if (produce) {
-        {
-          float h0 = 0.f, h1 = 0.f, h2 = 0.f, h3 = 0.f;
+      // One straight-line body per row: the four filter passes are independent multiply-add chains (the vertical ones
+      // need this row's horizontal result only at their LAST tap) and the scheduler may interleave them; the
+      // block-uniform conditions of the pipeline's warm-up rows only predicate the side effects.  Rows computed on a
+      // partly filled ring hold finite garbage that no owned sum and no drained output ever reads (see the header).
+      float2 h01 = make_float2(0.f, 0.f), h23 = make_float2(0.f, 0.f);
+      float2 ta = make_float2(0.f, 0.f);
+      float tb = 0.f;
 #pragma unroll
-          for (int k = 0; k < W; ++k) {
-            const float g = p.taps[k], u = s_in[b][0][t + k], v = s_in[b][1][t + k];
-            h0 = fmaf(g, u, h0); h1 = fmaf(g, v, h1);
-            h2 = fmaf(g, fmaf(u, u, v * v), h2); h3 = fmaf(g, u * v, h3);
-          }
-          hr[s][0] = h0; hr[s][1] = h1; hr[s][2] = h2; hr[s][3] = h3;
-        }
-        if (n >= i0) {                         // block-uniform: statistics rows i0-R .. are the ones outputs need
-          const int i = n - R;                 // statistics row finished by this iteration
-          float m1 = 0.f, m2 = 0.f, sq = 0.f, s12 = 0.f;
-#pragma unroll
-          for (int k = 0; k < W; ++k) {        // k = 0 is the oldest ring row (frame row n-10)
-            const int q = (s + 1 + k) % W;
-            const float g = p.taps[k];
-            m1 = fmaf(g, hr[q][0], m1); m2 = fmaf(g, hr[q][1], m2);
-            sq = fmaf(g, hr[q][2], sq); s12 = fmaf(g, hr[q][3], s12);
-          }
-          float A12 = 0.f, A11 = 0.f, B = 0.f;
-          if (ox_valid && i >= 0 && i < p.oh) {
-            const float m11 = m1 * m1, m22 = m2 * m2, m12 = m1 * m2;
-            const float rD = 1.f / ((sq - m11 - m22) + p.c2);
-            const float cs = (2.f * (s12 - m12) + p.c2) * rD;
-            const float rDl = 1.f / (m11 + m22 + p.c1);
-            const float lum = (2.f * m12 + p.c1) * rDl;
-            if (own_col && i >= i0) { acc_c += cs; acc_s += lum * cs; }
-            const float a_cs = p.ccs + p.css * lum;
-            A12 = a_cs * 2.f * rD;
-            A11 = -a_cs * cs * rD;
-            B = -m2 * A12 - 2.f * m1 * A11 + p.css * cs * 2.f * (m2 - lum * m1) * rDl;
-          }
-          ar[s][0] = A12; ar[s][1] = A11; ar[s][2] = B;
-          float v0 = 0.f, v1 = 0.f, v2 = 0.f;
-#pragma unroll
-          for (int k = 0; k < W; ++k) {        // V[i] = sum_k g[k] A[i-k]; A[i-k] sits k slots back
-            const int q = (s - k + W) % W;
-            const float g = p.taps[k];
-            v0 = fmaf(g, ar[q][0], v0); v1 = fmaf(g, ar[q][1], v1); v2 = fmaf(g, ar[q][2], v2);
-          }
-          s_v[b][0][t] = v0; s_v[b][1][t] = v1; s_v[b][2][t] = v2;
-        }
+      for (int k = 0; k < W; ++k) {
+        const float g = p.taps[k];
+        const float2 gg = make_float2(g, g);
+        const float4 e = s_in[b][t + k];
+        h01 = __ffma2_rn(gg, make_float2(e.x, e.y), h01);
+        h23 = __ffma2_rn(gg, make_float2(e.z, e.w), h23);
+        // V row io was written by the previous iteration into buffer b^1 (R pad entries in front: threads < R read them)
+        ta = __ffma2_rn(gg, s_va[b ^ 1][R + t - k], ta); tb = fmaf(g, s_vb[b ^ 1][R + t - k], tb);
       }
-      if (drain && t >= R) {                   // V row io was written by the previous iteration, buffer b^1
-        float t0 = 0.f, t1 = 0.f, t2 = 0.f;
+      hm[s] = h01; hs[s] = h23;
+      if (do_out) U[off_o] = yo * ta.x + 2.f * xo * ta.y + tb;
+      const int i = n - R;                     // statistics row finished by this iteration
+      float2 m = make_float2(0.f, 0.f), q = make_float2(0.f, 0.f);
 #pragma unroll
-        for (int k = 0; k < W; ++k) {
-          const float g = p.taps[k];
-          t0 = fmaf(g, s_v[b ^ 1][0][t - k], t0); t1 = fmaf(g, s_v[b ^ 1][1][t - k], t1);
-          t2 = fmaf(g, s_v[b ^ 1][2][t - k], t2);
-        }
-        if (do_out) U[off_o] = yo * t0 + 2.f * xo * t1 + t2;
+      for (int k = 0; k < W; ++k) {            // k = 0 is the oldest ring row (frame row n-10)
+        const int r = (s + 1 + k) % W;
+        const float g = p.taps[k];
+        const float2 gg = make_float2(g, g);
+        m = __ffma2_rn(gg, hm[r], m); q = __ffma2_rn(gg, hs[r], q);
       }
+      float A12, A11, B;
+      {
+        const float m1 = m.x, m2 = m.y, sq = q.x, s12 = q.y;
+        const float m11 = m1 * m1, m22 = m2 * m2, m12 = m1 * m2;
+        const float rD = vg_rcp((sq - m11 - m22) + p.c2);
+        const float cs = (2.f * (s12 - m12) + p.c2) * rD;
+        const float rDl = vg_rcp(m11 + m22 + p.c1);
+        const float lum = (2.f * m12 + p.c1) * rDl;
+        const bool valid = produce && ox_valid && i >= 0 && i < p.oh;
+        if (valid && own_col && i >= i0) { acc_c += cs; acc_s += lum * cs; }
+        const float a_cs = p.ccs + p.css * lum;
+        A12 = a_cs * 2.f * rD;
+        A11 = -a_cs * cs * rD;
+        B = -m2 * A12 - 2.f * m1 * A11 + p.css * cs * 2.f * (m2 - lum * m1) * rDl;
+        A12 = valid ? A12 : 0.f; A11 = valid ? A11 : 0.f; B = valid ? B : 0.f;
+      }
+      aa[s] = make_float2(A12, A11); ab[s] = B;
+      float2 va = make_float2(0.f, 0.f);
+      float vb = 0.f;
+#pragma unroll
+      for (int k = 0; k < W; ++k) {            // V[i] = sum_k g[k] A[i-k]; A[i-k] sits k slots back
+        const int r = (s - k + W) % W;
+        const float g = p.taps[k];
+        va = __ffma2_rn(make_float2(g, g), aa[r], va); vb = fmaf(g, ab[r], vb);
+      }
+      s_va[b][R + t] = va; s_vb[b][R + t] = vb;
     }
   }
 #pragma unroll
