@@ -117,6 +117,8 @@ _SIGS = {
     "icadv_ssim_vg_workspace_floats": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int]),
     "icadv_ssim_level_value_grad": (C.c_int, [_fp, _fp, _fp, _fp, _fp, _fp, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float),
                                               C.c_int, C.c_int, C.c_float, C.c_float, C.c_int, C.c_void_p]),
+    "icadv_msssim_coefficients": (C.c_int, [_fp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_float),
+                                            C.POINTER(C.c_float), C.c_int, _fp, _fp, _fp, C.c_int, C.c_int, C.c_void_p]),
     "icadv_ssim_combine": (C.c_int, [_fp, _fp, _fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                      C.c_void_p]),
     "icadv_avgpool2": (C.c_int, [_fp, _fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),

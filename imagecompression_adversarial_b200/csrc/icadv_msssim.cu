@@ -692,6 +692,45 @@ __global__ void __launch_bounds__(256) ssim_combine_kernel(float* __restrict__ U
   }
 }
 
+
+// All the scalar work between the level launches and the combine launches in ONE launch (it was five finalize launches and
+// ~30 ATen kernels on [levels, B, C] tensors per composition -- at one image per call, as the reference CLI runs, those
+// launches were a third of an ms-ssim iteration): per plane and level the block partials are summed in fixed order,
+//   v_l = relu(mean of the cs map)  (ssim map at the last level),   P = prod_l v_l^w_l,   value[b] = mean_c P,
+//   coef_l[plane] = upstream[b] / C * w_l * P / v_l / npx_l   (0 where v_l <= 0: the relu's gradient)
+// which is autograd of pytorch_msssim.ms_ssim's `torch.prod(relu(mcs_and_ssim) ** weights)` and its channel mean.
+constexpr int kMaxLevels = 8;
+struct MsCoefParams {
+  const float* ws; const float* upstream; float* value; float* coef;
+  int levels, batch, channels;
+  int ws_off[kMaxLevels], nb[kMaxLevels];
+  float inv_npx[kMaxLevels], weight[kMaxLevels];
+};
+
+__global__ void msssim_coef_kernel(const MsCoefParams p) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= p.batch) return;
+  const int planes = p.batch * p.channels;
+  const float up = p.upstream[b] / (float)p.channels;
+  float vsum = 0.f;
+  for (int c = 0; c < p.channels; ++c) {
+    const int pl = b * p.channels + c;
+    float v[kMaxLevels];
+    float P = 1.f;
+    for (int l = 0; l < p.levels; ++l) {
+      const float* w = p.ws + p.ws_off[l] + (int64_t)pl * p.nb[l] * 2 + (l == p.levels - 1 ? 0 : 1);
+      float s = 0.f;
+      for (int k = 0; k < p.nb[l]; ++k) s += w[2 * k];
+      v[l] = fmaxf(s * p.inv_npx[l], 0.f);
+      P *= powf(v[l], p.weight[l]);
+    }
+    vsum += P;
+    for (int l = 0; l < p.levels; ++l)
+      p.coef[l * planes + pl] = v[l] > 0.f ? up * p.weight[l] * P / v[l] * p.inv_npx[l] : 0.f;
+  }
+  p.value[b] = vsum / (float)p.channels;
+}
+
 }  // namespace icadv
 
 using namespace icadv;
@@ -790,7 +829,8 @@ int icadv_ssim_vg_workspace_floats(int planes, int h, int w, int same_pad) {
 int icadv_ssim_level_value_grad(const float* X, const float* Y, float* U, float* ws, float* ssim_sum, float* cs_sum,
                                 int planes, int h, int w, const float* win_taps_host, int win, int same_pad, float c1,
                                 float c2, int last_level, icadv_stream_t stream) {
-  ICADV_REQUIRE(X && Y && U && ws && ssim_sum && cs_sum && win_taps_host, "null pointer");
+  ICADV_REQUIRE(X && Y && U && ws && win_taps_host, "null pointer");
+  ICADV_REQUIRE((ssim_sum == nullptr) == (cs_sum == nullptr), "ssim_sum and cs_sum go together");
   ICADV_REQUIRE(win == kMaxWin, "the fused value + gradient level kernel takes the 11-tap window only");
   SsimVgParams p;
   p.X = X; p.Y = Y; p.U = U; p.ws = ws; p.h = h; p.w = w; p.pad = same_pad ? win / 2 : 0;
@@ -804,7 +844,28 @@ int icadv_ssim_level_value_grad(const float* X, const float* Y, float* U, float*
   dim3 grid(strips, nseg, planes);
   ssim_level_vg_kernel<<<grid, kVgT, 0, as_stream(stream)>>>(p);
   ICADV_CUDA_TRY(cudaGetLastError());
-  ssim_finalize_kernel<<<(planes + 127) / 128, 128, 0, as_stream(stream)>>>(ws, ssim_sum, cs_sum, planes, strips * nseg);
+  if (ssim_sum != nullptr) {   // NULL: the block partials stay in ws for icadv_msssim_coefficients
+    ssim_finalize_kernel<<<(planes + 127) / 128, 128, 0, as_stream(stream)>>>(ws, ssim_sum, cs_sum, planes, strips * nseg);
+    ICADV_CUDA_TRY(cudaGetLastError());
+  }
+  return ICADV_OK;
+}
+
+int icadv_msssim_coefficients(const float* ws_all, const int* ws_offset_host, const int* nblocks_host,
+                              const float* npx_host, const float* weights_host, int levels, const float* upstream,
+                              float* value, float* coef, int batch, int channels, icadv_stream_t stream) {
+  ICADV_REQUIRE(ws_all && ws_offset_host && nblocks_host && npx_host && weights_host && upstream && value && coef,
+                "null pointer");
+  ICADV_REQUIRE(levels >= 1 && levels <= kMaxLevels && batch >= 1 && channels >= 1, "bad msssim_coefficients args");
+  MsCoefParams p;
+  p.ws = ws_all; p.upstream = upstream; p.value = value; p.coef = coef;
+  p.levels = levels; p.batch = batch; p.channels = channels;
+  for (int l = 0; l < levels; ++l) {
+    ICADV_REQUIRE(nblocks_host[l] >= 1 && npx_host[l] > 0.f, "bad level geometry");
+    p.ws_off[l] = ws_offset_host[l]; p.nb[l] = nblocks_host[l];
+    p.inv_npx[l] = 1.f / npx_host[l]; p.weight[l] = weights_host[l];
+  }
+  msssim_coef_kernel<<<(batch + 63) / 64, 64, 0, as_stream(stream)>>>(p);
   ICADV_CUDA_TRY(cudaGetLastError());
   return ICADV_OK;
 }

@@ -120,11 +120,12 @@ class AttackEngine:
         msssim = self.att_metric == "ms-ssim"
         # MS-SSIM value + gradient (one pass per level, metrics.ms_ssim_value_and_grad): both images' 5-level pyramids
         # (4/3 of the image) read once, the gradient pyramid written once, + the two layout copies (read + write each).
-        # Library kernels: 2 layout + 5 x (level value-and-gradient, finalize, combine) + 8 pools.
-        ms_bytes = (4.0 / 3.0) * (2 + 1) * img + 4 * img
+        # Library kernels: 2 layout + 5 level value-and-gradient + 4 pools (the reference pyramid is cached) + 1 for all
+        # the scalar work + 5 combine.
+        ms_bytes = (4.0 / 3.0) * (2 + 1) * img + 4 * img   # (the cached reference pyramid is still READ every iteration)
         if msssim:
             rows.append({"name": "1 - ms_ssim(im_s, im_in) value + gradient (5 fused level launches + combine + layout copies)",
-                         "launch": self._msssim_budget_branch, "kernels": 25, "flops": 0.0, "bytes": ms_bytes,
+                         "launch": self._msssim_budget_branch, "kernels": 17, "flops": 0.0, "bytes": ms_bytes,
                          "bound": "hbm"})
 
         def stack(prog, lst, info):
@@ -136,7 +137,7 @@ class AttackEngine:
         stack(self.gs, self.gs.fwd, self.gs.fwd_info)
         if msssim:
             rows.append({"name": "ms_ssim(clamp(x_out), output_s) value + gradient + clamp rules",
-                         "launch": self._msssim_output_loss, "kernels": 25, "flops": 0.0, "bytes": ms_bytes + img,
+                         "launch": self._msssim_output_loss, "kernels": 17, "flops": 0.0, "bytes": ms_bytes + img,
                          "bound": "hbm"})
         else:
             rows.append({"name": "output_loss (clamp + MSE + gradient seed)",
@@ -168,8 +169,19 @@ class AttackEngine:
             self.output_s.copy_(torch.where(self.mask_tar.unsqueeze(0) > 0, output_t_nchw.permute(0, 2, 3, 1),
                                             self.output_s))
         if self.att_metric == "ms-ssim":
-            self.im_s_nchw = im_s_nchw.detach().contiguous().clone()
-            self.output_s_nchw = output_s_nchw.detach().contiguous().clone()
+            from . import metrics
+            # persistent buffers, refilled in place: the captured iteration reads these addresses on every replay, also
+            # after the engine is re-loaded with the next batch (a fresh clone per load would leave the graph reading
+            # the previous batch's freed tensors)
+            if self.im_s_nchw is None:
+                self.im_s_nchw = torch.empty(im_s_nchw.shape, device=self.device, dtype=torch.float32)
+                self.output_s_nchw = torch.empty_like(self.im_s_nchw)
+                self._pyr_im_s = self._pyr_out_s = None
+            self.im_s_nchw.copy_(im_s_nchw.detach())
+            self.output_s_nchw.copy_(output_s_nchw.detach())
+            # both reference images are fixed for the whole attack: their pool pyramids are built once per load
+            self._pyr_im_s = metrics.reference_pyramid(self.im_s_nchw, out=self._pyr_im_s)
+            self._pyr_out_s = metrics.reference_pyramid(self.output_s_nchw, out=self._pyr_out_s)
         if noise_init_nchw is None:
             self.noise.zero_()
         else:
@@ -235,7 +247,8 @@ class AttackEngine:
         """Budget branch of -att_metric ms-ssim: loss = 1 - ms_ssim(im_s, im_in) (attack_rd.py:335-336) and its gradient
         with respect to im_in (channels-last), for every image."""
         from . import metrics
-        ms_a, g_a = metrics.ms_ssim_value_and_grad(ops.nhwc_to_nchw(self.im_in), self.im_s_nchw, -self._ones)
+        ms_a, g_a = metrics.ms_ssim_value_and_grad(ops.nhwc_to_nchw(self.im_in), self.im_s_nchw, -self._ones,
+                                                   y_pyramid=self._pyr_im_s)
         self.last_loss_A = 1.0 - ms_a
         self._g_a_ext = ops.nchw_to_nhwc(g_a)
 
@@ -245,7 +258,7 @@ class AttackEngine:
         x = self.x_out
         # the clamp and its gradient rules ride on the two layout copies around the pyramid (one launch each side)
         out = ops.clamp01_nhwc_to_nchw(x) if self.clamp else ops.nhwc_to_nchw(x)
-        ms_b, g_o = metrics.ms_ssim_value_and_grad(out, self.output_s_nchw, self._ones)
+        ms_b, g_o = metrics.ms_ssim_value_and_grad(out, self.output_s_nchw, self._ones, y_pyramid=self._pyr_out_s)
         direct = self.g_x.is_contiguous() and self.g_x.shape == x.shape
         if self.clamp:
             g = ops.clamp01_backward_nchw_to_nhwc(g_o, x, out=self.g_x if direct else None)
@@ -279,7 +292,7 @@ class AttackEngine:
         fa, ba = self.ga.n_kernels()
         fs, bs = self.gs.n_kernels()
         if self.att_metric == "ms-ssim":   # the two value-and-gradient compositions: library kernels only (launch_table)
-            return 1 + 25 + fa + fs + 25 + bs + ba + 1
+            return 1 + 17 + fa + fs + 17 + bs + ba + 1
         return 1 + fa + fs + 2 + bs + ba + 1  # perturb fwd (1) + stacks + output_loss (2) + update (1)
 
     def run(self, iterations, record=None):

@@ -361,6 +361,15 @@ int icadv_ssim_vg_workspace_floats(int planes, int h, int w, int same_pad);
 int icadv_ssim_level_value_grad(const float* X, const float* Y, float* U, float* ws, float* ssim_sum, float* cs_sum,
                                 int planes, int h, int w, const float* win_taps_host, int win, int same_pad, float c1,
                                 float c2, int last_level, icadv_stream_t stream);
+/* The scalar step between the level launches and the combine launches, in one launch: sums the per-block partials the
+ * level launches left in ws_all (call icadv_ssim_level_value_grad with ssim_sum = cs_sum = NULL; level l's partials start
+ * at ws_all + ws_offset_host[l], nblocks_host[l] = icadv_ssim_vg_workspace_floats / (2 planes) blocks per plane),
+ * value[b] = mean_c prod_l relu(v_l)^w_l  (v_l = mean cs map, mean ssim map at the last level; npx_host[l] = map size) and
+ * coef [levels][planes] = d(sum_b upstream[b] value[b]) / d(sum of level l's map) -- what icadv_ssim_combine consumes.
+ * pytorch_msssim.ms_ssim (attack_rd.py:336,362; train.py:44,88) under autograd. */
+int icadv_msssim_coefficients(const float* ws_all, const int* ws_offset_host, const int* nblocks_host,
+                              const float* npx_host, const float* weights_host, int levels, const float* upstream,
+                              float* value, float* coef, int batch, int channels, icadv_stream_t stream);
 int icadv_ssim_combine(float* U, const float* coef, const float* Dnext, int planes, int h, int w, int next_h, int next_w,
                        int pad_h, int pad_w, icadv_stream_t stream);
 /* F.avg_pool2d(x, 2, stride 2, padding (pad_h, pad_w)) between levels */

@@ -353,6 +353,32 @@ def test_batch_budget_scope_matches_the_reference_batch_semantics(dev, metric, f
     assert len(rec_i) == steps
 
 
+@pytest.mark.parametrize("metric", ["L2", "ms-ssim"])
+def test_reloaded_engine_replays_its_graph_on_the_new_batch(dev, metric):
+    """An engine is cached and re-loaded image after image (the CLI attacks a directory one image at a time): the graph
+    captured for the first batch must read the SECOND batch's source and reference images on replay -- everything a
+    captured launch reads (for ms-ssim: the planar references and their pool pyramids) lives in persistent buffers."""
+    from imagecompression_adversarial_b200.engine import AttackEngine
+    _, pnet = pair("hyper", 1, dev)
+    pnet.train()
+    xs = images(3, 192, 192, dev)
+    refs = (xs * 0.9 + 0.05).contiguous()
+    kw = dict(steps=9, noise_budget=1e-4 if metric == "L2" else 2e-5, att_metric=metric, force_branch=1)
+
+    def attack(eng, i, iters=4):
+        eng.load(xs[i:i + 1], refs[i:i + 1])
+        eng.run(iters)
+        return eng.im_in_nchw().clone()
+
+    cached = AttackEngine(pnet, 1, 192, 192, use_graph=True, **kw)
+    outs = [attack(cached, i) for i in range(3)]
+    for i in (1, 2):
+        fresh = AttackEngine(pnet, 1, 192, 192, use_graph=True, **kw)
+        assert torch.equal(outs[i], attack(fresh, i)), i
+        del fresh
+    assert not torch.equal(outs[1], outs[2])
+
+
 @pytest.mark.parametrize("metric,hw", [("L2", (64, 64)), ("ms-ssim", (192, 192))])
 def test_graph_replay_equals_eager(dev, metric, hw):
     """The whole iteration -- for -att_metric ms-ssim including both 5-level MS-SSIM value-and-gradient compositions --
