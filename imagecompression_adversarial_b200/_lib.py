@@ -103,6 +103,8 @@ _SIGS = {
     "icadv_gdn_param_grad_workspace_floats": (C.c_int, [C.c_int]),
     "icadv_gdn_param_grad": (C.c_int, [_fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, C.c_int64, C.c_int, C.c_int, C.c_float,
                                        C.c_float, C.c_void_p]),
+    "icadv_gdn_param_operands": (C.c_int, [_fp, _fp, _fp, _fp, _fp, C.c_int64, C.c_int, C.c_void_p]),
+    "icadv_gdn_param_grad_finalize": (C.c_int, [_fp, _fp, _fp, _fp, _fp, _fp, C.c_int, C.c_float, C.c_float, C.c_void_p]),
     "icadv_sumsq": (C.c_int, [_fp, _fp, _fp, C.c_int64, C.c_void_p]),
     "icadv_adam_clip_step": (C.c_int, [_fp, _fp, _fp, _fp, C.c_int64, _fp, C.c_float, C.c_float, C.c_double, C.c_double,
                                        C.c_double, C.c_double, C.c_int, C.c_void_p]),

@@ -271,6 +271,34 @@ __global__ void __launch_bounds__(256) gdn_param_grad_kernel(const float* __rest
   if (ty == 0 && blockIdx.y == 0) pg[(int64_t)C * C + i0 + tx] = sign * accb;
 }
 
+// Tensor-path form of the same gradients: d gamma_ij = sum_px T_i X2_j is a contraction whose reduction axis is the pixel
+// axis -- exactly the 1x1 case of the tcgen05 weight gradient (icadv_wgrad_tc.cu: "input" X2 = x^2, "output gradient"
+// T = -+1/2 t), and d beta_i = sum_px T_i is its bias gradient.  This kernel writes the two operands (rounded to TF32 where
+// they are produced, like every operand of the tensor path); the CUDA-core kernel above stays for the parity mode and for
+// channel counts the tensor path does not take.  Config-5 update step: 6 x 0.30 ms -> see DESIGN.md.
+__global__ void __launch_bounds__(256) gdn_param_operands_kernel(const float4* __restrict__ g, const float4* __restrict__ y,
+                                                                 const float4* __restrict__ sc, float4* __restrict__ T,
+                                                                 float4* __restrict__ X2, int64_t n4, int inverse) {
+  const float half = inverse ? 0.5f : -0.5f;
+  for (int64_t i = blockIdx.x * 256 + threadIdx.x; i < n4; i += (int64_t)gridDim.x * 256) {
+    const float4 gv = __ldg(g + i), yv = __ldg(y + i), sv = __ldg(sc + i);
+    const float ga[4] = {gv.x, gv.y, gv.z, gv.w}, ya[4] = {yv.x, yv.y, yv.z, yv.w}, sa[4] = {sv.x, sv.y, sv.z, sv.w};
+    float t[4], x2[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float s2 = sa[k] * sa[k];
+      const float tv = inverse ? (s2 > 0.f ? ga[k] * ya[k] / s2 : 0.f) : ga[k] * ya[k] * s2;   // as gdn_param_grad_kernel
+      const float xj = sa[k] > 0.f ? ya[k] / sa[k] : 0.f;
+      uint32_t a, b;
+      asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(a) : "f"(half * tv));
+      asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(b) : "f"(xj * xj));
+      t[k] = __uint_as_float(a); x2[k] = __uint_as_float(b);
+    }
+    T[i] = make_float4(t[0], t[1], t[2], t[3]);
+    X2[i] = make_float4(x2[0], x2[1], x2[2], x2[3]);
+  }
+}
+
 // fixed-order sum over splits + chain rule through the non-negative reparametrisation eff = max(raw, bound)^2 - pedestal
 // with the LowerBound backward rule (pass if raw >= bound or the incoming gradient is negative).
 // partial: per split `stride` floats; this launch finalises the `count` entries starting at `offset` of every split.
@@ -404,6 +432,30 @@ int icadv_gdn_param_grad(const float* g, const float* y, const float* sc, const 
   ICADV_CUDA_TRY(cudaGetLastError());
   gdn_param_grad_finalize_kernel<<<(C + 255) / 256, 256, 0, as_stream(stream)>>>(ws, splits, stride, cnt, C, beta_raw,
                                                                                  g_beta, beta_bound);
+  ICADV_CUDA_TRY(cudaGetLastError());
+  return ICADV_OK;
+}
+
+int icadv_gdn_param_operands(const float* g, const float* y, const float* sc, float* T, float* X2, int64_t n,
+                             int inverse, icadv_stream_t stream) {
+  ICADV_REQUIRE(g && y && sc && T && X2 && n >= 4 && n % 4 == 0, "bad gdn_param_operands args");
+  gdn_param_operands_kernel<<<ew_blocks_t(n / 4), 256, 0, as_stream(stream)>>>(
+      reinterpret_cast<const float4*>(g), reinterpret_cast<const float4*>(y), reinterpret_cast<const float4*>(sc),
+      reinterpret_cast<float4*>(T), reinterpret_cast<float4*>(X2), n / 4, inverse);
+  ICADV_CUDA_TRY(cudaGetLastError());
+  return ICADV_OK;
+}
+
+int icadv_gdn_param_grad_finalize(const float* d_gamma_eff, const float* d_beta_eff, const float* beta_raw,
+                                  const float* gamma_raw, float* g_beta, float* g_gamma, int C, float beta_bound,
+                                  float gamma_bound, icadv_stream_t stream) {
+  ICADV_REQUIRE(d_gamma_eff && d_beta_eff && beta_raw && gamma_raw && g_beta && g_gamma && C >= 1, "null pointer");
+  const int64_t cnt = (int64_t)C * C;
+  gdn_param_grad_finalize_kernel<<<(int)((cnt + 255) / 256), 256, 0, as_stream(stream)>>>(d_gamma_eff, 1, 0, 0, cnt, gamma_raw,
+                                                                                          g_gamma, gamma_bound);
+  ICADV_CUDA_TRY(cudaGetLastError());
+  gdn_param_grad_finalize_kernel<<<(C + 255) / 256, 256, 0, as_stream(stream)>>>(d_beta_eff, 1, 0, 0, C, beta_raw, g_beta,
+                                                                                 beta_bound);
   ICADV_CUDA_TRY(cudaGetLastError());
   return ICADV_OK;
 }

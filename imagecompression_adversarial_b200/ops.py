@@ -493,6 +493,9 @@ def _chk_dense(t):
         raise L.IcadvError("expected a dense CUDA float32 tensor")
 
 
+GDN_PARAM_GRAD_TC = True   # False: the fp32 CUDA-core kernel everywhere (A/B tests)
+
+
 def gdn_param_grad(g, y, sc, beta_raw, gamma_raw, *, inverse, beta_bound, gamma_bound):
     """(d beta_raw [C], d gamma_raw [C,C]) from g = dL/dy, saved y and scale (channels-last)."""
     for t, nm in ((g, "g"), (y, "y"), (sc, "sc")):
@@ -500,6 +503,16 @@ def gdn_param_grad(g, y, sc, beta_raw, gamma_raw, *, inverse, beta_bound, gamma_
     Cc = y.shape[-1]
     gb = torch.empty(Cc, device=y.device, dtype=torch.float32)
     gg = torch.empty(Cc, Cc, device=y.device, dtype=torch.float32)
+    from . import precision
+    if (GDN_PARAM_GRAD_TC and not precision.split() and y.dim() == 4 and g.shape == y.shape == sc.shape and
+            conv_wgrad_tc_supported(Cc, Cc, 1, 1, in_hw=(y.shape[1], y.shape[2]))):
+        # tensor path: d gamma = the 1x1 weight gradient of (input x^2, output gradient -+1/2 t), d beta its bias gradient
+        T, X2 = torch.empty_like(y), torch.empty_like(y)
+        L.call("icadv_gdn_param_operands", _p(g), _p(y), _p(sc), _p(T), _p(X2), y.numel(), 1 if inverse else 0, _stream())
+        dw, db = conv_wgrad(X2, T, form=L.FORM_SCONV, ksize=1, stride=1, n_ch=Cc, want_bias=True, path="tc")
+        L.call("icadv_gdn_param_grad_finalize", _p(dw), _p(db), _p(beta_raw.detach().contiguous()),
+               _p(gamma_raw.detach().contiguous()), _p(gb), _p(gg), Cc, float(beta_bound), float(gamma_bound), _stream())
+        return gb, gg
     ws = torch.empty(L.lib().icadv_gdn_param_grad_workspace_floats(Cc), device=y.device, dtype=torch.float32)
     L.call("icadv_gdn_param_grad", _p(g), _p(y), _p(sc), _p(beta_raw.detach().contiguous()),
            _p(gamma_raw.detach().contiguous()), _p(gb), _p(gg), _p(ws), y.numel() // Cc, Cc, 1 if inverse else 0,

@@ -322,6 +322,15 @@ int icadv_gdn_param_grad_workspace_floats(int C);
 int icadv_gdn_param_grad(const float* g, const float* y, const float* sc, const float* beta_raw, const float* gamma_raw,
                          float* g_beta, float* g_gamma, float* ws, int64_t n_px, int C, int inverse, float beta_bound,
                          float gamma_bound, icadv_stream_t stream);
+/* The same gradients on the tensor path: icadv_gdn_param_operands writes T = -+1/2 g y sc^(+-2) and X2 = (y / sc)^2
+ * (TF32-rounded, same layout as g); d gamma_eff [C][C] = sum_px T_i X2_j is then the 1x1 case of icadv_conv_wgrad_ex
+ * (input X2, output gradient T) and d beta_eff [C] its bias gradient; icadv_gdn_param_grad_finalize applies the chain rule
+ * through the reparametrisation (as the last step of icadv_gdn_param_grad). */
+int icadv_gdn_param_operands(const float* g, const float* y, const float* sc, float* T, float* X2, int64_t n,
+                             int inverse, icadv_stream_t stream);
+int icadv_gdn_param_grad_finalize(const float* d_gamma_eff, const float* d_beta_eff, const float* beta_raw,
+                                  const float* gamma_raw, float* g_beta, float* g_gamma, int C, float beta_bound,
+                                  float gamma_bound, icadv_stream_t stream);
 /* out[0] = sum g^2 over a flat gradient buffer (ws: 128 floats): the global norm of clip_grad_norm_ (train.py:360) */
 int icadv_sumsq(const float* g, float* ws, float* out, int64_t n, icadv_stream_t stream);
 /* clip_grad_norm_(max_norm) + torch.optim.Adam step over ONE flat buffer (after the gradient all-reduce): gradients

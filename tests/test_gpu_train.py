@@ -335,6 +335,33 @@ def test_gdn_parameter_gradients_match_autograd(dev, inverse):
         assert rel(a, b) < 3e-3, (nm, rel(a, b))
 
 
+@pytest.mark.parametrize("inverse", [False, True])
+def test_gdn_parameter_gradients_tensor_path_matches_cuda_core_kernel(dev, inverse):
+    """d gamma / d beta through the tcgen05 weight-gradient kernel (1x1 case: operands T and x^2 written by
+    icadv_gdn_param_operands, TF32 products, fp32 accumulation) against the fp32 CUDA-core kernel on the same saved
+    tensors, ragged 8x8 tile edges included; the LowerBound rule of the reparametrisation is exercised on both."""
+    from imagecompression_adversarial_b200 import ops
+    C, n, h, w = 128, 3, 37, 50
+    g = torch.Generator(device=dev).manual_seed(17)
+    gy = torch.randn(n, h, w, C, device=dev, generator=g)
+    y = torch.randn(n, h, w, C, device=dev, generator=g)
+    sc = 0.5 + torch.rand(n, h, w, C, device=dev, generator=g)
+    beta_raw = 1.0 + torch.rand(C, device=dev, generator=g)
+    gamma_raw = 0.1 * torch.rand(C, C, device=dev, generator=g)
+    gamma_raw[0, :8] = 0.0            # below the bound
+    kw = dict(inverse=inverse, beta_bound=1e-3, gamma_bound=3.8e-6 ** 0.5)
+    res = {}
+    for tc in (True, False):
+        ops.GDN_PARAM_GRAD_TC = tc
+        try:
+            res[tc] = ops.gdn_param_grad(gy, y, sc, beta_raw, gamma_raw, **kw)
+        finally:
+            ops.GDN_PARAM_GRAD_TC = True
+    for a, b, nm in zip(res[True], res[False], ("beta", "gamma")):
+        assert float(b.abs().max()) > 0
+        assert rel(a, b) < 1e-3, (nm, rel(a, b))
+
+
 def test_fused_clip_adam_matches_torch(dev):
     from imagecompression_adversarial_b200 import training as ptr
     torch.manual_seed(8)
