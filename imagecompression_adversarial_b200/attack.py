@@ -112,9 +112,12 @@ def eval(im_adv, im_s, output_s, net, args):  # noqa: A001 (the reference shadow
     return im_, output_, bpp, mse_results, vi_results
 
 
-def attack_(im_s, net, args, record=None, noise_init=None, im_t=None):
+def attack_(im_s, net, args, record=None, noise_init=None, im_t=None, metrics_pass=True):
     """Same contract as attack_rd.attack_: returns
     (im_adv, output_adv, output_s, bpp_ori, bpp, mse_results, vi_results).
+    ``metrics_pass=False`` (used by ``training.adv_train_step``, which like train.py:342 consumes element [0] only) skips
+    the final evaluation pass of self_ensemble.eval and its host reads: the call then returns without synchronising, so
+    the caller's next launches queue up behind the attack, and elements [1], [4], [5], [6] of the tuple are None.
     ``im_t`` (the ``-t`` target image, same shape as ``im_s``) switches to the targeted / ROI loss with ``args.mask_loc``,
     ``args.lamb_bkg_in``, ``args.lamb_bkg_out``, ``args.lamb_tar`` (semantics: oracle/attack.py attack_our_roi; the
     reference's own path for these flags is dead code)."""
@@ -131,6 +134,9 @@ def attack_(im_s, net, args, record=None, noise_init=None, im_t=None):
     eng.load(im_s, output_s, noise_init, output_t)
     eng.run(args.steps, record=record)
     im_in = eng.im_in_nchw().contiguous()
+    if not metrics_pass:
+        im_adv = _clamp01(im_in) if args.clamp else im_in                  # what eval returns as im_ (self_ensemble.py:186)
+        return im_adv, None, output_s, bpp_ori, None, None, None
     im_adv, output_adv, bpp, mse_results, vi_results = eval(im_in, im_s, output_s, net, args)
     return im_adv, output_adv, output_s, bpp_ori, bpp, mse_results, vi_results
 

@@ -215,7 +215,8 @@ def adv_train_step(batch_x, net, args, criterion, optimizer, aux_optimizer, grou
         import copy
         args = copy.copy(args)
         args.budget_scope = budget_scope
-    batch_adv = attack_(batch_x, net, args)[0].detach()                  # :342-343
+    batch_adv = attack_(batch_x, net, args, metrics_pass=False)[0].detach()   # :342-343 (only [0] is used: no eval pass,
+                                                                           # no host sync between the attack and the update)
     if ev:
         ev[1].record()
     net.train()                                                          # :346
