@@ -185,6 +185,20 @@ __global__ void ssim_finalize_kernel(const float* __restrict__ ws, float* __rest
   ssim_sum[pl] = s; cs_sum[pl] = c;
 }
 
+// even width divisible by 4, no padding: a thread averages two float4 row pieces into one float2 (two outputs)
+__global__ void __launch_bounds__(256) avgpool2_vec_kernel(const float* __restrict__ x, float* __restrict__ y, int h, int w,
+                                                           int oh, int ow2) {
+  const int plane = blockIdx.y;
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  if (i >= oh * ow2) return;
+  const int oy = i / ow2, o2 = i - oy * ow2;
+  const float4* r0 = reinterpret_cast<const float4*>(x + ((int64_t)plane * h + 2 * oy) * w);
+  const float4 a = __ldg(r0 + o2), b = __ldg(r0 + (w >> 2) + o2);
+  // same association as the scalar kernel: ((x00 + x01) + x10) + x11, then * 0.25
+  reinterpret_cast<float2*>(y + ((int64_t)plane * oh + oy) * (2 * ow2))[o2] =
+      make_float2(0.25f * (((a.x + a.y) + b.x) + b.y), 0.25f * (((a.z + a.w) + b.z) + b.w));
+}
+
 // F.avg_pool2d(x, kernel_size=2, stride=2, padding=(ph, pw)), count_include_pad=True
 __global__ void avgpool2_kernel(const float* __restrict__ x, float* __restrict__ y, int planes, int h, int w, int oh,
                                 int ow, int ph, int pw) {
@@ -707,9 +721,11 @@ struct MsCoefParams {
   float inv_npx[kMaxLevels], weight[kMaxLevels];
 };
 
-__global__ void msssim_coef_kernel(const MsCoefParams p) {
-  const int b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= p.batch) return;
+// One warp per image: the 32 lanes share every partial list (lane k takes partials k, k + 32, ...; xor-butterfly sum, the
+// same order on every run), so the longest list -- 112 block partials per plane at one image -- is four loads deep.  (One
+// thread per image walking its lists serially measured 24 us at 16 images: longer than the kernels it replaced.)
+__global__ void __launch_bounds__(32) msssim_coef_kernel(const MsCoefParams p) {
+  const int b = blockIdx.x, lane = threadIdx.x;
   const int planes = p.batch * p.channels;
   const float up = p.upstream[b] / (float)p.channels;
   float vsum = 0.f;
@@ -717,18 +733,25 @@ __global__ void msssim_coef_kernel(const MsCoefParams p) {
     const int pl = b * p.channels + c;
     float v[kMaxLevels];
     float P = 1.f;
-    for (int l = 0; l < p.levels; ++l) {
+#pragma unroll
+    for (int l = 0; l < kMaxLevels; ++l) {
+      if (l >= p.levels) break;
       const float* w = p.ws + p.ws_off[l] + (int64_t)pl * p.nb[l] * 2 + (l == p.levels - 1 ? 0 : 1);
       float s = 0.f;
-      for (int k = 0; k < p.nb[l]; ++k) s += w[2 * k];
+      for (int k = lane; k < p.nb[l]; k += 32) s += __ldg(w + 2 * k);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
       v[l] = fmaxf(s * p.inv_npx[l], 0.f);
       P *= powf(v[l], p.weight[l]);
     }
     vsum += P;
-    for (int l = 0; l < p.levels; ++l)
-      p.coef[l * planes + pl] = v[l] > 0.f ? up * p.weight[l] * P / v[l] * p.inv_npx[l] : 0.f;
+#pragma unroll
+    for (int l = 0; l < kMaxLevels; ++l) {
+      if (l >= p.levels) break;
+      if (lane == 0) p.coef[l * planes + pl] = v[l] > 0.f ? up * p.weight[l] * P / v[l] * p.inv_npx[l] : 0.f;
+    }
   }
-  p.value[b] = vsum / (float)p.channels;
+  if (lane == 0) p.value[b] = vsum / (float)p.channels;
 }
 
 }  // namespace icadv
@@ -769,6 +792,13 @@ int icadv_ssim_level(const float* X, const float* Y, float* ws, float* ssim_sum,
 int icadv_avgpool2(const float* x, float* y, int planes, int h, int w, int pad_h, int pad_w, icadv_stream_t stream) {
   ICADV_REQUIRE(x && y && planes > 0 && h > 0 && w > 0, "bad avgpool2 args");
   const int oh = (h + 2 * pad_h - 2) / 2 + 1, ow = (w + 2 * pad_w - 2) / 2 + 1;
+  if (pad_h == 0 && pad_w == 0 && w % 4 == 0 && h % 2 == 0 && planes <= 65535 &&
+      reinterpret_cast<uintptr_t>(x) % 16 == 0 && reinterpret_cast<uintptr_t>(y) % 8 == 0) {
+    dim3 grid((oh * (ow / 2) + 255) / 256, planes);
+    avgpool2_vec_kernel<<<grid, 256, 0, as_stream(stream)>>>(x, y, h, w, oh, ow / 2);
+    ICADV_CUDA_TRY(cudaGetLastError());
+    return ICADV_OK;
+  }
   const int64_t total = (int64_t)planes * oh * ow;
   int64_t blocks = (total + 255) / 256;
   if (blocks > 148 * 16) blocks = 148 * 16;
@@ -865,7 +895,7 @@ int icadv_msssim_coefficients(const float* ws_all, const int* ws_offset_host, co
     p.ws_off[l] = ws_offset_host[l]; p.nb[l] = nblocks_host[l];
     p.inv_npx[l] = 1.f / npx_host[l]; p.weight[l] = weights_host[l];
   }
-  msssim_coef_kernel<<<(batch + 63) / 64, 64, 0, as_stream(stream)>>>(p);
+  msssim_coef_kernel<<<batch, 32, 0, as_stream(stream)>>>(p);
   ICADV_CUDA_TRY(cudaGetLastError());
   return ICADV_OK;
 }
@@ -875,7 +905,8 @@ int icadv_ssim_combine(float* U, const float* coef, const float* Dnext, int plan
   ICADV_REQUIRE(U && coef && planes > 0 && h > 0 && w > 0, "bad ssim_combine args");
   ICADV_REQUIRE(planes <= 65535 && h <= 65535, "grid too large");
   // the vector form needs 16-byte rows of U and 8-byte rows of parents that cover every pixel pair (nw = w / 2)
-  const bool vec = w % 4 == 0 && (Dnext == nullptr || (pad_w == 0 && next_w == w / 2));
+  const bool vec = w % 4 == 0 && (Dnext == nullptr || (pad_w == 0 && next_w == w / 2)) &&
+                   reinterpret_cast<uintptr_t>(U) % 16 == 0 && reinterpret_cast<uintptr_t>(Dnext) % 8 == 0;
   if (vec) {
     dim3 grid4((h * (w / 4) + 255) / 256, planes);
     ssim_combine4_kernel<<<grid4, 256, 0, as_stream(stream)>>>(U, coef, Dnext, h, w / 4, next_h, next_w, pad_h);
