@@ -352,8 +352,10 @@ def test_ifgsm_parity(dev):
 def test_config5_adv_train_step_300_attack_steps(dev):
     """BASELINE configs[4] at world size 1: one train.py --adv iteration (train.py:335-366) = attack_ with -steps 300
     on the batch, then the codec update; hyperprior q1, 256x256 crops.  The reference tests its budget on the BATCH mean
-    (attack_rd.py:333-334); this package attacks per image, so the comparison runs one image per step (batch 1), where
-    the two coincide."""
+    (attack_rd.py:333-334) and so does adv_train_step (budget_scope="batch"); this 300-step comparison runs one image per
+    step, the batch semantics themselves (shared branch, 1/B gradient scale) are pinned against the oracle on batches by
+    test_gpu_e2e.py::test_batch_budget_scope_matches_the_reference_batch_semantics and
+    test_gpu_train.py::test_adv_train_step_runs_and_tracks_oracle."""
     from imagecompression_adversarial_b200 import training as ptr
     from oracle import attack as oatk
     onet, pnet = pair("hyper", 1, dev)
