@@ -349,17 +349,18 @@ def test_ifgsm_parity(dev):
     assert abs(psnr(p[0], x) - psnr(o[0], x)) < PSNR_DB
 
 
-def test_config5_adv_train_step_300_attack_steps(dev):
+@pytest.mark.parametrize("n_img", [1, 2])
+def test_config5_adv_train_step_300_attack_steps(dev, n_img):
     """BASELINE configs[4] at world size 1: one train.py --adv iteration (train.py:335-366) = attack_ with -steps 300
     on the batch, then the codec update; hyperprior q1, 256x256 crops.  The reference tests its budget on the BATCH mean
-    (attack_rd.py:333-334) and so does adv_train_step (budget_scope="batch"); this 300-step comparison runs one image per
-    step, the batch semantics themselves (shared branch, 1/B gradient scale) are pinned against the oracle on batches by
+    (attack_rd.py:333-334) and so does adv_train_step (budget_scope="batch"); this 300-step comparison runs one image and a
+    batch of two per step, the batch semantics themselves (shared branch, 1/B gradient scale) are also pinned step by step by
     test_gpu_e2e.py::test_batch_budget_scope_matches_the_reference_batch_semantics and
     test_gpu_train.py::test_adv_train_step_runs_and_tracks_oracle."""
     from imagecompression_adversarial_b200 import training as ptr
     from oracle import attack as oatk
     onet, pnet = pair("hyper", 1, dev)
-    x = images(1, 256, 256, dev)
+    x = images(n_img, 256, 256, dev)     # n_img = 2: the batch-mean budget test and the 1/B gradient scale over 300 steps
     # same quantisation noise in both implementations
     g = torch.Generator(device=dev).manual_seed(5)
     with torch.no_grad():
